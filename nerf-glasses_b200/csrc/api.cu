@@ -1,0 +1,693 @@
+// api.cu - the C ABI of libnmr.so (include/nmr.h): context, scene management and frame orchestration.
+// Host-side mirror of NerfMeshRenderer / Testbed as far as the render path needs them
+// (S/nerf_mesh_renderer.cu:365-452, 499-598, 896-1000; S/ngp/testbed.cu:939-1135, 1481-1612; S/python_api.cu:83-111).
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/nmr.h"
+#include "host.h"
+#include "kernels.cuh"
+
+using namespace nmr;
+
+namespace {
+
+std::string g_create_error;
+
+struct CudaError : std::runtime_error { explicit CudaError(const std::string& m) : std::runtime_error(m) {} };
+#define CK(call)                                                                                                   \
+    do {                                                                                                           \
+        cudaError_t e_ = (call);                                                                                   \
+        if (e_ != cudaSuccess) throw CudaError(std::string(#call) + ": " + cudaGetErrorString(e_));                \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    void ensure(size_t count) {
+        if (count <= n) return;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        CK(cudaMalloc(&p, count * sizeof(T)));
+        n = count;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~DevBuf() { release(); }
+};
+
+struct Nerf {
+    HostModel host;                 // parameters are dropped after upload
+    DevBuf<uint16_t> d_params;
+    DevBuf<uint8_t> d_bitfield;
+    DeviceModel dev{};
+    float render_aabb_min[3], render_aabb_max[3];
+    float background[4] = {1.f, 1.f, 1.f, 1.f};     // S/ngp/testbed.cuh:525
+    float min_transmittance = 0.01f;                // S/ngp/testbed.cuh:484
+};
+
+struct Mesh {
+    HostMesh host;
+    float t[3], s[3], r[4];
+};
+
+struct Surfaces {
+    int w = 0, h = 0;
+    DevBuf<float4> image, accum, frame;
+    DevBuf<float> depth;
+    DevBuf<uint32_t> n_samples;
+    DevBuf<float4> queue;
+    DevBuf<unsigned long long> zbuf;
+    uint32_t spp = 0;
+    void resize(int W, int H, int mesh_scale) {
+        const size_t n = (size_t)W * H;
+        if (W != w || H != h) spp = 0;
+        image.ensure(n); accum.ensure(n); frame.ensure(n); depth.ensure(n); n_samples.ensure(n);
+        queue.ensure(n * kRayRecordFloat4s);
+        zbuf.ensure(n * (size_t)mesh_scale * mesh_scale);
+        w = W; h = H;
+    }
+};
+
+}  // namespace
+
+struct nmr_ctx {
+    std::mutex mu;
+    std::string last_error;
+    int device = 0, num_sms = 148;
+    int width = 0, height = 0;
+    int mesh_scale = 2;                                   // mesh_render_size_factor, S/nerf_mesh_renderer.cuh:112
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    OrbitCamera camera;
+    float cam12[12];
+    float light[3] = {1.f, 1.f, 1.f};                     // S/nerf_mesh_renderer.cuh:95
+    std::vector<std::unique_ptr<Nerf>> nerfs;
+    std::vector<std::unique_ptr<Mesh>> meshes;
+    // concatenated world-space mesh on the device
+    bool mesh_dirty = true;
+    DevBuf<float> d_wpos, d_wnrm, d_uv, d_tex;
+    DevBuf<uint32_t> d_idx;
+    MeshDevice mesh_dev{};
+    Surfaces surf;
+    DevBuf<uint32_t> d_counters;
+    uint32_t* h_counters = nullptr;                       // pinned
+    DevBuf<float> d_scratch;
+    int shard_rank = 0, shard_world = 1, shard_band = 8;
+    uint32_t debug_flags = 0;
+    nmr_stats stats{};
+    bool stats_pending = false;
+    std::string envmap_path;
+    DevBuf<uint8_t> d_flush;
+};
+
+namespace {
+
+int fail(nmr_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->last_error = msg; else g_create_error = msg;
+    return code;
+}
+
+template <typename F>
+int guarded(nmr_ctx* ctx, F&& f) {
+    if (!ctx) return fail(nullptr, NMR_ERR_INVALID, "null context");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    try {
+        cudaError_t e = cudaSetDevice(ctx->device);
+        if (e != cudaSuccess) return fail(ctx, NMR_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+        return f();
+    } catch (const CudaError& e) {
+        return fail(ctx, NMR_ERR_CUDA, e.what());
+    } catch (const std::bad_alloc&) {
+        return fail(ctx, NMR_ERR_INVALID, "out of host memory");
+    } catch (const std::exception& e) {
+        const std::string m = e.what();
+        const int code = m.rfind("cannot open", 0) == 0 ? NMR_ERR_IO : NMR_ERR_FORMAT;
+        return fail(ctx, code, m);
+    }
+}
+
+Nerf* get_nerf(nmr_ctx* ctx, int id) {
+    if (id < 0 || id >= (int)ctx->nerfs.size()) throw std::invalid_argument("unknown NeRF id");
+    return ctx->nerfs[(size_t)id].get();
+}
+
+void invert3(const float* cam12, float out[9]) {
+    // inverse of the matrix whose columns are U, V, W
+    const double a = cam12[0], b = cam12[3], c = cam12[6], d = cam12[1], e = cam12[4], f = cam12[7], g = cam12[2], h = cam12[5], i = cam12[8];
+    const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+    const double inv = det != 0.0 ? 1.0 / det : 0.0;
+    out[0] = (float)((e * i - f * h) * inv); out[1] = (float)((c * h - b * i) * inv); out[2] = (float)((b * f - c * e) * inv);
+    out[3] = (float)((f * g - d * i) * inv); out[4] = (float)((a * i - c * g) * inv); out[5] = (float)((c * d - a * f) * inv);
+    out[6] = (float)((d * h - e * g) * inv); out[7] = (float)((b * g - a * h) * inv); out[8] = (float)((a * e - b * d) * inv);
+}
+
+void upload_mesh_if_dirty(nmr_ctx* ctx) {
+    if (!ctx->mesh_dirty) return;
+    std::vector<float> wpos, wnrm, uv;
+    std::vector<uint32_t> idx;
+    for (const auto& m : ctx->meshes) {
+        std::vector<float> p, n;
+        transform_mesh(m->host, m->t, m->s, m->r, p, n);
+        const uint32_t base = (uint32_t)(wpos.size() / 3);
+        wpos.insert(wpos.end(), p.begin(), p.end());
+        wnrm.insert(wnrm.end(), n.begin(), n.end());
+        uv.insert(uv.end(), m->host.texcoords.begin(), m->host.texcoords.end());
+        for (uint32_t i : m->host.indices) idx.push_back(base + i);
+    }
+    MeshDevice d{};
+    d.n_tris = (uint32_t)(idx.size() / 3);
+    if (d.n_tris) {
+        ctx->d_wpos.ensure(wpos.size()); ctx->d_wnrm.ensure(wnrm.size()); ctx->d_uv.ensure(uv.size()); ctx->d_idx.ensure(idx.size());
+        CK(cudaMemcpyAsync(ctx->d_wpos.p, wpos.data(), wpos.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_wnrm.p, wnrm.data(), wnrm.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_uv.p, uv.data(), uv.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_idx.p, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        const HostMesh& m0 = ctx->meshes[0]->host;   // one material for the whole scene (first mesh), see DESIGN.md
+        std::memcpy(d.base_color, m0.base_color, 16); std::memcpy(d.emissive, m0.emissive, 12);
+        d.metallic = m0.metallic; d.roughness = m0.roughness;
+        std::vector<float> tex;
+        if (!m0.tex_rgba8.empty()) {
+            tex.resize((size_t)m0.tex_w * m0.tex_h * 4);
+            for (size_t i = 0; i < (size_t)m0.tex_w * m0.tex_h; ++i) {
+                for (int k = 0; k < 3; ++k) {
+                    const float sv = (float)m0.tex_rgba8[i * 4 + k] / 255.0f;
+                    tex[i * 4 + k] = sv <= 0.04045f ? sv / 12.92f : powf((sv + 0.055f) / 1.055f, 2.4f);
+                }
+                tex[i * 4 + 3] = (float)m0.tex_rgba8[i * 4 + 3] / 255.0f;
+            }
+            ctx->d_tex.ensure(tex.size());
+            CK(cudaMemcpyAsync(ctx->d_tex.p, tex.data(), tex.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+            d.tex_lin = ctx->d_tex.p; d.tex_w = m0.tex_w; d.tex_h = m0.tex_h;
+        }
+        CK(cudaStreamSynchronize(ctx->stream));   // host vectors go out of scope
+        d.wpos = ctx->d_wpos.p; d.wnrm = ctx->d_wnrm.p; d.uv = ctx->d_uv.p; d.idx = ctx->d_idx.p;
+    }
+    ctx->mesh_dev = d;
+    ctx->mesh_dirty = false;
+}
+
+FrameParams make_params(nmr_ctx* ctx, const Nerf& n, int W, int H, const float* cam12, uint32_t spp_index, bool to_srgb, bool with_mesh) {
+    FrameParams P{};
+    P.width = W; P.height = H;
+    std::memcpy(P.cam, cam12, sizeof(P.cam));
+    std::memcpy(P.aabb_min, n.render_aabb_min, 12); std::memcpy(P.aabb_max, n.render_aabb_max, 12);
+    std::memcpy(P.r2l, n.host.render_aabb_to_local, sizeof(P.r2l));
+    std::memcpy(P.taabb_min, n.host.aabb_min, 12); std::memcpy(P.taabb_max, n.host.aabb_max, 12);
+    P.cone_angle = n.host.cone_angle_constant;
+    P.spp_index = spp_index;
+    P.min_transmittance = n.min_transmittance;
+    P.rgb_activation = n.host.rgb_activation; P.density_activation = n.host.density_activation;
+    std::memcpy(P.background, n.background, 16);
+    P.to_srgb = to_srgb ? 1 : 0;
+    P.shard_rank = ctx->shard_rank; P.shard_world = ctx->shard_world; P.shard_band = ctx->shard_band;
+    P.mesh_scale = (with_mesh && ctx->mesh_dev.n_tris > 0) ? ctx->mesh_scale : 0;
+    std::memcpy(P.light, ctx->light, 12);
+    invert3(cam12, P.cam_inv);
+    return P;
+}
+
+// one sample-per-pixel pass: mesh stage -> init -> march.  Enqueues only; no host synchronisation.
+void enqueue_pass(nmr_ctx* ctx, Nerf& n, const FrameParams& P, bool timed) {
+    Surfaces& S = ctx->surf;
+    const int rows = rows_owned_by(P.height, P.shard_rank, P.shard_world, P.shard_band);
+    FrameOut out{S.image.p, S.accum.p, S.frame.p, S.depth.p, S.n_samples.p};
+    if (timed) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    uint64_t launches = 0;
+    if (P.mesh_scale > 0) { launch_mesh_raster(ctx->mesh_dev, P, rows, S.zbuf.p, ctx->stream); launches += 1; }
+    launch_init_rays(P, n.dev, ctx->mesh_dev, S.zbuf.p, rows, S.queue.p, ctx->d_counters.p, out, ctx->stream);
+    launches += 1;
+    if (timed) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    launch_march(P, n.dev, S.queue.p, ctx->d_counters.p, out, ctx->debug_flags, ctx->num_sms, ctx->stream);
+    launches += 1;
+    if (timed) {
+        CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, sizeof(uint32_t) * kNumCounters, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->stats.rays = (uint64_t)P.width * rows;
+        ctx->stats.mesh_rays = P.mesh_scale > 0 ? (uint64_t)P.width * rows * P.mesh_scale * P.mesh_scale : 0;
+        ctx->stats.kernel_launches = launches;
+        ctx->stats_pending = true;
+    }
+    CK(cudaGetLastError());
+}
+
+void finish_stats(nmr_ctx* ctx) {
+    if (!ctx->stats_pending) return;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.rays_alive = ctx->h_counters[0];
+    ctx->stats.samples = (uint64_t)ctx->h_counters[2] | ((uint64_t)ctx->h_counters[3] << 32);
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[2])); ctx->stats.gpu_ms = ms;
+    CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2])); ctx->stats.march_ms = ms;
+    ctx->stats_pending = false;
+}
+
+void set_camera_from_orbit(nmr_ctx* ctx) {
+    ctx->camera.matrix(ctx->width, ctx->height, ctx->cam12);
+    ctx->surf.spp = 0;   // updateModelViewProj -> reset_accumulation (S/nerf_mesh_renderer.cu:934-938)
+}
+
+}  // namespace
+
+extern "C" {
+
+NMR_API int nmr_create(int width, int height, int device, nmr_ctx** out_ctx) {
+    if (!out_ctx) return fail(nullptr, NMR_ERR_INVALID, "out_ctx is null");
+    *out_ctx = nullptr;
+    if (width <= 0 || height <= 0 || width > 16384 || height > 16384) return fail(nullptr, NMR_ERR_INVALID, "bad resolution");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) return fail(nullptr, NMR_ERR_CUDA, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count = 0"));
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+    if (device >= count) return fail(nullptr, NMR_ERR_INVALID, "device index out of range");
+    cudaDeviceProp prop{};
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(nullptr, NMR_ERR_CUDA, cudaGetErrorString(e));
+    if (prop.major != 10) return fail(nullptr, NMR_ERR_CUDA, std::string("libnmr is built for sm_100a only; device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor));
+    std::unique_ptr<nmr_ctx> ctx(new nmr_ctx());
+    ctx->device = device; ctx->num_sms = prop.multiProcessorCount; ctx->width = width; ctx->height = height;
+    try {
+        CK(cudaSetDevice(device));
+        CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        for (auto& ev : ctx->ev) CK(cudaEventCreate(&ev));
+        ctx->d_counters.ensure(kNumCounters);
+        ctx->d_scratch.ensure(64);
+        CK(cudaHostAlloc((void**)&ctx->h_counters, sizeof(uint32_t) * kNumCounters, cudaHostAllocDefault));
+        std::memset(ctx->h_counters, 0, sizeof(uint32_t) * kNumCounters);
+    } catch (const std::exception& ex) {
+        return fail(nullptr, NMR_ERR_CUDA, ex.what());
+    }
+    set_camera_from_orbit(ctx.get());
+    if (const char* v = std::getenv("NMR_MLP")) if (!std::strcmp(v, "scalar")) ctx->debug_flags |= kDebugScalarMlp;
+    if (const char* v = std::getenv("NMR_UMMA_SWAP")) if (!std::strcmp(v, "1")) ctx->debug_flags |= kDebugSwapLboSbo;
+    *out_ctx = ctx.release();
+    return NMR_OK;
+}
+
+NMR_API void nmr_destroy(nmr_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    ctx->nerfs.clear(); ctx->meshes.clear();
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+NMR_API const char* nmr_last_error(const nmr_ctx* ctx) { return ctx ? ctx->last_error.c_str() : g_create_error.c_str(); }
+
+NMR_API void* nmr_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+NMR_API void nmr_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+NMR_API int nmr_load_nerf(nmr_ctx* ctx, const char* path, int* out_id) {
+    return guarded(ctx, [&]() -> int {
+        if (!path) return fail(ctx, NMR_ERR_INVALID, "path is null");
+        std::unique_ptr<Nerf> n(new Nerf());
+        n->host = load_snapshot(path);
+        HostModel& h = n->host;
+        n->d_params.ensure(h.params.size());
+        CK(cudaMemcpyAsync(n->d_params.p, h.params.data(), h.params.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
+        n->d_bitfield.ensure(kBitfieldBytes);
+        if (!h.density_grid.empty()) {
+            DevBuf<uint16_t> d_grid;
+            d_grid.ensure(h.density_grid.size());
+            CK(cudaMemcpyAsync(d_grid.p, h.density_grid.data(), h.density_grid.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
+            launch_occupancy_build(d_grid.p, h.max_cascade + 1, n->d_bitfield.p, ctx->d_scratch.p, ctx->stream);
+            CK(cudaStreamSynchronize(ctx->stream));
+        } else {
+            CK(cudaMemsetAsync(n->d_bitfield.p, 0, kBitfieldBytes, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+        CK(cudaGetLastError());
+        DeviceModel& d = n->dev;
+        d.mlp = reinterpret_cast<const __half*>(n->d_params.p);
+        d.grid = reinterpret_cast<const __half2*>(n->d_params.p + h.mlp_params);
+        d.bitfield = n->d_bitfield.p;
+        d.dense_mask = 0; d.hash_type = h.hash_type;
+        for (int l = 0; l < h.n_levels; ++l) {
+            d.level_offset[l] = h.offsets[l]; d.level_size[l] = h.offsets[l + 1] - h.offsets[l]; d.level_scale[l] = h.scales[l];
+            d.stride_y[l] = h.stride_y[l]; d.stride_z[l] = h.stride_z[l];
+            if (h.dense[l]) d.dense_mask |= 1u << l;
+        }
+        std::memcpy(n->render_aabb_min, h.render_aabb_min, 12); std::memcpy(n->render_aabb_max, h.render_aabb_max, 12);
+        std::vector<uint16_t>().swap(h.params);
+        std::vector<uint16_t>().swap(h.density_grid);
+        ctx->nerfs.push_back(std::move(n));
+        ctx->surf.spp = 0;
+        if (out_id) *out_id = (int)ctx->nerfs.size() - 1;
+        return NMR_OK;
+    });
+}
+
+NMR_API int nmr_load_mesh(nmr_ctx* ctx, const char* path, const float t[3], const float s[3], const float r_wxyz[4], int* out_id) {
+    return guarded(ctx, [&]() -> int {
+        if (!path) return fail(ctx, NMR_ERR_INVALID, "path is null");
+        std::unique_ptr<Mesh> m(new Mesh());
+        m->host = load_gltf(path);
+        // loadMesh overwrites node 0's TRS with its arguments, defaults t=0, s=1, r=(0,0,0,1) (S/nerf_mesh_renderer.cuh:66-70)
+        const float dt[3] = {0.f, 0.f, 0.f}, ds[3] = {1.f, 1.f, 1.f}, dr[4] = {0.f, 0.f, 0.f, 1.f};
+        std::memcpy(m->t, t ? t : dt, 12); std::memcpy(m->s, s ? s : ds, 12); std::memcpy(m->r, r_wxyz ? r_wxyz : dr, 16);
+        if (!m->host.warning.empty()) ctx->last_error = m->host.warning;
+        ctx->meshes.push_back(std::move(m));
+        ctx->mesh_dirty = true;
+        ctx->surf.spp = 0;
+        if (out_id) *out_id = (int)ctx->meshes.size() - 1;
+        return NMR_OK;
+    });
+}
+
+NMR_API int nmr_set_mesh_transform(nmr_ctx* ctx, int mesh_id, const float t[3], const float s[3], const float r_wxyz[4]) {
+    return guarded(ctx, [&]() -> int {
+        if (mesh_id < 0 || mesh_id >= (int)ctx->meshes.size()) return fail(ctx, NMR_ERR_INVALID, "unknown mesh id");
+        Mesh& m = *ctx->meshes[(size_t)mesh_id];
+        if (t) std::memcpy(m.t, t, 12);
+        if (s) std::memcpy(m.s, s, 12);
+        if (r_wxyz) std::memcpy(m.r, r_wxyz, 16);
+        ctx->mesh_dirty = true; ctx->surf.spp = 0;
+        return NMR_OK;
+    });
+}
+NMR_API int nmr_get_mesh_transform(nmr_ctx* ctx, int mesh_id, float t[3], float s[3], float r_wxyz[4]) {
+    return guarded(ctx, [&]() -> int {
+        if (mesh_id < 0 || mesh_id >= (int)ctx->meshes.size()) return fail(ctx, NMR_ERR_INVALID, "unknown mesh id");
+        const Mesh& m = *ctx->meshes[(size_t)mesh_id];
+        if (t) std::memcpy(t, m.t, 12);
+        if (s) std::memcpy(s, m.s, 12);
+        if (r_wxyz) std::memcpy(r_wxyz, m.r, 16);
+        return NMR_OK;
+    });
+}
+
+NMR_API int nmr_set_envmap(nmr_ctx* ctx, const char* path) {
+    return guarded(ctx, [&]() -> int { ctx->envmap_path = path ? path : ""; return NMR_OK; });
+}
+
+NMR_API int nmr_get_render_aabb(nmr_ctx* ctx, int id, float mn[3], float mx[3]) {
+    return guarded(ctx, [&]() -> int { try { Nerf* n = get_nerf(ctx, id); std::memcpy(mn, n->render_aabb_min, 12); std::memcpy(mx, n->render_aabb_max, 12); return NMR_OK; } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); } });
+}
+NMR_API int nmr_set_render_aabb(nmr_ctx* ctx, int id, const float mn[3], const float mx[3]) {
+    return guarded(ctx, [&]() -> int { try { Nerf* n = get_nerf(ctx, id); if (mn) std::memcpy(n->render_aabb_min, mn, 12); if (mx) std::memcpy(n->render_aabb_max, mx, 12); ctx->surf.spp = 0; return NMR_OK; } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); } });
+}
+NMR_API int nmr_get_aabb(nmr_ctx* ctx, int id, float mn[3], float mx[3]) {
+    return guarded(ctx, [&]() -> int { try { Nerf* n = get_nerf(ctx, id); std::memcpy(mn, n->host.aabb_min, 12); std::memcpy(mx, n->host.aabb_max, 12); return NMR_OK; } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); } });
+}
+NMR_API int nmr_get_background(nmr_ctx* ctx, int id, float rgba[4]) {
+    return guarded(ctx, [&]() -> int { try { std::memcpy(rgba, get_nerf(ctx, id)->background, 16); return NMR_OK; } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); } });
+}
+NMR_API int nmr_set_background(nmr_ctx* ctx, int id, const float rgba[4]) {
+    return guarded(ctx, [&]() -> int { try { std::memcpy(get_nerf(ctx, id)->background, rgba, 16); return NMR_OK; } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); } });
+}
+NMR_API int nmr_set_min_transmittance(nmr_ctx* ctx, int id, float v) {
+    return guarded(ctx, [&]() -> int { try { get_nerf(ctx, id)->min_transmittance = v; return NMR_OK; } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); } });
+}
+
+NMR_API int nmr_orbit(nmr_ctx* ctx, float daz, float dpol, float dzoom) {
+    return guarded(ctx, [&]() -> int { ctx->camera.orbit(daz, dpol, dzoom); set_camera_from_orbit(ctx); return NMR_OK; });
+}
+NMR_API int nmr_get_camera(nmr_ctx* ctx, float out12[12]) {
+    return guarded(ctx, [&]() -> int { std::memcpy(out12, ctx->cam12, sizeof(ctx->cam12)); return NMR_OK; });
+}
+NMR_API int nmr_set_camera(nmr_ctx* ctx, const float in12[12]) {
+    return guarded(ctx, [&]() -> int {
+        std::memcpy(ctx->cam12, in12, sizeof(ctx->cam12));
+        for (int k = 0; k < 3; ++k) ctx->camera.eye[k] = in12[9 + k];   // keeps orbit() and the mesh stage coherent with the new pose
+        ctx->surf.spp = 0;
+        return NMR_OK;
+    });
+}
+
+NMR_API int nmr_set_shard(nmr_ctx* ctx, int rank, int world, int band) {
+    return guarded(ctx, [&]() -> int {
+        if (world < 1 || rank < 0 || rank >= world || band < 1) return fail(ctx, NMR_ERR_INVALID, "bad shard specification");
+        ctx->shard_rank = rank; ctx->shard_world = world; ctx->shard_band = band; ctx->surf.spp = 0;
+        return NMR_OK;
+    });
+}
+
+NMR_API int nmr_frame(nmr_ctx* ctx, int* keep_running) {
+    return guarded(ctx, [&]() -> int {
+        if (keep_running) *keep_running = 1;
+        if (ctx->nerfs.empty()) return NMR_OK;   // the reference draws an empty window
+        upload_mesh_if_dirty(ctx);
+        Nerf& n = *ctx->nerfs[0];
+        ctx->surf.resize(ctx->width, ctx->height, ctx->mesh_scale);
+        const FrameParams P = make_params(ctx, n, ctx->width, ctx->height, ctx->cam12, ctx->surf.spp, true, true);
+        enqueue_pass(ctx, n, P, true);
+        ++ctx->surf.spp;
+        CK(cudaStreamSynchronize(ctx->stream));   // frame() returns a finished frame (S/nerf_mesh_renderer.cu:578)
+        return NMR_OK;
+    });
+}
+
+NMR_API int nmr_read_frame(nmr_ctx* ctx, float* out_rgba) {
+    return guarded(ctx, [&]() -> int {
+        if (!out_rgba) return fail(ctx, NMR_ERR_INVALID, "out_rgba is null");
+        if (!ctx->surf.image.p || ctx->surf.w == 0) return fail(ctx, NMR_ERR_STATE, "nothing rendered yet");
+        CK(cudaMemcpyAsync(out_rgba, ctx->surf.image.p, (size_t)ctx->surf.w * ctx->surf.h * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return NMR_OK;
+    });
+}
+
+NMR_API int nmr_render(nmr_ctx* ctx, int nerf_id, int width, int height, int spp, int linear, float* out_rgba) {
+    return guarded(ctx, [&]() -> int {
+        if (width <= 0 || height <= 0 || spp < 1 || !out_rgba) return fail(ctx, NMR_ERR_INVALID, "bad render arguments");
+        Nerf* n;
+        try { n = get_nerf(ctx, nerf_id); } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); }
+        upload_mesh_if_dirty(ctx);
+        ctx->surf.resize(width, height, ctx->mesh_scale);
+        ctx->surf.spp = 0;   // reset_accumulation (S/python_api.cu:85)
+        // Testbed::render uses Testbed::m_camera, which frame()/orbit keep equal to viewProjectionMat; its aspect comes from the
+        // renderer's constructor resolution, not from (width, height), exactly like the reference.
+        for (int i = 0; i < spp; ++i) {
+            const FrameParams P = make_params(ctx, *n, width, height, ctx->cam12, ctx->surf.spp, !linear, true);
+            enqueue_pass(ctx, *n, P, i == spp - 1);
+            ++ctx->surf.spp;
+        }
+        CK(cudaMemcpyAsync(out_rgba, ctx->surf.image.p, (size_t)width * height * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->surf.spp = 0;   // the next frame() starts a fresh accumulation at its own resolution
+        return NMR_OK;
+    });
+}
+
+NMR_API int nmr_render_views(nmr_ctx* ctx, int nerf_id, int n_views, const float* cams12, int width, int height, int linear, float* out_rgba) {
+    return guarded(ctx, [&]() -> int {
+        if (width <= 0 || height <= 0 || n_views < 1 || !out_rgba || !cams12) return fail(ctx, NMR_ERR_INVALID, "bad render_views arguments");
+        Nerf* n;
+        try { n = get_nerf(ctx, nerf_id); } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); }
+        upload_mesh_if_dirty(ctx);
+        ctx->surf.resize(width, height, ctx->mesh_scale);
+        const size_t px = (size_t)width * height;
+        for (int v = 0; v < n_views; ++v) {
+            const FrameParams P = make_params(ctx, *n, width, height, cams12 + (size_t)v * 12, 0, !linear, true);
+            enqueue_pass(ctx, *n, P, v == n_views - 1);
+            // stream order makes the copy wait for this view's kernels and the next view's kernels wait for the copy
+            CK(cudaMemcpyAsync(out_rgba + (size_t)v * px * 4, ctx->surf.image.p, px * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->surf.spp = 0;
+        return NMR_OK;
+    });
+}
+
+NMR_API int nmr_get_device_image(nmr_ctx* ctx, void** out_dev_ptr, int* out_w, int* out_h) {
+    return guarded(ctx, [&]() -> int {
+        if (!ctx->surf.image.p) return fail(ctx, NMR_ERR_STATE, "nothing rendered yet");
+        if (out_dev_ptr) *out_dev_ptr = ctx->surf.image.p;
+        if (out_w) *out_w = ctx->surf.w;
+        if (out_h) *out_h = ctx->surf.h;
+        return NMR_OK;
+    });
+}
+
+NMR_API int nmr_copy_device_image(nmr_ctx* ctx, void* dst) {
+    return guarded(ctx, [&]() -> int {
+        if (!ctx->surf.image.p || !dst) return fail(ctx, NMR_ERR_STATE, "nothing rendered yet");
+        CK(cudaMemcpyAsync(dst, ctx->surf.image.p, (size_t)ctx->surf.w * ctx->surf.h * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return NMR_OK;
+    });
+}
+
+NMR_API int nmr_flush_l2(nmr_ctx* ctx) {
+    return guarded(ctx, [&]() -> int {
+        const size_t bytes = (size_t)256 << 20;
+        ctx->d_flush.ensure(bytes);
+        CK(cudaMemsetAsync(ctx->d_flush.p, 0x5A, bytes, ctx->stream));
+        return NMR_OK;
+    });
+}
+
+NMR_API int nmr_get_stats(nmr_ctx* ctx, nmr_stats* out) {
+    return guarded(ctx, [&]() -> int { if (!out) return fail(ctx, NMR_ERR_INVALID, "out is null"); finish_stats(ctx); *out = ctx->stats; return NMR_OK; });
+}
+NMR_API int nmr_synchronize(nmr_ctx* ctx) {
+    return guarded(ctx, [&]() -> int { CK(cudaStreamSynchronize(ctx->stream)); return NMR_OK; });
+}
+
+// Asynchronous frame for throughput measurements and pipelined callers: same work as nmr_frame without the trailing
+// synchronisation; call nmr_synchronize() / nmr_get_stats() / nmr_read_frame() to wait.
+NMR_API int nmr_frame_async(nmr_ctx* ctx) {
+    return guarded(ctx, [&]() -> int {
+        if (ctx->nerfs.empty()) return fail(ctx, NMR_ERR_STATE, "no NeRF loaded");
+        upload_mesh_if_dirty(ctx);
+        Nerf& n = *ctx->nerfs[0];
+        ctx->surf.resize(ctx->width, ctx->height, ctx->mesh_scale);
+        const FrameParams P = make_params(ctx, n, ctx->width, ctx->height, ctx->cam12, ctx->surf.spp, true, true);
+        enqueue_pass(ctx, n, P, true);
+        ++ctx->surf.spp;
+        return NMR_OK;
+    });
+}
+
+NMR_API int nmr_get_density_bitfield(nmr_ctx* ctx, int id, uint8_t* out) {
+    return guarded(ctx, [&]() -> int {
+        Nerf* n; try { n = get_nerf(ctx, id); } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); }
+        CK(cudaMemcpyAsync(out, n->d_bitfield.p, kBitfieldBytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return NMR_OK;
+    });
+}
+NMR_API int nmr_set_density_bitfield(nmr_ctx* ctx, int id, const uint8_t* in) {
+    return guarded(ctx, [&]() -> int {
+        Nerf* n; try { n = get_nerf(ctx, id); } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); }
+        CK(cudaMemcpyAsync(n->d_bitfield.p, in, kBitfieldBytes, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->surf.spp = 0;
+        return NMR_OK;
+    });
+}
+
+NMR_API int nmr_remove_floaties(nmr_ctx* ctx, int* out_clusters, int64_t* out_kept) {
+    return guarded(ctx, [&]() -> int {
+        if (ctx->nerfs.empty()) return fail(ctx, NMR_ERR_STATE, "no NeRF loaded");
+        Nerf& n = *ctx->nerfs.back();   // _nerfs.back(), S/nerf_mesh_renderer.cu:248
+        DevBuf<uint32_t> labels; labels.ensure(floaties_label_bytes() / 4);
+        DevBuf<unsigned long long> scratch; scratch.ensure(floaties_scratch_bytes() / 8);
+        launch_remove_floaties(n.d_bitfield.p, n.host.max_cascade, labels.p, scratch.p, ctx->stream);
+        unsigned long long res[4] = {0, 0, 0, 0};
+        CK(cudaMemcpyAsync(res, scratch.p, sizeof(res), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaGetLastError());
+        if (out_clusters) *out_clusters = (int)res[0];
+        if (out_kept) *out_kept = (int64_t)res[1];
+        ctx->surf.spp = 0;
+        return NMR_OK;
+    });
+}
+
+// ---- parity probes ------------------------------------------------------------------------------------------------
+NMR_API int nmr_debug_encode(nmr_ctx* ctx, int id, const float* pos, int64_t n, uint16_t* out) {
+    return guarded(ctx, [&]() -> int {
+        Nerf* nf; try { nf = get_nerf(ctx, id); } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); }
+        if (n <= 0) return NMR_OK;
+        DevBuf<float> d_pos; DevBuf<uint16_t> d_out;
+        d_pos.ensure((size_t)n * 3); d_out.ensure((size_t)n * ENC_WIDTH);
+        CK(cudaMemcpyAsync(d_pos.p, pos, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
+        launch_debug_encode(nf->dev, d_pos.p, n, d_out.p, ctx->stream);
+        CK(cudaMemcpyAsync(out, d_out.p, (size_t)n * ENC_WIDTH * 2, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaGetLastError());
+        return NMR_OK;
+    });
+}
+
+NMR_API int nmr_debug_network(nmr_ctx* ctx, int id, const float* pos, const float* dir, int64_t n, uint16_t* out4) {
+    return guarded(ctx, [&]() -> int {
+        Nerf* nf; try { nf = get_nerf(ctx, id); } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); }
+        if (n <= 0) return NMR_OK;
+        DevBuf<float> d_pos, d_dir; DevBuf<uint16_t> d_out;
+        d_pos.ensure((size_t)n * 3); d_dir.ensure((size_t)n * 3); d_out.ensure((size_t)n * 4);
+        CK(cudaMemcpyAsync(d_pos.p, pos, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d_dir.p, dir, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
+        launch_debug_network(nf->dev, d_pos.p, d_dir.p, n, d_out.p, ctx->debug_flags, ctx->stream);
+        CK(cudaMemcpyAsync(out4, d_out.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaGetLastError());
+        return NMR_OK;
+    });
+}
+
+NMR_API int nmr_debug_trace(nmr_ctx* ctx, int id, int width, int height, const uint32_t* pixels, int64_t n_pix, uint32_t max_samples,
+                            float* o_t, uint32_t* o_cell, uint32_t* o_mip, float* o_pos, uint32_t* o_count, float* o_ray) {
+    return guarded(ctx, [&]() -> int {
+        Nerf* nf; try { nf = get_nerf(ctx, id); } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); }
+        if (n_pix <= 0 || max_samples == 0) return NMR_OK;
+        const size_t ns = (size_t)n_pix * max_samples;
+        DevBuf<uint32_t> d_pix, d_cell, d_mip, d_cnt; DevBuf<float> d_t, d_pos, d_ray;
+        d_pix.ensure((size_t)n_pix); d_cell.ensure(ns); d_mip.ensure(ns); d_cnt.ensure((size_t)n_pix); d_t.ensure(ns); d_pos.ensure(ns * 3); d_ray.ensure((size_t)n_pix * 8);
+        CK(cudaMemcpyAsync(d_pix.p, pixels, (size_t)n_pix * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemsetAsync(d_t.p, 0, ns * 4, ctx->stream)); CK(cudaMemsetAsync(d_cell.p, 0, ns * 4, ctx->stream));
+        CK(cudaMemsetAsync(d_mip.p, 0, ns * 4, ctx->stream)); CK(cudaMemsetAsync(d_pos.p, 0, ns * 12, ctx->stream));
+        const FrameParams P = make_params(ctx, *nf, width, height, ctx->cam12, 0, true, false);
+        launch_debug_trace(P, nf->dev, d_pix.p, n_pix, max_samples, d_t.p, d_cell.p, d_mip.p, d_pos.p, d_cnt.p, d_ray.p, ctx->stream);
+        CK(cudaMemcpyAsync(o_t, d_t.p, ns * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(o_cell, d_cell.p, ns * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(o_mip, d_mip.p, ns * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(o_pos, d_pos.p, ns * 12, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(o_count, d_cnt.p, (size_t)n_pix * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(o_ray, d_ray.p, (size_t)n_pix * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaGetLastError());
+        return NMR_OK;
+    });
+}
+
+NMR_API int nmr_debug_mesh(nmr_ctx* ctx, int width, int height, float* o_rgba2, float* o_depth2, int32_t* o_tri2, float* o_surf, float* o_tsurf) {
+    return guarded(ctx, [&]() -> int {
+        upload_mesh_if_dirty(ctx);
+        if (ctx->mesh_dev.n_tris == 0) return fail(ctx, NMR_ERR_STATE, "no mesh loaded");
+        const int ms = ctx->mesh_scale;
+        const size_t n2 = (size_t)width * ms * height * ms, n1 = (size_t)width * height;
+        DevBuf<unsigned long long> zbuf; zbuf.ensure(n2);
+        DevBuf<float> d_rgba2, d_depth2, d_surf, d_ts; DevBuf<int32_t> d_tri2;
+        d_rgba2.ensure(n2 * 4); d_depth2.ensure(n2); d_tri2.ensure(n2); d_surf.ensure(n1 * 4); d_ts.ensure(n1);
+        FrameParams P{};
+        P.width = width; P.height = height; std::memcpy(P.cam, ctx->cam12, sizeof(P.cam));
+        P.shard_world = 1; P.shard_band = 8; P.mesh_scale = ms; std::memcpy(P.light, ctx->light, 12);
+        invert3(ctx->cam12, P.cam_inv);
+        launch_mesh_raster(ctx->mesh_dev, P, height, zbuf.p, ctx->stream);
+        launch_debug_mesh(ctx->mesh_dev, P, zbuf.p, d_rgba2.p, d_depth2.p, d_tri2.p, d_surf.p, d_ts.p, ctx->stream);
+        if (o_rgba2) CK(cudaMemcpyAsync(o_rgba2, d_rgba2.p, n2 * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        if (o_depth2) CK(cudaMemcpyAsync(o_depth2, d_depth2.p, n2 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (o_tri2) CK(cudaMemcpyAsync(o_tri2, d_tri2.p, n2 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (o_surf) CK(cudaMemcpyAsync(o_surf, d_surf.p, n1 * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        if (o_tsurf) CK(cudaMemcpyAsync(o_tsurf, d_ts.p, n1 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaGetLastError());
+        return NMR_OK;
+    });
+}
+
+NMR_API int nmr_debug_last_frame(nmr_ctx* ctx, float* o_frame, float* o_depth, uint32_t* o_ns) {
+    return guarded(ctx, [&]() -> int {
+        if (!ctx->surf.frame.p || ctx->surf.w == 0) return fail(ctx, NMR_ERR_STATE, "nothing rendered yet");
+        const size_t n = (size_t)ctx->surf.w * ctx->surf.h;
+        if (o_frame) CK(cudaMemcpyAsync(o_frame, ctx->surf.frame.p, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        if (o_depth) CK(cudaMemcpyAsync(o_depth, ctx->surf.depth.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (o_ns) CK(cudaMemcpyAsync(o_ns, ctx->surf.n_samples.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return NMR_OK;
+    });
+}
+
+// debug knob: bit 0 CUDA-core MLP, bit 1 swap UMMA descriptor offsets
+NMR_API int nmr_debug_set_flags(nmr_ctx* ctx, uint32_t flags) {
+    return guarded(ctx, [&]() -> int { ctx->debug_flags = flags; return NMR_OK; });
+}
+
+}  // extern "C"

@@ -1,0 +1,466 @@
+// device_common.cuh - device-side building blocks shared by every kernel of libnmr (sm_100a).
+//
+// Arithmetic contract (DESIGN.md "Numerics"): this translation unit is compiled with --fmad=false, so every
+// fp32 product and sum is rounded separately; the summation orders below are the ones the reference's Eigen/glm
+// expressions evaluate to (pinned on the host against the reference headers, tests/golden/ref_vectors.npz).  That
+// makes ray set-up, occupancy traversal (t, Morton cell, mip) and the fp16 hash-grid features reproducible to the bit.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nmr {
+
+constexpr uint32_t NERF_GRIDSIZE = 128;
+constexpr uint32_t NERF_CASCADES = 8;
+constexpr uint32_t GRID_CELLS = NERF_GRIDSIZE * NERF_GRIDSIZE * NERF_GRIDSIZE;
+constexpr int N_LEVELS = 16;
+constexpr int ENC_WIDTH = 32;
+
+// ---- plain data handed to kernels by value ------------------------------------------------------------------
+struct DeviceModel {
+    const __half2* grid;              // hash-table entries, all levels back to back
+    const __half* mlp;                // density net | rgb net, row-major [out][in] (params_binary order)
+    const uint8_t* bitfield;          // 2 MiB occupancy bits, Morton order per cascade
+    uint32_t level_offset[N_LEVELS];  // first entry of each level
+    uint32_t level_size[N_LEVELS];    // entries in each level
+    float level_scale[N_LEVELS];
+    uint32_t stride_y[N_LEVELS], stride_z[N_LEVELS];
+    uint32_t dense_mask;              // bit l set: level l is indexed densely
+    int hash_type;                    // 0 Prime, 1 CoherentPrime, 2 ReversedPrime
+};
+
+struct MeshDevice {
+    const float* wpos;      // [n_verts][3] world space
+    const float* wnrm;      // [n_verts][3]
+    const float* uv;        // [n_verts][2]
+    const uint32_t* idx;    // [n_tris][3]
+    const float* tex_lin;   // [h][w][4] linearised texture or nullptr
+    uint32_t n_tris;
+    int tex_w, tex_h;
+    float base_color[4], emissive[3], metallic, roughness;
+};
+
+struct FrameParams {
+    int width, height;
+    float cam[12];                    // column-major 3x4
+    float aabb_min[3], aabb_max[3];   // render aabb
+    float r2l[9];                     // render_aabb_to_local, row-major
+    float taabb_min[3], taabb_max[3]; // training aabb
+    float cone_angle;
+    uint32_t spp_index;
+    float min_transmittance;
+    int rgb_activation, density_activation;
+    float background[4];
+    int to_srgb;
+    int shard_rank, shard_world, shard_band;
+    int mesh_scale;                   // 0: no mesh stage
+    float light[3];
+    float cam_inv[9];                 // inverse of [U V W] (row-major), for the rasteriser's bounding boxes
+};
+
+// ---- tiny vector helpers -------------------------------------------------------------------------------------
+struct V3 { float x, y, z; };
+__device__ __forceinline__ V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ V3 vadd(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 vsub(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 vmul(V3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ V3 vcross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+// glm::dot - left to right
+__device__ __forceinline__ float gdot(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+// Eigen 3-element redux - e0 + (e1 + e2)
+__device__ __forceinline__ float edot(V3 a, V3 b) { return a.x * b.x + (a.y * b.y + a.z * b.z); }
+__device__ __forceinline__ V3 gnormalize(V3 a) { const float inv = 1.0f / sqrtf(gdot(a, a)); return vmul(a, inv); }
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return v < lo ? lo : (hi < v ? hi : v); }
+
+// ---- Morton code (T/include/tiny-cuda-nn/common_device.h:338-353) ---------------------------------------------
+__device__ __forceinline__ uint32_t expand_bits(uint32_t v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+__device__ __forceinline__ uint32_t morton3D(uint32_t x, uint32_t y, uint32_t z) { return expand_bits(x) | (expand_bits(y) << 1) | (expand_bits(z) << 2); }
+__host__ __device__ __forceinline__ uint32_t morton3D_invert(uint32_t x) {
+    x = x & 0x49249249u;
+    x = (x | (x >> 2)) & 0xc30c30c3u;
+    x = (x | (x >> 4)) & 0x0f00f00fu;
+    x = (x | (x >> 8)) & 0xff0000ffu;
+    x = (x | (x >> 16)) & 0x0000ffffu;
+    return x;
+}
+
+// ---- start jitter (S/ngp/random_val.cuh:163-294; Sobol dimension 0 is a bit reversal) -------------------------
+__device__ __forceinline__ uint32_t lk_permute(uint32_t x, uint32_t seed) {
+    x += seed;
+    x ^= x * 0x6c50b47cu;
+    x ^= x * 0xb82f1e52u;
+    x ^= x * 0xc7afe638u;
+    x ^= x * 0x8d22f6e6u;
+    return x;
+}
+__device__ __forceinline__ uint32_t nested_scramble(uint32_t x, uint32_t seed) { return __brev(lk_permute(__brev(x), seed)); }
+__device__ __forceinline__ float ld_random_val(uint32_t index, uint32_t seed) {
+    index = nested_scramble(index, seed);
+    const uint32_t s0 = seed ^ (0u + (seed << 6) + (seed >> 2));   // hash_combine(seed, 0)
+    return (float)nested_scramble(__brev(index), s0) * 2.3283064365386963e-10f;
+}
+
+// ---- step sizes (S/ngp/testbed.cu:177-232) -------------------------------------------------------------------
+#define NMR_SQRT3 1.73205080757f
+__device__ __forceinline__ float min_cone_stepsize() { return NMR_SQRT3 / 1024.0f; }
+__device__ __forceinline__ float max_cone_stepsize() { return (NMR_SQRT3 / 1024.0f) * 128.0f * 1024.0f / 128.0f; }
+__device__ __forceinline__ float calc_dt(float t, float cone_angle) { return clampf(t * cone_angle, min_cone_stepsize(), max_cone_stepsize()); }
+__device__ __forceinline__ float warp_dt(float dt) {
+    const float max_stepsize = min_cone_stepsize() * 128.0f;
+    return (dt - min_cone_stepsize()) / (max_stepsize - min_cone_stepsize());
+}
+__device__ __forceinline__ float unwarp_dt(float dt) {
+    const float max_stepsize = min_cone_stepsize() * 128.0f;
+    return dt * (max_stepsize - min_cone_stepsize()) + min_cone_stepsize();
+}
+
+// ---- occupancy-grid DDA (S/ngp/testbed.cu:188-202, 234-264, 293-315) -----------------------------------------
+// frexpf exponent: exact, with the bit trick for normal numbers
+__device__ __forceinline__ int frexp_exponent(float v) {
+    const uint32_t b = __float_as_uint(v) & 0x7FFFFFFFu;
+    if (b == 0u) return 0;
+    const uint32_t e = b >> 23;
+    if (e == 0u || e == 255u) { int ex; frexpf(v, &ex); return ex; }
+    return (int)e - 126;
+}
+__device__ __forceinline__ int mip_from_pos(V3 pos) {
+    const float maxval = fmaxf(fmaxf(fabsf(pos.x - 0.5f), fabsf(pos.y - 0.5f)), fabsf(pos.z - 0.5f));
+    const int e = frexp_exponent(maxval) + 1;
+    return min((int)NERF_CASCADES - 1, max(0, e));
+}
+__device__ __forceinline__ int mip_from_dt(float dt, V3 pos) {
+    const int mip = mip_from_pos(pos);
+    dt *= 2 * NERF_GRIDSIZE;
+    if (dt < 1.f) return mip;
+    return min((int)NERF_CASCADES - 1, max(frexp_exponent(dt), mip));
+}
+__device__ __forceinline__ uint32_t cascaded_grid_idx_at(V3 pos, uint32_t mip) {
+    const float mip_scale = __uint_as_float((127u - mip) << 23);   // scalbnf(1.0f, -mip)
+    pos.x -= 0.5f; pos.y -= 0.5f; pos.z -= 0.5f;
+    pos.x *= mip_scale; pos.y *= mip_scale; pos.z *= mip_scale;
+    pos.x += 0.5f; pos.y += 0.5f; pos.z += 0.5f;
+    const int ix = min(max(__float2int_rz(pos.x * (float)NERF_GRIDSIZE), 0), 127);
+    const int iy = min(max(__float2int_rz(pos.y * (float)NERF_GRIDSIZE), 0), 127);
+    const int iz = min(max(__float2int_rz(pos.z * (float)NERF_GRIDSIZE), 0), 127);
+    return morton3D((uint32_t)ix, (uint32_t)iy, (uint32_t)iz);
+}
+__device__ __forceinline__ bool occupied_at(V3 pos, const uint8_t* __restrict__ bitfield, uint32_t mip, uint32_t* cell_out = nullptr) {
+    const uint32_t idx = cascaded_grid_idx_at(pos, mip);
+    if (cell_out) *cell_out = idx;
+    return __ldg(bitfield + idx / 8 + (GRID_CELLS / 8) * mip) & (1u << (idx % 8));
+}
+__device__ __forceinline__ float distance_to_next_voxel(V3 pos, V3 dir, V3 idir, uint32_t res) {
+    const float r = (float)res;
+    const V3 p = v3(r * pos.x, r * pos.y, r * pos.z);
+    const float tx = (floorf(p.x + 0.5f + 0.5f * copysignf(1.0f, dir.x)) - p.x) * idir.x;
+    const float ty = (floorf(p.y + 0.5f + 0.5f * copysignf(1.0f, dir.y)) - p.y) * idir.y;
+    const float tz = (floorf(p.z + 0.5f + 0.5f * copysignf(1.0f, dir.z)) - p.z) * idir.z;
+    const float t = fminf(fminf(tx, ty), tz);
+    return fmaxf(t / r, 0.0f);
+}
+__device__ __forceinline__ float advance_to_next_voxel(float t, float cone_angle, V3 pos, V3 dir, V3 idir, uint32_t res) {
+    const float t_target = t + distance_to_next_voxel(pos, dir, idir, res);
+    do { t += calc_dt(t, cone_angle); } while (t < t_target);
+    return t;
+}
+
+// ---- boxes (S/ngp/bounding_box.cuh:106-167) -------------------------------------------------------------------
+__device__ __forceinline__ bool box_contains(const float* mn, const float* mx, V3 p) {
+    return p.x >= mn[0] && p.x <= mx[0] && p.y >= mn[1] && p.y <= mx[1] && p.z >= mn[2] && p.z <= mx[2];
+}
+__device__ __forceinline__ float box_ray_tmin(const float* mn, const float* mx, V3 pos, V3 dir) {
+    const float FMAXV = 3.402823466e+38f;
+    float tmin = (mn[0] - pos.x) / dir.x, tmax = (mx[0] - pos.x) / dir.x;
+    if (tmin > tmax) { const float c = tmin; tmin = tmax; tmax = c; }
+    float tymin = (mn[1] - pos.y) / dir.y, tymax = (mx[1] - pos.y) / dir.y;
+    if (tymin > tymax) { const float c = tymin; tymin = tymax; tymax = c; }
+    if (tmin > tymax || tymin > tmax) return FMAXV;
+    if (tymin > tmin) tmin = tymin;
+    if (tymax < tmax) tmax = tymax;
+    float tzmin = (mn[2] - pos.z) / dir.z, tzmax = (mx[2] - pos.z) / dir.z;
+    if (tzmin > tzmax) { const float c = tzmin; tzmin = tzmax; tzmax = c; }
+    if (tmin > tzmax || tzmin > tmax) return FMAXV;
+    if (tzmin > tmin) tmin = tzmin;
+    return tmin;
+}
+__device__ __forceinline__ V3 r2l_mul(const float* m, V3 p) {   // Eigen Matrix3f * Vector3f
+    return v3(m[0] * p.x + (m[1] * p.y + m[2] * p.z), m[3] * p.x + (m[4] * p.y + m[5] * p.z), m[6] * p.x + (m[7] * p.y + m[8] * p.z));
+}
+
+// ---- ray set-up (S/ngp/ngp_common.cuh:362-368; S/ngp/testbed.cu:435-464) ---------------------------------------
+struct RayInit { V3 origin, dir; float t; bool alive; };
+__device__ __forceinline__ RayInit init_ray(const FrameParams& P, uint32_t x, uint32_t y) {
+    const float* c = P.cam;
+    const float ux = 2.0f * (((float)x + 0.5f) / (float)P.width) - 1.0f;
+    const float uy = 2.0f * (((float)y + 0.5f) / (float)P.height) - 1.0f;
+    V3 d = v3(c[0] * ux + (c[3] * uy + c[6] * 1.0f), c[1] * ux + (c[4] * uy + c[7] * 1.0f), c[2] * ux + (c[5] * uy + c[8] * 1.0f));
+    const float z = edot(d, d);
+    if (z > 0.0f) { const float n = sqrtf(z); d = v3(d.x / n, d.y / n, d.z / n); }
+    RayInit r;
+    r.origin = v3(c[9] + 0.5f, c[10] + 0.5f, c[11] + 0.5f);
+    r.dir = d;
+    r.t = fmaxf(box_ray_tmin(P.aabb_min, P.aabb_max, r.origin, d), 0.0f) + 1e-6f;
+    r.alive = box_contains(P.aabb_min, P.aabb_max, vadd(r.origin, vmul(d, r.t)));
+    return r;
+}
+
+// advance_pos_nerf (S/ngp/testbed.cu:470-537); returns alive
+__device__ __forceinline__ bool advance_pos(const FrameParams& P, const uint8_t* __restrict__ bitfield, V3 origin, V3 dir, uint32_t pixel_idx,
+                                            float t_surface, bool alive, float& t_io, float& t_start) {
+    t_start = 0.f;
+    if (!alive) {
+        if (t_surface != 0.0f) { t_io = t_surface; return true; }
+        return false;
+    }
+    const V3 idir = v3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
+    const float cone = P.cone_angle;
+    float t = t_io;
+    float dt = calc_dt(t, cone);
+    t += ld_random_val(P.spp_index, pixel_idx * 786433u) * dt;
+    while (true) {
+        if (t_surface != 0.0f && t > t_surface) { t_io = t_surface; return true; }
+        const V3 pos = vadd(origin, vmul(dir, t));
+        if (!box_contains(P.aabb_min, P.aabb_max, r2l_mul(P.r2l, pos))) {
+            if (t_surface != 0.0f) { t_io = t_surface; return true; }
+            alive = false;
+            break;
+        }
+        dt = calc_dt(t, cone);
+        const uint32_t mip = (uint32_t)mip_from_dt(dt, pos);
+        if (occupied_at(pos, bitfield, mip)) break;
+        t = advance_to_next_voxel(t, cone, pos, dir, idir, NERF_GRIDSIZE >> mip);
+    }
+    t_io = t;
+    if (mip_from_pos(vadd(origin, vmul(dir, t))) == 0) t_start = t;
+    return alive;
+}
+
+// One step of generate_next_nerf_network_inputs (S/ngp/testbed.cu:564-633) with n_steps = 1.
+// Returns 1 with the sample (warped position, warped dt) and t advanced past it, or 0 when the ray produced no sample
+// (left the box, or reached an opaque mesh surface, in which case t is snapped to t_surface).
+struct Sample { V3 pos; float dt_warped; float t; uint32_t cell, mip; };
+__device__ __forceinline__ int next_sample(const FrameParams& P, const uint8_t* __restrict__ bitfield, V3 origin, V3 dir, V3 idir,
+                                           float t_start, float t_surface, float surf_w, bool ignore_surface, float& t_io, Sample& s) {
+    const float cone = P.cone_angle;
+    float t = t_io;
+    V3 pos; float dt; uint32_t mip, cell;
+    while (true) {
+        if (!ignore_surface && t_surface != 0.0f && t > t_surface && surf_w == 1.f) { t_io = t_surface; return 0; }
+        pos = vadd(origin, vmul(dir, t));
+        if (!box_contains(P.aabb_min, P.aabb_max, r2l_mul(P.r2l, pos))) return 0;
+        dt = calc_dt(t - t_start, cone);
+        mip = (uint32_t)mip_from_dt(dt, pos);
+        if (occupied_at(pos, bitfield, mip, &cell)) break;
+        t = advance_to_next_voxel(t, cone, pos, dir, idir, NERF_GRIDSIZE >> mip);
+    }
+    const V3 diag = v3(P.taabb_max[0] - P.taabb_min[0], P.taabb_max[1] - P.taabb_min[1], P.taabb_max[2] - P.taabb_min[2]);
+    s.pos = v3((pos.x - P.taabb_min[0]) / diag.x, (pos.y - P.taabb_min[1]) / diag.y, (pos.z - P.taabb_min[2]) / diag.z);
+    s.dt_warped = warp_dt(dt);
+    s.t = t; s.cell = cell; s.mip = mip;
+    t_io = t + dt;
+    return 1;
+}
+
+// ---- multiresolution hash-grid encoding (T/.../encodings/grid.h:111-186, 219-349) ------------------------------
+template <int HASH>
+__device__ __forceinline__ uint32_t grid_hash(uint32_t x, uint32_t y, uint32_t z) {
+    if (HASH == 0) return (x * 1958374283u) ^ (y * 2654435761u) ^ (z * 805459861u);
+    if (HASH == 2) return (x * 2165219737u) ^ (y * 1434869437u) ^ (z * 2097192037u);
+    return x ^ (y * 2654435761u) ^ (z * 805459861u);
+}
+
+// One level: eight half2 gathers, trilinear blend accumulated IN FP16 in corner order 0..7 (grid.h:317-343).
+template <int HASH>
+__device__ __forceinline__ __half2 encode_level(const DeviceModel& M, int level, V3 p01) {
+    const float scale = M.level_scale[level];
+    const uint32_t size = M.level_size[level];
+    const __half2* __restrict__ grid = M.grid + M.level_offset[level];
+    const float fx = p01.x * scale + 0.5f, fy = p01.y * scale + 0.5f, fz = p01.z * scale + 0.5f;
+    const float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
+    const uint32_t gx = (uint32_t)(int)flx, gy = (uint32_t)(int)fly, gz = (uint32_t)(int)flz;
+    const float wx1 = fx - flx, wy1 = fy - fly, wz1 = fz - flz;
+    const float wx0 = 1 - wx1, wy0 = 1 - wy1, wz0 = 1 - wz1;
+    const bool dense = (M.dense_mask >> level) & 1u;
+    uint32_t index[8];
+    if (dense) {
+        const uint32_t sy = M.stride_y[level], sz = M.stride_z[level];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const uint32_t x = gx + (c & 1), y = gy + ((c >> 1) & 1), z = gz + ((c >> 2) & 1);
+            uint32_t i = x + y * sy + z * sz;
+            if (i >= size) i %= size;          // only the wrap-around cells at the upper faces take this branch
+            index[c] = i;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const uint32_t x = gx + (c & 1), y = gy + ((c >> 1) & 1), z = gz + ((c >> 2) & 1);
+            index[c] = grid_hash<HASH>(x, y, z) & (size - 1u);   // a hashed level always has exactly 2^log2_hashmap_size entries
+        }
+    }
+    __half2 v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = __ldg(grid + index[c]);
+    __half2 acc = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        // weight = 1 * wx * wy * wz, multiplied in dimension order like the reference's loop
+        const float w = ((1.0f * ((c & 1) ? wx1 : wx0)) * (((c >> 1) & 1) ? wy1 : wy0)) * (((c >> 2) & 1) ? wz1 : wz0);
+        const float2 d = __half22float2(v[c]);
+        acc = __hadd2(acc, __floats2half2_rn(w * d.x, w * d.y));
+    }
+    return acc;
+}
+
+// All 16 levels of one sample, written as four 16-byte chunks (levels 4c..4c+3 -> features 8c..8c+7) at
+// dst + c * chunk_stride.  The chunk loop stays rolled (instruction-cache footprint), the four levels inside a chunk
+// are unrolled so 32 gathers are in flight per thread.
+template <int HASH>
+__device__ __forceinline__ void encode_chunks_t(const DeviceModel& M, V3 p01, char* dst, int chunk_stride) {
+#pragma unroll 1
+    for (int c = 0; c < N_LEVELS / 4; ++c) {
+        __half2 e[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) e[j] = encode_level<HASH>(M, 4 * c + j, p01);
+        uint4 v;
+        v.x = *reinterpret_cast<const uint32_t*>(&e[0]); v.y = *reinterpret_cast<const uint32_t*>(&e[1]);
+        v.z = *reinterpret_cast<const uint32_t*>(&e[2]); v.w = *reinterpret_cast<const uint32_t*>(&e[3]);
+        *reinterpret_cast<uint4*>(dst + (size_t)c * chunk_stride) = v;
+    }
+}
+__device__ __forceinline__ void encode_chunks(const DeviceModel& M, V3 p01, char* dst, int chunk_stride) {
+    if (M.hash_type == 1) encode_chunks_t<1>(M, p01, dst, chunk_stride);
+    else if (M.hash_type == 0) encode_chunks_t<0>(M, p01, dst, chunk_stride);
+    else encode_chunks_t<2>(M, p01, dst, chunk_stride);
+}
+
+// ---- SH degree 4 (T/.../encodings/spherical_harmonics.h:65-98) -------------------------------------------------
+__device__ __forceinline__ void sh4(V3 d01, __half2 out[8]) {
+    const float x = d01.x * 2.f - 1.f, y = d01.y * 2.f - 1.f, z = d01.z * 2.f - 1.f;
+    const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+    out[0] = __floats2half2_rn(0.28209479177387814f, -0.48860251190291987f * y);
+    out[1] = __floats2half2_rn(0.48860251190291987f * z, -0.48860251190291987f * x);
+    out[2] = __floats2half2_rn(1.0925484305920792f * xy, -1.0925484305920792f * yz);
+    out[3] = __floats2half2_rn(0.94617469575755997f * z2 - 0.31539156525251999f, -1.0925484305920792f * xz);
+    out[4] = __floats2half2_rn(0.54627421529603959f * x2 - 0.54627421529603959f * y2, 0.59004358992664352f * y * (-3.0f * x2 + y2));
+    out[5] = __floats2half2_rn(2.8906114426405538f * xy * z, 0.45704579946446572f * y * (1.0f - 5.0f * z2));
+    out[6] = __floats2half2_rn(0.3731763325901154f * z * (5.0f * z2 - 3.0f), 0.45704579946446572f * x * (1.0f - 5.0f * z2));
+    out[7] = __floats2half2_rn(1.4453057213202769f * z * (x2 - y2), 0.59004358992664352f * x * (-x2 + 3.0f * y2));
+}
+
+// ---- activations and colour transfer ---------------------------------------------------------------------------
+__device__ __forceinline__ float act_density(float v, int a) {
+    switch (a) { case 0: return v; case 1: return v > 0.f ? v : 0.f; case 2: return 1.0f / (1.0f + __expf(-v)); default: return __expf(v); }
+}
+__device__ __forceinline__ float act_rgb(float v, int a) {
+    switch (a) { case 0: return v; case 1: return v > 0.f ? v : 0.f; case 2: return 1.0f / (1.0f + __expf(-v)); default: return __expf(clampf(v, -10.f, 10.f)); }
+}
+__device__ __forceinline__ float linear_to_srgb(float l) { return l < 0.0031308f ? 12.92f * l : 1.055f * powf(l, 0.41666f) - 0.055f; }
+__device__ __forceinline__ float srgb_to_linear(float s) { return s <= 0.04045f ? s / 12.92f : powf((s + 0.055f) / 1.055f, 2.4f); }
+
+// ---- mesh stage: Moeller-Trumbore with back-face culling + the reference's PBR shading ------------------------
+// (S/optix/optix_scene.cu:71-85, 182-325; OptiX's own triangle test is not available: see DESIGN.md)
+__device__ __forceinline__ V3 mesh_ray_dir(const FrameParams& P, int x, int y, int W2, int H2) {
+    const float dx = 2.0f * (((float)x + 0.5f) / (float)W2) - 1.0f;
+    const float dy = 2.0f * (((float)y + 0.5f) / (float)H2) - 1.0f;
+    const float* c = P.cam;
+    return gnormalize(v3((dx * c[0] + dy * c[3]) + c[6], (dx * c[1] + dy * c[4]) + c[7], (dx * c[2] + dy * c[5]) + c[8]));
+}
+__device__ __forceinline__ V3 ld3(const float* p, uint32_t i) { return v3(__ldg(p + 3 * i), __ldg(p + 3 * i + 1), __ldg(p + 3 * i + 2)); }
+
+__device__ __forceinline__ bool ray_tri(V3 o, V3 d, V3 v0, V3 v1, V3 v2, float& t_out, float& u_out, float& v_out) {
+    const V3 e1 = vsub(v1, v0), e2 = vsub(v2, v0);
+    const V3 pv = vcross(d, e2);
+    const float det = gdot(e1, pv);
+    if (!(det > 0.0f)) return false;
+    const V3 tv = vsub(o, v0);
+    const float u = gdot(tv, pv);
+    if (u < 0.0f || u > det) return false;
+    const V3 qv = vcross(tv, e1);
+    const float v = gdot(d, qv);
+    if (v < 0.0f || u + v > det) return false;
+    const float t = gdot(e2, qv);
+    if (!(t > 0.0f)) return false;
+    const float inv = 1.0f / det;
+    t_out = t * inv; u_out = u * inv; v_out = v * inv;
+    return true;
+}
+
+__device__ __forceinline__ void tex_sample(const MeshDevice& M, float u, float v, float out[4]) {
+    const float fx = u * (float)M.tex_w - 0.5f, fy = v * (float)M.tex_h - 0.5f;
+    const float flx = floorf(fx), fly = floorf(fy);
+    const float ax = fx - flx, ay = fy - fly;
+    const int x0 = (int)flx, y0 = (int)fly;
+    const int xa = ((x0 % M.tex_w) + M.tex_w) % M.tex_w, xb = (((x0 + 1) % M.tex_w) + M.tex_w) % M.tex_w;
+    const int ya = ((y0 % M.tex_h) + M.tex_h) % M.tex_h, yb = (((y0 + 1) % M.tex_h) + M.tex_h) % M.tex_h;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float t00 = __ldg(M.tex_lin + ((size_t)ya * M.tex_w + xa) * 4 + k), t10 = __ldg(M.tex_lin + ((size_t)ya * M.tex_w + xb) * 4 + k);
+        const float t01 = __ldg(M.tex_lin + ((size_t)yb * M.tex_w + xa) * 4 + k), t11 = __ldg(M.tex_lin + ((size_t)yb * M.tex_w + xb) * 4 + k);
+        const float top = t00 * (1.0f - ax) + t10 * ax, bot = t01 * (1.0f - ax) + t11 * ax;
+        out[k] = top * (1.0f - ay) + bot * ay;
+    }
+}
+
+__device__ __forceinline__ float to_srgb_mesh(float c) {   // S/optix/optix_util.cuh:23-29
+    const float powed = powf(c, 1.0f / 2.4f);
+    return c < 0.0031308f ? 12.92f * c : 1.055f * powed - 0.055f;
+}
+
+__device__ __forceinline__ void shade_hit(const MeshDevice& M, const FrameParams& P, uint32_t tri, float bu, float bv, float hitT, V3 dir, float rgba[4]) {
+    const uint32_t i0 = __ldg(M.idx + tri * 3), i1 = __ldg(M.idx + tri * 3 + 1), i2 = __ldg(M.idx + tri * 3 + 2);
+    const float bw = 1.0f - bu - bv;
+    const V3 n = vadd(vadd(vmul(ld3(M.wnrm, i1), bu), vmul(ld3(M.wnrm, i2), bv)), vmul(ld3(M.wnrm, i0), bw));
+    const float uvx = (bu * __ldg(M.uv + i1 * 2) + bv * __ldg(M.uv + i2 * 2)) + bw * __ldg(M.uv + i0 * 2);
+    const float uvy = (bu * __ldg(M.uv + i1 * 2 + 1) + bv * __ldg(M.uv + i2 * 2 + 1)) + bw * __ldg(M.uv + i0 * 2 + 1);
+    float base[4] = {M.base_color[0], M.base_color[1], M.base_color[2], M.base_color[3]};
+    if (M.tex_lin) { float tx[4]; tex_sample(M, uvx, uvy, tx); for (int k = 0; k < 4; ++k) base[k] *= tx[k]; }
+    const float metallic = M.metallic, roughness = M.roughness, occlusion = 1.0f;
+    const V3 eye = v3(P.cam[9], P.cam[10], P.cam[11]);
+    const V3 light = v3(P.light[0], P.light[1], P.light[2]);
+    const V3 hitPos = vadd(eye, vmul(dir, hitT));
+    const V3 N = gnormalize(n);
+    const V3 V = gnormalize(vsub(eye, hitPos));
+    const V3 L = gnormalize(vsub(light, hitPos));
+    const V3 H = gnormalize(vadd(V, L));
+    const float ndl = gdot(L, N);
+    const float dl = fmaxf(0.f, ndl);
+    float fr[3] = {0.f, 0.f, 0.f};
+    const float dotNV = gdot(N, V), dotNL = ndl;
+    if (dotNV > 0 && dotNL > 0) {
+        const float dotNH = clampf(gdot(N, H), 0.0f, 1.0f);
+        const float dotLH = clampf(gdot(L, H), 0.0f, 1.0f);
+        const float alpha = roughness * roughness;
+        const float a2 = alpha * alpha;
+        const float f = (dotNH * a2 - dotNH) * dotNH + 1.0f;
+        const float D = a2 / (f * f);
+        const float lambdaV = fmaxf(0.f, dotNL) / sqrtf(a2 + (1.0f - a2) * dotNV * dotNV);
+        const float lambdaL = fmaxf(0.f, dotNV) / sqrtf(a2 + (1.0f - a2) * dotNL * dotNL);
+        const float G = 0.5f / (lambdaV + lambdaL + 0.0001f);
+        const float p5 = powf(1.0f - dotLH, 5.0f);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float f0 = (0.5f * alpha) * (1.0f - metallic) + base[k] * metallic;
+            const float F = f0 + (1.0f - f0) * p5;
+            fr[k] = fabsf((D * G * F) / 3.14159265358979323846f);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float fd = (1.0f - metallic) * base[k] * dl;
+        const float ambient = base[k] * .2f * occlusion;
+        float c = ambient + (fd + fr[k]) + M.emissive[k];
+        c = clampf(c, 0.f, 1.f);
+        rgba[k] = to_srgb_mesh(c);
+    }
+    rgba[3] = 1.f;
+}
+
+}  // namespace nmr

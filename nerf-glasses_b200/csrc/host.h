@@ -1,0 +1,87 @@
+// host.h - host-side model/mesh/camera structures and loaders of libnmr.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace nmr {
+
+constexpr int kMaxLevels = 16;
+constexpr uint32_t kGridSize = 128;
+constexpr uint32_t kCascades = 8;
+constexpr uint32_t kGridCells = kGridSize * kGridSize * kGridSize;
+constexpr uint32_t kBitfieldBytes = kCascades * kGridCells / 8;   // 2 MiB
+
+// What Testbed::load_snapshot + reset_network + Trainer::deserialize extract from a snapshot
+// (S/ngp/testbed.cu:939-1002, 1098-1115, 1158-1236; T/include/tiny-cuda-nn/trainer.h:285-310).
+struct HostModel {
+    // hash grid (T/include/tiny-cuda-nn/encodings/grid.h:959-1025)
+    int n_levels = 16, n_features_per_level = 2, log2_hashmap_size = 19, base_resolution = 16;
+    int hash_type = 1;                       // 0 Prime, 1 CoherentPrime, 2 ReversedPrime
+    float per_level_scale = 0.f;
+    uint32_t offsets[kMaxLevels + 1] = {};   // in entries (x n_features_per_level halves)
+    float scales[kMaxLevels] = {};
+    uint32_t resolutions[kMaxLevels] = {};
+    uint32_t stride_y[kMaxLevels] = {}, stride_z[kMaxLevels] = {};
+    int dense[kMaxLevels] = {};
+    // MLPs (FullyFusedMLP, 64 neurons)
+    int density_hidden = 1, rgb_hidden = 2;
+    // parameters, params_binary order: density net | rgb net | hash grid, as fp16 bit patterns
+    std::vector<uint16_t> params;
+    size_t mlp_params = 0;                   // number of MLP halves before the grid
+    // occupancy
+    int aabb_scale = 1, max_cascade = 0;
+    std::vector<uint16_t> density_grid;      // fp16, 128^3 * (max_cascade+1), Morton order
+    float cone_angle_constant = 0.f;
+    // boxes
+    float aabb_min[3] = {0, 0, 0}, aabb_max[3] = {1, 1, 1};               // m_aabb
+    float render_aabb_min[3] = {0, 0, 0}, render_aabb_max[3] = {1, 1, 1}; // m_render_aabb
+    float render_aabb_to_local[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};          // row-major
+    int rgb_activation = 2;                  // Logistic unless the dataset is HDR (S/ngp/testbed.cu:1028)
+    int density_activation = 3;              // Exponential (S/ngp/testbed.cuh:469)
+};
+
+// Throws std::runtime_error with a description on malformed / unsupported snapshots.
+HostModel load_snapshot(const std::string& path);
+// 2 MiB occupancy bitfield from the fp16 density grid (S/ngp/testbed.cu:119-166, 1120-1135) - host version used when the
+// device path is not wanted (tests of the loader); the product builds the bitfield on the device (occupancy kernels).
+void build_level_table(HostModel& m);
+
+struct HostMesh {
+    std::vector<float> positions;   // object space, xyz
+    std::vector<float> normals;
+    std::vector<float> texcoords;
+    std::vector<uint32_t> indices;
+    float base_color[4] = {1, 1, 1, 1};
+    float emissive[3] = {0, 0, 0};
+    float metallic = 1.f, roughness = 1.f;
+    int tex_w = 0, tex_h = 0;
+    std::vector<uint8_t> tex_rgba8;  // base colour texture (sRGB), row-major, may be empty
+    // node 0 TRS as loaded from the file (overwritten by load_mesh's t/s/r, S/nerf_mesh_renderer.cu:952-954)
+    float t[3] = {0, 0, 0}, s[3] = {1, 1, 1}, r_wxyz[4] = {1, 0, 0, 0};
+    std::string warning;            // e.g. "texture could not be decoded, using constant colour"
+};
+
+// glTF 2.0 (.gltf + external/embedded buffers, or .glb): all primitives of all nodes of the default scene are
+// concatenated like GltfScene::getMeshPrimitives (S/gltf_scene.h:195-224); material of the first primitive.
+HostMesh load_gltf(const std::string& path);
+// 8-bit PNG (grey / grey+alpha / RGB / RGBA / palette, non-interlaced) -> RGBA8.  Throws on anything else.
+void decode_png(const uint8_t* data, size_t size, int& w, int& h, std::vector<uint8_t>& rgba);
+
+// world-space vertices / normals for T*R*S (S/gltf_scene.h:122-127): out arrays sized like the inputs
+void transform_mesh(const HostMesh& m, const float t[3], const float s[3], const float r_wxyz[4],
+                    std::vector<float>& world_pos, std::vector<float>& world_nrm);
+
+// The NerfMeshRenderer camera (S/nerf_mesh_renderer.cuh:88-95; S/orbit_camera.h; flythrough_camera.h)
+struct OrbitCamera {
+    float view[16];
+    float eye[3] = {0.f, 0.f, 2.f};
+    float look[3] = {0.f, -0.000001f, -0.999999f};
+    float pivot[3] = {0.f, 0.f, 0.f};
+    float up[3] = {0.f, 1.f, 0.f};
+    OrbitCamera();
+    void orbit(float delta_azimuth, float delta_polar, float delta_scroll);
+    void matrix(int screen_w, int screen_h, float out12[12]) const;   // updateModelViewProj
+};
+
+}  // namespace nmr

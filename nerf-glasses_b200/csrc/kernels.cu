@@ -1,0 +1,758 @@
+// kernels.cu - the CUDA kernels of libnmr's render path (sm_100a only).
+//
+//   occupancy_*            snapshot density grid -> 2 MiB occupancy bitfield (load time)
+//   mesh_raster_kernel     glasses mesh -> 2x supersampled visibility buffer (64-bit atomicMin of hitT|triangle)
+//   init_rays_kernel       per pixel: ray set-up, mesh hand-off (shade + 2x2 resolve), first-hit DDA; dead pixels are
+//                          finished in place, live rays are appended to a compact queue
+//   march_kernel           persistent fused kernel: DDA sample generation, hash-grid encoding, both MLPs (tcgen05 tensor
+//                          cores, accumulators in tensor memory), SH, front-to-back compositing with mesh clipping,
+//                          shade/accumulate/tonemap - one thread per ray slot, 128 rays per CTA, rays refilled from the queue
+//
+// Reference behaviour restated per kernel: see the citations at each function and SURVEY.md section 8a.
+#include "kernels.cuh"
+
+#include <cstdio>
+
+namespace nmr {
+
+int rows_owned_by(int height, int rank, int world, int band) {
+    if (world <= 1) return height;
+    int n = 0;
+    for (int y0 = rank * band; y0 < height; y0 += world * band) n += (height - y0 < band) ? (height - y0) : band;
+    return n;
+}
+
+// local (owned) row -> image row
+__device__ __forceinline__ int shard_row(const FrameParams& P, int local_row) {
+    if (P.shard_world <= 1) return local_row;
+    const int b = local_row / P.shard_band;
+    return (b * P.shard_world + P.shard_rank) * P.shard_band + local_row % P.shard_band;
+}
+
+// =================================================================================================================
+// occupancy grid  (grid_to_bitfield / bitfield_max_pool, S/ngp/testbed.cu:119-166, 1120-1135)
+// =================================================================================================================
+__global__ void occupancy_mean_kernel(const __half* __restrict__ grid, double* __restrict__ sum) {
+    // mean over cascade 0 only, each term divided by n like the reference's reduce_sum functor
+    double local = 0.0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < GRID_CELLS; i += gridDim.x * blockDim.x)
+        local += (double)(fmaxf(__half2float(grid[i]), 0.f) / (float)GRID_CELLS);
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(sum, local);
+}
+
+__global__ void occupancy_bits_kernel(const __half* __restrict__ grid, uint32_t n_nonzero_bytes, const double* __restrict__ sum, uint8_t* __restrict__ bitfield) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= GRID_CELLS / 8 * NERF_CASCADES) return;
+    uint8_t bits = 0;
+    if (i < n_nonzero_bytes) {
+        const float thresh = fminf(0.01f, (float)*sum);
+#pragma unroll
+        for (uint32_t j = 0; j < 8; ++j) bits |= __half2float(grid[(size_t)i * 8 + j]) > thresh ? (uint8_t)(1u << j) : 0;
+    }
+    bitfield[i] = bits;
+}
+
+__global__ void occupancy_pool_kernel(const uint8_t* __restrict__ prev, uint8_t* __restrict__ next) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= GRID_CELLS / 64) return;
+    uint8_t bits = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < 8; ++j) bits |= prev[i * 8 + j] > 0 ? (uint8_t)(1u << j) : 0;
+    const uint32_t x = morton3D_invert(i >> 0) + NERF_GRIDSIZE / 8;
+    const uint32_t y = morton3D_invert(i >> 1) + NERF_GRIDSIZE / 8;
+    const uint32_t z = morton3D_invert(i >> 2) + NERF_GRIDSIZE / 8;
+    next[morton3D(x, y, z)] |= bits;   // distinct i map to distinct bytes: no race
+}
+
+void launch_occupancy_build(const uint16_t* d_grid, int n_cascades_present, uint8_t* d_bitfield, float* d_scratch, cudaStream_t s) {
+    double* sum = reinterpret_cast<double*>(d_scratch);
+    cudaMemsetAsync(sum, 0, sizeof(double), s);
+    const __half* g = reinterpret_cast<const __half*>(d_grid);
+    occupancy_mean_kernel<<<296, 256, 0, s>>>(g, sum);
+    const uint32_t total = GRID_CELLS / 8 * NERF_CASCADES;
+    occupancy_bits_kernel<<<(total + 255) / 256, 256, 0, s>>>(g, GRID_CELLS / 8 * (uint32_t)n_cascades_present, sum, d_bitfield);
+    for (uint32_t level = 1; level < NERF_CASCADES; ++level)
+        occupancy_pool_kernel<<<(GRID_CELLS / 64 + 255) / 256, 256, 0, s>>>(d_bitfield + (size_t)GRID_CELLS / 8 * (level - 1), d_bitfield + (size_t)GRID_CELLS / 8 * level);
+}
+
+// =================================================================================================================
+// mesh stage
+// =================================================================================================================
+constexpr unsigned long long kZMiss = ~0ull;
+
+// One warp per triangle: conservative screen bounding box, then the exact ray/triangle test per covered sub-pixel.
+// Replaces optixLaunch(2W x 2H) + RT-core traversal (S/nerf_mesh_renderer.cu:1454-1487, S/optix/optix_scene.cu:120-174).
+__global__ void __launch_bounds__(256) mesh_raster_kernel(MeshDevice mesh, FrameParams P, int W2, int H2, unsigned long long* __restrict__ zbuf) {
+    const uint32_t tri = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (tri >= mesh.n_tris) return;
+    const V3 eye = v3(P.cam[9], P.cam[10], P.cam[11]);
+    const V3 v0 = ld3(mesh.wpos, __ldg(mesh.idx + tri * 3)), v1 = ld3(mesh.wpos, __ldg(mesh.idx + tri * 3 + 1)), v2 = ld3(mesh.wpos, __ldg(mesh.idx + tri * 3 + 2));
+    int x0 = 0, y0 = 0, x1 = W2 - 1, y1 = H2 - 1;
+    {
+        const V3 vs[3] = {v0, v1, v2};
+        float minx = 1e30f, miny = 1e30f, maxx = -1e30f, maxy = -1e30f;
+        bool behind = false;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const V3 p = vsub(vs[k], eye);
+            const float a = P.cam_inv[0] * p.x + P.cam_inv[1] * p.y + P.cam_inv[2] * p.z;
+            const float b = P.cam_inv[3] * p.x + P.cam_inv[4] * p.y + P.cam_inv[5] * p.z;
+            const float c = P.cam_inv[6] * p.x + P.cam_inv[7] * p.y + P.cam_inv[8] * p.z;
+            if (!(c > 1e-4f)) { behind = true; break; }
+            const float px = (a / c + 1.0f) * 0.5f * (float)W2 - 0.5f, py = (b / c + 1.0f) * 0.5f * (float)H2 - 0.5f;
+            minx = fminf(minx, px); maxx = fmaxf(maxx, px); miny = fminf(miny, py); maxy = fmaxf(maxy, py);
+        }
+        if (!behind) {
+            if (maxx < -2.f || maxy < -2.f || minx > (float)W2 + 1.f || miny > (float)H2 + 1.f) return;
+            x0 = max(0, (int)floorf(minx) - 1); y0 = max(0, (int)floorf(miny) - 1);
+            x1 = min(W2 - 1, (int)ceilf(maxx) + 1); y1 = min(H2 - 1, (int)ceilf(maxy) + 1);
+            if (x1 < x0 || y1 < y0) return;
+        }
+    }
+    // shard: only sub-pixel rows belonging to owned image rows are needed, but testing ownership per row is cheap enough
+    const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
+    const int ms = P.mesh_scale;
+    for (int i = (int)lane; i < bw * bh; i += 32) {
+        const int x = x0 + i % bw, y = y0 + i / bw;
+        if (P.shard_world > 1 && ((y / ms) / P.shard_band) % P.shard_world != P.shard_rank) continue;
+        const V3 dir = mesh_ray_dir(P, x, y, W2, H2);
+        float t, u, v;
+        if (ray_tri(eye, dir, v0, v1, v2, t, u, v) && t < 1e16f) {
+            const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | tri;
+            atomicMin(zbuf + (size_t)y * W2 + x, key);
+        }
+    }
+}
+
+void launch_mesh_raster(const MeshDevice& mesh, const FrameParams& P, int rows_owned, unsigned long long* d_zbuf, cudaStream_t s) {
+    (void)rows_owned;
+    const int W2 = P.width * P.mesh_scale, H2 = P.height * P.mesh_scale;
+    cudaMemsetAsync(d_zbuf, 0xFF, (size_t)W2 * H2 * sizeof(unsigned long long), s);
+    if (mesh.n_tris == 0) return;
+    const uint32_t threads = mesh.n_tris * 32u;
+    mesh_raster_kernel<<<(threads + 255) / 256, 256, 0, s>>>(mesh, P, W2, H2, d_zbuf);
+}
+
+// closest hit of one sub-pixel -> shaded RGBA (alpha 1) and hitT; false on miss
+__device__ __forceinline__ bool mesh_tap(const MeshDevice& mesh, const FrameParams& P, const unsigned long long* __restrict__ zbuf, int x, int y, int W2, int H2,
+                                         float rgba[4], float& hit_t, int32_t* tri_out = nullptr) {
+    const unsigned long long key = __ldg(zbuf + (size_t)y * W2 + x);
+    if (key == kZMiss) { if (tri_out) *tri_out = -1; return false; }
+    const uint32_t tri = (uint32_t)(key & 0xFFFFFFFFull);
+    const V3 eye = v3(P.cam[9], P.cam[10], P.cam[11]);
+    const V3 dir = mesh_ray_dir(P, x, y, W2, H2);
+    const V3 v0 = ld3(mesh.wpos, __ldg(mesh.idx + tri * 3)), v1 = ld3(mesh.wpos, __ldg(mesh.idx + tri * 3 + 1)), v2 = ld3(mesh.wpos, __ldg(mesh.idx + tri * 3 + 2));
+    float t = 0.f, u = 0.f, v = 0.f;
+    ray_tri(eye, dir, v0, v1, v2, t, u, v);      // same arithmetic as the raster pass: reproduces the stored hit
+    shade_hit(mesh, P, tri, u, v, t, dir, rgba);
+    hit_t = t;
+    if (tri_out) *tri_out = (int32_t)tri;
+    return true;
+}
+
+// copyRaytracingBuffersToNerfRays (S/nerf_mesh_renderer.cu:64-100) fused with the shading of the taps
+__device__ __forceinline__ void mesh_resolve(const MeshDevice& mesh, const FrameParams& P, const unsigned long long* __restrict__ zbuf, int px, int py,
+                                             float surf[4], float& t_surface) {
+    const int ms = P.mesh_scale, W2 = P.width * ms, H2 = P.height * ms;
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f, depth = 0.f;
+    for (int i = 0; i < ms; ++i) {
+        for (int j = 0; j < ms; ++j) {
+            float rgba[4]; float ht;
+            if (mesh_tap(mesh, P, zbuf, px * ms + i, py * ms + j, W2, H2, rgba, ht)) {
+                c0 += rgba[0]; c1 += rgba[1]; c2 += rgba[2]; c3 += rgba[3];
+                depth = fmaxf(depth, ht);
+            } else {
+                c0 += 0.f; c1 += 0.f; c2 += 0.f; c3 += 0.f;
+            }
+        }
+    }
+    const float q = (float)(ms * ms);
+    surf[0] = c0 / q; surf[1] = c1 / q; surf[2] = c2 / q; surf[3] = c3 / q;
+    t_surface = depth;
+}
+
+// =================================================================================================================
+// pixel finish: shade_kernel_nerf + accumulate_kernel + tonemap_kernel
+// (S/ngp/testbed.cu:907-931; S/ngp/render_buffer.cu:232-267, 327-346, 537-566) fused into the ray's last step
+// =================================================================================================================
+__device__ __forceinline__ void finish_pixel(const FrameParams& P, const FrameOut& out, uint32_t idx, float r, float g, float b, float a, float depth, uint32_t n_samples) {
+    float4 fb = make_float4(0.f, 0.f, 0.f, 0.f);
+    float d = 1e10f;
+    if (a > 0.001f) {   // compact_kernel_nerf's hit criterion
+        fb = make_float4(srgb_to_linear(r), srgb_to_linear(g), srgb_to_linear(b), a);
+        if (a > 0.2f) d = depth;
+    }
+    if (out.frame) out.frame[idx] = fb;
+    if (out.depth) out.depth[idx] = d;
+    if (out.n_samples) out.n_samples[idx] = n_samples;
+    float4 acc = fb;
+    if (P.spp_index != 0) {
+        const float sc = (float)P.spp_index;
+        const float4 prev = out.accum[idx];
+        acc = make_float4((prev.x * sc + fb.x) / (sc + 1), (prev.y * sc + fb.y) / (sc + 1), (prev.z * sc + fb.z) / (sc + 1), (prev.w * sc + fb.w) / (sc + 1));
+    }
+    out.accum[idx] = acc;
+    const float w = (1 - acc.w) * P.background[3];
+    float cr = acc.x + srgb_to_linear(P.background[0]) * w;
+    float cg = acc.y + srgb_to_linear(P.background[1]) * w;
+    float cb = acc.z + srgb_to_linear(P.background[2]) * w;
+    float ca = acc.w + w;
+    if (P.to_srgb) {
+        cr = fminf(fmaxf(linear_to_srgb(cr), 0.f), 1.f); cg = fminf(fmaxf(linear_to_srgb(cg), 0.f), 1.f);
+        cb = fminf(fmaxf(linear_to_srgb(cb), 0.f), 1.f); ca = fminf(fmaxf(ca, 0.f), 1.f);
+    }
+    out.image[idx] = make_float4(cr, cg, cb, ca);
+}
+
+// =================================================================================================================
+// init_rays_kernel: init_rays_with_payload_kernel_nerf + mesh hand-off + advance_pos_nerf
+// (S/ngp/testbed.cu:355-537; S/nerf_mesh_renderer.cu:64-100)
+// =================================================================================================================
+__global__ void __launch_bounds__(128) init_rays_kernel(FrameParams P, DeviceModel M, MeshDevice mesh, const unsigned long long* __restrict__ zbuf, int rows_owned,
+                                                        float4* __restrict__ queue, uint32_t* __restrict__ counters, FrameOut out) {
+    // 16 x 8 pixel block, each warp an 8 x 4 tile so queue neighbours are screen neighbours
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    const int ly = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    if (x >= P.width || ly >= rows_owned) return;
+    const int y = shard_row(P, ly);
+    const uint32_t idx = (uint32_t)x + (uint32_t)P.width * (uint32_t)y;
+
+    RayInit r = init_ray(P, (uint32_t)x, (uint32_t)y);
+    float surf[4] = {0.f, 0.f, 0.f, 0.f};
+    float t_surface = 0.f;
+    if (P.mesh_scale > 0) mesh_resolve(mesh, P, zbuf, x, y, surf, t_surface);
+    float t = r.t, t_start;
+    const bool alive = advance_pos(P, M.bitfield, r.origin, r.dir, idx, t_surface, r.alive, t, t_start);
+    if (!alive) {
+        finish_pixel(P, out, idx, 0.f, 0.f, 0.f, 0.f, 0.f, 0u);
+        return;
+    }
+    const uint32_t slot = atomicAdd(&counters[0], 1u);
+    queue[(size_t)slot * kRayRecordFloat4s + 0] = make_float4(r.dir.x, r.dir.y, r.dir.z, t);
+    queue[(size_t)slot * kRayRecordFloat4s + 1] = make_float4(t_start, t_surface, __uint_as_float(idx), 0.f);
+    queue[(size_t)slot * kRayRecordFloat4s + 2] = make_float4(surf[0], surf[1], surf[2], surf[3]);
+}
+
+void launch_init_rays(const FrameParams& P, const DeviceModel& M, const MeshDevice& mesh, const unsigned long long* d_zbuf, int rows_owned,
+                      float4* d_queue, uint32_t* d_counters, const FrameOut& out, cudaStream_t s) {
+    cudaMemsetAsync(d_counters, 0, sizeof(uint32_t) * kNumCounters, s);
+    dim3 grid((P.width + 15) / 16, (rows_owned + 7) / 8);
+    init_rays_kernel<<<grid, 128, 0, s>>>(P, M, mesh, d_zbuf, rows_owned, d_queue, d_counters, out);
+}
+
+// =================================================================================================================
+// tcgen05 / tensor-memory plumbing (PTX ISA: tcgen05.*, mbarrier.*; descriptor bit layouts as in
+// cute/arch/mma_sm100_desc.hpp: SmemDescriptor, InstrDescriptor)
+// =================================================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// K-major, no swizzle: 8-row x 16-byte core matrices; lbo = byte distance between K-adjacent core matrices,
+// sbo = byte distance between M/N-adjacent core matrices (cute: ((8,n),2):((1,SBO),LBO) in uint128 units)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= 1ull << 46;                               // descriptor version for sm_100
+    return d;                                      // base_offset 0, layout_type 0 (SWIZZLE_NONE)
+}
+// kind::f16, A = B = F16, D = F32, both operands K-major, dense
+__device__ __forceinline__ constexpr uint32_t umma_idesc(uint32_t M, uint32_t N) {
+    return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t v[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t v[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// =================================================================================================================
+// network evaluation on a tile of 128 samples (one per thread)
+// NerfNetwork::inference_mixed_precision_impl (S/ngp/nerf_network.cuh:101-135):
+//   enc(32) -> 64 ReLU -> 16 ; [16 | SH16] -> 64 ReLU -> 64 ReLU -> 16 (3 used); density = channel 0 of the first net.
+// Layer semantics of T/src/fully_fused_mlp.cu:499-557: y = act(W x), fp16 activations between layers.
+// =================================================================================================================
+constexpr int kTile = 128;
+// weight matrices in params order: [out][in] row-major halves
+constexpr int kWD0 = 0, kWD1 = kWD0 + 64 * 32, kWR0 = kWD1 + 16 * 64, kWR1 = kWR0 + 64 * 32, kWR2 = kWR1 + 64 * 64, kWTotal = kWR2 + 16 * 64;   // 10240 halves
+
+struct __align__(128) MarchSmem {
+    __half w[kWTotal];            // 20480 B - tensor path: canonical K-major core-matrix layout; scalar path: plain row-major
+    __half act[kTile * 64];       // 16384 B - tensor path: A operand, chunk-major (k/8)*2048 + row*16; scalar path: row-major 64 halves per thread
+    __half act2[kTile * 64];      // 16384 B - scalar path only (second activation buffer)
+    uint64_t mbar;
+    uint32_t tmem_base;
+};
+struct __align__(128) MarchSmemTC {
+    __half w[kWTotal];
+    __half act[kTile * 64];
+    uint64_t mbar;
+    uint32_t tmem_base;
+};
+
+// ---- CUDA-core variant (bring-up / bisecting aid, selected with NMR_MLP=scalar): fp32 accumulation in k order ----
+__device__ __forceinline__ void scalar_layer(const __half* __restrict__ W, int n_out, int n_in, const __half* __restrict__ x_row, __half* __restrict__ y_row, bool relu) {
+    for (int j = 0; j < n_out; ++j) {
+        float acc = 0.f;
+        const __half* wr = W + j * n_in;
+        for (int k = 0; k < n_in; ++k) acc = acc + __half2float(wr[k]) * __half2float(x_row[k]);
+        if (relu) acc = acc > 0.f ? acc : 0.f;
+        y_row[j] = __float2half_rn(acc);
+    }
+}
+
+// the caller has written the 32 encoded features to the first 64 bytes of its row of S.act
+__device__ __forceinline__ void network_scalar(MarchSmem& S, V3 dir01, float raw[4]) {
+    __half* a = S.act + threadIdx.x * 64;
+    __half* b = S.act2 + threadIdx.x * 64;
+    scalar_layer(S.w + kWD0, 64, 32, a, b, true);
+    scalar_layer(S.w + kWD1, 16, 64, b, a, false);
+    const float density = __half2float(a[0]);
+    __half2 sh[8];
+    sh4(dir01, sh);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) reinterpret_cast<__half2*>(a)[8 + i] = sh[i];
+    scalar_layer(S.w + kWR0, 64, 32, a, b, true);
+    scalar_layer(S.w + kWR1, 64, 64, b, a, true);
+    scalar_layer(S.w + kWR2, 16, 64, a, b, false);
+    raw[0] = __half2float(b[0]); raw[1] = __half2float(b[1]); raw[2] = __half2float(b[2]); raw[3] = density;
+}
+
+// ---- tensor-core variant ----------------------------------------------------------------------------------------
+// smem operand layouts (K-major, SWIZZLE_NONE canonical layout, 16-byte "chunks" of 8 halves):
+//   A (activations, M = 128 rows):  byte(row, k) = (k/8)*2048 + row*16 + (k%8)*2      LBO = 2048, SBO = 128
+//   B (weights, N rows = outputs):  byte(n,   k) = (k/8)*(N*16) + n*16 + (k%8)*2      LBO = N*16, SBO = 128
+// Thread r owns row r of A and lane r of the accumulator in tensor memory, so every hand-off is thread-private:
+// tcgen05.ld 32x32b (lane = thread) -> ReLU/convert in registers -> st.shared of its own row (conflict-free, 512 B per warp store).
+__device__ __forceinline__ void stage_weights_tc(__half* sw, const __half* __restrict__ gw) {
+    // (matrix offset, N, K) for the five layers
+    const int off[5] = {kWD0, kWD1, kWR0, kWR1, kWR2};
+    const int Ns[5] = {64, 16, 64, 64, 16};
+    const int Ks[5] = {32, 64, 32, 64, 64};
+#pragma unroll
+    for (int m = 0; m < 5; ++m) {
+        const int N = Ns[m], K = Ks[m], chunks = K / 8;
+        for (int i = threadIdx.x; i < N * chunks; i += blockDim.x) {
+            const int n = i / chunks, c = i % chunks;
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(gw + off[m] + n * K + c * 8));
+            *reinterpret_cast<uint4*>(reinterpret_cast<char*>(sw + off[m]) + c * (N * 16) + n * 16) = v;
+        }
+    }
+}
+
+struct TcCtx {
+    uint32_t tmem;        // base address of this CTA's 64 accumulator columns
+    uint32_t a_addr;      // smem address of the A operand
+    uint32_t w_addr;      // smem address of the weights
+    uint64_t* mbar;
+    uint32_t phase;
+    bool swap;
+};
+
+// D[128 x N] = A[128 x K] * W^T  issued by one thread; K in {32, 64}
+__device__ __forceinline__ void tc_issue_layer(const TcCtx& c, int w_off_halves, uint32_t N, uint32_t K) {
+    const uint32_t idesc = umma_idesc(128, N);
+    const uint32_t a_lbo = 2048, a_sbo = 128, b_lbo = N * 16, b_sbo = 128;
+    const uint32_t b_addr = c.w_addr + (uint32_t)w_off_halves * 2u;
+    for (uint32_t k = 0; k < K / 16; ++k) {
+        const uint64_t ad = c.swap ? umma_desc(c.a_addr + k * 2 * a_lbo, a_sbo, a_lbo) : umma_desc(c.a_addr + k * 2 * a_lbo, a_lbo, a_sbo);
+        const uint64_t bd = c.swap ? umma_desc(b_addr + k * 2 * b_lbo, b_sbo, b_lbo) : umma_desc(b_addr + k * 2 * b_lbo, b_lbo, b_sbo);
+        umma_f16(c.tmem, ad, bd, idesc, k > 0 ? 1u : 0u);
+    }
+    umma_commit(c.mbar);
+}
+
+__device__ __forceinline__ uint32_t pack_relu_h2(uint32_t a, uint32_t b, bool relu) {
+    float x = __uint_as_float(a), y = __uint_as_float(b);
+    if (relu) { x = x > 0.f ? x : 0.f; y = y > 0.f ? y : 0.f; }
+    const __half2 h = __floats2half2_rn(x, y);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// accumulator columns [0, 64) of this thread's lane -> ReLU -> fp16 -> own row of A (8 chunks)
+__device__ __forceinline__ void tc_hidden_to_smem(const TcCtx& c, char* a_row_base) {
+    const uint32_t lane_addr = c.tmem + ((uint32_t)(threadIdx.x & ~31u) << 16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t v[16];
+        tmem_ld16(lane_addr + q * 16, v);
+        tmem_ld_wait();
+        uint4 lo, hi;
+        lo.x = pack_relu_h2(v[0], v[1], true); lo.y = pack_relu_h2(v[2], v[3], true); lo.z = pack_relu_h2(v[4], v[5], true); lo.w = pack_relu_h2(v[6], v[7], true);
+        hi.x = pack_relu_h2(v[8], v[9], true); hi.y = pack_relu_h2(v[10], v[11], true); hi.z = pack_relu_h2(v[12], v[13], true); hi.w = pack_relu_h2(v[14], v[15], true);
+        *reinterpret_cast<uint4*>(a_row_base + (2 * q) * 2048) = lo;
+        *reinterpret_cast<uint4*>(a_row_base + (2 * q + 1) * 2048) = hi;
+    }
+}
+
+// block-wide: every thread must call (idle threads leave stale rows - rows are independent in the GEMMs).
+// The caller has written the encoded features to chunks 0..3 of its row of A (encode_chunks with stride 2048).
+__device__ __forceinline__ void network_tc(MarchSmemTC& S, TcCtx& c, V3 dir01, float raw[4]) {
+    char* a_row = reinterpret_cast<char*>(S.act) + threadIdx.x * 16;
+    // ---- density layer 0: A = enc (K = 32)
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) { tc_fence_after(); tc_issue_layer(c, kWD0, 64, 32); }
+    mbar_wait(c.mbar, c.phase); c.phase ^= 1u;
+    tc_fence_after();
+    tc_hidden_to_smem(c, a_row);
+    // ---- density layer 1 (K = 64, N = 16)
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) { tc_fence_after(); tc_issue_layer(c, kWD1, 16, 64); }
+    mbar_wait(c.mbar, c.phase); c.phase ^= 1u;
+    tc_fence_after();
+    const uint32_t lane_addr = c.tmem + ((uint32_t)(threadIdx.x & ~31u) << 16);
+    {
+        uint32_t v[16];
+        tmem_ld16(lane_addr, v);
+        tmem_ld_wait();
+        uint4 lo, hi;
+        lo.x = pack_relu_h2(v[0], v[1], false); lo.y = pack_relu_h2(v[2], v[3], false); lo.z = pack_relu_h2(v[4], v[5], false); lo.w = pack_relu_h2(v[6], v[7], false);
+        hi.x = pack_relu_h2(v[8], v[9], false); hi.y = pack_relu_h2(v[10], v[11], false); hi.z = pack_relu_h2(v[12], v[13], false); hi.w = pack_relu_h2(v[14], v[15], false);
+        raw[3] = __low2float(*reinterpret_cast<const __half2*>(&lo.x));   // density = fp16(channel 0), extract_density
+        *reinterpret_cast<uint4*>(a_row + 0 * 2048) = lo;
+        *reinterpret_cast<uint4*>(a_row + 1 * 2048) = hi;
+        __half2 sh[8];
+        sh4(dir01, sh);
+        uint4 s0, s1;
+        s0.x = *reinterpret_cast<const uint32_t*>(&sh[0]); s0.y = *reinterpret_cast<const uint32_t*>(&sh[1]); s0.z = *reinterpret_cast<const uint32_t*>(&sh[2]); s0.w = *reinterpret_cast<const uint32_t*>(&sh[3]);
+        s1.x = *reinterpret_cast<const uint32_t*>(&sh[4]); s1.y = *reinterpret_cast<const uint32_t*>(&sh[5]); s1.z = *reinterpret_cast<const uint32_t*>(&sh[6]); s1.w = *reinterpret_cast<const uint32_t*>(&sh[7]);
+        *reinterpret_cast<uint4*>(a_row + 2 * 2048) = s0;
+        *reinterpret_cast<uint4*>(a_row + 3 * 2048) = s1;
+    }
+    // ---- rgb layer 0 (K = 32)
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) { tc_fence_after(); tc_issue_layer(c, kWR0, 64, 32); }
+    mbar_wait(c.mbar, c.phase); c.phase ^= 1u;
+    tc_fence_after();
+    tc_hidden_to_smem(c, a_row);
+    // ---- rgb layer 1 (K = 64)
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) { tc_fence_after(); tc_issue_layer(c, kWR1, 64, 64); }
+    mbar_wait(c.mbar, c.phase); c.phase ^= 1u;
+    tc_fence_after();
+    tc_hidden_to_smem(c, a_row);
+    // ---- rgb output layer (K = 64, N = 16, three channels used)
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) { tc_fence_after(); tc_issue_layer(c, kWR2, 16, 64); }
+    mbar_wait(c.mbar, c.phase); c.phase ^= 1u;
+    tc_fence_after();
+    {
+        uint32_t v[4];
+        tmem_ld4(lane_addr, v);
+        tmem_ld_wait();
+        raw[0] = __half2float(__float2half_rn(__uint_as_float(v[0])));
+        raw[1] = __half2float(__float2half_rn(__uint_as_float(v[1])));
+        raw[2] = __half2float(__float2half_rn(__uint_as_float(v[2])));
+    }
+    tc_fence_before();   // the next tile's first MMA overwrites these accumulator columns after the next __syncthreads
+}
+
+// =================================================================================================================
+// march_kernel
+// NerfTracer::trace's wavefront loop (S/ngp/testbed.cu:1938-2053) collapsed into one persistent kernel:
+// generate_next_nerf_network_inputs (n_steps = 1) -> network -> composite_kernel_nerf -> shade/accumulate/tonemap.
+// =================================================================================================================
+template <bool TC>
+__global__ void __launch_bounds__(kTile, TC ? 4 : 2) march_kernel(FrameParams P, DeviceModel M, const float4* __restrict__ queue, uint32_t* __restrict__ counters,
+                                                                    FrameOut out, uint32_t debug_flags) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    using Smem = typename std::conditional<TC, MarchSmemTC, MarchSmem>::type;
+    Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+
+    const uint32_t n_rays = counters[0];
+    TcCtx tc;
+    if (TC) {
+        if (threadIdx.x < 32) tmem_alloc(&S.tmem_base, 64);
+        if (threadIdx.x == 0) { mbar_init(&S.mbar, 1); fence_barrier_init(); }
+        stage_weights_tc(S.w, M.mlp);
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        tc.tmem = S.tmem_base; tc.a_addr = smem_u32(S.act); tc.w_addr = smem_u32(S.w); tc.mbar = &S.mbar; tc.phase = 0; tc.swap = (debug_flags & kDebugSwapLboSbo) != 0;
+    } else {
+        for (int i = threadIdx.x; i < kWTotal / 8; i += blockDim.x) reinterpret_cast<uint4*>(S.w)[i] = __ldg(reinterpret_cast<const uint4*>(M.mlp) + i);
+        __syncthreads();
+    }
+
+    const V3 origin = v3(P.cam[9] + 0.5f, P.cam[10] + 0.5f, P.cam[11] + 0.5f);
+    const V3 cam_origin = v3(P.cam[9], P.cam[10], P.cam[11]);
+    const V3 tdiag = v3(P.taabb_max[0] - P.taabb_min[0], P.taabb_max[1] - P.taabb_min[1], P.taabb_max[2] - P.taabb_min[2]);
+
+    // per-ray state (one ray slot per thread)
+    bool active = false, exhausted = false;
+    V3 dir = v3(0.f, 0.f, 1.f), idir = v3(0.f, 0.f, 1.f), dir01 = v3(0.5f, 0.5f, 1.f);
+    float t = 0.f, t_start = 0.f, t_surface = 0.f, max_weight = 0.f, depth = 0.f;
+    float sr = 0.f, sg = 0.f, sb = 0.f, sw = 0.f;        // surface colour (mesh hand-off)
+    float cr = 0.f, cg = 0.f, cb = 0.f, ca = 0.f;        // accumulated colour
+    uint32_t idx = 0, n_samples = 0;
+    unsigned long long total_samples = 0;
+
+    while (true) {
+        // ---- 1. every slot gets a sample, pulling new rays from the queue as rays end ----
+        Sample smp;
+        bool have = false;
+        while (!have) {
+            if (!active) {
+                if (exhausted) break;
+                const uint32_t slot = atomicAdd(&counters[1], 1u);
+                if (slot >= n_rays) { exhausted = true; break; }
+                const float4 q0 = __ldg(queue + (size_t)slot * kRayRecordFloat4s), q1 = __ldg(queue + (size_t)slot * kRayRecordFloat4s + 1), q2 = __ldg(queue + (size_t)slot * kRayRecordFloat4s + 2);
+                dir = v3(q0.x, q0.y, q0.z); t = q0.w; t_start = q1.x; t_surface = q1.y; idx = __float_as_uint(q1.z);
+                sr = q2.x; sg = q2.y; sb = q2.z; sw = q2.w;
+                idir = v3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
+                dir01 = v3((dir.x + 1.0f) * 0.5f, (dir.y + 1.0f) * 0.5f, (dir.z + 1.0f) * 0.5f);   // warp_direction
+                cr = cg = cb = ca = 0.f; max_weight = 0.f; depth = 0.f; n_samples = 0;
+                active = true;
+            }
+            if (next_sample(P, M.bitfield, origin, dir, idir, t_start, t_surface, sw, false, t, smp)) {
+                have = true;
+            } else {
+                // composite_kernel_nerf's tail for a ray whose batch came back empty (S/ngp/testbed.cu:886-901)
+                if (sw > 0) { const float k = 1.f - ca; cr += sr * k; cg += sg * k; cb += sb * k; ca += sw * k; }
+                finish_pixel(P, out, idx, cr, cg, cb, ca, depth, n_samples);
+                active = false;
+            }
+        }
+
+        // ---- 2. encode straight into this thread's row of the A operand ----
+        if (have) {
+            if (TC) encode_chunks(M, smp.pos, reinterpret_cast<char*>(S.act) + threadIdx.x * 16, 2048);
+            else encode_chunks(M, smp.pos, reinterpret_cast<char*>(S.act) + threadIdx.x * 128, 16);
+        }
+        if (!__syncthreads_or(have ? 1 : 0)) break;
+
+        // ---- 3. network ----
+        float raw[4];
+        if (TC) network_tc(reinterpret_cast<MarchSmemTC&>(S), tc, dir01, raw);
+        else network_scalar(reinterpret_cast<MarchSmem&>(S), dir01, raw);
+
+        // ---- 4. composite this sample (S/ngp/testbed.cu:830-884 with n_steps = 1) ----
+        if (have) {
+            ++n_samples; ++total_samples;
+            bool done = false;
+            float T = 1.f - ca;
+            const float dt = unwarp_dt(smp.dt_warped);
+            if (t > t_surface && sw > 0) {
+                cr += sr * sw * T; cg += sg * sw * T; cb += sb * sw * T; ca += sw * T;
+                sw = 0.f;
+                T = 1.f - ca;
+                if (ca > 0.99f) { const float a = ca; cr /= a; cg /= a; cb /= a; ca /= a; done = true; }
+            }
+            if (!done) {
+                const float alpha = 1.f - __expf(-act_density(raw[3], P.density_activation) * dt);
+                const float weight = alpha * T;
+                cr += act_rgb(raw[0], P.rgb_activation) * weight;
+                cg += act_rgb(raw[1], P.rgb_activation) * weight;
+                cb += act_rgb(raw[2], P.rgb_activation) * weight;
+                ca += weight;
+                if (weight > max_weight) {
+                    max_weight = weight;
+                    const V3 pos = v3(P.taabb_min[0] + smp.pos.x * tdiag.x, P.taabb_min[1] + smp.pos.y * tdiag.y, P.taabb_min[2] + smp.pos.z * tdiag.z);
+                    const V3 dd = vsub(pos, cam_origin);
+                    depth = sqrtf(edot(dd, dd));
+                }
+                if (ca > (1.0f - P.min_transmittance)) { const float a = ca; cr /= a; cg /= a; cb /= a; ca /= a; done = true; }
+            }
+            if (done) {
+                if (sw > 0) { const float k = 1.f - ca; cr += sr * k; cg += sg * k; cb += sb * k; ca += sw * k; }
+                finish_pixel(P, out, idx, cr, cg, cb, ca, depth, n_samples);
+                active = false;
+            }
+        }
+    }
+
+    // sample counter: one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) total_samples += __shfl_xor_sync(0xffffffffu, total_samples, o);
+    if ((threadIdx.x & 31) == 0 && total_samples) atomicAdd(reinterpret_cast<unsigned long long*>(counters + 2), total_samples);
+    if (TC) {
+        tc_fence_before();
+        __syncthreads();
+        if (threadIdx.x < 32) tmem_dealloc(tc.tmem, 64);
+    }
+}
+
+void launch_march(const FrameParams& P, const DeviceModel& M, const float4* d_queue, uint32_t* d_counters, const FrameOut& out,
+                  uint32_t debug_flags, int num_sms, cudaStream_t s) {
+    if (debug_flags & kDebugScalarMlp) {
+        static bool attr_set = false;
+        if (!attr_set) { cudaFuncSetAttribute(march_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmem)); attr_set = true; }
+        march_kernel<false><<<num_sms * 2, kTile, sizeof(MarchSmem), s>>>(P, M, d_queue, d_counters, out, debug_flags);
+    } else {
+        static bool attr_set = false;
+        if (!attr_set) { cudaFuncSetAttribute(march_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmemTC)); attr_set = true; }
+        march_kernel<true><<<num_sms * 4, kTile, sizeof(MarchSmemTC), s>>>(P, M, d_queue, d_counters, out, debug_flags);
+    }
+}
+
+// =================================================================================================================
+// parity probes
+// =================================================================================================================
+__global__ void debug_encode_kernel(DeviceModel M, const float* __restrict__ pos, int64_t n, uint16_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    encode_chunks(M, v3(pos[i * 3], pos[i * 3 + 1], pos[i * 3 + 2]), reinterpret_cast<char*>(out + i * ENC_WIDTH), 16);
+}
+void launch_debug_encode(const DeviceModel& M, const float* d_pos, int64_t n, uint16_t* d_out, cudaStream_t s) {
+    if (n <= 0) return;
+    debug_encode_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(M, d_pos, n, d_out);
+}
+
+template <bool TC>
+__global__ void __launch_bounds__(kTile) debug_network_kernel(DeviceModel M, const float* __restrict__ pos, const float* __restrict__ dir, int64_t n, uint16_t* __restrict__ out4, uint32_t debug_flags) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    using Smem = typename std::conditional<TC, MarchSmemTC, MarchSmem>::type;
+    Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+    TcCtx tc;
+    if (TC) {
+        if (threadIdx.x < 32) tmem_alloc(&S.tmem_base, 64);
+        if (threadIdx.x == 0) { mbar_init(&S.mbar, 1); fence_barrier_init(); }
+        stage_weights_tc(S.w, M.mlp);
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        tc.tmem = S.tmem_base; tc.a_addr = smem_u32(S.act); tc.w_addr = smem_u32(S.w); tc.mbar = &S.mbar; tc.phase = 0; tc.swap = (debug_flags & kDebugSwapLboSbo) != 0;
+    } else {
+        for (int i = threadIdx.x; i < kWTotal / 8; i += blockDim.x) reinterpret_cast<uint4*>(S.w)[i] = __ldg(reinterpret_cast<const uint4*>(M.mlp) + i);
+        __syncthreads();
+    }
+    for (int64_t base = (int64_t)blockIdx.x * kTile; base < n; base += (int64_t)gridDim.x * kTile) {
+        const int64_t i = base + threadIdx.x;
+        const bool have = i < n;
+        V3 d01 = v3(0.5f, 0.5f, 0.5f);
+        if (have) {
+            const V3 p = v3(pos[i * 3], pos[i * 3 + 1], pos[i * 3 + 2]);
+            if (TC) encode_chunks(M, p, reinterpret_cast<char*>(S.act) + threadIdx.x * 16, 2048);
+            else encode_chunks(M, p, reinterpret_cast<char*>(S.act) + threadIdx.x * 128, 16);
+            d01 = v3(dir[i * 3], dir[i * 3 + 1], dir[i * 3 + 2]);
+        }
+        float raw[4];
+        if (TC) network_tc(reinterpret_cast<MarchSmemTC&>(S), tc, d01, raw);
+        else network_scalar(reinterpret_cast<MarchSmem&>(S), d01, raw);
+        if (have) {
+            for (int k = 0; k < 4; ++k) { const __half h = __float2half_rn(raw[k]); out4[i * 4 + k] = *reinterpret_cast<const uint16_t*>(&h); }
+        }
+    }
+    if (TC) {
+        tc_fence_before();
+        __syncthreads();
+        if (threadIdx.x < 32) tmem_dealloc(tc.tmem, 64);
+    }
+}
+void launch_debug_network(const DeviceModel& M, const float* d_pos, const float* d_dir, int64_t n, uint16_t* d_out4, uint32_t debug_flags, cudaStream_t s) {
+    if (n <= 0) return;
+    const unsigned blocks = (unsigned)((n + kTile - 1) / kTile < 592 ? (n + kTile - 1) / kTile : 592);
+    if (debug_flags & kDebugScalarMlp) {
+        cudaFuncSetAttribute(debug_network_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmem));
+        debug_network_kernel<false><<<blocks, kTile, sizeof(MarchSmem), s>>>(M, d_pos, d_dir, n, d_out4, debug_flags);
+    } else {
+        cudaFuncSetAttribute(debug_network_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmemTC));
+        debug_network_kernel<true><<<blocks, kTile, sizeof(MarchSmemTC), s>>>(M, d_pos, d_dir, n, d_out4, debug_flags);
+    }
+}
+
+__global__ void debug_trace_kernel(FrameParams P, DeviceModel M, const uint32_t* __restrict__ pixels, int64_t n_pix, uint32_t max_samples,
+                                   float* __restrict__ o_t, uint32_t* __restrict__ o_cell, uint32_t* __restrict__ o_mip, float* __restrict__ o_pos,
+                                   uint32_t* __restrict__ o_count, float* __restrict__ o_ray) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pix) return;
+    const uint32_t pix = pixels[i];
+    const uint32_t x = pix % (uint32_t)P.width, y = pix / (uint32_t)P.width;
+    RayInit r = init_ray(P, x, y);
+    float t = r.t, t_start;
+    const bool alive = advance_pos(P, M.bitfield, r.origin, r.dir, pix, 0.f, r.alive, t, t_start);
+    float* rr = o_ray + i * 8;
+    rr[0] = r.origin.x; rr[1] = r.origin.y; rr[2] = r.origin.z; rr[3] = r.dir.x; rr[4] = r.dir.y; rr[5] = r.dir.z; rr[6] = t; rr[7] = alive ? 1.f : 0.f;
+    const V3 idir = v3(1.0f / r.dir.x, 1.0f / r.dir.y, 1.0f / r.dir.z);
+    uint32_t cnt = 0;
+    while (alive && cnt < max_samples) {
+        Sample s;
+        if (!next_sample(P, M.bitfield, r.origin, r.dir, idir, t_start, 0.f, 0.f, true, t, s)) break;
+        const int64_t o = i * max_samples + cnt;
+        o_t[o] = s.t; o_cell[o] = s.cell; o_mip[o] = s.mip;
+        o_pos[o * 3] = s.pos.x; o_pos[o * 3 + 1] = s.pos.y; o_pos[o * 3 + 2] = s.pos.z;
+        ++cnt;
+    }
+    o_count[i] = cnt;
+}
+void launch_debug_trace(const FrameParams& P, const DeviceModel& M, const uint32_t* d_pixels, int64_t n_pix, uint32_t max_samples,
+                        float* d_t, uint32_t* d_cell, uint32_t* d_mip, float* d_pos, uint32_t* d_count, float* d_ray, cudaStream_t s) {
+    if (n_pix <= 0) return;
+    debug_trace_kernel<<<(unsigned)((n_pix + 63) / 64), 64, 0, s>>>(P, M, d_pixels, n_pix, max_samples, d_t, d_cell, d_mip, d_pos, d_count, d_ray);
+}
+
+__global__ void debug_mesh_kernel(MeshDevice mesh, FrameParams P, const unsigned long long* __restrict__ zbuf, float* __restrict__ rgba2, float* __restrict__ depth2,
+                                  int32_t* __restrict__ tri2, float* __restrict__ surf, float* __restrict__ tsurf) {
+    const int ms = P.mesh_scale, W2 = P.width * ms, H2 = P.height * ms;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < W2 * H2 && (rgba2 || depth2 || tri2)) {
+        const int x = i % W2, y = i / W2;
+        float c[4] = {0.f, 0.f, 0.f, 0.f}; float ht = __uint_as_float(0xFFFFFFFFu); int32_t tri;
+        mesh_tap(mesh, P, zbuf, x, y, W2, H2, c, ht, &tri);
+        if (rgba2) { rgba2[i * 4] = c[0]; rgba2[i * 4 + 1] = c[1]; rgba2[i * 4 + 2] = c[2]; rgba2[i * 4 + 3] = c[3]; }
+        if (depth2) depth2[i] = ht;
+        if (tri2) tri2[i] = tri;
+    }
+    if (i < P.width * P.height && (surf || tsurf)) {
+        float s4[4]; float ts;
+        mesh_resolve(mesh, P, zbuf, i % P.width, i / P.width, s4, ts);
+        if (surf) { surf[i * 4] = s4[0]; surf[i * 4 + 1] = s4[1]; surf[i * 4 + 2] = s4[2]; surf[i * 4 + 3] = s4[3]; }
+        if (tsurf) tsurf[i] = ts;
+    }
+}
+void launch_debug_mesh(const MeshDevice& mesh, const FrameParams& P, const unsigned long long* d_zbuf, float* d_rgba2, float* d_depth2, int32_t* d_tri2,
+                       float* d_surf, float* d_tsurf, cudaStream_t s) {
+    const int n = P.width * P.mesh_scale * P.height * P.mesh_scale;
+    debug_mesh_kernel<<<(n + 127) / 128, 128, 0, s>>>(mesh, P, d_zbuf, d_rgba2, d_depth2, d_tri2, d_surf, d_tsurf);
+}
+
+}  // namespace nmr

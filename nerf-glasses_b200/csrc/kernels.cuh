@@ -1,0 +1,49 @@
+// kernels.cuh - launch interface between the C-ABI layer (api.cpp) and the CUDA kernels (kernels.cu, floaties.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_common.cuh"
+
+namespace nmr {
+
+// per-frame output surfaces (all device pointers; optional ones may be null)
+struct FrameOut {
+    float4* image;        // displayed image (tonemapped), W*H
+    float4* accum;        // running mean over spp (linear, premultiplied), W*H
+    float4* frame;        // this sample's linear premultiplied frame buffer (parity probe), W*H or null
+    float* depth;         // W*H or null
+    uint32_t* n_samples;  // network evaluations per ray, W*H or null
+};
+
+// device counters of one render: [0] rays queued by the init kernel, [1] queue cursor of the march kernel,
+// [2..3] total network evaluations (64-bit), [4] rays launched
+constexpr int kNumCounters = 8;
+constexpr int kRayRecordFloat4s = 3;   // queue record: (dir.xyz, t) (t_start, t_surface, idx, -) (surface rgba)
+
+enum DebugFlags : uint32_t {
+    kDebugScalarMlp = 1u,     // run the CUDA-core MLP instead of tcgen05 (NMR_MLP=scalar)
+    kDebugSwapLboSbo = 2u,    // swap the UMMA descriptor offsets (bring-up aid)
+};
+
+void launch_occupancy_build(const uint16_t* d_density_grid_fp16, int n_cascades_present, uint8_t* d_bitfield, float* d_scratch, cudaStream_t s);
+void launch_mesh_raster(const MeshDevice& mesh, const FrameParams& P, int rows_owned, unsigned long long* d_zbuf, cudaStream_t s);
+void launch_init_rays(const FrameParams& P, const DeviceModel& M, const MeshDevice& mesh, const unsigned long long* d_zbuf, int rows_owned,
+                      float4* d_queue, uint32_t* d_counters, const FrameOut& out, cudaStream_t s);
+void launch_march(const FrameParams& P, const DeviceModel& M, const float4* d_queue, uint32_t* d_counters, const FrameOut& out,
+                  uint32_t debug_flags, int num_sms, cudaStream_t s);
+// parity probes
+void launch_debug_encode(const DeviceModel& M, const float* d_pos, int64_t n, uint16_t* d_out, cudaStream_t s);
+void launch_debug_network(const DeviceModel& M, const float* d_pos, const float* d_dir, int64_t n, uint16_t* d_out4, uint32_t debug_flags, cudaStream_t s);
+void launch_debug_trace(const FrameParams& P, const DeviceModel& M, const uint32_t* d_pixels, int64_t n_pix, uint32_t max_samples,
+                        float* d_t, uint32_t* d_cell, uint32_t* d_mip, float* d_pos, uint32_t* d_count, float* d_ray, cudaStream_t s);
+void launch_debug_mesh(const MeshDevice& mesh, const FrameParams& P, const unsigned long long* d_zbuf, float* d_rgba2, float* d_depth2, int32_t* d_tri2,
+                       float* d_surf, float* d_tsurf, cudaStream_t s);
+// floatie pruning on the 2 MiB bitfield (floaties.cu); results[0] = clusters, results[1] = kept cells (host-visible after sync)
+void launch_remove_floaties(uint8_t* d_bitfield, int max_cascade, uint32_t* d_labels, unsigned long long* d_scratch, cudaStream_t s);
+size_t floaties_label_bytes();
+size_t floaties_scratch_bytes();
+
+int rows_owned_by(int height, int rank, int world, int band);
+
+}  // namespace nmr

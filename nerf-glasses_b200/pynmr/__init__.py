@@ -1,0 +1,476 @@
+"""pynmr - drop-in Python surface of the reference's pybind11 module of the same name
+(nerf_mesh_renderer/src/python_api.cu:156-623), implemented as a thin ctypes shim over the C ABI of libnmr.so
+(include/nmr.h).  `volume/render.py` of the reference runs unchanged against this module:
+
+    import pynmr as nmr
+    renderer = nmr.NerfMeshRenderer(1280, 720)
+    renderer.envmap("sunflowers_puresky_1k.png")           # accepted and ignored (missing in the reference module)
+    nerf = renderer.load_nerf("nerf.msgpack")
+    nerf.render_aabb.min = np.array([-0.2, 0.15, -0.2])
+    mesh = renderer.load_mesh("glasses.gltf", t=..., s=..., r=[w, x, y, z])
+    while renderer.frame():
+        renderer.orbit(daz, dpolar, 0)
+        im = nerf.render(1280, 720, linear=False)          # float32[H, W, 4], row 0 = bottom
+
+There is no CPU fallback: importing works anywhere, but constructing a NerfMeshRenderer needs libnmr.so and an
+sm_100 GPU and raises RuntimeError otherwise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libnmr.so")
+
+NMR_OK = 0
+
+
+class Stats(C.Structure):
+    _fields_ = [("rays", C.c_uint64), ("rays_alive", C.c_uint64), ("samples", C.c_uint64), ("mesh_rays", C.c_uint64),
+                ("kernel_launches", C.c_uint64), ("gpu_ms", C.c_float), ("march_ms", C.c_float)]
+
+
+_lib = None
+
+
+def lib():
+    """Loads libnmr.so (raises RuntimeError with the build hint when it is missing)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not found - build it with `python nerf-glasses_b200/build.py` (nvcc, sm_100a)")
+    L = C.CDLL(LIB_PATH)
+    vp, ip, fp = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float)
+    sig = {
+        "nmr_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
+        "nmr_destroy": (None, [vp]),
+        "nmr_last_error": (C.c_char_p, [vp]),
+        "nmr_load_nerf": (C.c_int, [vp, C.c_char_p, ip]),
+        "nmr_load_mesh": (C.c_int, [vp, C.c_char_p, fp, fp, fp, ip]),
+        "nmr_set_mesh_transform": (C.c_int, [vp, C.c_int, fp, fp, fp]),
+        "nmr_get_mesh_transform": (C.c_int, [vp, C.c_int, fp, fp, fp]),
+        "nmr_set_envmap": (C.c_int, [vp, C.c_char_p]),
+        "nmr_remove_floaties": (C.c_int, [vp, ip, C.POINTER(C.c_int64)]),
+        "nmr_get_render_aabb": (C.c_int, [vp, C.c_int, fp, fp]),
+        "nmr_set_render_aabb": (C.c_int, [vp, C.c_int, fp, fp]),
+        "nmr_get_aabb": (C.c_int, [vp, C.c_int, fp, fp]),
+        "nmr_get_background": (C.c_int, [vp, C.c_int, fp]),
+        "nmr_set_background": (C.c_int, [vp, C.c_int, fp]),
+        "nmr_set_min_transmittance": (C.c_int, [vp, C.c_int, C.c_float]),
+        "nmr_orbit": (C.c_int, [vp, C.c_float, C.c_float, C.c_float]),
+        "nmr_get_camera": (C.c_int, [vp, fp]),
+        "nmr_set_camera": (C.c_int, [vp, fp]),
+        "nmr_frame": (C.c_int, [vp, ip]),
+        "nmr_frame_async": (C.c_int, [vp]),
+        "nmr_read_frame": (C.c_int, [vp, vp]),
+        "nmr_render": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+        "nmr_render_views": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp]),
+        "nmr_set_shard": (C.c_int, [vp, C.c_int, C.c_int, C.c_int]),
+        "nmr_get_device_image": (C.c_int, [vp, C.POINTER(vp), ip, ip]),
+        "nmr_copy_device_image": (C.c_int, [vp, vp]),
+        "nmr_flush_l2": (C.c_int, [vp]),
+        "nmr_get_stats": (C.c_int, [vp, C.POINTER(Stats)]),
+        "nmr_synchronize": (C.c_int, [vp]),
+        "nmr_host_alloc": (vp, [C.c_size_t]),
+        "nmr_host_free": (None, [vp]),
+        "nmr_get_density_bitfield": (C.c_int, [vp, C.c_int, vp]),
+        "nmr_set_density_bitfield": (C.c_int, [vp, C.c_int, vp]),
+        "nmr_debug_encode": (C.c_int, [vp, C.c_int, vp, C.c_int64, vp]),
+        "nmr_debug_network": (C.c_int, [vp, C.c_int, vp, vp, C.c_int64, vp]),
+        "nmr_debug_trace": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int64, C.c_uint32, vp, vp, vp, vp, vp, vp]),
+        "nmr_debug_mesh": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]),
+        "nmr_debug_last_frame": (C.c_int, [vp, vp, vp, vp]),
+        "nmr_debug_set_flags": (C.c_int, [vp, C.c_uint32]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = [
+    "nmr_create", "nmr_destroy", "nmr_last_error", "nmr_load_nerf", "nmr_load_mesh", "nmr_set_mesh_transform",
+    "nmr_get_mesh_transform", "nmr_set_envmap", "nmr_remove_floaties", "nmr_get_render_aabb", "nmr_set_render_aabb",
+    "nmr_get_aabb", "nmr_get_background", "nmr_set_background", "nmr_set_min_transmittance", "nmr_orbit", "nmr_get_camera",
+    "nmr_set_camera", "nmr_frame", "nmr_frame_async", "nmr_read_frame", "nmr_render", "nmr_render_views", "nmr_set_shard",
+    "nmr_get_device_image", "nmr_copy_device_image", "nmr_flush_l2", "nmr_get_stats", "nmr_synchronize", "nmr_host_alloc", "nmr_host_free", "nmr_get_density_bitfield",
+    "nmr_set_density_bitfield", "nmr_debug_encode", "nmr_debug_network", "nmr_debug_trace", "nmr_debug_mesh",
+    "nmr_debug_last_frame", "nmr_debug_set_flags",
+]
+
+
+def _f3(v):
+    a = np.asarray(v, dtype=np.float32).reshape(-1)
+    return (C.c_float * len(a))(*[float(x) for x in a])
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class _PinnedArray:
+    """numpy array over page-locked memory from nmr_host_alloc (fast, asynchronous device->host copies)."""
+
+    def __init__(self, shape, dtype=np.float32):
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self._p = lib().nmr_host_alloc(n)
+        if not self._p:
+            raise MemoryError("nmr_host_alloc failed")
+        buf = (C.c_char * n).from_address(self._p)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_p", None):
+                lib().nmr_host_free(self._p)
+                self._p = None
+        except Exception:
+            pass
+
+
+class Vec3:
+    """glm::vec3 stand-in (S/python_api.cu:263-270)."""
+
+    def __init__(self, x=0.0, y=0.0, z=0.0, _on_change=None):
+        if not np.isscalar(x):
+            x, y, z = [float(v) for v in np.asarray(x).reshape(3)]
+        self._v = [float(x), float(y), float(z)]
+        self._cb = _on_change
+
+    def _set(self, i, val):
+        self._v[i] = float(val)
+        if self._cb:
+            self._cb(self)
+
+    x = property(lambda s: s._v[0], lambda s, v: s._set(0, v))
+    y = property(lambda s: s._v[1], lambda s, v: s._set(1, v))
+    z = property(lambda s: s._v[2], lambda s, v: s._set(2, v))
+
+    def __iter__(self):
+        return iter(self._v)
+
+    def __array__(self, dtype=None, copy=None):
+        return np.array(self._v, dtype=dtype or np.float32)
+
+    def __repr__(self):
+        return f"Vec3({self._v[0]}, {self._v[1]}, {self._v[2]})"
+
+
+class BoundingBox:
+    """ngp::BoundingBox (S/python_api.cu:242-261).  When obtained from Testbed.render_aabb it is a live view:
+    assigning .min / .max updates the renderer's crop box, like the reference's def_readwrite on the C++ object."""
+
+    def __init__(self, a=None, b=None, _owner=None):
+        self._owner = _owner
+        self._min = np.full(3, np.inf, dtype=np.float32) if a is None else np.asarray(a, dtype=np.float32).copy()
+        self._max = np.full(3, -np.inf, dtype=np.float32) if b is None else np.asarray(b, dtype=np.float32).copy()
+
+    def _pull(self):
+        if self._owner is not None:
+            self._min, self._max = self._owner._get_render_aabb()
+
+    def _push(self):
+        if self._owner is not None:
+            self._owner._set_render_aabb(self._min, self._max)
+
+    @property
+    def min(self):
+        self._pull()
+        return self._min.copy()
+
+    @min.setter
+    def min(self, v):
+        self._pull()
+        self._min = np.asarray(v, dtype=np.float32).reshape(3).copy()
+        self._push()
+
+    @property
+    def max(self):
+        self._pull()
+        return self._max.copy()
+
+    @max.setter
+    def max(self, v):
+        self._pull()
+        self._max = np.asarray(v, dtype=np.float32).reshape(3).copy()
+        self._push()
+
+    def center(self):
+        return 0.5 * (self.max + self.min)
+
+    def diag(self):
+        return self.max - self.min
+
+    def contains(self, p):
+        p = np.asarray(p, dtype=np.float32)
+        return bool(np.all(p >= self.min) and np.all(p <= self.max))
+
+    def relative_pos(self, p):
+        return (np.asarray(p, dtype=np.float32) - self.min) / self.diag()
+
+    def inflate(self, amount):
+        self._pull()
+        self._min = self._min - np.float32(amount)
+        self._max = self._max + np.float32(amount)
+        self._push()
+
+    def enlarge(self, other):
+        self._pull()
+        if isinstance(other, BoundingBox):
+            self._min = np.minimum(self._min, other.min); self._max = np.maximum(self._max, other.max)
+        else:
+            p = np.asarray(other, dtype=np.float32)
+            self._min = np.minimum(self._min, p); self._max = np.maximum(self._max, p)
+        self._push()
+
+    def intersection(self, other):
+        return BoundingBox(np.maximum(self.min, other.min), np.minimum(self.max, other.max))
+
+    def intersects(self, other):
+        i = self.intersection(other)
+        return not bool(np.any(i.max < i.min))
+
+    def __repr__(self):
+        return f"[min={self.min.tolist()}, max={self.max.tolist()}]"
+
+
+class _NerfSettings:
+    """Testbed.nerf (S/python_api.cu:470-496): the members that affect pixels."""
+
+    def __init__(self, tb):
+        self._tb = tb
+        self._min_t = 0.01
+
+    @property
+    def render_min_transmittance(self):
+        return self._min_t
+
+    @render_min_transmittance.setter
+    def render_min_transmittance(self, v):
+        self._min_t = float(v)
+        self._tb._r._ck(lib().nmr_set_min_transmittance(self._tb._r._h, self._tb._id, float(v)))
+
+
+class Testbed:
+    """ngp::Testbed as returned by NerfMeshRenderer.load_nerf (S/python_api.cu:299-496)."""
+
+    def __init__(self, renderer: "NerfMeshRenderer", nerf_id: int):
+        self._r, self._id = renderer, nerf_id
+        self.nerf = _NerfSettings(self)
+        self._render_aabb = BoundingBox(_owner=self)
+
+    # -- crop box
+    def _get_render_aabb(self):
+        mn = (C.c_float * 3)(); mx = (C.c_float * 3)()
+        self._r._ck(lib().nmr_get_render_aabb(self._r._h, self._id, mn, mx))
+        return np.array(list(mn), dtype=np.float32), np.array(list(mx), dtype=np.float32)
+
+    def _set_render_aabb(self, mn, mx):
+        self._r._ck(lib().nmr_set_render_aabb(self._r._h, self._id, _f3(mn), _f3(mx)))
+
+    @property
+    def render_aabb(self) -> BoundingBox:
+        return self._render_aabb
+
+    @render_aabb.setter
+    def render_aabb(self, box: BoundingBox):
+        self._set_render_aabb(box.min, box.max)
+
+    @property
+    def aabb(self) -> BoundingBox:
+        mn = (C.c_float * 3)(); mx = (C.c_float * 3)()
+        self._r._ck(lib().nmr_get_aabb(self._r._h, self._id, mn, mx))
+        return BoundingBox(list(mn), list(mx))
+
+    raw_aabb = aabb
+
+    @property
+    def background_color(self):
+        c = (C.c_float * 4)()
+        self._r._ck(lib().nmr_get_background(self._r._h, self._id, c))
+        return np.array(list(c), dtype=np.float32)
+
+    @background_color.setter
+    def background_color(self, rgba):
+        self._r._ck(lib().nmr_set_background(self._r._h, self._id, _f3(rgba)))
+
+    def render(self, width: int = 1920, height: int = 1080, spp: int = 1, linear: bool = True) -> np.ndarray:
+        """float32[H, W, 4]; row 0 is the bottom of the picture; sRGB when linear=False (S/python_api.cu:83-111)."""
+        out = _PinnedArray((height, width, 4))
+        self._r._ck(lib().nmr_render(self._r._h, self._id, int(width), int(height), int(spp), int(bool(linear)), _ptr(out.array)))
+        return _own(out)
+
+    def reset_accumulation(self, due_to_camera_movement: bool = False, immediate_redraw: bool = True):
+        cam = self._r.view_projection_mat
+        self._r.view_projection_mat = cam   # resets the sample counter
+
+
+def _own(pinned: _PinnedArray) -> np.ndarray:
+    """ndarray subclass instance that keeps its page-locked backing store alive."""
+    arr = pinned.array.view(_OwnedArray)
+    arr._owner = pinned
+    return arr
+
+
+class _OwnedArray(np.ndarray):
+    def __array_finalize__(self, obj):
+        self._owner = getattr(obj, "_owner", None)
+
+
+class GltfNode:
+    """GltfNode (S/python_api.cu:272-276): scale / translation are writable and re-transform the mesh."""
+
+    def __init__(self, renderer: "NerfMeshRenderer", mesh_id: int):
+        self._r, self._id = renderer, mesh_id
+
+    def _get(self):
+        t = (C.c_float * 3)(); s = (C.c_float * 3)(); r = (C.c_float * 4)()
+        self._r._ck(lib().nmr_get_mesh_transform(self._r._h, self._id, t, s, r))
+        return list(t), list(s), list(r)
+
+    @property
+    def translation(self):
+        return Vec3(*self._get()[0], _on_change=lambda v: setattr(self, "translation", v))
+
+    @translation.setter
+    def translation(self, v):
+        self._r._ck(lib().nmr_set_mesh_transform(self._r._h, self._id, _f3(list(v)), None, None))
+
+    @property
+    def scale(self):
+        return Vec3(*self._get()[1], _on_change=lambda v: setattr(self, "scale", v))
+
+    @scale.setter
+    def scale(self, v):
+        self._r._ck(lib().nmr_set_mesh_transform(self._r._h, self._id, None, _f3(list(v)), None))
+
+
+class GltfScene:
+    def __init__(self, renderer, mesh_id):
+        self.nodes = [GltfNode(renderer, mesh_id)]
+
+
+class NerfMeshRenderer:
+    """NerfMeshRenderer (S/python_api.cu:284-298), headless."""
+
+    def __init__(self, width: int, height: int, device: int = -1):
+        h = C.c_void_p()
+        rc = lib().nmr_create(int(width), int(height), int(device), C.byref(h))
+        if rc != NMR_OK:
+            raise RuntimeError("nmr_create failed: " + lib().nmr_last_error(None).decode())
+        self._h = h
+        self.width, self.height = int(width), int(height)
+        self._frame_buf = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().nmr_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def _err(self) -> str:
+        return lib().nmr_last_error(self._h).decode()
+
+    def _ck(self, rc: int):
+        if rc != NMR_OK:
+            raise RuntimeError(f"libnmr error {rc}: {self._err()}")
+
+    # -- reference surface ---------------------------------------------------------------------------------------
+    def frame(self) -> bool:
+        keep = C.c_int(1)
+        self._ck(lib().nmr_frame(self._h, C.byref(keep)))
+        return bool(keep.value)
+
+    def load_nerf(self, path: str):
+        nid = C.c_int(-1)
+        rc = lib().nmr_load_nerf(self._h, os.fsencode(path), C.byref(nid))
+        if rc != NMR_OK:   # the reference logs and returns None (S/nerf_mesh_renderer.cu:995-999)
+            print(f"[error] Failed to load NeRF {path}: {self._err()}", file=sys.stderr)
+            return None
+        return Testbed(self, nid.value)
+
+    def load_mesh(self, path: str, t=(0.0, 0.0, 0.0), s=(1.0, 1.0, 1.0), r=(0.0, 0.0, 0.0, 1.0)):
+        mid = C.c_int(-1)
+        rc = lib().nmr_load_mesh(self._h, os.fsencode(path), _f3(t), _f3(s), _f3(r), C.byref(mid))
+        if rc != NMR_OK:
+            print(f"[error] Failed to load mesh {path}: {self._err()}", file=sys.stderr)
+            return None
+        warn = self._err()
+        if warn:
+            print(f"[warn] {path}: {warn}", file=sys.stderr)
+        return GltfScene(self, mid.value)
+
+    def remove_floaties(self):
+        n = C.c_int(0); kept = C.c_int64(0)
+        self._ck(lib().nmr_remove_floaties(self._h, C.byref(n), C.byref(kept)))
+        return n.value, kept.value
+
+    def orbit(self, delta_azimuth: float, delta_polar: float, delta_zoom: float):
+        self._ck(lib().nmr_orbit(self._h, float(delta_azimuth), float(delta_polar), float(delta_zoom)))
+
+    @property
+    def view_projection_mat(self) -> np.ndarray:
+        m = (C.c_float * 12)()
+        self._ck(lib().nmr_get_camera(self._h, m))
+        return np.array(list(m), dtype=np.float32).reshape(4, 3).T.copy()   # 3x4, like Eigen -> numpy
+
+    @view_projection_mat.setter
+    def view_projection_mat(self, mat):
+        a = np.asarray(mat, dtype=np.float32).reshape(3, 4)
+        self._ck(lib().nmr_set_camera(self._h, _f3(a.T.reshape(-1))))
+
+    def envmap(self, path: str):
+        self._ck(lib().nmr_set_envmap(self._h, os.fsencode(path)))
+
+    # -- additions -----------------------------------------------------------------------------------------------
+    def read_frame(self) -> np.ndarray:
+        """Image of the last frame(): float32[H, W, 4], row 0 = bottom (replaces the reference's on-screen blit)."""
+        out = _PinnedArray((self.height, self.width, 4))
+        self._ck(lib().nmr_read_frame(self._h, _ptr(out.array)))
+        return _own(out)
+
+    def frame_async(self):
+        self._ck(lib().nmr_frame_async(self._h))
+
+    def synchronize(self):
+        self._ck(lib().nmr_synchronize(self._h))
+
+    def render_views(self, nerf: Testbed, cameras, width: int, height: int, linear: bool = False) -> np.ndarray:
+        """cameras: [n, 3, 4] -> float32[n, H, W, 4] rendered back to back (render.py's landmark pass in one call)."""
+        cams = np.ascontiguousarray(np.asarray(cameras, dtype=np.float32).reshape(-1, 3, 4).transpose(0, 2, 1)).reshape(-1, 12)
+        out = _PinnedArray((cams.shape[0], height, width, 4))
+        self._ck(lib().nmr_render_views(self._h, nerf._id, cams.shape[0], _ptr(cams), int(width), int(height), int(bool(linear)), _ptr(out.array)))
+        return _own(out)
+
+    def set_shard(self, rank: int, world: int, band: int = 8):
+        self._ck(lib().nmr_set_shard(self._h, int(rank), int(world), int(band)))
+
+    def device_image(self):
+        """(device pointer, width, height) of the float4 image of the last render."""
+        p = C.c_void_p(); w = C.c_int(); h = C.c_int()
+        self._ck(lib().nmr_get_device_image(self._h, C.byref(p), C.byref(w), C.byref(h)))
+        return p.value, w.value, h.value
+
+    def copy_device_image(self, dst_device_ptr: int):
+        self._ck(lib().nmr_copy_device_image(self._h, C.c_void_p(dst_device_ptr)))
+
+    def flush_l2(self):
+        self._ck(lib().nmr_flush_l2(self._h))
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._ck(lib().nmr_get_stats(self._h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+
+def free_temporary_memory():
+    """tcnn::free_all_gpu_memory_arenas in the reference (S/python_api.cu:159); libnmr has no arena to trim."""
+    return None

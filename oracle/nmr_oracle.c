@@ -1134,14 +1134,17 @@ static void shade_hit(const orc_mesh* M, uint32_t tri, float bu, float bv, float
 
 /* One primary ray per pixel of the (mesh_scale x) supersampled buffer; writes RGBA (alpha 1 hit / 0 miss) and
  * hitT (NaN on miss: the reference stores the uint payload -1 reinterpreted as float).  out_tri optional. */
+/* window = {x0, y0, x1, y1} in supersampled pixels restricts the work to a sub-rectangle (others untouched); NULL = all */
 ORC_API void orc_mesh_render(const orc_mesh* M, const float* camera12, const float* light_pos, int W2, int H2,
-                             float* rgba, float* depth, int32_t* out_tri) {
+                             float* rgba, float* depth, int32_t* out_tri, const int32_t* window) {
     const v3 U = v3_make(camera12[0], camera12[1], camera12[2]), Vv = v3_make(camera12[3], camera12[4], camera12[5]);
     const v3 Wv = v3_make(camera12[6], camera12[7], camera12[8]), eye = v3_make(camera12[9], camera12[10], camera12[11]);
     const v3 light = v3_make(light_pos[0], light_pos[1], light_pos[2]);
+    int wx0 = 0, wy0 = 0, wx1 = W2, wy1 = H2;
+    if (window && window[2] > window[0] && window[3] > window[1]) { wx0 = window[0]; wy0 = window[1]; wx1 = window[2]; wy1 = window[3]; }
 #pragma omp parallel for schedule(dynamic, 4)
-    for (int y = 0; y < H2; ++y) {
-        for (int x = 0; x < W2; ++x) {
+    for (int y = wy0; y < wy1; ++y) {
+        for (int x = wx0; x < wx1; ++x) {
             float dx = 2.0f * (((float)x + 0.5f) / (float)W2) - 1.0f;
             float dy = 2.0f * (((float)y + 0.5f) / (float)H2) - 1.0f;
             v3 dir = glm_normalize3(v3_make((dx * U.x + dy * Vv.x) + Wv.x, (dx * U.y + dy * Vv.y) + Wv.y, (dx * U.z + dy * Vv.z) + Wv.z));

@@ -78,7 +78,7 @@ def lib():
         "orc_mesh_create": (vp, [vp, vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp, vp, vp, C.c_float, C.c_float, vp, vp, C.c_int, C.c_int]),
         "orc_mesh_destroy": (None, [vp]),
         "orc_mesh_world_positions": (None, [vp, vp]),
-        "orc_mesh_render": (None, [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp]),
+        "orc_mesh_render": (None, [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp]),
         "orc_mesh_resolve": (None, [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),
         "orc_bitfield_to_cells": (None, [vp, vp]),
         "orc_cells_to_bitfield": (None, [vp, vp]),
@@ -291,11 +291,13 @@ class Mesh:
         lib().orc_mesh_world_positions(self.h, _p(out))
         return out
 
-    def render(self, camera12, W2: int, H2: int, light=(1.0, 1.0, 1.0)):
-        """-> (rgba f32[H2,W2,4], hitT f32[H2,W2] (NaN on miss), tri i32[H2,W2])"""
+    def render(self, camera12, W2: int, H2: int, light=(1.0, 1.0, 1.0), window=None):
+        """-> (rgba f32[H2,W2,4], hitT f32[H2,W2] (NaN on miss), tri i32[H2,W2]); window = (x0, y0, x1, y1) in
+        supersampled pixels renders only that sub-rectangle (the rest reads as a miss)."""
         cam = np.asarray(camera12, dtype=np.float32); lp = np.asarray(light, dtype=np.float32)
-        rgba = np.empty((H2, W2, 4), dtype=np.float32); depth = np.empty((H2, W2), dtype=np.float32); tri = np.empty((H2, W2), dtype=np.int32)
-        lib().orc_mesh_render(self.h, _p(cam), _p(lp), W2, H2, _p(rgba), _p(depth), _p(tri))
+        rgba = np.zeros((H2, W2, 4), dtype=np.float32); depth = np.full((H2, W2), np.nan, dtype=np.float32); tri = np.full((H2, W2), -1, dtype=np.int32)
+        win = None if window is None else np.asarray(window, dtype=np.int32)
+        lib().orc_mesh_render(self.h, _p(cam), _p(lp), W2, H2, _p(rgba), _p(depth), _p(tri), _p(win) if win is not None else None)
         return rgba, depth, tri
 
 

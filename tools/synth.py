@@ -416,7 +416,7 @@ def _png_bytes(rgba: np.ndarray) -> bytes:
 
 GLASSES_NPZ = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "glasses_mesh.npz")
 # fixed placement replacing the MediaPipe-derived transform
-GLASSES_T = (0.0, 0.05, 0.12)
+GLASSES_T = (0.0, 0.03, 0.215)   # in front of the synthetic head ellipsoid (semi-axis z = 0.20)
 GLASSES_S = (0.17, 0.17, 0.17)
 GLASSES_R_WXYZ = (0.7071068, 0.7071067, 0.0, 0.0)
 
