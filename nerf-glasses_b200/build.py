@@ -28,16 +28,19 @@ def needs_build() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, out: str = OUT, defines=()) -> str:
+    """defines: extra -D macros for tuning builds (e.g. NMR_ENCODE_UNROLL=4) written to another `out`."""
+    if not force and out == OUT and not needs_build():
         return OUT
-    cmd = ["nvcc", *NVCC_FLAGS]
+    cmd = ["nvcc", *NVCC_FLAGS] + [f"-D{d}" for d in defines]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", OUT] + [os.path.join(CSRC, f) for f in SOURCES] + ["-lz"]
+    cmd += ["-o", out] + [os.path.join(CSRC, f) for f in SOURCES] + ["-lz"]
     subprocess.check_call(cmd)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv or bool(defs), verbose="--verbose" in sys.argv, out=outs[0] if outs else OUT, defines=defs))

@@ -208,6 +208,10 @@ FrameParams make_params(nmr_ctx* ctx, const Nerf& n, int W, int H, const float* 
     P.min_transmittance = n.min_transmittance;
     P.rgb_activation = n.host.rgb_activation; P.density_activation = n.host.density_activation;
     std::memcpy(P.background, n.background, 16);
+    for (int k = 0; k < 3; ++k) {   // tonemap_kernel linearises the sRGB background colour (S/ngp/render_buffer.cu:548-550)
+        const float sv = n.background[k];
+        P.background_linear[k] = sv <= 0.04045f ? sv / 12.92f : powf((sv + 0.055f) / 1.055f, 2.4f);
+    }
     P.to_srgb = to_srgb ? 1 : 0;
     P.shard_rank = ctx->shard_rank; P.shard_world = ctx->shard_world; P.shard_band = ctx->shard_band;
     P.mesh_scale = (with_mesh && ctx->mesh_dev.n_tris > 0) ? ctx->mesh_scale : 0;
@@ -245,6 +249,8 @@ void finish_stats(nmr_ctx* ctx) {
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->stats.rays_alive = ctx->h_counters[0];
     ctx->stats.samples = (uint64_t)ctx->h_counters[2] | ((uint64_t)ctx->h_counters[3] << 32);
+    ctx->stats.batches = ctx->h_counters[4];
+    ctx->stats.batch_passes = ctx->h_counters[5];
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[2])); ctx->stats.gpu_ms = ms;
     CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2])); ctx->stats.march_ms = ms;
@@ -336,11 +342,16 @@ NMR_API int nmr_load_nerf(nmr_ctx* ctx, const char* path, int* out_id) {
         d.mlp = reinterpret_cast<const __half*>(n->d_params.p);
         d.grid = reinterpret_cast<const __half2*>(n->d_params.p + h.mlp_params);
         d.bitfield = n->d_bitfield.p;
-        d.dense_mask = 0; d.hash_type = h.hash_type;
+        d.dense_mask = 0; d.pow2_mask = 0;
+        {   // prime_hash<COHERENT> / reversed_prime_hash multipliers (T/.../encodings/grid.h:111-146)
+            static const uint32_t primes[3][3] = {{1958374283u, 2654435761u, 805459861u}, {1u, 2654435761u, 805459861u}, {2165219737u, 1434869437u, 2097192037u}};
+            for (int k = 0; k < 3; ++k) d.prime[k] = primes[h.hash_type][k];
+        }
         for (int l = 0; l < h.n_levels; ++l) {
             d.level_offset[l] = h.offsets[l]; d.level_size[l] = h.offsets[l + 1] - h.offsets[l]; d.level_scale[l] = h.scales[l];
             d.stride_y[l] = h.stride_y[l]; d.stride_z[l] = h.stride_z[l];
             if (h.dense[l]) d.dense_mask |= 1u << l;
+            if ((d.level_size[l] & (d.level_size[l] - 1u)) == 0) d.pow2_mask |= 1u << l;
         }
         std::memcpy(n->render_aabb_min, h.render_aabb_min, 12); std::memcpy(n->render_aabb_max, h.render_aabb_max, 12);
         std::vector<uint16_t>().swap(h.params);

@@ -27,7 +27,8 @@ struct DeviceModel {
     float level_scale[N_LEVELS];
     uint32_t stride_y[N_LEVELS], stride_z[N_LEVELS];
     uint32_t dense_mask;              // bit l set: level l is indexed densely
-    int hash_type;                    // 0 Prime, 1 CoherentPrime, 2 ReversedPrime
+    uint32_t pow2_mask;               // bit l set: level_size[l] is a power of two (index & (size - 1))
+    uint32_t prime[3];                // hash multipliers of the snapshot's hash type (CoherentPrime: 1, 2654435761, 805459861)
 };
 
 struct MeshDevice {
@@ -52,6 +53,7 @@ struct FrameParams {
     float min_transmittance;
     int rgb_activation, density_activation;
     float background[4];
+    float background_linear[3];       // srgb_to_linear(background), evaluated on the host
     int to_srgb;
     int shard_rank, shard_world, shard_band;
     int mesh_scale;                   // 0: no mesh stage
@@ -191,6 +193,8 @@ __device__ __forceinline__ float box_ray_tmin(const float* mn, const float* mx, 
     return tmin;
 }
 __device__ __forceinline__ V3 r2l_mul(const float* m, V3 p) {   // Eigen Matrix3f * Vector3f
+    // identity (the only value reachable without a custom snapshot): x*1 + (y*0 + z*0) == x exactly for finite inputs
+    if (m[0] == 1.f && m[4] == 1.f && m[8] == 1.f && m[1] == 0.f && m[2] == 0.f && m[3] == 0.f && m[5] == 0.f && m[6] == 0.f && m[7] == 0.f) return p;
     return v3(m[0] * p.x + (m[1] * p.y + m[2] * p.z), m[3] * p.x + (m[4] * p.y + m[5] * p.z), m[6] * p.x + (m[7] * p.y + m[8] * p.z));
 }
 
@@ -246,8 +250,11 @@ __device__ __forceinline__ bool advance_pos(const FrameParams& P, const uint8_t*
 // Returns 1 with the sample (warped position, warped dt) and t advanced past it, or 0 when the ray produced no sample
 // (left the box, or reached an opaque mesh surface, in which case t is snapped to t_surface).
 struct Sample { V3 pos; float dt_warped; float t; uint32_t cell, mip; };
+// Returns 1 with the sample and t advanced past it; 0 when the ray produced no sample (left the box, or reached an opaque
+// mesh surface, in which case t is snapped to t_surface); 2 when `budget` voxel tests were spent in empty space without
+// either outcome - t_io then holds the walk's state and the same call resumes it (the walk is a pure function of t).
 __device__ __forceinline__ int next_sample(const FrameParams& P, const uint8_t* __restrict__ bitfield, V3 origin, V3 dir, V3 idir,
-                                           float t_start, float t_surface, float surf_w, bool ignore_surface, float& t_io, Sample& s) {
+                                        float t_start, float t_surface, float surf_w, bool ignore_surface, int budget, float& t_io, Sample& s) {
     const float cone = P.cone_angle;
     float t = t_io;
     V3 pos; float dt; uint32_t mip, cell;
@@ -259,6 +266,7 @@ __device__ __forceinline__ int next_sample(const FrameParams& P, const uint8_t* 
         mip = (uint32_t)mip_from_dt(dt, pos);
         if (occupied_at(pos, bitfield, mip, &cell)) break;
         t = advance_to_next_voxel(t, cone, pos, dir, idir, NERF_GRIDSIZE >> mip);
+        if (--budget <= 0) { t_io = t; return 2; }
     }
     const V3 diag = v3(P.taabb_max[0] - P.taabb_min[0], P.taabb_max[1] - P.taabb_min[1], P.taabb_max[2] - P.taabb_min[2]);
     s.pos = v3((pos.x - P.taabb_min[0]) / diag.x, (pos.y - P.taabb_min[1]) / diag.y, (pos.z - P.taabb_min[2]) / diag.z);
@@ -269,15 +277,8 @@ __device__ __forceinline__ int next_sample(const FrameParams& P, const uint8_t* 
 }
 
 // ---- multiresolution hash-grid encoding (T/.../encodings/grid.h:111-186, 219-349) ------------------------------
-template <int HASH>
-__device__ __forceinline__ uint32_t grid_hash(uint32_t x, uint32_t y, uint32_t z) {
-    if (HASH == 0) return (x * 1958374283u) ^ (y * 2654435761u) ^ (z * 805459861u);
-    if (HASH == 2) return (x * 2165219737u) ^ (y * 1434869437u) ^ (z * 2097192037u);
-    return x ^ (y * 2654435761u) ^ (z * 805459861u);
-}
-
 // One level: eight half2 gathers, trilinear blend accumulated IN FP16 in corner order 0..7 (grid.h:317-343).
-template <int HASH>
+// Hash = x*p0 ^ y*p1 ^ z*p2 with the multipliers of the snapshot's hash type (prime_hash / reversed_prime_hash).
 __device__ __forceinline__ __half2 encode_level(const DeviceModel& M, int level, V3 p01) {
     const float scale = M.level_scale[level];
     const uint32_t size = M.level_size[level];
@@ -287,23 +288,27 @@ __device__ __forceinline__ __half2 encode_level(const DeviceModel& M, int level,
     const uint32_t gx = (uint32_t)(int)flx, gy = (uint32_t)(int)fly, gz = (uint32_t)(int)flz;
     const float wx1 = fx - flx, wy1 = fy - fly, wz1 = fz - flz;
     const float wx0 = 1 - wx1, wy0 = 1 - wy1, wz0 = 1 - wz1;
-    const bool dense = (M.dense_mask >> level) & 1u;
     uint32_t index[8];
-    if (dense) {
+    if ((M.dense_mask >> level) & 1u) {
         const uint32_t sy = M.stride_y[level], sz = M.stride_z[level];
+        const uint32_t y0 = gy * sy, z0 = gz * sz;
+        const bool pow2 = (M.pow2_mask >> level) & 1u;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            const uint32_t x = gx + (c & 1), y = gy + ((c >> 1) & 1), z = gz + ((c >> 2) & 1);
-            uint32_t i = x + y * sy + z * sz;
-            if (i >= size) i %= size;          // only the wrap-around cells at the upper faces take this branch
+            uint32_t i = (gx + (c & 1)) + (y0 + ((c >> 1) & 1) * sy) + (z0 + ((c >> 2) & 1) * sz);
+            // index % size.  A dense level holds >= res^3 entries and coordinates never exceed res, so i < 2 * size and one
+            // conditional subtraction is the exact modulo; the one exception is the uint32-wrapped stride quirk of
+            // res = 2048 levels (grid.h:164-186), whose size is a power of two.
+            if (pow2) i &= size - 1u; else if (i >= size) i -= size;
             index[c] = i;
         }
     } else {
+        const uint32_t p0 = M.prime[0], p1 = M.prime[1], p2 = M.prime[2];
+        const uint32_t hx = gx * p0, hy = gy * p1, hz = gz * p2;
+        const uint32_t mask = size - 1u;       // a hashed level always has exactly 2^log2_hashmap_size entries
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const uint32_t x = gx + (c & 1), y = gy + ((c >> 1) & 1), z = gz + ((c >> 2) & 1);
-            index[c] = grid_hash<HASH>(x, y, z) & (size - 1u);   // a hashed level always has exactly 2^log2_hashmap_size entries
-        }
+        for (int c = 0; c < 8; ++c)
+            index[c] = ((hx + (c & 1) * p0) ^ (hy + ((c >> 1) & 1) * p1) ^ (hz + ((c >> 2) & 1) * p2)) & mask;
     }
     __half2 v[8];
 #pragma unroll
@@ -319,26 +324,22 @@ __device__ __forceinline__ __half2 encode_level(const DeviceModel& M, int level,
     return acc;
 }
 
-// All 16 levels of one sample, written as four 16-byte chunks (levels 4c..4c+3 -> features 8c..8c+7) at
-// dst + c * chunk_stride.  The chunk loop stays rolled (instruction-cache footprint), the four levels inside a chunk
-// are unrolled so 32 gathers are in flight per thread.
-template <int HASH>
-__device__ __forceinline__ void encode_chunks_t(const DeviceModel& M, V3 p01, char* dst, int chunk_stride) {
-#pragma unroll 1
-    for (int c = 0; c < N_LEVELS / 4; ++c) {
-        __half2 e[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) e[j] = encode_level<HASH>(M, 4 * c + j, p01);
-        uint4 v;
-        v.x = *reinterpret_cast<const uint32_t*>(&e[0]); v.y = *reinterpret_cast<const uint32_t*>(&e[1]);
-        v.z = *reinterpret_cast<const uint32_t*>(&e[2]); v.w = *reinterpret_cast<const uint32_t*>(&e[3]);
-        *reinterpret_cast<uint4*>(dst + (size_t)c * chunk_stride) = v;
-    }
-}
+// All 16 levels of one sample.  Features (2l, 2l+1) of level l go to dst + (l / 4) * chunk_stride + (l % 4) * 4, i.e. four
+// 16-byte chunks of 8 features.  UNROLL levels are kept in flight per thread (8 * UNROLL gathers); the loop itself stays
+// rolled so the kernel fits the instruction cache.
+template <int UNROLL>
 __device__ __forceinline__ void encode_chunks(const DeviceModel& M, V3 p01, char* dst, int chunk_stride) {
-    if (M.hash_type == 1) encode_chunks_t<1>(M, p01, dst, chunk_stride);
-    else if (M.hash_type == 0) encode_chunks_t<0>(M, p01, dst, chunk_stride);
-    else encode_chunks_t<2>(M, p01, dst, chunk_stride);
+#pragma unroll 1
+    for (int l0 = 0; l0 < N_LEVELS; l0 += UNROLL) {
+        __half2 e[UNROLL];
+#pragma unroll
+        for (int j = 0; j < UNROLL; ++j) e[j] = encode_level(M, l0 + j, p01);
+#pragma unroll
+        for (int j = 0; j < UNROLL; ++j) {
+            const int l = l0 + j;
+            *reinterpret_cast<__half2*>(dst + (size_t)(l >> 2) * chunk_stride + (l & 3) * 4) = e[j];
+        }
+    }
 }
 
 // ---- SH degree 4 (T/.../encodings/spherical_harmonics.h:65-98) -------------------------------------------------
@@ -362,8 +363,11 @@ __device__ __forceinline__ float act_density(float v, int a) {
 __device__ __forceinline__ float act_rgb(float v, int a) {
     switch (a) { case 0: return v; case 1: return v > 0.f ? v : 0.f; case 2: return 1.0f / (1.0f + __expf(-v)); default: return __expf(clampf(v, -10.f, 10.f)); }
 }
-__device__ __forceinline__ float linear_to_srgb(float l) { return l < 0.0031308f ? 12.92f * l : 1.055f * powf(l, 0.41666f) - 0.055f; }
-__device__ __forceinline__ float srgb_to_linear(float s) { return s <= 0.04045f ? s / 12.92f : powf((s + 0.055f) / 1.055f, 2.4f); }
+// x^y for x > 0 through the SFU (ex2.approx(y * lg2.approx(x))): relative error ~1e-6, three orders of magnitude below the
+// 2/255 pixel tolerance; the accurate powf expands to ~100 instructions per call and there are six calls per pixel.
+__device__ __forceinline__ float fast_pow(float x, float y) { return exp2f(y * __log2f(x)); }
+__device__ __forceinline__ float linear_to_srgb(float l) { return l < 0.0031308f ? 12.92f * l : 1.055f * fast_pow(l, 0.41666f) - 0.055f; }
+__device__ __forceinline__ float srgb_to_linear(float s) { return s <= 0.04045f ? s / 12.92f : fast_pow((s + 0.055f) / 1.055f, 2.4f); }
 
 // ---- mesh stage: Moeller-Trumbore with back-face culling + the reference's PBR shading ------------------------
 // (S/optix/optix_scene.cu:71-85, 182-325; OptiX's own triangle test is not available: see DESIGN.md)

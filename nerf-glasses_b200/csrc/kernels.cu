@@ -195,9 +195,9 @@ __device__ __forceinline__ void finish_pixel(const FrameParams& P, const FrameOu
     }
     out.accum[idx] = acc;
     const float w = (1 - acc.w) * P.background[3];
-    float cr = acc.x + srgb_to_linear(P.background[0]) * w;
-    float cg = acc.y + srgb_to_linear(P.background[1]) * w;
-    float cb = acc.z + srgb_to_linear(P.background[2]) * w;
+    float cr = acc.x + P.background_linear[0] * w;
+    float cg = acc.y + P.background_linear[1] * w;
+    float cb = acc.z + P.background_linear[2] * w;
     float ca = acc.w + w;
     if (P.to_srgb) {
         cr = fminf(fmaxf(linear_to_srgb(cr), 0.f), 1.f); cg = fminf(fmaxf(linear_to_srgb(cg), 0.f), 1.f);
@@ -310,23 +310,30 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //   enc(32) -> 64 ReLU -> 16 ; [16 | SH16] -> 64 ReLU -> 64 ReLU -> 16 (3 used); density = channel 0 of the first net.
 // Layer semantics of T/src/fully_fused_mlp.cu:499-557: y = act(W x), fp16 activations between layers.
 // =================================================================================================================
-constexpr int kTile = 128;
+constexpr int kTile = 128;          // samples per MMA tile = threads per warpgroup
+constexpr int kGroupsTC = 2;        // warpgroups per CTA on the tensor path (they share the weights in shared memory)
 // weight matrices in params order: [out][in] row-major halves
 constexpr int kWD0 = 0, kWD1 = kWD0 + 64 * 32, kWR0 = kWD1 + 16 * 64, kWR1 = kWR0 + 64 * 32, kWR2 = kWR1 + 64 * 64, kWTotal = kWR2 + 16 * 64;   // 10240 halves
 
-struct __align__(128) MarchSmem {
-    __half w[kWTotal];            // 20480 B - tensor path: canonical K-major core-matrix layout; scalar path: plain row-major
-    __half act[kTile * 64];       // 16384 B - tensor path: A operand, chunk-major (k/8)*2048 + row*16; scalar path: row-major 64 halves per thread
-    __half act2[kTile * 64];      // 16384 B - scalar path only (second activation buffer)
-    uint64_t mbar;
-    uint32_t tmem_base;
+struct __align__(128) MarchSmem {   // CUDA-core path, one 128-thread group per CTA
+    __half w[kWTotal];            // plain row-major weights
+    __half act[kTile * 64];       // row-major, 64 halves per thread
+    __half act2[kTile * 64];
 };
 struct __align__(128) MarchSmemTC {
-    __half w[kWTotal];
-    __half act[kTile * 64];
-    uint64_t mbar;
+    __half w[kWTotal];                    // 20480 B, canonical K-major core-matrix layout, shared by the warpgroups
+    __half act[kGroupsTC][kTile * 64];    // 2 x 16384 B, A operands: chunk-major (k/8)*2048 + row*16
+    uint64_t mbar[kGroupsTC];
     uint32_t tmem_base;
 };
+
+// ---- warpgroup-scoped barriers (named barriers 1..kGroupsTC, 128 threads each) -----------------------------------
+__device__ __forceinline__ void group_sync(uint32_t bar_id) { asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory"); }
+__device__ __forceinline__ bool group_any(uint32_t bar_id, bool pred) {
+    uint32_t r;
+    asm volatile("{\n .reg .pred p, q;\n setp.ne.u32 p, %1, 0;\n bar.red.or.pred q, %2, 128, p;\n selp.u32 %0, 1, 0, q;\n}" : "=r"(r) : "r"((uint32_t)pred), "r"(bar_id) : "memory");
+    return r != 0;
+}
 
 // ---- CUDA-core variant (bring-up / bisecting aid, selected with NMR_MLP=scalar): fp32 accumulation in k order ----
 __device__ __forceinline__ void scalar_layer(const __half* __restrict__ W, int n_out, int n_in, const __half* __restrict__ x_row, __half* __restrict__ y_row, bool relu) {
@@ -360,10 +367,10 @@ __device__ __forceinline__ void network_scalar(MarchSmem& S, V3 dir01, float raw
 // smem operand layouts (K-major, SWIZZLE_NONE canonical layout, 16-byte "chunks" of 8 halves):
 //   A (activations, M = 128 rows):  byte(row, k) = (k/8)*2048 + row*16 + (k%8)*2      LBO = 2048, SBO = 128
 //   B (weights, N rows = outputs):  byte(n,   k) = (k/8)*(N*16) + n*16 + (k%8)*2      LBO = N*16, SBO = 128
-// Thread r owns row r of A and lane r of the accumulator in tensor memory, so every hand-off is thread-private:
-// tcgen05.ld 32x32b (lane = thread) -> ReLU/convert in registers -> st.shared of its own row (conflict-free, 512 B per warp store).
+// Thread r of a warpgroup owns row r of its A tile and lane r of its accumulator in tensor memory, so every hand-off is
+// thread-private: tcgen05.ld 32x32b (lane = thread) -> ReLU/convert in registers -> st.shared of its own row
+// (conflict-free, 512 B per warp store).
 __device__ __forceinline__ void stage_weights_tc(__half* sw, const __half* __restrict__ gw) {
-    // (matrix offset, N, K) for the five layers
     const int off[5] = {kWD0, kWD1, kWR0, kWR1, kWR2};
     const int Ns[5] = {64, 16, 64, 64, 16};
     const int Ks[5] = {32, 64, 32, 64, 64};
@@ -379,11 +386,13 @@ __device__ __forceinline__ void stage_weights_tc(__half* sw, const __half* __res
 }
 
 struct TcCtx {
-    uint32_t tmem;        // base address of this CTA's 64 accumulator columns
-    uint32_t a_addr;      // smem address of the A operand
+    uint32_t tmem;        // base address of this warpgroup's 64 accumulator columns
+    uint32_t a_addr;      // smem address of this warpgroup's A operand
     uint32_t w_addr;      // smem address of the weights
     uint64_t* mbar;
     uint32_t phase;
+    uint32_t bar_id;      // named barrier of the warpgroup
+    uint32_t row;         // thread index inside the warpgroup = tile row = accumulator lane
     bool swap;
 };
 
@@ -407,9 +416,19 @@ __device__ __forceinline__ uint32_t pack_relu_h2(uint32_t a, uint32_t b, bool re
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+// one layer's barrier / issue / wait sequence: the warpgroup's rows are in shared memory -> accumulator is ready
+__device__ __forceinline__ void tc_run_layer(TcCtx& c, int w_off_halves, uint32_t N, uint32_t K) {
+    fence_proxy_async();          // generic-proxy st.shared -> visible to the tensor core's async proxy
+    tc_fence_before();
+    group_sync(c.bar_id);
+    if (c.row == 0) { tc_fence_after(); tc_issue_layer(c, w_off_halves, N, K); }
+    mbar_wait(c.mbar, c.phase); c.phase ^= 1u;
+    tc_fence_after();
+}
+
 // accumulator columns [0, 64) of this thread's lane -> ReLU -> fp16 -> own row of A (8 chunks)
 __device__ __forceinline__ void tc_hidden_to_smem(const TcCtx& c, char* a_row_base) {
-    const uint32_t lane_addr = c.tmem + ((uint32_t)(threadIdx.x & ~31u) << 16);
+    const uint32_t lane_addr = c.tmem + ((c.row & ~31u) << 16);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         uint32_t v[16];
@@ -423,26 +442,14 @@ __device__ __forceinline__ void tc_hidden_to_smem(const TcCtx& c, char* a_row_ba
     }
 }
 
-// block-wide: every thread must call (idle threads leave stale rows - rows are independent in the GEMMs).
+// warpgroup-wide: all 128 threads must call (idle threads leave stale rows - rows are independent in the GEMMs).
 // The caller has written the encoded features to chunks 0..3 of its row of A (encode_chunks with stride 2048).
-__device__ __forceinline__ void network_tc(MarchSmemTC& S, TcCtx& c, V3 dir01, float raw[4]) {
-    char* a_row = reinterpret_cast<char*>(S.act) + threadIdx.x * 16;
-    // ---- density layer 0: A = enc (K = 32)
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    if (threadIdx.x == 0) { tc_fence_after(); tc_issue_layer(c, kWD0, 64, 32); }
-    mbar_wait(c.mbar, c.phase); c.phase ^= 1u;
-    tc_fence_after();
+__device__ __forceinline__ void network_tc(char* a_row, TcCtx& c, V3 dir01, float raw[4]) {
+    // ---- density net: enc(32) -> 64 ReLU -> 16
+    tc_run_layer(c, kWD0, 64, 32);
     tc_hidden_to_smem(c, a_row);
-    // ---- density layer 1 (K = 64, N = 16)
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    if (threadIdx.x == 0) { tc_fence_after(); tc_issue_layer(c, kWD1, 16, 64); }
-    mbar_wait(c.mbar, c.phase); c.phase ^= 1u;
-    tc_fence_after();
-    const uint32_t lane_addr = c.tmem + ((uint32_t)(threadIdx.x & ~31u) << 16);
+    tc_run_layer(c, kWD1, 16, 64);
+    const uint32_t lane_addr = c.tmem + ((c.row & ~31u) << 16);
     {
         uint32_t v[16];
         tmem_ld16(lane_addr, v);
@@ -451,7 +458,7 @@ __device__ __forceinline__ void network_tc(MarchSmemTC& S, TcCtx& c, V3 dir01, f
         lo.x = pack_relu_h2(v[0], v[1], false); lo.y = pack_relu_h2(v[2], v[3], false); lo.z = pack_relu_h2(v[4], v[5], false); lo.w = pack_relu_h2(v[6], v[7], false);
         hi.x = pack_relu_h2(v[8], v[9], false); hi.y = pack_relu_h2(v[10], v[11], false); hi.z = pack_relu_h2(v[12], v[13], false); hi.w = pack_relu_h2(v[14], v[15], false);
         raw[3] = __low2float(*reinterpret_cast<const __half2*>(&lo.x));   // density = fp16(channel 0), extract_density
-        *reinterpret_cast<uint4*>(a_row + 0 * 2048) = lo;
+        *reinterpret_cast<uint4*>(a_row + 0 * 2048) = lo;                 // rgb net input = [density net out (16) | SH (16)]
         *reinterpret_cast<uint4*>(a_row + 1 * 2048) = hi;
         __half2 sh[8];
         sh4(dir01, sh);
@@ -461,29 +468,12 @@ __device__ __forceinline__ void network_tc(MarchSmemTC& S, TcCtx& c, V3 dir01, f
         *reinterpret_cast<uint4*>(a_row + 2 * 2048) = s0;
         *reinterpret_cast<uint4*>(a_row + 3 * 2048) = s1;
     }
-    // ---- rgb layer 0 (K = 32)
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    if (threadIdx.x == 0) { tc_fence_after(); tc_issue_layer(c, kWR0, 64, 32); }
-    mbar_wait(c.mbar, c.phase); c.phase ^= 1u;
-    tc_fence_after();
+    // ---- rgb net: 32 -> 64 ReLU -> 64 ReLU -> 16 (three channels used)
+    tc_run_layer(c, kWR0, 64, 32);
     tc_hidden_to_smem(c, a_row);
-    // ---- rgb layer 1 (K = 64)
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    if (threadIdx.x == 0) { tc_fence_after(); tc_issue_layer(c, kWR1, 64, 64); }
-    mbar_wait(c.mbar, c.phase); c.phase ^= 1u;
-    tc_fence_after();
+    tc_run_layer(c, kWR1, 64, 64);
     tc_hidden_to_smem(c, a_row);
-    // ---- rgb output layer (K = 64, N = 16, three channels used)
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    if (threadIdx.x == 0) { tc_fence_after(); tc_issue_layer(c, kWR2, 16, 64); }
-    mbar_wait(c.mbar, c.phase); c.phase ^= 1u;
-    tc_fence_after();
+    tc_run_layer(c, kWR2, 16, 64);
     {
         uint32_t v[4];
         tmem_ld4(lane_addr, v);
@@ -492,133 +482,233 @@ __device__ __forceinline__ void network_tc(MarchSmemTC& S, TcCtx& c, V3 dir01, f
         raw[1] = __half2float(__float2half_rn(__uint_as_float(v[1])));
         raw[2] = __half2float(__float2half_rn(__uint_as_float(v[2])));
     }
-    tc_fence_before();   // the next tile's first MMA overwrites these accumulator columns after the next __syncthreads
+    tc_fence_before();   // the next tile's first MMA overwrites these accumulator columns after the next group barrier
+}
+
+// CTA prologue of the tensor path: TMEM allocation (64 columns per warpgroup), mbarriers, weights -> smem
+__device__ __forceinline__ TcCtx tc_setup(MarchSmemTC& S, const DeviceModel& M, uint32_t debug_flags) {
+    if (threadIdx.x < 32) tmem_alloc(&S.tmem_base, 64 * kGroupsTC);
+    if (threadIdx.x == 0) { for (int g = 0; g < kGroupsTC; ++g) mbar_init(&S.mbar[g], 1); fence_barrier_init(); }
+    stage_weights_tc(S.w, M.mlp);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t g = threadIdx.x / kTile;
+    TcCtx c;
+    c.tmem = S.tmem_base + g * 64; c.a_addr = smem_u32(S.act[g]); c.w_addr = smem_u32(S.w); c.mbar = &S.mbar[g]; c.phase = 0;
+    c.bar_id = 1 + g; c.row = threadIdx.x % kTile; c.swap = (debug_flags & kDebugSwapLboSbo) != 0;
+    return c;
+}
+__device__ __forceinline__ void tc_teardown(MarchSmemTC& S) {
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(S.tmem_base, 64 * kGroupsTC);
 }
 
 // =================================================================================================================
 // march_kernel
 // NerfTracer::trace's wavefront loop (S/ngp/testbed.cu:1938-2053) collapsed into one persistent kernel:
-// generate_next_nerf_network_inputs (n_steps = 1) -> network -> composite_kernel_nerf -> shade/accumulate/tonemap.
+// generate_next_nerf_network_inputs -> network -> composite_kernel_nerf -> shade/accumulate/tonemap.
+//
+// Work layout: kRayLanes = 8 adjacent lanes form a RAY GROUP.  Each iteration the group generates the next 8 occupied
+// samples of its ray (lane j keeps sample j), the 128 threads of a warpgroup evaluate their 128 samples as one network
+// tile, and the group composites its (up to) 8 results strictly in order with the reference's per-sample rule, so pixels
+// do not depend on the batching (the reference itself batches 1..8 samples per ray per iteration, S/ngp/testbed.cu:1996).
+// Samples generated past a ray's termination are discarded, exactly like the reference's n_steps batches.
+// Consecutive samples of one ray sit in adjacent lanes, so their hash-grid gathers share cache lines on the coarse and
+// middle levels; all per-ray state is replicated in the 8 lanes (same arithmetic in every lane), so no state is exchanged.
+// Groups pull new rays from the queue when their ray ends; tiles stay full until the queue drains.
 // =================================================================================================================
+constexpr int kRayLanes = 8;
+#ifndef NMR_ENCODE_UNROLL
+#define NMR_ENCODE_UNROLL 2
+#endif
+constexpr int kEncodeUnroll = NMR_ENCODE_UNROLL;   // hash-grid levels in flight per thread (8 gathers each)
+constexpr int kWalkBudget = 6;      // empty voxels a ray may skip per tile iteration before it sits the iteration out
+
 template <bool TC>
-__global__ void __launch_bounds__(kTile, TC ? 4 : 2) march_kernel(FrameParams P, DeviceModel M, const float4* __restrict__ queue, uint32_t* __restrict__ counters,
-                                                                    FrameOut out, uint32_t debug_flags) {
+__global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? 3 : 2) march_kernel(FrameParams P, DeviceModel M, const float4* __restrict__ queue,
+                                                                                          uint32_t* __restrict__ counters, FrameOut out, uint32_t debug_flags) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     using Smem = typename std::conditional<TC, MarchSmemTC, MarchSmem>::type;
     Smem& S = *reinterpret_cast<Smem*>(smem_raw);
 
     const uint32_t n_rays = counters[0];
     TcCtx tc;
+    char* a_row;
+    int enc_stride;
     if (TC) {
-        if (threadIdx.x < 32) tmem_alloc(&S.tmem_base, 64);
-        if (threadIdx.x == 0) { mbar_init(&S.mbar, 1); fence_barrier_init(); }
-        stage_weights_tc(S.w, M.mlp);
-        fence_proxy_async();
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-        tc.tmem = S.tmem_base; tc.a_addr = smem_u32(S.act); tc.w_addr = smem_u32(S.w); tc.mbar = &S.mbar; tc.phase = 0; tc.swap = (debug_flags & kDebugSwapLboSbo) != 0;
+        MarchSmemTC& T = reinterpret_cast<MarchSmemTC&>(S);
+        tc = tc_setup(T, M, debug_flags);
+        a_row = reinterpret_cast<char*>(T.act[threadIdx.x / kTile]) + tc.row * 16;
+        enc_stride = 2048;
     } else {
-        for (int i = threadIdx.x; i < kWTotal / 8; i += blockDim.x) reinterpret_cast<uint4*>(S.w)[i] = __ldg(reinterpret_cast<const uint4*>(M.mlp) + i);
+        MarchSmem& T = reinterpret_cast<MarchSmem&>(S);
+        for (int i = threadIdx.x; i < kWTotal / 8; i += blockDim.x) reinterpret_cast<uint4*>(T.w)[i] = __ldg(reinterpret_cast<const uint4*>(M.mlp) + i);
         __syncthreads();
+        a_row = reinterpret_cast<char*>(T.act) + threadIdx.x * 128;
+        enc_stride = 16;
     }
 
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t sub = lane & (kRayLanes - 1);             // which of the group's samples this lane evaluates
+    const uint32_t gbase = lane & ~(uint32_t)(kRayLanes - 1);
+    const uint32_t gmask = ((1u << kRayLanes) - 1u) << gbase;
     const V3 origin = v3(P.cam[9] + 0.5f, P.cam[10] + 0.5f, P.cam[11] + 0.5f);
-    const V3 cam_origin = v3(P.cam[9], P.cam[10], P.cam[11]);
-    const V3 tdiag = v3(P.taabb_max[0] - P.taabb_min[0], P.taabb_max[1] - P.taabb_min[1], P.taabb_max[2] - P.taabb_min[2]);
 
-    // per-ray state (one ray slot per thread)
-    bool active = false, exhausted = false;
-    V3 dir = v3(0.f, 0.f, 1.f), idir = v3(0.f, 0.f, 1.f), dir01 = v3(0.5f, 0.5f, 1.f);
+    // per-ray state, identical in the 8 lanes of a group
+    bool active = false, exhausted = false, pending_finish = false;
+    V3 dir = v3(0.f, 0.f, 1.f);
     float t = 0.f, t_start = 0.f, t_surface = 0.f, max_weight = 0.f, depth = 0.f;
     float sr = 0.f, sg = 0.f, sb = 0.f, sw = 0.f;        // surface colour (mesh hand-off)
     float cr = 0.f, cg = 0.f, cb = 0.f, ca = 0.f;        // accumulated colour
-    uint32_t idx = 0, n_samples = 0;
-    unsigned long long total_samples = 0;
+    uint32_t idx = 0, n_samples = 0, evaluated = 0, n_batches = 0, n_passes = 0;
 
     while (true) {
-        // ---- 1. every slot gets a sample, pulling new rays from the queue as rays end ----
-        Sample smp;
-        bool have = false;
-        while (!have) {
+        // ---- 1. next batch of up to 8 samples for this group's ray, pulling a new ray when the current one has ended ----
+        V3 my_pos = v3(0.f, 0.f, 0.f);
+        float my_dtw = 0.f, my_t_after = 0.f, t_batch_end = t;
+        uint32_t n_valid = 0;
+        bool paused = false;
+        while (true) {
+            if (pending_finish) {
+                // composite_kernel_nerf's tail for a finished ray (S/ngp/testbed.cu:886-901), then shade/accumulate/tonemap
+                if (sw > 0) { const float k = 1.f - ca; cr += sr * k; cg += sg * k; cb += sb * k; ca += sw * k; }
+                if (sub == 0) finish_pixel(P, out, idx, cr, cg, cb, ca, depth, n_samples);
+                active = false; pending_finish = false;
+            }
             if (!active) {
                 if (exhausted) break;
-                const uint32_t slot = atomicAdd(&counters[1], 1u);
+                uint32_t slot = 0;
+                if (sub == 0) slot = atomicAdd(&counters[1], 1u);
+                slot = __shfl_sync(gmask, slot, gbase);
                 if (slot >= n_rays) { exhausted = true; break; }
                 const float4 q0 = __ldg(queue + (size_t)slot * kRayRecordFloat4s), q1 = __ldg(queue + (size_t)slot * kRayRecordFloat4s + 1), q2 = __ldg(queue + (size_t)slot * kRayRecordFloat4s + 2);
                 dir = v3(q0.x, q0.y, q0.z); t = q0.w; t_start = q1.x; t_surface = q1.y; idx = __float_as_uint(q1.z);
                 sr = q2.x; sg = q2.y; sb = q2.z; sw = q2.w;
-                idir = v3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
-                dir01 = v3((dir.x + 1.0f) * 0.5f, (dir.y + 1.0f) * 0.5f, (dir.z + 1.0f) * 0.5f);   // warp_direction
                 cr = cg = cb = ca = 0.f; max_weight = 0.f; depth = 0.f; n_samples = 0;
                 active = true;
             }
-            if (next_sample(P, M.bitfield, origin, dir, idir, t_start, t_surface, sw, false, t, smp)) {
-                have = true;
-            } else {
-                // composite_kernel_nerf's tail for a ray whose batch came back empty (S/ngp/testbed.cu:886-901)
-                if (sw > 0) { const float k = 1.f - ca; cr += sr * k; cg += sg * k; cb += sb * k; ca += sw * k; }
-                finish_pixel(P, out, idx, cr, cg, cb, ca, depth, n_samples);
-                active = false;
+            const V3 idir = v3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
+            // Batch generation.  The reference walks samples one after the other (S/ngp/testbed.cu:596-629); inside an object
+            // nearly every step lands in an occupied cell, so the 8 lanes first test 8 consecutive steps IN PARALLEL (lane j
+            // replays the t += dt recurrence j times - same float operations, no memory access - and then does the one
+            // occupancy load of its own sample).  The accepted prefix is exactly what the sequential walk produces; at the
+            // first step that is not a plain "occupied, inside, not behind the mesh" step the group falls back to the
+            // sequential rule for that one sample and then tries the parallel test again.
+            float tt = t;
+            n_valid = 0;
+            paused = false;
+#pragma unroll 1
+            while (n_valid < (uint32_t)kRayLanes) {
+                ++n_passes;
+                float tc = tt, dtc = 0.f;
+                V3 pc = v3(0.f, 0.f, 0.f);
+                bool ok = sub >= n_valid;
+                if (ok) {
+                    for (uint32_t k = n_valid; k < sub; ++k) tc += calc_dt(tc - t_start, P.cone_angle);
+                    ok = !(t_surface != 0.0f && tc > t_surface && sw == 1.f);
+                    pc = vadd(origin, vmul(dir, tc));
+                    ok = ok && box_contains(P.aabb_min, P.aabb_max, r2l_mul(P.r2l, pc));
+                    if (ok) {
+                        dtc = calc_dt(tc - t_start, P.cone_angle);
+                        ok = occupied_at(pc, M.bitfield, (uint32_t)mip_from_dt(dtc, pc));
+                    }
+                }
+                const uint32_t fail = (__ballot_sync(gmask, !ok) >> gbase) & ~((1u << n_valid) - 1u) & ((1u << kRayLanes) - 1u);
+                const uint32_t first_fail = fail ? (uint32_t)(__ffs((int)fail) - 1) : (uint32_t)kRayLanes;
+                if (sub >= n_valid && sub < first_fail) {
+                    const V3 diag = v3(P.taabb_max[0] - P.taabb_min[0], P.taabb_max[1] - P.taabb_min[1], P.taabb_max[2] - P.taabb_min[2]);
+                    my_pos = v3((pc.x - P.taabb_min[0]) / diag.x, (pc.y - P.taabb_min[1]) / diag.y, (pc.z - P.taabb_min[2]) / diag.z);
+                    my_dtw = warp_dt(dtc);
+                    my_t_after = tc + dtc;
+                }
+                if (first_fail > n_valid) {        // advance the ray past the accepted prefix
+                    tt = __shfl_sync(gmask, tc + dtc, gbase + first_fail - 1);
+                    n_valid = first_fail;
+                }
+                if (n_valid >= (uint32_t)kRayLanes) break;
+                // sample number n_valid needs the general rule (empty-space skip, box exit or opaque mesh surface).  A long walk
+                // through empty cells is cut into slices of kWalkBudget voxels so that one ray cannot stall its tile: a paused
+                // walk keeps its state in t and resumes in the next iteration.
+                Sample smp;
+                const int rc = next_sample(P, M.bitfield, origin, dir, idir, t_start, t_surface, sw, false, kWalkBudget, tt, smp);
+                if (rc != 1) { paused = rc == 2; break; }
+                if (sub == n_valid) { my_pos = smp.pos; my_dtw = smp.dt_warped; my_t_after = tt; }
+                ++n_valid;
             }
+            t_batch_end = tt;
+            if (n_valid > 0 || paused) break;
+            pending_finish = true;      // the batch came back empty: the ray has ended
         }
+        const bool have = active && !pending_finish && sub < n_valid;
+        if (have && sub == 0) ++n_batches;
 
         // ---- 2. encode straight into this thread's row of the A operand ----
-        if (have) {
-            if (TC) encode_chunks(M, smp.pos, reinterpret_cast<char*>(S.act) + threadIdx.x * 16, 2048);
-            else encode_chunks(M, smp.pos, reinterpret_cast<char*>(S.act) + threadIdx.x * 128, 16);
+        if (have) { encode_chunks<kEncodeUnroll>(M, my_pos, a_row, enc_stride); ++evaluated; }
+        // tile-wide decisions: run the network when any lane has a sample; leave only when no ray is left (a tile whose
+        // rays are all in the middle of a paused empty-space walk has no sample this iteration but must keep going)
+        const bool any_have = TC ? group_any(tc.bar_id, have) : (__syncthreads_or(have ? 1 : 0) != 0);
+        if (!any_have) {
+            const bool any_active = TC ? group_any(tc.bar_id, active) : (__syncthreads_or(active ? 1 : 0) != 0);
+            if (!any_active) break;
+            if (active && !pending_finish) t = t_batch_end;
+            continue;
         }
-        if (!__syncthreads_or(have ? 1 : 0)) break;
 
         // ---- 3. network ----
         float raw[4];
-        if (TC) network_tc(reinterpret_cast<MarchSmemTC&>(S), tc, dir01, raw);
+        const V3 dir01 = v3((dir.x + 1.0f) * 0.5f, (dir.y + 1.0f) * 0.5f, (dir.z + 1.0f) * 0.5f);   // warp_direction
+        if (TC) network_tc(a_row, tc, dir01, raw);
         else network_scalar(reinterpret_cast<MarchSmem&>(S), dir01, raw);
 
-        // ---- 4. composite this sample (S/ngp/testbed.cu:830-884 with n_steps = 1) ----
-        if (have) {
-            ++n_samples; ++total_samples;
+        // ---- 4. composite the batch in order (S/ngp/testbed.cu:830-884, one sample at a time) ----
+        if (active && !pending_finish) {
             bool done = false;
-            float T = 1.f - ca;
-            const float dt = unwarp_dt(smp.dt_warped);
-            if (t > t_surface && sw > 0) {
-                cr += sr * sw * T; cg += sg * sw * T; cb += sb * sw * T; ca += sw * T;
-                sw = 0.f;
-                T = 1.f - ca;
-                if (ca > 0.99f) { const float a = ca; cr /= a; cg /= a; cb /= a; ca /= a; done = true; }
-            }
-            if (!done) {
-                const float alpha = 1.f - __expf(-act_density(raw[3], P.density_activation) * dt);
+#pragma unroll 1
+            for (uint32_t j = 0; j < n_valid; ++j) {
+                const uint32_t src = gbase + j;
+                const float r0 = __shfl_sync(gmask, raw[0], src), r1 = __shfl_sync(gmask, raw[1], src), r2 = __shfl_sync(gmask, raw[2], src), r3 = __shfl_sync(gmask, raw[3], src);
+                const float dtw = __shfl_sync(gmask, my_dtw, src), t_after = __shfl_sync(gmask, my_t_after, src);
+                const float px = __shfl_sync(gmask, my_pos.x, src), py = __shfl_sync(gmask, my_pos.y, src), pz = __shfl_sync(gmask, my_pos.z, src);
+                ++n_samples;
+                float T = 1.f - ca;
+                const float dt = unwarp_dt(dtw);
+                if (t_after > t_surface && sw > 0) {
+                    cr += sr * sw * T; cg += sg * sw * T; cb += sb * sw * T; ca += sw * T;
+                    sw = 0.f;
+                    T = 1.f - ca;
+                    if (ca > 0.99f) { const float a = ca; cr /= a; cg /= a; cb /= a; ca /= a; done = true; break; }
+                }
+                const float alpha = 1.f - __expf(-act_density(r3, P.density_activation) * dt);
                 const float weight = alpha * T;
-                cr += act_rgb(raw[0], P.rgb_activation) * weight;
-                cg += act_rgb(raw[1], P.rgb_activation) * weight;
-                cb += act_rgb(raw[2], P.rgb_activation) * weight;
+                cr += act_rgb(r0, P.rgb_activation) * weight;
+                cg += act_rgb(r1, P.rgb_activation) * weight;
+                cb += act_rgb(r2, P.rgb_activation) * weight;
                 ca += weight;
                 if (weight > max_weight) {
                     max_weight = weight;
-                    const V3 pos = v3(P.taabb_min[0] + smp.pos.x * tdiag.x, P.taabb_min[1] + smp.pos.y * tdiag.y, P.taabb_min[2] + smp.pos.z * tdiag.z);
-                    const V3 dd = vsub(pos, cam_origin);
+                    const V3 tdiag = v3(P.taabb_max[0] - P.taabb_min[0], P.taabb_max[1] - P.taabb_min[1], P.taabb_max[2] - P.taabb_min[2]);
+                    const V3 pos = v3(P.taabb_min[0] + px * tdiag.x, P.taabb_min[1] + py * tdiag.y, P.taabb_min[2] + pz * tdiag.z);
+                    const V3 dd = vsub(pos, v3(P.cam[9], P.cam[10], P.cam[11]));   // NeRF-space sample vs world-space eye, as in the reference
                     depth = sqrtf(edot(dd, dd));
                 }
-                if (ca > (1.0f - P.min_transmittance)) { const float a = ca; cr /= a; cg /= a; cb /= a; ca /= a; done = true; }
+                if (ca > (1.0f - P.min_transmittance)) { const float a = ca; cr /= a; cg /= a; cb /= a; ca /= a; done = true; break; }
             }
-            if (done) {
-                if (sw > 0) { const float k = 1.f - ca; cr += sr * k; cg += sg * k; cb += sb * k; ca += sw * k; }
-                finish_pixel(P, out, idx, cr, cg, cb, ca, depth, n_samples);
-                active = false;
-            }
+            if (done) pending_finish = true;
+            else t = t_batch_end;      // also the resume point of a paused empty-space walk
         }
     }
 
-    // sample counter: one atomic per warp
-    for (int o = 16; o > 0; o >>= 1) total_samples += __shfl_xor_sync(0xffffffffu, total_samples, o);
-    if ((threadIdx.x & 31) == 0 && total_samples) atomicAdd(reinterpret_cast<unsigned long long*>(counters + 2), total_samples);
-    if (TC) {
-        tc_fence_before();
-        __syncthreads();
-        if (threadIdx.x < 32) tmem_dealloc(tc.tmem, 64);
-    }
+    // evaluated-sample counter: one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) evaluated += __shfl_xor_sync(0xffffffffu, evaluated, o);
+    if (lane == 0 && evaluated) atomicAdd(reinterpret_cast<unsigned long long*>(counters + 2), (unsigned long long)evaluated);
+    if (sub == 0 && n_batches) { atomicAdd(&counters[4], n_batches); atomicAdd(&counters[5], n_passes); }
+    if (TC) tc_teardown(reinterpret_cast<MarchSmemTC&>(S));
 }
+
+constexpr int kMarchCtasPerSm = 3;   // __launch_bounds__(256, 3): 24 warps, 3 x 128 tensor-memory columns, 3 x 53 KB shared memory per SM
 
 void launch_march(const FrameParams& P, const DeviceModel& M, const float4* d_queue, uint32_t* d_counters, const FrameOut& out,
                   uint32_t debug_flags, int num_sms, cudaStream_t s) {
@@ -629,7 +719,7 @@ void launch_march(const FrameParams& P, const DeviceModel& M, const float4* d_qu
     } else {
         static bool attr_set = false;
         if (!attr_set) { cudaFuncSetAttribute(march_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmemTC)); attr_set = true; }
-        march_kernel<true><<<num_sms * 4, kTile, sizeof(MarchSmemTC), s>>>(P, M, d_queue, d_counters, out, debug_flags);
+        march_kernel<true><<<num_sms * kMarchCtasPerSm, kTile * kGroupsTC, sizeof(MarchSmemTC), s>>>(P, M, d_queue, d_counters, out, debug_flags);
     }
 }
 
@@ -639,7 +729,7 @@ void launch_march(const FrameParams& P, const DeviceModel& M, const float4* d_qu
 __global__ void debug_encode_kernel(DeviceModel M, const float* __restrict__ pos, int64_t n, uint16_t* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    encode_chunks(M, v3(pos[i * 3], pos[i * 3 + 1], pos[i * 3 + 2]), reinterpret_cast<char*>(out + i * ENC_WIDTH), 16);
+    encode_chunks<2>(M, v3(pos[i * 3], pos[i * 3 + 1], pos[i * 3 + 2]), reinterpret_cast<char*>(out + i * ENC_WIDTH), 16);
 }
 void launch_debug_encode(const DeviceModel& M, const float* d_pos, int64_t n, uint16_t* d_out, cudaStream_t s) {
     if (n <= 0) return;
@@ -647,56 +737,55 @@ void launch_debug_encode(const DeviceModel& M, const float* d_pos, int64_t n, ui
 }
 
 template <bool TC>
-__global__ void __launch_bounds__(kTile) debug_network_kernel(DeviceModel M, const float* __restrict__ pos, const float* __restrict__ dir, int64_t n, uint16_t* __restrict__ out4, uint32_t debug_flags) {
+__global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile) debug_network_kernel(DeviceModel M, const float* __restrict__ pos, const float* __restrict__ dir, int64_t n, uint16_t* __restrict__ out4, uint32_t debug_flags) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     using Smem = typename std::conditional<TC, MarchSmemTC, MarchSmem>::type;
     Smem& S = *reinterpret_cast<Smem*>(smem_raw);
     TcCtx tc;
+    char* a_row;
+    int enc_stride;
     if (TC) {
-        if (threadIdx.x < 32) tmem_alloc(&S.tmem_base, 64);
-        if (threadIdx.x == 0) { mbar_init(&S.mbar, 1); fence_barrier_init(); }
-        stage_weights_tc(S.w, M.mlp);
-        fence_proxy_async();
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-        tc.tmem = S.tmem_base; tc.a_addr = smem_u32(S.act); tc.w_addr = smem_u32(S.w); tc.mbar = &S.mbar; tc.phase = 0; tc.swap = (debug_flags & kDebugSwapLboSbo) != 0;
+        MarchSmemTC& T = reinterpret_cast<MarchSmemTC&>(S);
+        tc = tc_setup(T, M, debug_flags);
+        a_row = reinterpret_cast<char*>(T.act[threadIdx.x / kTile]) + tc.row * 16;
+        enc_stride = 2048;
     } else {
-        for (int i = threadIdx.x; i < kWTotal / 8; i += blockDim.x) reinterpret_cast<uint4*>(S.w)[i] = __ldg(reinterpret_cast<const uint4*>(M.mlp) + i);
+        MarchSmem& T = reinterpret_cast<MarchSmem&>(S);
+        for (int i = threadIdx.x; i < kWTotal / 8; i += blockDim.x) reinterpret_cast<uint4*>(T.w)[i] = __ldg(reinterpret_cast<const uint4*>(M.mlp) + i);
         __syncthreads();
+        a_row = reinterpret_cast<char*>(T.act) + threadIdx.x * 128;
+        enc_stride = 16;
     }
-    for (int64_t base = (int64_t)blockIdx.x * kTile; base < n; base += (int64_t)gridDim.x * kTile) {
+    // every warpgroup walks the same number of tiles, so its barriers stay matched
+    const int64_t per_cta = blockDim.x;
+    for (int64_t base = (int64_t)blockIdx.x * per_cta; base < n; base += (int64_t)gridDim.x * per_cta) {
         const int64_t i = base + threadIdx.x;
         const bool have = i < n;
         V3 d01 = v3(0.5f, 0.5f, 0.5f);
         if (have) {
-            const V3 p = v3(pos[i * 3], pos[i * 3 + 1], pos[i * 3 + 2]);
-            if (TC) encode_chunks(M, p, reinterpret_cast<char*>(S.act) + threadIdx.x * 16, 2048);
-            else encode_chunks(M, p, reinterpret_cast<char*>(S.act) + threadIdx.x * 128, 16);
+            encode_chunks<2>(M, v3(pos[i * 3], pos[i * 3 + 1], pos[i * 3 + 2]), a_row, enc_stride);
             d01 = v3(dir[i * 3], dir[i * 3 + 1], dir[i * 3 + 2]);
         }
         float raw[4];
-        if (TC) network_tc(reinterpret_cast<MarchSmemTC&>(S), tc, d01, raw);
+        if (TC) network_tc(a_row, tc, d01, raw);
         else network_scalar(reinterpret_cast<MarchSmem&>(S), d01, raw);
         if (have) {
             for (int k = 0; k < 4; ++k) { const __half h = __float2half_rn(raw[k]); out4[i * 4 + k] = *reinterpret_cast<const uint16_t*>(&h); }
         }
     }
-    if (TC) {
-        tc_fence_before();
-        __syncthreads();
-        if (threadIdx.x < 32) tmem_dealloc(tc.tmem, 64);
-    }
+    if (TC) tc_teardown(reinterpret_cast<MarchSmemTC&>(S));
 }
 void launch_debug_network(const DeviceModel& M, const float* d_pos, const float* d_dir, int64_t n, uint16_t* d_out4, uint32_t debug_flags, cudaStream_t s) {
     if (n <= 0) return;
-    const unsigned blocks = (unsigned)((n + kTile - 1) / kTile < 592 ? (n + kTile - 1) / kTile : 592);
     if (debug_flags & kDebugScalarMlp) {
+        const unsigned blocks = (unsigned)((n + kTile - 1) / kTile < 296 ? (n + kTile - 1) / kTile : 296);
         cudaFuncSetAttribute(debug_network_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmem));
         debug_network_kernel<false><<<blocks, kTile, sizeof(MarchSmem), s>>>(M, d_pos, d_dir, n, d_out4, debug_flags);
     } else {
+        const int per = kTile * kGroupsTC;
+        const unsigned blocks = (unsigned)((n + per - 1) / per < 296 ? (n + per - 1) / per : 296);
         cudaFuncSetAttribute(debug_network_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmemTC));
-        debug_network_kernel<true><<<blocks, kTile, sizeof(MarchSmemTC), s>>>(M, d_pos, d_dir, n, d_out4, debug_flags);
+        debug_network_kernel<true><<<blocks, per, sizeof(MarchSmemTC), s>>>(M, d_pos, d_dir, n, d_out4, debug_flags);
     }
 }
 
@@ -716,7 +805,7 @@ __global__ void debug_trace_kernel(FrameParams P, DeviceModel M, const uint32_t*
     uint32_t cnt = 0;
     while (alive && cnt < max_samples) {
         Sample s;
-        if (!next_sample(P, M.bitfield, r.origin, r.dir, idir, t_start, 0.f, 0.f, true, t, s)) break;
+        if (next_sample(P, M.bitfield, r.origin, r.dir, idir, t_start, 0.f, 0.f, true, 0x7fffffff, t, s) != 1) break;
         const int64_t o = i * max_samples + cnt;
         o_t[o] = s.t; o_cell[o] = s.cell; o_mip[o] = s.mip;
         o_pos[o * 3] = s.pos.x; o_pos[o * 3 + 1] = s.pos.y; o_pos[o * 3 + 2] = s.pos.z;

@@ -20,18 +20,19 @@ from __future__ import annotations
 import ctypes as C
 import os
 import sys
+import weakref
 
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libnmr.so")
+LIB_PATH = os.environ.get("NMR_LIB") or os.path.join(os.path.dirname(_HERE), "libnmr.so")   # NMR_LIB: tuning builds
 
 NMR_OK = 0
 
 
 class Stats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("rays_alive", C.c_uint64), ("samples", C.c_uint64), ("mesh_rays", C.c_uint64),
-                ("kernel_launches", C.c_uint64), ("gpu_ms", C.c_float), ("march_ms", C.c_float)]
+                ("kernel_launches", C.c_uint64), ("gpu_ms", C.c_float), ("march_ms", C.c_float), ("batches", C.c_uint64), ("batch_passes", C.c_uint64)]
 
 
 _lib = None
@@ -114,24 +115,32 @@ def _ptr(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
 
 
-class _PinnedArray:
-    """numpy array over page-locked memory from nmr_host_alloc (fast, asynchronous device->host copies)."""
+_pinned_pool: dict = {}     # size in bytes -> [device-registered host pointers ready for reuse]
 
-    def __init__(self, shape, dtype=np.float32):
-        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
-        self._p = lib().nmr_host_alloc(n)
-        if not self._p:
-            raise MemoryError("nmr_host_alloc failed")
-        buf = (C.c_char * n).from_address(self._p)
-        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
 
-    def __del__(self):
-        try:
-            if getattr(self, "_p", None):
-                lib().nmr_host_free(self._p)
-                self._p = None
-        except Exception:
-            pass
+def _pinned_release(nbytes: int, p: int):
+    _pinned_pool.setdefault(nbytes, []).append(p)
+
+
+def _pinned_array(shape, dtype=np.float32) -> np.ndarray:
+    """numpy array over page-locked memory from nmr_host_alloc (fast, asynchronous device->host copies).
+    The ctypes buffer at the root of the array's .base chain owns the allocation; when the last view dies the block goes
+    back to a per-size pool (page-locking tens of MB costs milliseconds, so a render loop must not allocate per frame)."""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    free = _pinned_pool.get(n)
+    p = free.pop() if free else lib().nmr_host_alloc(n)
+    if not p:
+        raise MemoryError("nmr_host_alloc failed")
+    buf = (C.c_char * n).from_address(p)
+    weakref.finalize(buf, _pinned_release, n, p)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+
+def free_pinned_pool():
+    """Returns every pooled page-locked block to the driver."""
+    for blocks in _pinned_pool.values():
+        while blocks:
+            lib().nmr_host_free(blocks.pop())
 
 
 class Vec3:
@@ -302,25 +311,13 @@ class Testbed:
 
     def render(self, width: int = 1920, height: int = 1080, spp: int = 1, linear: bool = True) -> np.ndarray:
         """float32[H, W, 4]; row 0 is the bottom of the picture; sRGB when linear=False (S/python_api.cu:83-111)."""
-        out = _PinnedArray((height, width, 4))
-        self._r._ck(lib().nmr_render(self._r._h, self._id, int(width), int(height), int(spp), int(bool(linear)), _ptr(out.array)))
-        return _own(out)
+        out = _pinned_array((height, width, 4))
+        self._r._ck(lib().nmr_render(self._r._h, self._id, int(width), int(height), int(spp), int(bool(linear)), _ptr(out)))
+        return out
 
     def reset_accumulation(self, due_to_camera_movement: bool = False, immediate_redraw: bool = True):
         cam = self._r.view_projection_mat
         self._r.view_projection_mat = cam   # resets the sample counter
-
-
-def _own(pinned: _PinnedArray) -> np.ndarray:
-    """ndarray subclass instance that keeps its page-locked backing store alive."""
-    arr = pinned.array.view(_OwnedArray)
-    arr._owner = pinned
-    return arr
-
-
-class _OwnedArray(np.ndarray):
-    def __array_finalize__(self, obj):
-        self._owner = getattr(obj, "_owner", None)
 
 
 class GltfNode:
@@ -433,9 +430,9 @@ class NerfMeshRenderer:
     # -- additions -----------------------------------------------------------------------------------------------
     def read_frame(self) -> np.ndarray:
         """Image of the last frame(): float32[H, W, 4], row 0 = bottom (replaces the reference's on-screen blit)."""
-        out = _PinnedArray((self.height, self.width, 4))
-        self._ck(lib().nmr_read_frame(self._h, _ptr(out.array)))
-        return _own(out)
+        out = _pinned_array((self.height, self.width, 4))
+        self._ck(lib().nmr_read_frame(self._h, _ptr(out)))
+        return out
 
     def frame_async(self):
         self._ck(lib().nmr_frame_async(self._h))
@@ -446,9 +443,9 @@ class NerfMeshRenderer:
     def render_views(self, nerf: Testbed, cameras, width: int, height: int, linear: bool = False) -> np.ndarray:
         """cameras: [n, 3, 4] -> float32[n, H, W, 4] rendered back to back (render.py's landmark pass in one call)."""
         cams = np.ascontiguousarray(np.asarray(cameras, dtype=np.float32).reshape(-1, 3, 4).transpose(0, 2, 1)).reshape(-1, 12)
-        out = _PinnedArray((cams.shape[0], height, width, 4))
-        self._ck(lib().nmr_render_views(self._h, nerf._id, cams.shape[0], _ptr(cams), int(width), int(height), int(bool(linear)), _ptr(out.array)))
-        return _own(out)
+        out = _pinned_array((cams.shape[0], height, width, 4))
+        self._ck(lib().nmr_render_views(self._h, nerf._id, cams.shape[0], _ptr(cams), int(width), int(height), int(bool(linear)), _ptr(out)))
+        return out
 
     def set_shard(self, rank: int, world: int, band: int = 8):
         self._ck(lib().nmr_set_shard(self._h, int(rank), int(world), int(band)))
@@ -472,5 +469,5 @@ class NerfMeshRenderer:
 
 
 def free_temporary_memory():
-    """tcnn::free_all_gpu_memory_arenas in the reference (S/python_api.cu:159); libnmr has no arena to trim."""
-    return None
+    """tcnn::free_all_gpu_memory_arenas in the reference (S/python_api.cu:159); here: the pinned host buffer pool."""
+    free_pinned_pool()

@@ -103,7 +103,9 @@ def test_render_no_mesh_pixels(scene):
     assert stats["samples"] > 5000
     # sample counts can differ only where a termination threshold is crossed within rounding of the network outputs
     assert np.mean(gns == ns) > 0.98
-    assert abs(int(st["samples"]) - stats["samples"]) <= 0.01 * stats["samples"]
+    assert abs(int(gns.sum()) - stats["samples"]) <= 0.01 * stats["samples"]
+    # the kernel evaluates rays in batches of 8 samples and discards what lies past a ray's termination
+    assert int(gns.sum()) <= int(st["samples"]) <= int(gns.sum()) + 8 * int(st["rays_alive"])
     assert np.max(np.abs(np.asarray(img) - want)) <= PIX_TOL
     assert H.psnr(np.asarray(img), want) >= 45.0
 
@@ -132,7 +134,8 @@ def test_accumulation_and_linear_output(scene):
     a = np.asarray(nerf.render(W, HH, 1, linear=True))
     b = np.asarray(nerf.render(W, HH, 2, linear=True))
     assert a.shape == (HH, W, 4) and np.isfinite(a).all() and np.isfinite(b).all()
-    assert np.max(np.abs(a - b)) < 0.25 and np.max(np.abs(a - b)) > 0       # second sample uses a different start jitter
+    d = np.abs(a - b)
+    assert 0 < float(d.mean()) < 0.01 and float(d.max()) <= 0.5 + 1e-6   # the second sample uses another start jitter; mean of two samples
 
 
 def test_sharded_render_equals_full(scene):
