@@ -3,6 +3,7 @@
 // (S/nerf_mesh_renderer.cu:365-452, 499-598, 896-1000; S/ngp/testbed.cu:939-1135, 1481-1612; S/python_api.cu:83-111).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -51,6 +52,7 @@ struct Nerf {
     DevBuf<uint8_t> d_bitfield;
     DeviceModel dev{};
     float render_aabb_min[3], render_aabb_max[3];
+    float occ_min[3], occ_max[3];                   // box around every occupied cell (see update_occupied_box)
     float background[4] = {1.f, 1.f, 1.f, 1.f};     // S/ngp/testbed.cuh:525
     float min_transmittance = 0.01f;                // S/ngp/testbed.cuh:484
 };
@@ -196,6 +198,34 @@ void upload_mesh_if_dirty(nmr_ctx* ctx) {
     ctx->mesh_dirty = false;
 }
 
+// World-space box around every occupied cell a sample can test, inflated by one cell of the coarsest cascade involved.
+// A position p tests cascade mip_from_pos(p) (S/ngp/testbed.cu:188-193): inside the unit cube that is cascade 0 (cascade 1
+// exactly on its boundary), in general cascades 0..max_cascade+1; cascade c cells are 2^c / 128 wide and centred on 0.5.
+void update_occupied_box(nmr_ctx* ctx, Nerf& n) {
+    DevBuf<int> d_b; d_b.ensure(48);
+    launch_occupancy_bounds(n.d_bitfield.p, d_b.p, ctx->stream);
+    int b[48];
+    CK(cudaMemcpyAsync(b, d_b.p, sizeof(b), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    const int top = std::min(n.host.max_cascade + 1, (int)kCascades - 1);
+    float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+    for (int c = 0; c <= top; ++c) {
+        const float cell = std::ldexp(1.0f, c) / 128.0f;
+        for (int k = 0; k < 3; ++k) {
+            if (b[c * 6 + 3 + k] < 0) continue;
+            lo[k] = std::min(lo[k], ((float)b[c * 6 + k] / 128.0f - 0.5f) * std::ldexp(1.0f, c) + 0.5f);
+            hi[k] = std::max(hi[k], ((float)(b[c * 6 + 3 + k] + 1) / 128.0f - 0.5f) * std::ldexp(1.0f, c) + 0.5f);
+        }
+        (void)cell;
+    }
+    const float margin = std::ldexp(1.0f, top) / 128.0f;
+    for (int k = 0; k < 3; ++k) {
+        if (hi[k] < lo[k]) { n.occ_min[k] = 1.f; n.occ_max[k] = -1.f; }     // nothing occupied: every ray misses
+        else { n.occ_min[k] = lo[k] - margin; n.occ_max[k] = hi[k] + margin; }
+    }
+}
+
 FrameParams make_params(nmr_ctx* ctx, const Nerf& n, int W, int H, const float* cam12, uint32_t spp_index, bool to_srgb, bool with_mesh) {
     FrameParams P{};
     P.width = W; P.height = H;
@@ -217,6 +247,7 @@ FrameParams make_params(nmr_ctx* ctx, const Nerf& n, int W, int H, const float* 
     P.mesh_scale = (with_mesh && ctx->mesh_dev.n_tris > 0) ? ctx->mesh_scale : 0;
     std::memcpy(P.light, ctx->light, 12);
     invert3(cam12, P.cam_inv);
+    std::memcpy(P.occ_min, n.occ_min, 12); std::memcpy(P.occ_max, n.occ_max, 12);
     return P;
 }
 
@@ -354,6 +385,7 @@ NMR_API int nmr_load_nerf(nmr_ctx* ctx, const char* path, int* out_id) {
             if ((d.level_size[l] & (d.level_size[l] - 1u)) == 0) d.pow2_mask |= 1u << l;
         }
         std::memcpy(n->render_aabb_min, h.render_aabb_min, 12); std::memcpy(n->render_aabb_max, h.render_aabb_max, 12);
+        update_occupied_box(ctx, *n);
         std::vector<uint16_t>().swap(h.params);
         std::vector<uint16_t>().swap(h.density_grid);
         ctx->nerfs.push_back(std::move(n));
@@ -578,6 +610,7 @@ NMR_API int nmr_set_density_bitfield(nmr_ctx* ctx, int id, const uint8_t* in) {
         Nerf* n; try { n = get_nerf(ctx, id); } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); }
         CK(cudaMemcpyAsync(n->d_bitfield.p, in, kBitfieldBytes, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
+        update_occupied_box(ctx, *n);
         ctx->surf.spp = 0;
         return NMR_OK;
     });
@@ -594,6 +627,7 @@ NMR_API int nmr_remove_floaties(nmr_ctx* ctx, int* out_clusters, int64_t* out_ke
         CK(cudaMemcpyAsync(res, scratch.p, sizeof(res), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         CK(cudaGetLastError());
+        update_occupied_box(ctx, n);
         if (out_clusters) *out_clusters = (int)res[0];
         if (out_kept) *out_kept = (int64_t)res[1];
         ctx->surf.spp = 0;

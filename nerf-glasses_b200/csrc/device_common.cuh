@@ -59,6 +59,7 @@ struct FrameParams {
     int mesh_scale;                   // 0: no mesh stage
     float light[3];
     float cam_inv[9];                 // inverse of [U V W] (row-major), for the rasteriser's bounding boxes
+    float occ_min[3], occ_max[3];     // box around every occupied grid cell a sample can test, inflated by one cell
 };
 
 // ---- tiny vector helpers -------------------------------------------------------------------------------------
@@ -199,7 +200,26 @@ __device__ __forceinline__ V3 r2l_mul(const float* m, V3 p) {   // Eigen Matrix3
 }
 
 // ---- ray set-up (S/ngp/ngp_common.cuh:362-368; S/ngp/testbed.cu:435-464) ---------------------------------------
-struct RayInit { V3 origin, dir; float t; bool alive; };
+struct RayInit { V3 origin, dir; float t; float t_limit; bool alive; };
+
+// Far intersection of the ray with the box around all occupied cells (negative when the ray misses it).  Past that
+// parameter no sample can land in an occupied cell, so a walk may stop there: the reference's own walk would only step
+// through empty cells until it leaves the render box (S/ngp/testbed.cu:506-532, 600-625) - same result, no arithmetic on t.
+__device__ __forceinline__ float occupied_exit(const FrameParams& P, V3 o, V3 d) {
+    float tmin = -3.402823466e+38f, tmax = 3.402823466e+38f;
+    const float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (dd[k] != 0.f) {
+            float a = (P.occ_min[k] - oo[k]) / dd[k], b = (P.occ_max[k] - oo[k]) / dd[k];
+            if (a > b) { const float c = a; a = b; b = c; }
+            tmin = fmaxf(tmin, a); tmax = fminf(tmax, b);
+        } else if (oo[k] < P.occ_min[k] || oo[k] > P.occ_max[k]) {
+            return -1.f;
+        }
+    }
+    return tmin <= tmax ? tmax : -1.f;
+}
 __device__ __forceinline__ RayInit init_ray(const FrameParams& P, uint32_t x, uint32_t y) {
     const float* c = P.cam;
     const float ux = 2.0f * (((float)x + 0.5f) / (float)P.width) - 1.0f;
@@ -212,12 +232,13 @@ __device__ __forceinline__ RayInit init_ray(const FrameParams& P, uint32_t x, ui
     r.dir = d;
     r.t = fmaxf(box_ray_tmin(P.aabb_min, P.aabb_max, r.origin, d), 0.0f) + 1e-6f;
     r.alive = box_contains(P.aabb_min, P.aabb_max, vadd(r.origin, vmul(d, r.t)));
+    r.t_limit = occupied_exit(P, r.origin, d);
     return r;
 }
 
 // advance_pos_nerf (S/ngp/testbed.cu:470-537); returns alive
 __device__ __forceinline__ bool advance_pos(const FrameParams& P, const uint8_t* __restrict__ bitfield, V3 origin, V3 dir, uint32_t pixel_idx,
-                                            float t_surface, bool alive, float& t_io, float& t_start) {
+                                            float t_surface, float t_limit, bool alive, float& t_io, float& t_start) {
     t_start = 0.f;
     if (!alive) {
         if (t_surface != 0.0f) { t_io = t_surface; return true; }
@@ -231,7 +252,7 @@ __device__ __forceinline__ bool advance_pos(const FrameParams& P, const uint8_t*
     while (true) {
         if (t_surface != 0.0f && t > t_surface) { t_io = t_surface; return true; }
         const V3 pos = vadd(origin, vmul(dir, t));
-        if (!box_contains(P.aabb_min, P.aabb_max, r2l_mul(P.r2l, pos))) {
+        if (t > t_limit || !box_contains(P.aabb_min, P.aabb_max, r2l_mul(P.r2l, pos))) {   // nothing occupied ahead == walked out of the box
             if (t_surface != 0.0f) { t_io = t_surface; return true; }
             alive = false;
             break;
@@ -254,12 +275,13 @@ struct Sample { V3 pos; float dt_warped; float t; uint32_t cell, mip; };
 // mesh surface, in which case t is snapped to t_surface); 2 when `budget` voxel tests were spent in empty space without
 // either outcome - t_io then holds the walk's state and the same call resumes it (the walk is a pure function of t).
 __device__ __forceinline__ int next_sample(const FrameParams& P, const uint8_t* __restrict__ bitfield, V3 origin, V3 dir, V3 idir,
-                                        float t_start, float t_surface, float surf_w, bool ignore_surface, int budget, float& t_io, Sample& s) {
+                                        float t_start, float t_surface, float surf_w, float t_limit, bool ignore_surface, int budget, float& t_io, Sample& s) {
     const float cone = P.cone_angle;
     float t = t_io;
     V3 pos; float dt; uint32_t mip, cell;
     while (true) {
         if (!ignore_surface && t_surface != 0.0f && t > t_surface && surf_w == 1.f) { t_io = t_surface; return 0; }
+        if (t > t_limit) return 0;                 // no occupied cell ahead: the walk could only run out of the render box
         pos = vadd(origin, vmul(dir, t));
         if (!box_contains(P.aabb_min, P.aabb_max, r2l_mul(P.r2l, pos))) return 0;
         dt = calc_dt(t - t_start, cone);

@@ -65,6 +65,27 @@ __global__ void occupancy_pool_kernel(const uint8_t* __restrict__ prev, uint8_t*
     next[morton3D(x, y, z)] |= bits;   // distinct i map to distinct bytes: no race
 }
 
+// min / max cell coordinate of the set cells of every cascade: out[c*6 + {0,1,2}] = min xyz, [3,4,5] = max xyz
+__global__ void occupancy_bounds_kernel(const uint8_t* __restrict__ bitfield, int* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;          // one byte = 8 Morton-consecutive cells = a 2x2x2 block
+    if (i >= GRID_CELLS / 8 * NERF_CASCADES) return;
+    const uint8_t bits = bitfield[i];
+    if (!bits) return;
+    const uint32_t c = i / (GRID_CELLS / 8), m = (i % (GRID_CELLS / 8)) * 8;
+    const int x = (int)morton3D_invert(m), y = (int)morton3D_invert(m >> 1), z = (int)morton3D_invert(m >> 2);
+    atomicMin(&out[c * 6 + 0], x); atomicMin(&out[c * 6 + 1], y); atomicMin(&out[c * 6 + 2], z);
+    atomicMax(&out[c * 6 + 3], x + 1); atomicMax(&out[c * 6 + 4], y + 1); atomicMax(&out[c * 6 + 5], z + 1);
+}
+
+void launch_occupancy_bounds(const uint8_t* d_bitfield, int* d_out48, cudaStream_t s) {
+    int init[48];
+    for (int c = 0; c < 8; ++c) { for (int k = 0; k < 3; ++k) { init[c * 6 + k] = 1 << 20; init[c * 6 + 3 + k] = -1; } }
+    cudaMemcpyAsync(d_out48, init, sizeof(init), cudaMemcpyHostToDevice, s);
+    cudaStreamSynchronize(s);   // `init` lives on this stack frame
+    const uint32_t total = GRID_CELLS / 8 * NERF_CASCADES;
+    occupancy_bounds_kernel<<<(total + 255) / 256, 256, 0, s>>>(d_bitfield, d_out48);
+}
+
 void launch_occupancy_build(const uint16_t* d_grid, int n_cascades_present, uint8_t* d_bitfield, float* d_scratch, cudaStream_t s) {
     double* sum = reinterpret_cast<double*>(d_scratch);
     cudaMemsetAsync(sum, 0, sizeof(double), s);
@@ -225,14 +246,14 @@ __global__ void __launch_bounds__(128) init_rays_kernel(FrameParams P, DeviceMod
     float t_surface = 0.f;
     if (P.mesh_scale > 0) mesh_resolve(mesh, P, zbuf, x, y, surf, t_surface);
     float t = r.t, t_start;
-    const bool alive = advance_pos(P, M.bitfield, r.origin, r.dir, idx, t_surface, r.alive, t, t_start);
+    const bool alive = advance_pos(P, M.bitfield, r.origin, r.dir, idx, t_surface, r.t_limit, r.alive, t, t_start);
     if (!alive) {
         finish_pixel(P, out, idx, 0.f, 0.f, 0.f, 0.f, 0.f, 0u);
         return;
     }
     const uint32_t slot = atomicAdd(&counters[0], 1u);
     queue[(size_t)slot * kRayRecordFloat4s + 0] = make_float4(r.dir.x, r.dir.y, r.dir.z, t);
-    queue[(size_t)slot * kRayRecordFloat4s + 1] = make_float4(t_start, t_surface, __uint_as_float(idx), 0.f);
+    queue[(size_t)slot * kRayRecordFloat4s + 1] = make_float4(t_start, t_surface, __uint_as_float(idx), r.t_limit);
     queue[(size_t)slot * kRayRecordFloat4s + 2] = make_float4(surf[0], surf[1], surf[2], surf[3]);
 }
 
@@ -560,7 +581,7 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? 3 : 2) ma
     // per-ray state, identical in the 8 lanes of a group
     bool active = false, exhausted = false, pending_finish = false;
     V3 dir = v3(0.f, 0.f, 1.f);
-    float t = 0.f, t_start = 0.f, t_surface = 0.f, max_weight = 0.f, depth = 0.f;
+    float t = 0.f, t_start = 0.f, t_surface = 0.f, t_limit = 0.f, max_weight = 0.f, depth = 0.f;
     float sr = 0.f, sg = 0.f, sb = 0.f, sw = 0.f;        // surface colour (mesh hand-off)
     float cr = 0.f, cg = 0.f, cb = 0.f, ca = 0.f;        // accumulated colour
     uint32_t idx = 0, n_samples = 0, evaluated = 0, n_batches = 0, n_passes = 0;
@@ -585,7 +606,7 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? 3 : 2) ma
                 slot = __shfl_sync(gmask, slot, gbase);
                 if (slot >= n_rays) { exhausted = true; break; }
                 const float4 q0 = __ldg(queue + (size_t)slot * kRayRecordFloat4s), q1 = __ldg(queue + (size_t)slot * kRayRecordFloat4s + 1), q2 = __ldg(queue + (size_t)slot * kRayRecordFloat4s + 2);
-                dir = v3(q0.x, q0.y, q0.z); t = q0.w; t_start = q1.x; t_surface = q1.y; idx = __float_as_uint(q1.z);
+                dir = v3(q0.x, q0.y, q0.z); t = q0.w; t_start = q1.x; t_surface = q1.y; idx = __float_as_uint(q1.z); t_limit = q1.w;
                 sr = q2.x; sg = q2.y; sb = q2.z; sw = q2.w;
                 cr = cg = cb = ca = 0.f; max_weight = 0.f; depth = 0.f; n_samples = 0;
                 active = true;
@@ -608,7 +629,7 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? 3 : 2) ma
                 bool ok = sub >= n_valid;
                 if (ok) {
                     for (uint32_t k = n_valid; k < sub; ++k) tc += calc_dt(tc - t_start, P.cone_angle);
-                    ok = !(t_surface != 0.0f && tc > t_surface && sw == 1.f);
+                    ok = !(t_surface != 0.0f && tc > t_surface && sw == 1.f) && !(tc > t_limit);
                     pc = vadd(origin, vmul(dir, tc));
                     ok = ok && box_contains(P.aabb_min, P.aabb_max, r2l_mul(P.r2l, pc));
                     if (ok) {
@@ -633,7 +654,7 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? 3 : 2) ma
                 // through empty cells is cut into slices of kWalkBudget voxels so that one ray cannot stall its tile: a paused
                 // walk keeps its state in t and resumes in the next iteration.
                 Sample smp;
-                const int rc = next_sample(P, M.bitfield, origin, dir, idir, t_start, t_surface, sw, false, kWalkBudget, tt, smp);
+                const int rc = next_sample(P, M.bitfield, origin, dir, idir, t_start, t_surface, sw, t_limit, false, kWalkBudget, tt, smp);
                 if (rc != 1) { paused = rc == 2; break; }
                 if (sub == n_valid) { my_pos = smp.pos; my_dtw = smp.dt_warped; my_t_after = tt; }
                 ++n_valid;
@@ -798,14 +819,14 @@ __global__ void debug_trace_kernel(FrameParams P, DeviceModel M, const uint32_t*
     const uint32_t x = pix % (uint32_t)P.width, y = pix / (uint32_t)P.width;
     RayInit r = init_ray(P, x, y);
     float t = r.t, t_start;
-    const bool alive = advance_pos(P, M.bitfield, r.origin, r.dir, pix, 0.f, r.alive, t, t_start);
+    const bool alive = advance_pos(P, M.bitfield, r.origin, r.dir, pix, 0.f, r.t_limit, r.alive, t, t_start);
     float* rr = o_ray + i * 8;
     rr[0] = r.origin.x; rr[1] = r.origin.y; rr[2] = r.origin.z; rr[3] = r.dir.x; rr[4] = r.dir.y; rr[5] = r.dir.z; rr[6] = t; rr[7] = alive ? 1.f : 0.f;
     const V3 idir = v3(1.0f / r.dir.x, 1.0f / r.dir.y, 1.0f / r.dir.z);
     uint32_t cnt = 0;
     while (alive && cnt < max_samples) {
         Sample s;
-        if (next_sample(P, M.bitfield, r.origin, r.dir, idir, t_start, 0.f, 0.f, true, 0x7fffffff, t, s) != 1) break;
+        if (next_sample(P, M.bitfield, r.origin, r.dir, idir, t_start, 0.f, 0.f, r.t_limit, true, 0x7fffffff, t, s) != 1) break;
         const int64_t o = i * max_samples + cnt;
         o_t[o] = s.t; o_cell[o] = s.cell; o_mip[o] = s.mip;
         o_pos[o * 3] = s.pos.x; o_pos[o * 3 + 1] = s.pos.y; o_pos[o * 3 + 2] = s.pos.z;
