@@ -1,0 +1,104 @@
+"""Data-parallel rendering over several GPUs, one process per GPU (torch.distributed; NCCL on GPUs, gloo in CPU tests).
+
+The reference is single-GPU (no NCCL/MPI anywhere); this module is the new host-side plumbing of
+SURVEY section 8e.  Rays are independent, every rank holds a full model replica, and nothing is exchanged while a frame
+renders.  Two partitionings:
+
+  views   each rank renders whole views (render.py's multi-view landmark pass): `view_slice`, no collective at all unless
+          the caller wants every image on one rank (`gather_views`).
+  tiles   one frame, rows dealt to ranks in bands of `band` rows, round-robin (nmr_set_shard): a rank renders only its rows;
+          `gather_frame` packs the owned rows and gathers them to `dst` with ONE collective, where they are scattered back
+          into a full image.  The gathered image is bit-identical to the single-GPU image (tests/test_gpu_parity.py).
+
+Tensors are torch tensors on whatever device the process group's backend moves (cuda for nccl, cpu for gloo).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def owned_rows(height: int, rank: int, world: int, band: int) -> np.ndarray:
+    """Image rows rendered by `rank`: row y belongs to rank (y // band) % world (same rule as csrc/kernels.cu:shard_row)."""
+    if world < 1 or not (0 <= rank < world) or band < 1:
+        raise ValueError("bad shard specification")
+    y = np.arange(height)
+    return y[(y // band) % world == rank]
+
+
+def max_owned_rows(height: int, world: int, band: int) -> int:
+    return max(len(owned_rows(height, r, world, band)) for r in range(world))
+
+
+def view_slice(n_views: int, rank: int, world: int) -> range:
+    """Contiguous block of views for `rank` (sizes differ by at most one)."""
+    base, extra = divmod(n_views, world)
+    start = rank * base + min(rank, extra)
+    return range(start, start + base + (1 if rank < extra else 0))
+
+
+def pack_rows(image, rows: np.ndarray, padded_rows: int):
+    """image [H, W, C] -> [padded_rows, W, C] holding the owned rows first (zero padding keeps gather sizes equal)."""
+    import torch
+    idx = torch.as_tensor(rows, dtype=torch.long, device=image.device)
+    out = torch.zeros((padded_rows,) + tuple(image.shape[1:]), dtype=image.dtype, device=image.device)
+    out[: len(rows)] = image.index_select(0, idx)
+    return out
+
+
+def gather_frame(local_image, rank: int, world: int, band: int, dst: int = 0, group=None):
+    """Gathers a row-sharded frame.  local_image: [H, W, C] tensor in which only this rank's rows are valid.
+    Returns the full [H, W, C] image on rank `dst`, None elsewhere.  One collective (gather); no other communication."""
+    import torch
+    import torch.distributed as dist
+    H = int(local_image.shape[0])
+    if world == 1:
+        return local_image
+    padded = max_owned_rows(H, world, band)
+    mine = pack_rows(local_image, owned_rows(H, rank, world, band), padded)
+    parts = [torch.empty_like(mine) for _ in range(world)] if rank == dst else None
+    dist.gather(mine, gather_list=parts, dst=dst, group=group)
+    if rank != dst:
+        return None
+    full = torch.empty_like(local_image)
+    for r in range(world):
+        rows = owned_rows(H, r, world, band)
+        full.index_copy_(0, torch.as_tensor(rows, dtype=torch.long, device=full.device), parts[r][: len(rows)])
+    return full
+
+
+def gather_views(local_views, n_views: int, rank: int, world: int, dst: int = 0, group=None):
+    """local_views: [n_local, H, W, C] (this rank's view_slice).  Returns [n_views, H, W, C] on `dst`, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return local_views
+    padded = max(len(view_slice(n_views, r, world)) for r in range(world))
+    mine = torch.zeros((padded,) + tuple(local_views.shape[1:]), dtype=local_views.dtype, device=local_views.device)
+    mine[: local_views.shape[0]] = local_views
+    parts = [torch.empty_like(mine) for _ in range(world)] if rank == dst else None
+    dist.gather(mine, gather_list=parts, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return torch.cat([parts[r][: len(view_slice(n_views, r, world))] for r in range(world)], dim=0)
+
+
+class ShardedRenderer:
+    """One frame across the process group: every rank calls render_frame(); rank `dst` gets the full image.
+
+    renderer: this rank's pynmr.NerfMeshRenderer (created on this rank's device, same scene loaded on every rank).
+    """
+
+    def __init__(self, renderer, rank: int, world: int, band: int = 8, group=None):
+        self.r, self.rank, self.world, self.band, self.group = renderer, rank, world, band, group
+        renderer.set_shard(rank, world, band)
+        self._buf = None
+
+    def render_frame(self, dst: int = 0):
+        """frame() on the local shard, then the gather.  Returns a torch.float32 [H, W, 4] cuda tensor on `dst`."""
+        import torch
+        self.r.frame_async()
+        H, W = self.r.height, self.r.width
+        if self._buf is None or tuple(self._buf.shape) != (H, W, 4):
+            self._buf = torch.empty((H, W, 4), dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
+        self.r.copy_device_image(self._buf.data_ptr())      # device->device on libnmr's stream, then a stream synchronise
+        return gather_frame(self._buf, self.rank, self.world, self.band, dst, self.group)

@@ -1,0 +1,142 @@
+"""ctypes front-end of oracle/_ref/libnmr_refgpu.so: the REFERENCE's own NeRF renderer (ngp::Testbed + tiny-cuda-nn),
+compiled for sm_100 from /root/reference by oracle/Makefile.refgpu.
+
+TEST INFRASTRUCTURE ONLY.  Used by the -m gpu tests (pinning libnmr and the C oracle against the reference's kernels
+on the same B200) and by bench.py's informational "reference kernels on this GPU" figure.  The product never imports it.
+The library only exists where it was built (this container) and on GPU boxes that received the built file via gpurun.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "_ref", "libnmr_refgpu.so")
+MAKEFILE = os.path.join(HERE, "Makefile.refgpu")
+
+
+def available() -> bool:
+    return os.path.exists(LIB)
+
+
+def build(jobs: int = 8) -> str | None:
+    """make -f oracle/Makefile.refgpu (about 25 minutes from scratch; incremental afterwards).  No-op without the
+    reference tree or nvcc."""
+    if not os.path.isdir("/root/reference/nerf_mesh_renderer") or shutil.which("nvcc") is None:
+        return LIB if available() else None
+    subprocess.check_call(["make", "-f", MAKEFILE, f"-j{jobs}"], stdout=subprocess.DEVNULL)
+    return LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(LIB)
+        vp = C.c_void_p
+        L.refgpu_create.restype = vp
+        L.refgpu_last_error.restype = C.c_char_p
+        L.refgpu_last_error.argtypes = [vp]
+        L.refgpu_destroy.argtypes = [vp]
+        L.refgpu_load_snapshot.argtypes = [vp, C.c_char_p]
+        L.refgpu_set_render_aabb.argtypes = [vp, vp, vp]
+        L.refgpu_get_render_aabb.argtypes = [vp, vp, vp]
+        L.refgpu_set_background.argtypes = [vp, vp]
+        L.refgpu_get_bitfield.argtypes = [vp, vp]
+        L.refgpu_set_bitfield.argtypes = [vp, vp]
+        L.refgpu_bitfield_bytes.restype = C.c_int64
+        L.refgpu_bitfield_bytes.argtypes = [vp]
+        L.refgpu_network.argtypes = [vp, vp, vp, C.c_int64, vp]
+        L.refgpu_encode.argtypes = [vp, vp, C.c_int64, vp]
+        L.refgpu_trace.argtypes = [vp, vp, C.c_int, C.c_int, C.c_uint32, vp, vp, C.c_uint32, vp, vp, vp, vp, vp]
+        L.refgpu_render.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class ReferenceRenderer:
+    """The reference's Testbed behind NerfMeshRenderer::loadNerf, headless."""
+
+    def __init__(self, snapshot_path: str):
+        self._L = lib()
+        self._h = self._L.refgpu_create()
+        if not self._h:
+            raise RuntimeError("refgpu_create failed: " + self._L.refgpu_last_error(None).decode())
+        self._ck(self._L.refgpu_load_snapshot(self._h, snapshot_path.encode()))
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise RuntimeError(self._L.refgpu_last_error(self._h).decode())
+
+    def close(self):
+        if self._h:
+            self._L.refgpu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_render_aabb(self, mn, mx):
+        a = np.ascontiguousarray(mn, dtype=np.float32); b = np.ascontiguousarray(mx, dtype=np.float32)
+        self._ck(self._L.refgpu_set_render_aabb(self._h, _p(a), _p(b)))
+
+    def render_aabb(self):
+        a = np.zeros(3, np.float32); b = np.zeros(3, np.float32)
+        self._ck(self._L.refgpu_get_render_aabb(self._h, _p(a), _p(b)))
+        return a, b
+
+    def bitfield(self) -> np.ndarray:
+        out = np.zeros(int(self._L.refgpu_bitfield_bytes(self._h)), dtype=np.uint8)
+        self._ck(self._L.refgpu_get_bitfield(self._h, _p(out)))
+        return out
+
+    def set_bitfield(self, bits: np.ndarray):
+        bits = np.ascontiguousarray(bits, dtype=np.uint8)
+        assert bits.size == int(self._L.refgpu_bitfield_bytes(self._h))
+        self._ck(self._L.refgpu_set_bitfield(self._h, _p(bits)))
+
+    def encode(self, pos: np.ndarray) -> np.ndarray:
+        pos = np.ascontiguousarray(pos, dtype=np.float32)
+        out = np.zeros((pos.shape[0], 32), dtype=np.uint16)
+        self._ck(self._L.refgpu_encode(self._h, _p(pos), pos.shape[0], _p(out)))
+        return out
+
+    def network(self, pos: np.ndarray, dir01: np.ndarray) -> np.ndarray:
+        """-> float16 [n, 16]: r, g, b raw, density raw, 12 padding channels."""
+        pos = np.ascontiguousarray(pos, dtype=np.float32); d = np.ascontiguousarray(dir01, dtype=np.float32)
+        out = np.zeros((pos.shape[0], 16), dtype=np.uint16)
+        self._ck(self._L.refgpu_network(self._h, _p(pos), _p(d), pos.shape[0], _p(out)))
+        return out.view(np.float16)
+
+    def trace(self, cam12, W, H, max_samples, spp_index=0, surf=None, ts=None):
+        cam12 = np.ascontiguousarray(cam12, dtype=np.float32)
+        n = W * H
+        ray = np.zeros((n, 10), np.float32); pos = np.zeros((n, max_samples, 3), np.float32)
+        dt = np.zeros((n, max_samples), np.float32); ta = np.zeros((n, max_samples), np.float32); cnt = np.zeros(n, np.uint32)
+        s = None if surf is None else np.ascontiguousarray(surf, dtype=np.float32)
+        t = None if ts is None else np.ascontiguousarray(ts, dtype=np.float32)
+        self._ck(self._L.refgpu_trace(self._h, _p(cam12), W, H, spp_index, _p(s), _p(t), max_samples, _p(ray), _p(pos), _p(dt), _p(ta), _p(cnt)))
+        return {"ray": ray, "pos": pos, "dt": dt, "t_after": ta, "count": cnt}
+
+    def render(self, cam12, W, H, spp=1, linear=False, surf=None, ts=None, repeat=1):
+        """-> (float32 [H, W, 4] bottom-up like Testbed.render, best device ms of Testbed::render_frame)."""
+        cam12 = np.ascontiguousarray(cam12, dtype=np.float32)
+        out = np.zeros((H, W, 4), np.float32)
+        s = None if surf is None else np.ascontiguousarray(surf, dtype=np.float32)
+        t = None if ts is None else np.ascontiguousarray(ts, dtype=np.float32)
+        ms = C.c_float(0)
+        self._ck(self._L.refgpu_render(self._h, _p(cam12), W, H, spp, 1 if linear else 0, _p(s), _p(t), _p(out), repeat, C.byref(ms)))
+        return out, float(ms.value)

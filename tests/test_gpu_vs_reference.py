@@ -1,0 +1,120 @@
+"""GPU tests against the REFERENCE'S OWN renderer: ngp::Testbed + tiny-cuda-nn compiled for sm_100 from /root/reference
+into oracle/_ref/libnmr_refgpu.so (oracle/Makefile.refgpu).  Same B200, same snapshot, same camera.
+
+The reference binary is built with nvcc's default FMA contraction, so its float results are not reproducible bit for bit
+by any independent build; integer structures must still agree exactly (occupancy bitfield) and
+everything downstream within BASELINE.json's tolerances: pixels <= 2/255 max-abs and >= 45 dB PSNR.
+Skipped where the library was not built (it only exists in the authoring container and on boxes that received it)."""
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+W, HH = 192, 108
+PIX_TOL = 2.0 / 255.0
+
+
+@pytest.fixture(scope="module")
+def pair(small_snapshot, glasses_gltf):
+    from oracle import refgpu
+    if not refgpu.available():
+        pytest.skip("oracle/_ref/libnmr_refgpu.so not built")
+    import pynmr
+    import synth
+    path, snap = small_snapshot
+    ref = refgpu.ReferenceRenderer(path)
+    r = pynmr.NerfMeshRenderer(W, HH)
+    nerf = r.load_nerf(path)
+    assert nerf is not None
+    r.orbit(0.35, -0.2, 4.0)
+    cam12 = np.ascontiguousarray(r.view_projection_mat.T.reshape(-1))
+    g = {"path": glasses_gltf, "t": synth.GLASSES_T, "s": synth.GLASSES_S, "r": synth.GLASSES_R_WXYZ}
+    yield {"ref": ref, "r": r, "nerf": nerf, "snap": snap, "cam12": cam12, "glasses": g}
+    ref.close()
+
+
+def test_reference_loads_same_scene(pair):
+    mn, mx = pair["ref"].render_aabb()
+    assert np.allclose(mn, pair["snap"]["render_aabb_min"]) and np.allclose(mx, pair["snap"]["render_aabb_max"])
+
+
+def test_occupancy_bitfield_equals_reference(pair):
+    # grid_to_bitfield + bitfield_max_pool (S/ngp/testbed.cu:119-166, 1120-1135) vs occupancy_*_kernel
+    assert np.array_equal(pair["ref"].bitfield(), H.get_bitfield(pair["r"], pair["nerf"]))
+
+
+def test_encoding_vs_reference_kernel_grid(pair):
+    # kernel_grid<__half,3,2> (T/.../grid.h:219-349).  Both accumulate the 8 corners in fp16 in the same order; the only
+    # difference is FMA contraction of pos*scale+0.5 and of the weight products in the reference binary.
+    rng = np.random.default_rng(5)
+    pos = rng.uniform(0, 1, size=(20000, 3)).astype(np.float32)
+    want = pair["ref"].encode(pos)
+    got = H.debug_encode(pair["r"], pair["nerf"], pos)
+    assert np.mean(want == got) > 0.97
+    d = np.abs(want.view(np.float16).astype(np.float32) - got.view(np.float16).astype(np.float32))
+    assert float(d.max()) <= 2.0 ** -9          # features are |x| <= 0.1: a few fp16 ulps
+
+
+def test_network_vs_reference_mlp(pair):
+    # encoding -> kernel_mlp_fused x2 + kernel_sh (fp16 accumulation in wmma) vs tcgen05 with fp32 accumulators
+    rng = np.random.default_rng(6)
+    n = 128 * 37 + 5
+    pos = rng.uniform(0.3, 0.7, size=(n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d01 = ((d + 1) * 0.5).astype(np.float32)
+    want = pair["ref"].network(pos, d01).astype(np.float32)[:, :4]
+    got = H.debug_network(pair["r"], pair["nerf"], pos, d01).astype(np.float32)
+    err = np.abs(got - want)
+    tol = 2.0 ** -6 * np.maximum(np.abs(want), 1.0)      # fp16-accumulated reference: ~1e-2 relative
+    assert np.mean(err <= tol) > 0.999, float(err.max())
+    assert float(err.mean()) < 2e-3
+
+
+def test_traversal_vs_reference_kernels(pair):
+    # init_rays_with_payload_kernel_nerf + advance_pos_nerf + generate_next_nerf_network_inputs, network out of the loop
+    MS = 48
+    want = pair["ref"].trace(pair["cam12"], W, HH, MS)
+    got = H.debug_trace(pair["r"], pair["nerf"], W, HH, np.arange(W * HH, dtype=np.uint32), MS)
+    aw, ag = want["ray"][:, 7] > 0, got["ray"][:, 7] > 0
+    assert aw.sum() > 1000
+    assert np.mean(aw == ag) > 0.999
+    assert np.allclose(want["ray"][:, :6], got["ray"][:, :6], atol=2e-7, rtol=0)
+    live = aw & ag
+    same = want["count"][live] == got["count"][live]
+    assert np.mean(same) > 0.98
+    assert abs(int(want["count"].sum()) - int(got["count"].sum())) <= 0.005 * int(want["count"].sum())
+    both = live & (want["count"] == got["count"])
+    valid = np.arange(MS)[None, :] < got["count"][:, None]
+    dpos = np.abs(want["pos"] - got["pos"]).max(axis=2)[both][valid[both]]
+    # a ray whose FMA-rounded start lands one step off stays one step (sqrt(3)/1024) off; everything else agrees to ~1 ulp
+    assert np.mean(dpos <= 1e-6) > 0.98
+    assert float(dpos.max()) <= 2.0 * 1.7320508 / 1024.0
+
+
+def _cmp(a, b):
+    d = np.abs(a - b)
+    return float(d.max()), H.psnr(a, b), float(np.mean(d.max(axis=2) > PIX_TOL))
+
+
+def test_nerf_pixels_vs_reference(pair):
+    want, _ = pair["ref"].render(pair["cam12"], W, HH, 1, False)
+    got = np.asarray(pair["nerf"].render(W, HH, 1, linear=False))
+    mx, ps, frac = _cmp(got, want)
+    assert ps >= 45.0, ps
+    assert frac <= 0.002, (mx, frac)         # silhouette pixels where one implementation takes one more sample
+
+
+def test_hybrid_pixels_vs_reference(pair):
+    r, nerf, g = pair["r"], pair["nerf"], pair["glasses"]
+    assert r.load_mesh(g["path"], t=g["t"], s=g["s"], r=g["r"]) is not None
+    # the OptiX stage is not buildable (SDK absent): both renderers receive the SAME resolved mesh buffers, produced by
+    # libnmr's mesh stage, and the reference consumes them through its own hand-off + compositing code
+    _, _, _, surf, ts = H.debug_mesh(r, W, HH)
+    assert (ts > 0).mean() > 0.003
+    want, _ = pair["ref"].render(pair["cam12"], W, HH, 1, False, surf=surf, ts=ts)
+    got = np.asarray(nerf.render(W, HH, 1, linear=False))
+    mx, ps, frac = _cmp(got, want)
+    assert ps >= 45.0, ps
+    assert frac <= 0.004, (mx, frac)
