@@ -105,6 +105,7 @@ struct nmr_ctx {
     uint32_t* h_counters = nullptr;                       // pinned
     DevBuf<float> d_scratch;
     int shard_rank = 0, shard_world = 1, shard_band = 8;
+    int surface_mode = 0;                                 // nmr_surface_mode
     uint32_t debug_flags = 0;
     nmr_stats stats{};
     bool stats_pending = false;
@@ -248,6 +249,7 @@ FrameParams make_params(nmr_ctx* ctx, const Nerf& n, int W, int H, const float* 
     std::memcpy(P.light, ctx->light, 12);
     invert3(cam12, P.cam_inv);
     std::memcpy(P.occ_min, n.occ_min, 12); std::memcpy(P.occ_max, n.occ_max, 12);
+    P.surface_mode = ctx->surface_mode;
     return P;
 }
 
@@ -262,7 +264,7 @@ void enqueue_pass(nmr_ctx* ctx, Nerf& n, const FrameParams& P, bool timed) {
     launch_init_rays(P, n.dev, ctx->mesh_dev, S.zbuf.p, rows, S.queue.p, ctx->d_counters.p, out, ctx->stream);
     launches += 1;
     if (timed) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-    launch_march(P, n.dev, S.queue.p, ctx->d_counters.p, out, ctx->debug_flags, ctx->num_sms, ctx->stream);
+    launch_march(P, n.dev, S.queue.p, ctx->d_counters.p, out, (uint32_t)P.width * (uint32_t)rows, ctx->debug_flags, ctx->num_sms, ctx->stream);
     launches += 1;
     if (timed) {
         CK(cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -379,7 +381,7 @@ NMR_API int nmr_load_nerf(nmr_ctx* ctx, const char* path, int* out_id) {
             for (int k = 0; k < 3; ++k) d.prime[k] = primes[h.hash_type][k];
         }
         for (int l = 0; l < h.n_levels; ++l) {
-            d.level_offset[l] = h.offsets[l]; d.level_size[l] = h.offsets[l + 1] - h.offsets[l]; d.level_scale[l] = h.scales[l];
+            d.level_offset[l] = h.offsets[l]; d.level_ptr[l] = d.grid + h.offsets[l]; d.level_size[l] = h.offsets[l + 1] - h.offsets[l]; d.level_scale[l] = h.scales[l];
             d.stride_y[l] = h.stride_y[l]; d.stride_z[l] = h.stride_z[l];
             if (h.dense[l]) d.dense_mask |= 1u << l;
             if ((d.level_size[l] & (d.level_size[l] - 1u)) == 0) d.pow2_mask |= 1u << l;
@@ -476,6 +478,14 @@ NMR_API int nmr_set_shard(nmr_ctx* ctx, int rank, int world, int band) {
     return guarded(ctx, [&]() -> int {
         if (world < 1 || rank < 0 || rank >= world || band < 1) return fail(ctx, NMR_ERR_INVALID, "bad shard specification");
         ctx->shard_rank = rank; ctx->shard_world = world; ctx->shard_band = band; ctx->surf.spp = 0;
+        return NMR_OK;
+    });
+}
+
+NMR_API int nmr_set_surface_insertion(nmr_ctx* ctx, int mode) {
+    return guarded(ctx, [&]() -> int {
+        if (mode < NMR_SURFACE_AUTO || mode > NMR_SURFACE_BATCH8) return fail(ctx, NMR_ERR_INVALID, "bad surface insertion mode");
+        ctx->surface_mode = mode; ctx->surf.spp = 0;
         return NMR_OK;
     });
 }

@@ -22,6 +22,7 @@ struct DeviceModel {
     const __half2* grid;              // hash-table entries, all levels back to back
     const __half* mlp;                // density net | rgb net, row-major [out][in] (params_binary order)
     const uint8_t* bitfield;          // 2 MiB occupancy bits, Morton order per cascade
+    const __half2* level_ptr[N_LEVELS];  // grid + level_offset[l]: 64-bit base per level, so a gather is base + 32-bit index
     uint32_t level_offset[N_LEVELS];  // first entry of each level
     uint32_t level_size[N_LEVELS];    // entries in each level
     float level_scale[N_LEVELS];
@@ -60,7 +61,16 @@ struct FrameParams {
     float light[3];
     float cam_inv[9];                 // inverse of [U V W] (row-major), for the rasteriser's bounding boxes
     float occ_min[3], occ_max[3];     // box around every occupied grid cell a sample can test, inflated by one cell
+    int surface_mode;                 // where a partially covering mesh surface enters the compositing order: SurfaceMode
 };
+
+// The reference blends the mesh surface in front of the first sample of the n_steps BATCH whose end passed t_surface
+// (composite_kernel_nerf tests payload.t, which generate_next_nerf_network_inputs has already advanced past the whole
+// batch, S/ngp/testbed.cu:620-633, 843), and n_steps = clamp(pixels / live rays, 1, 8) (S/ngp/testbed.cu:1996).  While at
+// most 1/8 of the pixels hold a live ray - render.py's framing - that is a fixed 8-sample batch counted from the ray's
+// first sample, a ray-local rule (kSurfaceBatch8).  kSurfaceAuto picks it under that condition and the exact per-sample
+// position otherwise; kSurfaceExact always inserts at the exact sample.
+enum SurfaceMode : int { kSurfaceAuto = 0, kSurfaceExact = 1, kSurfaceBatch8 = 2 };
 
 // ---- tiny vector helpers -------------------------------------------------------------------------------------
 struct V3 { float x, y, z; };
@@ -304,7 +314,7 @@ __device__ __forceinline__ int next_sample(const FrameParams& P, const uint8_t* 
 __device__ __forceinline__ __half2 encode_level(const DeviceModel& M, int level, V3 p01) {
     const float scale = M.level_scale[level];
     const uint32_t size = M.level_size[level];
-    const __half2* __restrict__ grid = M.grid + M.level_offset[level];
+    const __half2* __restrict__ grid = M.level_ptr[level];
     const float fx = p01.x * scale + 0.5f, fy = p01.y * scale + 0.5f, fz = p01.z * scale + 0.5f;
     const float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
     const uint32_t gx = (uint32_t)(int)flx, gy = (uint32_t)(int)fly, gz = (uint32_t)(int)flz;

@@ -430,11 +430,12 @@ __device__ __forceinline__ void tc_issue_layer(const TcCtx& c, int w_off_halves,
     umma_commit(c.mbar);
 }
 
+// two fp32 accumulators -> packed fp16 (a in the low half), optionally through ReLU: one cvt instruction either way
 __device__ __forceinline__ uint32_t pack_relu_h2(uint32_t a, uint32_t b, bool relu) {
-    float x = __uint_as_float(a), y = __uint_as_float(b);
-    if (relu) { x = x > 0.f ? x : 0.f; y = y > 0.f ? y : 0.f; }
-    const __half2 h = __floats2half2_rn(x, y);
-    return *reinterpret_cast<const uint32_t*>(&h);
+    uint32_t r;
+    if (relu) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(b)), "f"(__uint_as_float(a)));
+    else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(b)), "f"(__uint_as_float(a)));
+    return r;
 }
 
 // one layer's barrier / issue / wait sequence: the warpgroup's rows are in shared memory -> accumulator is ready
@@ -550,12 +551,14 @@ constexpr int kWalkBudget = 6;      // empty voxels a ray may skip per tile iter
 
 template <bool TC>
 __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? 3 : 2) march_kernel(FrameParams P, DeviceModel M, const float4* __restrict__ queue,
-                                                                                          uint32_t* __restrict__ counters, FrameOut out, uint32_t debug_flags) {
+                                                                                          uint32_t* __restrict__ counters, FrameOut out, uint32_t n_pixels, uint32_t debug_flags) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     using Smem = typename std::conditional<TC, MarchSmemTC, MarchSmem>::type;
     Smem& S = *reinterpret_cast<Smem*>(smem_raw);
 
     const uint32_t n_rays = counters[0];
+    // mesh surface insertion rule (SurfaceMode): the reference's 8-sample batches while <= 1/8 of the pixels are live
+    const bool batch8 = P.surface_mode == kSurfaceBatch8 || (P.surface_mode == kSurfaceAuto && (unsigned long long)n_rays * 8ull <= (unsigned long long)n_pixels);
     TcCtx tc;
     char* a_row;
     int enc_stride;
@@ -591,7 +594,7 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? 3 : 2) ma
         V3 my_pos = v3(0.f, 0.f, 0.f);
         float my_dtw = 0.f, my_t_after = 0.f, t_batch_end = t;
         uint32_t n_valid = 0;
-        bool paused = false;
+        bool paused = false, ended = false;
         while (true) {
             if (pending_finish) {
                 // composite_kernel_nerf's tail for a finished ray (S/ngp/testbed.cu:886-901), then shade/accumulate/tonemap
@@ -620,7 +623,7 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? 3 : 2) ma
             // sequential rule for that one sample and then tries the parallel test again.
             float tt = t;
             n_valid = 0;
-            paused = false;
+            paused = false; ended = false;
 #pragma unroll 1
             while (n_valid < (uint32_t)kRayLanes) {
                 ++n_passes;
@@ -654,8 +657,9 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? 3 : 2) ma
                 // through empty cells is cut into slices of kWalkBudget voxels so that one ray cannot stall its tile: a paused
                 // walk keeps its state in t and resumes in the next iteration.
                 Sample smp;
-                const int rc = next_sample(P, M.bitfield, origin, dir, idir, t_start, t_surface, sw, t_limit, false, kWalkBudget, tt, smp);
-                if (rc != 1) { paused = rc == 2; break; }
+                // (a ray that still carries a mesh surface under the batch rule never pauses: its batches must stay aligned to 8 samples)
+                const int rc = next_sample(P, M.bitfield, origin, dir, idir, t_start, t_surface, sw, t_limit, false, (batch8 && sw > 0.f) ? 0x7fffffff : kWalkBudget, tt, smp);
+                if (rc != 1) { paused = rc == 2; ended = rc == 0; break; }
                 if (sub == n_valid) { my_pos = smp.pos; my_dtw = smp.dt_warped; my_t_after = tt; }
                 ++n_valid;
             }
@@ -684,40 +688,48 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? 3 : 2) ma
         if (TC) network_tc(a_row, tc, dir01, raw);
         else network_scalar(reinterpret_cast<MarchSmem&>(S), dir01, raw);
 
-        // ---- 4. composite the batch in order (S/ngp/testbed.cu:830-884, one sample at a time) ----
+        // ---- 4. composite the batch in order (S/ngp/testbed.cu:830-884) ----
+        // Every lane first turns ITS OWN sample's network outputs into alpha / colour / depth candidate (the expensive part:
+        // an exponential, three logistics, a square root); the group then replays the reference's per-sample recurrence
+        // over those values, strictly in order, so pixels do not depend on how samples were batched.
+        float a_alpha = 0.f, a_r = 0.f, a_g = 0.f, a_b = 0.f, a_depth = 0.f;
+        if (have) {
+            a_alpha = 1.f - __expf(-act_density(raw[3], P.density_activation) * unwarp_dt(my_dtw));
+            a_r = act_rgb(raw[0], P.rgb_activation); a_g = act_rgb(raw[1], P.rgb_activation); a_b = act_rgb(raw[2], P.rgb_activation);
+            const V3 tdiag = v3(P.taabb_max[0] - P.taabb_min[0], P.taabb_max[1] - P.taabb_min[1], P.taabb_max[2] - P.taabb_min[2]);
+            const V3 pos = v3(P.taabb_min[0] + my_pos.x * tdiag.x, P.taabb_min[1] + my_pos.y * tdiag.y, P.taabb_min[2] + my_pos.z * tdiag.z);
+            const V3 dd = vsub(pos, v3(P.cam[9], P.cam[10], P.cam[11]));   // NeRF-space sample vs world-space eye, as in the reference
+            a_depth = sqrtf(edot(dd, dd));
+        }
         if (active && !pending_finish) {
             bool done = false;
+            // reference rule: the batch's end (payload.t after generate_next_nerf_network_inputs) decides, before its first sample
+            const bool pre_blend = batch8 && sw > 0.f && n_valid == (uint32_t)kRayLanes && t_batch_end > t_surface;
 #pragma unroll 1
             for (uint32_t j = 0; j < n_valid; ++j) {
                 const uint32_t src = gbase + j;
-                const float r0 = __shfl_sync(gmask, raw[0], src), r1 = __shfl_sync(gmask, raw[1], src), r2 = __shfl_sync(gmask, raw[2], src), r3 = __shfl_sync(gmask, raw[3], src);
-                const float dtw = __shfl_sync(gmask, my_dtw, src), t_after = __shfl_sync(gmask, my_t_after, src);
-                const float px = __shfl_sync(gmask, my_pos.x, src), py = __shfl_sync(gmask, my_pos.y, src), pz = __shfl_sync(gmask, my_pos.z, src);
+                const float alpha = __shfl_sync(gmask, a_alpha, src);
+                const float r0 = __shfl_sync(gmask, a_r, src), r1 = __shfl_sync(gmask, a_g, src), r2 = __shfl_sync(gmask, a_b, src);
                 ++n_samples;
                 float T = 1.f - ca;
-                const float dt = unwarp_dt(dtw);
-                if (t_after > t_surface && sw > 0) {
-                    cr += sr * sw * T; cg += sg * sw * T; cb += sb * sw * T; ca += sw * T;
-                    sw = 0.f;
-                    T = 1.f - ca;
-                    if (ca > 0.99f) { const float a = ca; cr /= a; cg /= a; cb /= a; ca /= a; done = true; break; }
+                if (sw > 0.f) {        // same in all lanes of the group
+                    const bool insert = batch8 ? (j == 0 && pre_blend) : (__shfl_sync(gmask, my_t_after, src) > t_surface);
+                    if (insert) {
+                        cr += sr * sw * T; cg += sg * sw * T; cb += sb * sw * T; ca += sw * T;
+                        sw = 0.f;
+                        T = 1.f - ca;
+                        if (ca > 0.99f) { const float a = ca; cr /= a; cg /= a; cb /= a; ca /= a; done = true; break; }
+                    }
                 }
-                const float alpha = 1.f - __expf(-act_density(r3, P.density_activation) * dt);
                 const float weight = alpha * T;
-                cr += act_rgb(r0, P.rgb_activation) * weight;
-                cg += act_rgb(r1, P.rgb_activation) * weight;
-                cb += act_rgb(r2, P.rgb_activation) * weight;
+                cr += r0 * weight; cg += r1 * weight; cb += r2 * weight;
                 ca += weight;
-                if (weight > max_weight) {
-                    max_weight = weight;
-                    const V3 tdiag = v3(P.taabb_max[0] - P.taabb_min[0], P.taabb_max[1] - P.taabb_min[1], P.taabb_max[2] - P.taabb_min[2]);
-                    const V3 pos = v3(P.taabb_min[0] + px * tdiag.x, P.taabb_min[1] + py * tdiag.y, P.taabb_min[2] + pz * tdiag.z);
-                    const V3 dd = vsub(pos, v3(P.cam[9], P.cam[10], P.cam[11]));   // NeRF-space sample vs world-space eye, as in the reference
-                    depth = sqrtf(edot(dd, dd));
-                }
+                if (weight > max_weight) { max_weight = weight; depth = __shfl_sync(gmask, a_depth, src); }
                 if (ca > (1.0f - P.min_transmittance)) { const float a = ca; cr /= a; cg /= a; cb /= a; ca /= a; done = true; break; }
             }
-            if (done) pending_finish = true;
+            // a batch that came back short because the walk ended (box exit, opaque mesh surface) is the ray's last one: the
+            // reference kills the ray when it produced fewer than n_steps samples (S/ngp/testbed.cu:886-901)
+            if (done || ended) pending_finish = true;
             else t = t_batch_end;      // also the resume point of a paused empty-space walk
         }
     }
@@ -732,15 +744,15 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? 3 : 2) ma
 constexpr int kMarchCtasPerSm = 3;   // __launch_bounds__(256, 3): 24 warps, 3 x 128 tensor-memory columns, 3 x 53 KB shared memory per SM
 
 void launch_march(const FrameParams& P, const DeviceModel& M, const float4* d_queue, uint32_t* d_counters, const FrameOut& out,
-                  uint32_t debug_flags, int num_sms, cudaStream_t s) {
+                  uint32_t n_pixels, uint32_t debug_flags, int num_sms, cudaStream_t s) {
     if (debug_flags & kDebugScalarMlp) {
         static bool attr_set = false;
         if (!attr_set) { cudaFuncSetAttribute(march_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmem)); attr_set = true; }
-        march_kernel<false><<<num_sms * 2, kTile, sizeof(MarchSmem), s>>>(P, M, d_queue, d_counters, out, debug_flags);
+        march_kernel<false><<<num_sms * 2, kTile, sizeof(MarchSmem), s>>>(P, M, d_queue, d_counters, out, n_pixels, debug_flags);
     } else {
         static bool attr_set = false;
         if (!attr_set) { cudaFuncSetAttribute(march_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmemTC)); attr_set = true; }
-        march_kernel<true><<<num_sms * kMarchCtasPerSm, kTile * kGroupsTC, sizeof(MarchSmemTC), s>>>(P, M, d_queue, d_counters, out, debug_flags);
+        march_kernel<true><<<num_sms * kMarchCtasPerSm, kTile * kGroupsTC, sizeof(MarchSmemTC), s>>>(P, M, d_queue, d_counters, out, n_pixels, debug_flags);
     }
 }
 

@@ -22,7 +22,7 @@ def scene(small_snapshot, glasses_gltf):
     nerf = r.load_nerf(path)
     assert nerf is not None
     r.orbit(0.35, -0.2, 4.0)     # zoom in so the head fills a good part of the frame
-    return {"r": r, "nerf": nerf, "snap": snap, "gltf": glasses_gltf,
+    return {"r": r, "nerf": nerf, "snap": snap, "path": path, "gltf": glasses_gltf,
             "glasses": {"path": glasses_gltf, "t": synth.GLASSES_T, "s": synth.GLASSES_S, "r": synth.GLASSES_R_WXYZ,
                         "texture": np.tile(np.array([128, 128, 128, 255], dtype=np.uint8), (4, 4, 1))}}
 
@@ -119,22 +119,53 @@ def test_render_no_mesh_pixels(scene):
 
 
 def test_render_hybrid_pixels(scene):
+    import pynmr
     r, nerf, snap, g = scene["r"], scene["nerf"], scene["snap"], scene["glasses"]
     mesh = r.load_mesh(g["path"], t=g["t"], s=g["s"], r=g["r"])
     assert mesh is not None
     rgba2, d2, tri2, surf, ts = H.debug_mesh(r, W, HH)
-    want, frame, ns, stats, (osurf, ots) = H.oracle_scene(snap, W, HH, cam12(r), glasses=g)
+    # n_steps_mode 1: the oracle replays the reference's wavefront loop, n_steps = clamp(pixels / live rays, 1, 8), which
+    # decides in front of which sample a mesh surface is blended (S/ngp/testbed.cu:843, 1996) - pinned against the
+    # reference's own renderer in test_gpu_vs_reference.py.  n_steps_mode 0: surface at its exact position.
+    want, frame, ns, stats, (osurf, ots) = H.oracle_scene(snap, W, HH, cam12(r), glasses=g, n_steps_mode=1)
+    want_exact = H.oracle_scene(snap, W, HH, cam12(r), glasses=g, n_steps_mode=0)[0]
     covered = float((ots > 0).mean())
     assert covered > 0.003, "glasses should cover part of the frame"
+    assert stats["alive_after_first_hit"] * 8 <= W * HH          # the framing where the reference runs 8-sample batches
+    assert np.max(np.abs(want - want_exact)) > 10 * PIX_TOL      # ... and where that choice is visible
     # mesh stage: same triangle test arithmetic -> identical hit depths; colours within libm rounding
     assert np.array_equal(ts.view(np.uint32), ots.view(np.uint32))
     assert np.max(np.abs(surf - osurf)) <= 1e-5
-    img = nerf.render(W, HH, 1, linear=False)
+    img = nerf.render(W, HH, 1, linear=False)                    # NMR_SURFACE_AUTO -> the reference's batches here
     assert np.max(np.abs(np.asarray(img) - want)) <= PIX_TOL
     assert H.psnr(np.asarray(img), want) >= 45.0
     # frame() renders the same hybrid image at the constructor resolution
     assert r.frame()
     assert np.max(np.abs(np.asarray(r.read_frame()) - want)) <= PIX_TOL
+    r.set_surface_insertion(pynmr.NerfMeshRenderer.SURFACE_EXACT)
+    try:
+        img = np.asarray(nerf.render(W, HH, 1, linear=False)).copy()
+    finally:
+        r.set_surface_insertion(pynmr.NerfMeshRenderer.SURFACE_AUTO)
+    assert np.max(np.abs(img - want_exact)) <= PIX_TOL
+
+
+def test_render_hybrid_pixels_close_up(scene):
+    """More than 1/8 of the pixels live: NMR_SURFACE_AUTO inserts the surface at its exact sample (oracle n_steps_mode 0)."""
+    import pynmr
+    snap, g = scene["snap"], scene["glasses"]
+    w, h = 96, 54
+    r = pynmr.NerfMeshRenderer(w, h)
+    nerf = r.load_nerf(scene["path"])
+    assert r.load_mesh(g["path"], t=g["t"], s=g["s"], r=g["r"]) is not None
+    r.orbit(0.2, -0.1, 9.0)                     # orbit radius is clamped to >= 1: walk the eye half-way in along the view axis
+    m = r.view_projection_mat
+    m[:, 3] += 0.5 * m[:, 2]
+    r.view_projection_mat = m
+    want, _, _, stats, _ = H.oracle_scene(snap, w, h, cam12(r), glasses=g, n_steps_mode=0)
+    assert stats["alive_after_first_hit"] * 8 > w * h
+    img = np.asarray(nerf.render(w, h, 1, linear=False))
+    assert np.max(np.abs(img - want)) <= PIX_TOL
 
 
 def test_accumulation_and_linear_output(scene):

@@ -8,7 +8,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--frames", type=int, default=4)
 ap.add_argument("--width", type=int, default=1920); ap.add_argument("--height", type=int, default=1080)
 ap.add_argument("--log2T", type=int, default=19); ap.add_argument("--regime", default="opaque"); ap.add_argument("--zoom", type=float, default=0.0)
-ap.add_argument("--no-mesh", action="store_true")
+ap.add_argument("--no-mesh", action="store_true"); ap.add_argument("--surface-mode", type=int, default=0)
 a = ap.parse_args()
 with tempfile.TemporaryDirectory() as d:
     snap = os.path.join(d, "s.msgpack"); synth.write_snapshot(snap, seed=1337, log2_hashmap_size=a.log2T, regime=a.regime)
@@ -18,6 +18,7 @@ with tempfile.TemporaryDirectory() as d:
     if not a.no_mesh:
         r.load_mesh(gltf, t=synth.GLASSES_T, s=synth.GLASSES_S, r=synth.GLASSES_R_WXYZ)
     r.remove_floaties()
+    r.set_surface_insertion(a.surface_mode)
 if a.zoom:
     r.orbit(0, 0, a.zoom)
 for i in range(a.frames):
