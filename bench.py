@@ -46,6 +46,17 @@ def measured_peaks():
         return 6650.0, "fallback"
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one march_kernel launch of this workload, from the committed
+    `ncu --set full` capture (profiles/r1_march_opaque_summary.json); None when the summary is missing."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_march_opaque_summary.json")) as f:
+            d = json.load(f)
+        return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -56,7 +67,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -195,7 +206,7 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
         "e2e": {"value": rays_all / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 48, "d2h_bytes_per_step": W * H * 16,
                 "fps": args.steps * world / e2e_s, "api": "pynmr.Testbed.render(width, height, 1, linear=False) -> pinned float32[H,W,4]"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_bytes(),
                      "kernel": "march_kernel<tcgen05>", "peak_source": peak_src + " copy bandwidth (MEASURED_PEAKS.json)",
                      "algorithmic_bytes_per_sample": ALGO_BYTES_PER_SAMPLE, "samples_per_launch": samples_per_launch,
                      "kernel_ms_per_launch": float(np.mean(march_ms)),
@@ -203,6 +214,60 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
                      "kernel_share_of_step": float(np.sum(march_ms)) / max(float(np.sum(dev_ms)), 1e-12)},
         "checksum": checksum,
     }
+    return out
+
+
+def stress_leg(args, local_rank: int, regime: str, zoom: float, steps: int = 12):
+    """The sample-bound regimes (not the headline): head filling the frame, opaque or translucent medium."""
+    import pynmr
+    import synth
+    W, H = args.width, args.height
+    with tempfile.TemporaryDirectory() as tmp:
+        snap, gltf = make_inputs(tmp, args.log2_hashmap_size, regime)
+        r = pynmr.NerfMeshRenderer(W, H, local_rank)
+        if r.load_nerf(snap) is None or r.load_mesh(gltf, t=synth.GLASSES_T, s=synth.GLASSES_S, r=synth.GLASSES_R_WXYZ) is None:
+            raise RuntimeError("stress inputs failed to load")
+        r.remove_floaties()
+    r.orbit(0.0, 0.0, zoom)
+    a, ms, mms, smp = 0.0, [], [], 0
+    for i in range(steps + 3):
+        a += 0.03; r.orbit(*orbit_step(a)); r.flush_l2(); r.frame_async(); st = r.stats()
+        if i >= 3:
+            ms.append(st["gpu_ms"]); mms.append(st["march_ms"]); smp += st["samples"]
+    tot, mtot = float(np.sum(ms)) / 1e3, float(np.sum(mms)) / 1e3
+    return {"workload": f"{W}x{H} hybrid, {regime} medium, orbit zoom {zoom:g}", "steps": steps, "ms_per_frame": tot / steps * 1e3,
+            "mrays_per_s": W * H * steps / tot / 1e6, "msamples_per_s": smp / tot / 1e6, "samples_per_frame": smp / steps,
+            "march_gbs_algorithmic": ALGO_BYTES_PER_SAMPLE * smp / mtot / 1e9, "march_tflops_algorithmic": ALGO_FLOP_PER_SAMPLE * smp / mtot / 1e12}
+
+
+def reference_gpu_leg(args, local_rank: int):
+    """Informational: the reference's OWN renderer (ngp::Testbed + tiny-cuda-nn recompiled for sm_100,
+    oracle/_ref/libnmr_refgpu.so) on this GPU, same snapshot / camera / mesh buffers; device time of Testbed::render_frame."""
+    from oracle import refgpu
+    if not refgpu.available():
+        return None
+    import helpers
+    import pynmr
+    import synth
+    W, H = args.width, args.height
+    with tempfile.TemporaryDirectory() as tmp:
+        snap, gltf = make_inputs(tmp, args.log2_hashmap_size, args.regime)
+        ref = refgpu.ReferenceRenderer(snap)
+        r = pynmr.NerfMeshRenderer(W, H, local_rank)
+        nerf = r.load_nerf(snap)
+        r.load_mesh(gltf, t=synth.GLASSES_T, s=synth.GLASSES_S, r=synth.GLASSES_R_WXYZ)
+    if args.zoom:
+        r.orbit(0.0, 0.0, args.zoom)
+    cam12 = np.ascontiguousarray(r.view_projection_mat.T.reshape(-1))
+    _, _, _, surf, ts = helpers.debug_mesh(r, W, H)
+    img_ref, ms = ref.render(cam12, W, H, 1, False, surf=surf, ts=ts, repeat=5)
+    ours = np.asarray(nerf.render(W, H, 1, linear=False))
+    st = r.stats()
+    d = np.abs(ours - img_ref)
+    out = {"what": "reference NeRF renderer (Testbed::render_frame, mesh hand-off buffers supplied) on the same GPU, floatie removal off, best of 5",
+           "ms_per_frame": ms, "mrays_per_s": W * H / ms / 1e3, "ours_ms_same_frame": st["gpu_ms"],
+           "max_abs_pixel_diff": float(d.max()), "psnr_db": float(helpers.psnr(ours, img_ref)), "pixels_over_2_255": int((d.max(axis=2) > 2 / 255).sum())}
+    ref.close()
     return out
 
 
@@ -271,7 +336,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--width", type=int, default=1920)
@@ -282,6 +347,7 @@ def main():
     ap.add_argument("--cpu-crop", type=int, nargs=2, default=[256, 144])
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the stress and reference-on-GPU legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -301,6 +367,12 @@ def main():
         dist = td
     out = run_ours(args, rank, world, local_rank, dist)
     if rank == 0:
+        if world == 1 and not args.no_extras:
+            out["stress"] = [stress_leg(args, local_rank, "opaque", 4.0), stress_leg(args, local_rank, "translucent", 4.0)]
+            try:
+                out["reference_gpu"] = reference_gpu_leg(args, local_rank)
+            except Exception as e:   # test infrastructure; never fails the bench
+                out["reference_gpu"] = {"error": str(e)[:200]}
         if not args.no_cpu_baseline:
             res = oracle_sample(args, args.cpu_steps, 1)
             out["cpu_baseline"] = {"value": res["rays"] / res["seconds"] / 1e6, "unit": "Mrays/s", "cores": res["cores"], "kind": "port",
