@@ -100,6 +100,7 @@ struct nmr_ctx {
     DevBuf<float> d_wpos, d_wnrm, d_uv, d_tex;
     DevBuf<uint32_t> d_idx;
     MeshDevice mesh_dev{};
+    float mesh_wmin[3] = {0.f, 0.f, 0.f}, mesh_wmax[3] = {0.f, 0.f, 0.f};   // world-space box of the concatenated mesh
     Surfaces surf;
     DevBuf<uint32_t> d_counters;
     uint32_t* h_counters = nullptr;                       // pinned
@@ -169,6 +170,11 @@ void upload_mesh_if_dirty(nmr_ctx* ctx) {
     }
     MeshDevice d{};
     d.n_tris = (uint32_t)(idx.size() / 3);
+    for (int k = 0; k < 3; ++k) { ctx->mesh_wmin[k] = 1e30f; ctx->mesh_wmax[k] = -1e30f; }
+    for (size_t i = 0; i < wpos.size(); ++i) {
+        ctx->mesh_wmin[i % 3] = std::min(ctx->mesh_wmin[i % 3], wpos[i]);
+        ctx->mesh_wmax[i % 3] = std::max(ctx->mesh_wmax[i % 3], wpos[i]);
+    }
     if (d.n_tris) {
         ctx->d_wpos.ensure(wpos.size()); ctx->d_wnrm.ensure(wnrm.size()); ctx->d_uv.ensure(uv.size()); ctx->d_idx.ensure(idx.size());
         CK(cudaMemcpyAsync(ctx->d_wpos.p, wpos.data(), wpos.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -227,6 +233,35 @@ void update_occupied_box(nmr_ctx* ctx, Nerf& n) {
     }
 }
 
+// Screen bounding box of the mesh's world-space box in the supersampled mesh frame, padded by two sub-pixels and aligned
+// to whole pixels; the whole frame when a corner lies behind the eye.  Only that window of the visibility buffer is
+// cleared, rasterised into and read back.
+void mesh_screen_box(const nmr_ctx* ctx, FrameParams& P) {
+    P.zb_x0 = P.zb_y0 = P.zb_w = P.zb_h = 0;
+    if (P.mesh_scale <= 0) return;
+    const int ms = P.mesh_scale, W2 = P.width * ms, H2 = P.height * ms;
+    float minx = 1e30f, miny = 1e30f, maxx = -1e30f, maxy = -1e30f;
+    bool behind = false;
+    for (int c = 0; c < 8 && !behind; ++c) {
+        const float q[3] = {((c & 1) ? ctx->mesh_wmax[0] : ctx->mesh_wmin[0]) - P.cam[9], ((c & 2) ? ctx->mesh_wmax[1] : ctx->mesh_wmin[1]) - P.cam[10],
+                            ((c & 4) ? ctx->mesh_wmax[2] : ctx->mesh_wmin[2]) - P.cam[11]};
+        const float a = P.cam_inv[0] * q[0] + P.cam_inv[1] * q[1] + P.cam_inv[2] * q[2];
+        const float b = P.cam_inv[3] * q[0] + P.cam_inv[4] * q[1] + P.cam_inv[5] * q[2];
+        const float w = P.cam_inv[6] * q[0] + P.cam_inv[7] * q[1] + P.cam_inv[8] * q[2];
+        if (!(w > 1e-3f)) { behind = true; break; }
+        const float px = (a / w + 1.0f) * 0.5f * (float)W2 - 0.5f, py = (b / w + 1.0f) * 0.5f * (float)H2 - 0.5f;
+        minx = std::min(minx, px); maxx = std::max(maxx, px); miny = std::min(miny, py); maxy = std::max(maxy, py);
+    }
+    int x0 = 0, y0 = 0, x1 = W2, y1 = H2;    // [x0, x1) x [y0, y1)
+    if (!behind) {
+        if (!(maxx >= -4.f && maxy >= -4.f && minx <= (float)W2 + 4.f && miny <= (float)H2 + 4.f)) return;   // off screen
+        x0 = std::max(0, ((int)std::floor(minx) - 2) / ms * ms); y0 = std::max(0, ((int)std::floor(miny) - 2) / ms * ms);
+        x1 = std::min(W2, (((int)std::ceil(maxx) + 3 + ms - 1) / ms) * ms); y1 = std::min(H2, (((int)std::ceil(maxy) + 3 + ms - 1) / ms) * ms);
+        if (x1 <= x0 || y1 <= y0) return;
+    }
+    P.zb_x0 = x0; P.zb_y0 = y0; P.zb_w = x1 - x0; P.zb_h = y1 - y0;
+}
+
 FrameParams make_params(nmr_ctx* ctx, const Nerf& n, int W, int H, const float* cam12, uint32_t spp_index, bool to_srgb, bool with_mesh) {
     FrameParams P{};
     P.width = W; P.height = H;
@@ -244,12 +279,22 @@ FrameParams make_params(nmr_ctx* ctx, const Nerf& n, int W, int H, const float* 
         P.background_linear[k] = sv <= 0.04045f ? sv / 12.92f : powf((sv + 0.055f) / 1.055f, 2.4f);
     }
     P.to_srgb = to_srgb ? 1 : 0;
+    {   // accumulate_kernel + tonemap_kernel of an empty pixel (S/ngp/render_buffer.cu:232-267, 537-566)
+        const float w = (1.f - 0.f) * n.background[3];
+        for (int k = 0; k < 3; ++k) {
+            float c = 0.f + P.background_linear[k] * w;
+            if (to_srgb) { c = c < 0.0031308f ? 12.92f * c : 1.055f * powf(c, 0.41666f) - 0.055f; c = std::min(std::max(c, 0.f), 1.f); }
+            P.background_out[k] = c;
+        }
+        P.background_out[3] = to_srgb ? std::min(std::max(0.f + w, 0.f), 1.f) : 0.f + w;
+    }
     P.shard_rank = ctx->shard_rank; P.shard_world = ctx->shard_world; P.shard_band = ctx->shard_band;
     P.mesh_scale = (with_mesh && ctx->mesh_dev.n_tris > 0) ? ctx->mesh_scale : 0;
     std::memcpy(P.light, ctx->light, 12);
     invert3(cam12, P.cam_inv);
     std::memcpy(P.occ_min, n.occ_min, 12); std::memcpy(P.occ_max, n.occ_max, 12);
     P.surface_mode = ctx->surface_mode;
+    mesh_screen_box(ctx, P);
     return P;
 }
 
@@ -257,11 +302,13 @@ FrameParams make_params(nmr_ctx* ctx, const Nerf& n, int W, int H, const float* 
 void enqueue_pass(nmr_ctx* ctx, Nerf& n, const FrameParams& P, bool timed) {
     Surfaces& S = ctx->surf;
     const int rows = rows_owned_by(P.height, P.shard_rank, P.shard_world, P.shard_band);
-    FrameOut out{S.image.p, S.accum.p, S.frame.p, S.depth.p, S.n_samples.p};
+    // the linear frame, depth and per-ray sample counts are parity probes (nmr_debug_last_frame): written only on request
+    const bool probes = (ctx->debug_flags & kDebugKeepProbes) != 0;
+    FrameOut out{S.image.p, S.accum.p, probes ? S.frame.p : nullptr, probes ? S.depth.p : nullptr, probes ? S.n_samples.p : nullptr};
     if (timed) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     uint64_t launches = 0;
     if (P.mesh_scale > 0) { launch_mesh_raster(ctx->mesh_dev, P, rows, S.zbuf.p, ctx->stream); launches += 1; }
-    launch_init_rays(P, n.dev, ctx->mesh_dev, S.zbuf.p, rows, S.queue.p, ctx->d_counters.p, out, ctx->stream);
+    launch_init_rays(P, n.dev, ctx->mesh_dev, S.zbuf.p, rows, S.queue.p, ctx->d_counters.p, out, ctx->num_sms, ctx->stream);
     launches += 1;
     if (timed) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     launch_march(P, n.dev, S.queue.p, ctx->d_counters.p, out, (uint32_t)P.width * (uint32_t)rows, ctx->debug_flags, ctx->num_sms, ctx->stream);
@@ -715,6 +762,7 @@ NMR_API int nmr_debug_mesh(nmr_ctx* ctx, int width, int height, float* o_rgba2, 
         P.width = width; P.height = height; std::memcpy(P.cam, ctx->cam12, sizeof(P.cam));
         P.shard_world = 1; P.shard_band = 8; P.mesh_scale = ms; std::memcpy(P.light, ctx->light, 12);
         invert3(ctx->cam12, P.cam_inv);
+        mesh_screen_box(ctx, P);
         launch_mesh_raster(ctx->mesh_dev, P, height, zbuf.p, ctx->stream);
         launch_debug_mesh(ctx->mesh_dev, P, zbuf.p, d_rgba2.p, d_depth2.p, d_tri2.p, d_surf.p, d_ts.p, ctx->stream);
         if (o_rgba2) CK(cudaMemcpyAsync(o_rgba2, d_rgba2.p, n2 * 16, cudaMemcpyDeviceToHost, ctx->stream));

@@ -55,6 +55,7 @@ struct FrameParams {
     int rgb_activation, density_activation;
     float background[4];
     float background_linear[3];       // srgb_to_linear(background), evaluated on the host
+    float background_out[4];          // displayed value of a pixel that hit nothing (accumulate + tonemap of zero), see finish_pixel
     int to_srgb;
     int shard_rank, shard_world, shard_band;
     int mesh_scale;                   // 0: no mesh stage
@@ -62,6 +63,10 @@ struct FrameParams {
     float cam_inv[9];                 // inverse of [U V W] (row-major), for the rasteriser's bounding boxes
     float occ_min[3], occ_max[3];     // box around every occupied grid cell a sample can test, inflated by one cell
     int surface_mode;                 // where a partially covering mesh surface enters the compositing order: SurfaceMode
+    // The mesh visibility buffer covers only the screen bounding box of the mesh (sub-pixel units of the mesh_scale x
+    // supersampled frame, aligned to whole pixels): zb_w == 0 means "mesh not in view".  Entry (x, y) lives at
+    // (y - zb_y0) * zb_w + (x - zb_x0).
+    int zb_x0, zb_y0, zb_w, zb_h;
 };
 
 // The reference blends the mesh surface in front of the first sample of the n_steps BATCH whose end passed t_surface
@@ -176,11 +181,15 @@ __device__ __forceinline__ float distance_to_next_voxel(V3 pos, V3 dir, V3 idir,
     const float ty = (floorf(p.y + 0.5f + 0.5f * copysignf(1.0f, dir.y)) - p.y) * idir.y;
     const float tz = (floorf(p.z + 0.5f + 0.5f * copysignf(1.0f, dir.z)) - p.z) * idir.z;
     const float t = fminf(fminf(tx, ty), tz);
-    return fmaxf(t / r, 0.0f);
+    // res is a power of two (128 >> mip): multiplying by its reciprocal is the division, exactly (the quotient of a normal
+    // float by 2^k is never inexact above the subnormal range, and t / r is then flushed to >= 0 by the max anyway)
+    return fmaxf(t * __uint_as_float((254u << 23) - __float_as_uint(r)), 0.0f);
 }
-__device__ __forceinline__ float advance_to_next_voxel(float t, float cone_angle, V3 pos, V3 dir, V3 idir, uint32_t res) {
+// uniform_dt: the cone angle is zero, so calc_dt(t, 0) = clamp(t * 0) is the constant minimum step for every finite t
+__device__ __forceinline__ float advance_to_next_voxel(float t, float cone_angle, bool uniform_dt, V3 pos, V3 dir, V3 idir, uint32_t res) {
     const float t_target = t + distance_to_next_voxel(pos, dir, idir, res);
-    do { t += calc_dt(t, cone_angle); } while (t < t_target);
+    if (uniform_dt) { const float dt0 = min_cone_stepsize(); do { t += dt0; } while (t < t_target); }
+    else { do { t += calc_dt(t, cone_angle); } while (t < t_target); }
     return t;
 }
 
@@ -210,14 +219,15 @@ __device__ __forceinline__ V3 r2l_mul(const float* m, V3 p) {   // Eigen Matrix3
 }
 
 // ---- ray set-up (S/ngp/ngp_common.cuh:362-368; S/ngp/testbed.cu:435-464) ---------------------------------------
-struct RayInit { V3 origin, dir; float t; float t_limit; bool alive; };
+struct RayInit { V3 origin, dir; float t; float t_occ_in, t_limit; bool alive; };   // [t_occ_in, t_limit]: ray inside the box around the occupied cells
 
 // Far intersection of the ray with the box around all occupied cells (negative when the ray misses it).  Past that
 // parameter no sample can land in an occupied cell, so a walk may stop there: the reference's own walk would only step
 // through empty cells until it leaves the render box (S/ngp/testbed.cu:506-532, 600-625) - same result, no arithmetic on t.
-__device__ __forceinline__ float occupied_exit(const FrameParams& P, V3 o, V3 d) {
+__device__ __forceinline__ float occupied_exit(const FrameParams& P, V3 o, V3 d, float& t_in) {
     float tmin = -3.402823466e+38f, tmax = 3.402823466e+38f;
     const float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+    t_in = 3.402823466e+38f;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         if (dd[k] != 0.f) {
@@ -228,8 +238,11 @@ __device__ __forceinline__ float occupied_exit(const FrameParams& P, V3 o, V3 d)
             return -1.f;
         }
     }
-    return tmin <= tmax ? tmax : -1.f;
+    if (!(tmin <= tmax)) return -1.f;
+    t_in = tmin;
+    return tmax;
 }
+
 __device__ __forceinline__ RayInit init_ray(const FrameParams& P, uint32_t x, uint32_t y) {
     const float* c = P.cam;
     const float ux = 2.0f * (((float)x + 0.5f) / (float)P.width) - 1.0f;
@@ -242,13 +255,13 @@ __device__ __forceinline__ RayInit init_ray(const FrameParams& P, uint32_t x, ui
     r.dir = d;
     r.t = fmaxf(box_ray_tmin(P.aabb_min, P.aabb_max, r.origin, d), 0.0f) + 1e-6f;
     r.alive = box_contains(P.aabb_min, P.aabb_max, vadd(r.origin, vmul(d, r.t)));
-    r.t_limit = occupied_exit(P, r.origin, d);
+    r.t_limit = occupied_exit(P, r.origin, d, r.t_occ_in);
     return r;
 }
 
 // advance_pos_nerf (S/ngp/testbed.cu:470-537); returns alive
 __device__ __forceinline__ bool advance_pos(const FrameParams& P, const uint8_t* __restrict__ bitfield, V3 origin, V3 dir, uint32_t pixel_idx,
-                                            float t_surface, float t_limit, bool alive, float& t_io, float& t_start) {
+                                            float t_surface, float t_occ_in, float t_limit, bool alive, float& t_io, float& t_start) {
     t_start = 0.f;
     if (!alive) {
         if (t_surface != 0.0f) { t_io = t_surface; return true; }
@@ -259,6 +272,7 @@ __device__ __forceinline__ bool advance_pos(const FrameParams& P, const uint8_t*
     float t = t_io;
     float dt = calc_dt(t, cone);
     t += ld_random_val(P.spp_index, pixel_idx * 786433u) * dt;
+    const bool uniform_dt = cone == 0.0f;
     while (true) {
         if (t_surface != 0.0f && t > t_surface) { t_io = t_surface; return true; }
         const V3 pos = vadd(origin, vmul(dir, t));
@@ -267,10 +281,11 @@ __device__ __forceinline__ bool advance_pos(const FrameParams& P, const uint8_t*
             alive = false;
             break;
         }
-        dt = calc_dt(t, cone);
+        dt = uniform_dt ? min_cone_stepsize() : calc_dt(t, cone);
         const uint32_t mip = (uint32_t)mip_from_dt(dt, pos);
-        if (occupied_at(pos, bitfield, mip)) break;
-        t = advance_to_next_voxel(t, cone, pos, dir, idir, NERF_GRIDSIZE >> mip);
+        // before the ray enters the box around the occupied cells every test is known to fail: no load, no Morton code
+        if (t >= t_occ_in && occupied_at(pos, bitfield, mip)) break;
+        t = advance_to_next_voxel(t, cone, uniform_dt, pos, dir, idir, NERF_GRIDSIZE >> mip);
     }
     t_io = t;
     if (mip_from_pos(vadd(origin, vmul(dir, t))) == 0) t_start = t;
@@ -287,6 +302,7 @@ struct Sample { V3 pos; float dt_warped; float t; uint32_t cell, mip; };
 __device__ __forceinline__ int next_sample(const FrameParams& P, const uint8_t* __restrict__ bitfield, V3 origin, V3 dir, V3 idir,
                                         float t_start, float t_surface, float surf_w, float t_limit, bool ignore_surface, int budget, float& t_io, Sample& s) {
     const float cone = P.cone_angle;
+    const bool uniform_dt = cone == 0.0f;
     float t = t_io;
     V3 pos; float dt; uint32_t mip, cell;
     while (true) {
@@ -294,10 +310,10 @@ __device__ __forceinline__ int next_sample(const FrameParams& P, const uint8_t* 
         if (t > t_limit) return 0;                 // no occupied cell ahead: the walk could only run out of the render box
         pos = vadd(origin, vmul(dir, t));
         if (!box_contains(P.aabb_min, P.aabb_max, r2l_mul(P.r2l, pos))) return 0;
-        dt = calc_dt(t - t_start, cone);
+        dt = uniform_dt ? min_cone_stepsize() : calc_dt(t - t_start, cone);
         mip = (uint32_t)mip_from_dt(dt, pos);
         if (occupied_at(pos, bitfield, mip, &cell)) break;
-        t = advance_to_next_voxel(t, cone, pos, dir, idir, NERF_GRIDSIZE >> mip);
+        t = advance_to_next_voxel(t, cone, uniform_dt, pos, dir, idir, NERF_GRIDSIZE >> mip);
         if (--budget <= 0) { t_io = t; return 2; }
     }
     const V3 diag = v3(P.taabb_max[0] - P.taabb_min[0], P.taabb_max[1] - P.taabb_min[1], P.taabb_max[2] - P.taabb_min[2]);

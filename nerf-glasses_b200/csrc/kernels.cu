@@ -110,7 +110,9 @@ __global__ void __launch_bounds__(256) mesh_raster_kernel(MeshDevice mesh, Frame
     if (tri >= mesh.n_tris) return;
     const V3 eye = v3(P.cam[9], P.cam[10], P.cam[11]);
     const V3 v0 = ld3(mesh.wpos, __ldg(mesh.idx + tri * 3)), v1 = ld3(mesh.wpos, __ldg(mesh.idx + tri * 3 + 1)), v2 = ld3(mesh.wpos, __ldg(mesh.idx + tri * 3 + 2));
-    int x0 = 0, y0 = 0, x1 = W2 - 1, y1 = H2 - 1;
+    // the visibility buffer only exists inside the mesh's screen bounding box
+    const int bx0 = P.zb_x0, by0 = P.zb_y0, bx1 = P.zb_x0 + P.zb_w - 1, by1 = P.zb_y0 + P.zb_h - 1;
+    int x0 = bx0, y0 = by0, x1 = bx1, y1 = by1;
     {
         const V3 vs[3] = {v0, v1, v2};
         float minx = 1e30f, miny = 1e30f, maxx = -1e30f, maxy = -1e30f;
@@ -127,8 +129,8 @@ __global__ void __launch_bounds__(256) mesh_raster_kernel(MeshDevice mesh, Frame
         }
         if (!behind) {
             if (maxx < -2.f || maxy < -2.f || minx > (float)W2 + 1.f || miny > (float)H2 + 1.f) return;
-            x0 = max(0, (int)floorf(minx) - 1); y0 = max(0, (int)floorf(miny) - 1);
-            x1 = min(W2 - 1, (int)ceilf(maxx) + 1); y1 = min(H2 - 1, (int)ceilf(maxy) + 1);
+            x0 = max(bx0, (int)floorf(minx) - 1); y0 = max(by0, (int)floorf(miny) - 1);
+            x1 = min(bx1, (int)ceilf(maxx) + 1); y1 = min(by1, (int)ceilf(maxy) + 1);
             if (x1 < x0 || y1 < y0) return;
         }
     }
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(256) mesh_raster_kernel(MeshDevice mesh, Frame
         float t, u, v;
         if (ray_tri(eye, dir, v0, v1, v2, t, u, v) && t < 1e16f) {
             const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | tri;
-            atomicMin(zbuf + (size_t)y * W2 + x, key);
+            atomicMin(zbuf + (size_t)(y - by0) * P.zb_w + (x - bx0), key);
         }
     }
 }
@@ -150,8 +152,8 @@ __global__ void __launch_bounds__(256) mesh_raster_kernel(MeshDevice mesh, Frame
 void launch_mesh_raster(const MeshDevice& mesh, const FrameParams& P, int rows_owned, unsigned long long* d_zbuf, cudaStream_t s) {
     (void)rows_owned;
     const int W2 = P.width * P.mesh_scale, H2 = P.height * P.mesh_scale;
-    cudaMemsetAsync(d_zbuf, 0xFF, (size_t)W2 * H2 * sizeof(unsigned long long), s);
-    if (mesh.n_tris == 0) return;
+    if (mesh.n_tris == 0 || P.zb_w <= 0 || P.zb_h <= 0) return;
+    cudaMemsetAsync(d_zbuf, 0xFF, (size_t)P.zb_w * P.zb_h * sizeof(unsigned long long), s);
     const uint32_t threads = mesh.n_tris * 32u;
     mesh_raster_kernel<<<(threads + 255) / 256, 256, 0, s>>>(mesh, P, W2, H2, d_zbuf);
 }
@@ -159,7 +161,8 @@ void launch_mesh_raster(const MeshDevice& mesh, const FrameParams& P, int rows_o
 // closest hit of one sub-pixel -> shaded RGBA (alpha 1) and hitT; false on miss
 __device__ __forceinline__ bool mesh_tap(const MeshDevice& mesh, const FrameParams& P, const unsigned long long* __restrict__ zbuf, int x, int y, int W2, int H2,
                                          float rgba[4], float& hit_t, int32_t* tri_out = nullptr) {
-    const unsigned long long key = __ldg(zbuf + (size_t)y * W2 + x);
+    const int rx = x - P.zb_x0, ry = y - P.zb_y0;
+    const unsigned long long key = (rx >= 0 && ry >= 0 && rx < P.zb_w && ry < P.zb_h) ? __ldg(zbuf + (size_t)ry * P.zb_w + rx) : kZMiss;
     if (key == kZMiss) { if (tri_out) *tri_out = -1; return false; }
     const uint32_t tri = (uint32_t)(key & 0xFFFFFFFFull);
     const V3 eye = v3(P.cam[9], P.cam[10], P.cam[11]);
@@ -178,6 +181,11 @@ __device__ __forceinline__ void mesh_resolve(const MeshDevice& mesh, const Frame
                                              float surf[4], float& t_surface) {
     const int ms = P.mesh_scale, W2 = P.width * ms, H2 = P.height * ms;
     float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f, depth = 0.f;
+    // the box is aligned to whole pixels: a pixel outside it has no tap inside it (0 + 0 + ... / q == 0 exactly)
+    if (px * ms < P.zb_x0 || py * ms < P.zb_y0 || px * ms >= P.zb_x0 + P.zb_w || py * ms >= P.zb_y0 + P.zb_h) {
+        surf[0] = surf[1] = surf[2] = surf[3] = 0.f; t_surface = 0.f;
+        return;
+    }
     for (int i = 0; i < ms; ++i) {
         for (int j = 0; j < ms; ++j) {
             float rgba[4]; float ht;
@@ -208,6 +216,12 @@ __device__ __forceinline__ void finish_pixel(const FrameParams& P, const FrameOu
     if (out.frame) out.frame[idx] = fb;
     if (out.depth) out.depth[idx] = d;
     if (out.n_samples) out.n_samples[idx] = n_samples;
+    if (a <= 0.001f && P.spp_index == 0) {
+        // nothing hit on the first sample of an accumulation: the pixel is the tonemapped background, a per-frame constant
+        out.accum[idx] = fb;
+        out.image[idx] = make_float4(P.background_out[0], P.background_out[1], P.background_out[2], P.background_out[3]);
+        return;
+    }
     float4 acc = fb;
     if (P.spp_index != 0) {
         const float sc = (float)P.spp_index;
@@ -231,22 +245,45 @@ __device__ __forceinline__ void finish_pixel(const FrameParams& P, const FrameOu
 // init_rays_kernel: init_rays_with_payload_kernel_nerf + mesh hand-off + advance_pos_nerf
 // (S/ngp/testbed.cu:355-537; S/nerf_mesh_renderer.cu:64-100)
 // =================================================================================================================
-__global__ void __launch_bounds__(128) init_rays_kernel(FrameParams P, DeviceModel M, MeshDevice mesh, const unsigned long long* __restrict__ zbuf, int rows_owned,
-                                                        float4* __restrict__ queue, uint32_t* __restrict__ counters, FrameOut out) {
-    // 16 x 8 pixel block, each warp an 8 x 4 tile so queue neighbours are screen neighbours
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-    const int ly = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
-    if (x >= P.width || ly >= rows_owned) return;
-    const int y = shard_row(P, ly);
+__device__ __forceinline__ void init_one_ray(const FrameParams& P, const DeviceModel& M, const MeshDevice& mesh, const unsigned long long* __restrict__ zbuf,
+                                             float4* __restrict__ queue, uint32_t* __restrict__ counters, const FrameOut& out, int x, int y) {
     const uint32_t idx = (uint32_t)x + (uint32_t)P.width * (uint32_t)y;
 
-    RayInit r = init_ray(P, (uint32_t)x, (uint32_t)y);
     float surf[4] = {0.f, 0.f, 0.f, 0.f};
     float t_surface = 0.f;
     if (P.mesh_scale > 0) mesh_resolve(mesh, P, zbuf, x, y, surf, t_surface);
+
+    // Most pixels see neither the mesh nor any occupied cell: their ray misses the box around the occupied cells, so
+    // advance_pos_nerf could only walk it out of the render box (dead ray, background pixel).  Decide that with the
+    // un-normalised direction and approximate reciprocals - the box carries a whole grid cell of margin - before paying for
+    // the exact ray set-up.
+    if (t_surface == 0.0f) {
+        const float* c = P.cam;
+        const float ux = 2.0f * (((float)x + 0.5f) / (float)P.width) - 1.0f;
+        const float uy = 2.0f * (((float)y + 0.5f) / (float)P.height) - 1.0f;
+        const float d[3] = {c[0] * ux + (c[3] * uy + c[6]), c[1] * ux + (c[4] * uy + c[7]), c[2] * ux + (c[5] * uy + c[8])};
+        const float o[3] = {c[9] + 0.5f, c[10] + 0.5f, c[11] + 0.5f};
+        float tmin = 0.f, tmax = 3.402823466e+38f;        // only the part of the line in front of the eye counts
+        bool miss = false;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (fabsf(d[k]) > 1e-12f) {
+                const float inv = __frcp_rn(d[k]);
+                const float a = (P.occ_min[k] - o[k]) * inv, b = (P.occ_max[k] - o[k]) * inv;
+                tmin = fmaxf(tmin, fminf(a, b)); tmax = fminf(tmax, fmaxf(a, b));
+            } else if (o[k] < P.occ_min[k] || o[k] > P.occ_max[k]) {
+                miss = true;
+            }
+        }
+        if (miss || tmin > tmax) {
+            finish_pixel(P, out, idx, 0.f, 0.f, 0.f, 0.f, 0.f, 0u);
+            return;
+        }
+    }
+
+    RayInit r = init_ray(P, (uint32_t)x, (uint32_t)y);
     float t = r.t, t_start;
-    const bool alive = advance_pos(P, M.bitfield, r.origin, r.dir, idx, t_surface, r.t_limit, r.alive, t, t_start);
+    const bool alive = advance_pos(P, M.bitfield, r.origin, r.dir, idx, t_surface, r.t_occ_in, r.t_limit, r.alive, t, t_start);
     if (!alive) {
         finish_pixel(P, out, idx, 0.f, 0.f, 0.f, 0.f, 0.f, 0u);
         return;
@@ -257,9 +294,21 @@ __global__ void __launch_bounds__(128) init_rays_kernel(FrameParams P, DeviceMod
     queue[(size_t)slot * kRayRecordFloat4s + 2] = make_float4(surf[0], surf[1], surf[2], surf[3]);
 }
 
+__global__ void __launch_bounds__(128) init_rays_kernel(FrameParams P, DeviceModel M, MeshDevice mesh, const unsigned long long* __restrict__ zbuf, int rows_owned,
+                                                        float4* __restrict__ queue, uint32_t* __restrict__ counters, FrameOut out) {
+    // 16 x 8 pixel block, each warp an 8 x 4 tile so queue neighbours are screen neighbours
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    const int ly = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    if (x >= P.width || ly >= rows_owned) return;
+    init_one_ray(P, M, mesh, zbuf, queue, counters, out, x, shard_row(P, ly));
+}
+
 void launch_init_rays(const FrameParams& P, const DeviceModel& M, const MeshDevice& mesh, const unsigned long long* d_zbuf, int rows_owned,
-                      float4* d_queue, uint32_t* d_counters, const FrameOut& out, cudaStream_t s) {
+                      float4* d_queue, uint32_t* d_counters, const FrameOut& out, int num_sms, cudaStream_t s) {
     cudaMemsetAsync(d_counters, 0, sizeof(uint32_t) * kNumCounters, s);
+    (void)num_sms;
+    if (rows_owned <= 0) return;
     dim3 grid((P.width + 15) / 16, (rows_owned + 7) / 8);
     init_rays_kernel<<<grid, 128, 0, s>>>(P, M, mesh, d_zbuf, rows_owned, d_queue, d_counters, out);
 }
@@ -831,7 +880,7 @@ __global__ void debug_trace_kernel(FrameParams P, DeviceModel M, const uint32_t*
     const uint32_t x = pix % (uint32_t)P.width, y = pix / (uint32_t)P.width;
     RayInit r = init_ray(P, x, y);
     float t = r.t, t_start;
-    const bool alive = advance_pos(P, M.bitfield, r.origin, r.dir, pix, 0.f, r.t_limit, r.alive, t, t_start);
+    const bool alive = advance_pos(P, M.bitfield, r.origin, r.dir, pix, 0.f, r.t_occ_in, r.t_limit, r.alive, t, t_start);
     float* rr = o_ray + i * 8;
     rr[0] = r.origin.x; rr[1] = r.origin.y; rr[2] = r.origin.z; rr[3] = r.dir.x; rr[4] = r.dir.y; rr[5] = r.dir.z; rr[6] = t; rr[7] = alive ? 1.f : 0.f;
     const V3 idir = v3(1.0f / r.dir.x, 1.0f / r.dir.y, 1.0f / r.dir.z);

@@ -17,13 +17,14 @@ struct FrameOut {
 };
 
 // device counters of one render: [0] rays queued by the init kernel, [1] queue cursor of the march kernel,
-// [2..3] total network evaluations (64-bit), [4] rays launched
+// [2..3] total network evaluations (64-bit), [4] ray batches, [5] batch generation passes, [6] tile cursor of the init kernel
 constexpr int kNumCounters = 8;
 constexpr int kRayRecordFloat4s = 3;   // queue record: (dir.xyz, t) (t_start, t_surface, idx, -) (surface rgba)
 
 enum DebugFlags : uint32_t {
     kDebugScalarMlp = 1u,     // run the CUDA-core MLP instead of tcgen05 (NMR_MLP=scalar)
     kDebugSwapLboSbo = 2u,    // swap the UMMA descriptor offsets (bring-up aid)
+    kDebugKeepProbes = 4u,    // also write the linear frame, depth and per-ray sample counts (nmr_debug_last_frame)
 };
 
 void launch_occupancy_build(const uint16_t* d_density_grid_fp16, int n_cascades_present, uint8_t* d_bitfield, float* d_scratch, cudaStream_t s);
@@ -31,7 +32,7 @@ void launch_occupancy_build(const uint16_t* d_density_grid_fp16, int n_cascades_
 void launch_occupancy_bounds(const uint8_t* d_bitfield, int* d_out48, cudaStream_t s);
 void launch_mesh_raster(const MeshDevice& mesh, const FrameParams& P, int rows_owned, unsigned long long* d_zbuf, cudaStream_t s);
 void launch_init_rays(const FrameParams& P, const DeviceModel& M, const MeshDevice& mesh, const unsigned long long* d_zbuf, int rows_owned,
-                      float4* d_queue, uint32_t* d_counters, const FrameOut& out, cudaStream_t s);
+                      float4* d_queue, uint32_t* d_counters, const FrameOut& out, int num_sms, cudaStream_t s);
 // n_pixels: pixels traced by this context in this pass (the reference's m_n_rays_initialized), for SurfaceMode auto
 void launch_march(const FrameParams& P, const DeviceModel& M, const float4* d_queue, uint32_t* d_counters, const FrameOut& out,
                   uint32_t n_pixels, uint32_t debug_flags, int num_sms, cudaStream_t s);

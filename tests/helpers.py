@@ -74,9 +74,12 @@ def get_bitfield(r, nerf):
     return b
 
 
+KEEP_PROBES = 4   # debug flag bit 2: renders also write the probe surfaces read by debug_last_frame
+
+
 def set_flags(r, flags):
     import pynmr
-    r._ck(pynmr.lib().nmr_debug_set_flags(r._h, flags))
+    r._ck(pynmr.lib().nmr_debug_set_flags(r._h, flags | KEEP_PROBES))
 
 
 def oracle_scene(snap, width, height, cam12, glasses=None, spp_index=0, n_steps_mode=0, aabb=None):

@@ -22,6 +22,7 @@ def scene(small_snapshot, glasses_gltf):
     nerf = r.load_nerf(path)
     assert nerf is not None
     r.orbit(0.35, -0.2, 4.0)     # zoom in so the head fills a good part of the frame
+    H.set_flags(r, 0)            # keep the probe surfaces (debug_last_frame)
     return {"r": r, "nerf": nerf, "snap": snap, "path": path, "gltf": glasses_gltf,
             "glasses": {"path": glasses_gltf, "t": synth.GLASSES_T, "s": synth.GLASSES_S, "r": synth.GLASSES_R_WXYZ,
                         "texture": np.tile(np.array([128, 128, 128, 255], dtype=np.uint8), (4, 4, 1))}}
