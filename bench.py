@@ -276,6 +276,7 @@ def oracle_sample(args, steps: int, warmup: int):
     sample of the same workload: a crop of the 1080p hybrid frame around the head, same model / mesh / camera path."""
     import synth
     from oracle import oracle as O
+    O.lib().orc_set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))   # torchrun pins OMP_NUM_THREADS=1
     W, H = args.width, args.height
     cw, ch = min(W, args.cpu_crop[0]), min(H, args.cpu_crop[1])
     x0, y0 = (W - cw) // 2, (H - ch) // 2
@@ -373,7 +374,7 @@ def main():
                 out["reference_gpu"] = reference_gpu_leg(args, local_rank)
             except Exception as e:   # test infrastructure; never fails the bench
                 out["reference_gpu"] = {"error": str(e)[:200]}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # cpu_baseline: rank 0 at N = 1 only
             res = oracle_sample(args, args.cpu_steps, 1)
             out["cpu_baseline"] = {"value": res["rays"] / res["seconds"] / 1e6, "unit": "Mrays/s", "cores": res["cores"], "kind": "port",
                                    "sample": res["sample"], "msamples_per_s": res["samples"] / res["seconds"] / 1e6}

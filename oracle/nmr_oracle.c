@@ -1312,6 +1312,15 @@ ORC_API int orc_remove_floaties(uint8_t* cells, int64_t* out_best_size, int64_t*
     return best >= 0 ? n_clusters : -1;
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm of bench.py runs on rank 0 alone and may use the host */
+ORC_API void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 ORC_API int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -98,6 +98,7 @@ def lib():
         "orc_mip_from_pos": (C.c_int, [vp]),
         "orc_calc_dt": (C.c_float, [C.c_float, C.c_float]),
         "orc_num_threads": (C.c_int, []),
+        "orc_set_num_threads": (None, [C.c_int]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
