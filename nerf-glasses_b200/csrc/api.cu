@@ -65,6 +65,7 @@ struct Mesh {
 struct Surfaces {
     int w = 0, h = 0;
     DevBuf<float4> image, accum, frame;
+    DevBuf<float4> image_alt;        // second image buffer of nmr_render_views (a view renders while the previous one is copied out)
     DevBuf<float> depth;
     DevBuf<uint32_t> n_samples;
     DevBuf<float4> queue;
@@ -89,6 +90,8 @@ struct nmr_ctx {
     int width = 0, height = 0;
     int mesh_scale = 2;                                   // mesh_render_size_factor, S/nerf_mesh_renderer.cuh:112
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;                   // device->host copies of nmr_render_views
+    cudaEvent_t ev_view[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // per image buffer: rendered, copied
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     OrbitCamera camera;
     float cam12[12];
@@ -364,6 +367,8 @@ NMR_API int nmr_create(int width, int height, int device, nmr_ctx** out_ctx) {
         CK(cudaSetDevice(device));
         CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         for (auto& ev : ctx->ev) CK(cudaEventCreate(&ev));
+        CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (auto& pair : ctx->ev_view) for (auto& ev : pair) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         ctx->d_counters.ensure(kNumCounters);
         ctx->d_scratch.ensure(64);
         CK(cudaHostAlloc((void**)&ctx->h_counters, sizeof(uint32_t) * kNumCounters, cudaHostAllocDefault));
@@ -385,6 +390,8 @@ NMR_API void nmr_destroy(nmr_ctx* ctx) {
     ctx->nerfs.clear(); ctx->meshes.clear();
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& pair : ctx->ev_view) for (auto& ev : pair) if (ev) cudaEventDestroy(ev);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -592,12 +599,24 @@ NMR_API int nmr_render_views(nmr_ctx* ctx, int nerf_id, int n_views, const float
         upload_mesh_if_dirty(ctx);
         ctx->surf.resize(width, height, ctx->mesh_scale);
         const size_t px = (size_t)width * height;
+        // Two image buffers, two streams: view v renders into buffer v % 2 while view v - 1 leaves the other one over PCIe.
+        Surfaces& S = ctx->surf;
+        S.image_alt.ensure(px);
+        float4* bufs[2] = {S.image.p, S.image_alt.p};
         for (int v = 0; v < n_views; ++v) {
+            const int b = v & 1;
+            if (v >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_view[b][1], 0));      // buffer b has been copied out
+            S.image.p = bufs[b];
             const FrameParams P = make_params(ctx, *n, width, height, cams12 + (size_t)v * 12, 0, !linear, true);
             enqueue_pass(ctx, *n, P, v == n_views - 1);
-            // stream order makes the copy wait for this view's kernels and the next view's kernels wait for the copy
-            CK(cudaMemcpyAsync(out_rgba + (size_t)v * px * 4, ctx->surf.image.p, px * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaEventRecord(ctx->ev_view[b][0], ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_view[b][0], 0));
+            CK(cudaMemcpyAsync(out_rgba + (size_t)v * px * 4, bufs[b], px * sizeof(float4), cudaMemcpyDeviceToHost, ctx->copy_stream));
+            CK(cudaEventRecord(ctx->ev_view[b][1], ctx->copy_stream));
         }
+        S.image.p = bufs[0];
+        if (((n_views - 1) & 1) == 1) { std::swap(S.image.p, S.image_alt.p); std::swap(S.image.n, S.image_alt.n); }   // nmr_get_device_image: the last view's buffer
+        CK(cudaStreamSynchronize(ctx->copy_stream));
         CK(cudaStreamSynchronize(ctx->stream));
         ctx->surf.spp = 0;
         return NMR_OK;
