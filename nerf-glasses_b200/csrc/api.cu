@@ -69,14 +69,16 @@ struct Surfaces {
     DevBuf<float> depth;
     DevBuf<uint32_t> n_samples;
     DevBuf<float4> queue;
-    DevBuf<unsigned long long> zbuf;
+    DevBuf<unsigned long long> zbuf;       // opaque window, then (scenes with lens surfaces) the lens window
+    DevBuf<float4> lens;                   // FrameOut::lens
+    DevBuf<float> lens_scratch;            // FrameOut::lens_scratch
     uint32_t spp = 0;
     void resize(int W, int H, int mesh_scale) {
         const size_t n = (size_t)W * H;
         if (W != w || H != h) spp = 0;
         image.ensure(n); accum.ensure(n); frame.ensure(n); depth.ensure(n); n_samples.ensure(n);
         queue.ensure(n * kRayRecordFloat4s);
-        zbuf.ensure(n * (size_t)mesh_scale * mesh_scale);
+        zbuf.ensure(n * (size_t)mesh_scale * mesh_scale * 2);
         w = W; h = H;
     }
 };
@@ -102,6 +104,11 @@ struct nmr_ctx {
     bool mesh_dirty = true;
     DevBuf<float> d_wpos, d_wnrm, d_uv, d_tex;
     DevBuf<uint32_t> d_idx;
+    DevBuf<uint8_t> d_tri_lens;
+    bool scene_has_lens = false;                          // some loaded mesh has a transmissive material
+    int lens_enabled = 1;                                 // nmr_set_lens
+    float lens_ior = 1.5f, lens_transmission = 1.f, lens_tint[3] = {1.f, 1.f, 1.f};
+    bool lens_params_set = false;                         // nmr_set_lens gave explicit parameters
     MeshDevice mesh_dev{};
     float mesh_wmin[3] = {0.f, 0.f, 0.f}, mesh_wmax[3] = {0.f, 0.f, 0.f};   // world-space box of the concatenated mesh
     Surfaces surf;
@@ -162,6 +169,8 @@ void upload_mesh_if_dirty(nmr_ctx* ctx) {
     if (!ctx->mesh_dirty) return;
     std::vector<float> wpos, wnrm, uv;
     std::vector<uint32_t> idx;
+    std::vector<uint8_t> tri_lens;
+    bool any_lens = false;
     for (const auto& m : ctx->meshes) {
         std::vector<float> p, n;
         transform_mesh(m->host, m->t, m->s, m->r, p, n);
@@ -170,7 +179,14 @@ void upload_mesh_if_dirty(nmr_ctx* ctx) {
         wnrm.insert(wnrm.end(), n.begin(), n.end());
         uv.insert(uv.end(), m->host.texcoords.begin(), m->host.texcoords.end());
         for (uint32_t i : m->host.indices) idx.push_back(base + i);
+        tri_lens.insert(tri_lens.end(), m->host.tri_lens.begin(), m->host.tri_lens.end());
+        tri_lens.resize(idx.size() / 3, 0);
+        if (m->host.has_lens && !any_lens) {   // lens parameters of the first lens material in the scene (nmr_set_lens overrides)
+            any_lens = true;
+            if (!ctx->lens_params_set) { ctx->lens_ior = m->host.lens_ior; ctx->lens_transmission = m->host.lens_transmission; std::memcpy(ctx->lens_tint, m->host.lens_tint, 12); }
+        }
     }
+    ctx->scene_has_lens = any_lens;
     MeshDevice d{};
     d.n_tris = (uint32_t)(idx.size() / 3);
     for (int k = 0; k < 3; ++k) { ctx->mesh_wmin[k] = 1e30f; ctx->mesh_wmax[k] = -1e30f; }
@@ -184,6 +200,11 @@ void upload_mesh_if_dirty(nmr_ctx* ctx) {
         CK(cudaMemcpyAsync(ctx->d_wnrm.p, wnrm.data(), wnrm.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(ctx->d_uv.p, uv.data(), uv.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(ctx->d_idx.p, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (any_lens) {
+            ctx->d_tri_lens.ensure(tri_lens.size());
+            CK(cudaMemcpyAsync(ctx->d_tri_lens.p, tri_lens.data(), tri_lens.size(), cudaMemcpyHostToDevice, ctx->stream));
+            d.tri_lens = ctx->d_tri_lens.p;
+        }
         const HostMesh& m0 = ctx->meshes[0]->host;   // one material for the whole scene (first mesh), see DESIGN.md
         std::memcpy(d.base_color, m0.base_color, 16); std::memcpy(d.emissive, m0.emissive, 12);
         d.metallic = m0.metallic; d.roughness = m0.roughness;
@@ -298,6 +319,13 @@ FrameParams make_params(nmr_ctx* ctx, const Nerf& n, int W, int H, const float* 
     std::memcpy(P.occ_min, n.occ_min, 12); std::memcpy(P.occ_max, n.occ_max, 12);
     P.surface_mode = ctx->surface_mode;
     mesh_screen_box(ctx, P);
+    P.lens_on = (P.mesh_scale > 0 && ctx->scene_has_lens && ctx->lens_enabled) ? 1 : 0;
+    {
+        const float r0 = (ctx->lens_ior - 1.f) / (ctx->lens_ior + 1.f);
+        P.lens_f0 = r0 * r0;
+        for (int k = 0; k < 3; ++k) P.lens_k[k] = ctx->lens_transmission * ctx->lens_tint[k];
+        P.lens_kmean = (P.lens_k[0] + P.lens_k[1] + P.lens_k[2]) / 3.f;
+    }
     return P;
 }
 
@@ -307,11 +335,18 @@ void enqueue_pass(nmr_ctx* ctx, Nerf& n, const FrameParams& P, bool timed) {
     const int rows = rows_owned_by(P.height, P.shard_rank, P.shard_world, P.shard_band);
     // the linear frame, depth and per-ray sample counts are parity probes (nmr_debug_last_frame): written only on request
     const bool probes = (ctx->debug_flags & kDebugKeepProbes) != 0;
-    FrameOut out{S.image.p, S.accum.p, probes ? S.frame.p : nullptr, probes ? S.depth.p : nullptr, probes ? S.n_samples.p : nullptr};
+    FrameOut out{S.image.p, S.accum.p, probes ? S.frame.p : nullptr, probes ? S.depth.p : nullptr, probes ? S.n_samples.p : nullptr, nullptr, nullptr};
+    MeshDevice mesh = ctx->mesh_dev;
+    if (!P.lens_on) mesh.tri_lens = nullptr;     // lenses off: their triangles are ordinary opaque surfaces
+    else {
+        S.lens.ensure((size_t)P.width * P.height * 2);
+        S.lens_scratch.ensure((size_t)ctx->num_sms * 3 * 32 * kLensStash);   // launch_march: num_sms x 3 CTAs x 32 ray groups
+        out.lens = S.lens.p; out.lens_scratch = S.lens_scratch.p;
+    }
     if (timed) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     uint64_t launches = 0;
-    if (P.mesh_scale > 0) { launch_mesh_raster(ctx->mesh_dev, P, rows, S.zbuf.p, ctx->stream); launches += 1; }
-    launch_init_rays(P, n.dev, ctx->mesh_dev, S.zbuf.p, rows, S.queue.p, ctx->d_counters.p, out, ctx->num_sms, ctx->stream);
+    if (P.mesh_scale > 0) { launch_mesh_raster(mesh, P, rows, S.zbuf.p, ctx->stream); launches += 1; }
+    launch_init_rays(P, n.dev, mesh, S.zbuf.p, rows, S.queue.p, ctx->d_counters.p, out, ctx->num_sms, ctx->stream);
     launches += 1;
     if (timed) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     launch_march(P, n.dev, S.queue.p, ctx->d_counters.p, out, (uint32_t)P.width * (uint32_t)rows, ctx->debug_flags, ctx->num_sms, ctx->stream);
@@ -532,6 +567,20 @@ NMR_API int nmr_set_shard(nmr_ctx* ctx, int rank, int world, int band) {
     return guarded(ctx, [&]() -> int {
         if (world < 1 || rank < 0 || rank >= world || band < 1) return fail(ctx, NMR_ERR_INVALID, "bad shard specification");
         ctx->shard_rank = rank; ctx->shard_world = world; ctx->shard_band = band; ctx->surf.spp = 0;
+        return NMR_OK;
+    });
+}
+
+NMR_API int nmr_set_lens(nmr_ctx* ctx, int enabled, float ior, float transmission, const float tint[3]) {
+    return guarded(ctx, [&]() -> int {
+        ctx->lens_enabled = enabled ? 1 : 0;
+        if (ior > 1.f || transmission >= 0.f || tint) {
+            if (!ctx->lens_params_set) ctx->lens_params_set = true;
+            if (ior > 1.f) ctx->lens_ior = ior;
+            if (transmission >= 0.f) ctx->lens_transmission = transmission > 1.f ? 1.f : transmission;
+            if (tint) std::memcpy(ctx->lens_tint, tint, 12);
+        }
+        ctx->surf.spp = 0;
         return NMR_OK;
     });
 }
@@ -768,22 +817,33 @@ NMR_API int nmr_debug_trace(nmr_ctx* ctx, int id, int width, int height, const u
     });
 }
 
+// shared by the mesh probes: frame parameters of the mesh stage alone + the visibility buffer of the current camera
+static void debug_mesh_stage(nmr_ctx* ctx, int width, int height, FrameParams& P, MeshDevice& mesh, DevBuf<unsigned long long>& zbuf) {
+    const int ms = ctx->mesh_scale;
+    P = FrameParams{};
+    P.width = width; P.height = height; std::memcpy(P.cam, ctx->cam12, sizeof(P.cam));
+    P.shard_world = 1; P.shard_band = 8; P.mesh_scale = ms; std::memcpy(P.light, ctx->light, 12);
+    invert3(ctx->cam12, P.cam_inv);
+    mesh_screen_box(ctx, P);
+    P.lens_on = (ctx->scene_has_lens && ctx->lens_enabled) ? 1 : 0;
+    mesh = ctx->mesh_dev;
+    if (!P.lens_on) mesh.tri_lens = nullptr;
+    zbuf.ensure((size_t)width * ms * height * ms * 2);
+    launch_mesh_raster(mesh, P, height, zbuf.p, ctx->stream);
+}
+
 NMR_API int nmr_debug_mesh(nmr_ctx* ctx, int width, int height, float* o_rgba2, float* o_depth2, int32_t* o_tri2, float* o_surf, float* o_tsurf) {
     return guarded(ctx, [&]() -> int {
         upload_mesh_if_dirty(ctx);
         if (ctx->mesh_dev.n_tris == 0) return fail(ctx, NMR_ERR_STATE, "no mesh loaded");
         const int ms = ctx->mesh_scale;
         const size_t n2 = (size_t)width * ms * height * ms, n1 = (size_t)width * height;
-        DevBuf<unsigned long long> zbuf; zbuf.ensure(n2);
+        DevBuf<unsigned long long> zbuf;
         DevBuf<float> d_rgba2, d_depth2, d_surf, d_ts; DevBuf<int32_t> d_tri2;
         d_rgba2.ensure(n2 * 4); d_depth2.ensure(n2); d_tri2.ensure(n2); d_surf.ensure(n1 * 4); d_ts.ensure(n1);
-        FrameParams P{};
-        P.width = width; P.height = height; std::memcpy(P.cam, ctx->cam12, sizeof(P.cam));
-        P.shard_world = 1; P.shard_band = 8; P.mesh_scale = ms; std::memcpy(P.light, ctx->light, 12);
-        invert3(ctx->cam12, P.cam_inv);
-        mesh_screen_box(ctx, P);
-        launch_mesh_raster(ctx->mesh_dev, P, height, zbuf.p, ctx->stream);
-        launch_debug_mesh(ctx->mesh_dev, P, zbuf.p, d_rgba2.p, d_depth2.p, d_tri2.p, d_surf.p, d_ts.p, ctx->stream);
+        FrameParams P; MeshDevice mesh;
+        debug_mesh_stage(ctx, width, height, P, mesh, zbuf);
+        launch_debug_mesh(mesh, P, zbuf.p, d_rgba2.p, d_depth2.p, d_tri2.p, d_surf.p, d_ts.p, nullptr, ctx->stream);
         if (o_rgba2) CK(cudaMemcpyAsync(o_rgba2, d_rgba2.p, n2 * 16, cudaMemcpyDeviceToHost, ctx->stream));
         if (o_depth2) CK(cudaMemcpyAsync(o_depth2, d_depth2.p, n2 * 4, cudaMemcpyDeviceToHost, ctx->stream));
         if (o_tri2) CK(cudaMemcpyAsync(o_tri2, d_tri2.p, n2 * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -791,6 +851,28 @@ NMR_API int nmr_debug_mesh(nmr_ctx* ctx, int width, int height, float* o_rgba2, 
         if (o_tsurf) CK(cudaMemcpyAsync(o_tsurf, d_ts.p, n1 * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         CK(cudaGetLastError());
+        return NMR_OK;
+    });
+}
+
+NMR_API int nmr_debug_lens(nmr_ctx* ctx, int width, int height, float* o_w, float* o_t, float* o_normal) {
+    return guarded(ctx, [&]() -> int {
+        upload_mesh_if_dirty(ctx);
+        if (ctx->mesh_dev.n_tris == 0) return fail(ctx, NMR_ERR_STATE, "no mesh loaded");
+        const size_t n1 = (size_t)width * height;
+        DevBuf<unsigned long long> zbuf;
+        DevBuf<float> d_lens; d_lens.ensure(n1 * 5);
+        FrameParams P; MeshDevice mesh;
+        debug_mesh_stage(ctx, width, height, P, mesh, zbuf);
+        launch_debug_mesh(mesh, P, zbuf.p, nullptr, nullptr, nullptr, nullptr, nullptr, d_lens.p, ctx->stream);
+        std::vector<float> h(n1 * 5);
+        CK(cudaMemcpyAsync(h.data(), d_lens.p, n1 * 20, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaGetLastError());
+        for (size_t i = 0; i < n1; ++i) {
+            if (o_w) o_w[i] = h[i * 5]; if (o_t) o_t[i] = h[i * 5 + 1];
+            if (o_normal) { o_normal[i * 3] = h[i * 5 + 2]; o_normal[i * 3 + 1] = h[i * 5 + 3]; o_normal[i * 3 + 2] = h[i * 5 + 4]; }
+        }
         return NMR_OK;
     });
 }

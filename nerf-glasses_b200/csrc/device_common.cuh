@@ -38,6 +38,7 @@ struct MeshDevice {
     const float* uv;        // [n_verts][2]
     const uint32_t* idx;    // [n_tris][3]
     const float* tex_lin;   // [h][w][4] linearised texture or nullptr
+    const uint8_t* tri_lens; // [n_tris] 1 = lens surface (transmissive material), or nullptr when the scene has none / lenses are off
     uint32_t n_tris;
     int tex_w, tex_h;
     float base_color[4], emissive[3], metallic, roughness;
@@ -67,6 +68,10 @@ struct FrameParams {
     // supersampled frame, aligned to whole pixels): zb_w == 0 means "mesh not in view".  Entry (x, y) lives at
     // (y - zb_y0) * zb_w + (x - zb_x0).
     int zb_x0, zb_y0, zb_w, zb_h;
+    // Lens surfaces (thin dielectric sheet, DESIGN.md "Secondary rays"): Schlick F0, transmitted colour factor
+    // transmission * tint and its mean.  lens_on == 0: no lens triangles in this frame.
+    int lens_on;
+    float lens_f0, lens_k[3], lens_kmean;
 };
 
 // The reference blends the mesh surface in front of the first sample of the n_steps BATCH whose end passed t_surface
@@ -307,9 +312,9 @@ __device__ __forceinline__ int next_sample(const FrameParams& P, const uint8_t* 
     V3 pos; float dt; uint32_t mip, cell;
     while (true) {
         if (!ignore_surface && t_surface != 0.0f && t > t_surface && surf_w == 1.f) { t_io = t_surface; return 0; }
-        if (t > t_limit) return 0;                 // no occupied cell ahead: the walk could only run out of the render box
+        if (t > t_limit) { t_io = t; return 0; }   // no occupied cell ahead: the walk could only run out of the render box
         pos = vadd(origin, vmul(dir, t));
-        if (!box_contains(P.aabb_min, P.aabb_max, r2l_mul(P.r2l, pos))) return 0;
+        if (!box_contains(P.aabb_min, P.aabb_max, r2l_mul(P.r2l, pos))) { t_io = t; return 0; }
         dt = uniform_dt ? min_cone_stepsize() : calc_dt(t - t_start, cone);
         mip = (uint32_t)mip_from_dt(dt, pos);
         if (occupied_at(pos, bitfield, mip, &cell)) break;

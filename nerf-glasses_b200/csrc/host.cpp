@@ -395,6 +395,29 @@ HostMesh load_gltf(const std::string& path) {
             else m.texcoords.resize(m.texcoords.size() + nv * 2, 0.f);
             if (prim.contains("indices")) read_indices(prim.at("indices").as_int(), base, m.indices);
             else for (uint32_t i = 0; i < (uint32_t)nv; ++i) m.indices.push_back(base + i);
+            {   // lens material?  (flags cover every triangle appended so far)
+                bool lens = false; float ior = 1.5f, transmission = 1.f, tint[3] = {1.f, 1.f, 1.f};
+                if (prim.contains("material") && doc.contains("materials")) {
+                    const Value& mat = doc.at("materials").at((size_t)prim.at("material").as_int());
+                    float alpha = 1.f;
+                    if (mat.contains("pbrMetallicRoughness") && mat.at("pbrMetallicRoughness").contains("baseColorFactor")) {
+                        const Value& bc = mat.at("pbrMetallicRoughness").at("baseColorFactor");
+                        for (int k = 0; k < 3; ++k) tint[k] = bc.at((size_t)k).as_float();
+                        alpha = bc.at(3).as_float();
+                    }
+                    if (mat.contains("alphaMode") && mat.at("alphaMode").as_string() == "BLEND" && alpha < 1.f) { lens = true; transmission = 1.f - alpha; }
+                    if (mat.contains("extensions")) {
+                        const Value& ext = mat.at("extensions");
+                        if (ext.contains("KHR_materials_transmission")) {
+                            const float tf = (float)ext.at("KHR_materials_transmission").value("transmissionFactor", 0.0);
+                            if (tf > 0.f) { lens = true; transmission = tf; }
+                        }
+                        if (ext.contains("KHR_materials_ior")) ior = (float)ext.at("KHR_materials_ior").value("ior", 1.5);
+                    }
+                }
+                m.tri_lens.resize(m.indices.size() / 3, lens ? 1 : 0);
+                if (lens && !m.has_lens) { m.has_lens = true; m.lens_ior = ior; m.lens_transmission = transmission; std::memcpy(m.lens_tint, tint, 12); }
+            }
             if (!have_material && prim.contains("material") && doc.contains("materials")) {
                 have_material = true;
                 const Value& mat = doc.at("materials").at((size_t)prim.at("material").as_int());
@@ -423,6 +446,7 @@ HostMesh load_gltf(const std::string& path) {
     }
     if (m.indices.empty()) throw std::runtime_error("gltf: no triangles found");
     m.indices.resize(m.indices.size() / 3 * 3);
+    m.tri_lens.resize(m.indices.size() / 3, 0);
     const uint32_t nverts = (uint32_t)(m.positions.size() / 3);
     for (uint32_t idx : m.indices) if (idx >= nverts) throw std::runtime_error("gltf: index out of range");
     if (missing_normals) {

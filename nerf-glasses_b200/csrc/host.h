@@ -60,6 +60,14 @@ struct HostMesh {
     // node 0 TRS as loaded from the file (overwritten by load_mesh's t/s/r, S/nerf_mesh_renderer.cu:952-954)
     float t[3] = {0, 0, 0}, s[3] = {1, 1, 1}, r_wxyz[4] = {1, 0, 0, 0};
     std::string warning;            // e.g. "texture could not be decoded, using constant colour"
+    // Lens surfaces (no reference equivalent - SURVEY.md 8f.1): triangles of primitives whose material is transmissive
+    // (KHR_materials_transmission.transmissionFactor > 0, or alphaMode BLEND with baseColorFactor alpha < 1).  They are
+    // not shaded as opaque surfaces; a ray meeting one splits into a reflected and a transmitted ray.
+    std::vector<uint8_t> tri_lens;  // one flag per triangle (indices.size() / 3), all zero when the file has no such material
+    bool has_lens = false;
+    float lens_ior = 1.5f;          // KHR_materials_ior.ior of the first lens material
+    float lens_transmission = 1.f;  // transmissionFactor, or 1 - alpha
+    float lens_tint[3] = {1, 1, 1}; // baseColorFactor rgb of the first lens material
 };
 
 // glTF 2.0 (.gltf + external/embedded buffers, or .glb): all primitives of all nodes of the default scene are

@@ -134,6 +134,9 @@ __global__ void __launch_bounds__(256) mesh_raster_kernel(MeshDevice mesh, Frame
             if (x1 < x0 || y1 < y0) return;
         }
     }
+    // lens surfaces have their own visibility window right behind the opaque one (nearest opaque hit and nearest lens hit
+    // are both needed per sub-pixel)
+    unsigned long long* __restrict__ zwin = zbuf + ((mesh.tri_lens != nullptr && __ldg(mesh.tri_lens + tri)) ? (size_t)P.zb_w * P.zb_h : (size_t)0);
     // shard: only sub-pixel rows belonging to owned image rows are needed, but testing ownership per row is cheap enough
     const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
     const int ms = P.mesh_scale;
@@ -144,7 +147,7 @@ __global__ void __launch_bounds__(256) mesh_raster_kernel(MeshDevice mesh, Frame
         float t, u, v;
         if (ray_tri(eye, dir, v0, v1, v2, t, u, v) && t < 1e16f) {
             const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | tri;
-            atomicMin(zbuf + (size_t)(y - by0) * P.zb_w + (x - bx0), key);
+            atomicMin(zwin + (size_t)(y - by0) * P.zb_w + (x - bx0), key);
         }
     }
 }
@@ -153,7 +156,7 @@ void launch_mesh_raster(const MeshDevice& mesh, const FrameParams& P, int rows_o
     (void)rows_owned;
     const int W2 = P.width * P.mesh_scale, H2 = P.height * P.mesh_scale;
     if (mesh.n_tris == 0 || P.zb_w <= 0 || P.zb_h <= 0) return;
-    cudaMemsetAsync(d_zbuf, 0xFF, (size_t)P.zb_w * P.zb_h * sizeof(unsigned long long), s);
+    cudaMemsetAsync(d_zbuf, 0xFF, (size_t)P.zb_w * P.zb_h * sizeof(unsigned long long) * (mesh.tri_lens ? 2 : 1), s);
     const uint32_t threads = mesh.n_tris * 32u;
     mesh_raster_kernel<<<(threads + 255) / 256, 256, 0, s>>>(mesh, P, W2, H2, d_zbuf);
 }
@@ -200,6 +203,50 @@ __device__ __forceinline__ void mesh_resolve(const MeshDevice& mesh, const Frame
     const float q = (float)(ms * ms);
     surf[0] = c0 / q; surf[1] = c1 / q; surf[2] = c2 / q; surf[3] = c3 / q;
     t_surface = depth;
+}
+
+// Lens hand-off of one pixel (new functionality, no reference equivalent - DESIGN.md "Secondary rays").  A tap counts when
+// its nearest lens hit lies in front of its nearest opaque hit; w = counted taps / taps, t = the smallest such hit distance,
+// n = unit shading normal there, turned towards the eye.  Hit distances are read back from the visibility keys (exact bits).
+struct LensHit { float w, t; V3 n; };
+__device__ __forceinline__ void lens_resolve(const MeshDevice& mesh, const FrameParams& P, const unsigned long long* __restrict__ zbuf, int px, int py, LensHit& L) {
+    L.w = 0.f; L.t = 0.f; L.n = v3(0.f, 0.f, 1.f);
+    const int ms = P.mesh_scale, W2 = P.width * ms, H2 = P.height * ms;
+    if (px * ms < P.zb_x0 || py * ms < P.zb_y0 || px * ms >= P.zb_x0 + P.zb_w || py * ms >= P.zb_y0 + P.zb_h) return;
+    const unsigned long long* __restrict__ zl = zbuf + (size_t)P.zb_w * P.zb_h;
+    int n_l = 0, bx = 0, by = 0; uint32_t btri = 0; float best = 3.402823466e+38f;
+    for (int i = 0; i < ms; ++i) {
+        for (int j = 0; j < ms; ++j) {
+            const int x = px * ms + i, y = py * ms + j;
+            const size_t o = (size_t)(y - P.zb_y0) * P.zb_w + (x - P.zb_x0);
+            const unsigned long long kl = __ldg(zl + o);
+            if (kl == kZMiss) continue;
+            const unsigned long long ko = __ldg(zbuf + o);
+            const float tl = __uint_as_float((uint32_t)(kl >> 32));
+            if (ko != kZMiss && !(tl < __uint_as_float((uint32_t)(ko >> 32)))) continue;
+            ++n_l;
+            if (tl < best) { best = tl; bx = x; by = y; btri = (uint32_t)(kl & 0xFFFFFFFFull); }
+        }
+    }
+    if (n_l == 0) return;
+    const V3 eye = v3(P.cam[9], P.cam[10], P.cam[11]);
+    const V3 dir = mesh_ray_dir(P, bx, by, W2, H2);
+    const uint32_t i0 = __ldg(mesh.idx + btri * 3), i1 = __ldg(mesh.idx + btri * 3 + 1), i2 = __ldg(mesh.idx + btri * 3 + 2);
+    float t = 0.f, u = 0.f, v = 0.f;
+    ray_tri(eye, dir, ld3(mesh.wpos, i0), ld3(mesh.wpos, i1), ld3(mesh.wpos, i2), t, u, v);
+    const float bw = 1.0f - u - v;
+    V3 n = gnormalize(vadd(vadd(vmul(ld3(mesh.wnrm, i1), u), vmul(ld3(mesh.wnrm, i2), v)), vmul(ld3(mesh.wnrm, i0), bw)));
+    L.w = (float)n_l / (float)(ms * ms); L.t = best; L.n = n;
+}
+
+// Fresnel split at the lens for a unit ray direction d: returns the Schlick reflectance and the mirrored direction
+__device__ __forceinline__ float lens_fresnel(const FrameParams& P, V3 d, V3 n, V3& refl) {
+    float c = gdot(d, n);
+    if (c > 0.f) { n = vmul(n, -1.f); c = -c; }        // normal towards the incoming ray
+    const float cosi = fminf(-c, 1.0f);
+    refl = gnormalize(vsub(d, vmul(n, 2.0f * c)));
+    const float m = 1.0f - cosi, m2 = m * m;
+    return P.lens_f0 + (1.0f - P.lens_f0) * (m2 * m2 * m);
 }
 
 // =================================================================================================================
@@ -252,12 +299,19 @@ __device__ __forceinline__ void init_one_ray(const FrameParams& P, const DeviceM
     float surf[4] = {0.f, 0.f, 0.f, 0.f};
     float t_surface = 0.f;
     if (P.mesh_scale > 0) mesh_resolve(mesh, P, zbuf, x, y, surf, t_surface);
+    LensHit L; L.w = 0.f; L.t = 0.f; L.n = v3(0.f, 0.f, 1.f);
+    if (P.lens_on) {
+        lens_resolve(mesh, P, zbuf, x, y, L);
+        if (L.w > 0.f && t_surface != 0.0f && t_surface < L.t) L.w = 0.f;   // an opaque part of the mesh is in front: no lens event
+    }
+    // the first mesh surface the primary ray can meet: it clips / revives the first-hit walk exactly like t_surface does
+    const float t_first = L.w > 0.f ? L.t : t_surface;
 
     // Most pixels see neither the mesh nor any occupied cell: their ray misses the box around the occupied cells, so
     // advance_pos_nerf could only walk it out of the render box (dead ray, background pixel).  Decide that with the
     // un-normalised direction and approximate reciprocals - the box carries a whole grid cell of margin - before paying for
     // the exact ray set-up.
-    if (t_surface == 0.0f) {
+    if (t_first == 0.0f) {
         const float* c = P.cam;
         const float ux = 2.0f * (((float)x + 0.5f) / (float)P.width) - 1.0f;
         const float uy = 2.0f * (((float)y + 0.5f) / (float)P.height) - 1.0f;
@@ -283,15 +337,19 @@ __device__ __forceinline__ void init_one_ray(const FrameParams& P, const DeviceM
 
     RayInit r = init_ray(P, (uint32_t)x, (uint32_t)y);
     float t = r.t, t_start;
-    const bool alive = advance_pos(P, M.bitfield, r.origin, r.dir, idx, t_surface, r.t_occ_in, r.t_limit, r.alive, t, t_start);
+    const bool alive = advance_pos(P, M.bitfield, r.origin, r.dir, idx, t_first, r.t_occ_in, r.t_limit, r.alive, t, t_start);
     if (!alive) {
         finish_pixel(P, out, idx, 0.f, 0.f, 0.f, 0.f, 0.f, 0u);
         return;
     }
     const uint32_t slot = atomicAdd(&counters[0], 1u);
     queue[(size_t)slot * kRayRecordFloat4s + 0] = make_float4(r.dir.x, r.dir.y, r.dir.z, t);
-    queue[(size_t)slot * kRayRecordFloat4s + 1] = make_float4(t_start, t_surface, __uint_as_float(idx), r.t_limit);
+    queue[(size_t)slot * kRayRecordFloat4s + 1] = make_float4(t_start, t_surface, __uint_as_float(idx | (L.w > 0.f ? kLensRayFlag : 0u)), r.t_limit);
     queue[(size_t)slot * kRayRecordFloat4s + 2] = make_float4(surf[0], surf[1], surf[2], surf[3]);
+    if (L.w > 0.f) {
+        out.lens[(size_t)idx * 2] = make_float4(L.n.x, L.n.y, L.n.z, L.t);
+        out.lens[(size_t)idx * 2 + 1] = make_float4(L.w, 0.f, 0.f, 0.f);
+    }
 }
 
 __global__ void __launch_bounds__(128) init_rays_kernel(FrameParams P, DeviceModel M, MeshDevice mesh, const unsigned long long* __restrict__ zbuf, int rows_owned,
@@ -628,10 +686,14 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? 3 : 2) ma
     const uint32_t sub = lane & (kRayLanes - 1);             // which of the group's samples this lane evaluates
     const uint32_t gbase = lane & ~(uint32_t)(kRayLanes - 1);
     const uint32_t gmask = ((1u << kRayLanes) - 1u) << gbase;
-    const V3 origin = v3(P.cam[9] + 0.5f, P.cam[10] + 0.5f, P.cam[11] + 0.5f);
+    const V3 cam_origin = v3(P.cam[9] + 0.5f, P.cam[10] + 0.5f, P.cam[11] + 0.5f);
+    // lens rays park the state of their other segments here (one slot per ray group; all 8 lanes write the same values)
+    float* __restrict__ stash = out.lens_scratch ? out.lens_scratch + ((size_t)blockIdx.x * (blockDim.x / kRayLanes) + threadIdx.x / kRayLanes) * kLensStash : nullptr;
 
     // per-ray state, identical in the 8 lanes of a group
     bool active = false, exhausted = false, pending_finish = false;
+    V3 origin = cam_origin;      // primary rays start at the eye; the reflected segment of a lens ray starts on the lens
+    uint32_t phase = 0;          // 0 ordinary ray; lens ray: 1 in front of the lens, 2 reflected segment, 3 behind the lens
     V3 dir = v3(0.f, 0.f, 1.f);
     float t = 0.f, t_start = 0.f, t_surface = 0.f, t_limit = 0.f, max_weight = 0.f, depth = 0.f;
     float sr = 0.f, sg = 0.f, sb = 0.f, sw = 0.f;        // surface colour (mesh hand-off)
@@ -648,8 +710,56 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? 3 : 2) ma
             if (pending_finish) {
                 // composite_kernel_nerf's tail for a finished ray (S/ngp/testbed.cu:886-901), then shade/accumulate/tonemap
                 if (sw > 0) { const float k = 1.f - ca; cr += sr * k; cg += sg * k; cb += sb * k; ca += sw * k; }
+                pending_finish = false;
+                if (phase == 1u || phase == 2u) {
+                    // ---- lens ray: the segment in front of the lens (1) or the reflected segment (2) has ended ----
+                    if (phase == 1u) {
+                        // split at the lens: park what was accumulated in front of it and where the primary walk stands
+                        const float4 l0 = __ldg(out.lens + (size_t)idx * 2);
+                        V3 refl;
+                        const float F = lens_fresnel(P, dir, v3(l0.x, l0.y, l0.z), refl);
+                        const float wl = __ldg(out.lens + (size_t)idx * 2 + 1).x;
+                        stash[0] = cr; stash[1] = cg; stash[2] = cb; stash[3] = ca; stash[7] = t; stash[14] = F; stash[15] = wl;
+                        stash[4] = 0.f; stash[5] = 0.f; stash[6] = 0.f;
+                        if (wl * F * (1.f - ca) >= 1.0f / 512.0f) {
+                            // reflected segment: a fresh ray from the hit point along the mirror direction, NeRF only
+                            stash[16] = dir.x; stash[17] = dir.y; stash[18] = dir.z;
+                            origin = vadd(cam_origin, vmul(dir, l0.w));
+                            dir = refl;
+                            float t_in;
+                            t_limit = occupied_exit(P, origin, dir, t_in);
+                            t = 1e-3f; t_start = 0.f; t_surface = 0.f; sr = sg = sb = sw = 0.f;
+                            cr = cg = cb = ca = 0.f;
+                            phase = 2u;
+                            continue;
+                        }
+                        stash[16] = dir.x; stash[17] = dir.y; stash[18] = dir.z;
+                    } else {
+                        // what the mirror direction sees: the march result over the background colour
+                        const float k = (1.f - ca) * P.background[3];
+                        stash[4] = cr + P.background[0] * k; stash[5] = cg + P.background[1] * k; stash[6] = cb + P.background[2] * k;
+                    }
+                    // transmitted segment: the primary ray carries on behind the lens, now with the opaque mesh surface (if any)
+                    origin = cam_origin;
+                    dir = v3(stash[16], stash[17], stash[18]);
+                    t = stash[7]; t_start = stash[8]; t_surface = stash[9]; sr = stash[10]; sg = stash[11]; sb = stash[12]; sw = stash[13]; t_limit = stash[19];
+                    cr = cg = cb = ca = 0.f;
+                    phase = 3u;
+                    continue;
+                }
+                if (phase == 3u) {
+                    // combine: front + T_front * ( w (F * reflected + (1 - F) k * behind) + (1 - w) * behind )
+                    const float F = stash[14], wl = stash[15], Tf = 1.f - stash[3];
+                    const float kr = (1.f - F) * P.lens_k[0], kg = (1.f - F) * P.lens_k[1], kb = (1.f - F) * P.lens_k[2];
+                    const float a_behind = ca;
+                    cr = stash[0] + Tf * (wl * (F * stash[4] + kr * cr) + (1.f - wl) * cr);
+                    cg = stash[1] + Tf * (wl * (F * stash[5] + kg * cg) + (1.f - wl) * cg);
+                    cb = stash[2] + Tf * (wl * (F * stash[6] + kb * cb) + (1.f - wl) * cb);
+                    ca = stash[3] + Tf * (wl * (F + (1.f - F) * ((1.f - P.lens_kmean) + P.lens_kmean * a_behind)) + (1.f - wl) * a_behind);
+                    phase = 0u;
+                }
                 if (sub == 0) finish_pixel(P, out, idx, cr, cg, cb, ca, depth, n_samples);
-                active = false; pending_finish = false;
+                active = false;
             }
             if (!active) {
                 if (exhausted) break;
@@ -662,6 +772,15 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? 3 : 2) ma
                 sr = q2.x; sg = q2.y; sb = q2.z; sw = q2.w;
                 cr = cg = cb = ca = 0.f; max_weight = 0.f; depth = 0.f; n_samples = 0;
                 active = true;
+                phase = 0u;
+                if (idx & kLensRayFlag) {
+                    // lens ray, first segment: samples up to the lens only, the opaque mesh surface waits behind it
+                    idx &= ~kLensRayFlag;
+                    stash[8] = t_start; stash[9] = t_surface; stash[10] = sr; stash[11] = sg; stash[12] = sb; stash[13] = sw; stash[19] = t_limit;
+                    t_limit = fminf(t_limit, __ldg(out.lens + (size_t)idx * 2).w);
+                    t_surface = 0.f; sr = sg = sb = sw = 0.f;
+                    phase = 1u;
+                }
             }
             const V3 idir = v3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
             // Batch generation.  The reference walks samples one after the other (S/ngp/testbed.cu:596-629); inside an object
@@ -715,6 +834,7 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? 3 : 2) ma
             t_batch_end = tt;
             if (n_valid > 0 || paused) break;
             pending_finish = true;      // the batch came back empty: the ray has ended
+            t = tt;                     // (where its walk stood - the transmitted segment of a lens ray resumes there)
         }
         const bool have = active && !pending_finish && sub < n_valid;
         if (have && sub == 0) ++n_batches;
@@ -778,8 +898,9 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? 3 : 2) ma
             }
             // a batch that came back short because the walk ended (box exit, opaque mesh surface) is the ray's last one: the
             // reference kills the ray when it produced fewer than n_steps samples (S/ngp/testbed.cu:886-901)
+            if (done && phase == 1u) phase = 0u;      // saturated in front of the lens: an ordinary ray after all
             if (done || ended) pending_finish = true;
-            else t = t_batch_end;      // also the resume point of a paused empty-space walk
+            t = t_batch_end;           // the walk's state: resume point of a paused empty-space walk or of a lens ray's next segment
         }
     }
 
@@ -902,7 +1023,7 @@ void launch_debug_trace(const FrameParams& P, const DeviceModel& M, const uint32
 }
 
 __global__ void debug_mesh_kernel(MeshDevice mesh, FrameParams P, const unsigned long long* __restrict__ zbuf, float* __restrict__ rgba2, float* __restrict__ depth2,
-                                  int32_t* __restrict__ tri2, float* __restrict__ surf, float* __restrict__ tsurf) {
+                                  int32_t* __restrict__ tri2, float* __restrict__ surf, float* __restrict__ tsurf, float* __restrict__ lens5) {
     const int ms = P.mesh_scale, W2 = P.width * ms, H2 = P.height * ms;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < W2 * H2 && (rgba2 || depth2 || tri2)) {
@@ -913,17 +1034,22 @@ __global__ void debug_mesh_kernel(MeshDevice mesh, FrameParams P, const unsigned
         if (depth2) depth2[i] = ht;
         if (tri2) tri2[i] = tri;
     }
-    if (i < P.width * P.height && (surf || tsurf)) {
+    if (i < P.width * P.height && (surf || tsurf || lens5)) {
         float s4[4]; float ts;
         mesh_resolve(mesh, P, zbuf, i % P.width, i / P.width, s4, ts);
         if (surf) { surf[i * 4] = s4[0]; surf[i * 4 + 1] = s4[1]; surf[i * 4 + 2] = s4[2]; surf[i * 4 + 3] = s4[3]; }
         if (tsurf) tsurf[i] = ts;
+        if (lens5) {   // same rule as init_one_ray
+            LensHit L; L.w = 0.f; L.t = 0.f; L.n = v3(0.f, 0.f, 1.f);
+            if (P.lens_on) { lens_resolve(mesh, P, zbuf, i % P.width, i / P.width, L); if (L.w > 0.f && ts != 0.0f && ts < L.t) L.w = 0.f; }
+            lens5[i * 5] = L.w; lens5[i * 5 + 1] = L.w > 0.f ? L.t : 0.f; lens5[i * 5 + 2] = L.n.x; lens5[i * 5 + 3] = L.n.y; lens5[i * 5 + 4] = L.n.z;
+        }
     }
 }
 void launch_debug_mesh(const MeshDevice& mesh, const FrameParams& P, const unsigned long long* d_zbuf, float* d_rgba2, float* d_depth2, int32_t* d_tri2,
-                       float* d_surf, float* d_tsurf, cudaStream_t s) {
+                       float* d_surf, float* d_tsurf, float* d_lens5, cudaStream_t s) {
     const int n = P.width * P.mesh_scale * P.height * P.mesh_scale;
-    debug_mesh_kernel<<<(n + 127) / 128, 128, 0, s>>>(mesh, P, d_zbuf, d_rgba2, d_depth2, d_tri2, d_surf, d_tsurf);
+    debug_mesh_kernel<<<(n + 127) / 128, 128, 0, s>>>(mesh, P, d_zbuf, d_rgba2, d_depth2, d_tri2, d_surf, d_tsurf, d_lens5);
 }
 
 }  // namespace nmr

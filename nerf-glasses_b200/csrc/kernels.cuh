@@ -14,7 +14,11 @@ struct FrameOut {
     float4* frame;        // this sample's linear premultiplied frame buffer (parity probe), W*H or null
     float* depth;         // W*H or null
     uint32_t* n_samples;  // network evaluations per ray, W*H or null
+    float4* lens;         // lens hand-off per pixel, 2 x W*H: (normal.xyz, t_lens) (coverage, -, -, -); null when the frame has no lens
+    float* lens_scratch;  // per ray group of the march kernel: state parked across the segments of a lens ray (kLensStash floats each)
 };
+constexpr uint32_t kLensRayFlag = 0x80000000u;   // bit 31 of the pixel index in a ray record: the pixel has a lens hand-off entry
+constexpr int kLensStash = 24;
 
 // device counters of one render: [0] rays queued by the init kernel, [1] queue cursor of the march kernel,
 // [2..3] total network evaluations (64-bit), [4] ray batches, [5] batch generation passes, [6] tile cursor of the init kernel
@@ -42,7 +46,7 @@ void launch_debug_network(const DeviceModel& M, const float* d_pos, const float*
 void launch_debug_trace(const FrameParams& P, const DeviceModel& M, const uint32_t* d_pixels, int64_t n_pix, uint32_t max_samples,
                         float* d_t, uint32_t* d_cell, uint32_t* d_mip, float* d_pos, uint32_t* d_count, float* d_ray, cudaStream_t s);
 void launch_debug_mesh(const MeshDevice& mesh, const FrameParams& P, const unsigned long long* d_zbuf, float* d_rgba2, float* d_depth2, int32_t* d_tri2,
-                       float* d_surf, float* d_tsurf, cudaStream_t s);
+                       float* d_surf, float* d_tsurf, float* d_lens5, cudaStream_t s);
 // floatie pruning on the 2 MiB bitfield (floaties.cu); results[0] = clusters, results[1] = kept cells (host-visible after sync)
 void launch_remove_floaties(uint8_t* d_bitfield, int max_cascade, uint32_t* d_labels, unsigned long long* d_scratch, cudaStream_t s);
 size_t floaties_label_bytes();

@@ -702,6 +702,8 @@ typedef struct {
     float rgba[4];
     float depth;
     uint32_t n_samples;           /* network evaluations consumed (composited or discarded) */
+    int saturated;                /* the last composite call ended on the transmittance / surface-opacity threshold */
+    int lens;                     /* lens ray (handled by march_lens_ray, not by the wavefront loop) */
 } ray_t;
 
 static inline float act_density(float v, int a) {
@@ -773,8 +775,10 @@ static void advance_pos(const orc_model* m, const orc_render_params* P, const aa
 typedef struct { v3 pos; float dt_warped; float t; uint32_t cell; uint32_t mip; } sample_t;
 
 /* generate_next_nerf_network_inputs (S/ngp/testbed.cu:564-633); returns number of samples written */
-static uint32_t generate_samples(const orc_model* m, const orc_render_params* P, const aabb_t* render_aabb, const aabb_t* train_aabb,
-                                 ray_t* r, uint32_t n_steps, sample_t* out, int ignore_surface) {
+/* t_stop (lens rays only, no reference equivalent): no sample beyond it; when the walk stops there or leaves the box, r->t
+ * keeps the walk's position so that a later segment can resume it.  Pass INFINITY for the reference's behaviour. */
+static uint32_t generate_samples_until(const orc_model* m, const orc_render_params* P, const aabb_t* render_aabb, const aabb_t* train_aabb,
+                                       ray_t* r, uint32_t n_steps, sample_t* out, int ignore_surface, float t_stop, int keep_walk_state) {
     v3 origin = r->origin, dir = r->dir;
     v3 idir = v3_make(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
     float cone_angle = P->cone_angle;
@@ -785,8 +789,9 @@ static uint32_t generate_samples(const orc_model* m, const orc_render_params* P,
             if (!ignore_surface && r->t_surface != 0.0f && t > r->t_surface && r->surf[3] == 1.f) {
                 r->n_steps = j; r->t = r->t_surface; return j;
             }
+            if (t > t_stop) { r->n_steps = j; r->t = t; return j; }
             pos = add3(origin, mul3(dir, t));
-            if (!aabb_contains(render_aabb, mat3_mul(P->render_aabb_to_local, pos))) { r->n_steps = j; return j; }
+            if (!aabb_contains(render_aabb, mat3_mul(P->render_aabb_to_local, pos))) { r->n_steps = j; if (keep_walk_state) r->t = t; return j; }
             dt = calc_dt(t - r->t_start, cone_angle);
             mip = (uint32_t)mip_from_dt(dt, pos);
             if (density_grid_occupied_at(pos, m->bitfield, mip)) break;
@@ -808,6 +813,11 @@ static uint32_t generate_samples(const orc_model* m, const orc_render_params* P,
     return n_steps;
 }
 
+static uint32_t generate_samples(const orc_model* m, const orc_render_params* P, const aabb_t* render_aabb, const aabb_t* train_aabb,
+                                 ray_t* r, uint32_t n_steps, sample_t* out, int ignore_surface) {
+    return generate_samples_until(m, P, render_aabb, train_aabb, r, n_steps, out, ignore_surface, INFINITY, 0);
+}
+
 /* composite_kernel_nerf (S/ngp/testbed.cu:784-905) for one ray and its batch of <= n_steps samples */
 static void composite_ray(const orc_render_params* P, const aabb_t* train_aabb, ray_t* r, uint32_t n_steps,
                           const sample_t* smp, const uint16_t* net_out /* [n][4] */, uint32_t current_step) {
@@ -815,6 +825,7 @@ static void composite_ray(const orc_render_params* P, const aabb_t* train_aabb, 
     float local_depth = r->depth;
     const v3 cam_origin = v3_make(P->camera[9], P->camera[10], P->camera[11]);
     uint32_t actual = r->n_steps, j = 0;
+    r->saturated = 0;
     for (; j < actual; ++j) {
         float sr = h2f(net_out[j * 4 + 0]), sg = h2f(net_out[j * 4 + 1]), sb = h2f(net_out[j * 4 + 2]), sd = h2f(net_out[j * 4 + 3]);
         v3 diag = sub3(train_aabb->max, train_aabb->min);
@@ -830,6 +841,7 @@ static void composite_ray(const orc_render_params* P, const aabb_t* train_aabb, 
             T = 1.f - c[3];
             if (c[3] > 0.99f) {
                 float a = c[3]; c[0] /= a; c[1] /= a; c[2] /= a; c[3] /= a;
+                r->saturated = 1;
                 break;
             }
         }
@@ -846,6 +858,7 @@ static void composite_ray(const orc_render_params* P, const aabb_t* train_aabb, 
         }
         if (c[3] > (1.0f - P->min_transmittance)) {
             float a = c[3]; c[0] /= a; c[1] /= a; c[2] /= a; c[3] /= a;
+            r->saturated = 1;
             break;
         }
     }
@@ -866,7 +879,92 @@ static void composite_ray(const orc_render_params* P, const aabb_t* train_aabb, 
  *   frame[W*H*4], depth[W*H]: outputs (cleared here like clear_frame; depth gets 1e10 from init).
  *   n_samples[W*H] (optional): network evaluations per ray.  stats[4] (optional): {rays alive after
  *   first-hit, total samples, wavefront iterations, rays hit}. */
+/* ---- lens rays (NEW functionality: the published reference traces primary rays only; this is the
+ * executable specification of libnmr's secondary rays, DESIGN.md "Secondary rays") ---------------------------------- */
+typedef struct { float f0, k[3], kmean, background[4]; } lens_params_t;
+
+/* Schlick reflectance of a thin lens for unit direction d and unit normal n (turned towards the ray); mirror direction out */
+static float lens_fresnel(const lens_params_t* L, v3 d, v3 n, v3* refl) {
+    float c = dot3(d, n);
+    if (c > 0.f) { n = mul3(n, -1.f); c = -c; }
+    float cosi = fminf(-c, 1.0f);
+    *refl = glm_normalize3(sub3(d, mul3(n, 2.0f * c)));
+    float mm = 1.0f - cosi, m2 = mm * mm;
+    return L->f0 + (1.0f - L->f0) * (m2 * m2 * mm);
+}
+
+/* marches one segment to its end with batches of n samples; returns samples consumed */
+static uint32_t march_segment(const orc_model* m, const orc_render_params* P, const aabb_t* render_aabb, const aabb_t* train_aabb,
+                              ray_t* r, uint32_t n, float t_stop, int keep_walk_state) {
+    uint32_t total = 0, step = 1;
+    while (r->alive && step < 10000u) {
+        sample_t smp[8]; uint16_t out[8 * 4];
+        uint32_t cnt = generate_samples_until(m, P, render_aabb, train_aabb, r, n, smp, 0, t_stop, keep_walk_state);
+        v3 dir01 = v3_make((r->dir.x + 1.0f) * 0.5f, (r->dir.y + 1.0f) * 0.5f, (r->dir.z + 1.0f) * 0.5f);
+        for (uint32_t j = 0; j < cnt; ++j) network_eval(m, smp[j].pos, dir01, out + j * 4, NULL);
+        total += cnt;
+        composite_ray(P, train_aabb, r, n, smp, out, step);
+        step += n;
+    }
+    return total;
+}
+
+/* One lens ray: r arrives after init_ray + advance_pos (clipped / revived at the lens like at a mesh surface).
+ * Segment 1: samples in front of the lens (t <= t_lens), opaque mesh surface inactive.  If the ray saturates there it is an
+ * ordinary ray.  Otherwise split: segment 2 = mirror ray from the hit point (NeRF only, over the background colour), taken when
+ * coverage * F * transmittance >= 1/512; segment 3 = the primary ray carries on from where its walk stood, now with the opaque
+ * surface (surf, t_surface).  Result = front + T_front * (w (F refl + (1 - F) k behind) + (1 - w) behind). */
+static void march_lens_ray(const orc_model* m, const orc_render_params* P, const aabb_t* render_aabb, const aabb_t* train_aabb, const lens_params_t* L,
+                           ray_t* r, uint32_t n, float w, float t_lens, v3 nrm, const float surf[4], float t_surf) {
+    const v3 dir = r->dir, origin = r->origin;
+    const float t_start = r->t_start;
+    r->t_surface = 0.f; r->surf[0] = r->surf[1] = r->surf[2] = r->surf[3] = 0.f;
+    r->n_samples += march_segment(m, P, render_aabb, train_aabb, r, n, t_lens, 1);   /* r->t must end where the walk stood: segment 3 resumes there */
+    if (r->saturated) return;
+    float front[4]; memcpy(front, r->rgba, 16);
+    const float t_resume = r->t;
+    v3 refl;
+    const float F = lens_fresnel(L, dir, nrm, &refl);
+    float LB[3] = { 0.f, 0.f, 0.f };
+    if (w * F * (1.f - front[3]) >= 1.0f / 512.0f) {
+        ray_t b; memset(&b, 0, sizeof(b));
+        b.origin = add3(origin, mul3(dir, t_lens)); b.dir = refl; b.t = 1e-3f; b.alive = 1; b.idx = r->idx;
+        r->n_samples += march_segment(m, P, render_aabb, train_aabb, &b, n, INFINITY, 0);
+        float k = (1.f - b.rgba[3]) * L->background[3];
+        for (int c = 0; c < 3; ++c) LB[c] = b.rgba[c] + L->background[c] * k;
+    }
+    ray_t c3; memset(&c3, 0, sizeof(c3));
+    c3.origin = origin; c3.dir = dir; c3.t = t_resume; c3.t_start = t_start; c3.t_surface = t_surf; memcpy(c3.surf, surf, 16); c3.alive = 1; c3.idx = r->idx;
+    r->n_samples += march_segment(m, P, render_aabb, train_aabb, &c3, n, INFINITY, 0);   /* payload.t semantics of the reference (composite_ray) */
+    const float Tf = 1.f - front[3];
+    for (int c = 0; c < 3; ++c) {
+        float kc = (1.f - F) * L->k[c];
+        r->rgba[c] = front[c] + Tf * (w * (F * LB[c] + kc * c3.rgba[c]) + (1.f - w) * c3.rgba[c]);
+    }
+    r->rgba[3] = front[3] + Tf * (w * (F + (1.f - F) * ((1.f - L->kmean) + L->kmean * c3.rgba[3])) + (1.f - w) * c3.rgba[3]);
+    r->depth = c3.depth;
+}
+
+static int render_impl(const orc_model* m, const orc_render_params* P, const float* surf_rgba, const float* t_surface,
+                       const float* lens_w, const float* lens_t, const float* lens_n, const lens_params_t* L,
+                       float* frame, float* depth, uint32_t* n_samples, uint64_t* stats);
+
 ORC_API int orc_render(const orc_model* m, const orc_render_params* P, const float* surf_rgba, const float* t_surface,
+                       float* frame, float* depth, uint32_t* n_samples, uint64_t* stats) {
+    return render_impl(m, P, surf_rgba, t_surface, NULL, NULL, NULL, NULL, frame, depth, n_samples, stats);
+}
+
+/* orc_render with lens hand-off: lens_w/lens_t [W*H], lens_n [W*H*3] (pixels with lens_w == 0 are ordinary), lens9 = f0, k[3],
+ * kmean, background rgba (the colour the mirror rays see behind the NeRF, in the network's sRGB-like colour space). */
+ORC_API int orc_render_lens(const orc_model* m, const orc_render_params* P, const float* surf_rgba, const float* t_surface,
+                            const float* lens_w, const float* lens_t, const float* lens_n, const float* lens9,
+                            float* frame, float* depth, uint32_t* n_samples, uint64_t* stats) {
+    lens_params_t L; L.f0 = lens9[0]; L.k[0] = lens9[1]; L.k[1] = lens9[2]; L.k[2] = lens9[3]; L.kmean = lens9[4]; memcpy(L.background, lens9 + 5, 16);
+    return render_impl(m, P, surf_rgba, t_surface, lens_w, lens_t, lens_n, &L, frame, depth, n_samples, stats);
+}
+
+static int render_impl(const orc_model* m, const orc_render_params* P, const float* surf_rgba, const float* t_surface,
+                       const float* lens_w, const float* lens_t, const float* lens_n, const lens_params_t* L,
                        float* frame, float* depth, uint32_t* n_samples, uint64_t* stats) {
     const int W = P->width, H = P->height;
     int x0 = P->x0, y0 = P->y0, x1 = P->x1, y1 = P->y1;
@@ -886,6 +984,7 @@ ORC_API int orc_render(const orc_model* m, const orc_render_params* P, const flo
             r->t_surface = t_surface[r->idx];
             memcpy(r->surf, surf_rgba + (size_t)r->idx * 4, 16);
         }
+        if (lens_w && lens_w[r->idx] > 0.f) { r->lens = 1; r->t_surface = lens_t[r->idx]; }   /* the first-hit walk is clipped / revived at the lens */
         depth[r->idx] = 1e10f;
         frame[(size_t)r->idx * 4 + 0] = frame[(size_t)r->idx * 4 + 1] = frame[(size_t)r->idx * 4 + 2] = frame[(size_t)r->idx * 4 + 3] = 0.f;
         advance_pos(m, P, &render_aabb, r);
@@ -894,6 +993,25 @@ ORC_API int orc_render(const orc_model* m, const orc_render_params* P, const flo
     for (size_t i = 0; i < N; ++i) n_alive0 += rays[i].alive ? 1 : 0;
     uint64_t total_samples = 0, iterations = 0;
     uint32_t step = 1;
+    /* lens rays are marched on their own after the wavefront loop, with the batch size the first iteration would use */
+    uint32_t n_lens = 1;
+    if (P->n_steps_mode == 1 && n_alive0 > 0) { uint64_t q = (uint64_t)N / n_alive0; n_lens = (uint32_t)(q < 1 ? 1 : (q > 8 ? 8 : q)); }
+    uint64_t lens_samples = 0;
+    if (L) {
+#pragma omp parallel for schedule(dynamic, 4) reduction(+:lens_samples)
+        for (int64_t i = 0; i < (int64_t)N; ++i) {
+            ray_t* r = &rays[i];
+            if (!r->lens || !r->alive) { if (r->lens) r->lens = 0; continue; }
+            const float* sf = surf_rgba ? surf_rgba + (size_t)r->idx * 4 : NULL;
+            float zero[4] = { 0.f, 0.f, 0.f, 0.f };
+            march_lens_ray(m, P, &render_aabb, &train_aabb, L, r, n_lens, lens_w[r->idx], lens_t[r->idx],
+                           v3_make(lens_n[(size_t)r->idx * 3], lens_n[(size_t)r->idx * 3 + 1], lens_n[(size_t)r->idx * 3 + 2]),
+                           sf ? sf : zero, t_surface ? t_surface[r->idx] : 0.f);
+            r->alive = 0;
+            lens_samples += r->n_samples;
+        }
+    }
+    total_samples += lens_samples;
     while (1) {
         uint64_t n_alive = 0;
         for (size_t i = 0; i < N; ++i) n_alive += rays[i].alive ? 1 : 0;
@@ -1004,6 +1122,7 @@ typedef struct {
     float base_color[4], emissive[3], metallic, roughness;
     int tex_w, tex_h;
     float* tex_lin;    /* [h][w][4] linearised sRGB texture (alpha linear) or NULL */
+    uint8_t* tri_lens;   /* per triangle: 1 = lens surface (NULL: none) */
 } orc_mesh;
 
 /* r_wxyz: the (w,x,y,z) quaternion NerfMeshRenderer::loadMesh builds from its Vector4f argument
@@ -1043,7 +1162,7 @@ ORC_API orc_mesh* orc_mesh_create(const float* pos, const float* nrm, const floa
     }
     return M;
 }
-ORC_API void orc_mesh_destroy(orc_mesh* M) { if (!M) return; free(M->wpos); free(M->wnrm); free(M->uv); free(M->idx); free(M->tex_lin); free(M); }
+ORC_API void orc_mesh_destroy(orc_mesh* M) { if (!M) return; free(M->wpos); free(M->wnrm); free(M->uv); free(M->idx); free(M->tex_lin); free(M->tri_lens); free(M); }
 ORC_API void orc_mesh_world_positions(const orc_mesh* M, float* out) { memcpy(out, M->wpos, sizeof(v3) * M->n_verts); }
 
 /* bilinear, wrap addressing, normalised coordinates, texel centres at +0.5 (S/cuda_texture.cu:22-28) */
@@ -1165,6 +1284,72 @@ ORC_API void orc_mesh_render(const orc_mesh* M, const float* camera12, const flo
             }
             if (out_tri) out_tri[i] = best;
         }
+    }
+}
+
+/* ---- lens surfaces (new functionality, see march_lens_ray) ---- */
+ORC_API void orc_mesh_set_lens(orc_mesh* M, const uint8_t* tri_lens) {
+    free(M->tri_lens); M->tri_lens = NULL;
+    if (tri_lens) { M->tri_lens = (uint8_t*)malloc(M->n_tris); memcpy(M->tri_lens, tri_lens, M->n_tris); }
+}
+
+/* Like orc_mesh_render but in two layers: the nearest OPAQUE hit (shaded RGBA + hitT, NaN on miss) and the nearest LENS hit
+ * (hitT, 0 on miss, and the unit shading normal). */
+ORC_API void orc_mesh_render_layers(const orc_mesh* M, const float* camera12, const float* light_pos, int W2, int H2,
+                                    float* rgba, float* depth, float* lens_depth, float* lens_normal) {
+    const v3 U = v3_make(camera12[0], camera12[1], camera12[2]), Vv = v3_make(camera12[3], camera12[4], camera12[5]);
+    const v3 Wv = v3_make(camera12[6], camera12[7], camera12[8]), eye = v3_make(camera12[9], camera12[10], camera12[11]);
+    const v3 light = v3_make(light_pos[0], light_pos[1], light_pos[2]);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int y = 0; y < H2; ++y) {
+        for (int x = 0; x < W2; ++x) {
+            float dx = 2.0f * (((float)x + 0.5f) / (float)W2) - 1.0f;
+            float dy = 2.0f * (((float)y + 0.5f) / (float)H2) - 1.0f;
+            v3 dir = glm_normalize3(v3_make((dx * U.x + dy * Vv.x) + Wv.x, (dx * U.y + dy * Vv.y) + Wv.y, (dx * U.z + dy * Vv.z) + Wv.z));
+            float best_t[2] = { 1e16f, 1e16f }, bu[2] = { 0, 0 }, bv[2] = { 0, 0 }; int32_t best[2] = { -1, -1 };
+            for (uint32_t tri = 0; tri < M->n_tris; ++tri) {
+                float t, u, v;
+                const int layer = (M->tri_lens && M->tri_lens[tri]) ? 1 : 0;
+                if (ray_tri(eye, dir, M->wpos[M->idx[tri * 3]], M->wpos[M->idx[tri * 3 + 1]], M->wpos[M->idx[tri * 3 + 2]], &t, &u, &v) && t < best_t[layer]) {
+                    best_t[layer] = t; bu[layer] = u; bv[layer] = v; best[layer] = (int32_t)tri;
+                }
+            }
+            size_t i = (size_t)y * W2 + x;
+            if (best[0] >= 0) { shade_hit(M, (uint32_t)best[0], bu[0], bv[0], best_t[0], eye, dir, light, rgba + i * 4); depth[i] = best_t[0]; }
+            else { rgba[i * 4] = rgba[i * 4 + 1] = rgba[i * 4 + 2] = rgba[i * 4 + 3] = 0.f; uint32_t nanbits = 0xFFFFFFFFu; memcpy(&depth[i], &nanbits, 4); }
+            lens_depth[i] = 0.f; lens_normal[i * 3] = 0.f; lens_normal[i * 3 + 1] = 0.f; lens_normal[i * 3 + 2] = 1.f;
+            if (best[1] >= 0) {
+                const uint32_t tri = (uint32_t)best[1], i0 = M->idx[tri * 3], i1 = M->idx[tri * 3 + 1], i2 = M->idx[tri * 3 + 2];
+                float bw = 1.0f - bu[1] - bv[1];
+                v3 n = glm_normalize3(add3(add3(mul3(M->wnrm[i1], bu[1]), mul3(M->wnrm[i2], bv[1])), mul3(M->wnrm[i0], bw)));
+                lens_depth[i] = best_t[1]; lens_normal[i * 3] = n.x; lens_normal[i * 3 + 1] = n.y; lens_normal[i * 3 + 2] = n.z;
+            }
+        }
+    }
+}
+
+/* Lens hand-off per pixel: a tap counts when it has a lens hit in front of its opaque hit; w = counted / taps, t = the nearest
+ * counted hit (first in tap order on ties), n = its normal.  The event is dropped when the pixel's opaque t_surface (max over
+ * the taps) lies in front of it. */
+ORC_API void orc_lens_resolve(const float* depth2, const float* lens_depth2, const float* lens_normal2, const float* t_surface, int W, int H, int mesh_scale,
+                              float* out_w, float* out_t, float* out_n) {
+    const int W2 = W * mesh_scale;
+#pragma omp parallel for schedule(static)
+    for (int idx = 0; idx < W * H; ++idx) {
+        int px = idx % W, py = idx / W, n_l = 0; float best = 3.402823466e+38f; size_t bi = 0;
+        for (int i = 0; i < mesh_scale; ++i) for (int j = 0; j < mesh_scale; ++j) {
+            size_t o = (size_t)(py * mesh_scale + j) * W2 + (size_t)(px * mesh_scale + i);
+            float tl = lens_depth2[o];
+            if (!(tl > 0.f)) continue;
+            float to = depth2[o];
+            if (to == to && !(tl < to)) continue;     /* opaque hit (not NaN) at or in front of the lens */
+            ++n_l;
+            if (tl < best) { best = tl; bi = o; }
+        }
+        float w = n_l ? (float)n_l / (float)(mesh_scale * mesh_scale) : 0.f;
+        if (w > 0.f && t_surface[idx] != 0.0f && t_surface[idx] < best) w = 0.f;
+        out_w[idx] = w; out_t[idx] = w > 0.f ? best : 0.f;
+        out_n[idx * 3] = n_l ? lens_normal2[bi * 3] : 0.f; out_n[idx * 3 + 1] = n_l ? lens_normal2[bi * 3 + 1] : 0.f; out_n[idx * 3 + 2] = n_l ? lens_normal2[bi * 3 + 2] : 1.f;
     }
 }
 

@@ -99,6 +99,10 @@ def lib():
         "orc_calc_dt": (C.c_float, [C.c_float, C.c_float]),
         "orc_num_threads": (C.c_int, []),
         "orc_set_num_threads": (None, [C.c_int]),
+        "orc_render_lens": (C.c_int, [vp, C.POINTER(RenderParams), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "orc_mesh_set_lens": (None, [vp, vp]),
+        "orc_mesh_render_layers": (None, [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp]),
+        "orc_lens_resolve": (None, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -230,8 +234,9 @@ class Model:
             P.x0, P.y0, P.x1, P.y1 = window
         return P
 
-    def render_frame(self, P: RenderParams, surf_rgba=None, t_surface=None):
-        """-> (frame f32[H,W,4] linear premultiplied, depth f32[H,W], n_samples u32[H,W], stats dict)"""
+    def render_frame(self, P: RenderParams, surf_rgba=None, t_surface=None, lens=None):
+        """-> (frame f32[H,W,4] linear premultiplied, depth f32[H,W], n_samples u32[H,W], stats dict)
+        lens (new functionality, no reference equivalent) = dict(w, t, n, f0, k (3), background (4)): per-pixel lens hand-off."""
         W, H = P.width, P.height
         frame = np.zeros((H, W, 4), dtype=np.float32); depth = np.zeros((H, W), dtype=np.float32)
         ns = np.zeros((H, W), dtype=np.uint32); stats = np.zeros(4, dtype=np.uint64)
@@ -239,7 +244,14 @@ class Model:
         if t_surface is not None:
             surf_rgba = np.ascontiguousarray(surf_rgba, dtype=np.float32); t_surface = np.ascontiguousarray(t_surface, dtype=np.float32)
             sp, tp = _p(surf_rgba), _p(t_surface)
-        rc = lib().orc_render(self.h, C.byref(P), sp, tp, _p(frame), _p(depth), _p(ns), _p(stats))
+        if lens is not None:
+            lw = np.ascontiguousarray(lens["w"], dtype=np.float32); lt = np.ascontiguousarray(lens["t"], dtype=np.float32)
+            ln = np.ascontiguousarray(lens["n"], dtype=np.float32)
+            k = np.asarray(lens["k"], dtype=np.float32)
+            l9 = np.array([lens["f0"], k[0], k[1], k[2], float((k[0] + k[1] + k[2]) / np.float32(3.0)), *lens["background"]], dtype=np.float32)
+            rc = lib().orc_render_lens(self.h, C.byref(P), sp, tp, _p(lw), _p(lt), _p(ln), _p(l9), _p(frame), _p(depth), _p(ns), _p(stats))
+        else:
+            rc = lib().orc_render(self.h, C.byref(P), sp, tp, _p(frame), _p(depth), _p(ns), _p(stats))
         if rc != 0:
             raise RuntimeError("orc_render failed")
         return frame, depth, ns, {"alive_after_first_hit": int(stats[0]), "samples": int(stats[1]),
@@ -287,6 +299,22 @@ class Mesh:
         except Exception:
             pass
 
+    def set_lens(self, tri_lens):
+        """Per-triangle lens flags (uint8) or None."""
+        if tri_lens is None:
+            lib().orc_mesh_set_lens(self.h, None)
+        else:
+            f = np.ascontiguousarray(tri_lens, dtype=np.uint8)
+            lib().orc_mesh_set_lens(self.h, _p(f))
+
+    def render_layers(self, camera12, W2: int, H2: int, light=(1.0, 1.0, 1.0)):
+        """-> (opaque rgba, opaque hitT (NaN on miss), lens hitT (0 on miss), lens unit normal)"""
+        cam = np.asarray(camera12, dtype=np.float32); lp = np.asarray(light, dtype=np.float32)
+        rgba = np.zeros((H2, W2, 4), dtype=np.float32); depth = np.zeros((H2, W2), dtype=np.float32)
+        ld = np.zeros((H2, W2), dtype=np.float32); ln = np.zeros((H2, W2, 3), dtype=np.float32)
+        lib().orc_mesh_render_layers(self.h, _p(cam), _p(lp), W2, H2, _p(rgba), _p(depth), _p(ld), _p(ln))
+        return rgba, depth, ld, ln
+
     def world_positions(self) -> np.ndarray:
         out = np.empty((self.n_verts, 3), dtype=np.float32)
         lib().orc_mesh_world_positions(self.h, _p(out))
@@ -308,6 +336,20 @@ def mesh_resolve(rgba2: np.ndarray, depth2: np.ndarray, W: int, H: int, mesh_sca
     surf = np.empty((H, W, 4), dtype=np.float32); ts = np.empty((H, W), dtype=np.float32)
     lib().orc_mesh_resolve(_p(rgba2), _p(depth2), W, H, mesh_scale, _p(surf), _p(ts))
     return surf, ts
+
+
+def lens_resolve(depth2, lens_depth2, lens_normal2, t_surface, W: int, H: int, mesh_scale: int = 2):
+    """-> (coverage w f32[H,W], t_lens f32[H,W], normal f32[H,W,3])"""
+    d2 = np.ascontiguousarray(depth2, dtype=np.float32); l2 = np.ascontiguousarray(lens_depth2, dtype=np.float32)
+    n2 = np.ascontiguousarray(lens_normal2, dtype=np.float32); ts = np.ascontiguousarray(t_surface, dtype=np.float32)
+    w = np.empty((H, W), dtype=np.float32); t = np.empty((H, W), dtype=np.float32); n = np.empty((H, W, 3), dtype=np.float32)
+    lib().orc_lens_resolve(_p(d2), _p(l2), _p(n2), _p(ts), W, H, mesh_scale, _p(w), _p(t), _p(n))
+    return w, t, n
+
+
+def lens_f0(ior: float) -> np.float32:
+    r0 = (np.float32(ior) - np.float32(1.0)) / (np.float32(ior) + np.float32(1.0))
+    return np.float32(r0 * r0)
 
 
 def bitfield_to_cells(bitfield: np.ndarray) -> np.ndarray:

@@ -60,6 +60,14 @@ def debug_mesh(r, W, H, ms=2):
     return rgba2, d2, tri2, surf, ts
 
 
+def debug_lens(r, W, H):
+    """Lens hand-off per pixel: coverage, hit distance, unit normal."""
+    import pynmr
+    w = np.zeros((H, W), dtype=np.float32); t = np.zeros((H, W), dtype=np.float32); n = np.zeros((H, W, 3), dtype=np.float32)
+    r._ck(pynmr.lib().nmr_debug_lens(r._h, W, H, p(w), p(t), p(n)))
+    return w, t, n
+
+
 def debug_last_frame(r, W, H):
     import pynmr
     fr = np.zeros((H, W, 4), dtype=np.float32); dp = np.zeros((H, W), dtype=np.float32); ns = np.zeros((H, W), dtype=np.uint32)
@@ -89,13 +97,25 @@ def oracle_scene(snap, width, height, cam12, glasses=None, spp_index=0, n_steps_
     m = O.Model.from_snapshot(snap)
     amin, amax = (snap["render_aabb_min"], snap["render_aabb_max"]) if aabb is None else aabb
     P = m.params_struct(width, height, cam12, aabb_min=amin, aabb_max=amax, spp_index=spp_index, n_steps_mode=n_steps_mode)
-    surf = ts = None
+    surf = ts = lens = None
     if glasses is not None:
         g = synth.read_gltf(glasses["path"])
         mesh = O.Mesh(g["positions"], g["normals"], g["texcoords"], g["indices"], glasses["t"], glasses["s"], glasses["r"],
                       g["base_color"], g["metallic"], g["roughness"], (0, 0, 0), glasses.get("texture"))
-        rgba2, d2, _ = mesh.render(cam12, 2 * width, 2 * height)
-        surf, ts = O.mesh_resolve(rgba2, d2, width, height, 2)
-    frame, depth, ns, stats = m.render_frame(P, surf, ts)
+        if g["lens"] is not None and glasses.get("lens", True):
+            # lens surfaces (new functionality): two visibility layers, lens hand-off, secondary rays in the oracle
+            mesh.set_lens(g["tri_lens"])
+            rgba2, d2, ld2, ln2 = mesh.render_layers(cam12, 2 * width, 2 * height)
+            surf, ts = O.mesh_resolve(rgba2, d2, width, height, 2)
+            lw, lt, lnn = O.lens_resolve(d2, ld2, ln2, ts, width, height, 2)
+            lp = g["lens"]
+            lens = {"w": lw, "t": lt, "n": lnn, "f0": O.lens_f0(lp["ior"]), "k": np.float32(lp["transmission"]) * lp["tint"].astype(np.float32),
+                    "background": (1.0, 1.0, 1.0, 1.0)}
+        else:
+            rgba2, d2, _ = mesh.render(cam12, 2 * width, 2 * height)
+            surf, ts = O.mesh_resolve(rgba2, d2, width, height, 2)
+    frame, depth, ns, stats = m.render_frame(P, surf, ts, lens=lens)
+    if lens is not None:
+        stats = dict(stats, lens=lens)
     img, _ = O.accumulate_tonemap(frame, None, 0, to_srgb=True)
     return img, frame, ns, stats, (surf, ts)

@@ -473,6 +473,71 @@ def write_glasses_gltf(out_dir: str, texture_rgba=(128, 128, 128, 255), npz_path
     return path
 
 
+LENS_IOR, LENS_TRANSMISSION, LENS_TINT = 1.5, 0.85, (0.75, 0.9, 1.0)
+
+
+def write_lens_glasses_gltf(out_dir: str, texture_rgba=(128, 128, 128, 255), npz_path: str = GLASSES_NPZ,
+                            ior: float = LENS_IOR, transmission: float = LENS_TRANSMISSION, tint=LENS_TINT) -> str:
+    """glasses.gltf with a second primitive: two lens panes inside the rims (two-sided quads in the plane of the front frame),
+    whose material is transmissive (KHR_materials_transmission + KHR_materials_ior).  The reference asset carries no such
+    material (one opaque primitive); this is the fixture of the lens / secondary-ray path."""
+    m = np.load(npz_path)
+    pos, nrm, uv, idx = m["positions"], m["normals"], m["texcoords"], m["indices"]
+    lp, ln, li = [], [], []
+    y0 = -0.03
+    for (xa, xb) in ((-0.68, -0.12), (0.12, 0.68)):
+        za, zb = -0.12, 0.28
+        quad = [(xa, y0, za), (xb, y0, za), (xb, y0, zb), (xa, y0, zb)]
+        b = len(lp)
+        lp += quad; ln += [(0.0, 1.0, 0.0)] * 4; li += [b, b + 2, b + 1, b, b + 3, b + 2]          # front face (+y)
+        b = len(lp)
+        lp += quad; ln += [(0.0, -1.0, 0.0)] * 4; li += [b, b + 1, b + 2, b, b + 2, b + 3]         # back face (-y)
+    lp = np.array(lp, dtype=np.float32); ln = np.array(ln, dtype=np.float32); luv = np.zeros((len(lp), 2), dtype=np.float32)
+    li = np.array(li, dtype=np.uint16)
+    os.makedirs(out_dir, exist_ok=True)
+    parts = [pos.astype("<f4").tobytes(), nrm.astype("<f4").tobytes(), uv.astype("<f4").tobytes(), idx.astype("<u2").tobytes()]
+    if len(parts[3]) % 4:
+        parts[3] += b"\0" * (4 - len(parts[3]) % 4)
+    parts += [lp.astype("<f4").tobytes(), ln.astype("<f4").tobytes(), luv.astype("<f4").tobytes(), li.astype("<u2").tobytes()]
+    offs = np.cumsum([0] + [len(p) for p in parts])
+    with open(os.path.join(out_dir, "glasses.bin"), "wb") as f:
+        f.write(b"".join(parts))
+    tex = np.tile(np.array(texture_rgba, dtype=np.uint8), (4, 4, 1))
+    with open(os.path.join(out_dir, "glasses.png"), "wb") as f:
+        f.write(_png_bytes(tex))
+    counts = [pos.shape[0], nrm.shape[0], uv.shape[0], idx.shape[0], lp.shape[0], ln.shape[0], luv.shape[0], li.shape[0]]
+    types = ["VEC3", "VEC3", "VEC2", "SCALAR"] * 2
+    comp = [5126, 5126, 5126, 5123] * 2
+    doc = {
+        "asset": {"generator": "nmr-b200 fixture writer", "version": "2.0"},
+        "extensionsUsed": ["KHR_materials_transmission", "KHR_materials_ior"],
+        "scene": 0,
+        "scenes": [{"name": "Scene", "nodes": [0]}],
+        "nodes": [{"mesh": 0, "name": "Glasses.001", "rotation": [float(x) for x in m["node_rotation_xyzw"]],
+                   "translation": [float(x) for x in m["node_translation"]]}],
+        "materials": [{"doubleSided": True, "name": "oculos",
+                       "pbrMetallicRoughness": {"baseColorTexture": {"index": 0}, "metallicFactor": 0, "roughnessFactor": float(m["roughness"])}},
+                      {"doubleSided": True, "name": "lens", "alphaMode": "BLEND",
+                       "pbrMetallicRoughness": {"baseColorFactor": [float(tint[0]), float(tint[1]), float(tint[2]), 1.0], "metallicFactor": 0, "roughnessFactor": 0.05},
+                       "extensions": {"KHR_materials_transmission": {"transmissionFactor": float(transmission)}, "KHR_materials_ior": {"ior": float(ior)}}}],
+        "meshes": [{"name": "Glasses.001", "primitives": [
+            {"attributes": {"POSITION": 0, "NORMAL": 1, "TEXCOORD_0": 2}, "indices": 3, "material": 0},
+            {"attributes": {"POSITION": 4, "NORMAL": 5, "TEXCOORD_0": 6}, "indices": 7, "material": 1}]}],
+        "textures": [{"sampler": 0, "source": 0}],
+        "images": [{"mimeType": "image/png", "name": "glasses", "uri": "glasses.png"}],
+        "accessors": [dict({"bufferView": i, "componentType": comp[i], "count": int(counts[i]), "type": types[i]},
+                           **({"max": [float(x) for x in (pos if i == 0 else lp).max(0)], "min": [float(x) for x in (pos if i == 0 else lp).min(0)]} if i in (0, 4) else {}))
+                      for i in range(8)],
+        "bufferViews": [{"buffer": 0, "byteLength": len(parts[i]) if i != 3 else idx.nbytes, "byteOffset": int(offs[i]), "target": 34963 if i % 4 == 3 else 34962} for i in range(8)],
+        "samplers": [{"magFilter": 9729, "minFilter": 9987}],
+        "buffers": [{"byteLength": int(offs[-1]), "uri": "glasses.bin"}],
+    }
+    path = os.path.join(out_dir, "glasses.gltf")
+    with open(path, "w") as f:
+        json.dump(doc, f, indent=1)
+    return path
+
+
 def read_gltf(path: str) -> dict:
     """Test-side glTF reader (json + numpy), independent of the C++ loader."""
     with open(path) as f:
@@ -489,13 +554,29 @@ def read_gltf(path: str) -> dict:
         arr = np.frombuffer(bufs[bv["buffer"]], dtype=dt, count=a["count"] * ncomp, offset=off)
         return arr.reshape(a["count"], ncomp) if ncomp > 1 else arr
     node = doc["nodes"][doc["scenes"][doc.get("scene", 0)]["nodes"][0]]
-    prim = doc["meshes"][node["mesh"]]["primitives"][0]
-    mat = doc["materials"][prim["material"]]["pbrMetallicRoughness"]
+    prims = doc["meshes"][node["mesh"]]["primitives"]
+    mat = doc["materials"][prims[0]["material"]]["pbrMetallicRoughness"]
+    P, N, T, I, L = [], [], [], [], []
+    lens = None
+    base = 0
+    for prim in prims:      # concatenated like the C++ loader; material of the first primitive; lens flags per triangle
+        p = acc(prim["attributes"]["POSITION"]).astype(np.float32)
+        P.append(p); N.append(acc(prim["attributes"]["NORMAL"]).astype(np.float32)); T.append(acc(prim["attributes"]["TEXCOORD_0"]).astype(np.float32))
+        i = acc(prim["indices"]).astype(np.int64) + base
+        I.append(i); base += p.shape[0]
+        md = doc["materials"][prim["material"]]
+        ext = md.get("extensions", {})
+        tf = float(ext.get("KHR_materials_transmission", {}).get("transmissionFactor", 0.0))
+        bc = md.get("pbrMetallicRoughness", {}).get("baseColorFactor", [1, 1, 1, 1])
+        is_lens = tf > 0.0 or (md.get("alphaMode") == "BLEND" and bc[3] < 1.0)
+        if is_lens and tf <= 0.0:
+            tf = 1.0 - bc[3]
+        L.append(np.full(i.size // 3, 1 if is_lens else 0, dtype=np.uint8))
+        if is_lens and lens is None:
+            lens = {"ior": float(ext.get("KHR_materials_ior", {}).get("ior", 1.5)), "transmission": tf, "tint": np.array(bc[:3], dtype=np.float32)}
     return {
-        "positions": acc(prim["attributes"]["POSITION"]).astype(np.float32),
-        "normals": acc(prim["attributes"]["NORMAL"]).astype(np.float32),
-        "texcoords": acc(prim["attributes"]["TEXCOORD_0"]).astype(np.float32),
-        "indices": acc(prim["indices"]).astype(np.uint16),
+        "positions": np.concatenate(P), "normals": np.concatenate(N), "texcoords": np.concatenate(T),
+        "indices": np.concatenate(I).astype(np.uint16), "tri_lens": np.concatenate(L), "lens": lens,
         "base_color": np.array(mat.get("baseColorFactor", [1, 1, 1, 1]), dtype=np.float32),
         "metallic": float(mat.get("metallicFactor", 1.0)), "roughness": float(mat.get("roughnessFactor", 1.0)),
     }
