@@ -271,6 +271,52 @@ def reference_gpu_leg(args, local_rank: int):
     return out
 
 
+def run_tiles(args, rank: int, world: int, local_rank: int, dist):
+    """--mode tiles (BASELINE configs[3]): ONE frame per step, its rows dealt to the ranks in bands, gathered to rank 0 with one
+    NCCL collective (pynmr/dist.py).  Strong scaling: total work per step is fixed.  Timed on the device (CUDA events on the
+    stream the gather runs on, after libnmr's stream has been joined), max over ranks."""
+    import torch
+    import pynmr
+    import synth
+    from pynmr import dist as D
+    W, H = args.width, args.height
+    with tempfile.TemporaryDirectory() as tmp:
+        snap, _ = make_inputs(tmp, args.log2_hashmap_size, args.regime)
+        gltf = synth.write_lens_glasses_gltf(os.path.join(tmp, "lensmesh")) if args.lens else synth.write_glasses_gltf(os.path.join(tmp, "mesh2"))
+        r = pynmr.NerfMeshRenderer(W, H, local_rank)
+        if r.load_nerf(snap) is None or r.load_mesh(gltf, t=synth.GLASSES_T, s=synth.GLASSES_S, r=synth.GLASSES_R_WXYZ) is None:
+            raise RuntimeError("inputs failed to load")
+        r.remove_floaties()
+    if args.zoom:
+        r.orbit(0.0, 0.0, args.zoom)
+    r.set_surface_insertion(pynmr.NerfMeshRenderer.SURFACE_BATCH8)     # one decision for all shards
+    sr = D.ShardedRenderer(r, rank, world, band=args.band)
+    a = 0.0
+    for _ in range(args.warmup):
+        a += 0.03; r.orbit(*orbit_step(a)); sr.render_frame(dst=0)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        a += 0.03; r.orbit(*orbit_step(a))
+        full = sr.render_frame(dst=0)           # copy_device_image joins libnmr's stream before the gather is enqueued
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t[0]); dist.barrier()
+    if rank != 0:
+        return None
+    return {"metric": "Mrays/s", "value": W * H * args.steps / (ms / 1e3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": f"one {W}x{H} hybrid frame per step{' with lens secondary rays' if args.lens else ''}, rows dealt to ranks in bands of {args.band}, NCCL gather to rank 0 (BASELINE configs[3])",
+                       "model": f"synthetic iNGP snapshot seed 1337 ({args.regime}), log2_hashmap_size={args.log2_hashmap_size}", "zoom": args.zoom,
+                       "parallelism": f"tiles: {world} ranks, one process per GPU, one gather per frame"},
+            "fps": args.steps / (ms / 1e3), "checksum": float(full[H // 2, W // 2, 0]) if full is not None else None}
+
+
 def oracle_sample(args, steps: int, warmup: int):
     """Times the CPU oracle (the reference has no CPU renderer; this is the restated reference algorithm) on a bounded
     sample of the same workload: a crop of the 1080p hybrid frame around the head, same model / mesh / camera path."""
@@ -349,6 +395,9 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the stress and reference-on-GPU legs")
+    ap.add_argument("--mode", default="views", choices=["views", "tiles"], help="views (default, the headline): every rank renders its own frames; tiles: one frame split over the ranks and gathered")
+    ap.add_argument("--band", type=int, default=16)
+    ap.add_argument("--lens", action="store_true", help="tiles mode: glasses with lens panes (secondary rays)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -366,6 +415,16 @@ def main():
         torch.cuda.set_device(local_rank)
         td.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
         dist = td
+    if args.mode == "tiles":
+        if world == 1:
+            import torch
+            torch.cuda.set_device(local_rank)
+        out = run_tiles(args, rank, world, local_rank, dist)
+        if rank == 0:
+            print(json.dumps(out), flush=True)
+        if dist is not None:
+            dist.barrier(); dist.destroy_process_group()
+        return 0
     out = run_ours(args, rank, world, local_rank, dist)
     if rank == 0:
         if world == 1 and not args.no_extras:

@@ -96,6 +96,20 @@ with tempfile.TemporaryDirectory() as d:
             print(json.dumps({"config": f"C4 3840x2160 hybrid frame, orbit zoom {zoom:g}", "gpu_ms": ms, "march_ms": mms, "fps": 1e3 / ms, "mrays_per_s": W * HH / ms / 1e3,
                               "samples_per_frame": smp, "msamples_per_s": smp / ms / 1e3}), flush=True)
 
+    if "4" in todo:     # the same 4K frame with lens panes: mirror + transmitted segments on the covered pixels
+        W, HH = 3840, 2160
+        lens_gltf = synth.write_lens_glasses_gltf(os.path.join(d, "lensmesh"))
+        r = pynmr.NerfMeshRenderer(W, HH)
+        nerf = r.load_nerf(snap19)
+        r.load_mesh(lens_gltf, t=synth.GLASSES_T, s=synth.GLASSES_S, r=synth.GLASSES_R_WXYZ)
+        r.remove_floaties()
+        for zoom in (0.0, 4.0):
+            if zoom:
+                r.orbit(0, 0, zoom)
+            ms, mms, smp = frames(r, 10)
+            print(json.dumps({"config": f"C4 3840x2160 hybrid frame with lens secondary rays, orbit zoom {zoom:g}", "gpu_ms": ms, "march_ms": mms, "fps": 1e3 / ms,
+                              "mrays_per_s": W * HH / ms / 1e3, "samples_per_frame": smp, "msamples_per_s": smp / ms / 1e3}), flush=True)
+
     if "5" in todo:
         W, HH = 1920, 1080
         for regime in ("opaque", "translucent"):
