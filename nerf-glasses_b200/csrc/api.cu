@@ -113,6 +113,8 @@ struct nmr_ctx {
     float mesh_wmin[3] = {0.f, 0.f, 0.f}, mesh_wmax[3] = {0.f, 0.f, 0.f};   // world-space box of the concatenated mesh
     Surfaces surf;
     DevBuf<uint32_t> d_counters;
+    DevBuf<uint32_t> d_bands;                             // nmr_render's bands: queue ends e[0..K], cursors c[0..K-1]
+    cudaEvent_t ev_band[8] = {};                          // band b rendered
     uint32_t* h_counters = nullptr;                       // pinned
     DevBuf<float> d_scratch;
     int shard_rank = 0, shard_world = 1, shard_band = 8;
@@ -362,6 +364,60 @@ void enqueue_pass(nmr_ctx* ctx, Nerf& n, const FrameParams& P, bool timed) {
     CK(cudaGetLastError());
 }
 
+// nmr_render's single-sample path: the frame is cut into K bands of contiguous rows.  All K ray set-ups run first (they fill
+// one queue; each band's end is latched on the device), so every band's march sees the whole frame's live-ray count - the
+// surface insertion rule must not depend on the banding - and then band b is marched and handed to the copy stream while band
+// b + 1 is marched: the 16 bytes per pixel cross PCIe underneath the rendering instead of after it.
+void enqueue_pass_banded(nmr_ctx* ctx, Nerf& n, const FrameParams& P0, float* out_host) {
+    constexpr int K = 4;
+    Surfaces& S = ctx->surf;
+    const int band_rows = (P0.height + K - 1) / K;
+    const bool probes = (ctx->debug_flags & kDebugKeepProbes) != 0;
+    FrameOut out{S.image.p, S.accum.p, probes ? S.frame.p : nullptr, probes ? S.depth.p : nullptr, probes ? S.n_samples.p : nullptr, nullptr, nullptr};
+    MeshDevice mesh = ctx->mesh_dev;
+    if (!P0.lens_on) mesh.tri_lens = nullptr;
+    else {
+        S.lens.ensure((size_t)P0.width * P0.height * 2);
+        S.lens_scratch.ensure((size_t)ctx->num_sms * 3 * 32 * kLensStash);
+        out.lens = S.lens.p; out.lens_scratch = S.lens_scratch.p;
+    }
+    ctx->d_bands.ensure(2 * (K + 1));
+    uint32_t* e = ctx->d_bands.p;            // e[0] = 0, e[b + 1] = queue length after band b's set-up
+    uint32_t* c = ctx->d_bands.p + (K + 1);  // c[b] = cursor of band b's march, starts at e[b]
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    uint64_t launches = 0;
+    if (P0.mesh_scale > 0) { launch_mesh_raster(mesh, P0, P0.height, S.zbuf.p, ctx->stream); launches += 1; }
+    CK(cudaMemsetAsync(e, 0, sizeof(uint32_t), ctx->stream));
+    for (int b = 0; b < K; ++b) {
+        FrameParams P = P0;
+        P.shard_rank = b; P.shard_world = K; P.shard_band = band_rows;
+        const int rows = rows_owned_by(P.height, b, K, band_rows);
+        launch_init_rays(P, n.dev, mesh, S.zbuf.p, rows, S.queue.p, ctx->d_counters.p, out, ctx->num_sms, ctx->stream, b == 0);
+        launches += 1;
+        CK(cudaMemcpyAsync(e + b + 1, ctx->d_counters.p, sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    CK(cudaMemcpyAsync(c, e, sizeof(uint32_t) * K, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    for (int b = 0; b < K; ++b) {
+        launch_march(P0, n.dev, S.queue.p, ctx->d_counters.p, out, (uint32_t)P0.width * (uint32_t)P0.height, ctx->debug_flags, ctx->num_sms, ctx->stream, e + b + 1, c + b);
+        launches += 1;
+        CK(cudaEventRecord(ctx->ev_band[b], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_band[b], 0));
+        const int y0 = b * band_rows, y1 = std::min(P0.height, (b + 1) * band_rows);
+        if (y1 > y0) {
+            const size_t off = (size_t)y0 * P0.width;
+            CK(cudaMemcpyAsync(out_host + off * 4, S.image.p + off, (size_t)(y1 - y0) * P0.width * sizeof(float4), cudaMemcpyDeviceToHost, ctx->copy_stream));
+        }
+    }
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, sizeof(uint32_t) * kNumCounters, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->stats.rays = (uint64_t)P0.width * P0.height;
+    ctx->stats.mesh_rays = P0.mesh_scale > 0 ? (uint64_t)P0.width * P0.height * P0.mesh_scale * P0.mesh_scale : 0;
+    ctx->stats.kernel_launches = launches;
+    ctx->stats_pending = true;
+    CK(cudaGetLastError());
+}
+
 void finish_stats(nmr_ctx* ctx) {
     if (!ctx->stats_pending) return;
     CK(cudaStreamSynchronize(ctx->stream));
@@ -404,6 +460,7 @@ NMR_API int nmr_create(int width, int height, int device, nmr_ctx** out_ctx) {
         for (auto& ev : ctx->ev) CK(cudaEventCreate(&ev));
         CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         for (auto& pair : ctx->ev_view) for (auto& ev : pair) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        for (auto& ev : ctx->ev_band) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         ctx->d_counters.ensure(kNumCounters);
         ctx->d_scratch.ensure(64);
         CK(cudaHostAlloc((void**)&ctx->h_counters, sizeof(uint32_t) * kNumCounters, cudaHostAllocDefault));
@@ -426,6 +483,7 @@ NMR_API void nmr_destroy(nmr_ctx* ctx) {
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto& pair : ctx->ev_view) for (auto& ev : pair) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->ev_band) if (ev) cudaEventDestroy(ev);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -628,6 +686,15 @@ NMR_API int nmr_render(nmr_ctx* ctx, int nerf_id, int width, int height, int spp
         ctx->surf.spp = 0;   // reset_accumulation (S/python_api.cu:85)
         // Testbed::render uses Testbed::m_camera, which frame()/orbit keep equal to viewProjectionMat; its aspect comes from the
         // renderer's constructor resolution, not from (width, height), exactly like the reference.
+        if (spp == 1 && ctx->shard_world == 1 && height >= 256) {
+            // one sample per pixel: bands of rows are copied out while the next ones are still being marched
+            const FrameParams P = make_params(ctx, *n, width, height, ctx->cam12, 0, !linear, true);
+            enqueue_pass_banded(ctx, *n, P, out_rgba);
+            CK(cudaStreamSynchronize(ctx->copy_stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            ctx->surf.spp = 0;
+            return NMR_OK;
+        }
         for (int i = 0; i < spp; ++i) {
             const FrameParams P = make_params(ctx, *n, width, height, ctx->cam12, ctx->surf.spp, !linear, true);
             enqueue_pass(ctx, *n, P, i == spp - 1);

@@ -367,8 +367,8 @@ __global__ void __launch_bounds__(128) init_rays_kernel(FrameParams P, DeviceMod
 }
 
 void launch_init_rays(const FrameParams& P, const DeviceModel& M, const MeshDevice& mesh, const unsigned long long* d_zbuf, int rows_owned,
-                      float4* d_queue, uint32_t* d_counters, const FrameOut& out, int num_sms, cudaStream_t s) {
-    cudaMemsetAsync(d_counters, 0, sizeof(uint32_t) * kNumCounters, s);
+                      float4* d_queue, uint32_t* d_counters, const FrameOut& out, int num_sms, cudaStream_t s, bool reset_counters) {
+    if (reset_counters) cudaMemsetAsync(d_counters, 0, sizeof(uint32_t) * kNumCounters, s);
     (void)num_sms;
     if (rows_owned <= 0) return;
     dim3 grid((P.width + 15) / 16, (rows_owned + 7) / 8);
@@ -662,12 +662,15 @@ constexpr int kWalkBudget = 6;      // empty voxels a ray may skip per tile iter
 
 template <bool TC>
 __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? 3 : 2) march_kernel(FrameParams P, DeviceModel M, const float4* __restrict__ queue,
-                                                                                          uint32_t* __restrict__ counters, FrameOut out, uint32_t n_pixels, uint32_t debug_flags) {
+                                                                                          uint32_t* __restrict__ counters, FrameOut out, uint32_t n_pixels, uint32_t debug_flags, const uint32_t* __restrict__ range_end, uint32_t* __restrict__ cursor) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     using Smem = typename std::conditional<TC, MarchSmemTC, MarchSmem>::type;
     Smem& S = *reinterpret_cast<Smem*>(smem_raw);
 
-    const uint32_t n_rays = counters[0];
+    // this launch consumes the queue records [*cursor at launch, *range_end): the whole queue of a frame (range_end =
+    // &counters[0], cursor = &counters[1]) or one band of it (nmr_render's copy-overlapped bands); the surface rule always
+    // looks at the whole frame's live-ray count
+    const uint32_t n_rays = counters[0], n_end = *range_end;
     // mesh surface insertion rule (SurfaceMode): the reference's 8-sample batches while <= 1/8 of the pixels are live
     const bool batch8 = P.surface_mode == kSurfaceBatch8 || (P.surface_mode == kSurfaceAuto && (unsigned long long)n_rays * 8ull <= (unsigned long long)n_pixels);
     TcCtx tc;
@@ -768,9 +771,9 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? 3 : 2) ma
             if (!active) {
                 if (exhausted) break;
                 uint32_t slot = 0;
-                if (sub == 0) slot = atomicAdd(&counters[1], 1u);
+                if (sub == 0) slot = atomicAdd(cursor, 1u);
                 slot = __shfl_sync(gmask, slot, gbase);
-                if (slot >= n_rays) { exhausted = true; break; }
+                if (slot >= n_end) { exhausted = true; break; }
                 const float4 q0 = __ldg(queue + (size_t)slot * kRayRecordFloat4s), q1 = __ldg(queue + (size_t)slot * kRayRecordFloat4s + 1), q2 = __ldg(queue + (size_t)slot * kRayRecordFloat4s + 2);
                 dir = v3(q0.x, q0.y, q0.z); t = q0.w; t_start = q1.x; t_surface = q1.y; idx = __float_as_uint(q1.z); t_limit = q1.w;
                 sr = q2.x; sg = q2.y; sb = q2.z; sw = q2.w;
@@ -918,15 +921,17 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? 3 : 2) ma
 constexpr int kMarchCtasPerSm = 3;   // __launch_bounds__(256, 3): 24 warps, 3 x 128 tensor-memory columns, 3 x 53 KB shared memory per SM
 
 void launch_march(const FrameParams& P, const DeviceModel& M, const float4* d_queue, uint32_t* d_counters, const FrameOut& out,
-                  uint32_t n_pixels, uint32_t debug_flags, int num_sms, cudaStream_t s) {
+                  uint32_t n_pixels, uint32_t debug_flags, int num_sms, cudaStream_t s, const uint32_t* d_range_end, uint32_t* d_cursor) {
+    if (!d_range_end) d_range_end = d_counters;
+    if (!d_cursor) d_cursor = d_counters + 1;
     if (debug_flags & kDebugScalarMlp) {
         static bool attr_set = false;
         if (!attr_set) { cudaFuncSetAttribute(march_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmem)); attr_set = true; }
-        march_kernel<false><<<num_sms * 2, kTile, sizeof(MarchSmem), s>>>(P, M, d_queue, d_counters, out, n_pixels, debug_flags);
+        march_kernel<false><<<num_sms * 2, kTile, sizeof(MarchSmem), s>>>(P, M, d_queue, d_counters, out, n_pixels, debug_flags, d_range_end, d_cursor);
     } else {
         static bool attr_set = false;
         if (!attr_set) { cudaFuncSetAttribute(march_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmemTC)); attr_set = true; }
-        march_kernel<true><<<num_sms * kMarchCtasPerSm, kTile * kGroupsTC, sizeof(MarchSmemTC), s>>>(P, M, d_queue, d_counters, out, n_pixels, debug_flags);
+        march_kernel<true><<<num_sms * kMarchCtasPerSm, kTile * kGroupsTC, sizeof(MarchSmemTC), s>>>(P, M, d_queue, d_counters, out, n_pixels, debug_flags, d_range_end, d_cursor);
     }
 }
 

@@ -36,10 +36,11 @@ void launch_occupancy_build(const uint16_t* d_density_grid_fp16, int n_cascades_
 void launch_occupancy_bounds(const uint8_t* d_bitfield, int* d_out48, cudaStream_t s);
 void launch_mesh_raster(const MeshDevice& mesh, const FrameParams& P, int rows_owned, unsigned long long* d_zbuf, cudaStream_t s);
 void launch_init_rays(const FrameParams& P, const DeviceModel& M, const MeshDevice& mesh, const unsigned long long* d_zbuf, int rows_owned,
-                      float4* d_queue, uint32_t* d_counters, const FrameOut& out, int num_sms, cudaStream_t s);
+                      float4* d_queue, uint32_t* d_counters, const FrameOut& out, int num_sms, cudaStream_t s, bool reset_counters = true);
 // n_pixels: pixels traced by this context in this pass (the reference's m_n_rays_initialized), for SurfaceMode auto
 void launch_march(const FrameParams& P, const DeviceModel& M, const float4* d_queue, uint32_t* d_counters, const FrameOut& out,
-                  uint32_t n_pixels, uint32_t debug_flags, int num_sms, cudaStream_t s);
+                  uint32_t n_pixels, uint32_t debug_flags, int num_sms, cudaStream_t s, const uint32_t* d_range_end = nullptr, uint32_t* d_cursor = nullptr);
+// (d_range_end / d_cursor: consume only the queue records [*d_cursor, *d_range_end) - default: the whole queue)
 // parity probes
 void launch_debug_encode(const DeviceModel& M, const float* d_pos, int64_t n, uint16_t* d_out, cudaStream_t s);
 void launch_debug_network(const DeviceModel& M, const float* d_pos, const float* d_dir, int64_t n, uint16_t* d_out4, uint32_t debug_flags, cudaStream_t s);
