@@ -342,7 +342,7 @@ void enqueue_pass(nmr_ctx* ctx, Nerf& n, const FrameParams& P, bool timed) {
     if (!P.lens_on) mesh.tri_lens = nullptr;     // lenses off: their triangles are ordinary opaque surfaces
     else {
         S.lens.ensure((size_t)P.width * P.height * 2);
-        S.lens_scratch.ensure((size_t)ctx->num_sms * 3 * 32 * kLensStash);   // launch_march: num_sms x 3 CTAs x 32 ray groups
+        S.lens_scratch.ensure((size_t)ctx->num_sms * 4 * 32 * kLensStash);   // launch_march: num_sms x 3 CTAs x 32 ray groups
         out.lens = S.lens.p; out.lens_scratch = S.lens_scratch.p;
     }
     if (timed) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
@@ -378,7 +378,7 @@ void enqueue_pass_banded(nmr_ctx* ctx, Nerf& n, const FrameParams& P0, float* ou
     if (!P0.lens_on) mesh.tri_lens = nullptr;
     else {
         S.lens.ensure((size_t)P0.width * P0.height * 2);
-        S.lens_scratch.ensure((size_t)ctx->num_sms * 3 * 32 * kLensStash);
+        S.lens_scratch.ensure((size_t)ctx->num_sms * 4 * 32 * kLensStash);
         out.lens = S.lens.p; out.lens_scratch = S.lens_scratch.p;
     }
     ctx->d_bands.ensure(2 * (K + 1));

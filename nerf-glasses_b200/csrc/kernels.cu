@@ -655,13 +655,16 @@ __device__ __forceinline__ void tc_teardown(MarchSmemTC& S) {
 // =================================================================================================================
 constexpr int kRayLanes = 8;
 #ifndef NMR_ENCODE_UNROLL
-#define NMR_ENCODE_UNROLL 2
+#define NMR_ENCODE_UNROLL 1
 #endif
 constexpr int kEncodeUnroll = NMR_ENCODE_UNROLL;   // hash-grid levels in flight per thread (8 gathers each)
 constexpr int kWalkBudget = 6;      // empty voxels a ray may skip per tile iteration before it sits the iteration out
 
+#ifndef NMR_MARCH_CTAS
+#define NMR_MARCH_CTAS 3
+#endif
 template <bool TC>
-__global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? 3 : 2) march_kernel(FrameParams P, DeviceModel M, const float4* __restrict__ queue,
+__global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH_CTAS : 2) march_kernel(FrameParams P, DeviceModel M, const float4* __restrict__ queue,
                                                                                           uint32_t* __restrict__ counters, FrameOut out, uint32_t n_pixels, uint32_t debug_flags, const uint32_t* __restrict__ range_end, uint32_t* __restrict__ cursor) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     using Smem = typename std::conditional<TC, MarchSmemTC, MarchSmem>::type;
@@ -918,7 +921,7 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? 3 : 2) ma
     if (TC) tc_teardown(reinterpret_cast<MarchSmemTC&>(S));
 }
 
-constexpr int kMarchCtasPerSm = 3;   // __launch_bounds__(256, 3): 24 warps, 3 x 128 tensor-memory columns, 3 x 53 KB shared memory per SM
+constexpr int kMarchCtasPerSm = NMR_MARCH_CTAS;   // __launch_bounds__(256, 3): 24 warps, 3 x 128 tensor-memory columns, 3 x 53 KB shared memory per SM
 
 void launch_march(const FrameParams& P, const DeviceModel& M, const float4* d_queue, uint32_t* d_counters, const FrameOut& out,
                   uint32_t n_pixels, uint32_t debug_flags, int num_sms, cudaStream_t s, const uint32_t* d_range_end, uint32_t* d_cursor) {
