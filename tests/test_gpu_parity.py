@@ -227,3 +227,48 @@ def test_errors_are_reported_not_raised(scene, tmp_path):
     bad.write_bytes(b"\x81\xa1x\x01")
     assert r.load_nerf(str(bad)) is None
     assert r.load_mesh(str(tmp_path / "missing.gltf")) is None
+
+
+def test_render_py_call_sequence(small_snapshot, glasses_gltf):
+    """The calls volume/render.py makes, in its order and with its argument types (numpy arrays, keyword names), minus
+    MediaPipe / OpenCV / numpy-quaternion which are not in this image (V/render.py:62-66, 70-95, 122-186, 196-258)."""
+    import pynmr as nmr
+    import synth
+    path, _ = small_snapshot
+    Wr, Hr = 256, 144
+    renderer = nmr.NerfMeshRenderer(Wr, Hr)
+    renderer.envmap("sunflowers_puresky_1k.png")                       # render.py:228 (absent from the reference module)
+    nerf = renderer.load_nerf(path)
+    assert nerf is not None
+    before = np.asarray(nerf.render(Wr, Hr, linear=False)).copy()
+    nerf.render_aabb.min = np.array([-0.2, 0.15, -0.2])                # render.py:234-235
+    nerf.render_aabb.max = np.array([1, 1, 1])
+    assert np.allclose(np.asarray(nerf.render_aabb.min), [-0.2, 0.15, -0.2])
+    # rotate_camera_to_face_face / find_3d_landmarks: frame(), render_image(), orbit(), view_projection_mat
+    views = []
+    for i in range(3):
+        assert renderer.frame() is True
+        im = np.uint8(np.asarray(nerf.render(Wr, Hr, linear=False)) * 255)[::-1, :]       # render_image()
+        assert im.shape == (Hr, Wr, 4) and im.dtype == np.uint8
+        cam = renderer.view_projection_mat
+        assert cam.shape == (3, 4)
+        origin = np.squeeze(np.array(np.transpose(cam[:, 3])))         # class Ray
+        direction = np.squeeze(np.array(cam[0:3, 0:3].dot(np.array([0.1, -0.2, 1]))))
+        assert origin.shape == (3,) and direction.shape == (3,)
+        views.append(im)
+        renderer.orbit(0.1, 0, np.sin(i))
+    assert not np.array_equal(views[0], views[2])
+    # place_glasses: load_mesh with numpy t / s / r (w, x, y, z)
+    mesh = renderer.load_mesh(glasses_gltf, t=np.array(synth.GLASSES_T), s=np.array([0.17, 0.17, 0.17]), r=np.array(synth.GLASSES_R_WXYZ))
+    assert mesh is not None
+    renderer.remove_floaties()                                         # render.py:238 (commented out there, bound in the module)
+    a, shown = 0.0, []
+    for _ in range(4):                                                 # the orbit loop, render.py:252-254
+        assert renderer.frame()
+        a += 0.03
+        renderer.orbit(-(np.sin(a * 1.733)) / 100, np.cos(a * 1.733) / 200, 0)
+        shown.append(np.asarray(renderer.read_frame()).copy())
+    assert all(np.isfinite(s).all() for s in shown) and not np.array_equal(shown[0], shown[-1])
+    nmr.free_temporary_memory()
+    after = np.asarray(nerf.render(Wr, Hr, linear=False))
+    assert after.shape == before.shape == (Hr, Wr, 4)
