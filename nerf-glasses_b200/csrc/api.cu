@@ -72,6 +72,8 @@ struct Surfaces {
     DevBuf<unsigned long long> zbuf;       // opaque window, then (scenes with lens surfaces) the lens window
     DevBuf<float4> lens;                   // FrameOut::lens
     DevBuf<float> lens_scratch;            // FrameOut::lens_scratch
+    // the reference's n_steps schedule for close-ups (SchedArgs): death histogram, batch boundaries + their count, surface rays
+    DevBuf<uint32_t> hist, surf_list;
     uint32_t spp = 0;
     void resize(int W, int H, int mesh_scale) {
         const size_t n = (size_t)W * H;
@@ -331,6 +333,24 @@ FrameParams make_params(nmr_ctx* ctx, const Nerf& n, int W, int H, const float* 
     return P;
 }
 
+// Frames that can need the reference's per-iteration n_steps schedule: a mesh is in view and the surface rule is `auto`.
+// Returns false (and leaves `sa` zeroed) otherwise.  The histogram is cleared on the stream.
+bool prepare_schedule(nmr_ctx* ctx, const FrameParams& P, SchedArgs& sa) {
+    sa = SchedArgs{};
+    if (!(P.mesh_scale > 0 && P.zb_w > 0 && P.surface_mode == kSurfaceAuto)) return false;
+    Surfaces& S = ctx->surf;
+    S.hist.ensure(kSchedBins); S.surf_list.ensure((size_t)P.width * P.height);
+    CK(cudaMemsetAsync(S.hist.p, 0, sizeof(uint32_t) * kSchedBins, ctx->stream));
+    sa.hist = S.hist.p; sa.surf_list = S.surf_list.p; sa.pass = 1;
+    return true;
+}
+// second pass over the rays that carry a mesh surface (exits at once unless more than 1/8 of the pixels were live)
+void enqueue_surface_pass(nmr_ctx* ctx, Nerf& n, const FrameParams& P, const FrameOut& out, uint32_t n_pixels, SchedArgs sa) {
+    Surfaces& S = ctx->surf;
+    sa.pass = 2;
+    launch_march(P, n.dev, S.queue.p, ctx->d_counters.p, out, n_pixels, ctx->debug_flags, ctx->num_sms, ctx->stream, ctx->d_counters.p + 7, ctx->d_counters.p + 6, &sa, 1);
+}
+
 // one sample-per-pixel pass: mesh stage -> init -> march.  Enqueues only; no host synchronisation.
 void enqueue_pass(nmr_ctx* ctx, Nerf& n, const FrameParams& P, bool timed) {
     Surfaces& S = ctx->surf;
@@ -347,12 +367,16 @@ void enqueue_pass(nmr_ctx* ctx, Nerf& n, const FrameParams& P, bool timed) {
     }
     if (timed) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     uint64_t launches = 0;
+    SchedArgs sa;
+    const bool sched = prepare_schedule(ctx, P, sa);
     if (P.mesh_scale > 0) { launch_mesh_raster(mesh, P, rows, S.zbuf.p, ctx->stream); launches += 1; }
-    launch_init_rays(P, n.dev, mesh, S.zbuf.p, rows, S.queue.p, ctx->d_counters.p, out, ctx->num_sms, ctx->stream);
+    launch_init_rays(P, n.dev, mesh, S.zbuf.p, rows, S.queue.p, ctx->d_counters.p, out, ctx->num_sms, ctx->stream, true, sched ? S.surf_list.p : nullptr);
     launches += 1;
     if (timed) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-    launch_march(P, n.dev, S.queue.p, ctx->d_counters.p, out, (uint32_t)P.width * (uint32_t)rows, ctx->debug_flags, ctx->num_sms, ctx->stream);
+    const uint32_t n_pixels = (uint32_t)P.width * (uint32_t)rows;
+    launch_march(P, n.dev, S.queue.p, ctx->d_counters.p, out, n_pixels, ctx->debug_flags, ctx->num_sms, ctx->stream, nullptr, nullptr, sched ? &sa : nullptr);
     launches += 1;
+    if (sched) { enqueue_surface_pass(ctx, n, P, out, n_pixels, sa); launches += 1; }
     if (timed) {
         CK(cudaEventRecord(ctx->ev[2], ctx->stream));
         CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, sizeof(uint32_t) * kNumCounters, cudaMemcpyDeviceToHost, ctx->stream));
@@ -386,28 +410,45 @@ void enqueue_pass_banded(nmr_ctx* ctx, Nerf& n, const FrameParams& P0, float* ou
     uint32_t* c = ctx->d_bands.p + (K + 1);  // c[b] = cursor of band b's march, starts at e[b]
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     uint64_t launches = 0;
+    SchedArgs sa;
+    const bool sched = prepare_schedule(ctx, P0, sa);
     if (P0.mesh_scale > 0) { launch_mesh_raster(mesh, P0, P0.height, S.zbuf.p, ctx->stream); launches += 1; }
     CK(cudaMemsetAsync(e, 0, sizeof(uint32_t), ctx->stream));
     for (int b = 0; b < K; ++b) {
         FrameParams P = P0;
         P.shard_rank = b; P.shard_world = K; P.shard_band = band_rows;
         const int rows = rows_owned_by(P.height, b, K, band_rows);
-        launch_init_rays(P, n.dev, mesh, S.zbuf.p, rows, S.queue.p, ctx->d_counters.p, out, ctx->num_sms, ctx->stream, b == 0);
+        launch_init_rays(P, n.dev, mesh, S.zbuf.p, rows, S.queue.p, ctx->d_counters.p, out, ctx->num_sms, ctx->stream, b == 0, sched ? S.surf_list.p : nullptr);
         launches += 1;
         CK(cudaMemcpyAsync(e + b + 1, ctx->d_counters.p, sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
     }
     CK(cudaMemcpyAsync(c, e, sizeof(uint32_t) * K, cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    const uint32_t n_pixels = (uint32_t)P0.width * (uint32_t)P0.height;
+    // rows that can show the mesh: their pixels are final only after the surface-ray pass
+    const int my0 = sched ? P0.zb_y0 / P0.mesh_scale : 0, my1 = sched ? (P0.zb_y0 + P0.zb_h + P0.mesh_scale - 1) / P0.mesh_scale : 0;
+    auto copy_band = [&](int b) {
+        const int y0 = b * band_rows, y1 = std::min(P0.height, (b + 1) * band_rows);
+        if (y1 <= y0) return;
+        const size_t off = (size_t)y0 * P0.width;
+        CK(cudaMemcpyAsync(out_host + off * 4, S.image.p + off, (size_t)(y1 - y0) * P0.width * sizeof(float4), cudaMemcpyDeviceToHost, ctx->copy_stream));
+    };
+    bool deferred[K] = {};
     for (int b = 0; b < K; ++b) {
-        launch_march(P0, n.dev, S.queue.p, ctx->d_counters.p, out, (uint32_t)P0.width * (uint32_t)P0.height, ctx->debug_flags, ctx->num_sms, ctx->stream, e + b + 1, c + b);
+        launch_march(P0, n.dev, S.queue.p, ctx->d_counters.p, out, n_pixels, ctx->debug_flags, ctx->num_sms, ctx->stream, e + b + 1, c + b, sched ? &sa : nullptr);
         launches += 1;
+        const int y0 = b * band_rows, y1 = std::min(P0.height, (b + 1) * band_rows);
+        deferred[b] = sched && y0 < my1 && y1 > my0;
+        if (deferred[b]) continue;
         CK(cudaEventRecord(ctx->ev_band[b], ctx->stream));
         CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_band[b], 0));
-        const int y0 = b * band_rows, y1 = std::min(P0.height, (b + 1) * band_rows);
-        if (y1 > y0) {
-            const size_t off = (size_t)y0 * P0.width;
-            CK(cudaMemcpyAsync(out_host + off * 4, S.image.p + off, (size_t)(y1 - y0) * P0.width * sizeof(float4), cudaMemcpyDeviceToHost, ctx->copy_stream));
-        }
+        copy_band(b);
+    }
+    if (sched) {
+        enqueue_surface_pass(ctx, n, P0, out, n_pixels, sa); launches += 1;
+        CK(cudaEventRecord(ctx->ev_band[K], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_band[K], 0));
+        for (int b = 0; b < K; ++b) if (deferred[b]) copy_band(b);
     }
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, sizeof(uint32_t) * kNumCounters, cudaMemcpyDeviceToHost, ctx->stream));

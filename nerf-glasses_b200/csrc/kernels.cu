@@ -297,7 +297,7 @@ __device__ __forceinline__ void finish_pixel(const FrameParams& P, const FrameOu
 // (S/ngp/testbed.cu:355-537; S/nerf_mesh_renderer.cu:64-100)
 // =================================================================================================================
 __device__ __forceinline__ void init_one_ray(const FrameParams& P, const DeviceModel& M, const MeshDevice& mesh, const unsigned long long* __restrict__ zbuf,
-                                             float4* __restrict__ queue, uint32_t* __restrict__ counters, const FrameOut& out, int x, int y) {
+                                             float4* __restrict__ queue, uint32_t* __restrict__ counters, const FrameOut& out, int x, int y, uint32_t* __restrict__ surf_list) {
     const uint32_t idx = (uint32_t)x + (uint32_t)P.width * (uint32_t)y;
 
     float surf[4] = {0.f, 0.f, 0.f, 0.f};
@@ -348,7 +348,9 @@ __device__ __forceinline__ void init_one_ray(const FrameParams& P, const DeviceM
     }
     const uint32_t slot = atomicAdd(&counters[0], 1u);
     queue[(size_t)slot * kRayRecordFloat4s + 0] = make_float4(r.dir.x, r.dir.y, r.dir.z, t);
-    queue[(size_t)slot * kRayRecordFloat4s + 1] = make_float4(t_start, t_surface, __uint_as_float(idx | (L.w > 0.f ? kLensRayFlag : 0u)), r.t_limit);
+    const bool carries_surface = L.w == 0.f && t_surface != 0.0f && surf[3] > 0.f;
+    if (carries_surface && surf_list) surf_list[atomicAdd(&counters[7], 1u)] = slot;
+    queue[(size_t)slot * kRayRecordFloat4s + 1] = make_float4(t_start, t_surface, __uint_as_float(idx | (L.w > 0.f ? kLensRayFlag : 0u) | (carries_surface ? kSurfRayFlag : 0u)), r.t_limit);
     queue[(size_t)slot * kRayRecordFloat4s + 2] = make_float4(surf[0], surf[1], surf[2], surf[3]);
     if (L.w > 0.f) {
         out.lens[(size_t)idx * 2] = make_float4(L.n.x, L.n.y, L.n.z, L.t);
@@ -357,22 +359,22 @@ __device__ __forceinline__ void init_one_ray(const FrameParams& P, const DeviceM
 }
 
 __global__ void __launch_bounds__(128) init_rays_kernel(FrameParams P, DeviceModel M, MeshDevice mesh, const unsigned long long* __restrict__ zbuf, int rows_owned,
-                                                        float4* __restrict__ queue, uint32_t* __restrict__ counters, FrameOut out) {
+                                                        float4* __restrict__ queue, uint32_t* __restrict__ counters, FrameOut out, uint32_t* __restrict__ surf_list) {
     // 16 x 8 pixel block, each warp an 8 x 4 tile so queue neighbours are screen neighbours
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
     const int ly = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
     if (x >= P.width || ly >= rows_owned) return;
-    init_one_ray(P, M, mesh, zbuf, queue, counters, out, x, shard_row(P, ly));
+    init_one_ray(P, M, mesh, zbuf, queue, counters, out, x, shard_row(P, ly), surf_list);
 }
 
 void launch_init_rays(const FrameParams& P, const DeviceModel& M, const MeshDevice& mesh, const unsigned long long* d_zbuf, int rows_owned,
-                      float4* d_queue, uint32_t* d_counters, const FrameOut& out, int num_sms, cudaStream_t s, bool reset_counters) {
+                      float4* d_queue, uint32_t* d_counters, const FrameOut& out, int num_sms, cudaStream_t s, bool reset_counters, uint32_t* d_surf_list) {
     if (reset_counters) cudaMemsetAsync(d_counters, 0, sizeof(uint32_t) * kNumCounters, s);
     (void)num_sms;
     if (rows_owned <= 0) return;
     dim3 grid((P.width + 15) / 16, (rows_owned + 7) / 8);
-    init_rays_kernel<<<grid, 128, 0, s>>>(P, M, mesh, d_zbuf, rows_owned, d_queue, d_counters, out);
+    init_rays_kernel<<<grid, 128, 0, s>>>(P, M, mesh, d_zbuf, rows_owned, d_queue, d_counters, out, d_surf_list);
 }
 
 // =================================================================================================================
@@ -663,9 +665,11 @@ constexpr int kWalkBudget = 6;      // empty voxels a ray may skip per tile iter
 #ifndef NMR_MARCH_CTAS
 #define NMR_MARCH_CTAS 3
 #endif
-template <bool TC>
+// PASS2: the surface-ray pass of SchedArgs (variable batch sizes from the schedule); the main instantiation keeps the batch
+// size a compile-time 8
+template <bool TC, bool PASS2>
 __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH_CTAS : 2) march_kernel(FrameParams P, DeviceModel M, const float4* __restrict__ queue,
-                                                                                          uint32_t* __restrict__ counters, FrameOut out, uint32_t n_pixels, uint32_t debug_flags, const uint32_t* __restrict__ range_end, uint32_t* __restrict__ cursor) {
+                                                                                          uint32_t* __restrict__ counters, FrameOut out, uint32_t n_pixels, uint32_t debug_flags, const uint32_t* __restrict__ range_end, uint32_t* __restrict__ cursor, SchedArgs sched) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     using Smem = typename std::conditional<TC, MarchSmemTC, MarchSmem>::type;
     Smem& S = *reinterpret_cast<Smem*>(smem_raw);
@@ -676,6 +680,35 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH
     const uint32_t n_rays = counters[0], n_end = *range_end;
     // mesh surface insertion rule (SurfaceMode): the reference's 8-sample batches while <= 1/8 of the pixels are live
     const bool batch8 = P.surface_mode == kSurfaceBatch8 || (P.surface_mode == kSurfaceAuto && (unsigned long long)n_rays * 8ull <= (unsigned long long)n_pixels);
+    // more than 1/8 live pixels under the auto rule: the reference's batch size varies per wavefront iteration (SchedArgs)
+    const bool two_pass = sched.pass != 0 && !batch8 && P.surface_mode == kSurfaceAuto;
+    constexpr bool pass2 = PASS2;
+    if (pass2 && (!two_pass || counters[7] == 0u)) return;            // nothing to redo (whole grid, before any barrier)
+    // The reference's wavefront loop (S/ngp/testbed.cu:1973-2047) replayed over the death histogram of pass 1: iteration k offers
+    // n_k = clamp(pixels / live rays, 1, 8) samples to every live ray; a ray whose death index lies in [s_k, s_k + n_k) is
+    // gone afterwards.  Every CTA of the surface-ray pass builds the boundaries s_0 .. s_K for itself (one thread, at most
+    // ~1800 short iterations; close-ups only).
+    uint16_t* sched_s = reinterpret_cast<uint16_t*>(smem_raw + sizeof(Smem));
+    uint32_t sched_len = 0u;
+    if (pass2) {
+        uint32_t* len_s = reinterpret_cast<uint32_t*>(sched_s + kSchedMax + 2);
+        if (threadIdx.x == 0) {
+            uint32_t alive = n_rays, s = 0, k = 0;
+            while (alive > 0u && k + 1u < kSchedMax && s < kSchedBins + 8u) {
+                const uint32_t q = n_pixels / alive, n = q < 1u ? 1u : (q > 8u ? 8u : q);
+                sched_s[k++] = (uint16_t)s;
+                uint32_t dead = 0;
+                for (uint32_t i = 0; i < n; ++i) dead += __ldg(sched.hist + min(s + i, kSchedBins - 1u));
+                alive -= min(dead, alive);
+                s += n;
+            }
+            sched_s[k] = (uint16_t)s;
+            *len_s = k;
+        }
+        __syncthreads();
+        sched_len = *len_s;
+    }
+    const bool batch_rule = batch8 || pass2;
     TcCtx tc;
     char* a_row;
     int enc_stride;
@@ -704,6 +737,8 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH
     bool active = false, exhausted = false, pending_finish = false;
     V3 origin = cam_origin;      // primary rays start at the eye; the reflected segment of a lens ray starts on the lens
     uint32_t phase = 0;          // 0 ordinary ray; lens ray: 1 in front of the lens, 2 reflected segment, 3 behind the lens
+    uint32_t kb = 0;             // surface-ray pass: schedule batch index of the ray's current batch
+    bool sat = false;            // the ray's last batch ended on the opacity threshold
     V3 dir = v3(0.f, 0.f, 1.f);
     float t = 0.f, t_start = 0.f, t_surface = 0.f, t_limit = 0.f, max_weight = 0.f, depth = 0.f;
     float sr = 0.f, sg = 0.f, sb = 0.f, sw = 0.f;        // surface colour (mesh hand-off)
@@ -714,7 +749,7 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH
         // ---- 1. next batch of up to 8 samples for this group's ray, pulling a new ray when the current one has ended ----
         V3 my_pos = v3(0.f, 0.f, 0.f);
         float my_dtw = 0.f, my_t_after = 0.f, t_batch_end = t;
-        uint32_t n_valid = 0;
+        uint32_t n_valid = 0, batch_cap = kRayLanes;
         bool paused = false, ended = false;
         while (true) {
             if (pending_finish) {
@@ -768,7 +803,13 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH
                     ca = stash[3] + Tf * (wl * (F + (1.f - F) * ((1.f - P.lens_kmean) + P.lens_kmean * a_behind)) + (1.f - wl) * a_behind);
                     phase = 0u;
                 }
-                if (sub == 0) finish_pixel(P, out, idx, cr, cg, cb, ca, depth, n_samples);
+                if (two_pass && !pass2) {
+                    // first of two passes: record where this ray dies in the reference's wavefront (sample index of the batch
+                    // that kills it); rays that carry a mesh surface are composited again by the second pass
+                    if (sub == 0) atomicAdd(sched.hist + min(sat ? n_samples - 1u : n_samples, kSchedBins - 1u), 1u);
+                    if (idx & kSurfRayFlag) { active = false; continue; }
+                }
+                if (sub == 0) finish_pixel(P, out, idx & ~kSurfRayFlag, cr, cg, cb, ca, depth, n_samples);
                 active = false;
             }
             if (!active) {
@@ -777,12 +818,13 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH
                 if (sub == 0) slot = atomicAdd(cursor, 1u);
                 slot = __shfl_sync(gmask, slot, gbase);
                 if (slot >= n_end) { exhausted = true; break; }
+                if (pass2) slot = __ldg(sched.surf_list + slot);
                 const float4 q0 = __ldg(queue + (size_t)slot * kRayRecordFloat4s), q1 = __ldg(queue + (size_t)slot * kRayRecordFloat4s + 1), q2 = __ldg(queue + (size_t)slot * kRayRecordFloat4s + 2);
                 dir = v3(q0.x, q0.y, q0.z); t = q0.w; t_start = q1.x; t_surface = q1.y; idx = __float_as_uint(q1.z); t_limit = q1.w;
                 sr = q2.x; sg = q2.y; sb = q2.z; sw = q2.w;
                 cr = cg = cb = ca = 0.f; max_weight = 0.f; depth = 0.f; n_samples = 0;
                 active = true;
-                phase = 0u;
+                phase = 0u; kb = 0u; sat = false;
                 if (idx & kLensRayFlag) {
                     // lens ray, first segment: samples up to the lens only, the opaque mesh surface waits behind it
                     idx &= ~kLensRayFlag;
@@ -802,12 +844,15 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH
             float tt = t;
             n_valid = 0;
             paused = false; ended = false;
+            uint32_t cap = kRayLanes;
+            if (pass2 && sw > 0.f && kb < sched_len) cap = (uint32_t)sched_s[kb + 1] - (uint32_t)sched_s[kb];   // the reference's n_steps of this iteration
+            batch_cap = cap;
 #pragma unroll 1
-            while (n_valid < (uint32_t)kRayLanes) {
+            while (n_valid < cap) {
                 ++n_passes;
                 float tc = tt, dtc = 0.f;
                 V3 pc = v3(0.f, 0.f, 0.f);
-                bool ok = sub >= n_valid;
+                bool ok = sub >= n_valid && sub < cap;
                 if (ok) {
                     for (uint32_t k = n_valid; k < sub; ++k) tc += calc_dt(tc - t_start, P.cone_angle);
                     ok = !(t_surface != 0.0f && tc > t_surface && sw == 1.f) && !(tc > t_limit);
@@ -830,13 +875,13 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH
                     tt = __shfl_sync(gmask, tc + dtc, gbase + first_fail - 1);
                     n_valid = first_fail;
                 }
-                if (n_valid >= (uint32_t)kRayLanes) break;
+                if (n_valid >= cap) break;
                 // sample number n_valid needs the general rule (empty-space skip, box exit or opaque mesh surface).  A long walk
                 // through empty cells is cut into slices of kWalkBudget voxels so that one ray cannot stall its tile: a paused
                 // walk keeps its state in t and resumes in the next iteration.
                 Sample smp;
                 // (a ray that still carries a mesh surface under the batch rule never pauses: its batches must stay aligned to 8 samples)
-                const int rc = next_sample(P, M.bitfield, origin, dir, idir, t_start, t_surface, sw, t_limit, false, (batch8 && sw > 0.f) ? 0x7fffffff : kWalkBudget, tt, smp);
+                const int rc = next_sample(P, M.bitfield, origin, dir, idir, t_start, t_surface, sw, t_limit, false, (batch_rule && sw > 0.f) ? 0x7fffffff : kWalkBudget, tt, smp);
                 if (rc != 1) { paused = rc == 2; ended = rc == 0; break; }
                 if (sub == n_valid) { my_pos = smp.pos; my_dtw = smp.dt_warped; my_t_after = tt; }
                 ++n_valid;
@@ -883,7 +928,7 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH
         if (active && !pending_finish) {
             bool done = false;
             // reference rule: the batch's end (payload.t after generate_next_nerf_network_inputs) decides, before its first sample
-            const bool pre_blend = batch8 && sw > 0.f && n_valid == (uint32_t)kRayLanes && t_batch_end > t_surface;
+            const bool pre_blend = batch_rule && sw > 0.f && n_valid == (pass2 ? batch_cap : (uint32_t)kRayLanes) && t_batch_end > t_surface;
 #pragma unroll 1
             for (uint32_t j = 0; j < n_valid; ++j) {
                 const uint32_t src = gbase + j;
@@ -892,7 +937,7 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH
                 ++n_samples;
                 float T = 1.f - ca;
                 if (sw > 0.f) {        // same in all lanes of the group
-                    const bool insert = batch8 ? (j == 0 && pre_blend) : (__shfl_sync(gmask, my_t_after, src) > t_surface);
+                    const bool insert = batch_rule ? (j == 0 && pre_blend) : (__shfl_sync(gmask, my_t_after, src) > t_surface);
                     if (insert) {
                         cr += sr * sw * T; cg += sg * sw * T; cb += sb * sw * T; ca += sw * T;
                         sw = 0.f;
@@ -909,6 +954,7 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH
             // a batch that came back short because the walk ended (box exit, opaque mesh surface) is the ray's last one: the
             // reference kills the ray when it produced fewer than n_steps samples (S/ngp/testbed.cu:886-901)
             if (done && phase == 1u) phase = 0u;      // saturated in front of the lens: an ordinary ray after all
+            sat = done; if (pass2) ++kb;
             if (done || ended) pending_finish = true;
             t = t_batch_end;           // the walk's state: resume point of a paused empty-space walk or of a lens ray's next segment
         }
@@ -921,20 +967,27 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH
     if (TC) tc_teardown(reinterpret_cast<MarchSmemTC&>(S));
 }
 
+constexpr size_t kSchedSmem = (kSchedMax + 2) * sizeof(uint16_t) + 16;   // schedule boundaries + their count behind the surface-ray pass's tile memory
 constexpr int kMarchCtasPerSm = NMR_MARCH_CTAS;   // __launch_bounds__(256, 3): 24 warps, 3 x 128 tensor-memory columns, 3 x 53 KB shared memory per SM
 
 void launch_march(const FrameParams& P, const DeviceModel& M, const float4* d_queue, uint32_t* d_counters, const FrameOut& out,
-                  uint32_t n_pixels, uint32_t debug_flags, int num_sms, cudaStream_t s, const uint32_t* d_range_end, uint32_t* d_cursor) {
+                  uint32_t n_pixels, uint32_t debug_flags, int num_sms, cudaStream_t s, const uint32_t* d_range_end, uint32_t* d_cursor,
+                  const SchedArgs* sched, int ctas_per_sm) {
     if (!d_range_end) d_range_end = d_counters;
     if (!d_cursor) d_cursor = d_counters + 1;
+    SchedArgs sa{};
+    if (sched) sa = *sched;
+    const int per_sm = ctas_per_sm > 0 ? ctas_per_sm : kMarchCtasPerSm;
     if (debug_flags & kDebugScalarMlp) {
         static bool attr_set = false;
-        if (!attr_set) { cudaFuncSetAttribute(march_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmem)); attr_set = true; }
-        march_kernel<false><<<num_sms * 2, kTile, sizeof(MarchSmem), s>>>(P, M, d_queue, d_counters, out, n_pixels, debug_flags, d_range_end, d_cursor);
+        if (!attr_set) { cudaFuncSetAttribute(march_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmem)); cudaFuncSetAttribute(march_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(MarchSmem) + kSchedSmem)); attr_set = true; }
+        if (sa.pass == 2) march_kernel<false, true><<<num_sms, kTile, sizeof(MarchSmem) + kSchedSmem, s>>>(P, M, d_queue, d_counters, out, n_pixels, debug_flags, d_range_end, d_cursor, sa);
+        else march_kernel<false, false><<<num_sms * 2, kTile, sizeof(MarchSmem), s>>>(P, M, d_queue, d_counters, out, n_pixels, debug_flags, d_range_end, d_cursor, sa);
     } else {
         static bool attr_set = false;
-        if (!attr_set) { cudaFuncSetAttribute(march_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmemTC)); attr_set = true; }
-        march_kernel<true><<<num_sms * kMarchCtasPerSm, kTile * kGroupsTC, sizeof(MarchSmemTC), s>>>(P, M, d_queue, d_counters, out, n_pixels, debug_flags, d_range_end, d_cursor);
+        if (!attr_set) { cudaFuncSetAttribute(march_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmemTC)); cudaFuncSetAttribute(march_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(MarchSmemTC) + kSchedSmem)); attr_set = true; }
+        if (sa.pass == 2) march_kernel<true, true><<<num_sms * per_sm, kTile * kGroupsTC, sizeof(MarchSmemTC) + kSchedSmem, s>>>(P, M, d_queue, d_counters, out, n_pixels, debug_flags, d_range_end, d_cursor, sa);
+        else march_kernel<true, false><<<num_sms * per_sm, kTile * kGroupsTC, sizeof(MarchSmemTC), s>>>(P, M, d_queue, d_counters, out, n_pixels, debug_flags, d_range_end, d_cursor, sa);
     }
 }
 

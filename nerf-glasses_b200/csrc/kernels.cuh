@@ -17,11 +17,22 @@ struct FrameOut {
     float4* lens;         // lens hand-off per pixel, 2 x W*H: (normal.xyz, t_lens) (coverage, -, -, -); null when the frame has no lens
     float* lens_scratch;  // per ray group of the march kernel: state parked across the segments of a lens ray (kLensStash floats each)
 };
+// The reference's n_steps schedule for frames with MORE than 1/8 live pixels (SurfaceMode auto): pass 1 marches every ray and
+// histograms the sample index at which each ray dies; pass 2 replays clamp(pixels / live rays, 1, 8) per wavefront iteration
+// over that histogram and re-marches the rays that carry a mesh surface with those batch sizes.
+struct SchedArgs {
+    uint32_t* hist;             // [kSchedBins] death histogram (pass 1 adds, pass 2 reads); null: no schedule machinery
+    const uint32_t* surf_list;  // queue slots of the rays that carry a mesh surface (pass 2 consumes these)
+    int pass;                   // 0: plain single pass, 1: first pass of a possible two, 2: surface-ray pass
+};
+constexpr uint32_t kSchedBins = 2048, kSchedMax = 2048;
+constexpr uint32_t kSurfRayFlag = 0x40000000u;   // bit 30 of the pixel index in a ray record: the ray carries a mesh surface
 constexpr uint32_t kLensRayFlag = 0x80000000u;   // bit 31 of the pixel index in a ray record: the pixel has a lens hand-off entry
 constexpr int kLensStash = 24;
 
 // device counters of one render: [0] rays queued by the init kernel, [1] queue cursor of the march kernel,
-// [2..3] total network evaluations (64-bit), [4] ray batches, [5] batch generation passes, [6] tile cursor of the init kernel
+// [2..3] total network evaluations (64-bit), [4] ray batches, [5] batch generation passes, [6] cursor of the surface-ray pass,
+// [7] rays that carry a mesh surface (length of the surface list)
 constexpr int kNumCounters = 8;
 constexpr int kRayRecordFloat4s = 3;   // queue record: (dir.xyz, t) (t_start, t_surface, idx, -) (surface rgba)
 
@@ -36,10 +47,11 @@ void launch_occupancy_build(const uint16_t* d_density_grid_fp16, int n_cascades_
 void launch_occupancy_bounds(const uint8_t* d_bitfield, int* d_out48, cudaStream_t s);
 void launch_mesh_raster(const MeshDevice& mesh, const FrameParams& P, int rows_owned, unsigned long long* d_zbuf, cudaStream_t s);
 void launch_init_rays(const FrameParams& P, const DeviceModel& M, const MeshDevice& mesh, const unsigned long long* d_zbuf, int rows_owned,
-                      float4* d_queue, uint32_t* d_counters, const FrameOut& out, int num_sms, cudaStream_t s, bool reset_counters = true);
+                      float4* d_queue, uint32_t* d_counters, const FrameOut& out, int num_sms, cudaStream_t s, bool reset_counters = true, uint32_t* d_surf_list = nullptr);
 // n_pixels: pixels traced by this context in this pass (the reference's m_n_rays_initialized), for SurfaceMode auto
 void launch_march(const FrameParams& P, const DeviceModel& M, const float4* d_queue, uint32_t* d_counters, const FrameOut& out,
-                  uint32_t n_pixels, uint32_t debug_flags, int num_sms, cudaStream_t s, const uint32_t* d_range_end = nullptr, uint32_t* d_cursor = nullptr);
+                  uint32_t n_pixels, uint32_t debug_flags, int num_sms, cudaStream_t s, const uint32_t* d_range_end = nullptr, uint32_t* d_cursor = nullptr,
+                  const SchedArgs* sched = nullptr, int ctas_per_sm = 0);
 // (d_range_end / d_cursor: consume only the queue records [*d_cursor, *d_range_end) - default: the whole queue)
 // parity probes
 void launch_debug_encode(const DeviceModel& M, const float* d_pos, int64_t n, uint16_t* d_out, cudaStream_t s);

@@ -152,10 +152,12 @@ def test_render_hybrid_pixels(scene):
 
 
 def test_render_hybrid_pixels_close_up(scene):
-    """More than 1/8 of the pixels live: NMR_SURFACE_AUTO inserts the surface at its exact sample (oracle n_steps_mode 0)."""
+    """More than 1/8 of the pixels live: the reference's n_steps = clamp(pixels / live rays, 1, 8) varies from wavefront
+    iteration to iteration.  NMR_SURFACE_AUTO replays that schedule (death histogram of a first pass -> schedule_kernel ->
+    second pass over the rays that carry a mesh surface); the oracle's n_steps_mode 1 is the reference's loop itself."""
     import pynmr
     snap, g = scene["snap"], scene["glasses"]
-    w, h = 96, 54
+    w, h = 160, 90
     r = pynmr.NerfMeshRenderer(w, h)
     nerf = r.load_nerf(scene["path"])
     assert r.load_mesh(g["path"], t=g["t"], s=g["s"], r=g["r"]) is not None
@@ -163,10 +165,26 @@ def test_render_hybrid_pixels_close_up(scene):
     m = r.view_projection_mat
     m[:, 3] += 0.5 * m[:, 2]
     r.view_projection_mat = m
-    want, _, _, stats, _ = H.oracle_scene(snap, w, h, cam12(r), glasses=g, n_steps_mode=0)
+    want, _, _, stats, _ = H.oracle_scene(snap, w, h, cam12(r), glasses=g, n_steps_mode=1)
+    want_exact = H.oracle_scene(snap, w, h, cam12(r), glasses=g, n_steps_mode=0)[0]
     assert stats["alive_after_first_hit"] * 8 > w * h
-    img = np.asarray(nerf.render(w, h, 1, linear=False))
+    assert np.max(np.abs(want - want_exact)) > 10 * PIX_TOL          # the schedule is visible in this frame
+    img = np.asarray(nerf.render(w, h, 1, linear=False)).copy()
     assert np.max(np.abs(img - want)) <= PIX_TOL
+    assert H.psnr(img, want) >= 45.0
+    r.set_surface_insertion(pynmr.NerfMeshRenderer.SURFACE_EXACT)
+    img = np.asarray(nerf.render(w, h, 1, linear=False)).copy()
+    assert np.max(np.abs(img - want_exact)) <= PIX_TOL
+    # same frame through the copy-overlapped band path of render() (height >= 256) and through frame()
+    r2 = pynmr.NerfMeshRenderer(480, 270)
+    nerf2 = r2.load_nerf(scene["path"])
+    assert r2.load_mesh(g["path"], t=g["t"], s=g["s"], r=g["r"]) is not None
+    r2.view_projection_mat = m
+    a = np.asarray(nerf2.render(480, 270, 1, linear=False)).copy()
+    assert r2.frame()
+    b = np.asarray(r2.read_frame())
+    assert r2.stats()["rays_alive"] * 8 > 480 * 270
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 
 def test_accumulation_and_linear_output(scene):
