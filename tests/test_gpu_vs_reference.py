@@ -31,7 +31,7 @@ def pair(small_snapshot, glasses_gltf):
     r.orbit(0.35, -0.2, 4.0)
     cam12 = np.ascontiguousarray(r.view_projection_mat.T.reshape(-1))
     g = {"path": glasses_gltf, "t": synth.GLASSES_T, "s": synth.GLASSES_S, "r": synth.GLASSES_R_WXYZ}
-    yield {"ref": ref, "r": r, "nerf": nerf, "snap": snap, "cam12": cam12, "glasses": g}
+    yield {"ref": ref, "r": r, "nerf": nerf, "snap": snap, "path": path, "cam12": cam12, "glasses": g}
     ref.close()
 
 
@@ -118,3 +118,30 @@ def test_hybrid_pixels_vs_reference(pair):
     mx, ps, frac = _cmp(got, want)
     assert ps >= 45.0, ps
     assert frac <= 0.004, (mx, frac)
+
+
+def test_hybrid_close_up_vs_reference(pair):
+    """More than 1/8 of the pixels live: the reference's n_steps varies per wavefront iteration, which moves the point where
+    the glasses enter the compositing order; NMR_SURFACE_AUTO replays that schedule."""
+    import pynmr
+    g = pair["glasses"]
+    w, h = 320, 180
+    r = pynmr.NerfMeshRenderer(w, h)
+    nerf = r.load_nerf(pair["path"])
+    assert r.load_mesh(g["path"], t=g["t"], s=g["s"], r=g["r"]) is not None
+    r.orbit(0.2, -0.1, 9.0)
+    m = r.view_projection_mat
+    m[:, 3] += 0.5 * m[:, 2]
+    r.view_projection_mat = m
+    c12 = np.ascontiguousarray(r.view_projection_mat.T.reshape(-1))
+    _, _, _, surf, ts = H.debug_mesh(r, w, h)
+    want, _ = pair["ref"].render(c12, w, h, 1, False, surf=surf, ts=ts)
+    got = np.asarray(nerf.render(w, h, 1, linear=False)).copy()
+    assert r.stats()["rays_alive"] * 8 > w * h
+    mx, ps, frac = _cmp(got, want)
+    assert ps >= 45.0, ps
+    assert frac <= 0.004, (mx, frac)
+    # and the schedule matters here: the exact-position rule is visibly different from the reference
+    r.set_surface_insertion(pynmr.NerfMeshRenderer.SURFACE_EXACT)
+    exact = np.asarray(nerf.render(w, h, 1, linear=False)).copy()
+    assert _cmp(exact, want)[2] > frac
