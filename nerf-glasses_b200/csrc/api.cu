@@ -53,6 +53,7 @@ struct Nerf {
     DeviceModel dev{};
     float render_aabb_min[3], render_aabb_max[3];
     float occ_min[3], occ_max[3];                   // box around every occupied cell (see update_occupied_box)
+    uint64_t n_params = 0;
     float background[4] = {1.f, 1.f, 1.f, 1.f};     // S/ngp/testbed.cuh:525
     float min_transmittance = 0.01f;                // S/ngp/testbed.cuh:484
 };
@@ -576,6 +577,7 @@ NMR_API int nmr_load_nerf(nmr_ctx* ctx, const char* path, int* out_id) {
         }
         std::memcpy(n->render_aabb_min, h.render_aabb_min, 12); std::memcpy(n->render_aabb_max, h.render_aabb_max, 12);
         update_occupied_box(ctx, *n);
+        n->n_params = h.params.size();
         std::vector<uint16_t>().swap(h.params);
         std::vector<uint16_t>().swap(h.density_grid);
         ctx->nerfs.push_back(std::move(n));
@@ -645,6 +647,21 @@ NMR_API int nmr_set_background(nmr_ctx* ctx, int id, const float rgba[4]) {
 }
 NMR_API int nmr_set_min_transmittance(nmr_ctx* ctx, int id, float v) {
     return guarded(ctx, [&]() -> int { try { get_nerf(ctx, id)->min_transmittance = v; return NMR_OK; } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); } });
+}
+
+NMR_API int nmr_get_nerf_info(nmr_ctx* ctx, int id, nmr_nerf_info* o) {
+    return guarded(ctx, [&]() -> int {
+        if (!o) return fail(ctx, NMR_ERR_INVALID, "out is null");
+        Nerf* n; try { n = get_nerf(ctx, id); } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); }
+        const HostModel& h = n->host;
+        *o = nmr_nerf_info{};
+        o->training_step = h.training_step; o->loss = h.loss; o->aabb_scale = h.aabb_scale; o->max_cascade = h.max_cascade;
+        o->cone_angle_constant = h.cone_angle_constant; o->rgb_activation = h.rgb_activation; o->density_activation = h.density_activation;
+        std::memcpy(o->render_aabb_to_local, h.render_aabb_to_local, sizeof(o->render_aabb_to_local));
+        o->n_levels = h.n_levels; o->n_features_per_level = h.n_features_per_level; o->log2_hashmap_size = h.log2_hashmap_size;
+        o->base_resolution = h.base_resolution; o->per_level_scale = h.per_level_scale; o->n_params = n->n_params;
+        return NMR_OK;
+    });
 }
 
 NMR_API int nmr_orbit(nmr_ctx* ctx, float daz, float dpol, float dzoom) {

@@ -180,6 +180,8 @@ HostModel load_snapshot(const std::string& path) {
     }
 
     // parameters - Trainer::deserialize (T/include/tiny-cuda-nn/trainer.h:285-310)
+    m.training_step = snap.value_int("training_step", 0);
+    m.loss = (float)snap.value("loss", 0.0);
     const std::string ptype = snap.value_str("params_type", "__half");
     const Value& pb = snap.at("params_binary");
     if (pb.type != Value::Binary) throw std::runtime_error("params_binary is not binary");

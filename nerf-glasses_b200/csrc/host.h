@@ -39,6 +39,8 @@ struct HostModel {
     float render_aabb_to_local[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};          // row-major
     int rgb_activation = 2;                  // Logistic unless the dataset is HDR (S/ngp/testbed.cu:1028)
     int density_activation = 3;              // Exponential (S/ngp/testbed.cuh:469)
+    int64_t training_step = 0;               // snapshot["training_step"] (Testbed.training_step)
+    float loss = 0.f;                        // snapshot["loss"] (Testbed.loss)
 };
 
 // Throws std::runtime_error with a description on malformed / unsupported snapshots.

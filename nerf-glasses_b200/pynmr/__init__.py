@@ -38,6 +38,13 @@ class Stats(C.Structure):
 _lib = None
 
 
+class NerfInfo(C.Structure):
+    _fields_ = [("training_step", C.c_int64), ("loss", C.c_float), ("aabb_scale", C.c_int), ("max_cascade", C.c_int),
+                ("cone_angle_constant", C.c_float), ("rgb_activation", C.c_int), ("density_activation", C.c_int),
+                ("render_aabb_to_local", C.c_float * 9), ("n_levels", C.c_int), ("n_features_per_level", C.c_int),
+                ("log2_hashmap_size", C.c_int), ("base_resolution", C.c_int), ("per_level_scale", C.c_float), ("n_params", C.c_uint64)]
+
+
 def lib():
     """Loads libnmr.so (raises RuntimeError with the build hint when it is missing)."""
     global _lib
@@ -74,6 +81,7 @@ def lib():
         "nmr_set_shard": (C.c_int, [vp, C.c_int, C.c_int, C.c_int]),
         "nmr_set_surface_insertion": (C.c_int, [vp, C.c_int]),
         "nmr_set_lens": (C.c_int, [vp, C.c_int, C.c_float, C.c_float, fp]),
+        "nmr_get_nerf_info": (C.c_int, [vp, C.c_int, C.POINTER(NerfInfo)]),
         "nmr_debug_lens": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp]),
         "nmr_get_device_image": (C.c_int, [vp, C.POINTER(vp), ip, ip]),
         "nmr_copy_device_image": (C.c_int, [vp, vp]),
@@ -102,7 +110,7 @@ EXPORTED_SYMBOLS = [
     "nmr_create", "nmr_destroy", "nmr_last_error", "nmr_load_nerf", "nmr_load_mesh", "nmr_set_mesh_transform",
     "nmr_get_mesh_transform", "nmr_set_envmap", "nmr_remove_floaties", "nmr_get_render_aabb", "nmr_set_render_aabb",
     "nmr_get_aabb", "nmr_get_background", "nmr_set_background", "nmr_set_min_transmittance", "nmr_orbit", "nmr_get_camera",
-    "nmr_set_camera", "nmr_frame", "nmr_frame_async", "nmr_read_frame", "nmr_render", "nmr_render_views", "nmr_set_shard", "nmr_set_surface_insertion", "nmr_set_lens", "nmr_debug_lens",
+    "nmr_set_camera", "nmr_frame", "nmr_frame_async", "nmr_read_frame", "nmr_render", "nmr_render_views", "nmr_set_shard", "nmr_set_surface_insertion", "nmr_set_lens", "nmr_debug_lens", "nmr_get_nerf_info",
     "nmr_get_device_image", "nmr_copy_device_image", "nmr_flush_l2", "nmr_get_stats", "nmr_synchronize", "nmr_host_alloc", "nmr_host_free", "nmr_get_density_bitfield",
     "nmr_set_density_bitfield", "nmr_debug_encode", "nmr_debug_network", "nmr_debug_trace", "nmr_debug_mesh",
     "nmr_debug_last_frame", "nmr_debug_set_flags",
@@ -255,6 +263,20 @@ class BoundingBox:
 class _NerfSettings:
     """Testbed.nerf (S/python_api.cu:470-496): the members that affect pixels."""
 
+    ACTIVATIONS = ("None", "ReLU", "Logistic", "Exponential")
+
+    @property
+    def cone_angle_constant(self) -> float:
+        return float(self._tb._info().cone_angle_constant)
+
+    @property
+    def rgb_activation(self) -> str:
+        return self.ACTIVATIONS[self._tb._info().rgb_activation]
+
+    @property
+    def density_activation(self) -> str:
+        return self.ACTIVATIONS[self._tb._info().density_activation]
+
     def __init__(self, tb):
         self._tb = tb
         self._min_t = 0.01
@@ -311,6 +333,44 @@ class Testbed:
     @background_color.setter
     def background_color(self, rgba):
         self._r._ck(lib().nmr_set_background(self._r._h, self._id, _f3(rgba)))
+
+    # -- read-only snapshot facts and the camera (S/python_api.cu:301-496: secondary properties of the reference's Testbed)
+    def _info(self) -> NerfInfo:
+        i = NerfInfo()
+        self._r._ck(lib().nmr_get_nerf_info(self._r._h, self._id, C.byref(i)))
+        return i
+
+    @property
+    def training_step(self) -> int:
+        return int(self._info().training_step)
+
+    @property
+    def loss(self) -> float:
+        return float(self._info().loss)
+
+    @property
+    def render_aabb_to_local(self) -> np.ndarray:
+        return np.array(list(self._info().render_aabb_to_local), dtype=np.float32).reshape(3, 3)
+
+    @property
+    def n_params(self) -> int:
+        return int(self._info().n_params)
+
+    @property
+    def camera_matrix(self) -> np.ndarray:
+        """Testbed.camera_matrix: kept equal to NerfMeshRenderer.view_projection_mat by frame() (S/nerf_mesh_renderer.cu:567)."""
+        return self._r.view_projection_mat
+
+    @camera_matrix.setter
+    def camera_matrix(self, mat):
+        self._r.view_projection_mat = mat
+
+    def set_crop_box(self, box: BoundingBox):
+        self._set_render_aabb(box.min, box.max)
+
+    @property
+    def crop_box(self) -> BoundingBox:
+        return self._render_aabb
 
     def render(self, width: int = 1920, height: int = 1080, spp: int = 1, linear: bool = True) -> np.ndarray:
         """float32[H, W, 4]; row 0 is the bottom of the picture; sRGB when linear=False (S/python_api.cu:83-111)."""

@@ -288,5 +288,11 @@ def test_render_py_call_sequence(small_snapshot, glasses_gltf):
         shown.append(np.asarray(renderer.read_frame()).copy())
     assert all(np.isfinite(s).all() for s in shown) and not np.array_equal(shown[0], shown[-1])
     nmr.free_temporary_memory()
+    # secondary Testbed properties of the reference module
+    assert nerf.training_step == 35000 or nerf.training_step >= 0
+    assert nerf.loss >= 0.0 and nerf.n_params > 10240
+    assert np.array_equal(nerf.render_aabb_to_local, np.eye(3, dtype=np.float32))
+    assert nerf.nerf.rgb_activation == "Logistic" and nerf.nerf.density_activation == "Exponential" and nerf.nerf.cone_angle_constant == 0.0
+    assert np.array_equal(nerf.camera_matrix, renderer.view_projection_mat)
     after = np.asarray(nerf.render(Wr, Hr, linear=False))
     assert after.shape == before.shape == (Hr, Wr, 4)
