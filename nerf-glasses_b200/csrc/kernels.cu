@@ -102,14 +102,13 @@ void launch_occupancy_build(const uint16_t* d_grid, int n_cascades_present, uint
 // =================================================================================================================
 constexpr unsigned long long kZMiss = ~0ull;
 
-// kRasterSlices warps per triangle: conservative screen bounding box, then the exact ray/triangle test per covered
+// `slices` warps per triangle (2 for ordinary meshes, 16 when the scene has lens panes - a few huge triangles): conservative screen bounding box, then the exact ray/triangle test per covered
 // sub-pixel; the box's sub-pixels are dealt to the triangle's warps in interleaved groups of 32, so that a triangle covering
 // tens of thousands of sub-pixels (a lens pane at 4K) does not hang on one warp.
 // Replaces optixLaunch(2W x 2H) + RT-core traversal (S/nerf_mesh_renderer.cu:1454-1487, S/optix/optix_scene.cu:120-174).
-constexpr uint32_t kRasterSlices = 16;
-__global__ void __launch_bounds__(256) mesh_raster_kernel(MeshDevice mesh, FrameParams P, int W2, int H2, unsigned long long* __restrict__ zbuf) {
+__global__ void __launch_bounds__(256) mesh_raster_kernel(MeshDevice mesh, FrameParams P, int W2, int H2, unsigned long long* __restrict__ zbuf, uint32_t slices) {
     const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t tri = warp_id / kRasterSlices, slice = warp_id % kRasterSlices;
+    const uint32_t tri = warp_id / slices, slice = warp_id % slices;
     const uint32_t lane = threadIdx.x & 31;
     if (tri >= mesh.n_tris) return;
     const V3 eye = v3(P.cam[9], P.cam[10], P.cam[11]);
@@ -144,7 +143,7 @@ __global__ void __launch_bounds__(256) mesh_raster_kernel(MeshDevice mesh, Frame
     // shard: only sub-pixel rows belonging to owned image rows are needed, but testing ownership per row is cheap enough
     const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
     const int ms = P.mesh_scale;
-    for (int i = (int)(slice * 32u + lane); i < bw * bh; i += 32 * (int)kRasterSlices) {
+    for (int i = (int)(slice * 32u + lane); i < bw * bh; i += 32 * (int)slices) {
         const int x = x0 + i % bw, y = y0 + i / bw;
         if (P.shard_world > 1 && ((y / ms) / P.shard_band) % P.shard_world != P.shard_rank) continue;
         const V3 dir = mesh_ray_dir(P, x, y, W2, H2);
@@ -161,8 +160,9 @@ void launch_mesh_raster(const MeshDevice& mesh, const FrameParams& P, int rows_o
     const int W2 = P.width * P.mesh_scale, H2 = P.height * P.mesh_scale;
     if (mesh.n_tris == 0 || P.zb_w <= 0 || P.zb_h <= 0) return;
     cudaMemsetAsync(d_zbuf, 0xFF, (size_t)P.zb_w * P.zb_h * sizeof(unsigned long long) * (mesh.tri_lens ? 2 : 1), s);
-    const uint32_t threads = mesh.n_tris * 32u * kRasterSlices;
-    mesh_raster_kernel<<<(threads + 255) / 256, 256, 0, s>>>(mesh, P, W2, H2, d_zbuf);
+    const uint32_t slices = mesh.tri_lens ? 16u : 2u;
+    const uint32_t threads = mesh.n_tris * 32u * slices;
+    mesh_raster_kernel<<<(threads + 255) / 256, 256, 0, s>>>(mesh, P, W2, H2, d_zbuf, slices);
 }
 
 // closest hit of one sub-pixel -> shaded RGBA (alpha 1) and hitT; false on miss
