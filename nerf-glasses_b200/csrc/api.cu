@@ -118,6 +118,10 @@ struct nmr_ctx {
     DevBuf<uint32_t> d_counters;
     DevBuf<uint32_t> d_bands;                             // nmr_render's bands: queue ends e[0..K], cursors c[0..K-1]
     cudaEvent_t ev_band[8] = {};                          // band b rendered
+    uint32_t* h_bands = nullptr;                          // pinned: the latched queue lengths of the last banded frame
+    int band_w = 0, band_h = 0;                           // resolution the band history below belongs to
+    bool band_was_empty[16] = {};                         // band queued no ray in the previous banded frame
+    DevBuf<uint32_t> d_band_counts;                       // rays queued per band of rows (written by the set-up kernel)
     uint32_t* h_counters = nullptr;                       // pinned
     DevBuf<float> d_scratch;
     int shard_rank = 0, shard_world = 1, shard_band = 8;
@@ -389,12 +393,19 @@ void enqueue_pass(nmr_ctx* ctx, Nerf& n, const FrameParams& P, bool timed) {
     CK(cudaGetLastError());
 }
 
-// nmr_render's single-sample path: the frame is cut into K bands of contiguous rows.  All K ray set-ups run first (they fill
-// one queue; each band's end is latched on the device), so every band's march sees the whole frame's live-ray count - the
-// surface insertion rule must not depend on the banding - and then band b is marched and handed to the copy stream while band
-// b + 1 is marched: the 16 bytes per pixel cross PCIe underneath the rendering instead of after it.
-void enqueue_pass_banded(nmr_ctx* ctx, Nerf& n, const FrameParams& P0, float* out_host) {
-    constexpr int K = 4;
+// nmr_render's single-sample path: the 16 bytes per pixel cross PCIe underneath the rendering instead of after it.
+// Rows that queue no ray (pure background) are final right after their ray set-up, and in render.py's framing that is most of
+// the picture.  Which rows those are is only known on the device, so the host goes by the previous frame rendered this way at
+// this resolution (kBands bands of rows; a band counts as busy unless it queued nothing last time): the rows above and
+// below the busy bands are set up first and handed to the copy stream at once; the busy rows are then set up, marched and
+// copied as one block, i.e. the latency-bound kernels run once over all the live rays, exactly as in frame().
+// The queue lengths latched after each set-up come back with the frame: if rows predicted empty did queue rays the frame is
+// rendered again the plain way (nmr_render checks), so the prediction only ever costs time, never pixels.
+constexpr int kBands = 12;
+struct BandPlan { int y0, y1; };     // busy rows [y0, y1); ranges in queue order: [0, y0), [y1, H), [y0, y1)
+
+BandPlan enqueue_pass_banded(nmr_ctx* ctx, Nerf& n, const FrameParams& P0, float* out_host) {
+    constexpr int K = kBands;
     Surfaces& S = ctx->surf;
     const int band_rows = (P0.height + K - 1) / K;
     const bool probes = (ctx->debug_flags & kDebugKeepProbes) != 0;
@@ -406,58 +417,74 @@ void enqueue_pass_banded(nmr_ctx* ctx, Nerf& n, const FrameParams& P0, float* ou
         S.lens_scratch.ensure((size_t)ctx->num_sms * 4 * 32 * kLensStash);
         out.lens = S.lens.p; out.lens_scratch = S.lens_scratch.p;
     }
-    ctx->d_bands.ensure(2 * (K + 1));
-    uint32_t* e = ctx->d_bands.p;            // e[0] = 0, e[b + 1] = queue length after band b's set-up
-    uint32_t* c = ctx->d_bands.p + (K + 1);  // c[b] = cursor of band b's march, starts at e[b]
+    if (ctx->band_w != P0.width || ctx->band_h != P0.height) {      // no history at this resolution: every band may hold rays
+        ctx->band_w = P0.width; ctx->band_h = P0.height;
+        for (bool& q : ctx->band_was_empty) q = false;
+    }
+    int b0 = 0, b1 = K;                                            // busy bands [b0, b1), one band of slack on either side
+    while (b0 < K && ctx->band_was_empty[b0]) ++b0;
+    while (b1 > b0 && ctx->band_was_empty[b1 - 1]) --b1;
+    if (b0 >= b1) { b0 = 0; b1 = 0; }                              // nothing was busy: the whole frame is "above"
+    else { b0 = std::max(0, b0 - 1); b1 = std::min(K, b1 + 1); }
+    BandPlan plan{std::min(P0.height, b0 * band_rows), std::min(P0.height, b1 * band_rows)};
+    if (b0 == 0 && b1 == 0) plan.y0 = plan.y1 = P0.height;
+
+    ctx->d_band_counts.ensure(K);
+    CK(cudaMemsetAsync(ctx->d_band_counts.p, 0, sizeof(uint32_t) * K, ctx->stream));
+    out.band_counts = ctx->d_band_counts.p; out.band_rows = band_rows;
+    ctx->d_bands.ensure(8);
+    uint32_t* e = ctx->d_bands.p;            // e[0] = 0, e[i + 1] = queue length after the i-th set-up
+    uint32_t* c = ctx->d_bands.p + 4;        // cursor of the busy block's march, starts at e[2]
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     uint64_t launches = 0;
     SchedArgs sa;
     const bool sched = prepare_schedule(ctx, P0, sa);
     if (P0.mesh_scale > 0) { launch_mesh_raster(mesh, P0, P0.height, S.zbuf.p, ctx->stream); launches += 1; }
     CK(cudaMemsetAsync(e, 0, sizeof(uint32_t), ctx->stream));
-    for (int b = 0; b < K; ++b) {
-        FrameParams P = P0;
-        P.shard_rank = b; P.shard_world = K; P.shard_band = band_rows;
-        const int rows = rows_owned_by(P.height, b, K, band_rows);
-        launch_init_rays(P, n.dev, mesh, S.zbuf.p, rows, S.queue.p, ctx->d_counters.p, out, ctx->num_sms, ctx->stream, b == 0, sched ? S.surf_list.p : nullptr);
-        launches += 1;
-        CK(cudaMemcpyAsync(e + b + 1, ctx->d_counters.p, sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
-    }
-    CK(cudaMemcpyAsync(c, e, sizeof(uint32_t) * K, cudaMemcpyDeviceToDevice, ctx->stream));
-    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-    const uint32_t n_pixels = (uint32_t)P0.width * (uint32_t)P0.height;
-    // rows that can show the mesh: their pixels are final only after the surface-ray pass
-    const int my0 = sched ? P0.zb_y0 / P0.mesh_scale : 0, my1 = sched ? (P0.zb_y0 + P0.zb_h + P0.mesh_scale - 1) / P0.mesh_scale : 0;
-    auto copy_band = [&](int b) {
-        const int y0 = b * band_rows, y1 = std::min(P0.height, (b + 1) * band_rows);
+    auto copy_rows = [&](int y0, int y1) {
         if (y1 <= y0) return;
         const size_t off = (size_t)y0 * P0.width;
         CK(cudaMemcpyAsync(out_host + off * 4, S.image.p + off, (size_t)(y1 - y0) * P0.width * sizeof(float4), cudaMemcpyDeviceToHost, ctx->copy_stream));
     };
-    bool deferred[K] = {};
-    for (int b = 0; b < K; ++b) {
-        launch_march(P0, n.dev, S.queue.p, ctx->d_counters.p, out, n_pixels, ctx->debug_flags, ctx->num_sms, ctx->stream, e + b + 1, c + b, sched ? &sa : nullptr);
-        launches += 1;
-        const int y0 = b * band_rows, y1 = std::min(P0.height, (b + 1) * band_rows);
-        deferred[b] = sched && y0 < my1 && y1 > my0;
-        if (deferred[b]) continue;
-        CK(cudaEventRecord(ctx->ev_band[b], ctx->stream));
-        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_band[b], 0));
-        copy_band(b);
+    auto hand_over = [&](int i, int y0, int y1) {   // everything enqueued so far on the render stream precedes the copy of these rows
+        CK(cudaEventRecord(ctx->ev_band[i], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_band[i], 0));
+        copy_rows(y0, y1);
+    };
+    const int ranges[3][2] = {{0, plan.y0}, {plan.y1, P0.height}, {plan.y0, plan.y1}};
+    for (int i = 0; i < 3; ++i) {
+        FrameParams P = P0;
+        P.row0 = ranges[i][0];
+        const int rows = ranges[i][1] - ranges[i][0];
+        if (rows > 0) {
+            launch_init_rays(P, n.dev, mesh, S.zbuf.p, rows, S.queue.p, ctx->d_counters.p, out, ctx->num_sms, ctx->stream, i == 0, sched ? S.surf_list.p : nullptr);
+            launches += 1;
+        } else if (i == 0) {
+            CK(cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(uint32_t) * kNumCounters, ctx->stream));
+        }
+        CK(cudaMemcpyAsync(e + i + 1, ctx->d_counters.p, sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        if (i < 2 && rows > 0) hand_over(i, ranges[i][0], ranges[i][1]);
     }
-    if (sched) {
-        enqueue_surface_pass(ctx, n, P0, out, n_pixels, sa); launches += 1;
-        CK(cudaEventRecord(ctx->ev_band[K], ctx->stream));
-        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_band[K], 0));
-        for (int b = 0; b < K; ++b) if (deferred[b]) copy_band(b);
+    CK(cudaMemcpyAsync(c, e + 2, sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_bands, e, sizeof(uint32_t) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    const uint32_t n_pixels = (uint32_t)P0.width * (uint32_t)P0.height;
+    if (plan.y1 > plan.y0) {
+        launch_march(P0, n.dev, S.queue.p, ctx->d_counters.p, out, n_pixels, ctx->debug_flags, ctx->num_sms, ctx->stream, e + 3, c, sched ? &sa : nullptr);
+        launches += 1;
+        if (sched) { enqueue_surface_pass(ctx, n, P0, out, n_pixels, sa); launches += 1; }
+        hand_over(2, plan.y0, plan.y1);
     }
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, sizeof(uint32_t) * kNumCounters, cudaMemcpyDeviceToHost, ctx->stream));
+    // per-band ray counts of this frame for the next prediction: the set-up kernels count queued rays per band
+    CK(cudaMemcpyAsync(ctx->h_bands + 4, ctx->d_band_counts.p, sizeof(uint32_t) * K, cudaMemcpyDeviceToHost, ctx->stream));
     ctx->stats.rays = (uint64_t)P0.width * P0.height;
     ctx->stats.mesh_rays = P0.mesh_scale > 0 ? (uint64_t)P0.width * P0.height * P0.mesh_scale * P0.mesh_scale : 0;
     ctx->stats.kernel_launches = launches;
     ctx->stats_pending = true;
     CK(cudaGetLastError());
+    return plan;
 }
 
 void finish_stats(nmr_ctx* ctx) {
@@ -506,6 +533,8 @@ NMR_API int nmr_create(int width, int height, int device, nmr_ctx** out_ctx) {
         ctx->d_counters.ensure(kNumCounters);
         ctx->d_scratch.ensure(64);
         CK(cudaHostAlloc((void**)&ctx->h_counters, sizeof(uint32_t) * kNumCounters, cudaHostAllocDefault));
+        CK(cudaHostAlloc((void**)&ctx->h_bands, sizeof(uint32_t) * 32, cudaHostAllocDefault));
+        std::memset(ctx->h_bands, 0, sizeof(uint32_t) * 32);
         std::memset(ctx->h_counters, 0, sizeof(uint32_t) * kNumCounters);
     } catch (const std::exception& ex) {
         return fail(nullptr, NMR_ERR_CUDA, ex.what());
@@ -523,6 +552,7 @@ NMR_API void nmr_destroy(nmr_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     ctx->nerfs.clear(); ctx->meshes.clear();
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->h_bands) cudaFreeHost(ctx->h_bands);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto& pair : ctx->ev_view) for (auto& ev : pair) if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->ev_band) if (ev) cudaEventDestroy(ev);
@@ -747,11 +777,16 @@ NMR_API int nmr_render(nmr_ctx* ctx, int nerf_id, int width, int height, int spp
         if (spp == 1 && ctx->shard_world == 1 && height >= 256) {
             // one sample per pixel: bands of rows are copied out while the next ones are still being marched
             const FrameParams P = make_params(ctx, *n, width, height, ctx->cam12, 0, !linear, true);
-            enqueue_pass_banded(ctx, *n, P, out_rgba);
+            const BandPlan plan = enqueue_pass_banded(ctx, *n, P, out_rgba);
             CK(cudaStreamSynchronize(ctx->copy_stream));
             CK(cudaStreamSynchronize(ctx->stream));
+            // rows predicted empty are [0, y0) and [y1, H): they were the first two set-ups (queue lengths h_bands[1], h_bands[2])
+            const bool mispredicted = ctx->h_bands[2] != 0u;
+            for (int b = 0; b < kBands; ++b) ctx->band_was_empty[b] = ctx->h_bands[4 + b] == 0u;
             ctx->surf.spp = 0;
-            return NMR_OK;
+            (void)plan;
+            if (!mispredicted) return NMR_OK;
+            // a band that used to be empty queued rays this time and was copied out unmarched: render the frame the plain way
         }
         for (int i = 0; i < spp; ++i) {
             const FrameParams P = make_params(ctx, *n, width, height, ctx->cam12, ctx->surf.spp, !linear, true);

@@ -59,6 +59,7 @@ struct FrameParams {
     float background_out[4];          // displayed value of a pixel that hit nothing (accumulate + tonemap of zero), see finish_pixel
     int to_srgb;
     int shard_rank, shard_world, shard_band;
+    int row0;                         // unsharded contexts: first image row of this pass (nmr_render's row ranges), normally 0
     int mesh_scale;                   // 0: no mesh stage
     float light[3];
     float cam_inv[9];                 // inverse of [U V W] (row-major), for the rasteriser's bounding boxes

@@ -24,7 +24,7 @@ int rows_owned_by(int height, int rank, int world, int band) {
 
 // local (owned) row -> image row
 __device__ __forceinline__ int shard_row(const FrameParams& P, int local_row) {
-    if (P.shard_world <= 1) return local_row;
+    if (P.shard_world <= 1) return local_row + P.row0;
     const int b = local_row / P.shard_band;
     return (b * P.shard_world + P.shard_rank) * P.shard_band + local_row % P.shard_band;
 }
@@ -347,6 +347,11 @@ __device__ __forceinline__ void init_one_ray(const FrameParams& P, const DeviceM
         return;
     }
     const uint32_t slot = atomicAdd(&counters[0], 1u);
+    if (out.band_counts) {      // one atomic per band present among the lanes that got here together
+        const uint32_t band = (uint32_t)(y / out.band_rows);
+        const uint32_t peers = __match_any_sync(__activemask(), band);
+        if ((uint32_t)(__ffs((int)peers) - 1) == (threadIdx.x & 31u)) atomicAdd(out.band_counts + band, (uint32_t)__popc(peers));
+    }
     queue[(size_t)slot * kRayRecordFloat4s + 0] = make_float4(r.dir.x, r.dir.y, r.dir.z, t);
     const bool carries_surface = L.w == 0.f && t_surface != 0.0f && surf[3] > 0.f;
     if (carries_surface && surf_list) surf_list[atomicAdd(&counters[7], 1u)] = slot;

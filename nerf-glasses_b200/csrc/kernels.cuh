@@ -16,6 +16,8 @@ struct FrameOut {
     uint32_t* n_samples;  // network evaluations per ray, W*H or null
     float4* lens;         // lens hand-off per pixel, 2 x W*H: (normal.xyz, t_lens) (coverage, -, -, -); null when the frame has no lens
     float* lens_scratch;  // per ray group of the march kernel: state parked across the segments of a lens ray (kLensStash floats each)
+    uint32_t* band_counts; // rays queued per band of `band_rows` image rows (nmr_render's row prediction), or null
+    int band_rows;
 };
 // The reference's n_steps schedule for frames with MORE than 1/8 live pixels (SurfaceMode auto): pass 1 marches every ray and
 // histograms the sample index at which each ray dies; pass 2 replays clamp(pixels / live rays, 1, 8) per wavefront iteration

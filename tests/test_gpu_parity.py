@@ -296,3 +296,31 @@ def test_render_py_call_sequence(small_snapshot, glasses_gltf):
     assert np.array_equal(nerf.camera_matrix, renderer.view_projection_mat)
     after = np.asarray(nerf.render(Wr, Hr, linear=False))
     assert after.shape == before.shape == (Hr, Wr, 4)
+
+
+def test_banded_render_equals_frame_under_camera_jumps(small_snapshot, glasses_gltf):
+    """Testbed.render() at >= 256 rows copies bands of rows out while later bands are still marched, and skips the march of
+    bands that were empty in the previous frame; when that guess is wrong the frame is rendered again.  Whatever the camera
+    does between calls, the image must equal frame()'s bit for bit."""
+    import pynmr
+    import synth
+    path, _ = small_snapshot
+    w, h = 384, 288
+    r = pynmr.NerfMeshRenderer(w, h)
+    nerf = r.load_nerf(path)
+    assert r.load_mesh(glasses_gltf, t=synth.GLASSES_T, s=synth.GLASSES_S, r=synth.GLASSES_R_WXYZ) is not None
+    r.orbit(0.0, 0.0, 3.0)
+    base = r.view_projection_mat
+    poses = []
+    for dy in (0.0, 0.0, 0.45, -0.45, 0.0, 0.45):          # head in the middle, twice, then pushed to the top / bottom bands and back
+        m = base.copy()
+        m[:, 3] += dy * m[:, 1] / np.linalg.norm(m[:, 1])
+        poses.append(m)
+    for m in poses:
+        r.view_projection_mat = m
+        a = np.asarray(nerf.render(w, h, 1, linear=False)).copy()
+        r.view_projection_mat = m
+        assert r.frame()
+        b = np.asarray(r.read_frame())
+        assert r.stats()["rays_alive"] > 500
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
