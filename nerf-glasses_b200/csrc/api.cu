@@ -440,7 +440,7 @@ BandPlan enqueue_pass_banded(nmr_ctx* ctx, Nerf& n, const FrameParams& P0, float
     SchedArgs sa;
     const bool sched = prepare_schedule(ctx, P0, sa);
     if (P0.mesh_scale > 0) { launch_mesh_raster(mesh, P0, P0.height, S.zbuf.p, ctx->stream); launches += 1; }
-    CK(cudaMemsetAsync(e, 0, sizeof(uint32_t), ctx->stream));
+    CK(cudaMemsetAsync(e, 0, sizeof(uint32_t) * 8, ctx->stream));
     auto copy_rows = [&](int y0, int y1) {
         if (y1 <= y0) return;
         const size_t off = (size_t)y0 * P0.width;
@@ -462,11 +462,9 @@ BandPlan enqueue_pass_banded(nmr_ctx* ctx, Nerf& n, const FrameParams& P0, float
         } else if (i == 0) {
             CK(cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(uint32_t) * kNumCounters, ctx->stream));
         }
-        CK(cudaMemcpyAsync(e + i + 1, ctx->d_counters.p, sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        launch_latch_word(ctx->d_counters.p, e + i + 1, i == 1 ? c : nullptr, ctx->stream);     // (the march cursor starts at e[2])
         if (i < 2 && rows > 0) hand_over(i, ranges[i][0], ranges[i][1]);
     }
-    CK(cudaMemcpyAsync(c, e + 2, sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->h_bands, e, sizeof(uint32_t) * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     const uint32_t n_pixels = (uint32_t)P0.width * (uint32_t)P0.height;
     if (plan.y1 > plan.y0) {
@@ -476,6 +474,8 @@ BandPlan enqueue_pass_banded(nmr_ctx* ctx, Nerf& n, const FrameParams& P0, float
         hand_over(2, plan.y0, plan.y1);
     }
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    // small read-backs last: the device->host engine is busy with the image rows, and nothing on the render stream may wait for it
+    CK(cudaMemcpyAsync(ctx->h_bands, e, sizeof(uint32_t) * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, sizeof(uint32_t) * kNumCounters, cudaMemcpyDeviceToHost, ctx->stream));
     // per-band ray counts of this frame for the next prediction: the set-up kernels count queued rays per band
     CK(cudaMemcpyAsync(ctx->h_bands + 4, ctx->d_band_counts.p, sizeof(uint32_t) * K, cudaMemcpyDeviceToHost, ctx->stream));
@@ -774,7 +774,8 @@ NMR_API int nmr_render(nmr_ctx* ctx, int nerf_id, int width, int height, int spp
         ctx->surf.spp = 0;   // reset_accumulation (S/python_api.cu:85)
         // Testbed::render uses Testbed::m_camera, which frame()/orbit keep equal to viewProjectionMat; its aspect comes from the
         // renderer's constructor resolution, not from (width, height), exactly like the reference.
-        if (spp == 1 && ctx->shard_world == 1 && height >= 256) {
+        static const bool no_bands = std::getenv("NMR_NO_BANDS") != nullptr;     // measurement aid: plain render + one copy
+        if (spp == 1 && ctx->shard_world == 1 && height >= 256 && !no_bands) {
             // one sample per pixel: bands of rows are copied out while the next ones are still being marched
             const FrameParams P = make_params(ctx, *n, width, height, ctx->cam12, 0, !linear, true);
             const BandPlan plan = enqueue_pass_banded(ctx, *n, P, out_rgba);

@@ -373,6 +373,15 @@ __global__ void __launch_bounds__(128) init_rays_kernel(FrameParams P, DeviceMod
     init_one_ray(P, M, mesh, zbuf, queue, counters, out, x, shard_row(P, ly), surf_list);
 }
 
+// dst[0] = src[0] (and dst2[0] = src[0] when given) on the stream, without involving a copy engine: a DMA engine busy with a
+// large device->host transfer would make a tiny cudaMemcpyAsync - and everything behind it on its stream - wait
+__global__ void latch_word_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, uint32_t* __restrict__ dst2) {
+    const uint32_t v = *src;
+    *dst = v;
+    if (dst2) *dst2 = v;
+}
+void launch_latch_word(const uint32_t* d_src, uint32_t* d_dst, uint32_t* d_dst2, cudaStream_t s) { latch_word_kernel<<<1, 1, 0, s>>>(d_src, d_dst, d_dst2); }
+
 void launch_init_rays(const FrameParams& P, const DeviceModel& M, const MeshDevice& mesh, const unsigned long long* d_zbuf, int rows_owned,
                       float4* d_queue, uint32_t* d_counters, const FrameOut& out, int num_sms, cudaStream_t s, bool reset_counters, uint32_t* d_surf_list) {
     if (reset_counters) cudaMemsetAsync(d_counters, 0, sizeof(uint32_t) * kNumCounters, s);
