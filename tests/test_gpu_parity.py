@@ -324,3 +324,50 @@ def test_banded_render_equals_frame_under_camera_jumps(small_snapshot, glasses_g
         b = np.asarray(r.read_frame())
         assert r.stats()["rays_alive"] > 500
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_aabb_scale_4_model(tmp_path):
+    """A snapshot with aabb_scale 4: three occupancy cascades (+ pooled parents), a render box of size 4, the cone-angle step
+    growth (cone_angle_constant 1/256, dt = clamp(t / 256)) and mip selection from both position and step size
+    (S/ngp/testbed.cu:188-202, 1098-1115).  Same bars as the unit-cube model; also checked against the reference's own
+    renderer where its library is present."""
+    import pynmr
+    import synth
+    from oracle import oracle as O
+    from oracle import refgpu
+    path = str(tmp_path / "s4.msgpack")
+    synth.write_snapshot(path, seed=7, log2_hashmap_size=15, aabb_scale=4)
+    snap = synth.read_snapshot(path)
+    w, h = 160, 90
+    r = pynmr.NerfMeshRenderer(w, h)
+    nerf = r.load_nerf(path)
+    assert nerf is not None
+    assert nerf.nerf.cone_angle_constant == 1.0 / 256.0
+    H.set_flags(r, 0)
+    r.orbit(0.4, -0.25, -1.5)
+    m = O.Model.from_snapshot(snap)
+    assert np.array_equal(H.get_bitfield(r, nerf), m.bitfield())
+    c12 = cam12(r)
+    P = m.params_struct(w, h, c12, aabb_min=snap["render_aabb_min"], aabb_max=snap["render_aabb_max"])
+    pixels = np.arange(0, w * h, 3, dtype=np.uint32)
+    want = m.trace_samples(P, pixels, 64)
+    got = H.debug_trace(r, nerf, w, h, pixels, 64)
+    assert want["count"].sum() > 2000 and int(want["mip"].max()) >= 1
+    for k in ("count", "cell", "mip"):
+        assert np.array_equal(got[k], want[k]), k
+    for k in ("t", "pos"):
+        assert np.array_equal(got[k].view(np.uint32), want[k].view(np.uint32)), k
+    img = np.asarray(nerf.render(w, h, 1, linear=False)).copy()
+    ref_img, _, ns, stats, _ = H.oracle_scene(snap, w, h, c12)
+    assert r.stats()["rays_alive"] == stats["alive_after_first_hit"] and stats["samples"] > 5000
+    assert np.max(np.abs(img - ref_img)) <= PIX_TOL and H.psnr(img, ref_img) >= 45.0
+    if refgpu.available():
+        ref = refgpu.ReferenceRenderer(path)
+        try:
+            assert np.array_equal(ref.bitfield(), m.bitfield())
+            theirs, _ = ref.render(c12, w, h, 1, False)
+        finally:
+            ref.close()
+        d = np.abs(img - theirs)
+        assert H.psnr(img, theirs) >= 45.0
+        assert float(np.mean(d.max(axis=2) > PIX_TOL)) <= 0.004

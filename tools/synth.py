@@ -157,8 +157,8 @@ class NetParams:
         assert params.size == self.n_params, (params.size, self.n_params)
 
 
-def n_params_for(n_levels=16, log2_hashmap_size=19, base_resolution=16, density_hidden=1, rgb_hidden=2, width=64):
-    offs, _, _ = level_table(n_levels, base_resolution, per_level_scale(n_levels, base_resolution), log2_hashmap_size)
+def n_params_for(n_levels=16, log2_hashmap_size=19, base_resolution=16, density_hidden=1, rgb_hidden=2, width=64, aabb_scale=1):
+    offs, _, _ = level_table(n_levels, base_resolution, per_level_scale(n_levels, base_resolution, aabb_scale), log2_hashmap_size)
     mlp = width * n_levels * 2 + (density_hidden - 1) * width * width + 16 * width
     mlp += width * 32 + (rgb_hidden - 1) * width * width + 16 * width
     return mlp + int(offs[-1]) * 2
@@ -274,13 +274,14 @@ def make_density_grid(rng: np.random.Generator, n_floaters: int = 64) -> np.ndar
 
 
 def make_params(rng: np.random.Generator, n_levels=16, log2_hashmap_size=19, base_resolution=16,
-                regime: str = "opaque", calibrate: bool = True) -> np.ndarray:
+                regime: str = "opaque", calibrate: bool = True, aabb_scale: int = 1) -> np.ndarray:
     """Random-init fp16 parameter vector in params_binary order.
 
     regime "opaque": density output row made non-negative and scaled so the median raw sigma
     inside the head ellipsoid is ~ +6 (rays saturate in ~5-10 samples);
     regime "translucent": median raw sigma ~ 0 (full-length marches, worst case)."""
-    n = n_params_for(n_levels, log2_hashmap_size, base_resolution)
+    n = n_params_for(n_levels, log2_hashmap_size, base_resolution, aabb_scale=aabb_scale)
+    calibrate = calibrate and aabb_scale == 1      # (the calibration helper assumes the unit-cube level table)
     p = np.empty(n, dtype=np.float16)
     o = 0
     shapes = [(64, n_levels * 2), (16, 64), (64, 32), (64, 64), (16, 64)]
@@ -362,13 +363,32 @@ def snapshot_dict(params: np.ndarray, density_grid: np.ndarray, n_levels=16, log
 
 
 def write_snapshot(path: str, seed: int = 1337, n_levels=16, log2_hashmap_size=19, base_resolution=16,
-                   regime: str = "opaque", n_floaters: int = 64, calibrate: bool = True) -> dict:
-    """Write a synthetic snapshot; returns {"params": fp16[], "density_grid": fp16[], "config": dict-without-binaries}."""
+                   regime: str = "opaque", n_floaters: int = 64, calibrate: bool = True, aabb_scale: int = 1) -> dict:
+    """Write a synthetic snapshot; returns {"params": fp16[], "density_grid": fp16[], "config": dict-without-binaries}.
+    aabb_scale > 1: log2(aabb_scale) + 1 occupancy cascades (a few blobs outside the unit cube in the coarser ones), a render
+    box of that size and the cone-angle step growth of the reference (S/ngp/testbed.cu:1098-1115)."""
     import msgpack
     rng = np.random.default_rng(seed)
     grid = make_density_grid(rng, n_floaters)
-    params = make_params(rng, n_levels, log2_hashmap_size, base_resolution, regime, calibrate)
-    d = snapshot_dict(params, grid, n_levels, log2_hashmap_size, base_resolution)
+    if aabb_scale > 1:
+        n_casc = int(np.log2(aabb_scale)) + 1
+        full = np.zeros(NERF_GRIDSIZE ** 3 * n_casc, dtype=np.float16)
+        full[:NERF_GRIDSIZE ** 3] = grid
+        for c in range(1, n_casc):       # blobs outside the centre octant (which the loader fills by pooling the finer cascade)
+            occ = np.zeros((NERF_GRIDSIZE,) * 3, dtype=bool)
+            for _ in range(6):
+                p = rng.integers(4, NERF_GRIDSIZE - 12, size=3)
+                if np.all((p > 24) & (p < 100)):
+                    p[int(rng.integers(0, 3))] = int(rng.choice([6, 108]))
+                s3 = rng.integers(3, 9, size=3)
+                occ[p[0]:p[0] + s3[0], p[1]:p[1] + s3[1], p[2]:p[2] + s3[2]] = True
+            xs, ys, zs = np.nonzero(occ)
+            full[c * NERF_GRIDSIZE ** 3 + morton3d(xs, ys, zs)] = np.float16(1.0)
+        grid = full
+    params = make_params(rng, n_levels, log2_hashmap_size, base_resolution, regime, calibrate, aabb_scale)
+    half = 0.5 * aabb_scale
+    d = snapshot_dict(params, grid, n_levels, log2_hashmap_size, base_resolution,
+                      render_aabb=(CROP_MIN, CROP_MAX) if aabb_scale == 1 else ([0.5 - half] * 3, [0.5 + half] * 3), aabb_scale=aabb_scale)
     os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
     with open(path, "wb") as f:
         f.write(msgpack.packb(d, use_bin_type=True))
