@@ -371,3 +371,56 @@ def test_aabb_scale_4_model(tmp_path):
         d = np.abs(img - theirs)
         assert H.psnr(img, theirs) >= 45.0
         assert float(np.mean(d.max(axis=2) > PIX_TOL)) <= 0.004
+
+
+def test_edge_cases(small_snapshot, glasses_gltf, tmp_path):
+    """Odd and tiny frames, an empty occupancy grid, a mesh out of view / behind the eye, the eye inside the head."""
+    import msgpack
+    import pynmr
+    import synth
+    path, snap = small_snapshot
+    g = {"path": glasses_gltf, "t": synth.GLASSES_T, "s": synth.GLASSES_S, "r": synth.GLASSES_R_WXYZ,
+         "texture": np.tile(np.array([128, 128, 128, 255], dtype=np.uint8), (4, 4, 1))}
+    # odd sizes, hybrid, against the oracle (the camera's aspect stays that of the constructor resolution, like the reference)
+    for (w, h) in ((37, 23), (1, 1), (2, 300)):
+        r = pynmr.NerfMeshRenderer(w, h)
+        nerf = r.load_nerf(path)
+        assert r.load_mesh(g["path"], t=g["t"], s=g["s"], r=g["r"]) is not None
+        r.orbit(0.3, -0.1, 5.0)
+        img = np.asarray(nerf.render(w, h, 1, linear=False)).copy()
+        want = H.oracle_scene(snap, w, h, cam12(r), glasses=g, n_steps_mode=1)[0]
+        assert img.shape == (h, w, 4)
+        assert np.max(np.abs(img - want)) <= PIX_TOL, (w, h)
+    # nothing occupied: every pixel is the background, no ray is queued
+    d = msgpack.unpackb(open(path, "rb").read(), raw=False, strict_map_key=False)
+    d["snapshot"]["density_grid_binary"] = np.zeros(128 ** 3, dtype=np.float16).tobytes()
+    empty = str(tmp_path / "empty.msgpack")
+    open(empty, "wb").write(msgpack.packb(d, use_bin_type=True))
+    r = pynmr.NerfMeshRenderer(64, 48)
+    nerf = r.load_nerf(empty)
+    img = np.asarray(nerf.render(64, 48, 1, linear=False))
+    assert r.stats()["rays_alive"] == 0 and r.stats()["samples"] == 0
+    assert np.allclose(img, 1.0, atol=1e-6)
+    assert r.remove_floaties() is not None          # no clusters: nothing to keep, nothing breaks
+    # mesh out of view and behind the eye: the frame equals the NeRF-only frame
+    r = pynmr.NerfMeshRenderer(96, 54)
+    nerf = r.load_nerf(path)
+    r.orbit(0.3, -0.1, 4.0)
+    plain = np.asarray(nerf.render(96, 54, 1, linear=False)).copy()
+    assert r.load_mesh(g["path"], t=(0.0, 30.0, 0.0), s=g["s"], r=g["r"]) is not None      # far above
+    assert np.array_equal(np.asarray(nerf.render(96, 54, 1, linear=False)).view(np.uint32), plain.view(np.uint32))
+    eye = r.view_projection_mat[:, 3]; fwd = r.view_projection_mat[:, 2]
+    r2 = pynmr.NerfMeshRenderer(96, 54)
+    nerf2 = r2.load_nerf(path)
+    r2.view_projection_mat = r.view_projection_mat
+    assert r2.load_mesh(g["path"], t=tuple(eye - 0.8 * fwd), s=g["s"], r=g["r"]) is not None    # behind the eye
+    assert np.array_equal(np.asarray(nerf2.render(96, 54, 1, linear=False)).view(np.uint32), plain.view(np.uint32))
+    # the eye inside the head: rays start in occupied cells
+    r3 = pynmr.NerfMeshRenderer(96, 54)
+    nerf3 = r3.load_nerf(path)
+    m = r3.view_projection_mat
+    m[:, 3] = (0.0, 0.0, 0.05)
+    r3.view_projection_mat = m
+    img = np.asarray(nerf3.render(96, 54, 1, linear=False)).copy()
+    want = H.oracle_scene(snap, 96, 54, cam12(r3))[0]
+    assert np.max(np.abs(img - want)) <= PIX_TOL
