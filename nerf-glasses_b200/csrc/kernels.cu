@@ -993,12 +993,16 @@ void launch_march(const FrameParams& P, const DeviceModel& M, const float4* d_qu
     if (sched) sa = *sched;
     const int per_sm = ctas_per_sm > 0 ? ctas_per_sm : kMarchCtasPerSm;
     if (debug_flags & kDebugScalarMlp) {
-        static bool attr_set = false;
+        static bool attr_set_dev[64] = {};      // the opt-in to > 48 KB of dynamic shared memory is per device
+        int dev = 0; cudaGetDevice(&dev);
+        bool& attr_set = attr_set_dev[dev & 63];
         if (!attr_set) { cudaFuncSetAttribute(march_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmem)); cudaFuncSetAttribute(march_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(MarchSmem) + kSchedSmem)); attr_set = true; }
         if (sa.pass == 2) march_kernel<false, true><<<num_sms, kTile, sizeof(MarchSmem) + kSchedSmem, s>>>(P, M, d_queue, d_counters, out, n_pixels, debug_flags, d_range_end, d_cursor, sa);
         else march_kernel<false, false><<<num_sms * 2, kTile, sizeof(MarchSmem), s>>>(P, M, d_queue, d_counters, out, n_pixels, debug_flags, d_range_end, d_cursor, sa);
     } else {
-        static bool attr_set = false;
+        static bool attr_set_dev[64] = {};
+        int dev = 0; cudaGetDevice(&dev);
+        bool& attr_set = attr_set_dev[dev & 63];
         if (!attr_set) { cudaFuncSetAttribute(march_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmemTC)); cudaFuncSetAttribute(march_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(MarchSmemTC) + kSchedSmem)); attr_set = true; }
         if (sa.pass == 2) march_kernel<true, true><<<num_sms * per_sm, kTile * kGroupsTC, sizeof(MarchSmemTC) + kSchedSmem, s>>>(P, M, d_queue, d_counters, out, n_pixels, debug_flags, d_range_end, d_cursor, sa);
         else march_kernel<true, false><<<num_sms * per_sm, kTile * kGroupsTC, sizeof(MarchSmemTC), s>>>(P, M, d_queue, d_counters, out, n_pixels, debug_flags, d_range_end, d_cursor, sa);

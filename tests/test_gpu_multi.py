@@ -90,3 +90,17 @@ def test_sharded_frame_and_views_nccl(small_snapshot, glasses_gltf):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res[0] == (0, True, True), res
+
+
+def test_two_contexts_on_two_devices_in_one_process(small_snapshot, glasses_gltf):
+    """One process driving two GPUs through two contexts ('single process driving 8 devices is sufficient'):
+    both devices render the same frame bit for bit."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    imgs = []
+    for dev in (0, 1):
+        r, nerf = _scene(dev, small_snapshot[0], glasses_gltf)
+        imgs.append(np.asarray(nerf.render(W, HH, 1, linear=False)).copy())
+        assert r.frame()
+    assert np.array_equal(imgs[0].view(np.uint32), imgs[1].view(np.uint32))
