@@ -310,20 +310,42 @@ def run_tiles(args, rank: int, world: int, local_rank: int, dist):
     if args.zoom:
         r.orbit(0.0, 0.0, args.zoom)
     r.set_surface_insertion(pynmr.NerfMeshRenderer.SURFACE_BATCH8)     # one decision for all shards
-    sr = D.ShardedRenderer(r, rank, world, band=args.band)
     a = 0.0
-    for _ in range(args.warmup):
-        a += 0.03; r.orbit(*orbit_step(a)); sr.render_frame(dst=0)
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        a += 0.03; r.orbit(*orbit_step(a))
-        full = sr.render_frame(dst=0)           # copy_device_image joins libnmr's stream before the gather is enqueued
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+    if args.gather == "peer":
+        # render + gather fused: every rank's kernels store their rows into rank 0's image over NVLink; device-side sequence
+        # flags order the frames, so the timed loop holds no collective and no host synchronisation.  Timed with events on the
+        # renderer's own stream (rank 0's stream ends each frame with the wait for all ranks' rows).
+        ps = D.PeerShardedRenderer(r, rank, world, band=args.band, dst=0)
+        stream = torch.cuda.ExternalStream(r.stream_ptr(), device=torch.device("cuda", local_rank))
+        for _ in range(args.warmup):
+            a += 0.03; r.orbit(*orbit_step(a)); ps.render_frame()
+        r.synchronize()
+        if dist is not None:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            a += 0.03; r.orbit(*orbit_step(a))
+            full = ps.render_frame(sync=False)
+        e1.record(stream); r.synchronize(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if full is not None:
+            full = full.clone()
+        ps.close()
+    else:
+        sr = D.ShardedRenderer(r, rank, world, band=args.band)
+        for _ in range(args.warmup):
+            a += 0.03; r.orbit(*orbit_step(a)); sr.render_frame(dst=0)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            a += 0.03; r.orbit(*orbit_step(a))
+            full = sr.render_frame(dst=0)           # copy_device_image joins libnmr's stream before the gather is enqueued
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
     if dist is not None:
         t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t[0]); dist.barrier()
@@ -331,9 +353,9 @@ def run_tiles(args, rank: int, world: int, local_rank: int, dist):
         return None
     return {"metric": "Mrays/s", "value": W * H * args.steps / (ms / 1e3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": {"workload": f"one {W}x{H} hybrid frame per step{' with lens secondary rays' if args.lens else ''}, rows dealt to ranks in bands of {args.band}, NCCL gather to rank 0 (BASELINE configs[3])",
+            "config": {"workload": f"one {W}x{H} hybrid frame per step{' with lens secondary rays' if args.lens else ''}, rows dealt to ranks in bands of {args.band}, {'peer stores into rank 0 image over NVLink, device-side flags' if args.gather == 'peer' else 'NCCL gather to rank 0'} (BASELINE configs[3])",
                        "model": f"synthetic iNGP snapshot seed 1337 ({args.regime}), log2_hashmap_size={args.log2_hashmap_size}", "zoom": args.zoom,
-                       "parallelism": f"tiles: {world} ranks, one process per GPU, one gather per frame"},
+                       "parallelism": f"tiles: {world} ranks, one process per GPU, " + ("no collective (fused peer stores)" if args.gather == "peer" else "one NCCL gather per frame")},
             "fps": args.steps / (ms / 1e3), "checksum": float(full[H // 2, W // 2, 0]) if full is not None else None}
 
 
@@ -417,6 +439,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the stress and reference-on-GPU legs")
     ap.add_argument("--mode", default="views", choices=["views", "tiles"], help="views (default, the headline): every rank renders its own frames; tiles: one frame split over the ranks and gathered")
     ap.add_argument("--band", type=int, default=16)
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="tiles mode: rows stored straight into rank 0's image by the render kernels (peer), or packed and gathered with NCCL")
     ap.add_argument("--lens", action="store_true", help="tiles mode: glasses with lens panes (secondary rays)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

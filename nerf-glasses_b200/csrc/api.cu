@@ -115,6 +115,14 @@ struct nmr_ctx {
     MeshDevice mesh_dev{};
     float mesh_wmin[3] = {0.f, 0.f, 0.f}, mesh_wmax[3] = {0.f, 0.f, 0.f};   // world-space box of the concatenated mesh
     Surfaces surf;
+    // shared frame target of tile-sharded rendering (nmr_gather_*): every rank's frame() writes its rows straight into ONE
+    // image in the destination rank's memory - its own kernels' stores travel over NVLink, there is no gather afterwards
+    DevBuf<float4> gather_image;                          // destination rank: the shared image (exported through CUDA IPC)
+    float4* frame_target = nullptr;                       // where frame() writes pixels: gather_image / a peer's, or null = own image
+    void* ipc_mapped = nullptr;                           // peer image opened with cudaIpcOpenMemHandle
+    uint32_t* gather_flags = nullptr;                     // sequence flags behind the shared image (kernels.cuh: kGather*)
+    uint32_t gather_seq = 0;                              // frames rendered into the shared image so far (same on every rank)
+    bool gather_is_dst = false;
     DevBuf<uint32_t> d_counters;
     DevBuf<uint32_t> d_bands;                             // nmr_render's bands: queue ends e[0..K], cursors c[0..K-1]
     cudaEvent_t ev_band[8] = {};                          // band b rendered
@@ -357,12 +365,12 @@ void enqueue_surface_pass(nmr_ctx* ctx, Nerf& n, const FrameParams& P, const Fra
 }
 
 // one sample-per-pixel pass: mesh stage -> init -> march.  Enqueues only; no host synchronisation.
-void enqueue_pass(nmr_ctx* ctx, Nerf& n, const FrameParams& P, bool timed) {
+void enqueue_pass(nmr_ctx* ctx, Nerf& n, const FrameParams& P, bool timed, float4* image_target = nullptr) {
     Surfaces& S = ctx->surf;
     const int rows = rows_owned_by(P.height, P.shard_rank, P.shard_world, P.shard_band);
     // the linear frame, depth and per-ray sample counts are parity probes (nmr_debug_last_frame): written only on request
     const bool probes = (ctx->debug_flags & kDebugKeepProbes) != 0;
-    FrameOut out{S.image.p, S.accum.p, probes ? S.frame.p : nullptr, probes ? S.depth.p : nullptr, probes ? S.n_samples.p : nullptr, nullptr, nullptr};
+    FrameOut out{image_target ? image_target : S.image.p, S.accum.p, probes ? S.frame.p : nullptr, probes ? S.depth.p : nullptr, probes ? S.n_samples.p : nullptr, nullptr, nullptr};
     MeshDevice mesh = ctx->mesh_dev;
     if (!P.lens_on) mesh.tri_lens = nullptr;     // lenses off: their triangles are ordinary opaque surfaces
     else {
@@ -550,6 +558,7 @@ NMR_API void nmr_destroy(nmr_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->ipc_mapped) { cudaIpcCloseMemHandle(ctx->ipc_mapped); ctx->ipc_mapped = nullptr; }
     ctx->nerfs.clear(); ctx->meshes.clear();
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->h_bands) cudaFreeHost(ctx->h_bands);
@@ -739,6 +748,24 @@ NMR_API int nmr_set_surface_insertion(nmr_ctx* ctx, int mode) {
     });
 }
 
+namespace {
+// A frame whose pixels go to a shared image (nmr_gather_*).  Device-side protocol, no host or NCCL step:
+//   other ranks wait until the destination is done with the previous frame, render (their stores cross NVLink), signal;
+//   the destination marks the previous frame consumed, renders its own rows, signals, then waits for every rank's signal -
+//   so once the destination's stream has drained, the shared image holds the whole frame.
+void enqueue_gather_frame(nmr_ctx* ctx, Nerf& n, const FrameParams& P) {
+    const uint32_t seq = ++ctx->gather_seq;
+    uint32_t* f = ctx->gather_flags;
+    if (ctx->gather_is_dst) launch_gather_signal(f + kGatherConsumed, seq - 1u, ctx->stream);
+    else launch_gather_wait(f, kGatherConsumed, 1, seq - 1u, f + kGatherError, ctx->stream);
+    enqueue_pass(ctx, n, P, true, ctx->frame_target);
+    launch_gather_signal(f + ctx->shard_rank, seq, ctx->stream);
+    if (ctx->gather_is_dst) launch_gather_wait(f, 0, ctx->shard_world, seq, f + kGatherError, ctx->stream);
+    CK(cudaGetLastError());
+}
+
+}  // namespace
+
 NMR_API int nmr_frame(nmr_ctx* ctx, int* keep_running) {
     return guarded(ctx, [&]() -> int {
         if (keep_running) *keep_running = 1;
@@ -747,7 +774,7 @@ NMR_API int nmr_frame(nmr_ctx* ctx, int* keep_running) {
         Nerf& n = *ctx->nerfs[0];
         ctx->surf.resize(ctx->width, ctx->height, ctx->mesh_scale);
         const FrameParams P = make_params(ctx, n, ctx->width, ctx->height, ctx->cam12, ctx->surf.spp, true, true);
-        enqueue_pass(ctx, n, P, true);
+        if (ctx->frame_target) enqueue_gather_frame(ctx, n, P); else enqueue_pass(ctx, n, P, true);
         ++ctx->surf.spp;
         CK(cudaStreamSynchronize(ctx->stream));   // frame() returns a finished frame (S/nerf_mesh_renderer.cu:578)
         return NMR_OK;
@@ -758,7 +785,8 @@ NMR_API int nmr_read_frame(nmr_ctx* ctx, float* out_rgba) {
     return guarded(ctx, [&]() -> int {
         if (!out_rgba) return fail(ctx, NMR_ERR_INVALID, "out_rgba is null");
         if (!ctx->surf.image.p || ctx->surf.w == 0) return fail(ctx, NMR_ERR_STATE, "nothing rendered yet");
-        CK(cudaMemcpyAsync(out_rgba, ctx->surf.image.p, (size_t)ctx->surf.w * ctx->surf.h * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+        const float4* src = (ctx->gather_image.p && ctx->frame_target == ctx->gather_image.p && ctx->surf.w == ctx->width && ctx->surf.h == ctx->height) ? ctx->gather_image.p : ctx->surf.image.p;
+        CK(cudaMemcpyAsync(out_rgba, src, (size_t)ctx->surf.w * ctx->surf.h * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         return NMR_OK;
     });
@@ -868,6 +896,64 @@ NMR_API int nmr_synchronize(nmr_ctx* ctx) {
     return guarded(ctx, [&]() -> int { CK(cudaStreamSynchronize(ctx->stream)); return NMR_OK; });
 }
 
+NMR_API int nmr_get_stream(nmr_ctx* ctx, void** out_stream) {
+    return guarded(ctx, [&]() -> int {
+        if (!out_stream) return fail(ctx, NMR_ERR_INVALID, "out_stream is null");
+        *out_stream = static_cast<void*>(ctx->stream);
+        return NMR_OK;
+    });
+}
+
+NMR_API int nmr_gather_create(nmr_ctx* ctx, uint8_t handle64[64], void** out_dev_ptr) {
+    return guarded(ctx, [&]() -> int {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+        if (!handle64) return fail(ctx, NMR_ERR_INVALID, "handle is null");
+        if (ctx->shard_world > kGatherMaxRanks) return fail(ctx, NMR_ERR_INVALID, "too many ranks for a shared frame target");
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->ipc_mapped) { CK(cudaIpcCloseMemHandle(ctx->ipc_mapped)); ctx->ipc_mapped = nullptr; }
+        const size_t px = (size_t)ctx->width * ctx->height;
+        ctx->gather_image.ensure(px + kGatherFlagWords * sizeof(uint32_t) / sizeof(float4));     // image, then the sequence flags
+        ctx->gather_flags = reinterpret_cast<uint32_t*>(ctx->gather_image.p + px);
+        CK(cudaMemset(ctx->gather_flags, 0, kGatherFlagWords * sizeof(uint32_t)));
+        cudaIpcMemHandle_t h;
+        CK(cudaIpcGetMemHandle(&h, ctx->gather_image.p));
+        std::memcpy(handle64, &h, 64);
+        ctx->frame_target = ctx->gather_image.p; ctx->gather_is_dst = true; ctx->gather_seq = 0;
+        if (out_dev_ptr) *out_dev_ptr = ctx->gather_image.p;
+        ctx->surf.spp = 0;
+        return NMR_OK;
+    });
+}
+NMR_API int nmr_gather_attach(nmr_ctx* ctx, const uint8_t handle64[64]) {
+    return guarded(ctx, [&]() -> int {
+        if (!handle64) return fail(ctx, NMR_ERR_INVALID, "handle is null");
+        if (ctx->shard_rank >= kGatherMaxRanks) return fail(ctx, NMR_ERR_INVALID, "too many ranks for a shared frame target");
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->ipc_mapped) { CK(cudaIpcCloseMemHandle(ctx->ipc_mapped)); ctx->ipc_mapped = nullptr; ctx->frame_target = nullptr; }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handle64, 64);
+        void* p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->ipc_mapped = p; ctx->frame_target = static_cast<float4*>(p);
+        ctx->gather_flags = reinterpret_cast<uint32_t*>(ctx->frame_target + (size_t)ctx->width * ctx->height);
+        ctx->gather_is_dst = false; ctx->gather_seq = 0;
+        ctx->surf.spp = 0;
+        return NMR_OK;
+    });
+}
+NMR_API int nmr_gather_detach(nmr_ctx* ctx) {
+    return guarded(ctx, [&]() -> int {
+        CK(cudaStreamSynchronize(ctx->stream));
+        uint32_t err = 0;
+        if (ctx->gather_flags) CK(cudaMemcpy(&err, ctx->gather_flags + kGatherError, sizeof(err), cudaMemcpyDeviceToHost));
+        if (ctx->ipc_mapped) { CK(cudaIpcCloseMemHandle(ctx->ipc_mapped)); ctx->ipc_mapped = nullptr; }
+        ctx->frame_target = nullptr; ctx->gather_flags = nullptr; ctx->gather_is_dst = false; ctx->gather_seq = 0;
+        ctx->surf.spp = 0;
+        if (err) return fail(ctx, NMR_ERR_STATE, "a rank of the shared frame target did not render a frame the others waited for");
+        return NMR_OK;
+    });
+}
+
 // Asynchronous frame for throughput measurements and pipelined callers: same work as nmr_frame without the trailing
 // synchronisation; call nmr_synchronize() / nmr_get_stats() / nmr_read_frame() to wait.
 NMR_API int nmr_frame_async(nmr_ctx* ctx) {
@@ -877,7 +963,7 @@ NMR_API int nmr_frame_async(nmr_ctx* ctx) {
         Nerf& n = *ctx->nerfs[0];
         ctx->surf.resize(ctx->width, ctx->height, ctx->mesh_scale);
         const FrameParams P = make_params(ctx, n, ctx->width, ctx->height, ctx->cam12, ctx->surf.spp, true, true);
-        enqueue_pass(ctx, n, P, true);
+        if (ctx->frame_target) enqueue_gather_frame(ctx, n, P); else enqueue_pass(ctx, n, P, true);
         ++ctx->surf.spp;
         return NMR_OK;
     });

@@ -382,6 +382,32 @@ __global__ void latch_word_kernel(const uint32_t* __restrict__ src, uint32_t* __
 }
 void launch_latch_word(const uint32_t* d_src, uint32_t* d_dst, uint32_t* d_dst2, cudaStream_t s) { latch_word_kernel<<<1, 1, 0, s>>>(d_src, d_dst, d_dst2); }
 
+// ---- tile-sharded frames written straight into one rank's image (nmr_gather_*): sequence flags in that rank's memory ----
+// flags[r] (r < 32) = last frame rank r has finished writing; flags[kGatherConsumed] = last frame the destination is done with;
+// flags[kGatherError] != 0 after a wait that ran out of time.  Stores of a rank's render kernels precede its signal kernel in
+// stream order; the fence + system-scope store below publish them to the peer that polls the flag.
+__global__ void gather_signal_kernel(volatile uint32_t* flag, uint32_t seq) {
+    __threadfence_system();
+    *flag = seq;
+    __threadfence_system();
+}
+__global__ void gather_wait_kernel(volatile uint32_t* flags, int first, int count, uint32_t seq, volatile uint32_t* err) {
+    const int i = threadIdx.x;
+    if (i >= count) return;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while ((int32_t)(flags[first + i] - seq) < 0) {
+        __nanosleep(200);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 2000000000ull) { *err = 1u; break; }     // 2 s: a rank never rendered this frame - give up instead of hanging the GPU
+    }
+    __threadfence_system();
+}
+void launch_gather_signal(uint32_t* d_flag, uint32_t seq, cudaStream_t s) { gather_signal_kernel<<<1, 1, 0, s>>>(d_flag, seq); }
+void launch_gather_wait(uint32_t* d_flags, int first, int count, uint32_t seq, uint32_t* d_err, cudaStream_t s) {
+    if (count > 0) gather_wait_kernel<<<1, 32, 0, s>>>(d_flags, first, count, seq, d_err);
+}
+
 void launch_init_rays(const FrameParams& P, const DeviceModel& M, const MeshDevice& mesh, const unsigned long long* d_zbuf, int rows_owned,
                       float4* d_queue, uint32_t* d_counters, const FrameOut& out, int num_sms, cudaStream_t s, bool reset_counters, uint32_t* d_surf_list) {
     if (reset_counters) cudaMemsetAsync(d_counters, 0, sizeof(uint32_t) * kNumCounters, s);

@@ -49,6 +49,10 @@ void launch_occupancy_build(const uint16_t* d_density_grid_fp16, int n_cascades_
 void launch_occupancy_bounds(const uint8_t* d_bitfield, int* d_out48, cudaStream_t s);
 void launch_mesh_raster(const MeshDevice& mesh, const FrameParams& P, int rows_owned, unsigned long long* d_zbuf, cudaStream_t s);
 void launch_latch_word(const uint32_t* d_src, uint32_t* d_dst, uint32_t* d_dst2, cudaStream_t s);
+// sequence flags of a shared frame target (nmr_gather_*): one word per rank + "consumed" + "error", behind the image
+constexpr int kGatherMaxRanks = 32, kGatherConsumed = 32, kGatherError = 33, kGatherFlagWords = 64;
+void launch_gather_signal(uint32_t* d_flag, uint32_t seq, cudaStream_t s);
+void launch_gather_wait(uint32_t* d_flags, int first, int count, uint32_t seq, uint32_t* d_err, cudaStream_t s);
 void launch_init_rays(const FrameParams& P, const DeviceModel& M, const MeshDevice& mesh, const unsigned long long* d_zbuf, int rows_owned,
                       float4* d_queue, uint32_t* d_counters, const FrameOut& out, int num_sms, cudaStream_t s, bool reset_counters = true, uint32_t* d_surf_list = nullptr);
 // n_pixels: pixels traced by this context in this pass (the reference's m_n_rays_initialized), for SurfaceMode auto

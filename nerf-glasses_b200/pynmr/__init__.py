@@ -82,6 +82,10 @@ def lib():
         "nmr_set_surface_insertion": (C.c_int, [vp, C.c_int]),
         "nmr_set_lens": (C.c_int, [vp, C.c_int, C.c_float, C.c_float, fp]),
         "nmr_get_nerf_info": (C.c_int, [vp, C.c_int, C.POINTER(NerfInfo)]),
+        "nmr_get_stream": (C.c_int, [vp, C.POINTER(vp)]),
+        "nmr_gather_create": (C.c_int, [vp, vp, C.POINTER(vp)]),
+        "nmr_gather_attach": (C.c_int, [vp, vp]),
+        "nmr_gather_detach": (C.c_int, [vp]),
         "nmr_debug_lens": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp]),
         "nmr_get_device_image": (C.c_int, [vp, C.POINTER(vp), ip, ip]),
         "nmr_copy_device_image": (C.c_int, [vp, vp]),
@@ -110,7 +114,7 @@ EXPORTED_SYMBOLS = [
     "nmr_create", "nmr_destroy", "nmr_last_error", "nmr_load_nerf", "nmr_load_mesh", "nmr_set_mesh_transform",
     "nmr_get_mesh_transform", "nmr_set_envmap", "nmr_remove_floaties", "nmr_get_render_aabb", "nmr_set_render_aabb",
     "nmr_get_aabb", "nmr_get_background", "nmr_set_background", "nmr_set_min_transmittance", "nmr_orbit", "nmr_get_camera",
-    "nmr_set_camera", "nmr_frame", "nmr_frame_async", "nmr_read_frame", "nmr_render", "nmr_render_views", "nmr_set_shard", "nmr_set_surface_insertion", "nmr_set_lens", "nmr_debug_lens", "nmr_get_nerf_info",
+    "nmr_set_camera", "nmr_frame", "nmr_frame_async", "nmr_read_frame", "nmr_render", "nmr_render_views", "nmr_set_shard", "nmr_set_surface_insertion", "nmr_set_lens", "nmr_debug_lens", "nmr_get_nerf_info", "nmr_gather_create", "nmr_gather_attach", "nmr_gather_detach", "nmr_get_stream",
     "nmr_get_device_image", "nmr_copy_device_image", "nmr_flush_l2", "nmr_get_stats", "nmr_synchronize", "nmr_host_alloc", "nmr_host_free", "nmr_get_density_bitfield",
     "nmr_set_density_bitfield", "nmr_debug_encode", "nmr_debug_network", "nmr_debug_trace", "nmr_debug_mesh",
     "nmr_debug_last_frame", "nmr_debug_set_flags",
@@ -522,6 +526,26 @@ class NerfMeshRenderer:
     def set_lens(self, enabled: bool = True, ior: float = -1.0, transmission: float = -1.0, tint=None):
         """Lens surfaces and their secondary rays (include/nmr.h: nmr_set_lens).  Negative / None keeps a parameter."""
         self._ck(lib().nmr_set_lens(self._h, int(bool(enabled)), float(ior), float(transmission), _f3(tint) if tint is not None else None))
+
+    def stream_ptr(self) -> int:
+        """cudaStream_t of this renderer as an integer (e.g. for torch.cuda.ExternalStream)."""
+        p = C.c_void_p()
+        self._ck(lib().nmr_get_stream(self._h, C.byref(p)))
+        return int(p.value or 0)
+
+    def gather_create(self):
+        """Destination rank of a tile-sharded frame: -> (64-byte IPC handle as bytes, device pointer of the shared image)."""
+        h = (C.c_uint8 * 64)(); p = C.c_void_p()
+        self._ck(lib().nmr_gather_create(self._h, h, C.byref(p)))
+        return bytes(h), p.value
+
+    def gather_attach(self, handle: bytes):
+        """Other ranks: frame() writes this rank's rows into the destination's shared image from now on."""
+        assert len(handle) == 64
+        self._ck(lib().nmr_gather_attach(self._h, (C.c_uint8 * 64)(*handle)))
+
+    def gather_detach(self):
+        self._ck(lib().nmr_gather_detach(self._h))
 
     def device_image(self):
         """(device pointer, width, height) of the float4 image of the last render."""

@@ -10,6 +10,10 @@ renders.  Two partitionings:
           `gather_frame` packs the owned rows and gathers them to `dst` with ONE collective, where they are scattered back
           into a full image.  The gathered image is bit-identical to the single-GPU image (tests/test_gpu_parity.py).
 
+  tiles, fused   `PeerShardedRenderer`: no gather at all - every rank's render kernels store their rows straight into ONE image
+          in the destination rank's memory (CUDA IPC mapping over NVLink, include/nmr.h: nmr_gather_*), ordered by
+          device-side sequence flags.  torch.distributed only carries the 64-byte IPC handle once, at set-up.
+
 Tensors are torch tensors on whatever device the process group's backend moves (cuda for nccl, cpu for gloo).
 """
 from __future__ import annotations
@@ -102,3 +106,51 @@ class ShardedRenderer:
             self._buf = torch.empty((H, W, 4), dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
         self.r.copy_device_image(self._buf.data_ptr())      # device->device on libnmr's stream, then a stream synchronise
         return gather_frame(self._buf, self.rank, self.world, self.band, dst, self.group)
+
+
+class _DeviceImage:
+    """float32 [H, W, 4] view of device memory owned by libnmr, for torch.as_tensor (CUDA array interface)."""
+
+    def __init__(self, ptr: int, height: int, width: int):
+        self.__cuda_array_interface__ = {"shape": (height, width, 4), "typestr": "<f4", "data": (int(ptr), False), "version": 3, "strides": None}
+
+
+class PeerShardedRenderer:
+    """One frame across the process group with the gather fused into the rendering: rank `dst` owns the image, every
+    rank's frame() writes its own rows into it through peer memory (NVLink).  Per frame there is no collective and no host
+    synchronisation between ranks; `render_frame()` returns the full image on `dst` (a view of the shared image, valid until
+    the next render_frame) and None elsewhere.  Every rank must call render_frame() the same number of times."""
+
+    def __init__(self, renderer, rank: int, world: int, band: int = 8, dst: int = 0, group=None):
+        import torch.distributed as dist
+        self.r, self.rank, self.world, self.band, self.dst, self.group = renderer, rank, world, band, dst, group
+        renderer.set_shard(rank, world, band)
+        self._image = None
+        box = [None]
+        if rank == dst:
+            handle, ptr = renderer.gather_create()
+            box[0] = handle
+            import torch
+            self._image = torch.as_tensor(_DeviceImage(ptr, renderer.height, renderer.width), device=torch.device("cuda", torch.cuda.current_device()))
+        if world > 1:
+            dist.broadcast_object_list(box, src=dst, group=group)
+            if rank != dst:
+                renderer.gather_attach(box[0])
+            dist.barrier(group=group)       # everybody is attached before the first frame
+
+    def render_frame(self, sync: bool = True):
+        """sync=False only enqueues (pipelined callers that consume the image on the renderer's stream, r.stream_ptr())."""
+        self.r.frame_async()
+        if self.rank != self.dst:
+            return None
+        if sync:
+            self.r.synchronize()            # the destination's stream ends with the wait for every rank's signal
+        return self._image
+
+    def close(self):
+        import torch.distributed as dist
+        if self.world > 1:
+            self.r.synchronize()
+            dist.barrier(group=self.group)  # nobody unmaps while a peer may still be writing
+        self.r.gather_detach()
+        self.r.set_shard(0, 1, self.band)

@@ -54,6 +54,21 @@ def _worker(rank, world, port, snap_path, gltf, q):
             r.frame()
             single = torch.from_numpy(np.asarray(r.read_frame()).copy()).cuda()
             ok_tiles = bool(torch.equal(full, single))
+        # tiles, fused: every rank's kernels store their rows into rank 0's image over NVLink, device-side flags, no collective
+        r.set_shard(0, 1, 8)
+        ps = D.PeerShardedRenderer(r, rank, world, band=8, dst=0)
+        ok_peer = None
+        for k in range(3):                      # several frames: the consumed / written handshake is exercised
+            r.orbit(0.02, 0.01, 0)
+            img = ps.render_frame()
+            if rank == 0:
+                peer_img = img.clone()
+        ps.close()
+        if rank == 0:
+            r.set_shard(0, 1, 8)
+            r.frame()
+            single = torch.from_numpy(np.asarray(r.read_frame()).copy()).cuda()
+            ok_peer = bool(torch.equal(peer_img, single))
         # views: 5 cameras dealt to ranks
         cams = []
         r.set_shard(0, 1, 8)
@@ -68,7 +83,7 @@ def _worker(rank, world, port, snap_path, gltf, q):
         if rank == 0:
             want = torch.from_numpy(np.asarray(r.render_views(nerf, cams, 96, 54)).copy()).cuda()
             ok_views = bool(torch.equal(got, want))
-        q.put((rank, ok_tiles, ok_views))
+        q.put((rank, ok_tiles, ok_views, ok_peer))
     finally:
         dist.destroy_process_group()
 
@@ -89,7 +104,7 @@ def test_sharded_frame_and_views_nccl(small_snapshot, glasses_gltf):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    assert res[0] == (0, True, True), res
+    assert res[0] == (0, True, True, True), res
 
 
 def test_two_contexts_on_two_devices_in_one_process(small_snapshot, glasses_gltf):
@@ -104,3 +119,20 @@ def test_two_contexts_on_two_devices_in_one_process(small_snapshot, glasses_gltf
         imgs.append(np.asarray(nerf.render(W, HH, 1, linear=False)).copy())
         assert r.frame()
     assert np.array_equal(imgs[0].view(np.uint32), imgs[1].view(np.uint32))
+
+
+def test_shared_frame_target_single_rank(small_snapshot, glasses_gltf):
+    """nmr_gather_* with a world of one (runs on any GPU box): the shared image, its sequence flags and the signal / wait kernels
+    are exercised over several frames; the image equals the ordinary frame."""
+    import torch
+    from pynmr import dist as D
+    torch.cuda.set_device(0)
+    r, nerf = _scene(0, small_snapshot[0], glasses_gltf)
+    ps = D.PeerShardedRenderer(r, 0, 1, band=8, dst=0)
+    for _ in range(3):
+        r.orbit(0.02, 0.01, 0)
+        got = ps.render_frame().clone()
+    ps.close()
+    assert r.frame()
+    want = torch.from_numpy(np.asarray(r.read_frame()).copy()).cuda()
+    assert torch.equal(got, want)
