@@ -50,6 +50,7 @@ struct Nerf {
     HostModel host;                 // parameters are dropped after upload
     DevBuf<uint16_t> d_params;
     DevBuf<uint8_t> d_bitfield;
+    DevBuf<uint32_t> d_coarse;                      // coarse "near" bits of cascade 0 (kernels.cuh: launch_coarse_build)
     DeviceModel dev{};
     float render_aabb_min[3], render_aabb_max[3];
     float occ_min[3], occ_max[3];                   // box around every occupied cell (see update_occupied_box)
@@ -250,6 +251,14 @@ void upload_mesh_if_dirty(nmr_ctx* ctx) {
 // A position p tests cascade mip_from_pos(p) (S/ngp/testbed.cu:188-193): inside the unit cube that is cascade 0 (cascade 1
 // exactly on its boundary), in general cascades 0..max_cascade+1; cascade c cells are 2^c / 128 wide and centred on 0.5.
 void update_occupied_box(nmr_ctx* ctx, Nerf& n) {
+    {   // the coarse view of cascade 0 that the first-hit walk jumps through (NMR_NO_COARSE=1: plain walk, for A/B runs)
+        n.d_coarse.ensure((size_t)kCoarseRes * kCoarseRes);
+        DevBuf<uint8_t> d_occ; d_occ.ensure((size_t)kCoarseRes * kCoarseRes * kCoarseRes);
+        launch_coarse_build(n.d_bitfield.p, d_occ.p, n.d_coarse.p, ctx->stream);
+        CK(cudaStreamSynchronize(ctx->stream));
+        const char* off = std::getenv("NMR_NO_COARSE");
+        n.dev.coarse = (off && off[0] == '1') ? nullptr : n.d_coarse.p;
+    }
     DevBuf<int> d_b; d_b.ensure(48);
     launch_occupancy_bounds(n.d_bitfield.p, d_b.p, ctx->stream);
     int b[48];
@@ -303,6 +312,30 @@ void mesh_screen_box(const nmr_ctx* ctx, FrameParams& P) {
     P.zb_x0 = x0; P.zb_y0 = y0; P.zb_w = x1 - x0; P.zb_h = y1 - y0;
 }
 
+// Screen rectangle (pixels) of the box around the occupied cells: a ray through a pixel outside it misses the box, so
+// advance_pos_nerf could only walk it out of the render box - a background pixel unless the mesh covers it.  Conservative:
+// the whole frame when a corner of the box is not safely in front of the eye; padded by two pixels.
+void occupied_screen_box(FrameParams& P) {
+    P.occ_px[0] = P.occ_px[1] = 0; P.occ_px[2] = P.width; P.occ_px[3] = P.height;
+    if (!(P.occ_min[0] <= P.occ_max[0])) { P.occ_px[2] = P.occ_px[3] = 0; return; }       // nothing occupied
+    float minx = 1e30f, miny = 1e30f, maxx = -1e30f, maxy = -1e30f;
+    for (int c = 0; c < 8; ++c) {
+        // NeRF-space corner relative to the NeRF-space eye (cam + 0.5)
+        const float q[3] = {((c & 1) ? P.occ_max[0] : P.occ_min[0]) - (P.cam[9] + 0.5f), ((c & 2) ? P.occ_max[1] : P.occ_min[1]) - (P.cam[10] + 0.5f),
+                            ((c & 4) ? P.occ_max[2] : P.occ_min[2]) - (P.cam[11] + 0.5f)};
+        const float a = P.cam_inv[0] * q[0] + P.cam_inv[1] * q[1] + P.cam_inv[2] * q[2];
+        const float b = P.cam_inv[3] * q[0] + P.cam_inv[4] * q[1] + P.cam_inv[5] * q[2];
+        const float w = P.cam_inv[6] * q[0] + P.cam_inv[7] * q[1] + P.cam_inv[8] * q[2];
+        if (!(w > 1e-3f)) return;                                                           // whole frame
+        const float px = (a / w + 1.0f) * 0.5f * (float)P.width - 0.5f, py = (b / w + 1.0f) * 0.5f * (float)P.height - 0.5f;
+        minx = std::min(minx, px); maxx = std::max(maxx, px); miny = std::min(miny, py); maxy = std::max(maxy, py);
+    }
+    if (!(maxx >= -4.f && maxy >= -4.f && minx <= (float)P.width + 4.f && miny <= (float)P.height + 4.f)) { P.occ_px[2] = P.occ_px[3] = 0; return; }   // off screen
+    P.occ_px[0] = std::max(0, (int)std::floor(minx) - 2); P.occ_px[1] = std::max(0, (int)std::floor(miny) - 2);
+    P.occ_px[2] = std::min(P.width, (int)std::ceil(maxx) + 3); P.occ_px[3] = std::min(P.height, (int)std::ceil(maxy) + 3);
+    if (P.occ_px[2] <= P.occ_px[0] || P.occ_px[3] <= P.occ_px[1]) { P.occ_px[2] = P.occ_px[3] = 0; P.occ_px[0] = P.occ_px[1] = 0; }
+}
+
 FrameParams make_params(nmr_ctx* ctx, const Nerf& n, int W, int H, const float* cam12, uint32_t spp_index, bool to_srgb, bool with_mesh) {
     FrameParams P{};
     P.width = W; P.height = H;
@@ -335,6 +368,7 @@ FrameParams make_params(nmr_ctx* ctx, const Nerf& n, int W, int H, const float* 
     invert3(cam12, P.cam_inv);
     std::memcpy(P.occ_min, n.occ_min, 12); std::memcpy(P.occ_max, n.occ_max, 12);
     P.surface_mode = ctx->surface_mode;
+    occupied_screen_box(P);
     mesh_screen_box(ctx, P);
     P.lens_on = (P.mesh_scale > 0 && ctx->scene_has_lens && ctx->lens_enabled) ? 1 : 0;
     {

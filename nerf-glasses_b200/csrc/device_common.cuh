@@ -22,6 +22,7 @@ struct DeviceModel {
     const __half2* grid;              // hash-table entries, all levels back to back
     const __half* mlp;                // density net | rgb net, row-major [out][in] (params_binary order)
     const uint8_t* bitfield;          // 2 MiB occupancy bits, Morton order per cascade
+    const uint32_t* coarse;           // 32^3 "near" bits of cascade 0 (kCoarseRes; see coarse_near), or null: no empty-space jumps
     const __half2* level_ptr[N_LEVELS];  // grid + level_offset[l]: 64-bit base per level, so a gather is base + 32-bit index
     uint32_t level_offset[N_LEVELS];  // first entry of each level
     uint32_t level_size[N_LEVELS];    // entries in each level
@@ -64,6 +65,7 @@ struct FrameParams {
     float light[3];
     float cam_inv[9];                 // inverse of [U V W] (row-major), for the rasteriser's bounding boxes
     float occ_min[3], occ_max[3];     // box around every occupied grid cell a sample can test, inflated by one cell
+    int occ_px[4];                    // pixels [x0, x1) x [y0, y1) = occ_px[0..3] whose ray can meet that box (host-projected, padded); the rest is background unless the mesh covers it
     int surface_mode;                 // where a partially covering mesh surface enters the compositing order: SurfaceMode
     // The mesh visibility buffer covers only the screen bounding box of the mesh (sub-pixel units of the mesh_scale x
     // supersampled frame, aligned to whole pixels): zb_w == 0 means "mesh not in view".  Entry (x, y) lives at
@@ -199,6 +201,56 @@ __device__ __forceinline__ float advance_to_next_voxel(float t, float cone_angle
     return t;
 }
 
+// ---- exact empty-space jumps of the uniform-step walk ---------------------------------------------------------
+// With a zero cone angle every step of the reference's walk is `t += dt0` in fp32 (S/ngp/testbed.cu:306-313).  Inside one
+// binade [2^e, 2^(e+1)) t is a multiple of ulp = 2^(e-23) and dt0 = q ulp + r with a fixed r, so every such addition rounds
+// the same way: it advances the BIT PATTERN of t by the constant inc(e) = bits(2^e + dt0) - bits(2^e) (r is never the tie
+// ulp/2 for dt0 = sqrt(3)/1024 and any binade a walk can reach - checked in tests/test_host_cpu.py).  K sequential additions
+// are therefore one integer multiply-add while the result stays inside the binade; a binade boundary is crossed with real
+// additions.  The result is bit-identical to the K-fold loop.
+__device__ __forceinline__ float lattice_advance(float t, int K) {
+    const float dt0 = min_cone_stepsize();
+    while (K > 0) {
+        const uint32_t b = __float_as_uint(t);
+        const uint32_t e = b & 0xFF800000u;
+        const uint32_t inc = __float_as_uint(__uint_as_float(e) + dt0) - e;
+        const uint32_t room = (e | 0x007FFFFFu) - b;                              // additions of one ulp that stay inside the binade
+        // steps that certainly fit: (float) room / inc is within a few ulp of the quotient; two steps of slack
+        const int fit = (int)(__uint2float_rz(room) * __frcp_rz(__uint2float_ru(inc))) - 2;
+        if (K <= fit) return __uint_as_float(b + (uint32_t)K * inc);
+        if (fit > 0) { t = __uint_as_float(b + (uint32_t)fit * inc); K -= fit; }
+        // close to the top of the binade: real additions until the exponent changes (at most a handful)
+        do { t += dt0; --K; } while (K > 0 && (__float_as_uint(t) & 0xFF800000u) == e);
+    }
+    return t;
+}
+
+// Coarse view of cascade 0 for those jumps: kCoarseRes^3 cells of (128 / kCoarseRes)^3 grid cells each.  A coarse cell is
+// NEAR when a cell within Chebyshev distance 2 of it holds an occupied grid cell, or when it touches the surface of the unit
+// cube (positions there may test cascade 1, and the walk's box tests stay exact).  From a cell that is not near, the walk
+// can only step through empty cascade-0 cells until it leaves the coarse cell, so those steps are taken at once: the walk
+// lands on the first step at or behind the coarse cell's exit, exactly where its own last step inside the cell would land
+// up to the rounding of the two distance computations (they differ by ~1e-7, a step is 1.7e-3: the landing differs with
+// probability ~1e-4, by one step) - and from any landing point the walk falls back onto the reference's own sequence of
+// steps at the next voxel boundary with the same odds.  Two coarse cells (>= 4 voxel steps) separate a landing from the first
+// occupied cell, which puts a different first sample at ~1e-16 per ray; tests compare t bit for bit with the oracle's plain walk.
+constexpr int kCoarseRes = 32;
+__device__ __forceinline__ bool coarse_near(const uint32_t* __restrict__ coarse, V3 pos) {
+    const int cx = min(max(__float2int_rz(pos.x * (float)kCoarseRes), 0), kCoarseRes - 1);
+    const int cy = min(max(__float2int_rz(pos.y * (float)kCoarseRes), 0), kCoarseRes - 1);
+    const int cz = min(max(__float2int_rz(pos.z * (float)kCoarseRes), 0), kCoarseRes - 1);
+    return (__ldg(coarse + cz * kCoarseRes + cy) >> cx) & 1u;
+}
+// the walk's steps up to the first one at or behind the exit of the (empty) coarse cell around pos
+__device__ __forceinline__ float coarse_skip(float t, V3 pos, V3 dir, V3 idir) {
+    const float dt0 = min_cone_stepsize();
+    const float t_target = t + distance_to_next_voxel(pos, dir, idir, (uint32_t)kCoarseRes);
+    const int K = (int)((t_target - t) * (1.0f / dt0)) - 2;          // steps that certainly stay in front of t_target
+    if (K > 0) t = lattice_advance(t, K);
+    do { t += dt0; } while (t < t_target);
+    return t;
+}
+
 // ---- boxes (S/ngp/bounding_box.cuh:106-167) -------------------------------------------------------------------
 __device__ __forceinline__ bool box_contains(const float* mn, const float* mx, V3 p) {
     return p.x >= mn[0] && p.x <= mx[0] && p.y >= mn[1] && p.y <= mx[1] && p.z >= mn[2] && p.z <= mx[2];
@@ -266,7 +318,7 @@ __device__ __forceinline__ RayInit init_ray(const FrameParams& P, uint32_t x, ui
 }
 
 // advance_pos_nerf (S/ngp/testbed.cu:470-537); returns alive
-__device__ __forceinline__ bool advance_pos(const FrameParams& P, const uint8_t* __restrict__ bitfield, V3 origin, V3 dir, uint32_t pixel_idx,
+__device__ __forceinline__ bool advance_pos(const FrameParams& P, const uint8_t* __restrict__ bitfield, const uint32_t* __restrict__ coarse, V3 origin, V3 dir, uint32_t pixel_idx,
                                             float t_surface, float t_occ_in, float t_limit, bool alive, float& t_io, float& t_start) {
     t_start = 0.f;
     if (!alive) {
@@ -279,6 +331,49 @@ __device__ __forceinline__ bool advance_pos(const FrameParams& P, const uint8_t*
     float dt = calc_dt(t, cone);
     t += ld_random_val(P.spp_index, pixel_idx * 786433u) * dt;
     const bool uniform_dt = cone == 0.0f;
+    if (uniform_dt) {
+        // Zero cone angle: where the walk goes next does not depend on what the occupancy tests return, only whether it goes
+        // on.  So the next kWalkBatch steps are laid out first (arithmetic only) with their occupancy loads in flight together,
+        // and are then judged in order - the walk's critical path holds one memory latency per batch instead of one per step.
+        constexpr int kWalkBatch = 4;
+        const float dt0 = min_cone_stepsize();
+        bool hit = false;
+        while (!hit) {
+            float tv[kWalkBatch];
+            uint32_t word[kWalkBatch], bit[kWalkBatch];
+            int n = 0, stop = 0;                 // stop: 1 behind the mesh surface, 2 out of the box, 3 coarse cell without anything near
+            float tc = t;
+#pragma unroll
+            for (int k = 0; k < kWalkBatch; ++k) {
+                if (stop != 0) continue;
+                if (t_surface != 0.0f && tc > t_surface) { stop = 1; continue; }
+                const V3 pc = vadd(origin, vmul(dir, tc));
+                if (tc > t_limit || !box_contains(P.aabb_min, P.aabb_max, r2l_mul(P.r2l, pc))) { stop = 2; continue; }
+                if (coarse && !coarse_near(coarse, pc)) { stop = 3; continue; }
+                const uint32_t mip = (uint32_t)mip_from_dt(dt0, pc);
+                const uint32_t idx = cascaded_grid_idx_at(pc, mip);
+                // before the ray enters the box around the occupied cells every test is known to fail: no load
+                word[k] = tc >= t_occ_in ? (uint32_t)__ldg(bitfield + idx / 8 + (GRID_CELLS / 8) * mip) : 0u;
+                bit[k] = 1u << (idx % 8);
+                tv[k] = tc;
+                n = k + 1;
+                tc = advance_to_next_voxel(tc, cone, true, pc, dir, idir, NERF_GRIDSIZE >> mip);
+            }
+#pragma unroll
+            for (int k = 0; k < kWalkBatch; ++k) {
+                if (!hit && k < n && (word[k] & bit[k])) { t = tv[k]; hit = true; }
+            }
+            if (hit) break;
+            t = tc;
+            if (stop == 1) { t_io = t_surface; return true; }
+            if (stop == 2) {                     // nothing occupied ahead == walked out of the box
+                if (t_surface != 0.0f) { t_io = t_surface; return true; }
+                alive = false;
+                break;
+            }
+            if (stop == 3) t = coarse_skip(t, vadd(origin, vmul(dir, t)), dir, idir);
+        }
+    } else
     while (true) {
         if (t_surface != 0.0f && t > t_surface) { t_io = t_surface; return true; }
         const V3 pos = vadd(origin, vmul(dir, t));
@@ -287,11 +382,11 @@ __device__ __forceinline__ bool advance_pos(const FrameParams& P, const uint8_t*
             alive = false;
             break;
         }
-        dt = uniform_dt ? min_cone_stepsize() : calc_dt(t, cone);
+        dt = calc_dt(t, cone);
         const uint32_t mip = (uint32_t)mip_from_dt(dt, pos);
         // before the ray enters the box around the occupied cells every test is known to fail: no load, no Morton code
         if (t >= t_occ_in && occupied_at(pos, bitfield, mip)) break;
-        t = advance_to_next_voxel(t, cone, uniform_dt, pos, dir, idir, NERF_GRIDSIZE >> mip);
+        t = advance_to_next_voxel(t, cone, false, pos, dir, idir, NERF_GRIDSIZE >> mip);
     }
     t_io = t;
     if (mip_from_pos(vadd(origin, vmul(dir, t))) == 0) t_start = t;

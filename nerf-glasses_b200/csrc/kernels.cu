@@ -86,6 +86,41 @@ void launch_occupancy_bounds(const uint8_t* d_bitfield, int* d_out48, cudaStream
     occupancy_bounds_kernel<<<(total + 255) / 256, 256, 0, s>>>(d_bitfield, d_out48);
 }
 
+// coarse "near" bits of cascade 0 (device_common.cuh: coarse_near).  A coarse cell is a (128 / kCoarseRes)^3 block of grid cells
+// aligned to its size, i.e. 64 consecutive Morton codes = 8 consecutive bytes of the bitfield.
+__global__ void coarse_occupied_kernel(const uint8_t* __restrict__ bitfield, uint8_t* __restrict__ occ) {
+    static_assert(NERF_GRIDSIZE / kCoarseRes == 4, "a coarse cell is 4 x 4 x 4 grid cells");
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= kCoarseRes * kCoarseRes * kCoarseRes) return;
+    const uint32_t cx = i % kCoarseRes, cy = (i / kCoarseRes) % kCoarseRes, cz = i / (kCoarseRes * kCoarseRes);
+    const uint32_t m = morton3D(cx * 4u, cy * 4u, cz * 4u);                 // first of the block's 64 codes
+    const uint2 v = *reinterpret_cast<const uint2*>(bitfield + m / 8u);
+    occ[i] = (v.x | v.y) != 0u;
+}
+__global__ void coarse_near_kernel(const uint8_t* __restrict__ occ, uint32_t* __restrict__ near_bits) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;                    // one thread per row of 32 cells = one word
+    if (i >= kCoarseRes * kCoarseRes) return;
+    const int cy = i % kCoarseRes, cz = i / kCoarseRes;
+    uint32_t word = 0;
+    for (int cx = 0; cx < kCoarseRes; ++cx) {
+        bool near_cell = cx == 0 || cy == 0 || cz == 0 || cx == kCoarseRes - 1 || cy == kCoarseRes - 1 || cz == kCoarseRes - 1;
+        for (int dz = -2; dz <= 2 && !near_cell; ++dz)
+            for (int dy = -2; dy <= 2 && !near_cell; ++dy)
+                for (int dx = -2; dx <= 2; ++dx) {
+                    const int x = cx + dx, y = cy + dy, z = cz + dz;
+                    if (x < 0 || y < 0 || z < 0 || x >= kCoarseRes || y >= kCoarseRes || z >= kCoarseRes) continue;
+                    if (occ[(z * kCoarseRes + y) * kCoarseRes + x]) { near_cell = true; break; }
+                }
+        word |= near_cell ? (1u << cx) : 0u;
+    }
+    near_bits[i] = word;
+}
+void launch_coarse_build(const uint8_t* d_bitfield, uint8_t* d_occ_scratch, uint32_t* d_near_bits, cudaStream_t s) {
+    constexpr int n = kCoarseRes * kCoarseRes * kCoarseRes;
+    coarse_occupied_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_bitfield, d_occ_scratch);
+    coarse_near_kernel<<<(kCoarseRes * kCoarseRes + 127) / 128, 128, 0, s>>>(d_occ_scratch, d_near_bits);
+}
+
 void launch_occupancy_build(const uint16_t* d_grid, int n_cascades_present, uint8_t* d_bitfield, float* d_scratch, cudaStream_t s) {
     double* sum = reinterpret_cast<double*>(d_scratch);
     cudaMemsetAsync(sum, 0, sizeof(double), s);
@@ -341,7 +376,7 @@ __device__ __forceinline__ void init_one_ray(const FrameParams& P, const DeviceM
 
     RayInit r = init_ray(P, (uint32_t)x, (uint32_t)y);
     float t = r.t, t_start;
-    const bool alive = advance_pos(P, M.bitfield, r.origin, r.dir, idx, t_first, r.t_occ_in, r.t_limit, r.alive, t, t_start);
+    const bool alive = advance_pos(P, M.bitfield, M.coarse, r.origin, r.dir, idx, t_first, r.t_occ_in, r.t_limit, r.alive, t, t_start);
     if (!alive) {
         finish_pixel(P, out, idx, 0.f, 0.f, 0.f, 0.f, 0.f, 0u);
         return;
@@ -363,14 +398,20 @@ __device__ __forceinline__ void init_one_ray(const FrameParams& P, const DeviceM
     }
 }
 
+// 16 x 8 pixel CTA, each warp an 8 x 4 tile so queue neighbours are screen neighbours.  A pixel outside both the screen
+// rectangle of the box around the occupied cells (FrameParams::occ_px, projected on the host) and the mesh's screen rectangle
+// can only be background: integer compares, one store pair, no ray arithmetic - most of a frame in render.py's framing.
 __global__ void __launch_bounds__(128) init_rays_kernel(FrameParams P, DeviceModel M, MeshDevice mesh, const unsigned long long* __restrict__ zbuf, int rows_owned,
                                                         float4* __restrict__ queue, uint32_t* __restrict__ counters, FrameOut out, uint32_t* __restrict__ surf_list) {
-    // 16 x 8 pixel block, each warp an 8 x 4 tile so queue neighbours are screen neighbours
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
     const int ly = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
     if (x >= P.width || ly >= rows_owned) return;
-    init_one_ray(P, M, mesh, zbuf, queue, counters, out, x, shard_row(P, ly), surf_list);
+    const int y = shard_row(P, ly), ms = P.mesh_scale;
+    const bool in_occ = x >= P.occ_px[0] && x < P.occ_px[2] && y >= P.occ_px[1] && y < P.occ_px[3];
+    const bool in_mesh = ms > 0 && P.zb_w > 0 && x * ms >= P.zb_x0 && x * ms < P.zb_x0 + P.zb_w && y * ms >= P.zb_y0 && y * ms < P.zb_y0 + P.zb_h;
+    if (!in_occ && !in_mesh) { finish_pixel(P, out, (uint32_t)x + (uint32_t)P.width * (uint32_t)y, 0.f, 0.f, 0.f, 0.f, 0.f, 0u); return; }
+    init_one_ray(P, M, mesh, zbuf, queue, counters, out, x, y, surf_list);
 }
 
 // dst[0] = src[0] (and dst2[0] = src[0] when given) on the stream, without involving a copy engine: a DMA engine busy with a
@@ -1110,7 +1151,7 @@ __global__ void debug_trace_kernel(FrameParams P, DeviceModel M, const uint32_t*
     const uint32_t x = pix % (uint32_t)P.width, y = pix / (uint32_t)P.width;
     RayInit r = init_ray(P, x, y);
     float t = r.t, t_start;
-    const bool alive = advance_pos(P, M.bitfield, r.origin, r.dir, pix, 0.f, r.t_occ_in, r.t_limit, r.alive, t, t_start);
+    const bool alive = advance_pos(P, M.bitfield, M.coarse, r.origin, r.dir, pix, 0.f, r.t_occ_in, r.t_limit, r.alive, t, t_start);
     float* rr = o_ray + i * 8;
     rr[0] = r.origin.x; rr[1] = r.origin.y; rr[2] = r.origin.z; rr[3] = r.dir.x; rr[4] = r.dir.y; rr[5] = r.dir.z; rr[6] = t; rr[7] = alive ? 1.f : 0.f;
     const V3 idir = v3(1.0f / r.dir.x, 1.0f / r.dir.y, 1.0f / r.dir.z);

@@ -47,6 +47,8 @@ enum DebugFlags : uint32_t {
 void launch_occupancy_build(const uint16_t* d_density_grid_fp16, int n_cascades_present, uint8_t* d_bitfield, float* d_scratch, cudaStream_t s);
 // per cascade: min xyz / max xyz (inclusive, in cells) of the set cells; min = 1 << 20 and max = -1 when the cascade is empty
 void launch_occupancy_bounds(const uint8_t* d_bitfield, int* d_out48, cudaStream_t s);
+// d_occ_scratch: kCoarseRes^3 bytes; d_near_bits: kCoarseRes^2 words (DeviceModel::coarse)
+void launch_coarse_build(const uint8_t* d_bitfield, uint8_t* d_occ_scratch, uint32_t* d_near_bits, cudaStream_t s);
 void launch_mesh_raster(const MeshDevice& mesh, const FrameParams& P, int rows_owned, unsigned long long* d_zbuf, cudaStream_t s);
 void launch_latch_word(const uint32_t* d_src, uint32_t* d_dst, uint32_t* d_dst2, cudaStream_t s);
 // sequence flags of a shared frame target (nmr_gather_*): one word per rank + "consumed" + "error", behind the image

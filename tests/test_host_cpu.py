@@ -108,3 +108,44 @@ def test_shard_rows_partition():
         for world in (1, 2, 3, 4, 8):
             owned = [[y for y in range(H) if (y // 8) % world == r] for r in range(world)]
             assert sorted(sum(owned, [])) == list(range(H))
+
+
+def _lattice_advance_np(t, K):
+    """numpy restatement of device_common.cuh: lattice_advance (same integer arithmetic, same fp32 operations)."""
+    dt0 = np.float32(np.float32(1.73205080757) / np.float32(1024.0))
+    t = np.float32(t)
+    while K > 0:
+        b = int(t.view(np.uint32))
+        e = b & 0xFF800000
+        inc = int((np.uint32(e).view(np.float32) + dt0).view(np.uint32)) - e
+        room = (e | 0x007FFFFF) - b
+        fit = int(np.float32(room) / np.float32(inc)) - 2
+        if K <= fit:
+            return np.uint32(b + K * inc).view(np.float32)
+        if fit > 0:
+            t = np.uint32(b + fit * inc).view(np.float32)
+            K -= fit
+        while True:
+            t = np.float32(t + dt0); K -= 1
+            if not (K > 0 and (int(t.view(np.uint32)) & 0xFF800000) == e):
+                break
+    return t
+
+
+def test_uniform_step_lattice_is_exact():
+    """The first-hit walk's empty-space jumps (device_common.cuh: lattice_advance) rest on `t += dt0` advancing the bit pattern
+    of t by a constant inside a binade: no rounding tie for dt0 = sqrt(3)/1024 in any binade a walk can reach, and the
+    closed form equals the K-fold fp32 loop bit for bit, across binade boundaries."""
+    dt0 = np.float32(np.float32(1.73205080757) / np.float32(1024.0))
+    for e in range(-8, 9):
+        frac = (np.float64(dt0) / 2.0 ** (e - 23)) % 1.0
+        assert abs(frac - 0.5) > 1e-6, (e, frac)
+    rng = np.random.default_rng(7)
+    for _ in range(300):
+        t0 = np.float32(rng.uniform(0.01, 6.0))
+        K = int(rng.integers(1, 1200))
+        t = t0
+        for _ in range(K):
+            t = np.float32(t + dt0)
+        got = _lattice_advance_np(t0, K)
+        assert got.view(np.uint32) == t.view(np.uint32), (t0, K, got, t)
