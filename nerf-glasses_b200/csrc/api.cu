@@ -1042,6 +1042,32 @@ NMR_API int nmr_remove_floaties(nmr_ctx* ctx, int* out_clusters, int64_t* out_ke
 }
 
 // ---- parity probes ------------------------------------------------------------------------------------------------
+namespace {
+int run_probe(nmr_ctx* ctx, int id, int mode, int64_t n, const float* points_world, const float* direction, float* out) {
+    return guarded(ctx, [&]() -> int {
+        Nerf* nf; try { nf = get_nerf(ctx, id); } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); }
+        if (n < 0 || (n > 0 && (!points_world || !out)) || !direction) return fail(ctx, NMR_ERR_INVALID, "null argument");
+        if (n == 0) return NMR_OK;
+        DevBuf<float> d_pts, d_out;
+        d_pts.ensure((size_t)n * 3); d_out.ensure((size_t)n);
+        CK(cudaMemcpyAsync(d_pts.p, points_world, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
+        const FrameParams P = make_params(ctx, *nf, ctx->width, ctx->height, ctx->cam12, 0, true, false);
+        launch_probe(P, nf->dev, d_pts.p, direction, n, mode, d_out.p, ctx->debug_flags, ctx->num_sms, ctx->stream);
+        CK(cudaMemcpyAsync(out, d_out.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaGetLastError());
+        return NMR_OK;
+    });
+}
+}  // namespace
+
+NMR_API int nmr_probe_points(nmr_ctx* ctx, int nerf_id, int64_t n, const float* points_world, const float direction[3], float* out_alpha) {
+    return run_probe(ctx, nerf_id, 0, n, points_world, direction, out_alpha);
+}
+NMR_API int nmr_probe_rays(nmr_ctx* ctx, int nerf_id, int64_t n, const float* origins_world, const float direction[3], float* out_distance) {
+    return run_probe(ctx, nerf_id, 1, n, origins_world, direction, out_distance);
+}
+
 NMR_API int nmr_debug_encode(nmr_ctx* ctx, int id, const float* pos, int64_t n, uint16_t* out) {
     return guarded(ctx, [&]() -> int {
         Nerf* nf; try { nf = get_nerf(ctx, id); } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); }

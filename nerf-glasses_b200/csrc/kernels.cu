@@ -1142,6 +1142,76 @@ void launch_debug_network(const DeviceModel& M, const float* d_pos, const float*
     }
 }
 
+// ---- density probes of the collision tool ---------------------------------------------------------------------
+// NerfTracer::intersects (mode 0, S/ngp/testbed.cu:1891-1935) and NerfTracer::collide + check_collision (mode 1, :1814-1888,
+// :721-782) over the payloads NerfMeshRenderer::collide writes (origin = world point + 0.5, one direction for all,
+// t = t_start = 0, S/nerf_mesh_renderer.cu:1564-1574).  One thread per point / ray; a warpgroup evaluates its 128 samples as
+// one tcgen05 tile per step, exactly like the march kernel.  The reference marches in batches of 8 and checks the batch in
+// order, so "first sample with alpha > 0" does not depend on the batching; a ray that leaves the render box keeps distance 0.
+__global__ void __launch_bounds__(kTile * kGroupsTC) probe_kernel(FrameParams P, DeviceModel M, const float* __restrict__ points_world, float dx, float dy, float dz,
+                                                                  int64_t n, int mode, float* __restrict__ out, uint32_t debug_flags) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    MarchSmemTC& T = *reinterpret_cast<MarchSmemTC*>(smem_raw);
+    TcCtx tc = tc_setup(T, M, debug_flags);
+    char* a_row = reinterpret_cast<char*>(T.act[threadIdx.x / kTile]) + tc.row * 16;
+    const V3 dir = v3(dx, dy, dz);
+    const V3 idir = v3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
+    const V3 dir01 = v3((dir.x + 1.0f) * 0.5f, (dir.y + 1.0f) * 0.5f, (dir.z + 1.0f) * 0.5f);
+    const V3 diag = v3(P.taabb_max[0] - P.taabb_min[0], P.taabb_max[1] - P.taabb_min[1], P.taabb_max[2] - P.taabb_min[2]);
+    const int64_t n_tiles = (n + kTile - 1) / kTile;
+    for (int64_t tile = (int64_t)blockIdx.x * kGroupsTC + threadIdx.x / kTile; tile < n_tiles; tile += (int64_t)gridDim.x * kGroupsTC) {
+        const int64_t i = tile * kTile + tc.row;
+        bool active = i < n;
+        V3 origin = v3(0.5f, 0.5f, 0.5f);
+        if (active) origin = v3(points_world[i * 3] + 0.5f, points_world[i * 3 + 1] + 0.5f, points_world[i * 3 + 2] + 0.5f);
+        float t = 0.f, result = 0.f;
+        while (group_any(tc.bar_id, active)) {
+            bool have = false;
+            V3 wpos = v3(0.f, 0.f, 0.f);
+            float dtw = 0.f;
+            if (active) {
+                if (mode == 0) {
+                    wpos = v3((origin.x - P.taabb_min[0]) / diag.x, (origin.y - P.taabb_min[1]) / diag.y, (origin.z - P.taabb_min[2]) / diag.z);
+                    have = true;
+                } else {
+                    Sample smp;
+                    if (next_sample(P, M.bitfield, origin, dir, idir, 0.f, 0.f, 0.f, 3.402823466e+38f, true, 0x7fffffff, t, smp) == 1) { wpos = smp.pos; dtw = smp.dt_warped; have = true; }
+                    else active = false;       // left the render box without a collision
+                }
+            }
+            if (!group_any(tc.bar_id, have)) continue;
+            if (have) encode_chunks<kEncodeUnroll>(M, wpos, a_row, 2048);
+            float raw[4];
+            network_tc(a_row, tc, dir01, raw);
+            if (have) {
+                const V3 pos = v3(P.taabb_min[0] + wpos.x * diag.x, P.taabb_min[1] + wpos.y * diag.y, P.taabb_min[2] + wpos.z * diag.z);   // unwarp_position
+                if (mode == 0) {
+                    const float dt = min_cone_stepsize();
+                    const float alpha = 1.f - __expf(-act_density(raw[3], P.density_activation) * dt);
+                    const int mip = max(0, mip_from_dt(dt, pos));
+                    if (occupied_at(pos, M.bitfield, (uint32_t)mip)) result = alpha;
+                    active = false;
+                } else {
+                    const float alpha = 1.f - __expf(-act_density(raw[3], P.density_activation) * unwarp_dt(dtw));
+                    if (alpha > 0.f) { const V3 dd = vsub(pos, origin); result = sqrtf(edot(dd, dd)); active = false; }
+                }
+            }
+        }
+        if (i < n) out[i] = result;
+    }
+    tc_teardown(T);
+}
+void launch_probe(const FrameParams& P, const DeviceModel& M, const float* d_points_world, const float dir[3], int64_t n, int mode, float* d_out,
+                  uint32_t debug_flags, int num_sms, cudaStream_t s) {
+    if (n <= 0) return;
+    static bool attr_set_dev[64] = {};
+    int dev = 0; cudaGetDevice(&dev);
+    bool& attr_set = attr_set_dev[dev & 63];
+    if (!attr_set) { cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmemTC)); attr_set = true; }
+    const int64_t per = kTile * kGroupsTC, want = (n + per - 1) / per, cap = (int64_t)num_sms * 2;
+    probe_kernel<<<(unsigned)(want < cap ? want : cap), kTile * kGroupsTC, sizeof(MarchSmemTC), s>>>(P, M, d_points_world, dir[0], dir[1], dir[2], n, mode, d_out, debug_flags);
+}
+
 __global__ void debug_trace_kernel(FrameParams P, DeviceModel M, const uint32_t* __restrict__ pixels, int64_t n_pix, uint32_t max_samples,
                                    float* __restrict__ o_t, uint32_t* __restrict__ o_cell, uint32_t* __restrict__ o_mip, float* __restrict__ o_pos,
                                    uint32_t* __restrict__ o_count, float* __restrict__ o_ray) {

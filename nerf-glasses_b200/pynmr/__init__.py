@@ -83,6 +83,8 @@ def lib():
         "nmr_set_lens": (C.c_int, [vp, C.c_int, C.c_float, C.c_float, fp]),
         "nmr_get_nerf_info": (C.c_int, [vp, C.c_int, C.POINTER(NerfInfo)]),
         "nmr_get_stream": (C.c_int, [vp, C.POINTER(vp)]),
+        "nmr_probe_points": (C.c_int, [vp, C.c_int, C.c_int64, vp, fp, vp]),
+        "nmr_probe_rays": (C.c_int, [vp, C.c_int, C.c_int64, vp, fp, vp]),
         "nmr_gather_create": (C.c_int, [vp, vp, C.POINTER(vp)]),
         "nmr_gather_attach": (C.c_int, [vp, vp]),
         "nmr_gather_detach": (C.c_int, [vp]),
@@ -114,7 +116,7 @@ EXPORTED_SYMBOLS = [
     "nmr_create", "nmr_destroy", "nmr_last_error", "nmr_load_nerf", "nmr_load_mesh", "nmr_set_mesh_transform",
     "nmr_get_mesh_transform", "nmr_set_envmap", "nmr_remove_floaties", "nmr_get_render_aabb", "nmr_set_render_aabb",
     "nmr_get_aabb", "nmr_get_background", "nmr_set_background", "nmr_set_min_transmittance", "nmr_orbit", "nmr_get_camera",
-    "nmr_set_camera", "nmr_frame", "nmr_frame_async", "nmr_read_frame", "nmr_render", "nmr_render_views", "nmr_set_shard", "nmr_set_surface_insertion", "nmr_set_lens", "nmr_debug_lens", "nmr_get_nerf_info", "nmr_gather_create", "nmr_gather_attach", "nmr_gather_detach", "nmr_get_stream",
+    "nmr_set_camera", "nmr_frame", "nmr_frame_async", "nmr_read_frame", "nmr_render", "nmr_render_views", "nmr_set_shard", "nmr_set_surface_insertion", "nmr_set_lens", "nmr_debug_lens", "nmr_get_nerf_info", "nmr_gather_create", "nmr_gather_attach", "nmr_gather_detach", "nmr_get_stream", "nmr_probe_points", "nmr_probe_rays",
     "nmr_get_device_image", "nmr_copy_device_image", "nmr_flush_l2", "nmr_get_stats", "nmr_synchronize", "nmr_host_alloc", "nmr_host_free", "nmr_get_density_bitfield",
     "nmr_set_density_bitfield", "nmr_debug_encode", "nmr_debug_network", "nmr_debug_trace", "nmr_debug_mesh",
     "nmr_debug_last_frame", "nmr_debug_set_flags",
@@ -380,6 +382,20 @@ class Testbed:
         """float32[H, W, 4]; row 0 is the bottom of the picture; sRGB when linear=False (S/python_api.cu:83-111)."""
         out = _pinned_array((height, width, 4))
         self._r._ck(lib().nmr_render(self._r._h, self._id, int(width), int(height), int(spp), int(bool(linear)), _ptr(out)))
+        return out
+
+    def probe_points(self, points_world, direction) -> np.ndarray:
+        """NerfTracer::intersects over world-space points (include/nmr.h: nmr_probe_points) -> alpha per point."""
+        pts = np.ascontiguousarray(points_world, dtype=np.float32).reshape(-1, 3)
+        out = np.zeros(len(pts), dtype=np.float32)
+        self._r._ck(lib().nmr_probe_points(self._r._h, self._id, len(pts), _ptr(pts), _f3(direction), _ptr(out)))
+        return out
+
+    def probe_rays(self, origins_world, direction) -> np.ndarray:
+        """NerfTracer::collide over world-space origins (include/nmr.h: nmr_probe_rays) -> distance to the first dense sample, 0 = none."""
+        pts = np.ascontiguousarray(origins_world, dtype=np.float32).reshape(-1, 3)
+        out = np.zeros(len(pts), dtype=np.float32)
+        self._r._ck(lib().nmr_probe_rays(self._r._h, self._id, len(pts), _ptr(pts), _f3(direction), _ptr(out)))
         return out
 
     def reset_accumulation(self, due_to_camera_movement: bool = False, immediate_redraw: bool = True):

@@ -1108,6 +1108,69 @@ ORC_API void orc_trace_samples(const orc_model* m, const orc_render_params* P, c
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* Density probes of the collision tool                                           */
+/* ------------------------------------------------------------------------------------------ */
+/* NerfTracer::intersects (S/ngp/testbed.cu:1891-1935) with the payloads NerfMeshRenderer::collide writes
+ * (S/nerf_mesh_renderer.cu:1564-1574: origin = world point + 0.5): one network evaluation at the point with the minimum
+ * step; out[i] = 1 - exp(-density * dt) when the cell under the point is occupied, untouched (0) otherwise. */
+ORC_API void orc_probe_points(const orc_model* m, const orc_render_params* P, const float* points_world, const float* dir, int64_t n, float* out) {
+    aabb_t train_aabb; memcpy(&train_aabb.min, P->train_aabb_min, 12); memcpy(&train_aabb.max, P->train_aabb_max, 12);
+    v3 d = v3_make(dir[0], dir[1], dir[2]);
+    v3 dir01 = v3_make((d.x + 1.0f) * 0.5f, (d.y + 1.0f) * 0.5f, (d.z + 1.0f) * 0.5f);
+    v3 diag = sub3(train_aabb.max, train_aabb.min);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t i = 0; i < n; ++i) {
+        v3 origin = v3_make(points_world[i * 3] + 0.5f, points_world[i * 3 + 1] + 0.5f, points_world[i * 3 + 2] + 0.5f);
+        v3 rel = sub3(origin, train_aabb.min);
+        v3 warped = v3_make(rel.x / diag.x, rel.y / diag.y, rel.z / diag.z);
+        uint16_t o4[4];
+        network_eval(m, warped, dir01, o4, NULL);
+        float dt = MIN_CONE_STEPSIZE();
+        float alpha = 1.f - expf(-act_density(h2f(o4[3]), P->density_activation) * dt);
+        v3 pos = v3_make(train_aabb.min.x + warped.x * diag.x, train_aabb.min.y + warped.y * diag.y, train_aabb.min.z + warped.z * diag.z);   /* unwarp_position */
+        int mip = mip_from_dt(dt, pos); if (mip < 0) mip = 0;
+        out[i] = 0.f;
+        if (density_grid_occupied_at(pos, m->bitfield, (uint32_t)mip)) out[i] = alpha;
+    }
+}
+
+/* NerfTracer::collide (S/ngp/testbed.cu:1814-1888) + check_collision (:721-782): rays from origin = world point + 0.5 along
+ * `dir`, t = t_start = 0, batches of 8 samples; out[i] = |sample position - origin| of the first sample whose
+ * alpha = 1 - exp(-density * dt) is positive, 0 for a ray that leaves the render box without one (the reference keeps such
+ * a ray alive - its short batch is generated again and again until MARCH_ITER - and its distance stays at the memset 0). */
+ORC_API void orc_probe_rays(const orc_model* m, const orc_render_params* P, const float* origins_world, const float* dir, int64_t n, float* out) {
+    aabb_t render_aabb; memcpy(&render_aabb.min, P->aabb_min, 12); memcpy(&render_aabb.max, P->aabb_max, 12);
+    aabb_t train_aabb; memcpy(&train_aabb.min, P->train_aabb_min, 12); memcpy(&train_aabb.max, P->train_aabb_max, 12);
+    v3 d = v3_make(dir[0], dir[1], dir[2]);
+    v3 dir01 = v3_make((d.x + 1.0f) * 0.5f, (d.y + 1.0f) * 0.5f, (d.z + 1.0f) * 0.5f);
+    v3 diag = sub3(train_aabb.max, train_aabb.min);
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t i = 0; i < n; ++i) {
+        ray_t r; memset(&r, 0, sizeof(r));
+        r.origin = v3_make(origins_world[i * 3] + 0.5f, origins_world[i * 3 + 1] + 0.5f, origins_world[i * 3 + 2] + 0.5f);
+        r.dir = d; r.alive = 1; r.idx = (uint32_t)i;
+        out[i] = 0.f;
+        int done = 0;
+        while (!done) {
+            sample_t smp[8];
+            uint32_t got = generate_samples(m, P, &render_aabb, &train_aabb, &r, 8, smp, 1);
+            for (uint32_t j = 0; j < got && !done; ++j) {
+                uint16_t o4[4];
+                network_eval(m, smp[j].pos, dir01, o4, NULL);
+                float alpha = 1.f - expf(-act_density(h2f(o4[3]), P->density_activation) * unwarp_dt(smp[j].dt_warped));
+                if (alpha > 0.f) {
+                    v3 pos = v3_make(train_aabb.min.x + smp[j].pos.x * diag.x, train_aabb.min.y + smp[j].pos.y * diag.y, train_aabb.min.z + smp[j].pos.z * diag.z);
+                    v3 dd = sub3(pos, r.origin);
+                    out[i] = sqrtf(edot3(dd, dd));
+                    done = 1;
+                }
+            }
+            if (got < 8) done = 1;      /* left the render box: never collides */
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* Mesh stage  (S/optix/optix_scene.cu:71-85, 120-325; S/optix/optix_util.cuh:23-29;            */
 /*              S/gltf_scene.h:122-127; S/nerf_mesh_renderer.cu:64-100)                         */
 /* OptiX's BVH traversal / triangle test live in the driver: "parity unpinned" at the           */

@@ -74,6 +74,8 @@ def lib():
         "orc_network": (None, [vp, vp, vp, C.c_int64, vp]),
         "orc_render": (C.c_int, [vp, C.POINTER(RenderParams), vp, vp, vp, vp, vp, vp]),
         "orc_accumulate_tonemap": (None, [vp, vp, C.c_int64, C.c_uint32, vp, C.c_int, vp]),
+        "orc_probe_points": (None, [vp, C.POINTER(RenderParams), vp, vp, C.c_int64, vp]),
+        "orc_probe_rays": (None, [vp, C.POINTER(RenderParams), vp, vp, C.c_int64, vp]),
         "orc_trace_samples": (None, [vp, C.POINTER(RenderParams), vp, C.c_int64, C.c_uint32, vp, vp, vp, vp, vp, vp]),
         "orc_mesh_create": (vp, [vp, vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp, vp, vp, C.c_float, C.c_float, vp, vp, C.c_int, C.c_int]),
         "orc_mesh_destroy": (None, [vp]),
@@ -256,6 +258,20 @@ class Model:
             raise RuntimeError("orc_render failed")
         return frame, depth, ns, {"alive_after_first_hit": int(stats[0]), "samples": int(stats[1]),
                                  "iterations": int(stats[2]), "rays_hit": int(stats[3])}
+
+    def probe_points(self, P: RenderParams, points_world: np.ndarray, direction) -> np.ndarray:
+        """NerfTracer::intersects: alpha of one minimum step at each point, 0 where the cell is not occupied."""
+        pts = np.ascontiguousarray(points_world, dtype=np.float32).reshape(-1, 3); d = np.ascontiguousarray(direction, dtype=np.float32)
+        out = np.zeros(len(pts), dtype=np.float32)
+        lib().orc_probe_points(self.h, C.byref(P), _p(pts), _p(d), len(pts), _p(out))
+        return out
+
+    def probe_rays(self, P: RenderParams, origins_world: np.ndarray, direction) -> np.ndarray:
+        """NerfTracer::collide + check_collision: distance to the first sample with positive alpha, 0 when there is none."""
+        pts = np.ascontiguousarray(origins_world, dtype=np.float32).reshape(-1, 3); d = np.ascontiguousarray(direction, dtype=np.float32)
+        out = np.zeros(len(pts), dtype=np.float32)
+        lib().orc_probe_rays(self.h, C.byref(P), _p(pts), _p(d), len(pts), _p(out))
+        return out
 
     def trace_samples(self, P: RenderParams, pixels: np.ndarray, max_samples: int):
         pixels = np.ascontiguousarray(pixels, dtype=np.uint32); n = pixels.size

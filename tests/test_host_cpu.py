@@ -149,3 +149,29 @@ def test_uniform_step_lattice_is_exact():
             t = np.float32(t + dt0)
         got = _lattice_advance_np(t0, K)
         assert got.view(np.uint32) == t.view(np.uint32), (t0, K, got, t)
+
+
+def test_oracle_probes_are_consistent(small_snapshot):
+    """Oracle restatement of the collision tool's probes (NerfTracer::intersects / collide): a collision lies in an occupied
+    cell of the density grid, a ray outside the render box reports 0, and a point probe is positive only on occupied cells."""
+    from oracle import oracle as O
+    _, snap = small_snapshot
+    m = O.Model.from_snapshot(snap)
+    P = m.params_struct(64, 64, O.OrbitCamera(64, 64).matrix(), aabb_min=snap["render_aabb_min"], aabb_max=snap["render_aabb_max"])
+    rng = np.random.default_rng(3)
+    n = 512
+    org = np.stack([rng.uniform(-0.3, 0.3, n), np.full(n, 0.45), rng.uniform(-0.3, 0.3, n)], axis=1).astype(np.float32)
+    d = np.array([0.0, -1.0, 0.0], dtype=np.float32)
+    dist = m.probe_rays(P, org, d)
+    hit = dist > 0
+    assert 50 < hit.sum() < n - 50
+    bits = m.bitfield()
+    pos = org[hit] + 0.5 + d[None, :] * dist[hit, None]
+    cells = np.array([O.lib().orc_cascaded_grid_idx_at(np.ascontiguousarray(q, dtype=np.float32).ctypes.data_as(C.c_void_p), 0) for q in pos], dtype=np.uint32)
+    assert np.all((bits[cells // 8] >> (cells % 8)) & 1)
+    assert np.array_equal(m.probe_rays(P, np.array([[5, 5, 5], [-3, 0, 0]], np.float32), d), np.zeros(2, np.float32))
+    pts = rng.uniform(-0.35, 0.35, size=(800, 3)).astype(np.float32)
+    alpha = m.probe_points(P, pts, d)
+    pc = np.array([O.lib().orc_cascaded_grid_idx_at(np.ascontiguousarray(q + 0.5, dtype=np.float32).ctypes.data_as(C.c_void_p), 0) for q in pts], dtype=np.uint32)
+    occ = ((bits[pc // 8] >> (pc % 8)) & 1).astype(bool)
+    assert np.all(alpha[~occ] == 0) and (alpha[occ] > 0).mean() > 0.95
