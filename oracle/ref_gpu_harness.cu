@@ -204,6 +204,41 @@ REF_API int refgpu_encode(void* h, const float* pos, int64_t n, uint16_t* out_n_
     });
 }
 
+// The collision tool's density probes exactly as NerfMeshRenderer::collide drives them (S/nerf_mesh_renderer.cu:1548-1574,
+// 1657-1694): payloads memset to zero, alive, one direction, origin = world point + 0.5, written into the tracer's ray buffer;
+// mode 0 = NerfTracer::intersects (S/ngp/testbed.cu:1891-1935), mode 1 = NerfTracer::collide (:1814-1888).  The reference
+// relies on a previous frame having sized the tracer's buffers; the harness calls its enlarge() for n rays instead.
+REF_API int refgpu_probe(void* h, int mode, const float* points_world, const float* dir, int64_t n, float* out) {
+    RefCtx* r = static_cast<RefCtx*>(h);
+    return guarded(r, [&] {
+        Testbed& t = *r->tb;
+        cudaStream_t stream = t.m_stream.get();
+        t.m_nerf.tracer.enlarge((size_t)n, t.m_network->padded_output_width(), t.m_nerf_network->n_extra_dims(), stream);
+        std::vector<NerfPayload> payloads((size_t)n);
+        std::memset((void*)payloads.data(), 0, sizeof(NerfPayload) * (size_t)n);
+        for (int64_t i = 0; i < n; ++i) {
+            payloads[(size_t)i].alive = true;
+            payloads[(size_t)i].dir = {dir[0], dir[1], dir[2]};
+            payloads[(size_t)i].idx = (uint32_t)i;
+            payloads[(size_t)i].origin = {points_world[i * 3] + 0.5f, points_world[i * 3 + 1] + 0.5f, points_world[i * 3 + 2] + 0.5f};
+        }
+        CUDA_CHECK_THROW(cudaMemcpy(t.m_nerf.tracer.rays_init().payload, payloads.data(), sizeof(NerfPayload) * (size_t)n, cudaMemcpyHostToDevice));
+        GPUMemory<float> dist((size_t)n);
+        dist.memset(0);
+        if (mode == 0)
+            t.m_nerf.tracer.intersects((int)n, *t.m_nerf_network, t.m_aabb, t.get_inference_extra_dims(stream), t.m_nerf.density_activation,
+                                       t.m_nerf.density_grid_bitfield.data(), dist.data(), stream);
+        else
+            t.m_nerf.tracer.collide((int)n, *t.m_nerf_network, t.m_render_aabb, t.m_render_aabb_to_local, t.m_aabb, t.m_nerf.cone_angle_constant,
+                                    t.m_nerf.density_grid_bitfield.data(), t.get_inference_extra_dims(stream), t.m_nerf.density_activation, dist.data(), stream);
+        CUDA_CHECK_THROW(cudaStreamSynchronize(stream));
+        std::vector<float> hst((size_t)n);
+        dist.copy_to_host(hst);
+        std::memcpy(out, hst.data(), sizeof(float) * (size_t)n);
+        t.m_nerf.tracer.clear();
+    });
+}
+
 // Ray set-up + first-hit DDA (init_rays_with_payload_kernel_nerf + advance_pos_nerf, S/ngp/testbed.cu:355-537) for every
 // pixel, then generate_next_nerf_network_inputs (S/ngp/testbed.cu:564-633) with n_steps = 1 repeated max_samples times:
 // the occupied-sample sequence of each ray with the network out of the loop.

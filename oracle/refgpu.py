@@ -55,6 +55,8 @@ def lib():
         L.refgpu_network.argtypes = [vp, vp, vp, C.c_int64, vp]
         L.refgpu_encode.argtypes = [vp, vp, C.c_int64, vp]
         L.refgpu_trace.argtypes = [vp, vp, C.c_int, C.c_int, C.c_uint32, vp, vp, C.c_uint32, vp, vp, vp, vp, vp]
+        if hasattr(L, "refgpu_probe"):
+            L.refgpu_probe.argtypes = [vp, C.c_int, vp, vp, C.c_int64, vp]
         L.refgpu_render.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp]
         _lib = L
     return _lib
@@ -120,6 +122,13 @@ class ReferenceRenderer:
         out = np.zeros((pos.shape[0], 16), dtype=np.uint16)
         self._ck(self._L.refgpu_network(self._h, _p(pos), _p(d), pos.shape[0], _p(out)))
         return out.view(np.float16)
+
+    def probe(self, mode: int, points_world: np.ndarray, direction) -> np.ndarray:
+        """The reference's NerfTracer::intersects (mode 0) / collide (mode 1) over world-space points, as NerfMeshRenderer::collide calls them."""
+        pts = np.ascontiguousarray(points_world, dtype=np.float32).reshape(-1, 3); d = np.ascontiguousarray(direction, dtype=np.float32)
+        out = np.zeros(len(pts), np.float32)
+        self._ck(self._L.refgpu_probe(self._h, int(mode), _p(pts), _p(d), len(pts), _p(out)))
+        return out
 
     def trace(self, cam12, W, H, max_samples, spp_index=0, surf=None, ts=None):
         cam12 = np.ascontiguousarray(cam12, dtype=np.float32)

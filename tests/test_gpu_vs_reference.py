@@ -145,3 +145,29 @@ def test_hybrid_close_up_vs_reference(pair):
     r.set_surface_insertion(pynmr.NerfMeshRenderer.SURFACE_EXACT)
     exact = np.asarray(nerf.render(w, h, 1, linear=False)).copy()
     assert _cmp(exact, want)[2] > frac
+
+
+def test_collision_probes_vs_reference(pair):
+    """nmr_probe_points / nmr_probe_rays vs the reference's own NerfTracer::intersects / collide (driven the way
+    NerfMeshRenderer::collide drives them) on the same GPU and snapshot.  The reference binary contracts FMAs, so a ray may
+    take its first dense sample one step apart: distances agree to a step on all but a handful of rays, hit masks likewise."""
+    ref, nerf = pair["ref"], pair["nerf"]
+    rng = np.random.default_rng(21)
+    pts = rng.uniform(-0.35, 0.35, size=(4000, 3)).astype(np.float32)
+    d = np.array([0.0, -1.0, 0.0], dtype=np.float32)
+    a_ref, a_got = ref.probe(0, pts, d), nerf.probe_points(pts, d)
+    assert (a_ref > 0).sum() > 200
+    assert np.mean((a_ref > 0) == (a_got > 0)) >= 0.999
+    both = (a_ref > 0) & (a_got > 0)
+    assert np.max(np.abs(a_ref[both] - a_got[both])) <= 5e-3
+    n = 2048
+    org = np.stack([rng.uniform(-0.3, 0.3, n), np.full(n, 0.45), rng.uniform(-0.3, 0.3, n)], axis=1).astype(np.float32)
+    for dd in ([0.0, -1.0, 0.0], [0.3, -0.9, 0.2]):
+        dd = np.asarray(dd, dtype=np.float32)
+        d_ref, d_got = ref.probe(1, org, dd), nerf.probe_rays(org, dd)
+        assert (d_ref > 0).sum() > 100 and (d_ref == 0).sum() > 100
+        assert np.mean((d_ref > 0) == (d_got > 0)) >= 0.995
+        both = (d_ref > 0) & (d_got > 0)
+        step = 1.7320508 / 1024 * np.linalg.norm(dd)
+        assert np.mean(np.abs(d_ref[both] - d_got[both]) <= 1.01 * step) >= 0.995
+        assert np.median(np.abs(d_ref[both] - d_got[both])) <= 1e-6
