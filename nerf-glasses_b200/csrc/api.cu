@@ -57,6 +57,7 @@ struct Nerf {
     uint64_t n_params = 0;
     float background[4] = {1.f, 1.f, 1.f, 1.f};     // S/ngp/testbed.cuh:525
     float min_transmittance = 0.01f;                // S/ngp/testbed.cuh:484
+    int tonemap_curve = 0;                          // Testbed.tonemap_curve (ETonemapCurve), Identity by default
 };
 
 struct Mesh {
@@ -353,10 +354,14 @@ FrameParams make_params(nmr_ctx* ctx, const Nerf& n, int W, int H, const float* 
         P.background_linear[k] = sv <= 0.04045f ? sv / 12.92f : powf((sv + 0.055f) / 1.055f, 2.4f);
     }
     P.to_srgb = to_srgb ? 1 : 0;
+    P.tonemap_curve = n.tonemap_curve;
     {   // accumulate_kernel + tonemap_kernel of an empty pixel (S/ngp/render_buffer.cu:232-267, 537-566)
         const float w = (1.f - 0.f) * n.background[3];
+        float c3[3];
+        for (int k = 0; k < 3; ++k) c3[k] = 0.f + P.background_linear[k] * w;
+        tonemap_curve_apply(c3[0], c3[1], c3[2], n.tonemap_curve);
         for (int k = 0; k < 3; ++k) {
-            float c = 0.f + P.background_linear[k] * w;
+            float c = c3[k];
             if (to_srgb) { c = c < 0.0031308f ? 12.92f * c : 1.055f * powf(c, 0.41666f) - 0.055f; c = std::min(std::max(c, 0.f), 1.f); }
             P.background_out[k] = c;
         }
@@ -717,6 +722,18 @@ NMR_API int nmr_get_background(nmr_ctx* ctx, int id, float rgba[4]) {
 }
 NMR_API int nmr_set_background(nmr_ctx* ctx, int id, const float rgba[4]) {
     return guarded(ctx, [&]() -> int { try { std::memcpy(get_nerf(ctx, id)->background, rgba, 16); return NMR_OK; } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); } });
+}
+NMR_API int nmr_set_tonemap_curve(nmr_ctx* ctx, int id, int curve) {
+    return guarded(ctx, [&]() -> int {
+        if (curve < 0 || curve > 3) return fail(ctx, NMR_ERR_INVALID, "tonemap curve must be 0 (Identity), 1 (ACES), 2 (Hable) or 3 (Reinhard)");
+        try { get_nerf(ctx, id)->tonemap_curve = curve; ctx->surf.spp = 0; return NMR_OK; } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); }
+    });
+}
+NMR_API int nmr_get_tonemap_curve(nmr_ctx* ctx, int id, int* out_curve) {
+    return guarded(ctx, [&]() -> int {
+        if (!out_curve) return fail(ctx, NMR_ERR_INVALID, "out_curve is null");
+        try { *out_curve = get_nerf(ctx, id)->tonemap_curve; return NMR_OK; } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); }
+    });
 }
 NMR_API int nmr_set_min_transmittance(nmr_ctx* ctx, int id, float v) {
     return guarded(ctx, [&]() -> int { try { get_nerf(ctx, id)->min_transmittance = v; return NMR_OK; } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); } });

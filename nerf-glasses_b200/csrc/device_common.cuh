@@ -59,6 +59,7 @@ struct FrameParams {
     float background_linear[3];       // srgb_to_linear(background), evaluated on the host
     float background_out[4];          // displayed value of a pixel that hit nothing (accumulate + tonemap of zero), see finish_pixel
     int to_srgb;
+    int tonemap_curve;                // Testbed.tonemap_curve: 0 Identity, 1 ACES, 2 Hable, 3 Reinhard (S/ngp/render_buffer.cu:269-325)
     int shard_rank, shard_world, shard_band;
     int row0;                         // unsharded contexts: first image row of this pass (nmr_render's row ranges), normally 0
     int mesh_scale;                   // 0: no mesh stage
@@ -517,6 +518,34 @@ __device__ __forceinline__ float act_rgb(float v, int a) {
 __device__ __forceinline__ float fast_pow(float x, float y) { return exp2f(y * __log2f(x)); }
 __device__ __forceinline__ float linear_to_srgb(float l) { return l < 0.0031308f ? 12.92f * l : 1.055f * fast_pow(l, 0.41666f) - 0.055f; }
 __device__ __forceinline__ float srgb_to_linear(float s) { return s <= 0.04045f ? s / 12.92f : fast_pow((s + 0.055f) / 1.055f, 2.4f); }
+
+// tonemap(x, curve) (S/ngp/render_buffer.cu:269-325); host and device (make_params evaluates the background pixel with it)
+__host__ __device__ __forceinline__ void tonemap_curve_apply(float& r, float& g, float& b, int curve) {
+    if (curve == 0) return;
+    r = fmaxf(r, 0.f); g = fmaxf(g, 0.f); b = fmaxf(b, 0.f);
+    float k0, k1, k2, k3, k4, k5;
+    if (curve == 1) {
+        k0 = 0.6f * 0.6f * 2.51f; k1 = 0.6f * 0.03f; k2 = 0.0f; k3 = 0.6f * 0.6f * 2.43f; k4 = 0.6f * 0.59f; k5 = 0.14f;
+    } else if (curve == 2) {
+        const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
+        k0 = A * F - A * E; k1 = C * B * F - B * E; k2 = 0.0f; k3 = A * F; k4 = B * F; k5 = D * F * F;
+        const float W = 11.2f;
+        const float nom = k0 * (W * W) + k1 * W + k2, denom = k3 * (W * W) + k4 * W + k5;
+        const float white_scale = denom / nom;
+        k0 = 4.0f * k0 * white_scale; k1 = 2.0f * k1 * white_scale; k2 = k2 * white_scale; k3 = 4.0f * k3; k4 = 2.0f * k4;
+    } else {
+        const float Y = 0.2126f * r + (0.7152f * g + 0.0722f * b);
+        const float s = 1.f / (Y + 1.0f);
+        r = r * s; g = g * s; b = b * s;
+        return;
+    }
+    float* c[3] = {&r, &g, &b};
+    for (int k = 0; k < 3; ++k) {
+        const float x = *c[k], sq = x * x;
+        const float nom = sq * k0 + k1 * x + k2, denom = k3 * sq + k4 * x + k5;
+        *c[k] = nom / denom;
+    }
+}
 
 // ---- mesh stage: Moeller-Trumbore with back-face culling + the reference's PBR shading ------------------------
 // (S/optix/optix_scene.cu:71-85, 182-325; OptiX's own triangle test is not available: see DESIGN.md)

@@ -320,6 +320,7 @@ __device__ __forceinline__ void finish_pixel(const FrameParams& P, const FrameOu
     float cg = acc.y + P.background_linear[1] * w;
     float cb = acc.z + P.background_linear[2] * w;
     float ca = acc.w + w;
+    tonemap_curve_apply(cr, cg, cb, P.tonemap_curve);
     if (P.to_srgb) {
         cr = fminf(fmaxf(linear_to_srgb(cr), 0.f), 1.f); cg = fminf(fmaxf(linear_to_srgb(cg), 0.f), 1.f);
         cb = fminf(fmaxf(linear_to_srgb(cb), 0.f), 1.f); ca = fminf(fmaxf(ca, 0.f), 1.f);

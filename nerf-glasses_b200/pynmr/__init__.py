@@ -18,6 +18,7 @@ sm_100 GPU and raises RuntimeError otherwise.
 from __future__ import annotations
 
 import ctypes as C
+import enum
 import os
 import sys
 import weakref
@@ -83,6 +84,8 @@ def lib():
         "nmr_set_lens": (C.c_int, [vp, C.c_int, C.c_float, C.c_float, fp]),
         "nmr_get_nerf_info": (C.c_int, [vp, C.c_int, C.POINTER(NerfInfo)]),
         "nmr_get_stream": (C.c_int, [vp, C.POINTER(vp)]),
+        "nmr_set_tonemap_curve": (C.c_int, [vp, C.c_int, C.c_int]),
+        "nmr_get_tonemap_curve": (C.c_int, [vp, C.c_int, ip]),
         "nmr_probe_points": (C.c_int, [vp, C.c_int, C.c_int64, vp, fp, vp]),
         "nmr_probe_rays": (C.c_int, [vp, C.c_int, C.c_int64, vp, fp, vp]),
         "nmr_gather_create": (C.c_int, [vp, vp, C.POINTER(vp)]),
@@ -116,7 +119,7 @@ EXPORTED_SYMBOLS = [
     "nmr_create", "nmr_destroy", "nmr_last_error", "nmr_load_nerf", "nmr_load_mesh", "nmr_set_mesh_transform",
     "nmr_get_mesh_transform", "nmr_set_envmap", "nmr_remove_floaties", "nmr_get_render_aabb", "nmr_set_render_aabb",
     "nmr_get_aabb", "nmr_get_background", "nmr_set_background", "nmr_set_min_transmittance", "nmr_orbit", "nmr_get_camera",
-    "nmr_set_camera", "nmr_frame", "nmr_frame_async", "nmr_read_frame", "nmr_render", "nmr_render_views", "nmr_set_shard", "nmr_set_surface_insertion", "nmr_set_lens", "nmr_debug_lens", "nmr_get_nerf_info", "nmr_gather_create", "nmr_gather_attach", "nmr_gather_detach", "nmr_get_stream", "nmr_probe_points", "nmr_probe_rays",
+    "nmr_set_camera", "nmr_frame", "nmr_frame_async", "nmr_read_frame", "nmr_render", "nmr_render_views", "nmr_set_shard", "nmr_set_surface_insertion", "nmr_set_lens", "nmr_debug_lens", "nmr_get_nerf_info", "nmr_gather_create", "nmr_gather_attach", "nmr_gather_detach", "nmr_get_stream", "nmr_probe_points", "nmr_probe_rays", "nmr_set_tonemap_curve", "nmr_get_tonemap_curve",
     "nmr_get_device_image", "nmr_copy_device_image", "nmr_flush_l2", "nmr_get_stats", "nmr_synchronize", "nmr_host_alloc", "nmr_host_free", "nmr_get_density_bitfield",
     "nmr_set_density_bitfield", "nmr_debug_encode", "nmr_debug_network", "nmr_debug_trace", "nmr_debug_mesh",
     "nmr_debug_last_frame", "nmr_debug_set_flags",
@@ -297,6 +300,14 @@ class _NerfSettings:
         self._tb._r._ck(lib().nmr_set_min_transmittance(self._tb._r._h, self._tb._id, float(v)))
 
 
+class TonemapCurve(enum.IntEnum):
+    """pynmr.TonemapCurve (S/python_api.cu:228-232)."""
+    Identity = 0
+    ACES = 1
+    Hable = 2
+    Reinhard = 3
+
+
 class Testbed:
     """ngp::Testbed as returned by NerfMeshRenderer.load_nerf (S/python_api.cu:299-496)."""
 
@@ -339,6 +350,16 @@ class Testbed:
     @background_color.setter
     def background_color(self, rgba):
         self._r._ck(lib().nmr_set_background(self._r._h, self._id, _f3(rgba)))
+
+    @property
+    def tonemap_curve(self) -> "TonemapCurve":
+        c = C.c_int()
+        self._r._ck(lib().nmr_get_tonemap_curve(self._r._h, self._id, C.byref(c)))
+        return TonemapCurve(c.value)
+
+    @tonemap_curve.setter
+    def tonemap_curve(self, curve):
+        self._r._ck(lib().nmr_set_tonemap_curve(self._r._h, self._id, int(curve)))
 
     # -- read-only snapshot facts and the camera (S/python_api.cu:301-496: secondary properties of the reference's Testbed)
     def _info(self) -> NerfInfo:

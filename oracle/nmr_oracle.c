@@ -1058,8 +1058,37 @@ static int render_impl(const orc_model* m, const orc_render_params* P, const flo
 
 /* accumulate_kernel + tonemap_kernel (S/ngp/render_buffer.cu:232-267, 327-346, 537-566), colour space Linear,
  * tonemap curve Identity, exposure 0.  accum is updated in place; out gets the displayed float4 image. */
-ORC_API void orc_accumulate_tonemap(const float* frame, float* accum, int64_t n_pixels, uint32_t spp_index,
-                                    const float* background_rgba, int to_srgb, float* out) {
+/* tonemap(x, curve) (S/ngp/render_buffer.cu:269-325): 0 Identity, 1 ACES, 2 Hable, 3 Reinhard */
+static void tonemap_curve(float c[3], int curve) {
+    if (curve == 0) return;
+    for (int k = 0; k < 3; ++k) c[k] = fmaxf(c[k], 0.f);
+    float k0, k1, k2, k3, k4, k5;
+    if (curve == 1) {
+        k0 = 0.6f * 0.6f * 2.51f; k1 = 0.6f * 0.03f; k2 = 0.0f; k3 = 0.6f * 0.6f * 2.43f; k4 = 0.6f * 0.59f; k5 = 0.14f;
+    } else if (curve == 2) {
+        const float A = 0.15f, B = 0.50f, Cc = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
+        k0 = A * F - A * E; k1 = Cc * B * F - B * E; k2 = 0.0f; k3 = A * F; k4 = B * F; k5 = D * F * F;
+        const float W = 11.2f;
+        const float nom = k0 * (W * W) + k1 * W + k2, denom = k3 * (W * W) + k4 * W + k5;
+        const float white_scale = denom / nom;
+        k0 = 4.0f * k0 * white_scale; k1 = 2.0f * k1 * white_scale; k2 = k2 * white_scale; k3 = 4.0f * k3; k4 = 2.0f * k4;
+    } else {
+        const float Y = 0.2126f * c[0] + (0.7152f * c[1] + 0.0722f * c[2]);   /* Eigen 3-element dot */
+        const float s = 1.f / (Y + 1.0f);
+        for (int k = 0; k < 3; ++k) c[k] = c[k] * s;
+        return;
+    }
+    for (int k = 0; k < 3; ++k) {
+        const float sq = c[k] * c[k];
+        const float nom = sq * k0 + k1 * c[k] + k2, denom = k3 * sq + k4 * c[k] + k5;
+        c[k] = nom / denom;
+    }
+}
+
+/* accumulate_kernel + tonemap_kernel (S/ngp/render_buffer.cu:232-267, 327-346, 537-566); exposure 0 (m_exposure is not
+ * reachable from the Python API); tonemap_curve = Testbed.tonemap_curve */
+ORC_API void orc_accumulate_tonemap_curve(const float* frame, float* accum, int64_t n_pixels, uint32_t spp_index,
+                                          const float* background_rgba, int to_srgb, int curve, float* out) {
     const float sc = (float)spp_index;
     float bg[4] = { srgb_to_linear(background_rgba[0]), srgb_to_linear(background_rgba[1]), srgb_to_linear(background_rgba[2]), background_rgba[3] };
     const float expo = powf(2.0f, 0.0f);
@@ -1071,10 +1100,16 @@ ORC_API void orc_accumulate_tonemap(const float* frame, float* accum, int64_t n_
         float col[4] = { a[0], a[1], a[2], a[3] };
         float weight = (1 - col[3]) * bg[3];
         col[0] += bg[0] * weight; col[1] += bg[1] * weight; col[2] += bg[2] * weight; col[3] += weight;
-        for (int k = 0; k < 3; ++k) { col[k] *= expo; if (to_srgb) col[k] = linear_to_srgb(col[k]); }
+        for (int k = 0; k < 3; ++k) col[k] *= expo;
+        tonemap_curve(col, curve);
+        if (to_srgb) for (int k = 0; k < 3; ++k) col[k] = linear_to_srgb(col[k]);
         if (to_srgb) for (int k = 0; k < 4; ++k) col[k] = fminf(fmaxf(col[k], 0.0f), 1.0f);
         memcpy(out + i * 4, col, 16);
     }
+}
+ORC_API void orc_accumulate_tonemap(const float* frame, float* accum, int64_t n_pixels, uint32_t spp_index,
+                                    const float* background_rgba, int to_srgb, float* out) {
+    orc_accumulate_tonemap_curve(frame, accum, n_pixels, spp_index, background_rgba, to_srgb, 0, out);
 }
 
 /* Traversal trace for bit-exactness tests: the first max_samples occupied samples of each listed pixel

@@ -74,6 +74,7 @@ def lib():
         "orc_network": (None, [vp, vp, vp, C.c_int64, vp]),
         "orc_render": (C.c_int, [vp, C.POINTER(RenderParams), vp, vp, vp, vp, vp, vp]),
         "orc_accumulate_tonemap": (None, [vp, vp, C.c_int64, C.c_uint32, vp, C.c_int, vp]),
+        "orc_accumulate_tonemap_curve": (None, [vp, vp, C.c_int64, C.c_uint32, vp, C.c_int, C.c_int, vp]),
         "orc_probe_points": (None, [vp, C.POINTER(RenderParams), vp, vp, C.c_int64, vp]),
         "orc_probe_rays": (None, [vp, C.POINTER(RenderParams), vp, vp, C.c_int64, vp]),
         "orc_trace_samples": (None, [vp, C.POINTER(RenderParams), vp, C.c_int64, C.c_uint32, vp, vp, vp, vp, vp, vp]),
@@ -282,14 +283,14 @@ class Model:
         return {"t": t, "cell": cell, "mip": mip, "pos": pos, "count": cnt, "ray": ray}
 
 
-def accumulate_tonemap(frame: np.ndarray, accum: np.ndarray | None, spp_index: int, background=(1.0, 1.0, 1.0, 1.0), to_srgb=True):
+def accumulate_tonemap(frame: np.ndarray, accum: np.ndarray | None, spp_index: int, background=(1.0, 1.0, 1.0, 1.0), to_srgb=True, curve: int = 0):
     """-> (image f32[H,W,4], accum).  accum None starts a new accumulation."""
     frame = np.ascontiguousarray(frame, dtype=np.float32)
     if accum is None:
         accum = np.zeros_like(frame)
     out = np.empty_like(frame)
     bg = np.asarray(background, dtype=np.float32)
-    lib().orc_accumulate_tonemap(_p(frame), _p(accum), frame.shape[0] * frame.shape[1], spp_index, _p(bg), int(to_srgb), _p(out))
+    lib().orc_accumulate_tonemap_curve(_p(frame), _p(accum), frame.shape[0] * frame.shape[1], spp_index, _p(bg), int(to_srgb), int(curve), _p(out))
     return out, accum
 
 

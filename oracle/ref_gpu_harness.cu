@@ -125,6 +125,11 @@ REF_API int refgpu_get_render_aabb(void* h, float* mn, float* mx) {
     for (int k = 0; k < 3; ++k) { mn[k] = r->tb->m_render_aabb.min[k]; mx[k] = r->tb->m_render_aabb.max[k]; }
     return 0;
 }
+// Testbed.tonemap_curve (S/python_api.cu:448): ETonemapCurve 0 Identity, 1 ACES, 2 Hable, 3 Reinhard
+REF_API int refgpu_set_tonemap_curve(void* h, int curve) {
+    static_cast<RefCtx*>(h)->tb->m_tonemap_curve = (ETonemapCurve)curve;
+    return 0;
+}
 REF_API int refgpu_set_background(void* h, const float* rgba) {
     static_cast<RefCtx*>(h)->tb->m_background_color = Array4f{rgba[0], rgba[1], rgba[2], rgba[3]};
     return 0;

@@ -55,6 +55,8 @@ def lib():
         L.refgpu_network.argtypes = [vp, vp, vp, C.c_int64, vp]
         L.refgpu_encode.argtypes = [vp, vp, C.c_int64, vp]
         L.refgpu_trace.argtypes = [vp, vp, C.c_int, C.c_int, C.c_uint32, vp, vp, C.c_uint32, vp, vp, vp, vp, vp]
+        if hasattr(L, "refgpu_set_tonemap_curve"):
+            L.refgpu_set_tonemap_curve.argtypes = [vp, C.c_int]
         if hasattr(L, "refgpu_probe"):
             L.refgpu_probe.argtypes = [vp, C.c_int, vp, vp, C.c_int64, vp]
         L.refgpu_render.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp]
@@ -122,6 +124,9 @@ class ReferenceRenderer:
         out = np.zeros((pos.shape[0], 16), dtype=np.uint16)
         self._ck(self._L.refgpu_network(self._h, _p(pos), _p(d), pos.shape[0], _p(out)))
         return out.view(np.float16)
+
+    def set_tonemap_curve(self, curve: int):
+        self._ck(self._L.refgpu_set_tonemap_curve(self._h, int(curve)))
 
     def probe(self, mode: int, points_world: np.ndarray, direction) -> np.ndarray:
         """The reference's NerfTracer::intersects (mode 0) / collide (mode 1) over world-space points, as NerfMeshRenderer::collide calls them."""

@@ -424,3 +424,24 @@ def test_edge_cases(small_snapshot, glasses_gltf, tmp_path):
     img = np.asarray(nerf3.render(96, 54, 1, linear=False)).copy()
     want = H.oracle_scene(snap, 96, 54, cam12(r3))[0]
     assert np.max(np.abs(img - want)) <= PIX_TOL
+
+
+@pytest.mark.parametrize("curve", [1, 2, 3], ids=["ACES", "Hable", "Reinhard"])
+def test_tonemap_curves_match_oracle(scene, curve):
+    """Testbed.tonemap_curve: the displayed image equals the oracle's accumulate + tonemap of the same linear frame."""
+    from oracle import oracle as O
+    r, nerf = scene["r"], scene["nerf"]
+    try:
+        nerf.tonemap_curve = curve
+        img = np.asarray(nerf.render(W, HH, 1, linear=False)).copy()
+        fr, _, _ = H.debug_last_frame(r, W, HH)
+        want, _ = O.accumulate_tonemap(fr, None, 0, to_srgb=True, curve=curve)
+        assert np.max(np.abs(img - want)) <= 1e-5
+        lin = np.asarray(nerf.render(W, HH, 1, linear=True)).copy()
+        fr, _, _ = H.debug_last_frame(r, W, HH)
+        want_lin, _ = O.accumulate_tonemap(fr, None, 0, to_srgb=False, curve=curve)
+        assert np.max(np.abs(lin - want_lin)) <= 1e-5
+        with pytest.raises(RuntimeError):
+            nerf.tonemap_curve = 7
+    finally:
+        nerf.tonemap_curve = 0

@@ -171,3 +171,26 @@ def test_collision_probes_vs_reference(pair):
         step = 1.7320508 / 1024 * np.linalg.norm(dd)
         assert np.mean(np.abs(d_ref[both] - d_got[both]) <= 1.01 * step) >= 0.995
         assert np.median(np.abs(d_ref[both] - d_got[both])) <= 1e-6
+
+
+@pytest.mark.parametrize("curve", [1, 2, 3], ids=["ACES", "Hable", "Reinhard"])
+def test_tonemap_curves_vs_reference(pair, curve):
+    """Testbed.tonemap_curve (tonemap_kernel's ACES / Hable / Reinhard branches, S/ngp/render_buffer.cu:269-325) vs the
+    reference's own render on the same GPU."""
+    ref, r, nerf = pair["ref"], pair["r"], pair["nerf"]
+    try:
+        ref.set_tonemap_curve(curve)
+        nerf.tonemap_curve = curve
+        assert int(nerf.tonemap_curve) == curve
+        # (an earlier test may have loaded the glasses into this renderer: both sides get the same mesh hand-off buffers)
+        _, _, _, surf, ts = H.debug_mesh(r, W, HH)
+        want, _ = ref.render(pair["cam12"], W, HH, 1, False, surf=surf, ts=ts)
+        got = np.asarray(nerf.render(W, HH, 1, linear=False))
+        mx, ps, frac = _cmp(got, want)
+        assert ps >= 45.0 and frac <= 0.004, (mx, ps, frac)
+        ref.set_tonemap_curve(0)
+        ident, _ = ref.render(pair["cam12"], W, HH, 1, False, surf=surf, ts=ts)
+        assert np.abs(ident - want).max() > 0.05          # the curve does change the picture
+    finally:
+        ref.set_tonemap_curve(0)
+        nerf.tonemap_curve = 0
