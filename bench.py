@@ -446,9 +446,19 @@ def main():
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
+    # stdout carries exactly ONE line, the JSON: whatever libraries print meanwhile (NCCL's version banner, the reference's C++
+    # code) goes to stderr - file descriptor 1 points at stderr until the line is written
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     if args.impl == "reference":
         if rank == 0:
-            print(json.dumps(run_reference(args)), flush=True)
+            emit(run_reference(args))
         return 0
 
     dist = None
@@ -464,7 +474,7 @@ def main():
             torch.cuda.set_device(local_rank)
         out = run_tiles(args, rank, world, local_rank, dist)
         if rank == 0:
-            print(json.dumps(out), flush=True)
+            emit(out)
         if dist is not None:
             dist.barrier(); dist.destroy_process_group()
         return 0
@@ -481,7 +491,7 @@ def main():
             res = oracle_sample(args, args.cpu_steps, 1)
             out["cpu_baseline"] = {"value": res["rays"] / res["seconds"] / 1e6, "unit": "Mrays/s", "cores": res["cores"], "kind": "port",
                                    "sample": res["sample"], "msamples_per_s": res["samples"] / res["seconds"] / 1e6}
-        print(json.dumps(out), flush=True)
+        emit(out)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
