@@ -688,7 +688,8 @@ typedef struct {
     float min_transmittance;      /* 0.01 */
     int32_t rgb_activation;       /* 0 None 1 ReLU 2 Logistic 3 Exponential */
     int32_t density_activation;
-    int32_t n_steps_mode;         /* 0: one sample per wavefront iteration; 1: the reference's clamp(N0/N_alive,1,8) */
+    int32_t n_steps_mode;         /* 0: one sample per wavefront iteration; 1: the reference's clamp(N0/N_alive,1,8); 2: always 8 (what 1 gives
+                                     while at most 1/8 of the FRAME's pixels are live - for windows of a larger frame) */
     int32_t x0, y0, x1, y1;       /* pixel window [x0,x1) x [y0,y1) to render (others untouched); all 0 = full frame */
 } orc_render_params;
 
@@ -996,6 +997,7 @@ static int render_impl(const orc_model* m, const orc_render_params* P, const flo
     /* lens rays are marched on their own after the wavefront loop, with the batch size the first iteration would use */
     uint32_t n_lens = 1;
     if (P->n_steps_mode == 1 && n_alive0 > 0) { uint64_t q = (uint64_t)N / n_alive0; n_lens = (uint32_t)(q < 1 ? 1 : (q > 8 ? 8 : q)); }
+    if (P->n_steps_mode == 2) n_lens = 8;
     uint64_t lens_samples = 0;
     if (L) {
 #pragma omp parallel for schedule(dynamic, 4) reduction(+:lens_samples)
@@ -1021,6 +1023,7 @@ static int render_impl(const orc_model* m, const orc_render_params* P, const flo
             uint64_t q = (uint64_t)N / n_alive;     /* m_n_rays_initialized / n_alive, S/ngp/testbed.cu:1996 */
             n = (uint32_t)(q < 1 ? 1 : (q > 8 ? 8 : q));
         }
+        if (P->n_steps_mode == 2) n = 8;
         uint64_t iter_samples = 0;
 #pragma omp parallel for schedule(dynamic, 16) reduction(+:iter_samples)
         for (int64_t i = 0; i < (int64_t)N; ++i) {

@@ -445,3 +445,60 @@ def test_tonemap_curves_match_oracle(scene, curve):
             nerf.tonemap_curve = 7
     finally:
         nerf.tonemap_curve = 0
+
+
+def test_full_size_frame_properties(tmp_path, glasses_gltf):
+    """BASELINE configs[1] at its full size (1920x1080 hybrid frame, log2_hashmap_size 19 model, floatie removal on), through
+    size-independent properties: the same camera renders the same bits twice; Testbed.render() (rows copied out under the
+    rendering) equals frame(); row shards of three ranks reassemble the full frame bit for bit; a crop around the glasses
+    agrees with the oracle rendering that window of the full-resolution frame."""
+    import pynmr
+    import synth
+    from oracle import oracle as O
+    FW, FH = 1920, 1080
+    path = str(tmp_path / "full.msgpack")
+    synth.write_snapshot(path, seed=1337, log2_hashmap_size=19)
+    snap = synth.read_snapshot(path)
+    r = pynmr.NerfMeshRenderer(FW, FH)
+    nerf = r.load_nerf(path)
+    assert nerf is not None and r.load_mesh(glasses_gltf, t=synth.GLASSES_T, s=synth.GLASSES_S, r=synth.GLASSES_R_WXYZ) is not None
+    r.remove_floaties()
+    r.set_surface_insertion(pynmr.NerfMeshRenderer.SURFACE_BATCH8)       # ray-local rule: shards decide like the full frame
+    r.orbit(-0.01, 0.004, 0.0)
+    cam = r.view_projection_mat
+    assert r.frame()
+    a = np.asarray(r.read_frame()).copy()
+    st = r.stats()
+    assert st["rays"] == FW * FH and st["rays_alive"] > 20000 and st["samples"] > 200000
+    r.view_projection_mat = cam                                           # restarts the accumulation
+    assert r.frame()
+    b = np.asarray(r.read_frame()).copy()
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    c = np.asarray(nerf.render(FW, FH, 1, linear=False)).copy()
+    assert np.array_equal(a.view(np.uint32), c.view(np.uint32))
+    merged = np.zeros_like(a)
+    for rank in range(3):
+        r.set_shard(rank, 3, 16)
+        r.view_projection_mat = cam
+        assert r.frame()
+        part = np.asarray(r.read_frame())
+        rows = [y for y in range(FH) if (y // 16) % 3 == rank]
+        merged[rows] = part[rows]
+    r.set_shard(0, 1, 16)
+    assert np.array_equal(merged.view(np.uint32), a.view(np.uint32))
+    # oracle on a 96 x 54 window around the glasses of the same full-resolution frame
+    x0, y0, cw, ch = 912, 540, 96, 54
+    m = O.Model.from_snapshot(snap)
+    m.set_bitfield(O.remove_floaties_bitfield(m.bitfield())[0])
+    g = synth.read_gltf(glasses_gltf)
+    mesh = O.Mesh(g["positions"], g["normals"], g["texcoords"], g["indices"], synth.GLASSES_T, synth.GLASSES_S, synth.GLASSES_R_WXYZ,
+                  g["base_color"], g["metallic"], g["roughness"], (0, 0, 0), np.tile(np.array([128, 128, 128, 255], dtype=np.uint8), (4, 4, 1)))
+    c12 = np.ascontiguousarray(cam.T.reshape(-1))
+    rgba2, d2, _ = mesh.render(c12, 2 * FW, 2 * FH, window=(2 * x0, 2 * y0, 2 * (x0 + cw), 2 * (y0 + ch)))
+    surf, ts = O.mesh_resolve(rgba2, d2, FW, FH, 2)
+    P = m.params_struct(FW, FH, c12, aabb_min=snap["render_aabb_min"], aabb_max=snap["render_aabb_max"], n_steps_mode=2, window=(x0, y0, x0 + cw, y0 + ch))
+    frame, _, _, _ = m.render_frame(P, surf, ts)
+    want, _ = O.accumulate_tonemap(frame[y0:y0 + ch, x0:x0 + cw].copy(), None, 0, to_srgb=True)
+    got = a[y0:y0 + ch, x0:x0 + cw]
+    assert (ts[y0:y0 + ch, x0:x0 + cw] > 0).mean() > 0.02                 # the window does see the glasses
+    assert np.max(np.abs(got - want)) <= PIX_TOL and H.psnr(got, want) >= 45.0
