@@ -50,6 +50,7 @@ struct Nerf {
     HostModel host;                 // parameters are dropped after upload
     DevBuf<uint16_t> d_params;
     DevBuf<uint8_t> d_bitfield;
+    DevBuf<uint16_t> d_mlp_tc;                      // MLP weights in the tensor-core operand layout
     DevBuf<uint32_t> d_coarse;                      // coarse "near" bits of cascade 0 (kernels.cuh: launch_coarse_build)
     DeviceModel dev{};
     float render_aabb_min[3], render_aabb_max[3];
@@ -640,6 +641,9 @@ NMR_API int nmr_load_nerf(nmr_ctx* ctx, const char* path, int* out_id) {
         CK(cudaGetLastError());
         DeviceModel& d = n->dev;
         d.mlp = reinterpret_cast<const __half*>(n->d_params.p);
+        n->d_mlp_tc.ensure(10240);
+        launch_weights_canonical(n->d_params.p, n->d_mlp_tc.p, ctx->stream);
+        d.mlp_tc = std::getenv("NMR_NO_BULK_WEIGHTS") ? nullptr : reinterpret_cast<const __half*>(n->d_mlp_tc.p);
         d.grid = reinterpret_cast<const __half2*>(n->d_params.p + h.mlp_params);
         d.bitfield = n->d_bitfield.p;
         d.dense_mask = 0; d.pow2_mask = 0;

@@ -21,6 +21,7 @@ constexpr int ENC_WIDTH = 32;
 struct DeviceModel {
     const __half2* grid;              // hash-table entries, all levels back to back
     const __half* mlp;                // density net | rgb net, row-major [out][in] (params_binary order)
+    const __half* mlp_tc;             // the same 10 240 weights in the tensor-core operand layout (kernels.cu: stage_weights_tc), or null
     const uint8_t* bitfield;          // 2 MiB occupancy bits, Morton order per cascade
     const uint32_t* coarse;           // 32^3 "near" bits of cascade 0 (kCoarseRes; see coarse_near), or null: no empty-space jumps
     const __half2* level_ptr[N_LEVELS];  // grid + level_offset[l]: 64-bit base per level, so a gather is base + 32-bit index

@@ -10,6 +10,7 @@
 //
 // Reference behaviour restated per kernel: see the citations at each function and SURVEY.md section 8a.
 #include "kernels.cuh"
+#include <cstdlib>
 
 #include <cstdio>
 
@@ -403,8 +404,15 @@ __device__ __forceinline__ void init_one_ray(const FrameParams& P, const DeviceM
 // rectangle of the box around the occupied cells (FrameParams::occ_px, projected on the host) and the mesh's screen rectangle
 // can only be background: integer compares, one store pair, no ray arithmetic - most of a frame in render.py's framing.
 __global__ void __launch_bounds__(128) init_rays_kernel(FrameParams P, DeviceModel M, MeshDevice mesh, const unsigned long long* __restrict__ zbuf, int rows_owned,
-                                                        float4* __restrict__ queue, uint32_t* __restrict__ counters, FrameOut out, uint32_t* __restrict__ surf_list) {
+                                                        float4* __restrict__ queue, uint32_t* __restrict__ counters, FrameOut out, uint32_t* __restrict__ surf_list, uint32_t prefetch_lines) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // The hash table (23 MiB at log2T 19) is about to be gathered from at random by the march kernel.  When it may have left
+    // the L2 since the last frame, a 4-byte gather costs a DRAM round trip per level; the first CTAs of this kernel (background
+    // rows, nothing else to do) ask for it line by line instead, sequentially, while the first-hit walks keep the SMs busy.
+    if (prefetch_lines) {
+        const uint32_t g = (blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+        if (g < prefetch_lines) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(M.grid) + (size_t)g * 128u));
+    }
     const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
     const int ly = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
     if (x >= P.width || ly >= rows_owned) return;
@@ -456,7 +464,11 @@ void launch_init_rays(const FrameParams& P, const DeviceModel& M, const MeshDevi
     (void)num_sms;
     if (rows_owned <= 0) return;
     dim3 grid((P.width + 15) / 16, (rows_owned + 7) / 8);
-    init_rays_kernel<<<grid, 128, 0, s>>>(P, M, mesh, d_zbuf, rows_owned, d_queue, d_counters, out, d_surf_list);
+    // tables that fit the L2 comfortably are prefetched by the frame's first set-up pass (see the kernel); NMR_NO_PREFETCH=1 for A/B runs
+    static const bool no_prefetch = std::getenv("NMR_NO_PREFETCH") != nullptr;
+    const size_t table_bytes = ((size_t)M.level_offset[N_LEVELS - 1] + M.level_size[N_LEVELS - 1]) * sizeof(__half2);
+    const uint32_t prefetch_lines = (reset_counters && !no_prefetch && table_bytes <= ((size_t)48 << 20)) ? (uint32_t)(table_bytes / 128) : 0u;
+    init_rays_kernel<<<grid, 128, 0, s>>>(P, M, mesh, d_zbuf, rows_owned, d_queue, d_counters, out, d_surf_list, prefetch_lines);
 }
 
 // =================================================================================================================
@@ -540,6 +552,7 @@ struct __align__(128) MarchSmemTC {
     __half w[kWTotal];                    // 20480 B, canonical K-major core-matrix layout, shared by the warpgroups
     __half act[kGroupsTC][kTile * 64];    // 2 x 16384 B, A operands: chunk-major (k/8)*2048 + row*16
     uint64_t mbar[kGroupsTC];
+    uint64_t wbar;                        // completion of the bulk copy that brings the weights in
     uint32_t tmem_base;
 };
 
@@ -599,6 +612,11 @@ __device__ __forceinline__ void stage_weights_tc(__half* sw, const __half* __res
             *reinterpret_cast<uint4*>(reinterpret_cast<char*>(sw + off[m]) + c * (N * 16) + n * 16) = v;
         }
     }
+}
+
+__global__ void weights_to_canonical_kernel(const __half* __restrict__ gw, __half* __restrict__ out) { stage_weights_tc(out, gw); }
+void launch_weights_canonical(const uint16_t* d_mlp, uint16_t* d_out, cudaStream_t s) {
+    weights_to_canonical_kernel<<<1, 256, 0, s>>>(reinterpret_cast<const __half*>(d_mlp), reinterpret_cast<__half*>(d_out));
 }
 
 struct TcCtx {
@@ -706,7 +724,22 @@ __device__ __forceinline__ void network_tc(char* a_row, TcCtx& c, V3 dir01, floa
 __device__ __forceinline__ TcCtx tc_setup(MarchSmemTC& S, const DeviceModel& M, uint32_t debug_flags) {
     if (threadIdx.x < 32) tmem_alloc(&S.tmem_base, 64 * kGroupsTC);
     if (threadIdx.x == 0) { for (int g = 0; g < kGroupsTC; ++g) mbar_init(&S.mbar[g], 1); fence_barrier_init(); }
-    stage_weights_tc(S.w, M.mlp);
+    if (M.mlp_tc) {
+        // weights already in the canonical layout (weights_to_canonical_kernel at load time): one 20 KB bulk copy per CTA
+        // (cp.async.bulk, the TMA engine) instead of 1280 16-byte loads + re-indexed stores by the CTA's threads
+        if (threadIdx.x == 0) {
+            mbar_init(&S.wbar, 1);
+            fence_barrier_init();
+            const uint32_t bytes = kWTotal * (uint32_t)sizeof(__half);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&S.wbar)), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(S.w)), "l"(M.mlp_tc), "r"(bytes), "r"(smem_u32(&S.wbar)) : "memory");
+        }
+        __syncthreads();                 // the barrier is initialised before anybody waits on it
+        mbar_wait(&S.wbar, 0);
+    } else {
+        stage_weights_tc(S.w, M.mlp);
+    }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();

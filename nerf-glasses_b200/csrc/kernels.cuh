@@ -49,6 +49,8 @@ void launch_occupancy_build(const uint16_t* d_density_grid_fp16, int n_cascades_
 void launch_occupancy_bounds(const uint8_t* d_bitfield, int* d_out48, cudaStream_t s);
 // d_occ_scratch: kCoarseRes^3 bytes; d_near_bits: kCoarseRes^2 words (DeviceModel::coarse)
 void launch_coarse_build(const uint8_t* d_bitfield, uint8_t* d_occ_scratch, uint32_t* d_near_bits, cudaStream_t s);
+// d_out: 10 240 halves; the MLP weights re-laid out as the tcgen05 B operands the march kernel keeps in shared memory
+void launch_weights_canonical(const uint16_t* d_mlp, uint16_t* d_out, cudaStream_t s);
 void launch_mesh_raster(const MeshDevice& mesh, const FrameParams& P, int rows_owned, unsigned long long* d_zbuf, cudaStream_t s);
 void launch_latch_word(const uint32_t* d_src, uint32_t* d_dst, uint32_t* d_dst2, cudaStream_t s);
 // sequence flags of a shared frame target (nmr_gather_*): one word per rank + "consumed" + "error", behind the image
