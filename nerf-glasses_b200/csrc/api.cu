@@ -388,12 +388,12 @@ FrameParams make_params(nmr_ctx* ctx, const Nerf& n, int W, int H, const float* 
 
 // Frames that can need the reference's per-iteration n_steps schedule: a mesh is in view and the surface rule is `auto`.
 // Returns false (and leaves `sa` zeroed) otherwise.  The histogram is cleared on the stream.
-bool prepare_schedule(nmr_ctx* ctx, const FrameParams& P, SchedArgs& sa) {
+bool prepare_schedule(nmr_ctx* ctx, const FrameParams& P, SchedArgs& sa, bool clear = true) {
     sa = SchedArgs{};
     if (!(P.mesh_scale > 0 && P.zb_w > 0 && P.surface_mode == kSurfaceAuto)) return false;
     Surfaces& S = ctx->surf;
     S.hist.ensure(kSchedBins); S.surf_list.ensure((size_t)P.width * P.height);
-    CK(cudaMemsetAsync(S.hist.p, 0, sizeof(uint32_t) * kSchedBins, ctx->stream));
+    if (clear) CK(cudaMemsetAsync(S.hist.p, 0, sizeof(uint32_t) * kSchedBins, ctx->stream));
     sa.hist = S.hist.p; sa.surf_list = S.surf_list.p; sa.pass = 1;
     return true;
 }
@@ -421,9 +421,12 @@ void enqueue_pass(nmr_ctx* ctx, Nerf& n, const FrameParams& P, bool timed, float
     if (timed) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     uint64_t launches = 0;
     SchedArgs sa;
-    const bool sched = prepare_schedule(ctx, P, sa);
-    if (P.mesh_scale > 0) { launch_mesh_raster(mesh, P, rows, S.zbuf.p, ctx->stream); launches += 1; }
-    launch_init_rays(P, n.dev, mesh, S.zbuf.p, rows, S.queue.p, ctx->d_counters.p, out, ctx->num_sms, ctx->stream, true, sched ? S.surf_list.p : nullptr);
+    const bool sched = prepare_schedule(ctx, P, sa, false);
+    // counters, schedule histogram and the mesh visibility window are cleared by one kernel (not three memset nodes)
+    launch_frame_clear(ctx->d_counters.p, sched ? S.hist.p : nullptr, S.zbuf.p, zbuf_window_words(mesh, P), ctx->stream);
+    launches += 1;
+    if (P.mesh_scale > 0) { launch_mesh_raster(mesh, P, rows, S.zbuf.p, ctx->stream, false); launches += 1; }
+    launch_init_rays(P, n.dev, mesh, S.zbuf.p, rows, S.queue.p, ctx->d_counters.p, out, ctx->num_sms, ctx->stream, false, sched ? S.surf_list.p : nullptr, 1);
     launches += 1;
     if (timed) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     const uint32_t n_pixels = (uint32_t)P.width * (uint32_t)rows;

@@ -191,11 +191,30 @@ __global__ void __launch_bounds__(256) mesh_raster_kernel(MeshDevice mesh, Frame
     }
 }
 
-void launch_mesh_raster(const MeshDevice& mesh, const FrameParams& P, int rows_owned, unsigned long long* d_zbuf, cudaStream_t s) {
+// One launch instead of three memset nodes at the head of a frame: device counters, the schedule histogram and the mesh
+// visibility window (every stream node costs 2-4 us of device time on a 250 us frame).
+__global__ void frame_clear_kernel(uint32_t* __restrict__ counters, uint32_t* __restrict__ hist, ulonglong2* __restrict__ zbuf2, size_t zbuf_pairs) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    if (i < (size_t)kNumCounters) counters[i] = 0u;
+    if (hist) for (size_t k = i; k < kSchedBins; k += stride) hist[k] = 0u;
+    if (zbuf2) for (size_t k = i; k < zbuf_pairs; k += stride) zbuf2[k] = make_ulonglong2(~0ull, ~0ull);
+}
+size_t zbuf_window_words(const MeshDevice& mesh, const FrameParams& P) {
+    if (P.mesh_scale <= 0 || mesh.n_tris == 0 || P.zb_w <= 0 || P.zb_h <= 0) return 0;
+    return (size_t)P.zb_w * P.zb_h * (mesh.tri_lens ? 2 : 1);
+}
+void launch_frame_clear(uint32_t* d_counters, uint32_t* d_hist, unsigned long long* d_zbuf, size_t zbuf_words, cudaStream_t s) {
+    const size_t pairs = (zbuf_words + 1) / 2;        // the buffer is allocated for the whole 2W x 2H frame (even), the window never fills it to the last word
+    const size_t work = pairs > kSchedBins ? pairs : kSchedBins;
+    const unsigned blocks = (unsigned)((work + 255) / 256 < 592 ? (work + 255) / 256 : 592);
+    frame_clear_kernel<<<blocks ? blocks : 1, 256, 0, s>>>(d_counters, d_hist, zbuf_words ? reinterpret_cast<ulonglong2*>(d_zbuf) : nullptr, pairs);
+}
+
+void launch_mesh_raster(const MeshDevice& mesh, const FrameParams& P, int rows_owned, unsigned long long* d_zbuf, cudaStream_t s, bool clear) {
     (void)rows_owned;
     const int W2 = P.width * P.mesh_scale, H2 = P.height * P.mesh_scale;
     if (mesh.n_tris == 0 || P.zb_w <= 0 || P.zb_h <= 0) return;
-    cudaMemsetAsync(d_zbuf, 0xFF, (size_t)P.zb_w * P.zb_h * sizeof(unsigned long long) * (mesh.tri_lens ? 2 : 1), s);
+    if (clear) cudaMemsetAsync(d_zbuf, 0xFF, (size_t)P.zb_w * P.zb_h * sizeof(unsigned long long) * (mesh.tri_lens ? 2 : 1), s);
     const uint32_t slices = mesh.tri_lens ? 16u : 2u;
     const uint32_t threads = mesh.n_tris * 32u * slices;
     mesh_raster_kernel<<<(threads + 255) / 256, 256, 0, s>>>(mesh, P, W2, H2, d_zbuf, slices);
@@ -459,7 +478,7 @@ void launch_gather_wait(uint32_t* d_flags, int first, int count, uint32_t seq, u
 }
 
 void launch_init_rays(const FrameParams& P, const DeviceModel& M, const MeshDevice& mesh, const unsigned long long* d_zbuf, int rows_owned,
-                      float4* d_queue, uint32_t* d_counters, const FrameOut& out, int num_sms, cudaStream_t s, bool reset_counters, uint32_t* d_surf_list) {
+                      float4* d_queue, uint32_t* d_counters, const FrameOut& out, int num_sms, cudaStream_t s, bool reset_counters, uint32_t* d_surf_list, int first_pass) {
     if (reset_counters) cudaMemsetAsync(d_counters, 0, sizeof(uint32_t) * kNumCounters, s);
     (void)num_sms;
     if (rows_owned <= 0) return;
@@ -467,7 +486,8 @@ void launch_init_rays(const FrameParams& P, const DeviceModel& M, const MeshDevi
     // tables that fit the L2 comfortably are prefetched by the frame's first set-up pass (see the kernel); NMR_NO_PREFETCH=1 for A/B runs
     static const bool no_prefetch = std::getenv("NMR_NO_PREFETCH") != nullptr;
     const size_t table_bytes = ((size_t)M.level_offset[N_LEVELS - 1] + M.level_size[N_LEVELS - 1]) * sizeof(__half2);
-    const uint32_t prefetch_lines = (reset_counters && !no_prefetch && table_bytes <= ((size_t)48 << 20)) ? (uint32_t)(table_bytes / 128) : 0u;
+    const bool first = first_pass < 0 ? reset_counters : first_pass != 0;     // the frame's first set-up pass
+    const uint32_t prefetch_lines = (first && !no_prefetch && table_bytes <= ((size_t)48 << 20)) ? (uint32_t)(table_bytes / 128) : 0u;
     init_rays_kernel<<<grid, 128, 0, s>>>(P, M, mesh, d_zbuf, rows_owned, d_queue, d_counters, out, d_surf_list, prefetch_lines);
 }
 

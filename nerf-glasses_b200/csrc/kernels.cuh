@@ -51,14 +51,18 @@ void launch_occupancy_bounds(const uint8_t* d_bitfield, int* d_out48, cudaStream
 void launch_coarse_build(const uint8_t* d_bitfield, uint8_t* d_occ_scratch, uint32_t* d_near_bits, cudaStream_t s);
 // d_out: 10 240 halves; the MLP weights re-laid out as the tcgen05 B operands the march kernel keeps in shared memory
 void launch_weights_canonical(const uint16_t* d_mlp, uint16_t* d_out, cudaStream_t s);
-void launch_mesh_raster(const MeshDevice& mesh, const FrameParams& P, int rows_owned, unsigned long long* d_zbuf, cudaStream_t s);
+void launch_mesh_raster(const MeshDevice& mesh, const FrameParams& P, int rows_owned, unsigned long long* d_zbuf, cudaStream_t s, bool clear = true);
+// counters + (optional) schedule histogram + (optional) mesh visibility window in one launch; zbuf_window_words: words of the window (both layers)
+size_t zbuf_window_words(const MeshDevice& mesh, const FrameParams& P);
+void launch_frame_clear(uint32_t* d_counters, uint32_t* d_hist, unsigned long long* d_zbuf, size_t zbuf_words, cudaStream_t s);
 void launch_latch_word(const uint32_t* d_src, uint32_t* d_dst, uint32_t* d_dst2, cudaStream_t s);
 // sequence flags of a shared frame target (nmr_gather_*): one word per rank + "consumed" + "error", behind the image
 constexpr int kGatherMaxRanks = 32, kGatherConsumed = 32, kGatherError = 33, kGatherFlagWords = 64;
 void launch_gather_signal(uint32_t* d_flag, uint32_t seq, cudaStream_t s);
 void launch_gather_wait(uint32_t* d_flags, int first, int count, uint32_t seq, uint32_t* d_err, cudaStream_t s);
 void launch_init_rays(const FrameParams& P, const DeviceModel& M, const MeshDevice& mesh, const unsigned long long* d_zbuf, int rows_owned,
-                      float4* d_queue, uint32_t* d_counters, const FrameOut& out, int num_sms, cudaStream_t s, bool reset_counters = true, uint32_t* d_surf_list = nullptr);
+                      float4* d_queue, uint32_t* d_counters, const FrameOut& out, int num_sms, cudaStream_t s, bool reset_counters = true, uint32_t* d_surf_list = nullptr, int first_pass = -1);
+// (first_pass: 1 / 0 = this is / is not the frame's first set-up pass, -1 = it is iff reset_counters)
 // n_pixels: pixels traced by this context in this pass (the reference's m_n_rays_initialized), for SurfaceMode auto
 void launch_march(const FrameParams& P, const DeviceModel& M, const float4* d_queue, uint32_t* d_counters, const FrameOut& out,
                   uint32_t n_pixels, uint32_t debug_flags, int num_sms, cudaStream_t s, const uint32_t* d_range_end = nullptr, uint32_t* d_cursor = nullptr,
