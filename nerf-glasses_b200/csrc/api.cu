@@ -100,6 +100,11 @@ struct nmr_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;                   // device->host copies of nmr_render_views
     cudaEvent_t ev_view[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // per image buffer: rendered, copied
+    // nmr_render_views: views are independent frames, and a single frame leaves most of the GPU idle (both its kernels wait on
+    // dependent chains).  Helper contexts ("lanes": own stream, ray queue, counters, visibility buffer, image) render several
+    // views at once; they borrow the parent's model and mesh buffers.
+    std::vector<nmr_ctx*> lanes;
+    int march_ctas = 0;                                   // CTAs per SM of this context's march kernel (0 = default); lanes share the SMs
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     OrbitCamera camera;
     float cam12[12];
@@ -430,7 +435,7 @@ void enqueue_pass(nmr_ctx* ctx, Nerf& n, const FrameParams& P, bool timed, float
     launches += 1;
     if (timed) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     const uint32_t n_pixels = (uint32_t)P.width * (uint32_t)rows;
-    launch_march(P, n.dev, S.queue.p, ctx->d_counters.p, out, n_pixels, ctx->debug_flags, ctx->num_sms, ctx->stream, nullptr, nullptr, sched ? &sa : nullptr);
+    launch_march(P, n.dev, S.queue.p, ctx->d_counters.p, out, n_pixels, ctx->debug_flags, ctx->num_sms, ctx->stream, nullptr, nullptr, sched ? &sa : nullptr, ctx->march_ctas);
     launches += 1;
     if (sched) { enqueue_surface_pass(ctx, n, P, out, n_pixels, sa); launches += 1; }
     if (timed) {
@@ -551,6 +556,33 @@ void finish_stats(nmr_ctx* ctx) {
     ctx->stats_pending = false;
 }
 
+// a helper context of nmr_render_views on the parent's device: streams, events and counters of its own, nothing loaded
+nmr_ctx* make_lane(nmr_ctx* parent) {
+    std::unique_ptr<nmr_ctx> l(new nmr_ctx());
+    l->device = parent->device; l->num_sms = parent->num_sms; l->width = parent->width; l->height = parent->height;
+    CK(cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking));
+    for (auto& ev : l->ev) CK(cudaEventCreate(&ev));
+    for (auto& pair : l->ev_view) for (auto& ev : pair) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    l->d_counters.ensure(kNumCounters);
+    CK(cudaHostAlloc((void**)&l->h_counters, sizeof(uint32_t) * kNumCounters, cudaHostAllocDefault));
+    std::memset(l->h_counters, 0, sizeof(uint32_t) * kNumCounters);
+    return l.release();
+}
+void destroy_lane(nmr_ctx* l) {
+    if (!l) return;
+    if (l->stream) cudaStreamSynchronize(l->stream);
+    if (l->h_counters) cudaFreeHost(l->h_counters);
+    for (auto& ev : l->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& pair : l->ev_view) for (auto& ev : pair) if (ev) cudaEventDestroy(ev);
+    if (l->stream) cudaStreamDestroy(l->stream);
+    delete l;
+}
+// what a lane needs to know about the scene for enqueue_pass: the parent's mesh buffers (borrowed) and settings
+void sync_lane(nmr_ctx* l, const nmr_ctx* parent) {
+    l->mesh_dev = parent->mesh_dev; l->mesh_scale = parent->mesh_scale; l->debug_flags = parent->debug_flags;
+    l->scene_has_lens = parent->scene_has_lens; l->surface_mode = parent->surface_mode;
+}
+
 void set_camera_from_orbit(nmr_ctx* ctx) {
     ctx->camera.matrix(ctx->width, ctx->height, ctx->cam12);
     ctx->surf.spp = 0;   // updateModelViewProj -> reset_accumulation (S/nerf_mesh_renderer.cu:934-938)
@@ -602,6 +634,8 @@ NMR_API void nmr_destroy(nmr_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->ipc_mapped) { cudaIpcCloseMemHandle(ctx->ipc_mapped); ctx->ipc_mapped = nullptr; }
+    for (nmr_ctx* l : ctx->lanes) destroy_lane(l);
+    ctx->lanes.clear();
     ctx->nerfs.clear(); ctx->meshes.clear();
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->h_bands) cudaFreeHost(ctx->h_bands);
@@ -895,7 +929,45 @@ NMR_API int nmr_render_views(nmr_ctx* ctx, int nerf_id, int n_views, const float
         upload_mesh_if_dirty(ctx);
         ctx->surf.resize(width, height, ctx->mesh_scale);
         const size_t px = (size_t)width * height;
-        // Two image buffers, two streams: view v renders into buffer v % 2 while view v - 1 leaves the other one over PCIe.
+        // lanes: 8 up to 1 Mpixel per view, 4 up to 1080p, 2 above (a lane holds ~130 bytes per pixel); NMR_VIEW_LANES overrides
+        static const int n_lanes_env = [] { const char* v = std::getenv("NMR_VIEW_LANES"); return v ? std::atoi(v) : 0; }();
+        const int n_lanes_auto = px <= ((size_t)1 << 20) ? 8 : (px <= (size_t)1920 * 1080 ? 4 : 2);
+        const int K = std::max(1, std::min(std::min(n_lanes_env > 0 ? n_lanes_env : n_lanes_auto, 8), n_views));
+        if (K > 1 && ctx->shard_world == 1) {
+            // K views in flight: lane v % K renders view v on its own stream with a march grid of one CTA per SM (K marches fill
+            // the SMs together, and one view's tail overlaps the others' set-up); a view leaves over PCIe on the copy stream as
+            // soon as it is complete, and a lane renders its next view once its image has been copied out.
+            while ((int)ctx->lanes.size() < K) ctx->lanes.push_back(make_lane(ctx));
+            CK(cudaEventRecord(ctx->ev_view[0][0], ctx->stream));          // everything enqueued on the context's stream so far comes first
+            for (int k = 0; k < K; ++k) {
+                nmr_ctx* l = ctx->lanes[(size_t)k];
+                sync_lane(l, ctx);
+                l->march_ctas = K >= 3 ? 1 : 2;
+                l->surf.resize(width, height, ctx->mesh_scale);
+                CK(cudaStreamWaitEvent(l->stream, ctx->ev_view[0][0], 0));
+            }
+            for (int v = 0; v < n_views; ++v) {
+                nmr_ctx* l = ctx->lanes[(size_t)(v % K)];
+                if (v >= K) CK(cudaStreamWaitEvent(l->stream, l->ev_view[0][1], 0));      // the lane's previous image has been copied out
+                const FrameParams P = make_params(ctx, *n, width, height, cams12 + (size_t)v * 12, 0, !linear, true);
+                enqueue_pass(l, *n, P, v == n_views - 1);
+                CK(cudaEventRecord(l->ev_view[0][0], l->stream));
+                CK(cudaStreamWaitEvent(ctx->copy_stream, l->ev_view[0][0], 0));
+                CK(cudaMemcpyAsync(out_rgba + (size_t)v * px * 4, l->surf.image.p, px * sizeof(float4), cudaMemcpyDeviceToHost, ctx->copy_stream));
+                CK(cudaEventRecord(l->ev_view[0][1], ctx->copy_stream));
+            }
+            nmr_ctx* last = ctx->lanes[(size_t)((n_views - 1) % K)];
+            // nmr_get_device_image / nmr_get_stats after the call refer to the last view
+            CK(cudaMemcpyAsync(ctx->surf.image.p, last->surf.image.p, px * sizeof(float4), cudaMemcpyDeviceToDevice, last->stream));
+            CK(cudaStreamSynchronize(ctx->copy_stream));
+            for (int k = 0; k < K; ++k) CK(cudaStreamSynchronize(ctx->lanes[(size_t)k]->stream));
+            finish_stats(last);
+            ctx->stats = last->stats; ctx->stats_pending = false;
+            ctx->surf.spp = 0;
+            return NMR_OK;
+        }
+        // one view at a time (sharded contexts, NMR_VIEW_LANES=1): two image buffers, two streams - view v renders into buffer
+        // v % 2 while view v - 1 leaves the other one over PCIe.
         Surfaces& S = ctx->surf;
         S.image_alt.ensure(px);
         float4* bufs[2] = {S.image.p, S.image_alt.p};
