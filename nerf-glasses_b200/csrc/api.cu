@@ -923,7 +923,7 @@ NMR_API int nmr_render(nmr_ctx* ctx, int nerf_id, int width, int height, int spp
 
 NMR_API int nmr_render_views(nmr_ctx* ctx, int nerf_id, int n_views, const float* cams12, int width, int height, int linear, float* out_rgba) {
     return guarded(ctx, [&]() -> int {
-        if (width <= 0 || height <= 0 || n_views < 1 || !out_rgba || !cams12) return fail(ctx, NMR_ERR_INVALID, "bad render_views arguments");
+        if (width <= 0 || height <= 0 || n_views < 1 || !cams12) return fail(ctx, NMR_ERR_INVALID, "bad render_views arguments");
         Nerf* n;
         try { n = get_nerf(ctx, nerf_id); } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); }
         upload_mesh_if_dirty(ctx);
@@ -948,9 +948,10 @@ NMR_API int nmr_render_views(nmr_ctx* ctx, int nerf_id, int n_views, const float
             }
             for (int v = 0; v < n_views; ++v) {
                 nmr_ctx* l = ctx->lanes[(size_t)(v % K)];
-                if (v >= K) CK(cudaStreamWaitEvent(l->stream, l->ev_view[0][1], 0));      // the lane's previous image has been copied out
+                if (v >= K && out_rgba) CK(cudaStreamWaitEvent(l->stream, l->ev_view[0][1], 0));      // the lane's previous image has been copied out
                 const FrameParams P = make_params(ctx, *n, width, height, cams12 + (size_t)v * 12, 0, !linear, true);
                 enqueue_pass(l, *n, P, v == n_views - 1);
+                if (!out_rgba) continue;                                                   // images stay on the device
                 CK(cudaEventRecord(l->ev_view[0][0], l->stream));
                 CK(cudaStreamWaitEvent(ctx->copy_stream, l->ev_view[0][0], 0));
                 CK(cudaMemcpyAsync(out_rgba + (size_t)v * px * 4, l->surf.image.p, px * sizeof(float4), cudaMemcpyDeviceToHost, ctx->copy_stream));
@@ -978,6 +979,7 @@ NMR_API int nmr_render_views(nmr_ctx* ctx, int nerf_id, int n_views, const float
             const FrameParams P = make_params(ctx, *n, width, height, cams12 + (size_t)v * 12, 0, !linear, true);
             enqueue_pass(ctx, *n, P, v == n_views - 1);
             CK(cudaEventRecord(ctx->ev_view[b][0], ctx->stream));
+            if (!out_rgba) { CK(cudaEventRecord(ctx->ev_view[b][1], ctx->stream)); continue; }
             CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_view[b][0], 0));
             CK(cudaMemcpyAsync(out_rgba + (size_t)v * px * 4, bufs[b], px * sizeof(float4), cudaMemcpyDeviceToHost, ctx->copy_stream));
             CK(cudaEventRecord(ctx->ev_view[b][1], ctx->copy_stream));

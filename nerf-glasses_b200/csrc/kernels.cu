@@ -99,27 +99,25 @@ __global__ void coarse_occupied_kernel(const uint8_t* __restrict__ bitfield, uin
     occ[i] = (v.x | v.y) != 0u;
 }
 __global__ void coarse_near_kernel(const uint8_t* __restrict__ occ, uint32_t* __restrict__ near_bits) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;                    // one thread per row of 32 cells = one word
-    if (i >= kCoarseRes * kCoarseRes) return;
-    const int cy = i % kCoarseRes, cz = i / kCoarseRes;
-    uint32_t word = 0;
-    for (int cx = 0; cx < kCoarseRes; ++cx) {
-        bool near_cell = cx == 0 || cy == 0 || cz == 0 || cx == kCoarseRes - 1 || cy == kCoarseRes - 1 || cz == kCoarseRes - 1;
-        for (int dz = -2; dz <= 2 && !near_cell; ++dz)
-            for (int dy = -2; dy <= 2 && !near_cell; ++dy)
-                for (int dx = -2; dx <= 2; ++dx) {
-                    const int x = cx + dx, y = cy + dy, z = cz + dz;
-                    if (x < 0 || y < 0 || z < 0 || x >= kCoarseRes || y >= kCoarseRes || z >= kCoarseRes) continue;
-                    if (occ[(z * kCoarseRes + y) * kCoarseRes + x]) { near_cell = true; break; }
-                }
-        word |= near_cell ? (1u << cx) : 0u;
-    }
-    near_bits[i] = word;
+    static_assert(kCoarseRes == 32, "one warp = one row of coarse cells = one word");
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;                    // one thread per coarse cell, one warp per row
+    if (i >= kCoarseRes * kCoarseRes * kCoarseRes) return;
+    const int cx = i % kCoarseRes, cy = (i / kCoarseRes) % kCoarseRes, cz = i / (kCoarseRes * kCoarseRes);
+    bool near_cell = cx == 0 || cy == 0 || cz == 0 || cx == kCoarseRes - 1 || cy == kCoarseRes - 1 || cz == kCoarseRes - 1;
+    for (int dz = -2; dz <= 2 && !near_cell; ++dz)
+        for (int dy = -2; dy <= 2 && !near_cell; ++dy)
+            for (int dx = -2; dx <= 2; ++dx) {
+                const int x = cx + dx, y = cy + dy, z = cz + dz;
+                if (x < 0 || y < 0 || z < 0 || x >= kCoarseRes || y >= kCoarseRes || z >= kCoarseRes) continue;
+                if (occ[(z * kCoarseRes + y) * kCoarseRes + x]) { near_cell = true; break; }
+            }
+    const uint32_t word = __ballot_sync(0xffffffffu, near_cell);
+    if (cx == 0) near_bits[cz * kCoarseRes + cy] = word;
 }
 void launch_coarse_build(const uint8_t* d_bitfield, uint8_t* d_occ_scratch, uint32_t* d_near_bits, cudaStream_t s) {
     constexpr int n = kCoarseRes * kCoarseRes * kCoarseRes;
     coarse_occupied_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_bitfield, d_occ_scratch);
-    coarse_near_kernel<<<(kCoarseRes * kCoarseRes + 127) / 128, 128, 0, s>>>(d_occ_scratch, d_near_bits);
+    coarse_near_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_occ_scratch, d_near_bits);
 }
 
 void launch_occupancy_build(const uint16_t* d_grid, int n_cascades_present, uint8_t* d_bitfield, float* d_scratch, cudaStream_t s) {

@@ -544,11 +544,12 @@ class NerfMeshRenderer:
     def synchronize(self):
         self._ck(lib().nmr_synchronize(self._h))
 
-    def render_views(self, nerf: Testbed, cameras, width: int, height: int, linear: bool = False) -> np.ndarray:
-        """cameras: [n, 3, 4] -> float32[n, H, W, 4] rendered back to back (render.py's landmark pass in one call)."""
+    def render_views(self, nerf: Testbed, cameras, width: int, height: int, linear: bool = False, to_host: bool = True):
+        """cameras: [n, 3, 4] -> float32[n, H, W, 4] (render.py's landmark pass in one call; up to 8 views in flight on the GPU).
+        to_host=False leaves the images on the device (returns None; device_image() is the last view)."""
         cams = np.ascontiguousarray(np.asarray(cameras, dtype=np.float32).reshape(-1, 3, 4).transpose(0, 2, 1)).reshape(-1, 12)
-        out = _pinned_array((cams.shape[0], height, width, 4))
-        self._ck(lib().nmr_render_views(self._h, nerf._id, cams.shape[0], _ptr(cams), int(width), int(height), int(bool(linear)), _ptr(out)))
+        out = _pinned_array((cams.shape[0], height, width, 4)) if to_host else None
+        self._ck(lib().nmr_render_views(self._h, nerf._id, cams.shape[0], _ptr(cams), int(width), int(height), int(bool(linear)), _ptr(out) if to_host else None))
         return out
 
     def set_shard(self, rank: int, world: int, band: int = 8):
