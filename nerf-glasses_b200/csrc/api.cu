@@ -147,6 +147,7 @@ struct nmr_ctx {
     bool stats_pending = false;
     std::string envmap_path;
     DevBuf<uint8_t> d_flush;
+    DevBuf<unsigned long long> d_phase_log;               // NMR_PHASE_LOG (measurement aid)
 };
 
 namespace {
@@ -416,6 +417,13 @@ void enqueue_pass(nmr_ctx* ctx, Nerf& n, const FrameParams& P, bool timed, float
     // the linear frame, depth and per-ray sample counts are parity probes (nmr_debug_last_frame): written only on request
     const bool probes = (ctx->debug_flags & kDebugKeepProbes) != 0;
     FrameOut out{image_target ? image_target : S.image.p, S.accum.p, probes ? S.frame.p : nullptr, probes ? S.depth.p : nullptr, probes ? S.n_samples.p : nullptr, nullptr, nullptr};
+    static const char* phase_log_path = std::getenv("NMR_PHASE_LOG");      // measurement aid: see FrameOut::phase_log
+    if (phase_log_path && timed) {
+        const size_t words = (size_t)ctx->num_sms * 4 * 2 * kPhaseIters * 5;
+        ctx->d_phase_log.ensure(words);
+        CK(cudaMemsetAsync(ctx->d_phase_log.p, 0, words * 8, ctx->stream));
+        out.phase_log = ctx->d_phase_log.p;
+    }
     MeshDevice mesh = ctx->mesh_dev;
     if (!P.lens_on) mesh.tri_lens = nullptr;     // lenses off: their triangles are ordinary opaque surfaces
     else {
@@ -554,6 +562,13 @@ void finish_stats(nmr_ctx* ctx) {
     CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[2])); ctx->stats.gpu_ms = ms;
     CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2])); ctx->stats.march_ms = ms;
     ctx->stats_pending = false;
+    if (const char* path = std::getenv("NMR_PHASE_LOG")) {
+        if (ctx->d_phase_log.p) {        // raw dump of the last timed frame's phase clocks
+            std::vector<unsigned long long> h(ctx->d_phase_log.n);
+            CK(cudaMemcpy(h.data(), ctx->d_phase_log.p, h.size() * 8, cudaMemcpyDeviceToHost));
+            if (FILE* f = std::fopen(path, "wb")) { std::fwrite(h.data(), 8, h.size(), f); std::fclose(f); }
+        }
+    }
 }
 
 // a helper context of nmr_render_views on the parent's device: streams, events and counters of its own, nothing loaded

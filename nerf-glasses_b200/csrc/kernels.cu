@@ -878,7 +878,19 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH
     float cr = 0.f, cg = 0.f, cb = 0.f, ca = 0.f;        // accumulated colour
     uint32_t idx = 0, n_samples = 0, evaluated = 0, n_batches = 0, n_passes = 0;
 
+#ifdef NMR_PHASE_LOG_BUILD      // measurement build only (python nerf-glasses_b200/build.py -DNMR_PHASE_LOG_BUILD --out=...): FrameOut::phase_log
+    uint32_t tile_iter = 0;
+    unsigned long long* plog = nullptr;
+    if (TC && !PASS2 && out.phase_log && (threadIdx.x % kTile) == 0)
+        plog = out.phase_log + ((size_t)blockIdx.x * kGroupsTC + threadIdx.x / kTile) * kPhaseIters * 5;
+#define NMR_PLOG(k) do { if (plog && tile_iter < (uint32_t)kPhaseIters) plog[tile_iter * 5 + (k)] = clock64(); } while (0)
+#define NMR_PLOG_NEXT() (++tile_iter)
+#else
+#define NMR_PLOG(k) do { } while (0)
+#define NMR_PLOG_NEXT() do { } while (0)
+#endif
     while (true) {
+        NMR_PLOG(0);
         // ---- 1. next batch of up to 8 samples for this group's ray, pulling a new ray when the current one has ended ----
         V3 my_pos = v3(0.f, 0.f, 0.f);
         float my_dtw = 0.f, my_t_after = 0.f, t_batch_end = t;
@@ -1027,6 +1039,7 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH
         const bool have = active && !pending_finish && sub < n_valid;
         if (have && sub == 0) ++n_batches;
 
+        NMR_PLOG(1);
         // ---- 2. encode straight into this thread's row of the A operand ----
         if (have) { encode_chunks<kEncodeUnroll>(M, my_pos, a_row, enc_stride); ++evaluated; }
         // tile-wide decisions: run the network when any lane has a sample; leave only when no ray is left (a tile whose
@@ -1039,12 +1052,14 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH
             continue;
         }
 
+        NMR_PLOG(2);     // (after the tile-wide barrier: the slowest lane's encoding)
         // ---- 3. network ----
         float raw[4];
         const V3 dir01 = v3((dir.x + 1.0f) * 0.5f, (dir.y + 1.0f) * 0.5f, (dir.z + 1.0f) * 0.5f);   // warp_direction
         if (TC) network_tc(a_row, tc, dir01, raw);
         else network_scalar(reinterpret_cast<MarchSmem&>(S), dir01, raw);
 
+        NMR_PLOG(3);
         // ---- 4. composite the batch in order (S/ngp/testbed.cu:830-884) ----
         // Every lane first turns ITS OWN sample's network outputs into alpha / colour / depth candidate (the expensive part:
         // an exponential, three logistics, a square root); the group then replays the reference's per-sample recurrence
@@ -1091,6 +1106,8 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH
             if (done || ended) pending_finish = true;
             t = t_batch_end;           // the walk's state: resume point of a paused empty-space walk or of a lens ray's next segment
         }
+        NMR_PLOG(4);
+        NMR_PLOG_NEXT();
     }
 
     // evaluated-sample counter: one atomic per warp

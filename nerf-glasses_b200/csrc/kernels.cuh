@@ -18,7 +18,11 @@ struct FrameOut {
     float* lens_scratch;  // per ray group of the march kernel: state parked across the segments of a lens ray (kLensStash floats each)
     uint32_t* band_counts; // rays queued per band of `band_rows` image rows (nmr_render's row prediction), or null
     int band_rows;
+    // measurement aid (NMR_PHASE_LOG): per warpgroup of the march kernel and tile iteration, clock64 at the iteration's start, after
+    // batch generation, after the encoding, after the network, after compositing: [n_warpgroups][kPhaseIters][5]; null normally
+    unsigned long long* phase_log;
 };
+constexpr int kPhaseIters = 16;
 // The reference's n_steps schedule for frames with MORE than 1/8 live pixels (SurfaceMode auto): pass 1 marches every ray and
 // histograms the sample index at which each ray dies; pass 2 replays clamp(pixels / live rays, 1, 8) per wavefront iteration
 // over that histogram and re-marches the rays that carry a mesh surface with those batch sizes.

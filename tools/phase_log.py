@@ -1,0 +1,46 @@
+"""Where a march tile iteration's time goes (measurement aid).  Needs the instrumented build:
+
+    python nerf-glasses_b200/build.py -DNMR_PHASE_LOG_BUILD --out=$PWD/build/libnmr_phase.so
+    NMR_LIB=$PWD/build/libnmr_phase.so NMR_PHASE_LOG=/tmp/phase.bin python tools/phase_log.py [--regime translucent --zoom 4]
+
+Per warpgroup and tile iteration the kernel stores clock64 at: iteration start, after batch generation, after the encoding (+ the
+tile barrier), after the network, after compositing.  Prints medians per iteration index in microseconds (SM clock 1.965 GHz)."""
+import argparse, os, sys, tempfile
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tools"), os.path.join(ROOT, "nerf-glasses_b200")):
+    sys.path.insert(0, p)
+import numpy as np
+import pynmr, synth
+ap = argparse.ArgumentParser()
+ap.add_argument("--regime", default="opaque"); ap.add_argument("--zoom", type=float, default=0.0); ap.add_argument("--mhz", type=float, default=1965.0)
+a = ap.parse_args()
+path = os.environ["NMR_PHASE_LOG"]
+with tempfile.TemporaryDirectory() as d:
+    snap = os.path.join(d, "s.msgpack"); synth.write_snapshot(snap, seed=1337, log2_hashmap_size=19, regime=a.regime)
+    gltf = synth.write_glasses_gltf(os.path.join(d, "mesh"))
+    r = pynmr.NerfMeshRenderer(1920, 1080, 0)
+    nerf = r.load_nerf(snap); r.load_mesh(gltf, t=synth.GLASSES_T, s=synth.GLASSES_S, r=synth.GLASSES_R_WXYZ); r.remove_floaties()
+if a.zoom:
+    r.orbit(0, 0, a.zoom)
+for i in range(5):
+    r.orbit(0.01, 0.002, 0); r.flush_l2(); r.frame_async(); st = r.stats()
+print(f"frame: gpu_ms {st['gpu_ms']:.3f} march_ms {st['march_ms']:.3f} samples {st['samples']} alive {st['rays_alive']} batches {st['batches']}")
+raw = np.fromfile(path, dtype=np.uint64).reshape(-1, 16, 5).astype(np.int64)
+us = 1.0 / a.mhz
+start = raw[:, 0, 0]
+ok = start > 0
+print(f"warpgroups logged: {int(ok.sum())} of {len(raw)}")
+t00 = start[ok].min()       # (clock64 is per SM: offsets between SMs are only roughly comparable)
+print("iter  n_wg   start(us, vs first)   generate   encode+barrier   network   composite   total")
+for it in range(16):
+    v = raw[:, it, :]
+    m = (v[:, 0] > 0) & (v[:, 4] > v[:, 0])
+    if m.sum() == 0:
+        break
+    v = v[m]
+    d = np.diff(v, axis=1) * us
+    print(f"{it:4d} {int(m.sum()):5d}   {np.median((v[:, 0] - t00)) * us:10.1f}      {np.median(d[:, 0]):8.2f}   {np.median(d[:, 1]):8.2f}   {np.median(d[:, 2]):10.2f}   {np.median(d[:, 3]):8.2f}   {np.median((v[:, 4] - v[:, 0])) * us:8.2f}")
+tot = (raw[:, :, 4] - raw[:, :, 0]) * us
+valid = (raw[:, :, 0] > 0) & (raw[:, :, 4] > raw[:, :, 0])
+per_wg_iters = valid.sum(axis=1)
+print("iterations per warpgroup: median", np.median(per_wg_iters[ok]), "max", per_wg_iters.max(), " busy time per warpgroup (us): median %.1f max %.1f" % (np.median((tot * valid).sum(axis=1)[ok]), (tot * valid).sum(axis=1).max()))
