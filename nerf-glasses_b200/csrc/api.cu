@@ -948,7 +948,7 @@ NMR_API int nmr_render_views(nmr_ctx* ctx, int nerf_id, int n_views, const float
         static const int n_lanes_env = [] { const char* v = std::getenv("NMR_VIEW_LANES"); return v ? std::atoi(v) : 0; }();
         const int n_lanes_auto = px <= ((size_t)1 << 20) ? 8 : (px <= (size_t)1920 * 1080 ? 4 : 2);
         const int K = std::max(1, std::min(std::min(n_lanes_env > 0 ? n_lanes_env : n_lanes_auto, 8), n_views));
-        if (K > 1 && ctx->shard_world == 1) {
+        if (K > 1 && ctx->shard_world == 1 && !(ctx->debug_flags & kDebugKeepProbes)) {      // (parity probes read the context's own surfaces)
             // K views in flight: lane v % K renders view v on its own stream with a march grid of one CTA per SM (K marches fill
             // the SMs together, and one view's tail overlaps the others' set-up); a view leaves over PCIe on the copy stream as
             // soon as it is complete, and a lane renders its next view once its image has been copied out.
