@@ -640,6 +640,7 @@ NMR_API int nmr_create(int width, int height, int device, nmr_ctx** out_ctx) {
     set_camera_from_orbit(ctx.get());
     if (const char* v = std::getenv("NMR_MLP")) if (!std::strcmp(v, "scalar")) ctx->debug_flags |= kDebugScalarMlp;
     if (const char* v = std::getenv("NMR_UMMA_SWAP")) if (!std::strcmp(v, "1")) ctx->debug_flags |= kDebugSwapLboSbo;
+    if (const char* v = std::getenv("NMR_NO_SHARED_ENCODE")) if (!std::strcmp(v, "1")) ctx->debug_flags |= kDebugNoSharedEncode;
     *out_ctx = ctx.release();
     return NMR_OK;
 }

@@ -493,6 +493,16 @@ __device__ __forceinline__ void encode_chunks(const DeviceModel& M, V3 p01, char
     }
 }
 
+// Levels first, first + step, ... of one sample (step lanes share a sample when a warp has few of them, see march_kernel step 2);
+// same destination layout as encode_chunks.  The loop stays rolled: one copy of encode_level in the kernel.
+__device__ __forceinline__ void encode_levels_strided(const DeviceModel& M, V3 p01, char* dst, int chunk_stride, uint32_t first, uint32_t step) {
+#pragma unroll 1
+    for (uint32_t l = first; l < (uint32_t)N_LEVELS; l += step) {
+        const __half2 e = encode_level(M, (int)l, p01);
+        *reinterpret_cast<__half2*>(dst + (size_t)(l >> 2) * chunk_stride + (l & 3u) * 4u) = e;
+    }
+}
+
 // ---- SH degree 4 (T/.../encodings/spherical_harmonics.h:65-98) -------------------------------------------------
 __device__ __forceinline__ void sh4(V3 d01, __half2 out[8]) {
     const float x = d01.x * 2.f - 1.f, y = d01.y * 2.f - 1.f, z = d01.z * 2.f - 1.f;

@@ -1041,7 +1041,27 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH
 
         NMR_PLOG(1);
         // ---- 2. encode straight into this thread's row of the A operand ----
-        if (have) { encode_chunks<kEncodeUnroll>(M, my_pos, a_row, enc_stride); ++evaluated; }
+        // A full warp encodes 32 samples, one per lane, 16 dependent gather rounds each.  In the sparse iterations at the end of a
+        // launch a warp holds few samples and the rounds are pure latency: its lanes then SHARE the samples - with n samples in the
+        // warp, 32 / n' lanes (n' = n rounded up to a power of two) take the levels of one sample between them and write them
+        // into that sample's row of the A tile (rows of a warp's lanes are 16 bytes apart).
+        if (TC && kEncodeUnroll == 1 && !(debug_flags & kDebugNoSharedEncode)) {
+            const uint32_t hm = __ballot_sync(0xffffffffu, have);
+            const uint32_t n_have = (uint32_t)__popc(hm);
+            const uint32_t share = n_have > 16u ? 1u : (n_have > 8u ? 2u : (n_have > 4u ? 4u : (n_have > 2u ? 8u : 16u)));   // lanes per sample
+            uint32_t src = lane, first = 0u;
+            bool work = have;
+            if (share > 1u) {
+                const uint32_t k = lane / share;                    // which of the warp's samples this lane helps with
+                first = lane % share;
+                work = k < n_have;
+                src = work ? __fns(hm, 0u, (int)k + 1) : lane;
+            }
+            const V3 p = v3(__shfl_sync(0xffffffffu, my_pos.x, src), __shfl_sync(0xffffffffu, my_pos.y, src), __shfl_sync(0xffffffffu, my_pos.z, src));
+            if (work) encode_levels_strided(M, p, a_row + ((int)src - (int)lane) * 16, enc_stride, first, share);
+            if (share > 1u) __syncwarp();
+            if (have) ++evaluated;
+        } else if (have) { encode_chunks<kEncodeUnroll>(M, my_pos, a_row, enc_stride); ++evaluated; }
         // tile-wide decisions: run the network when any lane has a sample; leave only when no ray is left (a tile whose
         // rays are all in the middle of a paused empty-space walk has no sample this iteration but must keep going)
         const bool any_have = TC ? group_any(tc.bar_id, have) : (__syncthreads_or(have ? 1 : 0) != 0);

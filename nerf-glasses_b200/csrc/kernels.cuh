@@ -45,7 +45,8 @@ constexpr int kRayRecordFloat4s = 3;   // queue record: (dir.xyz, t) (t_start, t
 enum DebugFlags : uint32_t {
     kDebugScalarMlp = 1u,     // run the CUDA-core MLP instead of tcgen05 (NMR_MLP=scalar)
     kDebugSwapLboSbo = 2u,    // swap the UMMA descriptor offsets (bring-up aid)
-    kDebugKeepProbes = 4u,    // also write the linear frame, depth and per-ray sample counts (nmr_debug_last_frame)
+    kDebugKeepProbes = 4u,
+    kDebugNoSharedEncode = 8u, // every lane encodes its own sample even when the warp holds few (A/B of the shared encoding)    // also write the linear frame, depth and per-ray sample counts (nmr_debug_last_frame)
 };
 
 void launch_occupancy_build(const uint16_t* d_density_grid_fp16, int n_cascades_present, uint8_t* d_bitfield, float* d_scratch, cudaStream_t s);
