@@ -861,11 +861,20 @@ namespace {
 //   other ranks wait until the destination is done with the previous frame, render (their stores cross NVLink), signal;
 //   the destination marks the previous frame consumed, renders its own rows, signals, then waits for every rank's signal -
 //   so once the destination's stream has drained, the shared image holds the whole frame.
-void enqueue_gather_frame(nmr_ctx* ctx, Nerf& n, const FrameParams& P) {
+void enqueue_gather_frame(nmr_ctx* ctx, Nerf& n, const FrameParams& P0) {
     const uint32_t seq = ++ctx->gather_seq;
     uint32_t* f = ctx->gather_flags;
-    if (ctx->gather_is_dst) launch_gather_signal(f + kGatherConsumed, seq - 1u, ctx->stream);
-    else launch_gather_wait(f, kGatherConsumed, 1, seq - 1u, f + kGatherError, ctx->stream);
+    // The destination's NVLink ingress is what a shared frame costs (a 4K float4 frame is 133 MB).  Pixels outside both screen
+    // rectangles are constant background and the rectangles are the same on every rank, so the destination fills those itself,
+    // for all rows, and nobody sends them.
+    FrameParams P = P0;
+    P.bg_filled_elsewhere = 1;
+    if (ctx->gather_is_dst) {
+        launch_gather_signal(f + kGatherConsumed, seq - 1u, ctx->stream);
+        launch_fill_background(P, ctx->frame_target, ctx->stream);
+    } else {
+        launch_gather_wait(f, kGatherConsumed, 1, seq - 1u, f + kGatherError, ctx->stream);
+    }
     enqueue_pass(ctx, n, P, true, ctx->frame_target);
     launch_gather_signal(f + ctx->shard_rank, seq, ctx->stream);
     if (ctx->gather_is_dst) launch_gather_wait(f, 0, ctx->shard_world, seq, f + kGatherError, ctx->stream);

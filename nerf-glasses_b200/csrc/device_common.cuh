@@ -63,6 +63,7 @@ struct FrameParams {
     int tonemap_curve;                // Testbed.tonemap_curve: 0 Identity, 1 ACES, 2 Hable, 3 Reinhard (S/ngp/render_buffer.cu:269-325)
     int shard_rank, shard_world, shard_band;
     int row0;                         // unsharded contexts: first image row of this pass (nmr_render's row ranges), normally 0
+    int bg_filled_elsewhere;          // shared frame target (nmr_gather_*): pixels outside both screen rectangles are written by the destination rank's fill kernel, not by this pass
     int mesh_scale;                   // 0: no mesh stage
     float light[3];
     float cam_inv[9];                 // inverse of [U V W] (row-major), for the rasteriser's bounding boxes

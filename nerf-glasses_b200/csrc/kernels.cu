@@ -436,8 +436,36 @@ __global__ void __launch_bounds__(128) init_rays_kernel(FrameParams P, DeviceMod
     const int y = shard_row(P, ly), ms = P.mesh_scale;
     const bool in_occ = x >= P.occ_px[0] && x < P.occ_px[2] && y >= P.occ_px[1] && y < P.occ_px[3];
     const bool in_mesh = ms > 0 && P.zb_w > 0 && x * ms >= P.zb_x0 && x * ms < P.zb_x0 + P.zb_w && y * ms >= P.zb_y0 && y * ms < P.zb_y0 + P.zb_h;
-    if (!in_occ && !in_mesh) { finish_pixel(P, out, (uint32_t)x + (uint32_t)P.width * (uint32_t)y, 0.f, 0.f, 0.f, 0.f, 0.f, 0u); return; }
+    if (!in_occ && !in_mesh) {
+        const uint32_t idx = (uint32_t)x + (uint32_t)P.width * (uint32_t)y;
+        if (P.bg_filled_elsewhere) {
+            // the constant background of these pixels is written into the shared image by its owner (fill_background_kernel): only
+            // pixels inside the rectangles cross NVLink.  The local accumulator still gets its value (zero stays zero under accumulation).
+            out.accum[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (out.frame) out.frame[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (out.depth) out.depth[idx] = 1e10f;
+            if (out.n_samples) out.n_samples[idx] = 0u;
+        } else {
+            finish_pixel(P, out, idx, 0.f, 0.f, 0.f, 0.f, 0.f, 0u);
+        }
+        return;
+    }
     init_one_ray(P, M, mesh, zbuf, queue, counters, out, x, y, surf_list);
+}
+
+// Shared frame target, destination rank: the constant background of every pixel outside both screen rectangles (the same
+// rectangles on every rank: same camera, same scene), for ALL rows - so that the other ranks only send the pixels inside them.
+__global__ void fill_background_kernel(FrameParams P, float4* __restrict__ image) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= P.width) return;
+    const int ms = P.mesh_scale;
+    const bool in_occ = x >= P.occ_px[0] && x < P.occ_px[2] && y >= P.occ_px[1] && y < P.occ_px[3];
+    const bool in_mesh = ms > 0 && P.zb_w > 0 && x * ms >= P.zb_x0 && x * ms < P.zb_x0 + P.zb_w && y * ms >= P.zb_y0 && y * ms < P.zb_y0 + P.zb_h;
+    if (!in_occ && !in_mesh) image[(size_t)y * P.width + x] = make_float4(P.background_out[0], P.background_out[1], P.background_out[2], P.background_out[3]);
+}
+void launch_fill_background(const FrameParams& P, float4* d_image, cudaStream_t s) {
+    dim3 grid((P.width + 255) / 256, P.height);
+    fill_background_kernel<<<grid, 256, 0, s>>>(P, d_image);
 }
 
 // dst[0] = src[0] (and dst2[0] = src[0] when given) on the stream, without involving a copy engine: a DMA engine busy with a

@@ -63,6 +63,8 @@ void launch_frame_clear(uint32_t* d_counters, uint32_t* d_hist, unsigned long lo
 void launch_latch_word(const uint32_t* d_src, uint32_t* d_dst, uint32_t* d_dst2, cudaStream_t s);
 // sequence flags of a shared frame target (nmr_gather_*): one word per rank + "consumed" + "error", behind the image
 constexpr int kGatherMaxRanks = 32, kGatherConsumed = 32, kGatherError = 33, kGatherFlagWords = 64;
+// destination rank of a shared frame target: constant background of every pixel outside both screen rectangles, all rows
+void launch_fill_background(const FrameParams& P, float4* d_image, cudaStream_t s);
 void launch_gather_signal(uint32_t* d_flag, uint32_t seq, cudaStream_t s);
 void launch_gather_wait(uint32_t* d_flags, int first, int count, uint32_t seq, uint32_t* d_err, cudaStream_t s);
 void launch_init_rays(const FrameParams& P, const DeviceModel& M, const MeshDevice& mesh, const unsigned long long* d_zbuf, int rows_owned,
