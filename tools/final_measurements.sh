@@ -1,3 +1,6 @@
+# The measurement run behind profiles/ (one B200 box, ~3 minutes): GPU tests, bench (both arms), smoke, ncu launch lists, three
+# `ncu --set full` captures, the other BASELINE configs.  Outputs land in gpurun_out/r4_*; tools/ncu_summary.py turns the reports
+# into profiles/r1_*_summary.json.   gpurun --timeout 2400 -- bash tools/final_measurements.sh
 set -x
 timeout 900 python -m pytest tests -m gpu -q > gpurun_out/r4_pytest.log 2>&1; tail -3 gpurun_out/r4_pytest.log
 timeout 600 python bench.py > gpurun_out/r4_bench.json 2> gpurun_out/r4_bench.err; tail -c 600 gpurun_out/r4_bench.json
