@@ -70,6 +70,9 @@ struct Surfaces {
     int w = 0, h = 0;
     DevBuf<float4> image, accum, frame;
     DevBuf<float4> image_alt;        // second image buffer of nmr_render_views (a view renders while the previous one is copied out)
+    DevBuf<float4> bg_image;         // nmr_render: an image of nothing but the background colour (rows known to be background leave from here at once)
+    float bg_value[4] = {-1.f, -1.f, -1.f, -1.f};   // what bg_image holds
+    size_t bg_pixels = 0;
     DevBuf<float> depth;
     DevBuf<uint32_t> n_samples;
     DevBuf<float4> queue;
@@ -505,11 +508,35 @@ BandPlan enqueue_pass_banded(nmr_ctx* ctx, Nerf& n, const FrameParams& P0, float
     const bool sched = prepare_schedule(ctx, P0, sa);
     if (P0.mesh_scale > 0) { launch_mesh_raster(mesh, P0, P0.height, S.zbuf.p, ctx->stream); launches += 1; }
     CK(cudaMemsetAsync(e, 0, sizeof(uint32_t) * 8, ctx->stream));
-    auto copy_rows = [&](int y0, int y1) {
+    auto copy_rows = [&](int y0, int y1, const float4* src = nullptr) {
         if (y1 <= y0) return;
         const size_t off = (size_t)y0 * P0.width;
-        CK(cudaMemcpyAsync(out_host + off * 4, S.image.p + off, (size_t)(y1 - y0) * P0.width * sizeof(float4), cudaMemcpyDeviceToHost, ctx->copy_stream));
+        CK(cudaMemcpyAsync(out_host + off * 4, (src ? src : S.image.p) + off, (size_t)(y1 - y0) * P0.width * sizeof(float4), cudaMemcpyDeviceToHost, ctx->copy_stream));
     };
+    // Rows above and below both screen rectangles (occupied box, mesh) are background whatever the GPU does - the host knows
+    // them before anything is launched.  They leave at once from an image of nothing but the background colour, so the copy
+    // engine, which bounds this call, starts at time zero instead of after the first set-up pass.  (The set-up kernel still
+    // writes them into the device image.)
+    int known_top = 0, known_bot = P0.height;          // rows [0, known_top) and [known_bot, H) are known background
+    {
+        int r0 = P0.height, r1 = 0;                    // rows that may hold anything else: union of the rectangles
+        if (P0.occ_px[2] > P0.occ_px[0] && P0.occ_px[3] > P0.occ_px[1]) { r0 = std::min(r0, P0.occ_px[1]); r1 = std::max(r1, P0.occ_px[3]); }
+        if (P0.mesh_scale > 0 && P0.zb_w > 0 && P0.zb_h > 0) {
+            r0 = std::min(r0, P0.zb_y0 / P0.mesh_scale); r1 = std::max(r1, (P0.zb_y0 + P0.zb_h + P0.mesh_scale - 1) / P0.mesh_scale);
+        }
+        if (r1 <= r0) { known_top = P0.height; known_bot = P0.height; } else { known_top = std::max(0, r0); known_bot = std::min(P0.height, r1); }
+        static const bool off = std::getenv("NMR_NO_KNOWN_ROWS") != nullptr;      // A/B aid
+        if (off) { known_top = 0; known_bot = P0.height; }
+        const size_t px = (size_t)P0.width * P0.height;
+        if (S.bg_pixels != px || std::memcmp(S.bg_value, P0.background_out, 16) != 0) {
+            S.bg_image.ensure(px);
+            std::vector<float4> all(px, make_float4(P0.background_out[0], P0.background_out[1], P0.background_out[2], P0.background_out[3]));
+            CK(cudaMemcpy(S.bg_image.p, all.data(), px * sizeof(float4), cudaMemcpyHostToDevice));       // once per resolution / background colour
+            std::memcpy(S.bg_value, P0.background_out, 16); S.bg_pixels = px;
+        }
+        copy_rows(0, known_top, S.bg_image.p);
+        copy_rows(known_bot, P0.height, S.bg_image.p);
+    }
     auto hand_over = [&](int i, int y0, int y1) {   // everything enqueued so far on the render stream precedes the copy of these rows
         CK(cudaEventRecord(ctx->ev_band[i], ctx->stream));
         CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_band[i], 0));
@@ -527,7 +554,7 @@ BandPlan enqueue_pass_banded(nmr_ctx* ctx, Nerf& n, const FrameParams& P0, float
             CK(cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(uint32_t) * kNumCounters, ctx->stream));
         }
         launch_latch_word(ctx->d_counters.p, e + i + 1, i == 1 ? c : nullptr, ctx->stream);     // (the march cursor starts at e[2])
-        if (i < 2 && rows > 0) hand_over(i, ranges[i][0], ranges[i][1]);
+        if (i < 2 && rows > 0) hand_over(i, std::max(ranges[i][0], i == 0 ? known_top : 0), std::min(ranges[i][1], i == 1 ? known_bot : P0.height));   // (minus the rows that have left already)
     }
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     const uint32_t n_pixels = (uint32_t)P0.width * (uint32_t)P0.height;
@@ -535,7 +562,7 @@ BandPlan enqueue_pass_banded(nmr_ctx* ctx, Nerf& n, const FrameParams& P0, float
         launch_march(P0, n.dev, S.queue.p, ctx->d_counters.p, out, n_pixels, ctx->debug_flags, ctx->num_sms, ctx->stream, e + 3, c, sched ? &sa : nullptr);
         launches += 1;
         if (sched) { enqueue_surface_pass(ctx, n, P0, out, n_pixels, sa); launches += 1; }
-        hand_over(2, plan.y0, plan.y1);
+        hand_over(2, std::max(plan.y0, known_top), std::min(plan.y1, known_bot));      // (the busy block minus the rows that have left already)
     }
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     // small read-backs last: the device->host engine is busy with the image rows, and nothing on the render stream may wait for it
