@@ -22,6 +22,15 @@ for i in range(3000):
         m = r.view_projection_mat; m2 = m.copy(); m2[:, 3] += 0.45 * m2[:, 2]
         out = r.render_views(nerf, np.stack([m, m2]), 640, 360)
         assert np.isfinite(out).all()
+    elif i % 13 == 0:
+        d = nerf.probe_rays(np.random.default_rng(i).uniform(-0.3, 0.3, (257, 3)).astype(np.float32), [0.1, -0.95, 0.1])
+        assert np.isfinite(d).all()
+    elif i % 17 == 0:
+        nerf.tonemap_curve = (i // 17) % 4
+    elif i == 1000:
+        h, ptr = r.gather_create()               # shared frame target, one rank: the flag kernels in the loop for a while
+    elif i == 2000:
+        r.gather_detach()
     else:
         assert r.frame()
     n += 1
