@@ -400,6 +400,15 @@ FrameParams make_params(nmr_ctx* ctx, const Nerf& n, int W, int H, const float* 
 bool prepare_schedule(nmr_ctx* ctx, const FrameParams& P, SchedArgs& sa, bool clear = true) {
     sa = SchedArgs{};
     if (!(P.mesh_scale > 0 && P.zb_w > 0 && P.surface_mode == kSurfaceAuto)) return false;
+    {   // Only pixels inside the two screen rectangles can queue a ray.  When even ALL of them together are at most 1/8 of the pixels
+        // this pass traces, the kernel's own rule (live rays * 8 <= pixels) must come out as "8-sample batches": the schedule replay -
+        // histogram, surface list, second march launch - cannot be needed, whatever the device finds.
+        const long long ms = P.mesh_scale;
+        const long long occ = (long long)std::max(0, P.occ_px[2] - P.occ_px[0]) * std::max(0, P.occ_px[3] - P.occ_px[1]);
+        const long long mesh_px = ((long long)P.zb_w / ms + 2) * ((long long)P.zb_h / ms + 2);
+        const long long traced = (long long)P.width * rows_owned_by(P.height, P.shard_rank, P.shard_world, P.shard_band);
+        if ((occ + mesh_px) * 8 <= traced) return false;
+    }
     Surfaces& S = ctx->surf;
     S.hist.ensure(kSchedBins); S.surf_list.ensure((size_t)P.width * P.height);
     if (clear) CK(cudaMemsetAsync(S.hist.p, 0, sizeof(uint32_t) * kSchedBins, ctx->stream));
