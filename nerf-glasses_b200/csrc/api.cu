@@ -35,6 +35,9 @@ template <typename T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;              // owns device memory
+    DevBuf& operator=(const DevBuf&) = delete;
     void ensure(size_t count) {
         if (count <= n) return;
         if (p) cudaFree(p);
