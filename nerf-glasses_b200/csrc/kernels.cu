@@ -10,6 +10,7 @@
 //
 // Reference behaviour restated per kernel: see the citations at each function and SURVEY.md section 8a.
 #include "kernels.cuh"
+#include <algorithm>
 #include <cstdlib>
 
 #include <cstdio>
@@ -421,7 +422,7 @@ __device__ __forceinline__ void init_one_ray(const FrameParams& P, const DeviceM
 // rectangle of the box around the occupied cells (FrameParams::occ_px, projected on the host) and the mesh's screen rectangle
 // can only be background: integer compares, one store pair, no ray arithmetic - most of a frame in render.py's framing.
 __global__ void __launch_bounds__(128) init_rays_kernel(FrameParams P, DeviceModel M, MeshDevice mesh, const unsigned long long* __restrict__ zbuf, int rows_owned,
-                                                        float4* __restrict__ queue, uint32_t* __restrict__ counters, FrameOut out, uint32_t* __restrict__ surf_list, uint32_t prefetch_lines) {
+                                                        float4* __restrict__ queue, uint32_t* __restrict__ counters, FrameOut out, uint32_t* __restrict__ surf_list, uint32_t prefetch_lines, uint2 block_rot) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // The hash table (23 MiB at log2T 19) is about to be gathered from at random by the march kernel.  When it may have left
     // the L2 since the last frame, a 4-byte gather costs a DRAM round trip per level; the first CTAs of this kernel (background
@@ -430,8 +431,12 @@ __global__ void __launch_bounds__(128) init_rays_kernel(FrameParams P, DeviceMod
         const uint32_t g = (blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
         if (g < prefetch_lines) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(M.grid) + (size_t)g * 128u));
     }
-    const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-    const int ly = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    // CTAs are handed out in index order; the ones over the screen rectangles carry the kernel's long dependent chains (first-hit
+    // walks), so the index space is rotated to start there: those chains begin at time zero and the cheap background CTAs fill in
+    // behind them, instead of the walks starting only when the scheduler reaches the middle of the picture.
+    const int bx = (int)((blockIdx.x + block_rot.x) % gridDim.x), by = (int)((blockIdx.y + block_rot.y) % gridDim.y);
+    const int x = bx * 16 + (warp & 1) * 8 + (lane & 7);
+    const int ly = by * 8 + (warp >> 1) * 4 + (lane >> 3);
     if (x >= P.width || ly >= rows_owned) return;
     const int y = shard_row(P, ly), ms = P.mesh_scale;
     const bool in_occ = x >= P.occ_px[0] && x < P.occ_px[2] && y >= P.occ_px[1] && y < P.occ_px[3];
@@ -514,7 +519,17 @@ void launch_init_rays(const FrameParams& P, const DeviceModel& M, const MeshDevi
     const size_t table_bytes = ((size_t)M.level_offset[N_LEVELS - 1] + M.level_size[N_LEVELS - 1]) * sizeof(__half2);
     const bool first = first_pass < 0 ? reset_counters : first_pass != 0;     // the frame's first set-up pass
     const uint32_t prefetch_lines = (first && !no_prefetch && table_bytes <= ((size_t)48 << 20)) ? (uint32_t)(table_bytes / 128) : 0u;
-    init_rays_kernel<<<grid, 128, 0, s>>>(P, M, mesh, d_zbuf, rows_owned, d_queue, d_counters, out, d_surf_list, prefetch_lines);
+    // first CTA row / column over the screen rectangles (unsharded passes: local row = image row - row0); NMR_NO_BLOCK_ROTATION=1 for A/B runs
+    uint2 rot = make_uint2(0u, 0u);
+    static const bool no_rot = std::getenv("NMR_NO_BLOCK_ROTATION") != nullptr;
+    if (!no_rot && P.shard_world <= 1) {
+        int x0 = P.width, y0 = P.height;
+        if (P.occ_px[2] > P.occ_px[0] && P.occ_px[3] > P.occ_px[1]) { x0 = std::min(x0, P.occ_px[0]); y0 = std::min(y0, P.occ_px[1]); }
+        if (P.mesh_scale > 0 && P.zb_w > 0 && P.zb_h > 0) { x0 = std::min(x0, P.zb_x0 / P.mesh_scale); y0 = std::min(y0, P.zb_y0 / P.mesh_scale); }
+        const int ly0 = y0 - P.row0;
+        if (x0 < P.width && ly0 >= 0 && ly0 < rows_owned) rot = make_uint2((unsigned)(x0 / 16) % grid.x, (unsigned)(ly0 / 8) % grid.y);
+    }
+    init_rays_kernel<<<grid, 128, 0, s>>>(P, M, mesh, d_zbuf, rows_owned, d_queue, d_counters, out, d_surf_list, prefetch_lines, rot);
 }
 
 // =================================================================================================================
