@@ -502,3 +502,37 @@ def test_full_size_frame_properties(tmp_path, glasses_gltf):
     got = a[y0:y0 + ch, x0:x0 + cw]
     assert (ts[y0:y0 + ch, x0:x0 + cw] > 0).mean() > 0.02                 # the window does see the glasses
     assert np.max(np.abs(got - want)) <= PIX_TOL and H.psnr(got, want) >= 45.0
+
+
+def test_render_views_lanes_equal_single_renders(small_snapshot, glasses_gltf):
+    """nmr_render_views keeps up to 8 views in flight (helper contexts on their own streams).  19 hybrid views - more than there are
+    lanes, so lanes are reused behind their copies - must equal 19 separate Testbed.render() calls bit for bit; with
+    to_host=False the last view is what stays readable on the device."""
+    import pynmr
+    import synth
+    path, _ = small_snapshot
+    w, h = 160, 90
+    r = pynmr.NerfMeshRenderer(w, h)
+    nerf = r.load_nerf(path)
+    assert nerf is not None and r.load_mesh(glasses_gltf, t=synth.GLASSES_T, s=synth.GLASSES_S, r=synth.GLASSES_R_WXYZ) is not None
+    r.remove_floaties()
+    r.orbit(0.2, -0.1, 3.0)
+    cams = []
+    for k in range(19):
+        r.orbit(0.11, 0.013 * ((k % 5) - 2), 0.1 * ((k % 3) - 1))
+        cams.append(r.view_projection_mat)
+    cams = np.stack(cams)
+    out = np.asarray(r.render_views(nerf, cams, w, h, linear=False)).copy()
+    assert out.shape == (19, h, w, 4)
+    for k in range(19):
+        r.view_projection_mat = cams[k]
+        single = np.asarray(nerf.render(w, h, 1, linear=False))
+        assert np.array_equal(out[k].view(np.uint32), single.view(np.uint32)), k
+    assert r.render_views(nerf, cams, w, h, linear=False, to_host=False) is None
+    ptr, dw, dh = r.device_image()
+    assert (dw, dh) == (w, h) and ptr
+    import torch
+    last = torch.empty((h, w, 4), dtype=torch.float32, device="cuda")
+    r.copy_device_image(last.data_ptr())
+    assert np.array_equal(last.cpu().numpy().view(np.uint32), out[18].view(np.uint32))
+    assert r.stats()["rays"] == w * h
