@@ -76,6 +76,9 @@ struct Surfaces {
     DevBuf<float4> bg_image;         // nmr_render: an image of nothing but the background colour (rows known to be background leave from here at once)
     float bg_value[4] = {-1.f, -1.f, -1.f, -1.f};   // what bg_image holds
     size_t bg_pixels = 0;
+    int bg_format = -1;
+    int image_format = 0;            // PixelFormat of what `image` holds
+    bool image_is_frame = false;     // `image` holds the last frame() (constructor resolution, float32), not a render() / render_views() result
     DevBuf<float> depth;
     DevBuf<uint32_t> n_samples;
     DevBuf<float4> queue;
@@ -388,6 +391,16 @@ FrameParams make_params(nmr_ctx* ctx, const Nerf& n, int W, int H, const float* 
     P.surface_mode = ctx->surface_mode;
     occupied_screen_box(P);
     mesh_screen_box(ctx, P);
+    if (P.shard_world > 1 && P.surface_mode == kSurfaceAuto) {
+        // A tile-sharded context sees only its own rows: the auto rule's "live rays * 8 <= pixels" and the schedule histogram would
+        // be evaluated per rank, and ranks could decide differently from each other and from the single-GPU frame.  Decide from what
+        // every rank knows alike - the two screen rectangles of the WHOLE frame: when they prove the 8-sample batches (render.py's
+        // framing, every BASELINE config) use them, otherwise the exact position (both are ray-local rules).
+        const long long ms = P.mesh_scale > 0 ? P.mesh_scale : 1;
+        const long long occ = (long long)std::max(0, P.occ_px[2] - P.occ_px[0]) * std::max(0, P.occ_px[3] - P.occ_px[1]);
+        const long long mesh_px = P.mesh_scale > 0 ? ((long long)P.zb_w / ms + 2) * ((long long)P.zb_h / ms + 2) : 0;
+        P.surface_mode = (occ + mesh_px) * 8 <= (long long)P.width * P.height ? kSurfaceBatch8 : kSurfaceExact;
+    }
     P.lens_on = (P.mesh_scale > 0 && ctx->scene_has_lens && ctx->lens_enabled) ? 1 : 0;
     {
         const float r0 = (ctx->lens_ior - 1.f) / (ctx->lens_ior + 1.f);
@@ -426,12 +439,13 @@ void enqueue_surface_pass(nmr_ctx* ctx, Nerf& n, const FrameParams& P, const Fra
 }
 
 // one sample-per-pixel pass: mesh stage -> init -> march.  Enqueues only; no host synchronisation.
-void enqueue_pass(nmr_ctx* ctx, Nerf& n, const FrameParams& P, bool timed, float4* image_target = nullptr) {
+void enqueue_pass(nmr_ctx* ctx, Nerf& n, const FrameParams& P, bool timed, void* image_target = nullptr) {
     Surfaces& S = ctx->surf;
     const int rows = rows_owned_by(P.height, P.shard_rank, P.shard_world, P.shard_band);
     // the linear frame, depth and per-ray sample counts are parity probes (nmr_debug_last_frame): written only on request
     const bool probes = (ctx->debug_flags & kDebugKeepProbes) != 0;
-    FrameOut out{image_target ? image_target : S.image.p, S.accum.p, probes ? S.frame.p : nullptr, probes ? S.depth.p : nullptr, probes ? S.n_samples.p : nullptr, nullptr, nullptr};
+    FrameOut out{image_target ? image_target : static_cast<void*>(S.image.p), S.accum.p, probes ? S.frame.p : nullptr, probes ? S.depth.p : nullptr, probes ? S.n_samples.p : nullptr, nullptr, nullptr};
+    if (!image_target) { S.image_format = P.out_format; S.image_is_frame = false; }
     static const char* phase_log_path = std::getenv("NMR_PHASE_LOG");      // measurement aid: see FrameOut::phase_log
     if (phase_log_path && timed) {
         const size_t words = (size_t)ctx->num_sms * 4 * 2 * kPhaseIters * 5;
@@ -483,9 +497,11 @@ void enqueue_pass(nmr_ctx* ctx, Nerf& n, const FrameParams& P, bool timed, float
 constexpr int kBands = 12;
 struct BandPlan { int y0, y1; };     // busy rows [y0, y1); ranges in queue order: [0, y0), [y1, H), [y0, y1)
 
-BandPlan enqueue_pass_banded(nmr_ctx* ctx, Nerf& n, const FrameParams& P0, float* out_host) {
+BandPlan enqueue_pass_banded(nmr_ctx* ctx, Nerf& n, const FrameParams& P0, void* out_host) {
     constexpr int K = kBands;
     Surfaces& S = ctx->surf;
+    const size_t bpp = pixel_bytes(P0.out_format);
+    S.image_format = P0.out_format; S.image_is_frame = false;
     const int band_rows = (P0.height + K - 1) / K;
     const bool probes = (ctx->debug_flags & kDebugKeepProbes) != 0;
     FrameOut out{S.image.p, S.accum.p, probes ? S.frame.p : nullptr, probes ? S.depth.p : nullptr, probes ? S.n_samples.p : nullptr, nullptr, nullptr};
@@ -520,10 +536,10 @@ BandPlan enqueue_pass_banded(nmr_ctx* ctx, Nerf& n, const FrameParams& P0, float
     const bool sched = prepare_schedule(ctx, P0, sa);
     if (P0.mesh_scale > 0) { launch_mesh_raster(mesh, P0, P0.height, S.zbuf.p, ctx->stream); launches += 1; }
     CK(cudaMemsetAsync(e, 0, sizeof(uint32_t) * 8, ctx->stream));
-    auto copy_rows = [&](int y0, int y1, const float4* src = nullptr) {
+    auto copy_rows = [&](int y0, int y1, const void* src = nullptr) {
         if (y1 <= y0) return;
-        const size_t off = (size_t)y0 * P0.width;
-        CK(cudaMemcpyAsync(out_host + off * 4, (src ? src : S.image.p) + off, (size_t)(y1 - y0) * P0.width * sizeof(float4), cudaMemcpyDeviceToHost, ctx->copy_stream));
+        const size_t off = (size_t)y0 * P0.width * bpp;
+        CK(cudaMemcpyAsync(static_cast<char*>(out_host) + off, static_cast<const char*>(src ? src : static_cast<const void*>(S.image.p)) + off, (size_t)(y1 - y0) * P0.width * bpp, cudaMemcpyDeviceToHost, ctx->copy_stream));
     };
     // Rows above and below both screen rectangles (occupied box, mesh) are background whatever the GPU does - the host knows
     // them before anything is launched.  They leave at once from an image of nothing but the background colour, so the copy
@@ -540,11 +556,13 @@ BandPlan enqueue_pass_banded(nmr_ctx* ctx, Nerf& n, const FrameParams& P0, float
         static const bool off = std::getenv("NMR_NO_KNOWN_ROWS") != nullptr;      // A/B aid
         if (off) { known_top = 0; known_bot = P0.height; }
         const size_t px = (size_t)P0.width * P0.height;
-        if (S.bg_pixels != px || std::memcmp(S.bg_value, P0.background_out, 16) != 0) {
-            S.bg_image.ensure(px);
-            std::vector<float4> all(px, make_float4(P0.background_out[0], P0.background_out[1], P0.background_out[2], P0.background_out[3]));
-            CK(cudaMemcpy(S.bg_image.p, all.data(), px * sizeof(float4), cudaMemcpyHostToDevice));       // once per resolution / background colour
-            std::memcpy(S.bg_value, P0.background_out, 16); S.bg_pixels = px;
+        if (S.bg_pixels != px || S.bg_format != P0.out_format || std::memcmp(S.bg_value, P0.background_out, 16) != 0) {
+            S.bg_image.ensure(px);      // (float4 capacity: enough for every format)
+            FrameParams Pb = P0;        // every pixel "outside both rectangles": the fill kernel writes the constant in the frame's format
+            Pb.occ_px[0] = Pb.occ_px[1] = Pb.occ_px[2] = Pb.occ_px[3] = 0; Pb.mesh_scale = 0; Pb.zb_w = Pb.zb_h = 0;
+            launch_fill_background(Pb, S.bg_image.p, ctx->stream);                                       // once per resolution / background colour / format
+            CK(cudaStreamSynchronize(ctx->stream));
+            std::memcpy(S.bg_value, P0.background_out, 16); S.bg_pixels = px; S.bg_format = P0.out_format;
         }
         copy_rows(0, known_top, S.bg_image.p);
         copy_rows(known_bot, P0.height, S.bg_image.p);
@@ -931,8 +949,15 @@ NMR_API int nmr_frame(nmr_ctx* ctx, int* keep_running) {
         ctx->surf.resize(ctx->width, ctx->height, ctx->mesh_scale);
         const FrameParams P = make_params(ctx, n, ctx->width, ctx->height, ctx->cam12, ctx->surf.spp, true, true);
         if (ctx->frame_target) enqueue_gather_frame(ctx, n, P); else enqueue_pass(ctx, n, P, true);
+        ctx->surf.image_is_frame = true;
         ++ctx->surf.spp;
         CK(cudaStreamSynchronize(ctx->stream));   // frame() returns a finished frame (S/nerf_mesh_renderer.cu:578)
+        if (ctx->frame_target && ctx->gather_is_dst) {
+            // a wait of the shared-frame protocol that ran out of time leaves an incomplete image: fail this frame, not the detach
+            uint32_t err = 0;
+            CK(cudaMemcpy(&err, ctx->gather_flags + kGatherError, sizeof(err), cudaMemcpyDeviceToHost));
+            if (err) return fail(ctx, NMR_ERR_STATE, "shared frame target: a rank did not deliver its rows in time; the image is incomplete");
+        }
         return NMR_OK;
     });
 }
@@ -941,16 +966,22 @@ NMR_API int nmr_read_frame(nmr_ctx* ctx, float* out_rgba) {
     return guarded(ctx, [&]() -> int {
         if (!out_rgba) return fail(ctx, NMR_ERR_INVALID, "out_rgba is null");
         if (!ctx->surf.image.p || ctx->surf.w == 0) return fail(ctx, NMR_ERR_STATE, "nothing rendered yet");
-        const float4* src = (ctx->gather_image.p && ctx->frame_target == ctx->gather_image.p && ctx->surf.w == ctx->width && ctx->surf.h == ctx->height) ? ctx->gather_image.p : ctx->surf.image.p;
-        CK(cudaMemcpyAsync(out_rgba, src, (size_t)ctx->surf.w * ctx->surf.h * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+        // the caller's buffer holds width * height float4 of the CONSTRUCTOR resolution: only the image of a frame() may go there
+        // (render() / render_views() resize the surfaces to their own resolution and format)
+        if (!ctx->surf.image_is_frame || ctx->surf.w != ctx->width || ctx->surf.h != ctx->height || ctx->surf.image_format != kPixelF32)
+            return fail(ctx, NMR_ERR_STATE, "the last image on this context is not a frame(): call frame() before read_frame()");
+        const float4* src = (ctx->gather_image.p && ctx->frame_target == ctx->gather_image.p) ? ctx->gather_image.p : ctx->surf.image.p;
+        CK(cudaMemcpyAsync(out_rgba, src, (size_t)ctx->width * ctx->height * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         return NMR_OK;
     });
 }
 
-NMR_API int nmr_render(nmr_ctx* ctx, int nerf_id, int width, int height, int spp, int linear, float* out_rgba) {
+NMR_API int nmr_render_format(nmr_ctx* ctx, int nerf_id, int width, int height, int spp, int linear, int format, void* out_rgba) {
     return guarded(ctx, [&]() -> int {
         if (width <= 0 || height <= 0 || spp < 1 || !out_rgba) return fail(ctx, NMR_ERR_INVALID, "bad render arguments");
+        if (format < NMR_PIXEL_F32 || format > NMR_PIXEL_U8) return fail(ctx, NMR_ERR_INVALID, "bad pixel format");
+        const size_t bpp = pixel_bytes(format);
         Nerf* n;
         try { n = get_nerf(ctx, nerf_id); } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); }
         upload_mesh_if_dirty(ctx);
@@ -961,7 +992,8 @@ NMR_API int nmr_render(nmr_ctx* ctx, int nerf_id, int width, int height, int spp
         static const bool no_bands = std::getenv("NMR_NO_BANDS") != nullptr;     // measurement aid: plain render + one copy
         if (spp == 1 && ctx->shard_world == 1 && height >= 256 && !no_bands) {
             // one sample per pixel: bands of rows are copied out while the next ones are still being marched
-            const FrameParams P = make_params(ctx, *n, width, height, ctx->cam12, 0, !linear, true);
+            FrameParams P = make_params(ctx, *n, width, height, ctx->cam12, 0, !linear, true);
+            P.out_format = format;
             const BandPlan plan = enqueue_pass_banded(ctx, *n, P, out_rgba);
             CK(cudaStreamSynchronize(ctx->copy_stream));
             CK(cudaStreamSynchronize(ctx->stream));
@@ -974,20 +1006,27 @@ NMR_API int nmr_render(nmr_ctx* ctx, int nerf_id, int width, int height, int spp
             // a band that used to be empty queued rays this time and was copied out unmarched: render the frame the plain way
         }
         for (int i = 0; i < spp; ++i) {
-            const FrameParams P = make_params(ctx, *n, width, height, ctx->cam12, ctx->surf.spp, !linear, true);
+            FrameParams P = make_params(ctx, *n, width, height, ctx->cam12, ctx->surf.spp, !linear, true);
+            P.out_format = format;
             enqueue_pass(ctx, *n, P, i == spp - 1);
             ++ctx->surf.spp;
         }
-        CK(cudaMemcpyAsync(out_rgba, ctx->surf.image.p, (size_t)width * height * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(out_rgba, ctx->surf.image.p, (size_t)width * height * bpp, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         ctx->surf.spp = 0;   // the next frame() starts a fresh accumulation at its own resolution
         return NMR_OK;
     });
 }
+NMR_API int nmr_render(nmr_ctx* ctx, int nerf_id, int width, int height, int spp, int linear, float* out_rgba) {
+    return nmr_render_format(ctx, nerf_id, width, height, spp, linear, NMR_PIXEL_F32, out_rgba);
+}
 
-NMR_API int nmr_render_views(nmr_ctx* ctx, int nerf_id, int n_views, const float* cams12, int width, int height, int linear, float* out_rgba) {
+NMR_API int nmr_render_views_format(nmr_ctx* ctx, int nerf_id, int n_views, const float* cams12, int width, int height, int linear, int format, void* out_rgba_v) {
     return guarded(ctx, [&]() -> int {
         if (width <= 0 || height <= 0 || n_views < 1 || !cams12) return fail(ctx, NMR_ERR_INVALID, "bad render_views arguments");
+        if (format < NMR_PIXEL_F32 || format > NMR_PIXEL_U8) return fail(ctx, NMR_ERR_INVALID, "bad pixel format");
+        const size_t bpp = pixel_bytes(format);
+        char* out_rgba = static_cast<char*>(out_rgba_v);
         Nerf* n;
         try { n = get_nerf(ctx, nerf_id); } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); }
         upload_mesh_if_dirty(ctx);
@@ -1013,17 +1052,19 @@ NMR_API int nmr_render_views(nmr_ctx* ctx, int nerf_id, int n_views, const float
             for (int v = 0; v < n_views; ++v) {
                 nmr_ctx* l = ctx->lanes[(size_t)(v % K)];
                 if (v >= K && out_rgba) CK(cudaStreamWaitEvent(l->stream, l->ev_view[0][1], 0));      // the lane's previous image has been copied out
-                const FrameParams P = make_params(ctx, *n, width, height, cams12 + (size_t)v * 12, 0, !linear, true);
+                FrameParams P = make_params(ctx, *n, width, height, cams12 + (size_t)v * 12, 0, !linear, true);
+                P.out_format = format;
                 enqueue_pass(l, *n, P, v == n_views - 1);
                 if (!out_rgba) continue;                                                   // images stay on the device
                 CK(cudaEventRecord(l->ev_view[0][0], l->stream));
                 CK(cudaStreamWaitEvent(ctx->copy_stream, l->ev_view[0][0], 0));
-                CK(cudaMemcpyAsync(out_rgba + (size_t)v * px * 4, l->surf.image.p, px * sizeof(float4), cudaMemcpyDeviceToHost, ctx->copy_stream));
+                CK(cudaMemcpyAsync(out_rgba + (size_t)v * px * bpp, l->surf.image.p, px * bpp, cudaMemcpyDeviceToHost, ctx->copy_stream));
                 CK(cudaEventRecord(l->ev_view[0][1], ctx->copy_stream));
             }
             nmr_ctx* last = ctx->lanes[(size_t)((n_views - 1) % K)];
             // nmr_get_device_image / nmr_get_stats after the call refer to the last view
-            CK(cudaMemcpyAsync(ctx->surf.image.p, last->surf.image.p, px * sizeof(float4), cudaMemcpyDeviceToDevice, last->stream));
+            CK(cudaMemcpyAsync(ctx->surf.image.p, last->surf.image.p, px * bpp, cudaMemcpyDeviceToDevice, last->stream));
+            ctx->surf.image_format = format; ctx->surf.image_is_frame = false;
             CK(cudaStreamSynchronize(ctx->copy_stream));
             for (int k = 0; k < K; ++k) CK(cudaStreamSynchronize(ctx->lanes[(size_t)k]->stream));
             finish_stats(last);
@@ -1032,29 +1073,33 @@ NMR_API int nmr_render_views(nmr_ctx* ctx, int nerf_id, int n_views, const float
             return NMR_OK;
         }
         // one view at a time (sharded contexts, NMR_VIEW_LANES=1): two image buffers, two streams - view v renders into buffer
-        // v % 2 while view v - 1 leaves the other one over PCIe.
+        // v % 2 while view v - 1 leaves the other one over PCIe.  (The target is handed to enqueue_pass explicitly: the two
+        // DevBufs keep owning their own allocation whatever happens in between.)
         Surfaces& S = ctx->surf;
         S.image_alt.ensure(px);
         float4* bufs[2] = {S.image.p, S.image_alt.p};
         for (int v = 0; v < n_views; ++v) {
             const int b = v & 1;
             if (v >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_view[b][1], 0));      // buffer b has been copied out
-            S.image.p = bufs[b];
-            const FrameParams P = make_params(ctx, *n, width, height, cams12 + (size_t)v * 12, 0, !linear, true);
-            enqueue_pass(ctx, *n, P, v == n_views - 1);
+            FrameParams P = make_params(ctx, *n, width, height, cams12 + (size_t)v * 12, 0, !linear, true);
+            P.out_format = format;
+            enqueue_pass(ctx, *n, P, v == n_views - 1, bufs[b]);
             CK(cudaEventRecord(ctx->ev_view[b][0], ctx->stream));
             if (!out_rgba) { CK(cudaEventRecord(ctx->ev_view[b][1], ctx->stream)); continue; }
             CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_view[b][0], 0));
-            CK(cudaMemcpyAsync(out_rgba + (size_t)v * px * 4, bufs[b], px * sizeof(float4), cudaMemcpyDeviceToHost, ctx->copy_stream));
+            CK(cudaMemcpyAsync(out_rgba + (size_t)v * px * bpp, bufs[b], px * bpp, cudaMemcpyDeviceToHost, ctx->copy_stream));
             CK(cudaEventRecord(ctx->ev_view[b][1], ctx->copy_stream));
         }
-        S.image.p = bufs[0];
         if (((n_views - 1) & 1) == 1) { std::swap(S.image.p, S.image_alt.p); std::swap(S.image.n, S.image_alt.n); }   // nmr_get_device_image: the last view's buffer
+        S.image_format = format; S.image_is_frame = false;
         CK(cudaStreamSynchronize(ctx->copy_stream));
         CK(cudaStreamSynchronize(ctx->stream));
         ctx->surf.spp = 0;
         return NMR_OK;
     });
+}
+NMR_API int nmr_render_views(nmr_ctx* ctx, int nerf_id, int n_views, const float* cams12, int width, int height, int linear, float* out_rgba) {
+    return nmr_render_views_format(ctx, nerf_id, n_views, cams12, width, height, linear, NMR_PIXEL_F32, out_rgba);
 }
 
 NMR_API int nmr_get_device_image(nmr_ctx* ctx, void** out_dev_ptr, int* out_w, int* out_h) {
@@ -1067,10 +1112,12 @@ NMR_API int nmr_get_device_image(nmr_ctx* ctx, void** out_dev_ptr, int* out_w, i
     });
 }
 
-NMR_API int nmr_copy_device_image(nmr_ctx* ctx, void* dst) {
+NMR_API int nmr_copy_device_image(nmr_ctx* ctx, void* dst, size_t dst_bytes) {
     return guarded(ctx, [&]() -> int {
         if (!ctx->surf.image.p || !dst) return fail(ctx, NMR_ERR_STATE, "nothing rendered yet");
-        CK(cudaMemcpyAsync(dst, ctx->surf.image.p, (size_t)ctx->surf.w * ctx->surf.h * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+        const size_t bytes = (size_t)ctx->surf.w * ctx->surf.h * pixel_bytes(ctx->surf.image_format);
+        if (dst_bytes < bytes) return fail(ctx, NMR_ERR_INVALID, "destination holds " + std::to_string(dst_bytes) + " bytes, the last image has " + std::to_string(bytes));
+        CK(cudaMemcpyAsync(dst, ctx->surf.image.p, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         return NMR_OK;
     });
@@ -1160,6 +1207,7 @@ NMR_API int nmr_frame_async(nmr_ctx* ctx) {
         ctx->surf.resize(ctx->width, ctx->height, ctx->mesh_scale);
         const FrameParams P = make_params(ctx, n, ctx->width, ctx->height, ctx->cam12, ctx->surf.spp, true, true);
         if (ctx->frame_target) enqueue_gather_frame(ctx, n, P); else enqueue_pass(ctx, n, P, true);
+        ctx->surf.image_is_frame = true;
         ++ctx->surf.spp;
         return NMR_OK;
     });
@@ -1356,6 +1404,32 @@ NMR_API int nmr_debug_last_frame(nmr_ctx* ctx, float* o_frame, float* o_depth, u
         CK(cudaStreamSynchronize(ctx->stream));
         return NMR_OK;
     });
+}
+
+NMR_API int nmr_debug_parse_gltf(const char* path, int64_t out_counts[5], char* err, size_t err_len) {
+    auto put = [&](const std::string& m) { if (err && err_len) { std::snprintf(err, err_len, "%s", m.c_str()); } };
+    put("");
+    if (!path) { put("path is null"); return NMR_ERR_INVALID; }
+    try {
+        const HostMesh m = load_gltf(path);
+        if (out_counts) {
+            int64_t lens = 0; for (uint8_t f : m.tri_lens) lens += f ? 1 : 0;
+            out_counts[0] = (int64_t)(m.positions.size() / 3); out_counts[1] = (int64_t)(m.indices.size() / 3); out_counts[2] = lens;
+            out_counts[3] = m.tex_w; out_counts[4] = m.tex_h;
+        }
+        // what nmr_load_mesh does next on the host: the arrays transform_mesh walks must cover every vertex
+        std::vector<float> wp, wn;
+        const float t[3] = {0.f, 0.f, 0.f}, sc[3] = {1.f, 1.f, 1.f}, q[4] = {0.f, 0.f, 0.f, 1.f};
+        transform_mesh(m, t, sc, q, wp, wn);
+        if (!m.warning.empty()) put(m.warning);
+        return NMR_OK;
+    } catch (const std::bad_alloc&) {
+        put("out of host memory"); return NMR_ERR_INVALID;
+    } catch (const std::exception& e) {
+        const std::string msg = e.what();
+        put(msg);
+        return msg.rfind("cannot open", 0) == 0 ? NMR_ERR_IO : NMR_ERR_FORMAT;
+    }
 }
 
 // debug knob: bit 0 CUDA-core MLP, bit 1 swap UMMA descriptor offsets

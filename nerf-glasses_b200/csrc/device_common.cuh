@@ -78,7 +78,24 @@ struct FrameParams {
     // transmission * tint and its mean.  lens_on == 0: no lens triangles in this frame.
     int lens_on;
     float lens_f0, lens_k[3], lens_kmean;
+    int out_format;                   // PixelFormat of FrameOut::image (nmr_pixel_format of include/nmr.h)
 };
+
+// Displayed image formats.  kPixelU8 is what render.py turns every frame into on the host (np.uint8(img * 255), V/render.py:62-66):
+// trunc(clamp(v, 0, 1) * 255) with the product rounded to fp32 first, like numpy's float32 arithmetic followed by the C cast.
+enum PixelFormat : int { kPixelF32 = 0, kPixelF16 = 1, kPixelU8 = 2 };
+__device__ __forceinline__ void store_pixel(void* __restrict__ image, int fmt, uint32_t idx, float r, float g, float b, float a) {
+    if (fmt == kPixelF32) {
+        reinterpret_cast<float4*>(image)[idx] = make_float4(r, g, b, a);
+    } else if (fmt == kPixelU8) {
+        const uint32_t ur = __float2uint_rz(__saturatef(r) * 255.0f), ug = __float2uint_rz(__saturatef(g) * 255.0f);
+        const uint32_t ub = __float2uint_rz(__saturatef(b) * 255.0f), ua = __float2uint_rz(__saturatef(a) * 255.0f);
+        reinterpret_cast<uint32_t*>(image)[idx] = ur | (ug << 8) | (ub << 16) | (ua << 24);
+    } else {
+        const __half2 lo = __floats2half2_rn(r, g), hi = __floats2half2_rn(b, a);
+        reinterpret_cast<uint2*>(image)[idx] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+    }
+}
 
 // The reference blends the mesh surface in front of the first sample of the n_steps BATCH whose end passed t_surface
 // (composite_kernel_nerf tests payload.t, which generate_next_nerf_network_inputs has already advanced past the whole

@@ -267,7 +267,7 @@ void decode_png(const uint8_t* data, size_t size, int& w, int& h, std::vector<ui
         switch (color_type) {
             case 0: r = g = b = s[0]; break;
             case 2: r = s[0]; g = s[1]; b = s[2]; break;
-            case 3: { const size_t k = s[0]; if (k * 3 + 2 >= palette.size() + 0 && k * 3 + 2 > palette.size()) throw std::runtime_error("png: palette index out of range");
+            case 3: { const size_t k = s[0]; if (k * 3 + 2 >= palette.size()) throw std::runtime_error("png: palette index out of range");
                       r = palette[k * 3]; g = palette[k * 3 + 1]; b = palette[k * 3 + 2]; if (k < trns.size()) a = trns[k]; break; }
             case 4: r = g = b = s[0]; a = s[1]; break;
             default: r = s[0]; g = s[1]; b = s[2]; a = s[3]; break;
@@ -331,37 +331,56 @@ HostMesh load_gltf(const std::string& path) {
         if (b.contains("uri")) buffers.push_back(load_uri(b.at("uri").as_string(), base_dir));
         else buffers.push_back(glb_bin);
     }
+    // every offset / length / count / index of the document is untrusted: negative values are rejected before the cast to size_t,
+    // and range checks are written so that they cannot wrap (len > size || off > size - len)
+    auto nonneg = [](int64_t v, const char* what) -> size_t {
+        if (v < 0) throw std::runtime_error(std::string("gltf: negative ") + what);
+        return (size_t)v;
+    };
+    auto elem = [&](const char* array, int64_t idx) -> const Value& {
+        if (!doc.contains(array)) throw std::runtime_error(std::string("gltf: no ") + array);
+        const Value& arr = doc.at(array);
+        if (idx < 0 || (size_t)idx >= arr.size()) throw std::runtime_error(std::string("gltf: index into ") + array + " out of range");
+        return arr.at((size_t)idx);
+    };
     auto view_bytes = [&](int64_t view_idx, size_t& stride) -> std::pair<const uint8_t*, size_t> {
-        const Value& bv = doc.at("bufferViews").at((size_t)view_idx);
-        const size_t bi = (size_t)bv.at("buffer").as_int();
+        const Value& bv = elem("bufferViews", view_idx);
+        const size_t bi = nonneg(bv.at("buffer").as_int(), "buffer index");
         if (bi >= buffers.size()) throw std::runtime_error("gltf: buffer index out of range");
-        const size_t off = (size_t)bv.value_int("byteOffset", 0), len = (size_t)bv.at("byteLength").as_int();
-        if (off + len > buffers[bi].size()) throw std::runtime_error("gltf: bufferView exceeds buffer");
-        stride = (size_t)bv.value_int("byteStride", 0);
+        const size_t off = nonneg(bv.value_int("byteOffset", 0), "byteOffset"), len = nonneg(bv.at("byteLength").as_int(), "byteLength");
+        const size_t size = buffers[bi].size();
+        if (len > size || off > size - len) throw std::runtime_error("gltf: bufferView exceeds buffer");
+        stride = nonneg(bv.value_int("byteStride", 0), "byteStride");
+        if (stride > 4096) throw std::runtime_error("gltf: byteStride out of range");
         return {buffers[bi].data() + off, len};
     };
+    // accessor of `count` elements of `esz` bytes, `stride` apart, starting `off` bytes into a view of `avail` bytes
+    auto check_span = [](size_t count, size_t off, size_t stride, size_t esz, size_t avail, const char* what) {
+        if (!count) return;
+        if (esz > avail || off > avail - esz || (count - 1) > (avail - esz - off) / (stride ? stride : 1)) throw std::runtime_error(std::string("gltf: ") + what + " exceeds bufferView");
+    };
     auto read_accessor_f32 = [&](int64_t acc_idx, int ncomp, std::vector<float>& out) {
-        const Value& a = doc.at("accessors").at((size_t)acc_idx);
+        const Value& a = elem("accessors", acc_idx);
         if (a.at("componentType").as_int() != 5126) throw std::runtime_error("gltf: vertex attributes must be float");
         const std::string type = a.at("type").as_string();
         const int have = type == "SCALAR" ? 1 : type == "VEC2" ? 2 : type == "VEC3" ? 3 : type == "VEC4" ? 4 : 0;
         if (have < ncomp) throw std::runtime_error("gltf: accessor type too narrow");
         size_t stride; auto vb = view_bytes(a.at("bufferView").as_int(), stride);
-        const size_t count = (size_t)a.at("count").as_int(), off = (size_t)a.value_int("byteOffset", 0);
+        const size_t count = nonneg(a.at("count").as_int(), "accessor count"), off = nonneg(a.value_int("byteOffset", 0), "accessor byteOffset");
         if (!stride) stride = (size_t)have * 4;
-        if (count && off + (count - 1) * stride + (size_t)ncomp * 4 > vb.second) throw std::runtime_error("gltf: accessor exceeds bufferView");
+        check_span(count, off, stride, (size_t)ncomp * 4, vb.second, "accessor");
         for (size_t i = 0; i < count; ++i) for (int c = 0; c < ncomp; ++c) { float f; std::memcpy(&f, vb.first + off + i * stride + (size_t)c * 4, 4); out.push_back(f); }
         return count;
     };
     auto read_indices = [&](int64_t acc_idx, uint32_t base, std::vector<uint32_t>& out) {
-        const Value& a = doc.at("accessors").at((size_t)acc_idx);
+        const Value& a = elem("accessors", acc_idx);
         const int64_t ct = a.at("componentType").as_int();
         const size_t esz = ct == 5121 ? 1 : ct == 5123 ? 2 : ct == 5125 ? 4 : 0;
         if (!esz) throw std::runtime_error("gltf: unsupported index type");
         size_t stride; auto vb = view_bytes(a.at("bufferView").as_int(), stride);
-        const size_t count = (size_t)a.at("count").as_int(), off = (size_t)a.value_int("byteOffset", 0);
+        const size_t count = nonneg(a.at("count").as_int(), "accessor count"), off = nonneg(a.value_int("byteOffset", 0), "accessor byteOffset");
         if (!stride) stride = esz;
-        if (count && off + (count - 1) * stride + esz > vb.second) throw std::runtime_error("gltf: index accessor exceeds bufferView");
+        check_span(count, off, stride, esz, vb.second, "index accessor");
         for (size_t i = 0; i < count; ++i) {
             const uint8_t* q = vb.first + off + i * stride;
             uint32_t v = esz == 1 ? q[0] : esz == 2 ? (uint32_t)(q[0] | (q[1] << 8)) : (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
@@ -370,7 +389,7 @@ HostMesh load_gltf(const std::string& path) {
     };
 
     HostMesh m;
-    const size_t scene_idx = (size_t)doc.value_int("scene", 0);
+    const size_t scene_idx = nonneg(doc.value_int("scene", 0), "scene index");
     if (!doc.contains("scenes") || scene_idx >= doc.at("scenes").size()) throw std::runtime_error("gltf: no default scene");
     const Value& scene_nodes = doc.at("scenes").at(scene_idx).at("nodes");
     if (scene_nodes.size() == 0) throw std::runtime_error("gltf: scene has no nodes");
@@ -379,21 +398,27 @@ HostMesh load_gltf(const std::string& path) {
     std::vector<int64_t> stack;
     for (size_t i = scene_nodes.size(); i-- > 0;) stack.push_back(scene_nodes.at(i).as_int());
     bool missing_normals = false;
+    // a node is visited once: a child list that leads back to an ancestor (or a node shared by two parents) is not a tree
+    std::vector<uint8_t> visited(doc.contains("nodes") ? doc.at("nodes").size() : 0, 0);
     while (!stack.empty()) {
         const int64_t ni = stack.back(); stack.pop_back();
-        const Value& node = doc.at("nodes").at((size_t)ni);
+        const Value& node = elem("nodes", ni);
+        if (visited[(size_t)ni]) throw std::runtime_error("gltf: node graph is not a tree (cycle or shared node)");
+        visited[(size_t)ni] = 1;
         if (node.contains("children")) for (const Value& c : node.at("children").arr) stack.push_back(c.as_int());
         if (!node.contains("mesh")) continue;
-        const Value& mesh = doc.at("meshes").at((size_t)node.at("mesh").as_int());
+        const Value& mesh = elem("meshes", node.at("mesh").as_int());
         for (const Value& prim : mesh.at("primitives").arr) {
             if (prim.value_int("mode", 4) != 4) continue;   // triangles only
             const Value& attrs = prim.at("attributes");
             if (!attrs.contains("POSITION")) continue;
             const uint32_t base = (uint32_t)(m.positions.size() / 3);
             const size_t nv = read_accessor_f32(attrs.at("POSITION").as_int(), 3, m.positions);
-            if (attrs.contains("NORMAL")) read_accessor_f32(attrs.at("NORMAL").as_int(), 3, m.normals);
+            // every attribute of a primitive has one entry per vertex (glTF 2.0, 3.7.2.1): a shorter NORMAL / TEXCOORD_0 accessor
+            // would leave transform_mesh and the shader reading past the end of the arrays
+            if (attrs.contains("NORMAL")) { if (read_accessor_f32(attrs.at("NORMAL").as_int(), 3, m.normals) != nv) throw std::runtime_error("gltf: NORMAL count differs from POSITION count"); }
             else { m.normals.resize(m.normals.size() + nv * 3, 0.f); missing_normals = true; }
-            if (attrs.contains("TEXCOORD_0")) read_accessor_f32(attrs.at("TEXCOORD_0").as_int(), 2, m.texcoords);
+            if (attrs.contains("TEXCOORD_0")) { if (read_accessor_f32(attrs.at("TEXCOORD_0").as_int(), 2, m.texcoords) != nv) throw std::runtime_error("gltf: TEXCOORD_0 count differs from POSITION count"); }
             else m.texcoords.resize(m.texcoords.size() + nv * 2, 0.f);
             if (prim.contains("indices")) read_indices(prim.at("indices").as_int(), base, m.indices);
             else for (uint32_t i = 0; i < (uint32_t)nv; ++i) m.indices.push_back(base + i);

@@ -324,7 +324,7 @@ __device__ __forceinline__ void finish_pixel(const FrameParams& P, const FrameOu
     if (a <= 0.001f && P.spp_index == 0) {
         // nothing hit on the first sample of an accumulation: the pixel is the tonemapped background, a per-frame constant
         out.accum[idx] = fb;
-        out.image[idx] = make_float4(P.background_out[0], P.background_out[1], P.background_out[2], P.background_out[3]);
+        store_pixel(out.image, P.out_format, idx, P.background_out[0], P.background_out[1], P.background_out[2], P.background_out[3]);
         return;
     }
     float4 acc = fb;
@@ -344,7 +344,7 @@ __device__ __forceinline__ void finish_pixel(const FrameParams& P, const FrameOu
         cr = fminf(fmaxf(linear_to_srgb(cr), 0.f), 1.f); cg = fminf(fmaxf(linear_to_srgb(cg), 0.f), 1.f);
         cb = fminf(fmaxf(linear_to_srgb(cb), 0.f), 1.f); ca = fminf(fmaxf(ca, 0.f), 1.f);
     }
-    out.image[idx] = make_float4(cr, cg, cb, ca);
+    store_pixel(out.image, P.out_format, idx, cr, cg, cb, ca);
 }
 
 // =================================================================================================================
@@ -460,15 +460,15 @@ __global__ void __launch_bounds__(128) init_rays_kernel(FrameParams P, DeviceMod
 
 // Shared frame target, destination rank: the constant background of every pixel outside both screen rectangles (the same
 // rectangles on every rank: same camera, same scene), for ALL rows - so that the other ranks only send the pixels inside them.
-__global__ void fill_background_kernel(FrameParams P, float4* __restrict__ image) {
+__global__ void fill_background_kernel(FrameParams P, void* __restrict__ image) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= P.width) return;
     const int ms = P.mesh_scale;
     const bool in_occ = x >= P.occ_px[0] && x < P.occ_px[2] && y >= P.occ_px[1] && y < P.occ_px[3];
     const bool in_mesh = ms > 0 && P.zb_w > 0 && x * ms >= P.zb_x0 && x * ms < P.zb_x0 + P.zb_w && y * ms >= P.zb_y0 && y * ms < P.zb_y0 + P.zb_h;
-    if (!in_occ && !in_mesh) image[(size_t)y * P.width + x] = make_float4(P.background_out[0], P.background_out[1], P.background_out[2], P.background_out[3]);
+    if (!in_occ && !in_mesh) store_pixel(image, P.out_format, (uint32_t)y * (uint32_t)P.width + (uint32_t)x, P.background_out[0], P.background_out[1], P.background_out[2], P.background_out[3]);
 }
-void launch_fill_background(const FrameParams& P, float4* d_image, cudaStream_t s) {
+void launch_fill_background(const FrameParams& P, void* d_image, cudaStream_t s) {
     dim3 grid((P.width + 255) / 256, P.height);
     fill_background_kernel<<<grid, 256, 0, s>>>(P, d_image);
 }
@@ -491,7 +491,7 @@ __global__ void gather_signal_kernel(volatile uint32_t* flag, uint32_t seq) {
     *flag = seq;
     __threadfence_system();
 }
-__global__ void gather_wait_kernel(volatile uint32_t* flags, int first, int count, uint32_t seq, volatile uint32_t* err) {
+__global__ void gather_wait_kernel(volatile uint32_t* flags, int first, int count, uint32_t seq, volatile uint32_t* err, unsigned long long timeout_ns) {
     const int i = threadIdx.x;
     if (i >= count) return;
     unsigned long long t0, t1;
@@ -499,13 +499,15 @@ __global__ void gather_wait_kernel(volatile uint32_t* flags, int first, int coun
     while ((int32_t)(flags[first + i] - seq) < 0) {
         __nanosleep(200);
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 2000000000ull) { *err = 1u; break; }     // 2 s: a rank never rendered this frame - give up instead of hanging the GPU
+        if (t1 - t0 > timeout_ns) { *err = 1u; break; }        // a rank never rendered this frame - give up instead of hanging the GPU; the destination's frame() fails
     }
     __threadfence_system();
 }
 void launch_gather_signal(uint32_t* d_flag, uint32_t seq, cudaStream_t s) { gather_signal_kernel<<<1, 1, 0, s>>>(d_flag, seq); }
 void launch_gather_wait(uint32_t* d_flags, int first, int count, uint32_t seq, uint32_t* d_err, cudaStream_t s) {
-    if (count > 0) gather_wait_kernel<<<1, 32, 0, s>>>(d_flags, first, count, seq, d_err);
+    // NMR_GATHER_TIMEOUT_MS: how long a rank may take between frames (saving images, a debugger) before the others give up; 10 s
+    static const unsigned long long timeout_ns = [] { const char* v = std::getenv("NMR_GATHER_TIMEOUT_MS"); const long long ms = v ? std::atoll(v) : 10000; return (unsigned long long)(ms > 0 ? ms : 10000) * 1000000ull; }();
+    if (count > 0) gather_wait_kernel<<<1, 32, 0, s>>>(d_flags, first, count, seq, d_err, timeout_ns);
 }
 
 void launch_init_rays(const FrameParams& P, const DeviceModel& M, const MeshDevice& mesh, const unsigned long long* d_zbuf, int rows_owned,

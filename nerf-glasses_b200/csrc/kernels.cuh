@@ -9,7 +9,7 @@ namespace nmr {
 
 // per-frame output surfaces (all device pointers; optional ones may be null)
 struct FrameOut {
-    float4* image;        // displayed image (tonemapped), W*H
+    void* image;          // displayed image (tonemapped), W*H pixels of FrameParams::out_format (float4 / half4 / uchar4)
     float4* accum;        // running mean over spp (linear, premultiplied), W*H
     float4* frame;        // this sample's linear premultiplied frame buffer (parity probe), W*H or null
     float* depth;         // W*H or null
@@ -64,7 +64,9 @@ void launch_latch_word(const uint32_t* d_src, uint32_t* d_dst, uint32_t* d_dst2,
 // sequence flags of a shared frame target (nmr_gather_*): one word per rank + "consumed" + "error", behind the image
 constexpr int kGatherMaxRanks = 32, kGatherConsumed = 32, kGatherError = 33, kGatherFlagWords = 64;
 // destination rank of a shared frame target: constant background of every pixel outside both screen rectangles, all rows
-void launch_fill_background(const FrameParams& P, float4* d_image, cudaStream_t s);
+void launch_fill_background(const FrameParams& P, void* d_image, cudaStream_t s);
+// bytes of one pixel of an image in FrameParams::out_format
+inline size_t pixel_bytes(int out_format) { return out_format == kPixelU8 ? 4 : (out_format == kPixelF16 ? 8 : 16); }
 void launch_gather_signal(uint32_t* d_flag, uint32_t seq, cudaStream_t s);
 void launch_gather_wait(uint32_t* d_flags, int first, int count, uint32_t seq, uint32_t* d_err, cudaStream_t s);
 void launch_init_rays(const FrameParams& P, const DeviceModel& M, const MeshDevice& mesh, const unsigned long long* d_zbuf, int rows_owned,

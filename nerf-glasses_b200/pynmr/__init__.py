@@ -79,6 +79,9 @@ def lib():
         "nmr_read_frame": (C.c_int, [vp, vp]),
         "nmr_render": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
         "nmr_render_views": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp]),
+        "nmr_render_format": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+        "nmr_render_views_format": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+        "nmr_debug_parse_gltf": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64), C.c_char_p, C.c_size_t]),
         "nmr_set_shard": (C.c_int, [vp, C.c_int, C.c_int, C.c_int]),
         "nmr_set_surface_insertion": (C.c_int, [vp, C.c_int]),
         "nmr_set_lens": (C.c_int, [vp, C.c_int, C.c_float, C.c_float, fp]),
@@ -93,7 +96,7 @@ def lib():
         "nmr_gather_detach": (C.c_int, [vp]),
         "nmr_debug_lens": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp]),
         "nmr_get_device_image": (C.c_int, [vp, C.POINTER(vp), ip, ip]),
-        "nmr_copy_device_image": (C.c_int, [vp, vp]),
+        "nmr_copy_device_image": (C.c_int, [vp, vp, C.c_size_t]),
         "nmr_flush_l2": (C.c_int, [vp]),
         "nmr_get_stats": (C.c_int, [vp, C.POINTER(Stats)]),
         "nmr_synchronize": (C.c_int, [vp]),
@@ -122,8 +125,34 @@ EXPORTED_SYMBOLS = [
     "nmr_set_camera", "nmr_frame", "nmr_frame_async", "nmr_read_frame", "nmr_render", "nmr_render_views", "nmr_set_shard", "nmr_set_surface_insertion", "nmr_set_lens", "nmr_debug_lens", "nmr_get_nerf_info", "nmr_gather_create", "nmr_gather_attach", "nmr_gather_detach", "nmr_get_stream", "nmr_probe_points", "nmr_probe_rays", "nmr_set_tonemap_curve", "nmr_get_tonemap_curve",
     "nmr_get_device_image", "nmr_copy_device_image", "nmr_flush_l2", "nmr_get_stats", "nmr_synchronize", "nmr_host_alloc", "nmr_host_free", "nmr_get_density_bitfield",
     "nmr_set_density_bitfield", "nmr_debug_encode", "nmr_debug_network", "nmr_debug_trace", "nmr_debug_mesh",
-    "nmr_debug_last_frame", "nmr_debug_set_flags",
+    "nmr_debug_last_frame", "nmr_debug_set_flags", "nmr_render_format", "nmr_render_views_format", "nmr_debug_parse_gltf",
 ]
+
+
+PIXEL_F32, PIXEL_F16, PIXEL_U8 = 0, 1, 2
+
+
+def _pixel_format(dtype) -> int:
+    """numpy dtype of an output image -> nmr_pixel_format (include/nmr.h)."""
+    dt = np.dtype(dtype)
+    if dt == np.float32:
+        return PIXEL_F32
+    if dt == np.float16:
+        return PIXEL_F16
+    if dt == np.uint8:
+        return PIXEL_U8
+    raise ValueError(f"unsupported image dtype {dt}: float32, float16 or uint8")
+
+
+def parse_gltf(path: str) -> dict:
+    """Host-only check of a .gltf / .glb through the loader behind load_mesh (no GPU needed).  Raises RuntimeError with the loader's
+    message on malformed input."""
+    counts = (C.c_int64 * 5)()
+    err = C.create_string_buffer(512)
+    rc = lib().nmr_debug_parse_gltf(os.fsencode(path), counts, err, len(err))
+    if rc != NMR_OK:
+        raise RuntimeError(f"libnmr error {rc}: {err.value.decode(errors='replace')}")
+    return {"vertices": counts[0], "triangles": counts[1], "lens_triangles": counts[2], "texture": (counts[3], counts[4]), "warning": err.value.decode(errors="replace")}
 
 
 def _f3(v):
@@ -399,10 +428,16 @@ class Testbed:
     def crop_box(self) -> BoundingBox:
         return self._render_aabb
 
-    def render(self, width: int = 1920, height: int = 1080, spp: int = 1, linear: bool = True) -> np.ndarray:
-        """float32[H, W, 4]; row 0 is the bottom of the picture; sRGB when linear=False (S/python_api.cu:83-111)."""
-        out = _pinned_array((height, width, 4))
-        self._r._ck(lib().nmr_render(self._r._h, self._id, int(width), int(height), int(spp), int(bool(linear)), _ptr(out)))
+    def render(self, width: int = 1920, height: int = 1080, spp: int = 1, linear: bool = True, dtype=np.float32) -> np.ndarray:
+        """float32[H, W, 4]; row 0 is the bottom of the picture; sRGB when linear=False (S/python_api.cu:83-111).
+        dtype (addition): np.uint8 returns what render.py computes from the float image right after the call,
+        np.uint8(img * 255) (V/render.py:62-66), converted on the device - a quarter of the bytes cross PCIe; np.float16: half."""
+        fmt = _pixel_format(dtype)
+        out = _pinned_array((height, width, 4), dtype=np.dtype(dtype))
+        if fmt == PIXEL_F32:
+            self._r._ck(lib().nmr_render(self._r._h, self._id, int(width), int(height), int(spp), int(bool(linear)), _ptr(out)))
+        else:
+            self._r._ck(lib().nmr_render_format(self._r._h, self._id, int(width), int(height), int(spp), int(bool(linear)), fmt, _ptr(out)))
         return out
 
     def probe_points(self, points_world, direction) -> np.ndarray:
@@ -544,12 +579,13 @@ class NerfMeshRenderer:
     def synchronize(self):
         self._ck(lib().nmr_synchronize(self._h))
 
-    def render_views(self, nerf: Testbed, cameras, width: int, height: int, linear: bool = False, to_host: bool = True):
-        """cameras: [n, 3, 4] -> float32[n, H, W, 4] (render.py's landmark pass in one call; up to 8 views in flight on the GPU).
-        to_host=False leaves the images on the device (returns None; device_image() is the last view)."""
+    def render_views(self, nerf: Testbed, cameras, width: int, height: int, linear: bool = False, to_host: bool = True, dtype=np.float32):
+        """cameras: [n, 3, 4] -> dtype[n, H, W, 4] (render.py's landmark pass in one call; up to 8 views in flight on the GPU).
+        to_host=False leaves the images on the device (returns None; device_image() is the last view).  dtype as in Testbed.render."""
         cams = np.ascontiguousarray(np.asarray(cameras, dtype=np.float32).reshape(-1, 3, 4).transpose(0, 2, 1)).reshape(-1, 12)
-        out = _pinned_array((cams.shape[0], height, width, 4)) if to_host else None
-        self._ck(lib().nmr_render_views(self._h, nerf._id, cams.shape[0], _ptr(cams), int(width), int(height), int(bool(linear)), _ptr(out) if to_host else None))
+        fmt = _pixel_format(dtype)
+        out = _pinned_array((cams.shape[0], height, width, 4), dtype=np.dtype(dtype)) if to_host else None
+        self._ck(lib().nmr_render_views_format(self._h, nerf._id, cams.shape[0], _ptr(cams), int(width), int(height), int(bool(linear)), fmt, _ptr(out) if to_host else None))
         return out
 
     def set_shard(self, rank: int, world: int, band: int = 8):
@@ -591,8 +627,9 @@ class NerfMeshRenderer:
         self._ck(lib().nmr_get_device_image(self._h, C.byref(p), C.byref(w), C.byref(h)))
         return p.value, w.value, h.value
 
-    def copy_device_image(self, dst_device_ptr: int):
-        self._ck(lib().nmr_copy_device_image(self._h, C.c_void_p(dst_device_ptr)))
+    def copy_device_image(self, dst_device_ptr: int, dst_bytes: int):
+        """Last image (its own resolution / format) -> caller-owned device memory of dst_bytes bytes."""
+        self._ck(lib().nmr_copy_device_image(self._h, C.c_void_p(dst_device_ptr), int(dst_bytes)))
 
     def flush_l2(self):
         self._ck(lib().nmr_flush_l2(self._h))

@@ -104,7 +104,7 @@ class ShardedRenderer:
         H, W = self.r.height, self.r.width
         if self._buf is None or tuple(self._buf.shape) != (H, W, 4):
             self._buf = torch.empty((H, W, 4), dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
-        self.r.copy_device_image(self._buf.data_ptr())      # device->device on libnmr's stream, then a stream synchronise
+        self.r.copy_device_image(self._buf.data_ptr(), self._buf.numel() * 4)      # device->device on libnmr's stream, then a stream synchronise
         return gather_frame(self._buf, self.rank, self.world, self.band, dst, self.group)
 
 
@@ -140,11 +140,14 @@ class PeerShardedRenderer:
 
     def render_frame(self, sync: bool = True):
         """sync=False only enqueues (pipelined callers that consume the image on the renderer's stream, r.stream_ptr())."""
-        self.r.frame_async()
         if self.rank != self.dst:
+            self.r.frame_async()
             return None
         if sync:
-            self.r.synchronize()            # the destination's stream ends with the wait for every rank's signal
+            self.r.frame()                  # the destination's stream ends with the wait for every rank's signal; raises when a
+                                            # rank did not deliver its rows in time (the image would be incomplete)
+        else:
+            self.r.frame_async()
         return self._image
 
     def close(self):

@@ -1395,15 +1395,17 @@ ORC_API void orc_mesh_set_lens(orc_mesh* M, const uint8_t* tri_lens) {
 }
 
 /* Like orc_mesh_render but in two layers: the nearest OPAQUE hit (shaded RGBA + hitT, NaN on miss) and the nearest LENS hit
- * (hitT, 0 on miss, and the unit shading normal). */
+ * (hitT, 0 on miss, and the unit shading normal).  window as in orc_mesh_render (the caller pre-fills the rest as misses). */
 ORC_API void orc_mesh_render_layers(const orc_mesh* M, const float* camera12, const float* light_pos, int W2, int H2,
-                                    float* rgba, float* depth, float* lens_depth, float* lens_normal) {
+                                    float* rgba, float* depth, float* lens_depth, float* lens_normal, const int32_t* window) {
     const v3 U = v3_make(camera12[0], camera12[1], camera12[2]), Vv = v3_make(camera12[3], camera12[4], camera12[5]);
     const v3 Wv = v3_make(camera12[6], camera12[7], camera12[8]), eye = v3_make(camera12[9], camera12[10], camera12[11]);
     const v3 light = v3_make(light_pos[0], light_pos[1], light_pos[2]);
+    int wx0 = 0, wy0 = 0, wx1 = W2, wy1 = H2;
+    if (window && window[2] > window[0] && window[3] > window[1]) { wx0 = window[0]; wy0 = window[1]; wx1 = window[2]; wy1 = window[3]; }
 #pragma omp parallel for schedule(dynamic, 4)
-    for (int y = 0; y < H2; ++y) {
-        for (int x = 0; x < W2; ++x) {
+    for (int y = wy0; y < wy1; ++y) {
+        for (int x = wx0; x < wx1; ++x) {
             float dx = 2.0f * (((float)x + 0.5f) / (float)W2) - 1.0f;
             float dy = 2.0f * (((float)y + 0.5f) / (float)H2) - 1.0f;
             v3 dir = glm_normalize3(v3_make((dx * U.x + dy * Vv.x) + Wv.x, (dx * U.y + dy * Vv.y) + Wv.y, (dx * U.z + dy * Vv.z) + Wv.z));

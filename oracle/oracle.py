@@ -104,7 +104,7 @@ def lib():
         "orc_set_num_threads": (None, [C.c_int]),
         "orc_render_lens": (C.c_int, [vp, C.POINTER(RenderParams), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "orc_mesh_set_lens": (None, [vp, vp]),
-        "orc_mesh_render_layers": (None, [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp]),
+        "orc_mesh_render_layers": (None, [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]),
         "orc_lens_resolve": (None, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
@@ -324,12 +324,14 @@ class Mesh:
             f = np.ascontiguousarray(tri_lens, dtype=np.uint8)
             lib().orc_mesh_set_lens(self.h, _p(f))
 
-    def render_layers(self, camera12, W2: int, H2: int, light=(1.0, 1.0, 1.0)):
-        """-> (opaque rgba, opaque hitT (NaN on miss), lens hitT (0 on miss), lens unit normal)"""
+    def render_layers(self, camera12, W2: int, H2: int, light=(1.0, 1.0, 1.0), window=None):
+        """-> (opaque rgba, opaque hitT (NaN on miss), lens hitT (0 on miss), lens unit normal); window = (x0, y0, x1, y1) in
+        supersampled pixels renders only that sub-rectangle (the rest reads as a miss in both layers)."""
         cam = np.asarray(camera12, dtype=np.float32); lp = np.asarray(light, dtype=np.float32)
-        rgba = np.zeros((H2, W2, 4), dtype=np.float32); depth = np.zeros((H2, W2), dtype=np.float32)
-        ld = np.zeros((H2, W2), dtype=np.float32); ln = np.zeros((H2, W2, 3), dtype=np.float32)
-        lib().orc_mesh_render_layers(self.h, _p(cam), _p(lp), W2, H2, _p(rgba), _p(depth), _p(ld), _p(ln))
+        rgba = np.zeros((H2, W2, 4), dtype=np.float32); depth = np.full((H2, W2), np.nan, dtype=np.float32)
+        ld = np.zeros((H2, W2), dtype=np.float32); ln = np.zeros((H2, W2, 3), dtype=np.float32); ln[..., 2] = 1.0
+        win = None if window is None else np.asarray(window, dtype=np.int32)
+        lib().orc_mesh_render_layers(self.h, _p(cam), _p(lp), W2, H2, _p(rgba), _p(depth), _p(ld), _p(ln), _p(win) if win is not None else None)
         return rgba, depth, ld, ln
 
     def world_positions(self) -> np.ndarray:

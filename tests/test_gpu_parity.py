@@ -533,6 +533,6 @@ def test_render_views_lanes_equal_single_renders(small_snapshot, glasses_gltf):
     assert (dw, dh) == (w, h) and ptr
     import torch
     last = torch.empty((h, w, 4), dtype=torch.float32, device="cuda")
-    r.copy_device_image(last.data_ptr())
+    r.copy_device_image(last.data_ptr(), last.numel() * 4)
     assert np.array_equal(last.cpu().numpy().view(np.uint32), out[18].view(np.uint32))
     assert r.stats()["rays"] == w * h

@@ -175,3 +175,108 @@ def test_oracle_probes_are_consistent(small_snapshot):
     pc = np.array([O.lib().orc_cascaded_grid_idx_at(np.ascontiguousarray(q + 0.5, dtype=np.float32).ctypes.data_as(C.c_void_p), 0) for q in pts], dtype=np.uint32)
     occ = ((bits[pc // 8] >> (pc % 8)) & 1).astype(bool)
     assert np.all(alpha[~occ] == 0) and (alpha[occ] > 0).mean() > 0.95
+
+
+# ---- the glTF / PNG loader on malformed input (host-only entry point nmr_debug_parse_gltf) ---------------------
+def _tiny_gltf(tmp_path, mutate=None, name="m.gltf"):
+    """A one-triangle glTF with embedded buffers; `mutate(doc)` breaks it."""
+    import base64
+    import json
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], dtype="<f4").tobytes()
+    nrm = np.array([[0, 0, 1]] * 3, dtype="<f4").tobytes()
+    uv = np.zeros((3, 2), dtype="<f4").tobytes()
+    idx = np.array([0, 1, 2, 0], dtype="<u2").tobytes()
+    blob = pos + nrm + uv + idx
+    doc = {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0]}], "nodes": [{"mesh": 0}],
+           "meshes": [{"primitives": [{"attributes": {"POSITION": 0, "NORMAL": 1, "TEXCOORD_0": 2}, "indices": 3}]}],
+           "accessors": [{"bufferView": 0, "componentType": 5126, "count": 3, "type": "VEC3"},
+                         {"bufferView": 1, "componentType": 5126, "count": 3, "type": "VEC3"},
+                         {"bufferView": 2, "componentType": 5126, "count": 3, "type": "VEC2"},
+                         {"bufferView": 3, "componentType": 5123, "count": 3, "type": "SCALAR"}],
+           "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": 36}, {"buffer": 0, "byteOffset": 36, "byteLength": 36},
+                           {"buffer": 0, "byteOffset": 72, "byteLength": 24}, {"buffer": 0, "byteOffset": 96, "byteLength": 8}],
+           "buffers": [{"byteLength": len(blob), "uri": "data:application/octet-stream;base64," + base64.b64encode(blob).decode()}]}
+    if mutate:
+        mutate(doc)
+    p = tmp_path / name
+    p.write_text(json.dumps(doc))
+    return str(p)
+
+
+def test_gltf_loader_accepts_the_fixtures(tmp_path, glasses_gltf):
+    import pynmr
+    import synth
+    assert pynmr.parse_gltf(_tiny_gltf(tmp_path))["triangles"] == 1
+    g = pynmr.parse_gltf(glasses_gltf)
+    assert (g["vertices"], g["triangles"], g["lens_triangles"], g["texture"]) == (1864, 2952, 0, (4, 4))
+    lens = pynmr.parse_gltf(synth.write_lens_glasses_gltf(str(tmp_path / "lens")))
+    assert lens["triangles"] == 2952 + 8 and lens["lens_triangles"] == 8
+
+
+@pytest.mark.parametrize("case", ["negative_view_offset", "huge_view_length", "negative_accessor_offset", "negative_count", "count_overflow",
+                                  "short_normals", "short_texcoords", "node_cycle", "node_self_child", "bad_buffer_index", "bad_accessor_index",
+                                  "index_out_of_range", "negative_scene", "huge_stride"])
+def test_gltf_loader_rejects_malformed_files(tmp_path, case):
+    """Untrusted offsets / lengths / counts / indices: every one of these used to crash, hang or read out of bounds
+    (negative byteOffset passing an unsigned bounds check, NORMAL shorter than POSITION, a child list leading back to its parent)."""
+    import pynmr
+
+    def mutate(d):
+        if case == "negative_view_offset": d["bufferViews"][0]["byteOffset"] = -64
+        elif case == "huge_view_length": d["bufferViews"][1]["byteLength"] = 2 ** 62
+        elif case == "negative_accessor_offset": d["accessors"][0]["byteOffset"] = -12
+        elif case == "negative_count": d["accessors"][3]["count"] = -3
+        elif case == "count_overflow": d["accessors"][0]["count"] = 2 ** 61
+        elif case == "short_normals": d["accessors"][1]["count"] = 1
+        elif case == "short_texcoords": d["accessors"][2]["count"] = 2
+        elif case == "node_cycle": d["nodes"] = [{"children": [1]}, {"children": [0], "mesh": 0}]
+        elif case == "node_self_child": d["nodes"] = [{"children": [0], "mesh": 0}]
+        elif case == "bad_buffer_index": d["bufferViews"][0]["buffer"] = 7
+        elif case == "bad_accessor_index": d["meshes"][0]["primitives"][0]["attributes"]["POSITION"] = -1
+        elif case == "index_out_of_range": d["accessors"][3]["byteOffset"] = 2      # reads indices 1, 2, 0 -> fine; then break one
+        elif case == "negative_scene": d["scene"] = -1
+        elif case == "huge_stride": d["bufferViews"][0]["byteStride"] = 2 ** 40
+
+    if case == "index_out_of_range":
+        import base64
+        import json
+        path = _tiny_gltf(tmp_path)
+        d = json.loads(open(path).read())
+        raw = bytearray(base64.b64decode(d["buffers"][0]["uri"].split(",", 1)[1]))
+        raw[96:98] = np.array([9], dtype="<u2").tobytes()
+        d["buffers"][0]["uri"] = "data:application/octet-stream;base64," + base64.b64encode(bytes(raw)).decode()
+        open(path, "w").write(json.dumps(d))
+    else:
+        path = _tiny_gltf(tmp_path, mutate)
+    with pytest.raises(RuntimeError, match="libnmr error -3"):
+        pynmr.parse_gltf(path)
+
+
+def test_png_palette_index_is_bounds_checked(tmp_path):
+    """decode_png: palette index k with k*3+2 == palette.size() reads one byte past the palette - such a texture is
+    now reported as unusable (the loader falls back to baseColorFactor and says so) instead of being read out of bounds."""
+    import base64
+    import struct
+    import zlib
+    import pynmr
+
+    def chunk(tag, body):
+        return struct.pack(">I", len(body)) + tag + body + struct.pack(">I", zlib.crc32(tag + body) & 0xFFFFFFFF)
+
+    def png(palette_bytes, index):
+        ihdr = struct.pack(">IIBBBBB", 1, 1, 8, 3, 0, 0, 0)
+        return b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", ihdr) + chunk(b"PLTE", palette_bytes) + chunk(b"IDAT", zlib.compress(bytes([0, index]))) + chunk(b"IEND", b"")
+
+    def with_texture(data):
+        def mutate(d):
+            d["materials"] = [{"pbrMetallicRoughness": {"baseColorTexture": {"index": 0}}}]
+            d["meshes"][0]["primitives"][0]["material"] = 0
+            d["textures"] = [{"source": 0}]
+            d["images"] = [{"uri": "data:image/png;base64," + base64.b64encode(data).decode()}]
+        return mutate
+
+    ok = pynmr.parse_gltf(_tiny_gltf(tmp_path, with_texture(png(bytes([10, 20, 30, 40, 50, 60]), 1)), "ok.gltf"))
+    assert ok["texture"] == (1, 1) and ok["warning"] == ""
+    for pal, idx in ((bytes([10, 20, 30, 40, 50]), 1), (bytes([10, 20, 30]), 1), (bytes([10, 20]), 0)):       # k*3+2 == size, > size
+        bad = pynmr.parse_gltf(_tiny_gltf(tmp_path, with_texture(png(pal, idx)), "bad.gltf"))
+        assert bad["texture"] == (0, 0) and "palette" in bad["warning"]
