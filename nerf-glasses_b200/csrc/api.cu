@@ -391,16 +391,6 @@ FrameParams make_params(nmr_ctx* ctx, const Nerf& n, int W, int H, const float* 
     P.surface_mode = ctx->surface_mode;
     occupied_screen_box(P);
     mesh_screen_box(ctx, P);
-    if (P.shard_world > 1 && P.surface_mode == kSurfaceAuto) {
-        // A tile-sharded context sees only its own rows: the auto rule's "live rays * 8 <= pixels" and the schedule histogram would
-        // be evaluated per rank, and ranks could decide differently from each other and from the single-GPU frame.  Decide from what
-        // every rank knows alike - the two screen rectangles of the WHOLE frame: when they prove the 8-sample batches (render.py's
-        // framing, every BASELINE config) use them, otherwise the exact position (both are ray-local rules).
-        const long long ms = P.mesh_scale > 0 ? P.mesh_scale : 1;
-        const long long occ = (long long)std::max(0, P.occ_px[2] - P.occ_px[0]) * std::max(0, P.occ_px[3] - P.occ_px[1]);
-        const long long mesh_px = P.mesh_scale > 0 ? ((long long)P.zb_w / ms + 2) * ((long long)P.zb_h / ms + 2) : 0;
-        P.surface_mode = (occ + mesh_px) * 8 <= (long long)P.width * P.height ? kSurfaceBatch8 : kSurfaceExact;
-    }
     P.lens_on = (P.mesh_scale > 0 && ctx->scene_has_lens && ctx->lens_enabled) ? 1 : 0;
     {
         const float r0 = (ctx->lens_ior - 1.f) / (ctx->lens_ior + 1.f);
@@ -1058,7 +1048,7 @@ NMR_API int nmr_render_views_format(nmr_ctx* ctx, int nerf_id, int n_views, cons
                 if (!out_rgba) continue;                                                   // images stay on the device
                 CK(cudaEventRecord(l->ev_view[0][0], l->stream));
                 CK(cudaStreamWaitEvent(ctx->copy_stream, l->ev_view[0][0], 0));
-                CK(cudaMemcpyAsync(out_rgba + (size_t)v * px * bpp, l->surf.image.p, px * bpp, cudaMemcpyDeviceToHost, ctx->copy_stream));
+                CK(cudaMemcpyAsync(out_rgba + (size_t)v * px * bpp, l->surf.image.p, px * bpp, cudaMemcpyDefault, ctx->copy_stream));     // (host or device destination)
                 CK(cudaEventRecord(l->ev_view[0][1], ctx->copy_stream));
             }
             nmr_ctx* last = ctx->lanes[(size_t)((n_views - 1) % K)];
@@ -1087,7 +1077,7 @@ NMR_API int nmr_render_views_format(nmr_ctx* ctx, int nerf_id, int n_views, cons
             CK(cudaEventRecord(ctx->ev_view[b][0], ctx->stream));
             if (!out_rgba) { CK(cudaEventRecord(ctx->ev_view[b][1], ctx->stream)); continue; }
             CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_view[b][0], 0));
-            CK(cudaMemcpyAsync(out_rgba + (size_t)v * px * bpp, bufs[b], px * bpp, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            CK(cudaMemcpyAsync(out_rgba + (size_t)v * px * bpp, bufs[b], px * bpp, cudaMemcpyDefault, ctx->copy_stream));
             CK(cudaEventRecord(ctx->ev_view[b][1], ctx->copy_stream));
         }
         if (((n_views - 1) & 1) == 1) { std::swap(S.image.p, S.image_alt.p); std::swap(S.image.n, S.image_alt.n); }   // nmr_get_device_image: the last view's buffer
@@ -1128,6 +1118,32 @@ NMR_API int nmr_flush_l2(nmr_ctx* ctx) {
         const size_t bytes = (size_t)256 << 20;
         ctx->d_flush.ensure(bytes);
         CK(cudaMemsetAsync(ctx->d_flush.p, 0x5A, bytes, ctx->stream));
+        return NMR_OK;
+    });
+}
+
+NMR_API int nmr_measure_l2(nmr_ctx* ctx, size_t bytes, int mode, float* out_gbs) {
+    return guarded(ctx, [&]() -> int {
+        if (!out_gbs || (mode != 0 && mode != 1)) return fail(ctx, NMR_ERR_INVALID, "bad arguments");
+        size_t pow2 = (size_t)1 << 24;
+        while (pow2 * 2 <= bytes && pow2 < ((size_t)1 << 30)) pow2 *= 2;       // power-of-two size (the gather mode masks its indices)
+        DevBuf<uint8_t> buf; buf.ensure(pow2);
+        CK(cudaMemsetAsync(buf.p, 0x11, pow2, ctx->stream));
+        const uint32_t n_vec = (uint32_t)(pow2 / 16), loads = mode == 0 ? 512u : 2048u;
+        uint32_t* sink = reinterpret_cast<uint32_t*>(ctx->d_scratch.p);          // never written in practice (the kernel's condition does not hold)
+        launch_l2_probe(buf.p, n_vec, loads, mode, sink, ctx->num_sms, ctx->stream);      // warm: the buffer is L2-resident afterwards
+        float best = 0.f;
+        for (int rep = 0; rep < 5; ++rep) {
+            CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+            launch_l2_probe(buf.p, n_vec, loads, mode, sink, ctx->num_sms, ctx->stream);
+            CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            float ms = 0.f; CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+            const double total = (double)ctx->num_sms * 8 * 256 * loads * (mode == 0 ? 16.0 : 4.0);
+            if (ms > 0.f) best = std::max(best, (float)(total / (ms * 1e-3) / 1e9));
+        }
+        CK(cudaGetLastError());
+        *out_gbs = best;
         return NMR_OK;
     });
 }

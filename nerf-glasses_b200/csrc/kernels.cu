@@ -1211,6 +1211,43 @@ void launch_march(const FrameParams& P, const DeviceModel& M, const float4* d_qu
 }
 
 // =================================================================================================================
+// measurement helper: what the L2 delivers to the SMs on this GPU (bench.py's roofline denominators; not part of a render)
+//   mode 0: coalesced 16-byte loads over a buffer that fits the L2 (the L2 -> SM bandwidth ceiling)
+//   mode 1: independent 4-byte gathers at hashed indices, eight in flight per thread - the access pattern of the hashed
+//           levels of the grid encoder with no arithmetic around it (each gather moves a 32-byte sector): the ceiling of
+//           "algorithmic gather bytes per second" for that pattern
+// =================================================================================================================
+__global__ void __launch_bounds__(256) l2_probe_kernel(const uint4* __restrict__ buf, uint32_t n_vec, uint32_t loads_per_thread, int mode, uint32_t* __restrict__ sink) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, n_threads = gridDim.x * blockDim.x;
+    uint32_t acc = 0;
+    if (mode == 0) {
+        uint32_t i = tid % n_vec;
+        for (uint32_t k = 0; k < loads_per_thread; k += 4) {
+            uint4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { v[j] = __ldcg(buf + i); i += n_threads; if (i >= n_vec) i -= n_vec; }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc ^= v[j].x ^ v[j].y ^ v[j].z ^ v[j].w;
+        }
+    } else {
+        const uint32_t* __restrict__ w = reinterpret_cast<const uint32_t*>(buf);
+        const uint32_t mask = n_vec * 4u - 1u;                     // n_vec is a power of two in this mode
+        uint32_t x = tid * 2654435761u + 12345u;
+        for (uint32_t k = 0; k < loads_per_thread; k += 8) {
+            uint32_t v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { x = x * 1664525u + 1013904223u; v[j] = __ldg(w + ((x >> 4) & mask)); }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc ^= v[j];
+        }
+    }
+    if (acc == 0x9E3779B9u) *sink = acc;      // keeps the loads alive
+}
+void launch_l2_probe(const void* d_buf, uint32_t n_vec, uint32_t loads_per_thread, int mode, uint32_t* d_sink, int num_sms, cudaStream_t s) {
+    l2_probe_kernel<<<num_sms * 8, 256, 0, s>>>(reinterpret_cast<const uint4*>(d_buf), n_vec, loads_per_thread, mode, d_sink);
+}
+
+// =================================================================================================================
 // parity probes
 // =================================================================================================================
 __global__ void debug_encode_kernel(DeviceModel M, const float* __restrict__ pos, int64_t n, uint16_t* __restrict__ out) {

@@ -80,6 +80,8 @@ void launch_march(const FrameParams& P, const DeviceModel& M, const float4* d_qu
 // density probes of the collision tool: mode 0 = NerfTracer::intersects (alpha at points), 1 = NerfTracer::collide (distance along dir)
 void launch_probe(const FrameParams& P, const DeviceModel& M, const float* d_points_world, const float dir[3], int64_t n, int mode, float* d_out,
                   uint32_t debug_flags, int num_sms, cudaStream_t s);
+// measurement helper (bench.py): L2 -> SM throughput probe, see kernels.cu
+void launch_l2_probe(const void* d_buf, uint32_t n_vec, uint32_t loads_per_thread, int mode, uint32_t* d_sink, int num_sms, cudaStream_t s);
 // parity probes
 void launch_debug_encode(const DeviceModel& M, const float* d_pos, int64_t n, uint16_t* d_out, cudaStream_t s);
 void launch_debug_network(const DeviceModel& M, const float* d_pos, const float* d_dir, int64_t n, uint16_t* d_out4, uint32_t debug_flags, cudaStream_t s);

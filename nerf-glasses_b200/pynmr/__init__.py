@@ -98,6 +98,7 @@ def lib():
         "nmr_get_device_image": (C.c_int, [vp, C.POINTER(vp), ip, ip]),
         "nmr_copy_device_image": (C.c_int, [vp, vp, C.c_size_t]),
         "nmr_flush_l2": (C.c_int, [vp]),
+        "nmr_measure_l2": (C.c_int, [vp, C.c_size_t, C.c_int, fp]),
         "nmr_get_stats": (C.c_int, [vp, C.POINTER(Stats)]),
         "nmr_synchronize": (C.c_int, [vp]),
         "nmr_host_alloc": (vp, [C.c_size_t]),
@@ -125,7 +126,7 @@ EXPORTED_SYMBOLS = [
     "nmr_set_camera", "nmr_frame", "nmr_frame_async", "nmr_read_frame", "nmr_render", "nmr_render_views", "nmr_set_shard", "nmr_set_surface_insertion", "nmr_set_lens", "nmr_debug_lens", "nmr_get_nerf_info", "nmr_gather_create", "nmr_gather_attach", "nmr_gather_detach", "nmr_get_stream", "nmr_probe_points", "nmr_probe_rays", "nmr_set_tonemap_curve", "nmr_get_tonemap_curve",
     "nmr_get_device_image", "nmr_copy_device_image", "nmr_flush_l2", "nmr_get_stats", "nmr_synchronize", "nmr_host_alloc", "nmr_host_free", "nmr_get_density_bitfield",
     "nmr_set_density_bitfield", "nmr_debug_encode", "nmr_debug_network", "nmr_debug_trace", "nmr_debug_mesh",
-    "nmr_debug_last_frame", "nmr_debug_set_flags", "nmr_render_format", "nmr_render_views_format", "nmr_debug_parse_gltf",
+    "nmr_debug_last_frame", "nmr_debug_set_flags", "nmr_render_format", "nmr_render_views_format", "nmr_debug_parse_gltf", "nmr_measure_l2",
 ]
 
 
@@ -579,11 +580,14 @@ class NerfMeshRenderer:
     def synchronize(self):
         self._ck(lib().nmr_synchronize(self._h))
 
-    def render_views(self, nerf: Testbed, cameras, width: int, height: int, linear: bool = False, to_host: bool = True, dtype=np.float32):
+    def render_views(self, nerf: Testbed, cameras, width: int, height: int, linear: bool = False, to_host: bool = True, dtype=np.float32, out_device_ptr: int = 0):
         """cameras: [n, 3, 4] -> dtype[n, H, W, 4] (render.py's landmark pass in one call; up to 8 views in flight on the GPU).
         to_host=False leaves the images on the device (returns None; device_image() is the last view).  dtype as in Testbed.render."""
         cams = np.ascontiguousarray(np.asarray(cameras, dtype=np.float32).reshape(-1, 3, 4).transpose(0, 2, 1)).reshape(-1, 12)
         fmt = _pixel_format(dtype)
+        if out_device_ptr:       # images go to caller-owned device memory (n x H x W x 4 elements of dtype), e.g. a torch tensor
+            self._ck(lib().nmr_render_views_format(self._h, nerf._id, cams.shape[0], _ptr(cams), int(width), int(height), int(bool(linear)), fmt, C.c_void_p(int(out_device_ptr))))
+            return None
         out = _pinned_array((cams.shape[0], height, width, 4), dtype=np.dtype(dtype)) if to_host else None
         self._ck(lib().nmr_render_views_format(self._h, nerf._id, cams.shape[0], _ptr(cams), int(width), int(height), int(bool(linear)), fmt, _ptr(out) if to_host else None))
         return out
@@ -633,6 +637,12 @@ class NerfMeshRenderer:
 
     def flush_l2(self):
         self._ck(lib().nmr_flush_l2(self._h))
+
+    def measure_l2(self, nbytes: int = 32 << 20, gather: bool = False) -> float:
+        """GB/s the L2 delivers to the SMs from a resident buffer (include/nmr.h: nmr_measure_l2)."""
+        v = C.c_float(0)
+        self._ck(lib().nmr_measure_l2(self._h, int(nbytes), 1 if gather else 0, C.byref(v)))
+        return float(v.value)
 
     def stats(self) -> dict:
         s = Stats()

@@ -92,9 +92,14 @@ class ShardedRenderer:
     renderer: this rank's pynmr.NerfMeshRenderer (created on this rank's device, same scene loaded on every rank).
     """
 
-    def __init__(self, renderer, rank: int, world: int, band: int = 8, group=None):
+    def __init__(self, renderer, rank: int, world: int, band: int = 8, group=None, surface_mode: int | None = 2):
         self.r, self.rank, self.world, self.band, self.group = renderer, rank, world, band, group
         renderer.set_shard(rank, world, band)
+        # one mesh-surface rule for all ranks: the default (auto) rule counts the live rays of a context's own rows, so shards could
+        # decide differently from each other (include/nmr.h: nmr_set_shard); 8-sample batches are what a single GPU picks in
+        # render.py's framing
+        if surface_mode is not None:
+            renderer.set_surface_insertion(surface_mode)
         self._buf = None
 
     def render_frame(self, dst: int = 0):
@@ -121,10 +126,12 @@ class PeerShardedRenderer:
     synchronisation between ranks; `render_frame()` returns the full image on `dst` (a view of the shared image, valid until
     the next render_frame) and None elsewhere.  Every rank must call render_frame() the same number of times."""
 
-    def __init__(self, renderer, rank: int, world: int, band: int = 8, dst: int = 0, group=None):
+    def __init__(self, renderer, rank: int, world: int, band: int = 8, dst: int = 0, group=None, surface_mode: int | None = 2):
         import torch.distributed as dist
         self.r, self.rank, self.world, self.band, self.dst, self.group = renderer, rank, world, band, dst, group
         renderer.set_shard(rank, world, band)
+        if surface_mode is not None:        # one mesh-surface rule for all ranks, see ShardedRenderer (2 = NMR_SURFACE_BATCH8)
+            renderer.set_surface_insertion(surface_mode)
         self._image = None
         box = [None]
         if rank == dst:

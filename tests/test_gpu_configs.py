@@ -279,3 +279,59 @@ def test_first_hit_bit_exact_over_random_poses(small_snapshot):
         assert np.array_equal(got["cell"], want["cell"]) and np.array_equal(got["mip"], want["mip"])
         total += w * h; total_live += int(live.sum())
     assert total >= 10_000_000 and total_live > 500_000
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# compact image outputs: converted on the device, equal to what render.py computes on the host
+# ---------------------------------------------------------------------------------------------------------------------------
+def test_u8_and_f16_outputs_equal_host_conversion(small_snapshot, glasses_gltf):
+    import pynmr
+    import synth
+    path, _ = small_snapshot
+    for (w, h) in ((192, 108), (384, 288)):                    # below / above the row-banded copy path of render()
+        r = pynmr.NerfMeshRenderer(w, h)
+        nerf = r.load_nerf(path)
+        assert r.load_mesh(glasses_gltf, t=synth.GLASSES_T, s=synth.GLASSES_S, r=synth.GLASSES_R_WXYZ) is not None
+        r.orbit(0.35, -0.2, 4.0)
+        for linear in (False, True):
+            f32 = np.asarray(nerf.render(w, h, 1, linear=linear)).copy()
+            u8 = np.asarray(nerf.render(w, h, 1, linear=linear, dtype=np.uint8)).copy()
+            f16 = np.asarray(nerf.render(w, h, 1, linear=linear, dtype=np.float16)).copy()
+            assert u8.dtype == np.uint8 and u8.shape == (h, w, 4) and f16.dtype == np.float16
+            assert np.array_equal(u8, np.uint8(np.clip(f32, 0.0, 1.0) * 255))            # render.py: np.uint8(img * 255)
+            assert np.array_equal(f16.view(np.uint16), f32.astype(np.float16).view(np.uint16))
+            assert len(np.unique(u8[..., 0])) > 20
+        # render.py's frame loop: frame() then render(); read_frame() refuses to hand out a render() image as the frame
+        assert r.frame()
+        fr = np.asarray(r.read_frame()).copy()
+        assert np.array_equal(np.uint8(fr * 255), np.asarray(nerf.render(w, h, 1, linear=False, dtype=np.uint8)))
+        with pytest.raises(RuntimeError):
+            r.read_frame()
+        # batched views in u8
+        cams = []
+        for k in range(5):
+            r.orbit(0.07, 0.01, 0)
+            cams.append(r.view_projection_mat)
+        v32 = np.asarray(r.render_views(nerf, np.stack(cams), w, h)).copy()
+        v8 = np.asarray(r.render_views(nerf, np.stack(cams), w, h, dtype=np.uint8)).copy()
+        assert np.array_equal(v8, np.uint8(v32 * 255))
+
+
+def test_read_frame_and_copy_device_image_check_sizes(small_snapshot):
+    """a render() at another resolution must not let read_frame() overrun the caller's buffer."""
+    import pynmr
+    path, _ = small_snapshot
+    r = pynmr.NerfMeshRenderer(128, 72)
+    nerf = r.load_nerf(path)
+    assert r.frame()
+    a = np.asarray(r.read_frame()).copy()
+    nerf.render(320, 180, 1, linear=False)                     # resizes the surfaces
+    with pytest.raises(RuntimeError):
+        r.read_frame()
+    import torch
+    small = torch.empty(16, dtype=torch.float32, device="cuda")
+    with pytest.raises(RuntimeError):
+        r.copy_device_image(small.data_ptr(), small.numel() * 4)
+    r.view_projection_mat = r.view_projection_mat
+    assert r.frame()
+    assert np.array_equal(np.asarray(r.read_frame()).view(np.uint32), a.view(np.uint32))
