@@ -253,6 +253,7 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
         "config": workload_config(args, world),
         "fps": args.steps * world / (total_dev_ms / 1e3),
+        "ms_per_step_median": float(np.median(dev_ms)), "ms_per_step_max": float(np.max(dev_ms)),
         "msamples_per_s": samples_all / (total_dev_ms / 1e3) / 1e6,
         "samples_per_frame": samples_per_launch, "rays_alive_per_frame": alive / max(1, args.steps),
         "floaties": {"clusters": clusters, "kept_cells": kept},

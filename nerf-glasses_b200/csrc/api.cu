@@ -38,12 +38,13 @@ struct DevBuf {
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;              // owns device memory
     DevBuf& operator=(const DevBuf&) = delete;
-    void ensure(size_t count) {
-        if (count <= n) return;
+    bool ensure(size_t count) {      // true when the buffer was (re)allocated: its contents are undefined
+        if (count <= n) return false;
         if (p) cudaFree(p);
         p = nullptr; n = 0;
         CK(cudaMalloc(&p, count * sizeof(T)));
         n = count;
+        return true;
     }
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
     ~DevBuf() { release(); }
@@ -55,6 +56,7 @@ struct Nerf {
     DevBuf<uint8_t> d_bitfield;
     DevBuf<uint16_t> d_mlp_tc;                      // MLP weights in the tensor-core operand layout
     DevBuf<uint32_t> d_coarse;                      // coarse "near" bits of cascade 0 (kernels.cuh: launch_coarse_build)
+    DevBuf<uint4> d_bricks;                         // coarse levels of the hash grid as 2x2x2 bricks (DeviceModel::brick)
     DeviceModel dev{};
     float render_aabb_min[3], render_aabb_max[3];
     float occ_min[3], occ_max[3];                   // box around every occupied cell (see update_occupied_box)
@@ -68,6 +70,8 @@ struct Mesh {
     HostMesh host;
     float t[3], s[3], r[4];
 };
+
+constexpr size_t kQueueSlack = 32768;   // >= ray groups of a march launch (SMs x CTAs per SM x 32)
 
 struct Surfaces {
     int w = 0, h = 0;
@@ -92,7 +96,9 @@ struct Surfaces {
         const size_t n = (size_t)W * H;
         if (W != w || H != h) spp = 0;
         image.ensure(n); accum.ensure(n); frame.ensure(n); depth.ensure(n); n_samples.ensure(n);
-        queue.ensure(n * kRayRecordFloat4s);
+        // a fresh ray queue holds kEmptyRecord (all ones) in every ready word, see kernels.cuh
+        // (+ kQueueSlack records: in an overlapped frame every ray group of the march kernel may hold one slot past the last record)
+        if (queue.ensure((n + kQueueSlack) * kRayRecordFloat4s)) { CK(cudaMemset(queue.p, 0xFF, queue.n * sizeof(float4))); CK(cudaDeviceSynchronize()); }
         zbuf.ensure(n * (size_t)mesh_scale * mesh_scale * 2);
         w = W; h = H;
     }
@@ -141,16 +147,13 @@ struct nmr_ctx {
     uint32_t gather_seq = 0;                              // frames rendered into the shared image so far (same on every rank)
     bool gather_is_dst = false;
     DevBuf<uint32_t> d_counters;
-    DevBuf<uint32_t> d_bands;                             // nmr_render's bands: queue ends e[0..K], cursors c[0..K-1]
-    cudaEvent_t ev_band[8] = {};                          // band b rendered
-    uint32_t* h_bands = nullptr;                          // pinned: the latched queue lengths of the last banded frame
-    int band_w = 0, band_h = 0;                           // resolution the band history below belongs to
-    bool band_was_empty[16] = {};                         // band queued no ray in the previous banded frame
-    DevBuf<uint32_t> d_band_counts;                       // rays queued per band of rows (written by the set-up kernel)
+    cudaEvent_t ev_rows = nullptr;                        // nmr_render: the frame is complete, its rows may be copied out
     uint32_t* h_counters = nullptr;                       // pinned
     DevBuf<float> d_scratch;
     int shard_rank = 0, shard_world = 1, shard_band = 8;
     int surface_mode = 0;                                 // nmr_surface_mode
+    int overlap = 1;                                      // nmr_set_overlap: march kernel consumes the ray queue while the set-up kernel fills it
+    bool last_overlapped = false;                         // the last timed pass ran overlapped (march time comes from device timestamps)
     uint32_t debug_flags = 0;
     nmr_stats stats{};
     bool stats_pending = false;
@@ -183,6 +186,13 @@ int guarded(nmr_ctx* ctx, F&& f) {
         const int code = m.rfind("cannot open", 0) == 0 ? NMR_ERR_IO : NMR_ERR_FORMAT;
         return fail(ctx, code, m);
     }
+}
+
+// the model as the kernels see it under the context's debug flags
+DeviceModel model_for(const nmr_ctx* ctx, const Nerf& n) {
+    DeviceModel d = n.dev;
+    if (ctx->debug_flags & kDebugNoBricks) d.n_brick = 0;
+    return d;
 }
 
 Nerf* get_nerf(nmr_ctx* ctx, int id) {
@@ -403,8 +413,9 @@ FrameParams make_params(nmr_ctx* ctx, const Nerf& n, int W, int H, const float* 
 
 // Frames that can need the reference's per-iteration n_steps schedule: a mesh is in view and the surface rule is `auto`.
 // Returns false (and leaves `sa` zeroed) otherwise.  The histogram is cleared on the stream.
-bool prepare_schedule(nmr_ctx* ctx, const FrameParams& P, SchedArgs& sa, bool clear = true) {
+bool prepare_schedule(nmr_ctx* ctx, const FrameParams& P, SchedArgs& sa, bool clear = true, bool* proved_batch8 = nullptr) {
     sa = SchedArgs{};
+    if (proved_batch8) *proved_batch8 = false;
     if (!(P.mesh_scale > 0 && P.zb_w > 0 && P.surface_mode == kSurfaceAuto)) return false;
     {   // Only pixels inside the two screen rectangles can queue a ray.  When even ALL of them together are at most 1/8 of the pixels
         // this pass traces, the kernel's own rule (live rays * 8 <= pixels) must come out as "8-sample batches": the schedule replay -
@@ -413,7 +424,7 @@ bool prepare_schedule(nmr_ctx* ctx, const FrameParams& P, SchedArgs& sa, bool cl
         const long long occ = (long long)std::max(0, P.occ_px[2] - P.occ_px[0]) * std::max(0, P.occ_px[3] - P.occ_px[1]);
         const long long mesh_px = ((long long)P.zb_w / ms + 2) * ((long long)P.zb_h / ms + 2);
         const long long traced = (long long)P.width * rows_owned_by(P.height, P.shard_rank, P.shard_world, P.shard_band);
-        if ((occ + mesh_px) * 8 <= traced) return false;
+        if ((occ + mesh_px) * 8 <= traced) { if (proved_batch8) *proved_batch8 = true; return false; }
     }
     Surfaces& S = ctx->surf;
     S.hist.ensure(kSchedBins); S.surf_list.ensure((size_t)P.width * P.height);
@@ -425,7 +436,7 @@ bool prepare_schedule(nmr_ctx* ctx, const FrameParams& P, SchedArgs& sa, bool cl
 void enqueue_surface_pass(nmr_ctx* ctx, Nerf& n, const FrameParams& P, const FrameOut& out, uint32_t n_pixels, SchedArgs sa) {
     Surfaces& S = ctx->surf;
     sa.pass = 2;
-    launch_march(P, n.dev, S.queue.p, ctx->d_counters.p, out, n_pixels, ctx->debug_flags, ctx->num_sms, ctx->stream, ctx->d_counters.p + 7, ctx->d_counters.p + 6, &sa, 1);
+    launch_march(P, model_for(ctx, n), S.queue.p, ctx->d_counters.p, out, n_pixels, ctx->debug_flags, ctx->num_sms, ctx->stream, ctx->d_counters.p + 7, ctx->d_counters.p + 6, &sa, 1);
 }
 
 // one sample-per-pixel pass: mesh stage -> init -> march.  Enqueues only; no host synchronisation.
@@ -453,17 +464,30 @@ void enqueue_pass(nmr_ctx* ctx, Nerf& n, const FrameParams& P, bool timed, void*
     if (timed) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     uint64_t launches = 0;
     SchedArgs sa;
-    const bool sched = prepare_schedule(ctx, P, sa, false);
-    // counters, schedule histogram and the mesh visibility window are cleared by one kernel (not three memset nodes)
-    launch_frame_clear(ctx->d_counters.p, sched ? S.hist.p : nullptr, S.zbuf.p, zbuf_window_words(mesh, P), ctx->stream);
+    bool proved_batch8 = false;
+    const bool sched = prepare_schedule(ctx, P, sa, false, &proved_batch8);
+    // OVERLAPPED frame: the march kernel starts while the set-up kernel is still running and consumes the queue as it fills
+    // (kernels.cu: march_kernel).  Possible whenever the march kernel does not need the frame's final live-ray count up front,
+    // i.e. whenever the mesh-surface rule is known on the host: no mesh in view, a pinned rule, or the screen rectangles prove the
+    // 8-sample batches (every BASELINE config); close-ups under the auto rule keep the serial order (they need the count and the
+    // death histogram).  The CUDA-core bring-up variant stays serial as well.
+    static const bool no_overlap_env = std::getenv("NMR_NO_OVERLAP") != nullptr;
+    const bool overlap = ctx->overlap && !no_overlap_env && !sched && !(ctx->debug_flags & kDebugScalarMlp);
+    FrameParams Pm = P;
+    if (overlap && proved_batch8) Pm.surface_mode = kSurfaceBatch8;
+    // counters, schedule histogram, the mesh visibility window and the ready words of the last frame's queue records are
+    // cleared by one kernel (not four memset nodes)
+    launch_frame_clear(ctx->d_counters.p, sched ? S.hist.p : nullptr, S.zbuf.p, zbuf_window_words(mesh, P), S.queue.p, ctx->stream);
     launches += 1;
     if (P.mesh_scale > 0) { launch_mesh_raster(mesh, P, rows, S.zbuf.p, ctx->stream, false); launches += 1; }
-    launch_init_rays(P, n.dev, mesh, S.zbuf.p, rows, S.queue.p, ctx->d_counters.p, out, ctx->num_sms, ctx->stream, false, sched ? S.surf_list.p : nullptr, 1);
-    launches += 1;
-    if (timed) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    const int init_ctas = launch_init_rays(P, n.dev, mesh, S.zbuf.p, rows, S.queue.p, ctx->d_counters.p, out, ctx->num_sms, ctx->stream, false, sched ? S.surf_list.p : nullptr, 1);
+    launches += rows > 0 ? (init_ctas > 0 ? 2 : 1) : 0;                       // background kernel + set-up kernel over the tile box
+    if (timed && !overlap) CK(cudaEventRecord(ctx->ev[1], ctx->stream));      // (an event between the two kernels would serialise them)
     const uint32_t n_pixels = (uint32_t)P.width * (uint32_t)rows;
-    launch_march(P, n.dev, S.queue.p, ctx->d_counters.p, out, n_pixels, ctx->debug_flags, ctx->num_sms, ctx->stream, nullptr, nullptr, sched ? &sa : nullptr, ctx->march_ctas);
+    launch_march(Pm, model_for(ctx, n), S.queue.p, ctx->d_counters.p, out, n_pixels, ctx->debug_flags, ctx->num_sms, ctx->stream, nullptr, nullptr, sched ? &sa : nullptr, ctx->march_ctas,
+                 overlap ? init_ctas : -1);
     launches += 1;
+    if (timed) ctx->last_overlapped = overlap;
     if (sched) { enqueue_surface_pass(ctx, n, P, out, n_pixels, sa); launches += 1; }
     if (timed) {
         CK(cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -476,65 +500,19 @@ void enqueue_pass(nmr_ctx* ctx, Nerf& n, const FrameParams& P, bool timed, void*
     CK(cudaGetLastError());
 }
 
-// nmr_render's single-sample path: the 16 bytes per pixel cross PCIe underneath the rendering instead of after it.
-// Rows that queue no ray (pure background) are final right after their ray set-up, and in render.py's framing that is most of
-// the picture.  Which rows those are is only known on the device, so the host goes by the previous frame rendered this way at
-// this resolution (kBands bands of rows; a band counts as busy unless it queued nothing last time): the rows above and
-// below the busy bands are set up first and handed to the copy stream at once; the busy rows are then set up, marched and
-// copied as one block, i.e. the latency-bound kernels run once over all the live rays, exactly as in frame().
-// The queue lengths latched after each set-up come back with the frame: if rows predicted empty did queue rays the frame is
-// rendered again the plain way (nmr_render checks), so the prediction only ever costs time, never pixels.
-constexpr int kBands = 12;
-struct BandPlan { int y0, y1; };     // busy rows [y0, y1); ranges in queue order: [0, y0), [y1, H), [y0, y1)
-
-BandPlan enqueue_pass_banded(nmr_ctx* ctx, Nerf& n, const FrameParams& P0, void* out_host) {
-    constexpr int K = kBands;
+// nmr_render's single-sample path: the image crosses PCIe underneath the rendering instead of after it.
+// Rows above and below both screen rectangles (occupied box, mesh) are background whatever the GPU does - the host knows them
+// before anything is launched, and in render.py's framing they are most of the picture.  They leave at once on the copy stream
+// from an image of nothing but the background colour, so the copy engine, which bounds a float32 call, starts at time zero; the
+// rows in between follow as one block when the frame (one overlapped pass, exactly as in frame()) is complete.
+void enqueue_pass_with_copy(nmr_ctx* ctx, Nerf& n, const FrameParams& P0, void* out_host) {
     Surfaces& S = ctx->surf;
     const size_t bpp = pixel_bytes(P0.out_format);
-    S.image_format = P0.out_format; S.image_is_frame = false;
-    const int band_rows = (P0.height + K - 1) / K;
-    const bool probes = (ctx->debug_flags & kDebugKeepProbes) != 0;
-    FrameOut out{S.image.p, S.accum.p, probes ? S.frame.p : nullptr, probes ? S.depth.p : nullptr, probes ? S.n_samples.p : nullptr, nullptr, nullptr};
-    MeshDevice mesh = ctx->mesh_dev;
-    if (!P0.lens_on) mesh.tri_lens = nullptr;
-    else {
-        S.lens.ensure((size_t)P0.width * P0.height * 2);
-        S.lens_scratch.ensure((size_t)ctx->num_sms * 4 * 32 * kLensStash);
-        out.lens = S.lens.p; out.lens_scratch = S.lens_scratch.p;
-    }
-    if (ctx->band_w != P0.width || ctx->band_h != P0.height) {      // no history at this resolution: every band may hold rays
-        ctx->band_w = P0.width; ctx->band_h = P0.height;
-        for (bool& q : ctx->band_was_empty) q = false;
-    }
-    int b0 = 0, b1 = K;                                            // busy bands [b0, b1), one band of slack on either side
-    while (b0 < K && ctx->band_was_empty[b0]) ++b0;
-    while (b1 > b0 && ctx->band_was_empty[b1 - 1]) --b1;
-    if (b0 >= b1) { b0 = 0; b1 = 0; }                              // nothing was busy: the whole frame is "above"
-    else { b0 = std::max(0, b0 - 1); b1 = std::min(K, b1 + 1); }
-    BandPlan plan{std::min(P0.height, b0 * band_rows), std::min(P0.height, b1 * band_rows)};
-    if (b0 == 0 && b1 == 0) plan.y0 = plan.y1 = P0.height;
-
-    ctx->d_band_counts.ensure(K);
-    CK(cudaMemsetAsync(ctx->d_band_counts.p, 0, sizeof(uint32_t) * K, ctx->stream));
-    out.band_counts = ctx->d_band_counts.p; out.band_rows = band_rows;
-    ctx->d_bands.ensure(8);
-    uint32_t* e = ctx->d_bands.p;            // e[0] = 0, e[i + 1] = queue length after the i-th set-up
-    uint32_t* c = ctx->d_bands.p + 4;        // cursor of the busy block's march, starts at e[2]
-    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-    uint64_t launches = 0;
-    SchedArgs sa;
-    const bool sched = prepare_schedule(ctx, P0, sa);
-    if (P0.mesh_scale > 0) { launch_mesh_raster(mesh, P0, P0.height, S.zbuf.p, ctx->stream); launches += 1; }
-    CK(cudaMemsetAsync(e, 0, sizeof(uint32_t) * 8, ctx->stream));
-    auto copy_rows = [&](int y0, int y1, const void* src = nullptr) {
+    auto copy_rows = [&](int y0, int y1, const void* src) {
         if (y1 <= y0) return;
         const size_t off = (size_t)y0 * P0.width * bpp;
-        CK(cudaMemcpyAsync(static_cast<char*>(out_host) + off, static_cast<const char*>(src ? src : static_cast<const void*>(S.image.p)) + off, (size_t)(y1 - y0) * P0.width * bpp, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        CK(cudaMemcpyAsync(static_cast<char*>(out_host) + off, static_cast<const char*>(src) + off, (size_t)(y1 - y0) * P0.width * bpp, cudaMemcpyDeviceToHost, ctx->copy_stream));
     };
-    // Rows above and below both screen rectangles (occupied box, mesh) are background whatever the GPU does - the host knows
-    // them before anything is launched.  They leave at once from an image of nothing but the background colour, so the copy
-    // engine, which bounds this call, starts at time zero instead of after the first set-up pass.  (The set-up kernel still
-    // writes them into the device image.)
     int known_top = 0, known_bot = P0.height;          // rows [0, known_top) and [known_bot, H) are known background
     {
         int r0 = P0.height, r1 = 0;                    // rows that may hold anything else: union of the rectangles
@@ -554,48 +532,16 @@ BandPlan enqueue_pass_banded(nmr_ctx* ctx, Nerf& n, const FrameParams& P0, void*
             CK(cudaStreamSynchronize(ctx->stream));
             std::memcpy(S.bg_value, P0.background_out, 16); S.bg_pixels = px; S.bg_format = P0.out_format;
         }
-        copy_rows(0, known_top, S.bg_image.p);
-        copy_rows(known_bot, P0.height, S.bg_image.p);
     }
-    auto hand_over = [&](int i, int y0, int y1) {   // everything enqueued so far on the render stream precedes the copy of these rows
-        CK(cudaEventRecord(ctx->ev_band[i], ctx->stream));
-        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_band[i], 0));
-        copy_rows(y0, y1);
-    };
-    const int ranges[3][2] = {{0, plan.y0}, {plan.y1, P0.height}, {plan.y0, plan.y1}};
-    for (int i = 0; i < 3; ++i) {
-        FrameParams P = P0;
-        P.row0 = ranges[i][0];
-        const int rows = ranges[i][1] - ranges[i][0];
-        if (rows > 0) {
-            launch_init_rays(P, n.dev, mesh, S.zbuf.p, rows, S.queue.p, ctx->d_counters.p, out, ctx->num_sms, ctx->stream, i == 0, sched ? S.surf_list.p : nullptr);
-            launches += 1;
-        } else if (i == 0) {
-            CK(cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(uint32_t) * kNumCounters, ctx->stream));
-        }
-        launch_latch_word(ctx->d_counters.p, e + i + 1, i == 1 ? c : nullptr, ctx->stream);     // (the march cursor starts at e[2])
-        if (i < 2 && rows > 0) hand_over(i, std::max(ranges[i][0], i == 0 ? known_top : 0), std::min(ranges[i][1], i == 1 ? known_bot : P0.height));   // (minus the rows that have left already)
-    }
-    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-    const uint32_t n_pixels = (uint32_t)P0.width * (uint32_t)P0.height;
-    if (plan.y1 > plan.y0) {
-        launch_march(P0, n.dev, S.queue.p, ctx->d_counters.p, out, n_pixels, ctx->debug_flags, ctx->num_sms, ctx->stream, e + 3, c, sched ? &sa : nullptr);
-        launches += 1;
-        if (sched) { enqueue_surface_pass(ctx, n, P0, out, n_pixels, sa); launches += 1; }
-        hand_over(2, std::max(plan.y0, known_top), std::min(plan.y1, known_bot));      // (the busy block minus the rows that have left already)
-    }
-    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
-    // small read-backs last: the device->host engine is busy with the image rows, and nothing on the render stream may wait for it
-    CK(cudaMemcpyAsync(ctx->h_bands, e, sizeof(uint32_t) * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, sizeof(uint32_t) * kNumCounters, cudaMemcpyDeviceToHost, ctx->stream));
-    // per-band ray counts of this frame for the next prediction: the set-up kernels count queued rays per band
-    CK(cudaMemcpyAsync(ctx->h_bands + 4, ctx->d_band_counts.p, sizeof(uint32_t) * K, cudaMemcpyDeviceToHost, ctx->stream));
-    ctx->stats.rays = (uint64_t)P0.width * P0.height;
-    ctx->stats.mesh_rays = P0.mesh_scale > 0 ? (uint64_t)P0.width * P0.height * P0.mesh_scale * P0.mesh_scale : 0;
-    ctx->stats.kernel_launches = launches;
-    ctx->stats_pending = true;
+    // The frame's kernels are submitted FIRST: copies submitted to the copy stream ahead of them hold them back until the copies
+    // are done (measured: 0.87 ms per float32 call against 0.65 ms this way round, profiles/r2_experiments.md).
+    enqueue_pass(ctx, n, P0, true);
+    copy_rows(0, known_top, S.bg_image.p);
+    copy_rows(known_bot, P0.height, S.bg_image.p);
+    CK(cudaEventRecord(ctx->ev_rows, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rows, 0));
+    copy_rows(known_top, known_bot, S.image.p);
     CK(cudaGetLastError());
-    return plan;
 }
 
 void finish_stats(nmr_ctx* ctx) {
@@ -607,7 +553,15 @@ void finish_stats(nmr_ctx* ctx) {
     ctx->stats.batch_passes = ctx->h_counters[5];
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[2])); ctx->stats.gpu_ms = ms;
-    CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2])); ctx->stats.march_ms = ms;
+    if (ctx->last_overlapped) {
+        // overlapped frame: no event separates the two kernels; the march kernel's own span (first CTA start to last CTA end,
+        // globaltimer) includes the time it waited for the set-up kernel to queue rays
+        const uint64_t t0 = (uint64_t)ctx->h_counters[kCntMarchStart] | ((uint64_t)ctx->h_counters[kCntMarchStart + 1] << 32);
+        const uint64_t t1 = (uint64_t)ctx->h_counters[kCntMarchEnd] | ((uint64_t)ctx->h_counters[kCntMarchEnd + 1] << 32);
+        ctx->stats.march_ms = t1 > t0 ? (float)((double)(t1 - t0) * 1e-6) : 0.f;
+    } else {
+        CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2])); ctx->stats.march_ms = ms;
+    }
     ctx->stats_pending = false;
     if (const char* path = std::getenv("NMR_PHASE_LOG")) {
         if (ctx->d_phase_log.p) {        // raw dump of the last timed frame's phase clocks
@@ -626,6 +580,7 @@ nmr_ctx* make_lane(nmr_ctx* parent) {
     for (auto& ev : l->ev) CK(cudaEventCreate(&ev));
     for (auto& pair : l->ev_view) for (auto& ev : pair) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     l->d_counters.ensure(kNumCounters);
+    CK(cudaMemset(l->d_counters.p, 0, sizeof(uint32_t) * kNumCounters));
     CK(cudaHostAlloc((void**)&l->h_counters, sizeof(uint32_t) * kNumCounters, cudaHostAllocDefault));
     std::memset(l->h_counters, 0, sizeof(uint32_t) * kNumCounters);
     return l.release();
@@ -642,7 +597,7 @@ void destroy_lane(nmr_ctx* l) {
 // what a lane needs to know about the scene for enqueue_pass: the parent's mesh buffers (borrowed) and settings
 void sync_lane(nmr_ctx* l, const nmr_ctx* parent) {
     l->mesh_dev = parent->mesh_dev; l->mesh_scale = parent->mesh_scale; l->debug_flags = parent->debug_flags;
-    l->scene_has_lens = parent->scene_has_lens; l->surface_mode = parent->surface_mode;
+    l->scene_has_lens = parent->scene_has_lens; l->surface_mode = parent->surface_mode; l->overlap = parent->overlap;
 }
 
 void set_camera_from_orbit(nmr_ctx* ctx) {
@@ -674,12 +629,11 @@ NMR_API int nmr_create(int width, int height, int device, nmr_ctx** out_ctx) {
         for (auto& ev : ctx->ev) CK(cudaEventCreate(&ev));
         CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         for (auto& pair : ctx->ev_view) for (auto& ev : pair) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        for (auto& ev : ctx->ev_band) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ev_rows, cudaEventDisableTiming));
         ctx->d_counters.ensure(kNumCounters);
+        CK(cudaMemset(ctx->d_counters.p, 0, sizeof(uint32_t) * kNumCounters));
         ctx->d_scratch.ensure(64);
         CK(cudaHostAlloc((void**)&ctx->h_counters, sizeof(uint32_t) * kNumCounters, cudaHostAllocDefault));
-        CK(cudaHostAlloc((void**)&ctx->h_bands, sizeof(uint32_t) * 32, cudaHostAllocDefault));
-        std::memset(ctx->h_bands, 0, sizeof(uint32_t) * 32);
         std::memset(ctx->h_counters, 0, sizeof(uint32_t) * kNumCounters);
     } catch (const std::exception& ex) {
         return fail(nullptr, NMR_ERR_CUDA, ex.what());
@@ -701,10 +655,9 @@ NMR_API void nmr_destroy(nmr_ctx* ctx) {
     ctx->lanes.clear();
     ctx->nerfs.clear(); ctx->meshes.clear();
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
-    if (ctx->h_bands) cudaFreeHost(ctx->h_bands);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto& pair : ctx->ev_view) for (auto& ev : pair) if (ev) cudaEventDestroy(ev);
-    for (auto& ev : ctx->ev_band) if (ev) cudaEventDestroy(ev);
+    if (ctx->ev_rows) cudaEventDestroy(ctx->ev_rows);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -756,6 +709,32 @@ NMR_API int nmr_load_nerf(nmr_ctx* ctx, const char* path, int* out_id) {
             d.stride_y[l] = h.stride_y[l]; d.stride_z[l] = h.stride_z[l];
             if (h.dense[l]) d.dense_mask |= 1u << l;
             if ((d.level_size[l] & (d.level_size[l] - 1u)) == 0) d.pow2_mask |= 1u << l;
+        }
+        {   // Brick layout of the coarse levels: a prefix of the levels, as many as fit the budget (NMR_BRICK_MB, default 28 MiB:
+            // levels 0-5 of the stock configuration - the five dense levels and the first hashed one, 27 MiB next to a 23 MiB
+            // table in a 126 MB L2; 0 switches the layout off).  Cells per axis = the level's resolution: a position in the unit
+            // cube never produces a larger cell coordinate (scale <= res - 1).
+            static const long brick_mb = [] { const char* v = std::getenv("NMR_BRICK_MB"); return v ? std::atol(v) : 28L; }();
+            size_t cells_total = 0; int n_brick = 0;
+            for (int l = 0; l < h.n_levels; ++l) {
+                const size_t r3 = (size_t)h.resolutions[l] * h.resolutions[l] * h.resolutions[l];
+                if (h.resolutions[l] > 1024u || (cells_total + r3) * 32 > (size_t)std::max(0L, brick_mb) << 20) break;
+                cells_total += r3; ++n_brick;
+            }
+            d.n_brick = 0;
+            if (n_brick > 0) {
+                n->d_bricks.ensure(cells_total * 2);
+                size_t off = 0;
+                for (int l = 0; l < n_brick; ++l) {
+                    const uint32_t r = h.resolutions[l];
+                    d.brick[l] = n->d_bricks.p + off * 2; d.brick_res[l] = r;
+                    launch_brick_build(d, l, r, n->d_bricks.p + off * 2, ctx->stream);
+                    off += (size_t)r * r * r;
+                }
+                CK(cudaStreamSynchronize(ctx->stream));
+                CK(cudaGetLastError());
+                d.n_brick = (uint32_t)n_brick;
+            }
         }
         std::memcpy(n->render_aabb_min, h.render_aabb_min, 12); std::memcpy(n->render_aabb_max, h.render_aabb_max, 12);
         update_occupied_box(ctx, *n);
@@ -895,6 +874,10 @@ NMR_API int nmr_set_lens(nmr_ctx* ctx, int enabled, float ior, float transmissio
     });
 }
 
+NMR_API int nmr_set_overlap(nmr_ctx* ctx, int enabled) {
+    return guarded(ctx, [&]() -> int { ctx->overlap = enabled ? 1 : 0; return NMR_OK; });
+}
+
 NMR_API int nmr_set_surface_insertion(nmr_ctx* ctx, int mode) {
     return guarded(ctx, [&]() -> int {
         if (mode < NMR_SURFACE_AUTO || mode > NMR_SURFACE_BATCH8) return fail(ctx, NMR_ERR_INVALID, "bad surface insertion mode");
@@ -981,19 +964,14 @@ NMR_API int nmr_render_format(nmr_ctx* ctx, int nerf_id, int width, int height, 
         // renderer's constructor resolution, not from (width, height), exactly like the reference.
         static const bool no_bands = std::getenv("NMR_NO_BANDS") != nullptr;     // measurement aid: plain render + one copy
         if (spp == 1 && ctx->shard_world == 1 && height >= 256 && !no_bands) {
-            // one sample per pixel: bands of rows are copied out while the next ones are still being marched
+            // one sample per pixel: the rows known to be background leave while the frame is still being rendered
             FrameParams P = make_params(ctx, *n, width, height, ctx->cam12, 0, !linear, true);
             P.out_format = format;
-            const BandPlan plan = enqueue_pass_banded(ctx, *n, P, out_rgba);
+            enqueue_pass_with_copy(ctx, *n, P, out_rgba);
             CK(cudaStreamSynchronize(ctx->copy_stream));
             CK(cudaStreamSynchronize(ctx->stream));
-            // rows predicted empty are [0, y0) and [y1, H): they were the first two set-ups (queue lengths h_bands[1], h_bands[2])
-            const bool mispredicted = ctx->h_bands[2] != 0u;
-            for (int b = 0; b < kBands; ++b) ctx->band_was_empty[b] = ctx->h_bands[4 + b] == 0u;
             ctx->surf.spp = 0;
-            (void)plan;
-            if (!mispredicted) return NMR_OK;
-            // a band that used to be empty queued rays this time and was copied out unmarched: render the frame the plain way
+            return NMR_OK;
         }
         for (int i = 0; i < spp; ++i) {
             FrameParams P = make_params(ctx, *n, width, height, ctx->cam12, ctx->surf.spp, !linear, true);
@@ -1278,7 +1256,7 @@ int run_probe(nmr_ctx* ctx, int id, int mode, int64_t n, const float* points_wor
         d_pts.ensure((size_t)n * 3); d_out.ensure((size_t)n);
         CK(cudaMemcpyAsync(d_pts.p, points_world, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
         const FrameParams P = make_params(ctx, *nf, ctx->width, ctx->height, ctx->cam12, 0, true, false);
-        launch_probe(P, nf->dev, d_pts.p, direction, n, mode, d_out.p, ctx->debug_flags, ctx->num_sms, ctx->stream);
+        launch_probe(P, model_for(ctx, *nf), d_pts.p, direction, n, mode, d_out.p, ctx->debug_flags, ctx->num_sms, ctx->stream);
         CK(cudaMemcpyAsync(out, d_out.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         CK(cudaGetLastError());
@@ -1301,7 +1279,7 @@ NMR_API int nmr_debug_encode(nmr_ctx* ctx, int id, const float* pos, int64_t n, 
         DevBuf<float> d_pos; DevBuf<uint16_t> d_out;
         d_pos.ensure((size_t)n * 3); d_out.ensure((size_t)n * ENC_WIDTH);
         CK(cudaMemcpyAsync(d_pos.p, pos, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
-        launch_debug_encode(nf->dev, d_pos.p, n, d_out.p, ctx->stream);
+        launch_debug_encode(model_for(ctx, *nf), d_pos.p, n, d_out.p, ctx->stream);
         CK(cudaMemcpyAsync(out, d_out.p, (size_t)n * ENC_WIDTH * 2, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         CK(cudaGetLastError());
@@ -1317,7 +1295,7 @@ NMR_API int nmr_debug_network(nmr_ctx* ctx, int id, const float* pos, const floa
         d_pos.ensure((size_t)n * 3); d_dir.ensure((size_t)n * 3); d_out.ensure((size_t)n * 4);
         CK(cudaMemcpyAsync(d_pos.p, pos, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(d_dir.p, dir, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
-        launch_debug_network(nf->dev, d_pos.p, d_dir.p, n, d_out.p, ctx->debug_flags, ctx->stream);
+        launch_debug_network(model_for(ctx, *nf), d_pos.p, d_dir.p, n, d_out.p, ctx->debug_flags, ctx->stream);
         CK(cudaMemcpyAsync(out4, d_out.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         CK(cudaGetLastError());

@@ -32,6 +32,13 @@ struct DeviceModel {
     uint32_t dense_mask;              // bit l set: level l is indexed densely
     uint32_t pow2_mask;               // bit l set: level_size[l] is a power of two (index & (size - 1))
     uint32_t prime[3];                // hash multipliers of the snapshot's hash type (CoherentPrime: 1, 2654435761, 805459861)
+    // Levels [0, n_brick) re-laid out at load time as 2x2x2 BRICKS (brick_build_kernel): cell (gx, gy, gz) of a level of `brick_res`
+    // cells per axis owns 32 bytes = the eight corner entries of that cell in corner order, i.e. exactly the values the plain
+    // layout returns for the indices of grid.h:317-343 (index wrap included).  One 32-byte sector per sample and level instead of
+    // eight 4-byte gathers with eight index computations; values and blend order unchanged, so the features stay bit-identical.
+    const uint4* brick[N_LEVELS];
+    uint32_t brick_res[N_LEVELS];
+    uint32_t n_brick;
 };
 
 struct MeshDevice {
@@ -446,18 +453,23 @@ __device__ __forceinline__ int next_sample(const FrameParams& P, const uint8_t* 
 }
 
 // ---- multiresolution hash-grid encoding (T/.../encodings/grid.h:111-186, 219-349) ------------------------------
-// One level: eight half2 gathers, trilinear blend accumulated IN FP16 in corner order 0..7 (grid.h:317-343).
-// Hash = x*p0 ^ y*p1 ^ z*p2 with the multipliers of the snapshot's hash type (prime_hash / reversed_prime_hash).
-__device__ __forceinline__ __half2 encode_level(const DeviceModel& M, int level, V3 p01) {
-    const float scale = M.level_scale[level];
-    const uint32_t size = M.level_size[level];
-    const __half2* __restrict__ grid = M.level_ptr[level];
+// Per level: cell coordinates and trilinear weights, the eight corner entries (three ways to fetch them, below), and the blend
+// accumulated IN FP16 in corner order 0..7 with every product rounded to fp32 and then to fp16 first (grid.h:317-343).
+struct LevelCell { uint32_t gx, gy, gz; float wx0, wx1, wy0, wy1, wz0, wz1; };
+__device__ __forceinline__ LevelCell level_cell(float scale, V3 p01) {
     const float fx = p01.x * scale + 0.5f, fy = p01.y * scale + 0.5f, fz = p01.z * scale + 0.5f;
     const float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
-    const uint32_t gx = (uint32_t)(int)flx, gy = (uint32_t)(int)fly, gz = (uint32_t)(int)flz;
-    const float wx1 = fx - flx, wy1 = fy - fly, wz1 = fz - flz;
-    const float wx0 = 1 - wx1, wy0 = 1 - wy1, wz0 = 1 - wz1;
-    uint32_t index[8];
+    LevelCell c;
+    c.gx = (uint32_t)(int)flx; c.gy = (uint32_t)(int)fly; c.gz = (uint32_t)(int)flz;
+    c.wx1 = fx - flx; c.wy1 = fy - fly; c.wz1 = fz - flz;
+    c.wx0 = 1 - c.wx1; c.wy0 = 1 - c.wy1; c.wz0 = 1 - c.wz1;
+    return c;
+}
+
+// indices of the eight corners of cell (gx, gy, gz) in the plain layout of `level`: dense (x + y * stride_y + z * stride_z, mod
+// size) or hashed (x*p0 ^ y*p1 ^ z*p2 with the multipliers of the snapshot's hash type, prime_hash / reversed_prime_hash)
+__device__ __forceinline__ void level_indices(const DeviceModel& M, int level, uint32_t gx, uint32_t gy, uint32_t gz, uint32_t index[8]) {
+    const uint32_t size = M.level_size[level];
     if ((M.dense_mask >> level) & 1u) {
         const uint32_t sy = M.stride_y[level], sz = M.stride_z[level];
         const uint32_t y0 = gy * sy, z0 = gz * sz;
@@ -473,29 +485,76 @@ __device__ __forceinline__ __half2 encode_level(const DeviceModel& M, int level,
         }
     } else {
         const uint32_t p0 = M.prime[0], p1 = M.prime[1], p2 = M.prime[2];
-        const uint32_t hx = gx * p0, hy = gy * p1, hz = gz * p2;
+        const uint32_t hx0 = gx * p0, hy0 = gy * p1, hz0 = gz * p2;
+        const uint32_t hx1 = hx0 + p0, hy1 = hy0 + p1, hz1 = hz0 + p2;
         const uint32_t mask = size - 1u;       // a hashed level always has exactly 2^log2_hashmap_size entries
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-            index[c] = ((hx + (c & 1) * p0) ^ (hy + ((c >> 1) & 1) * p1) ^ (hz + ((c >> 2) & 1) * p2)) & mask;
+        // the four (y, z) partial hashes once, then one (a ^ b) & mask per corner
+        const uint32_t yz00 = hy0 ^ hz0, yz10 = hy1 ^ hz0, yz01 = hy0 ^ hz1, yz11 = hy1 ^ hz1;
+        index[0] = (hx0 ^ yz00) & mask; index[1] = (hx1 ^ yz00) & mask; index[2] = (hx0 ^ yz10) & mask; index[3] = (hx1 ^ yz10) & mask;
+        index[4] = (hx0 ^ yz01) & mask; index[5] = (hx1 ^ yz01) & mask; index[6] = (hx0 ^ yz11) & mask; index[7] = (hx1 ^ yz11) & mask;
     }
-    __half2 v[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) v[c] = __ldg(grid + index[c]);
+}
+
+// two fp32 products in one instruction (FMUL2, sm_100): each lane is an ordinary round-to-nearest fp32 multiply, so results equal
+// two separate multiplies bit for bit
+__device__ __forceinline__ unsigned long long f32x2(float lo, float hi) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ unsigned long long mul_f32x2(unsigned long long a, unsigned long long b) { unsigned long long d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ void split_f32x2(unsigned long long v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+
+// acc = sum over corners c = 0..7, in that order, of fp16(w_c * v[c]) with w_c = ((1 * wx) * wy) * wz (grid.h:326-343).
+// Corners 2k and 2k + 1 differ in x only: their weights are one FMUL2 pair, and so are their products per feature.
+__device__ __forceinline__ __half2 blend_corners(const __half2 v[8], const LevelCell& c) {
+    const unsigned long long wx = f32x2(c.wx0, c.wx1);
+    const unsigned long long wxy0 = mul_f32x2(wx, f32x2(c.wy0, c.wy0)), wxy1 = mul_f32x2(wx, f32x2(c.wy1, c.wy1));
+    const unsigned long long wz0 = f32x2(c.wz0, c.wz0), wz1 = f32x2(c.wz1, c.wz1);
+    const unsigned long long w[4] = {mul_f32x2(wxy0, wz0), mul_f32x2(wxy1, wz0), mul_f32x2(wxy0, wz1), mul_f32x2(wxy1, wz1)};
     __half2 acc = __floats2half2_rn(0.f, 0.f);
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        // weight = 1 * wx * wy * wz, multiplied in dimension order like the reference's loop
-        const float w = ((1.0f * ((c & 1) ? wx1 : wx0)) * (((c >> 1) & 1) ? wy1 : wy0)) * (((c >> 2) & 1) ? wz1 : wz0);
-        const float2 d = __half22float2(v[c]);
-        acc = __hadd2(acc, __floats2half2_rn(w * d.x, w * d.y));
+    for (int k = 0; k < 4; ++k) {
+        const float2 a = __half22float2(v[2 * k]), b = __half22float2(v[2 * k + 1]);
+        float x0, x1, y0, y1;
+        split_f32x2(mul_f32x2(w[k], f32x2(a.x, b.x)), x0, x1);
+        split_f32x2(mul_f32x2(w[k], f32x2(a.y, b.y)), y0, y1);
+        acc = __hadd2(acc, __floats2half2_rn(x0, y0));
+        acc = __hadd2(acc, __floats2half2_rn(x1, y1));
     }
     return acc;
 }
 
+// One level of one sample.  BRICKS: levels below M.n_brick fetch their eight corners with a single 32-byte load from the brick
+// layout (a cell coordinate outside the brick grid - a position outside the unit cube - takes the plain path); the others, and
+// every level when !BRICKS, gather them one by one from the plain layout.  One copy of the cell arithmetic and of the blend.
+template <bool BRICKS>
+__device__ __forceinline__ __half2 encode_level_t(const DeviceModel& M, int level, V3 p01) {
+    const LevelCell c = level_cell(M.level_scale[level], p01);
+    __half2 v[8];
+    bool bricked = false;
+    if (BRICKS && (uint32_t)level < M.n_brick) {
+        const uint32_t res = M.brick_res[level];
+        if (c.gx < res && c.gy < res && c.gz < res) {
+            const uint4* __restrict__ b = M.brick[level] + 2u * ((c.gz * res + c.gy) * res + c.gx);
+            uint32_t r[8];
+            asm("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(b));
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = *reinterpret_cast<const __half2*>(&r[k]);
+            bricked = true;
+        }
+    }
+    if (!bricked) {
+        uint32_t index[8];
+        level_indices(M, level, c.gx, c.gy, c.gz, index);
+        const __half2* __restrict__ grid = M.level_ptr[level];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = __ldg(grid + index[k]);
+    }
+    return blend_corners(v, c);
+}
+__device__ __forceinline__ __half2 encode_level(const DeviceModel& M, int level, V3 p01) { return encode_level_t<false>(M, level, p01); }
+
 // All 16 levels of one sample.  Features (2l, 2l+1) of level l go to dst + (l / 4) * chunk_stride + (l % 4) * 4, i.e. four
 // 16-byte chunks of 8 features.  UNROLL levels are kept in flight per thread (8 * UNROLL gathers); the loop itself stays
-// rolled so the kernel fits the instruction cache.
+// rolled so the kernel fits the instruction cache.  (Parity probes and the probe kernel; plain layout only.)
 template <int UNROLL>
 __device__ __forceinline__ void encode_chunks(const DeviceModel& M, V3 p01, char* dst, int chunk_stride) {
 #pragma unroll 1
@@ -512,11 +571,11 @@ __device__ __forceinline__ void encode_chunks(const DeviceModel& M, V3 p01, char
 }
 
 // Levels first, first + step, ... of one sample (step lanes share a sample when a warp has few of them, see march_kernel step 2);
-// same destination layout as encode_chunks.  The loop stays rolled: one copy of encode_level in the kernel.
+// same destination layout as encode_chunks.  Bricked levels take the brick path.  The loop stays rolled: one copy of each path.
 __device__ __forceinline__ void encode_levels_strided(const DeviceModel& M, V3 p01, char* dst, int chunk_stride, uint32_t first, uint32_t step) {
 #pragma unroll 1
     for (uint32_t l = first; l < (uint32_t)N_LEVELS; l += step) {
-        const __half2 e = encode_level(M, (int)l, p01);
+        const __half2 e = encode_level_t<true>(M, (int)l, p01);
         *reinterpret_cast<__half2*>(dst + (size_t)(l >> 2) * chunk_stride + (l & 3u) * 4u) = e;
     }
 }

@@ -121,6 +121,26 @@ void launch_coarse_build(const uint8_t* d_bitfield, uint8_t* d_occ_scratch, uint
     coarse_near_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_occ_scratch, d_near_bits);
 }
 
+// Brick layout of one level (DeviceModel::brick): cell (gx, gy, gz) -> the eight corner entries the plain layout returns for it,
+// in corner order.  Load time only.
+__global__ void brick_build_kernel(DeviceModel M, int level, uint32_t res, uint4* __restrict__ out) {
+    const uint32_t cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= res * res * res) return;
+    const uint32_t gx = cell % res, gy = (cell / res) % res, gz = cell / (res * res);
+    uint32_t index[8];
+    level_indices(M, level, gx, gy, gz, index);
+    const uint32_t* __restrict__ grid = reinterpret_cast<const uint32_t*>(M.level_ptr[level]);
+    uint32_t v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = __ldg(grid + index[c]);
+    out[2 * (size_t)cell] = make_uint4(v[0], v[1], v[2], v[3]);
+    out[2 * (size_t)cell + 1] = make_uint4(v[4], v[5], v[6], v[7]);
+}
+void launch_brick_build(const DeviceModel& M, int level, uint32_t res, void* d_out, cudaStream_t s) {
+    const uint32_t cells = res * res * res;
+    brick_build_kernel<<<(cells + 255) / 256, 256, 0, s>>>(M, level, res, reinterpret_cast<uint4*>(d_out));
+}
+
 void launch_occupancy_build(const uint16_t* d_grid, int n_cascades_present, uint8_t* d_bitfield, float* d_scratch, cudaStream_t s) {
     double* sum = reinterpret_cast<double*>(d_scratch);
     cudaMemsetAsync(sum, 0, sizeof(double), s);
@@ -192,9 +212,13 @@ __global__ void __launch_bounds__(256) mesh_raster_kernel(MeshDevice mesh, Frame
 
 // One launch instead of three memset nodes at the head of a frame: device counters, the schedule histogram and the mesh
 // visibility window (every stream node costs 2-4 us of device time on a 250 us frame).
-__global__ void frame_clear_kernel(uint32_t* __restrict__ counters, uint32_t* __restrict__ hist, ulonglong2* __restrict__ zbuf2, size_t zbuf_pairs) {
+__global__ void frame_clear_kernel(uint32_t* __restrict__ counters, uint32_t* __restrict__ hist, ulonglong2* __restrict__ zbuf2, size_t zbuf_pairs, float4* __restrict__ queue) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
-    if (i < (size_t)kNumCounters) counters[i] = 0u;
+    // ready words of the records the previous frame queued (its march kernel left their number; nobody writes that word here)
+    const uint32_t prev = counters[kCntPrevCount];
+    if (queue) for (size_t k = i; k < (size_t)prev; k += stride) reinterpret_cast<uint32_t*>(queue + k * kRayRecordFloat4s + 1)[2] = kEmptyRecord;
+    if (i < (size_t)kFrameCounters) counters[i] = 0u;
+    if (i == 0) { counters[kCntMarchStart] = 0xFFFFFFFFu; counters[kCntMarchStart + 1] = 0xFFFFFFFFu; counters[kCntMarchEnd] = 0u; counters[kCntMarchEnd + 1] = 0u; }
     if (hist) for (size_t k = i; k < kSchedBins; k += stride) hist[k] = 0u;
     if (zbuf2) for (size_t k = i; k < zbuf_pairs; k += stride) zbuf2[k] = make_ulonglong2(~0ull, ~0ull);
 }
@@ -202,11 +226,12 @@ size_t zbuf_window_words(const MeshDevice& mesh, const FrameParams& P) {
     if (P.mesh_scale <= 0 || mesh.n_tris == 0 || P.zb_w <= 0 || P.zb_h <= 0) return 0;
     return (size_t)P.zb_w * P.zb_h * (mesh.tri_lens ? 2 : 1);
 }
-void launch_frame_clear(uint32_t* d_counters, uint32_t* d_hist, unsigned long long* d_zbuf, size_t zbuf_words, cudaStream_t s) {
+void launch_frame_clear(uint32_t* d_counters, uint32_t* d_hist, unsigned long long* d_zbuf, size_t zbuf_words, float4* d_queue, cudaStream_t s) {
     const size_t pairs = (zbuf_words + 1) / 2;        // the buffer is allocated for the whole 2W x 2H frame (even), the window never fills it to the last word
-    const size_t work = pairs > kSchedBins ? pairs : kSchedBins;
+    const size_t floor_work = (size_t)148 * 256;      // (the previous frame's record count is only known on the device: keep a grid that copes with a busy frame)
+    const size_t work = std::max(std::max(pairs, (size_t)kSchedBins), floor_work);
     const unsigned blocks = (unsigned)((work + 255) / 256 < 592 ? (work + 255) / 256 : 592);
-    frame_clear_kernel<<<blocks ? blocks : 1, 256, 0, s>>>(d_counters, d_hist, zbuf_words ? reinterpret_cast<ulonglong2*>(d_zbuf) : nullptr, pairs);
+    frame_clear_kernel<<<blocks ? blocks : 1, 256, 0, s>>>(d_counters, d_hist, zbuf_words ? reinterpret_cast<ulonglong2*>(d_zbuf) : nullptr, pairs, d_queue);
 }
 
 void launch_mesh_raster(const MeshDevice& mesh, const FrameParams& P, int rows_owned, unsigned long long* d_zbuf, cudaStream_t s, bool clear) {
@@ -402,60 +427,83 @@ __device__ __forceinline__ void init_one_ray(const FrameParams& P, const DeviceM
         return;
     }
     const uint32_t slot = atomicAdd(&counters[0], 1u);
-    if (out.band_counts) {      // one atomic per band present among the lanes that got here together
-        const uint32_t band = (uint32_t)(y / out.band_rows);
-        const uint32_t peers = __match_any_sync(__activemask(), band);
-        if ((uint32_t)(__ffs((int)peers) - 1) == (threadIdx.x & 31u)) atomicAdd(out.band_counts + band, (uint32_t)__popc(peers));
-    }
     queue[(size_t)slot * kRayRecordFloat4s + 0] = make_float4(r.dir.x, r.dir.y, r.dir.z, t);
     const bool carries_surface = L.w == 0.f && t_surface != 0.0f && surf[3] > 0.f;
     if (carries_surface && surf_list) surf_list[atomicAdd(&counters[7], 1u)] = slot;
-    queue[(size_t)slot * kRayRecordFloat4s + 1] = make_float4(t_start, t_surface, __uint_as_float(idx | (L.w > 0.f ? kLensRayFlag : 0u) | (carries_surface ? kSurfRayFlag : 0u)), r.t_limit);
+    float* q1 = reinterpret_cast<float*>(queue + (size_t)slot * kRayRecordFloat4s + 1);
+    q1[0] = t_start; q1[1] = t_surface; q1[3] = r.t_limit;
     queue[(size_t)slot * kRayRecordFloat4s + 2] = make_float4(surf[0], surf[1], surf[2], surf[3]);
     if (L.w > 0.f) {
         out.lens[(size_t)idx * 2] = make_float4(L.n.x, L.n.y, L.n.z, L.t);
         out.lens[(size_t)idx * 2 + 1] = make_float4(L.w, 0.f, 0.f, 0.f);
     }
+    // the ready word last, with release semantics: whoever reads it (acquire) also sees the rest of the record and the lens entry
+    const uint32_t ready = idx | (L.w > 0.f ? kLensRayFlag : 0u) | (carries_surface ? kSurfRayFlag : 0u);
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(q1 + 2), "r"(ready) : "memory");
 }
+
+// A pixel that can only be background (outside both screen rectangles): the finished pixel of an empty ray
+__device__ __forceinline__ void background_pixel(const FrameParams& P, const FrameOut& out, uint32_t idx) {
+    if (P.bg_filled_elsewhere) {
+        // the constant background of these pixels is written into the shared image by its owner (fill_background_kernel): only
+        // pixels inside the rectangles cross NVLink.  The local accumulator still gets its value (zero stays zero under accumulation).
+        out.accum[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (out.frame) out.frame[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (out.depth) out.depth[idx] = 1e10f;
+        if (out.n_samples) out.n_samples[idx] = 0u;
+    } else {
+        finish_pixel(P, out, idx, 0.f, 0.f, 0.f, 0.f, 0.f, 0u);
+    }
+}
+
+// The set-up kernel only covers the TILE BOX: the 16 x 8 pixel tiles [tile_x0, tile_x0 + gridDim.x) x [tile_y0, ...) of local
+// (owned) rows that the union of the two screen rectangles touches.  Everything else is background, written by background_kernel.
+struct TileBox { int x0, y0, nx, ny; };     // in tiles; nx == 0: no rectangle in view, no set-up kernel at all
 
 // 16 x 8 pixel CTA, each warp an 8 x 4 tile so queue neighbours are screen neighbours.  A pixel outside both the screen
 // rectangle of the box around the occupied cells (FrameParams::occ_px, projected on the host) and the mesh's screen rectangle
-// can only be background: integer compares, one store pair, no ray arithmetic - most of a frame in render.py's framing.
-__global__ void __launch_bounds__(128) init_rays_kernel(FrameParams P, DeviceModel M, MeshDevice mesh, const unsigned long long* __restrict__ zbuf, int rows_owned,
-                                                        float4* __restrict__ queue, uint32_t* __restrict__ counters, FrameOut out, uint32_t* __restrict__ surf_list, uint32_t prefetch_lines, uint2 block_rot) {
+// can only be background: integer compares, one store pair, no ray arithmetic.
+__device__ __forceinline__ void init_rays_body(const FrameParams& P, const DeviceModel& M, const MeshDevice& mesh, const unsigned long long* __restrict__ zbuf, int rows_owned,
+                                               float4* __restrict__ queue, uint32_t* __restrict__ counters, const FrameOut& out, uint32_t* __restrict__ surf_list, TileBox box, uint2 block_rot) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // The hash table (23 MiB at log2T 19) is about to be gathered from at random by the march kernel.  When it may have left
-    // the L2 since the last frame, a 4-byte gather costs a DRAM round trip per level; the first CTAs of this kernel (background
-    // rows, nothing else to do) ask for it line by line instead, sequentially, while the first-hit walks keep the SMs busy.
-    if (prefetch_lines) {
-        const uint32_t g = (blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
-        if (g < prefetch_lines) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(M.grid) + (size_t)g * 128u));
-    }
-    // CTAs are handed out in index order; the ones over the screen rectangles carry the kernel's long dependent chains (first-hit
-    // walks), so the index space is rotated to start there: those chains begin at time zero and the cheap background CTAs fill in
-    // behind them, instead of the walks starting only when the scheduler reaches the middle of the picture.
-    const int bx = (int)((blockIdx.x + block_rot.x) % gridDim.x), by = (int)((blockIdx.y + block_rot.y) % gridDim.y);
+    // CTAs are handed out in index order; the ones over the occupied cells carry the kernel's long dependent chains (first-hit
+    // walks), so the index space is rotated to start there: those chains begin at time zero.
+    const int bx = (int)((blockIdx.x + block_rot.x) % gridDim.x) + box.x0, by = (int)((blockIdx.y + block_rot.y) % gridDim.y) + box.y0;
     const int x = bx * 16 + (warp & 1) * 8 + (lane & 7);
     const int ly = by * 8 + (warp >> 1) * 4 + (lane >> 3);
     if (x >= P.width || ly >= rows_owned) return;
     const int y = shard_row(P, ly), ms = P.mesh_scale;
     const bool in_occ = x >= P.occ_px[0] && x < P.occ_px[2] && y >= P.occ_px[1] && y < P.occ_px[3];
     const bool in_mesh = ms > 0 && P.zb_w > 0 && x * ms >= P.zb_x0 && x * ms < P.zb_x0 + P.zb_w && y * ms >= P.zb_y0 && y * ms < P.zb_y0 + P.zb_h;
-    if (!in_occ && !in_mesh) {
-        const uint32_t idx = (uint32_t)x + (uint32_t)P.width * (uint32_t)y;
-        if (P.bg_filled_elsewhere) {
-            // the constant background of these pixels is written into the shared image by its owner (fill_background_kernel): only
-            // pixels inside the rectangles cross NVLink.  The local accumulator still gets its value (zero stays zero under accumulation).
-            out.accum[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (out.frame) out.frame[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (out.depth) out.depth[idx] = 1e10f;
-            if (out.n_samples) out.n_samples[idx] = 0u;
-        } else {
-            finish_pixel(P, out, idx, 0.f, 0.f, 0.f, 0.f, 0.f, 0u);
-        }
-        return;
-    }
+    if (!in_occ && !in_mesh) { background_pixel(P, out, (uint32_t)x + (uint32_t)P.width * (uint32_t)y); return; }
     init_one_ray(P, M, mesh, zbuf, queue, counters, out, x, y, surf_list);
+}
+__global__ void __launch_bounds__(128) init_rays_kernel(FrameParams P, DeviceModel M, MeshDevice mesh, const unsigned long long* __restrict__ zbuf, int rows_owned,
+                                                        float4* __restrict__ queue, uint32_t* __restrict__ counters, FrameOut out, uint32_t* __restrict__ surf_list, TileBox box, uint2 block_rot) {
+    // Overlapped frames: the march kernel behind this one is launched with programmatic stream serialisation - it may start as
+    // soon as every CTA of this grid has got here (i.e. is resident or done; the tile box is at most a few waves), and then
+    // consumes the queue while the first-hit walks are still running.  Harmless when the next kernel is an ordinary launch.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    init_rays_body(P, M, mesh, zbuf, rows_owned, queue, counters, out, surf_list, box, block_rot);
+    // this CTA's records are complete: count it (the march kernel compares the count with the grid size to learn that the queue is final)
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence(); atomicAdd(&counters[kCntInitDone], 1u); }
+}
+
+// Every owned pixel OUTSIDE the tile box: constant background (one store pair per pixel, bandwidth-bound), by a grid sized to the
+// machine instead of thousands of tiny CTAs in front of the march kernel.  Its first threads also ask for the hash table line
+// by line (prefetch.global.L2): the march kernel is about to gather from it at random, and when it has left the L2 since the
+// last frame a 4-byte gather would cost a DRAM round trip per level.
+__global__ void __launch_bounds__(256) background_kernel(FrameParams P, FrameOut out, int rows_owned, TileBox box, const char* __restrict__ prefetch_base, uint32_t prefetch_lines) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, n_threads = gridDim.x * blockDim.x;
+    for (uint32_t g = tid; g < prefetch_lines; g += n_threads) asm volatile("prefetch.global.L2 [%0];" ::"l"(prefetch_base + (size_t)g * 128u));
+    const int bx0 = box.x0 * 16, bx1 = (box.x0 + box.nx) * 16, by0 = box.y0 * 8, by1 = (box.y0 + box.ny) * 8;
+    const uint32_t W = (uint32_t)P.width, n = W * (uint32_t)rows_owned;
+    for (uint32_t i = tid; i < n; i += n_threads) {
+        const int ly = (int)(i / W), x = (int)(i - (uint32_t)ly * W);
+        if (box.nx > 0 && x >= bx0 && x < bx1 && ly >= by0 && ly < by1) continue;
+        background_pixel(P, out, (uint32_t)x + W * (uint32_t)shard_row(P, ly));
+    }
 }
 
 // Shared frame target, destination rank: the constant background of every pixel outside both screen rectangles (the same
@@ -472,16 +520,6 @@ void launch_fill_background(const FrameParams& P, void* d_image, cudaStream_t s)
     dim3 grid((P.width + 255) / 256, P.height);
     fill_background_kernel<<<grid, 256, 0, s>>>(P, d_image);
 }
-
-// dst[0] = src[0] (and dst2[0] = src[0] when given) on the stream, without involving a copy engine: a DMA engine busy with a
-// large device->host transfer would make a tiny cudaMemcpyAsync - and everything behind it on its stream - wait
-__global__ void latch_word_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, uint32_t* __restrict__ dst2) {
-    const uint32_t v = *src;
-    *dst = v;
-    if (dst2) *dst2 = v;
-}
-void launch_latch_word(const uint32_t* d_src, uint32_t* d_dst, uint32_t* d_dst2, cudaStream_t s) { latch_word_kernel<<<1, 1, 0, s>>>(d_src, d_dst, d_dst2); }
-
 // ---- tile-sharded frames written straight into one rank's image (nmr_gather_*): sequence flags in that rank's memory ----
 // flags[r] (r < 32) = last frame rank r has finished writing; flags[kGatherConsumed] = last frame the destination is done with;
 // flags[kGatherError] != 0 after a wait that ran out of time.  Stores of a rank's render kernels precede its signal kernel in
@@ -510,28 +548,56 @@ void launch_gather_wait(uint32_t* d_flags, int first, int count, uint32_t seq, u
     if (count > 0) gather_wait_kernel<<<1, 32, 0, s>>>(d_flags, first, count, seq, d_err, timeout_ns);
 }
 
-void launch_init_rays(const FrameParams& P, const DeviceModel& M, const MeshDevice& mesh, const unsigned long long* d_zbuf, int rows_owned,
-                      float4* d_queue, uint32_t* d_counters, const FrameOut& out, int num_sms, cudaStream_t s, bool reset_counters, uint32_t* d_surf_list, int first_pass) {
-    if (reset_counters) cudaMemsetAsync(d_counters, 0, sizeof(uint32_t) * kNumCounters, s);
-    (void)num_sms;
-    if (rows_owned <= 0) return;
-    dim3 grid((P.width + 15) / 16, (rows_owned + 7) / 8);
-    // tables that fit the L2 comfortably are prefetched by the frame's first set-up pass (see the kernel); NMR_NO_PREFETCH=1 for A/B runs
+// owned rows of this context with image row < y (rows are dealt to ranks in bands, kernels.cu: shard_row)
+static int local_rows_below(const FrameParams& P, int y) {
+    if (y <= 0) return 0;
+    if (P.shard_world <= 1) return std::max(0, y - P.row0);
+    const int cycle = P.shard_world * P.shard_band, full = y / cycle, rem = y % cycle;
+    return full * P.shard_band + std::min(std::max(rem - P.shard_rank * P.shard_band, 0), P.shard_band);
+}
+
+int launch_init_rays(const FrameParams& P, const DeviceModel& M, const MeshDevice& mesh, const unsigned long long* d_zbuf, int rows_owned,
+                     float4* d_queue, uint32_t* d_counters, const FrameOut& out, int num_sms, cudaStream_t s, bool reset_counters, uint32_t* d_surf_list, int first_pass) {
+    if (reset_counters) cudaMemsetAsync(d_counters, 0, sizeof(uint32_t) * kFrameCounters, s);
+    if (rows_owned <= 0) return 0;
+    // union of the two screen rectangles in pixels (image rows), then in 16 x 8 tiles of local rows
+    int x0 = P.width, y0 = P.height, x1 = 0, y1 = 0;
+    const bool have_occ = P.occ_px[2] > P.occ_px[0] && P.occ_px[3] > P.occ_px[1];
+    if (have_occ) { x0 = std::min(x0, P.occ_px[0]); y0 = std::min(y0, P.occ_px[1]); x1 = std::max(x1, P.occ_px[2]); y1 = std::max(y1, P.occ_px[3]); }
+    if (P.mesh_scale > 0 && P.zb_w > 0 && P.zb_h > 0) {
+        const int ms = P.mesh_scale;
+        x0 = std::min(x0, P.zb_x0 / ms); y0 = std::min(y0, P.zb_y0 / ms);
+        x1 = std::max(x1, (P.zb_x0 + P.zb_w + ms - 1) / ms); y1 = std::max(y1, (P.zb_y0 + P.zb_h + ms - 1) / ms);
+    }
+    TileBox box{0, 0, 0, 0};
+    uint2 rot = make_uint2(0u, 0u);
+    if (x1 > x0 && y1 > y0) {
+        const int ly0 = local_rows_below(P, y0), ly1 = std::min(rows_owned, local_rows_below(P, y1));
+        x0 = std::max(0, x0); x1 = std::min(P.width, x1);
+        if (ly1 > ly0 && x1 > x0) {
+            box.x0 = x0 / 16; box.y0 = ly0 / 8; box.nx = (x1 + 15) / 16 - box.x0; box.ny = (ly1 + 7) / 8 - box.y0;
+            // first CTA column / row over the occupied cells; NMR_NO_BLOCK_ROTATION=1 for A/B runs
+            static const bool no_rot = std::getenv("NMR_NO_BLOCK_ROTATION") != nullptr;
+            if (!no_rot && have_occ) {
+                const int rx = std::max(x0, P.occ_px[0]) / 16 - box.x0, ry = local_rows_below(P, std::max(y0, P.occ_px[1])) / 8 - box.y0;
+                if (rx >= 0 && rx < box.nx && ry >= 0 && ry < box.ny) rot = make_uint2((unsigned)rx, (unsigned)ry);
+            }
+        }
+    }
+    // tables that fit the L2 comfortably are prefetched by the frame's first set-up pass; NMR_NO_PREFETCH=1 for A/B runs
     static const bool no_prefetch = std::getenv("NMR_NO_PREFETCH") != nullptr;
     const size_t table_bytes = ((size_t)M.level_offset[N_LEVELS - 1] + M.level_size[N_LEVELS - 1]) * sizeof(__half2);
     const bool first = first_pass < 0 ? reset_counters : first_pass != 0;     // the frame's first set-up pass
     const uint32_t prefetch_lines = (first && !no_prefetch && table_bytes <= ((size_t)48 << 20)) ? (uint32_t)(table_bytes / 128) : 0u;
-    // first CTA row / column over the screen rectangles (unsharded passes: local row = image row - row0); NMR_NO_BLOCK_ROTATION=1 for A/B runs
-    uint2 rot = make_uint2(0u, 0u);
-    static const bool no_rot = std::getenv("NMR_NO_BLOCK_ROTATION") != nullptr;
-    if (!no_rot && P.shard_world <= 1) {
-        int x0 = P.width, y0 = P.height;
-        if (P.occ_px[2] > P.occ_px[0] && P.occ_px[3] > P.occ_px[1]) { x0 = std::min(x0, P.occ_px[0]); y0 = std::min(y0, P.occ_px[1]); }
-        if (P.mesh_scale > 0 && P.zb_w > 0 && P.zb_h > 0) { x0 = std::min(x0, P.zb_x0 / P.mesh_scale); y0 = std::min(y0, P.zb_y0 / P.mesh_scale); }
-        const int ly0 = y0 - P.row0;
-        if (x0 < P.width && ly0 >= 0 && ly0 < rows_owned) rot = make_uint2((unsigned)(x0 / 16) % grid.x, (unsigned)(ly0 / 8) % grid.y);
-    }
-    init_rays_kernel<<<grid, 128, 0, s>>>(P, M, mesh, d_zbuf, rows_owned, d_queue, d_counters, out, d_surf_list, prefetch_lines, rot);
+    background_kernel<<<num_sms * 4, 256, 0, s>>>(P, out, rows_owned, box, reinterpret_cast<const char*>(M.grid), prefetch_lines);
+    if (box.nx <= 0) return 0;
+    // NMR_INIT_SMEM_KB (tuning aid): unused dynamic shared memory that caps how many CTAs of the set-up kernel share an SM, so that
+    // CTAs of an overlapped march kernel find registers next to them
+    static const int pad_kb = [] { const char* v = std::getenv("NMR_INIT_SMEM_KB"); return v ? std::atoi(v) : 0; }();
+    static bool pad_attr = false;
+    if (pad_kb > 48 && !pad_attr) { cudaFuncSetAttribute(init_rays_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pad_kb * 1024); pad_attr = true; }
+    init_rays_kernel<<<dim3((unsigned)box.nx, (unsigned)box.ny), 128, (size_t)pad_kb * 1024, s>>>(P, M, mesh, d_zbuf, rows_owned, d_queue, d_counters, out, d_surf_list, box, rot);
+    return box.nx * box.ny;
 }
 
 // =================================================================================================================
@@ -610,6 +676,7 @@ struct __align__(128) MarchSmem {   // CUDA-core path, one 128-thread group per 
     __half w[kWTotal];            // plain row-major weights
     __half act[kTile * 64];       // row-major, 64 halves per thread
     __half act2[kTile * 64];
+    unsigned long long t_begin;   // globaltimer at the CTA's start (deadline of an overlapped frame's waits)
 };
 struct __align__(128) MarchSmemTC {
     __half w[kWTotal];                    // 20480 B, canonical K-major core-matrix layout, shared by the warpgroups
@@ -617,6 +684,7 @@ struct __align__(128) MarchSmemTC {
     uint64_t mbar[kGroupsTC];
     uint64_t wbar;                        // completion of the bulk copy that brings the weights in
     uint32_t tmem_base;
+    unsigned long long t_begin;           // globaltimer at the CTA's start (deadline of an overlapped frame's waits)
 };
 
 // ---- warpgroup-scoped barriers (named barriers 1..kGroupsTC, 128 threads each) -----------------------------------
@@ -845,17 +913,27 @@ constexpr int kWalkBudget = 6;      // empty voxels a ray may skip per tile iter
 #endif
 // PASS2: the surface-ray pass of SchedArgs (variable batch sizes from the schedule); the main instantiation keeps the batch
 // size a compile-time 8
-template <bool TC, bool PASS2>
+template <bool TC, bool PASS2, bool OVERLAP = false>
 __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH_CTAS : 2) march_kernel(FrameParams P, DeviceModel M, const float4* __restrict__ queue,
-                                                                                          uint32_t* __restrict__ counters, FrameOut out, uint32_t n_pixels, uint32_t debug_flags, const uint32_t* __restrict__ range_end, uint32_t* __restrict__ cursor, SchedArgs sched) {
+                                                                                          uint32_t* __restrict__ counters, FrameOut out, uint32_t n_pixels, uint32_t debug_flags, const uint32_t* __restrict__ range_end, uint32_t* __restrict__ cursor, SchedArgs sched, int overlap_init_ctas) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     using Smem = typename std::conditional<TC, MarchSmemTC, MarchSmem>::type;
     Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+    // OVERLAPPED frame (overlap_init_ctas >= 0): this grid was launched with programmatic stream serialisation behind the set-up
+    // kernel and runs next to it.  It never waits for that grid as a whole (no griddepcontrol.wait): every queue record carries a
+    // ready word (kernels.cuh: kEmptyRecord) and counters[kCntInitDone] says when the queue is final.
+    constexpr bool overlap = OVERLAP && !PASS2;       // (a compile-time variant: the serial kernel carries none of the extra state)
+    if (threadIdx.x == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        atomicMin(reinterpret_cast<unsigned long long*>(counters + kCntMarchStart), now);
+        if (overlap) S.t_begin = now;          // (read only behind the tile barriers further down)
+    }
 
     // this launch consumes the queue records [*cursor at launch, *range_end): the whole queue of a frame (range_end =
     // &counters[0], cursor = &counters[1]) or one band of it (nmr_render's copy-overlapped bands); the surface rule always
     // looks at the whole frame's live-ray count
-    const uint32_t n_rays = counters[0], n_end = *range_end;
+    const uint32_t n_rays = overlap ? 0u : counters[0], n_end = overlap ? 0u : *range_end;
     // mesh surface insertion rule (SurfaceMode): the reference's 8-sample batches while <= 1/8 of the pixels are live
     const bool batch8 = P.surface_mode == kSurfaceBatch8 || (P.surface_mode == kSurfaceAuto && (unsigned long long)n_rays * 8ull <= (unsigned long long)n_pixels);
     // more than 1/8 live pixels under the auto rule: the reference's batch size varies per wavefront iteration (SchedArgs)
@@ -913,6 +991,8 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH
 
     // per-ray state, identical in the 8 lanes of a group
     bool active = false, exhausted = false, pending_finish = false;
+    bool waiting = false;        // overlapped frames: this group holds a queue slot whose record has not been written yet
+    uint32_t my_slot = kEmptyRecord;
     V3 origin = cam_origin;      // primary rays start at the eye; the reflected segment of a lens ray starts on the lens
     uint32_t phase = 0;          // 0 ordinary ray; lens ray: 1 in front of the lens, 2 reflected segment, 3 behind the lens
     uint32_t kb = 0;             // surface-ray pass: schedule batch index of the ray's current batch
@@ -1005,11 +1085,32 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH
             if (!active) {
                 if (exhausted) break;
                 uint32_t slot = 0;
-                if (sub == 0) slot = atomicAdd(cursor, 1u);
-                slot = __shfl_sync(gmask, slot, gbase);
-                if (slot >= n_end) { exhausted = true; break; }
+                if (!overlap || my_slot == kEmptyRecord) {
+                    if (sub == 0) slot = atomicAdd(cursor, 1u);
+                    slot = __shfl_sync(gmask, slot, gbase);
+                    if (overlap) my_slot = slot;
+                } else {
+                    slot = my_slot;
+                }
+                if (overlap) {
+                    waiting = false;
+                    // the record is there when its ready word is; when it is not and the set-up kernel has finished, re-read once (a
+                    // record committed before the last CTA signed off is visible by now): still empty = beyond the end of the queue
+                    const uint32_t* rw = reinterpret_cast<const uint32_t*>(queue + (size_t)slot * kRayRecordFloat4s + 1) + 2;
+                    uint32_t w;
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(w) : "l"(rw) : "memory");
+                    if (w == kEmptyRecord) {
+                        uint32_t done;
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(done) : "l"(counters + kCntInitDone) : "memory");
+                        const bool fin = done >= (uint32_t)overlap_init_ctas;
+                        if (fin) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(w) : "l"(rw) : "memory");
+                        if (w == kEmptyRecord) { exhausted = fin; waiting = !fin; break; }
+                    }
+                } else if (slot >= n_end) { exhausted = true; break; }
+                if (overlap) my_slot = kEmptyRecord;
                 if (pass2) slot = __ldg(sched.surf_list + slot);
-                const float4 q0 = __ldg(queue + (size_t)slot * kRayRecordFloat4s), q1 = __ldg(queue + (size_t)slot * kRayRecordFloat4s + 1), q2 = __ldg(queue + (size_t)slot * kRayRecordFloat4s + 2);
+                // (L2 loads: the records may have been written while this kernel was running)
+                const float4 q0 = __ldcg(queue + (size_t)slot * kRayRecordFloat4s), q1 = __ldcg(queue + (size_t)slot * kRayRecordFloat4s + 1), q2 = __ldcg(queue + (size_t)slot * kRayRecordFloat4s + 2);
                 dir = v3(q0.x, q0.y, q0.z); t = q0.w; t_start = q1.x; t_surface = q1.y; idx = __float_as_uint(q1.z); t_limit = q1.w;
                 sr = q2.x; sg = q2.y; sb = q2.z; sw = q2.w;
                 cr = cg = cb = ca = 0.f; max_weight = 0.f; depth = 0.f; n_samples = 0;
@@ -1111,9 +1212,16 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH
         // rays are all in the middle of a paused empty-space walk has no sample this iteration but must keep going)
         const bool any_have = TC ? group_any(tc.bar_id, have) : (__syncthreads_or(have ? 1 : 0) != 0);
         if (!any_have) {
-            const bool any_active = TC ? group_any(tc.bar_id, active) : (__syncthreads_or(active ? 1 : 0) != 0);
+            const bool any_active = TC ? group_any(tc.bar_id, active || (overlap && waiting)) : (__syncthreads_or((active || (overlap && waiting)) ? 1 : 0) != 0);
             if (!any_active) break;
             if (active && !pending_finish) t = t_batch_end;
+            if (overlap && waiting) {                      // nothing to do in this tile until the set-up kernel queues more rays
+                __nanosleep(200);
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                // never hang the GPU on a producer that does not deliver (2 s: a frame takes milliseconds): give the slot up
+                if (now - S.t_begin > 2000000000ull) { waiting = false; exhausted = true; }
+            }
             continue;
         }
 
@@ -1179,15 +1287,38 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH
     for (int o = 16; o > 0; o >>= 1) evaluated += __shfl_xor_sync(0xffffffffu, evaluated, o);
     if (lane == 0 && evaluated) atomicAdd(reinterpret_cast<unsigned long long*>(counters + 2), (unsigned long long)evaluated);
     if (sub == 0 && n_batches) { atomicAdd(&counters[4], n_batches); atomicAdd(&counters[5], n_passes); }
+    if (threadIdx.x == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        atomicMax(reinterpret_cast<unsigned long long*>(counters + kCntMarchEnd), now);
+        // how many records this frame queued, for the next frame's clear kernel (every CTA stores the same final value; the
+        // set-up kernel has finished by the time a CTA gets here)
+        if (!PASS2) counters[kCntPrevCount] = overlap ? *reinterpret_cast<volatile uint32_t*>(counters) : max(n_rays, n_end);
+    }
     if (TC) tc_teardown(reinterpret_cast<MarchSmemTC&>(S));
 }
 
 constexpr size_t kSchedSmem = (kSchedMax + 2) * sizeof(uint16_t) + 16;   // schedule boundaries + their count behind the surface-ray pass's tile memory
 constexpr int kMarchCtasPerSm = NMR_MARCH_CTAS;   // __launch_bounds__(256, 3): 24 warps, 3 x 128 tensor-memory columns, 3 x 53 KB shared memory per SM
 
+namespace {
+// <<<>>> or, for an overlapped frame, cudaLaunchKernelEx with programmatic stream serialisation (the kernel may start while the
+// set-up kernel in front of it is still running)
+template <typename K, typename... Args>
+void launch_march_variant(K kernel, unsigned grid, unsigned block, size_t smem, cudaStream_t s, bool programmatic, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = programmatic ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+}  // namespace
+
 void launch_march(const FrameParams& P, const DeviceModel& M, const float4* d_queue, uint32_t* d_counters, const FrameOut& out,
                   uint32_t n_pixels, uint32_t debug_flags, int num_sms, cudaStream_t s, const uint32_t* d_range_end, uint32_t* d_cursor,
-                  const SchedArgs* sched, int ctas_per_sm) {
+                  const SchedArgs* sched, int ctas_per_sm, int overlap_init_ctas) {
     if (!d_range_end) d_range_end = d_counters;
     if (!d_cursor) d_cursor = d_counters + 1;
     SchedArgs sa{};
@@ -1198,15 +1329,16 @@ void launch_march(const FrameParams& P, const DeviceModel& M, const float4* d_qu
         int dev = 0; cudaGetDevice(&dev);
         bool& attr_set = attr_set_dev[dev & 63];
         if (!attr_set) { cudaFuncSetAttribute(march_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmem)); cudaFuncSetAttribute(march_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(MarchSmem) + kSchedSmem)); attr_set = true; }
-        if (sa.pass == 2) march_kernel<false, true><<<num_sms, kTile, sizeof(MarchSmem) + kSchedSmem, s>>>(P, M, d_queue, d_counters, out, n_pixels, debug_flags, d_range_end, d_cursor, sa);
-        else march_kernel<false, false><<<num_sms * 2, kTile, sizeof(MarchSmem), s>>>(P, M, d_queue, d_counters, out, n_pixels, debug_flags, d_range_end, d_cursor, sa);
+        if (sa.pass == 2) launch_march_variant(march_kernel<false, true>, num_sms, kTile, sizeof(MarchSmem) + kSchedSmem, s, false, P, M, d_queue, d_counters, out, n_pixels, debug_flags, d_range_end, d_cursor, sa, -1);
+        else launch_march_variant(march_kernel<false, false>, num_sms * 2, kTile, sizeof(MarchSmem), s, false, P, M, d_queue, d_counters, out, n_pixels, debug_flags, d_range_end, d_cursor, sa, -1);
     } else {
         static bool attr_set_dev[64] = {};
         int dev = 0; cudaGetDevice(&dev);
         bool& attr_set = attr_set_dev[dev & 63];
-        if (!attr_set) { cudaFuncSetAttribute(march_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmemTC)); cudaFuncSetAttribute(march_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(MarchSmemTC) + kSchedSmem)); attr_set = true; }
-        if (sa.pass == 2) march_kernel<true, true><<<num_sms * per_sm, kTile * kGroupsTC, sizeof(MarchSmemTC) + kSchedSmem, s>>>(P, M, d_queue, d_counters, out, n_pixels, debug_flags, d_range_end, d_cursor, sa);
-        else march_kernel<true, false><<<num_sms * per_sm, kTile * kGroupsTC, sizeof(MarchSmemTC), s>>>(P, M, d_queue, d_counters, out, n_pixels, debug_flags, d_range_end, d_cursor, sa);
+        if (!attr_set) { cudaFuncSetAttribute(march_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmemTC)); cudaFuncSetAttribute(march_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmemTC)); cudaFuncSetAttribute(march_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(MarchSmemTC) + kSchedSmem)); attr_set = true; }
+        if (sa.pass == 2) launch_march_variant(march_kernel<true, true>, num_sms * per_sm, kTile * kGroupsTC, sizeof(MarchSmemTC) + kSchedSmem, s, false, P, M, d_queue, d_counters, out, n_pixels, debug_flags, d_range_end, d_cursor, sa, -1);
+        else if (overlap_init_ctas >= 0) launch_march_variant(march_kernel<true, false, true>, num_sms * per_sm, kTile * kGroupsTC, sizeof(MarchSmemTC), s, true, P, M, d_queue, d_counters, out, n_pixels, debug_flags, d_range_end, d_cursor, sa, overlap_init_ctas);
+        else launch_march_variant(march_kernel<true, false>, num_sms * per_sm, kTile * kGroupsTC, sizeof(MarchSmemTC), s, false, P, M, d_queue, d_counters, out, n_pixels, debug_flags, d_range_end, d_cursor, sa, -1);
     }
 }
 
@@ -1253,7 +1385,8 @@ void launch_l2_probe(const void* d_buf, uint32_t n_vec, uint32_t loads_per_threa
 __global__ void debug_encode_kernel(DeviceModel M, const float* __restrict__ pos, int64_t n, uint16_t* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    encode_chunks<2>(M, v3(pos[i * 3], pos[i * 3 + 1], pos[i * 3 + 2]), reinterpret_cast<char*>(out + i * ENC_WIDTH), 16);
+    // the march kernel's own path (bricked coarse levels when the model has them; nmr_debug_set_flags bit 4 hides them for A/B checks)
+    encode_levels_strided(M, v3(pos[i * 3], pos[i * 3 + 1], pos[i * 3 + 2]), reinterpret_cast<char*>(out + i * ENC_WIDTH), 16, 0u, 1u);
 }
 void launch_debug_encode(const DeviceModel& M, const float* d_pos, int64_t n, uint16_t* d_out, cudaStream_t s) {
     if (n <= 0) return;
@@ -1287,7 +1420,7 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile) debug_network_
         const bool have = i < n;
         V3 d01 = v3(0.5f, 0.5f, 0.5f);
         if (have) {
-            encode_chunks<2>(M, v3(pos[i * 3], pos[i * 3 + 1], pos[i * 3 + 2]), a_row, enc_stride);
+            encode_levels_strided(M, v3(pos[i * 3], pos[i * 3 + 1], pos[i * 3 + 2]), a_row, enc_stride, 0u, 1u);
             d01 = v3(dir[i * 3], dir[i * 3 + 1], dir[i * 3 + 2]);
         }
         float raw[4];
@@ -1351,7 +1484,7 @@ __global__ void __launch_bounds__(kTile * kGroupsTC) probe_kernel(FrameParams P,
                 }
             }
             if (!group_any(tc.bar_id, have)) continue;
-            if (have) encode_chunks<kEncodeUnroll>(M, wpos, a_row, 2048);
+            if (have) encode_levels_strided(M, wpos, a_row, 2048, 0u, 1u);
             float raw[4];
             network_tc(a_row, tc, dir01, raw);
             if (have) {

@@ -16,8 +16,6 @@ struct FrameOut {
     uint32_t* n_samples;  // network evaluations per ray, W*H or null
     float4* lens;         // lens hand-off per pixel, 2 x W*H: (normal.xyz, t_lens) (coverage, -, -, -); null when the frame has no lens
     float* lens_scratch;  // per ray group of the march kernel: state parked across the segments of a lens ray (kLensStash floats each)
-    uint32_t* band_counts; // rays queued per band of `band_rows` image rows (nmr_render's row prediction), or null
-    int band_rows;
     // measurement aid (NMR_PHASE_LOG): per warpgroup of the march kernel and tile iteration, clock64 at the iteration's start, after
     // batch generation, after the encoding, after the network, after compositing: [n_warpgroups][kPhaseIters][5]; null normally
     unsigned long long* phase_log;
@@ -38,15 +36,25 @@ constexpr int kLensStash = 24;
 
 // device counters of one render: [0] rays queued by the init kernel, [1] queue cursor of the march kernel,
 // [2..3] total network evaluations (64-bit), [4] ray batches, [5] batch generation passes, [6] cursor of the surface-ray pass,
-// [7] rays that carry a mesh surface (length of the surface list)
-constexpr int kNumCounters = 8;
-constexpr int kRayRecordFloat4s = 3;   // queue record: (dir.xyz, t) (t_start, t_surface, idx, -) (surface rgba)
+// [7] rays that carry a mesh surface (length of the surface list), [8] CTAs of the set-up kernel that have finished (the march
+// kernel of an overlapped frame learns from it that the queue is complete).  These nine are zeroed at the head of a frame.
+// [9] queue records the PREVIOUS frame wrote (its march kernel stores it; the next frame's clear kernel resets their ready words),
+// [10..11] / [12..13] globaltimer of the first march CTA's start / the last one's end (64-bit min / max) of this frame.
+constexpr int kNumCounters = 16, kFrameCounters = 9;
+constexpr int kCntInitDone = 8, kCntPrevCount = 9, kCntMarchStart = 10, kCntMarchEnd = 12;
+constexpr int kRayRecordFloat4s = 3;   // queue record: (dir.xyz, t) (t_start, t_surface, idx, t_limit) (surface rgba)
+// The idx word of a record is its READY word: the set-up kernel stores it last, with release semantics, and the march kernel
+// reads it first, with acquire semantics - so the march kernel can consume the queue while the set-up kernel is still appending to
+// it (overlapped frames).  Records that are not (yet) written hold kEmptyRecord there: the queue is filled with it when it is
+// allocated, and every frame's clear kernel resets the records of the frame before.
+constexpr uint32_t kEmptyRecord = 0xFFFFFFFFu;
 
 enum DebugFlags : uint32_t {
     kDebugScalarMlp = 1u,     // run the CUDA-core MLP instead of tcgen05 (NMR_MLP=scalar)
     kDebugSwapLboSbo = 2u,    // swap the UMMA descriptor offsets (bring-up aid)
     kDebugKeepProbes = 4u,
-    kDebugNoSharedEncode = 8u, // every lane encodes its own sample even when the warp holds few (A/B of the shared encoding)    // also write the linear frame, depth and per-ray sample counts (nmr_debug_last_frame)
+    kDebugNoSharedEncode = 8u, // every lane encodes its own sample even when the warp holds few (A/B of the shared encoding)
+    kDebugNoBricks = 16u,      // gather every level from the plain hash-table layout (A/B of the brick layout of the coarse levels)
 };
 
 void launch_occupancy_build(const uint16_t* d_density_grid_fp16, int n_cascades_present, uint8_t* d_bitfield, float* d_scratch, cudaStream_t s);
@@ -54,13 +62,14 @@ void launch_occupancy_build(const uint16_t* d_density_grid_fp16, int n_cascades_
 void launch_occupancy_bounds(const uint8_t* d_bitfield, int* d_out48, cudaStream_t s);
 // d_occ_scratch: kCoarseRes^3 bytes; d_near_bits: kCoarseRes^2 words (DeviceModel::coarse)
 void launch_coarse_build(const uint8_t* d_bitfield, uint8_t* d_occ_scratch, uint32_t* d_near_bits, cudaStream_t s);
+// one level of the hash grid re-laid out as 2x2x2 bricks (res^3 cells x 32 bytes), see DeviceModel::brick
+void launch_brick_build(const DeviceModel& M, int level, uint32_t res, void* d_out, cudaStream_t s);
 // d_out: 10 240 halves; the MLP weights re-laid out as the tcgen05 B operands the march kernel keeps in shared memory
 void launch_weights_canonical(const uint16_t* d_mlp, uint16_t* d_out, cudaStream_t s);
 void launch_mesh_raster(const MeshDevice& mesh, const FrameParams& P, int rows_owned, unsigned long long* d_zbuf, cudaStream_t s, bool clear = true);
 // counters + (optional) schedule histogram + (optional) mesh visibility window in one launch; zbuf_window_words: words of the window (both layers)
 size_t zbuf_window_words(const MeshDevice& mesh, const FrameParams& P);
-void launch_frame_clear(uint32_t* d_counters, uint32_t* d_hist, unsigned long long* d_zbuf, size_t zbuf_words, cudaStream_t s);
-void launch_latch_word(const uint32_t* d_src, uint32_t* d_dst, uint32_t* d_dst2, cudaStream_t s);
+void launch_frame_clear(uint32_t* d_counters, uint32_t* d_hist, unsigned long long* d_zbuf, size_t zbuf_words, float4* d_queue, cudaStream_t s);
 // sequence flags of a shared frame target (nmr_gather_*): one word per rank + "consumed" + "error", behind the image
 constexpr int kGatherMaxRanks = 32, kGatherConsumed = 32, kGatherError = 33, kGatherFlagWords = 64;
 // destination rank of a shared frame target: constant background of every pixel outside both screen rectangles, all rows
@@ -69,13 +78,19 @@ void launch_fill_background(const FrameParams& P, void* d_image, cudaStream_t s)
 inline size_t pixel_bytes(int out_format) { return out_format == kPixelU8 ? 4 : (out_format == kPixelF16 ? 8 : 16); }
 void launch_gather_signal(uint32_t* d_flag, uint32_t seq, cudaStream_t s);
 void launch_gather_wait(uint32_t* d_flags, int first, int count, uint32_t seq, uint32_t* d_err, cudaStream_t s);
-void launch_init_rays(const FrameParams& P, const DeviceModel& M, const MeshDevice& mesh, const unsigned long long* d_zbuf, int rows_owned,
-                      float4* d_queue, uint32_t* d_counters, const FrameOut& out, int num_sms, cudaStream_t s, bool reset_counters = true, uint32_t* d_surf_list = nullptr, int first_pass = -1);
+// ray set-up of the owned rows: background_kernel (every pixel outside the tile box of the two screen rectangles) + init_rays_kernel
+// (the tile box).  Returns the number of CTAs of init_rays_kernel (what an overlapped march launch has to wait for; 0: not launched).
+int launch_init_rays(const FrameParams& P, const DeviceModel& M, const MeshDevice& mesh, const unsigned long long* d_zbuf, int rows_owned,
+                     float4* d_queue, uint32_t* d_counters, const FrameOut& out, int num_sms, cudaStream_t s, bool reset_counters = true, uint32_t* d_surf_list = nullptr, int first_pass = -1);
 // (first_pass: 1 / 0 = this is / is not the frame's first set-up pass, -1 = it is iff reset_counters)
 // n_pixels: pixels traced by this context in this pass (the reference's m_n_rays_initialized), for SurfaceMode auto
 void launch_march(const FrameParams& P, const DeviceModel& M, const float4* d_queue, uint32_t* d_counters, const FrameOut& out,
                   uint32_t n_pixels, uint32_t debug_flags, int num_sms, cudaStream_t s, const uint32_t* d_range_end = nullptr, uint32_t* d_cursor = nullptr,
-                  const SchedArgs* sched = nullptr, int ctas_per_sm = 0);
+                  const SchedArgs* sched = nullptr, int ctas_per_sm = 0, int overlap_init_ctas = -1);
+// (overlap_init_ctas >= 0: OVERLAPPED frame - the kernel is launched with programmatic stream serialisation right behind the
+//  set-up kernel of `overlap_init_ctas` CTAs and consumes the whole queue while that kernel is still filling it; d_range_end is
+//  ignored.  The caller has resolved the mesh-surface rule on the host: P.surface_mode is not `auto` when a mesh is in view.)
+
 // (d_range_end / d_cursor: consume only the queue records [*d_cursor, *d_range_end) - default: the whole queue)
 // density probes of the collision tool: mode 0 = NerfTracer::intersects (alpha at points), 1 = NerfTracer::collide (distance along dir)
 void launch_probe(const FrameParams& P, const DeviceModel& M, const float* d_points_world, const float dir[3], int64_t n, int mode, float* d_out,

@@ -84,6 +84,7 @@ def lib():
         "nmr_debug_parse_gltf": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64), C.c_char_p, C.c_size_t]),
         "nmr_set_shard": (C.c_int, [vp, C.c_int, C.c_int, C.c_int]),
         "nmr_set_surface_insertion": (C.c_int, [vp, C.c_int]),
+        "nmr_set_overlap": (C.c_int, [vp, C.c_int]),
         "nmr_set_lens": (C.c_int, [vp, C.c_int, C.c_float, C.c_float, fp]),
         "nmr_get_nerf_info": (C.c_int, [vp, C.c_int, C.POINTER(NerfInfo)]),
         "nmr_get_stream": (C.c_int, [vp, C.POINTER(vp)]),
@@ -126,7 +127,7 @@ EXPORTED_SYMBOLS = [
     "nmr_set_camera", "nmr_frame", "nmr_frame_async", "nmr_read_frame", "nmr_render", "nmr_render_views", "nmr_set_shard", "nmr_set_surface_insertion", "nmr_set_lens", "nmr_debug_lens", "nmr_get_nerf_info", "nmr_gather_create", "nmr_gather_attach", "nmr_gather_detach", "nmr_get_stream", "nmr_probe_points", "nmr_probe_rays", "nmr_set_tonemap_curve", "nmr_get_tonemap_curve",
     "nmr_get_device_image", "nmr_copy_device_image", "nmr_flush_l2", "nmr_get_stats", "nmr_synchronize", "nmr_host_alloc", "nmr_host_free", "nmr_get_density_bitfield",
     "nmr_set_density_bitfield", "nmr_debug_encode", "nmr_debug_network", "nmr_debug_trace", "nmr_debug_mesh",
-    "nmr_debug_last_frame", "nmr_debug_set_flags", "nmr_render_format", "nmr_render_views_format", "nmr_debug_parse_gltf", "nmr_measure_l2",
+    "nmr_debug_last_frame", "nmr_debug_set_flags", "nmr_render_format", "nmr_render_views_format", "nmr_debug_parse_gltf", "nmr_measure_l2", "nmr_set_overlap",
 ]
 
 
@@ -600,6 +601,10 @@ class NerfMeshRenderer:
     def set_surface_insertion(self, mode: int):
         """Where a partially covering mesh surface enters the compositing order (include/nmr.h: nmr_surface_mode)."""
         self._ck(lib().nmr_set_surface_insertion(self._h, int(mode)))
+
+    def set_overlap(self, enabled: bool = True):
+        """March kernel consuming the ray queue while the set-up kernel fills it (include/nmr.h: nmr_set_overlap); pixels do not change."""
+        self._ck(lib().nmr_set_overlap(self._h, int(bool(enabled))))
 
     def set_lens(self, enabled: bool = True, ior: float = -1.0, transmission: float = -1.0, tint=None):
         """Lens surfaces and their secondary rays (include/nmr.h: nmr_set_lens).  Negative / None keeps a parameter."""
