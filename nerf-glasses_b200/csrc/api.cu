@@ -64,6 +64,10 @@ struct Nerf {
     float background[4] = {1.f, 1.f, 1.f, 1.f};     // S/ngp/testbed.cuh:525
     float min_transmittance = 0.01f;                // S/ngp/testbed.cuh:484
     int tonemap_curve = 0;                          // Testbed.tonemap_curve (ETonemapCurve), Identity by default
+    // Testbed::m_model_translation / m_model_rotation (S/ngp/testbed.cuh:508-509): translation in world units, rotation as three
+    // angles in units of pi about X, Y, Z; model_rot = AngleAxis(rx pi, X) * AngleAxis(ry pi, Y) * AngleAxis(rz pi, Z), row-major
+    float model_translation[3] = {0.f, 0.f, 0.f}, model_rotation_pi[3] = {0.f, 0.f, 0.f};
+    float model_rot[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
 };
 
 struct Mesh {
@@ -87,6 +91,9 @@ struct Surfaces {
     DevBuf<uint32_t> n_samples;
     DevBuf<float4> queue;
     DevBuf<unsigned long long> zbuf;       // opaque window, then (scenes with lens surfaces) the lens window
+    DevBuf<float4> comb_frame, comb_accum; // several NeRFs in one frame: merged linear frame and its running mean
+    DevBuf<float> comb_depth;
+    bool comb_valid = false;               // comb_frame / comb_depth hold the last frame()'s merged buffers
     DevBuf<float4> lens;                   // FrameOut::lens
     DevBuf<float> lens_scratch;            // FrameOut::lens_scratch
     // the reference's n_steps schedule for close-ups (SchedArgs): death histogram, batch boundaries + their count, surface rays
@@ -348,8 +355,11 @@ void occupied_screen_box(FrameParams& P) {
     float minx = 1e30f, miny = 1e30f, maxx = -1e30f, maxy = -1e30f;
     for (int c = 0; c < 8; ++c) {
         // NeRF-space corner relative to the NeRF-space eye (cam + 0.5)
-        const float q[3] = {((c & 1) ? P.occ_max[0] : P.occ_min[0]) - (P.cam[9] + 0.5f), ((c & 2) ? P.occ_max[1] : P.occ_min[1]) - (P.cam[10] + 0.5f),
-                            ((c & 4) ? P.occ_max[2] : P.occ_min[2]) - (P.cam[11] + 0.5f)};
+        // a NeRF-space point p lies on the ray of the pixel whose camera direction d satisfies R d || p - origin, i.e. d || R^T (p - origin)
+        const float v[3] = {((c & 1) ? P.occ_max[0] : P.occ_min[0]) - P.ray_origin[0], ((c & 2) ? P.occ_max[1] : P.occ_min[1]) - P.ray_origin[1],
+                            ((c & 4) ? P.occ_max[2] : P.occ_min[2]) - P.ray_origin[2]};
+        const float* R = P.model_rot;
+        const float q[3] = {R[0] * v[0] + R[3] * v[1] + R[6] * v[2], R[1] * v[0] + R[4] * v[1] + R[7] * v[2], R[2] * v[0] + R[5] * v[1] + R[8] * v[2]};
         const float a = P.cam_inv[0] * q[0] + P.cam_inv[1] * q[1] + P.cam_inv[2] * q[2];
         const float b = P.cam_inv[3] * q[0] + P.cam_inv[4] * q[1] + P.cam_inv[5] * q[2];
         const float w = P.cam_inv[6] * q[0] + P.cam_inv[7] * q[1] + P.cam_inv[8] * q[2];
@@ -399,6 +409,19 @@ FrameParams make_params(nmr_ctx* ctx, const Nerf& n, int W, int H, const float* 
     invert3(cam12, P.cam_inv);
     std::memcpy(P.occ_min, n.occ_min, 12); std::memcpy(P.occ_max, n.occ_max, 12);
     P.surface_mode = ctx->surface_mode;
+    {   // model matrix: ray origin = R eye + 0.5 + R t_model in fp32, sums left to right (the oracle restates the same expression)
+        std::memcpy(P.model_rot, n.model_rot, sizeof(P.model_rot));
+        const float* R = n.model_rot; const float* e = cam12 + 9; const float* tm = n.model_translation;
+        const bool identity = R[0] == 1.f && R[4] == 1.f && R[8] == 1.f && R[1] == 0.f && R[2] == 0.f && R[3] == 0.f && R[5] == 0.f && R[6] == 0.f && R[7] == 0.f;
+        for (int k = 0; k < 3; ++k) {
+            if (identity) P.ray_origin[k] = (tm[k] != 0.f) ? (e[k] + 0.5f) + tm[k] : e[k] + 0.5f;
+            else {
+                const float ro = (R[k * 3] * e[0] + R[k * 3 + 1] * e[1]) + R[k * 3 + 2] * e[2];
+                const float rt = (R[k * 3] * tm[0] + R[k * 3 + 1] * tm[1]) + R[k * 3 + 2] * tm[2];
+                P.ray_origin[k] = (ro + 0.5f) + rt;
+            }
+        }
+    }
     occupied_screen_box(P);
     mesh_screen_box(ctx, P);
     P.lens_on = (P.mesh_scale > 0 && ctx->scene_has_lens && ctx->lens_enabled) ? 1 : 0;
@@ -440,11 +463,12 @@ void enqueue_surface_pass(nmr_ctx* ctx, Nerf& n, const FrameParams& P, const Fra
 }
 
 // one sample-per-pixel pass: mesh stage -> init -> march.  Enqueues only; no host synchronisation.
-void enqueue_pass(nmr_ctx* ctx, Nerf& n, const FrameParams& P, bool timed, void* image_target = nullptr) {
+void enqueue_pass(nmr_ctx* ctx, Nerf& n, const FrameParams& P, bool timed, void* image_target = nullptr, bool force_probes = false) {
     Surfaces& S = ctx->surf;
     const int rows = rows_owned_by(P.height, P.shard_rank, P.shard_world, P.shard_band);
     // the linear frame, depth and per-ray sample counts are parity probes (nmr_debug_last_frame): written only on request
-    const bool probes = (ctx->debug_flags & kDebugKeepProbes) != 0;
+    // (or when several NeRFs are merged by their depth buffers)
+    const bool probes = force_probes || (ctx->debug_flags & kDebugKeepProbes) != 0;
     FrameOut out{image_target ? image_target : static_cast<void*>(S.image.p), S.accum.p, probes ? S.frame.p : nullptr, probes ? S.depth.p : nullptr, probes ? S.n_samples.p : nullptr, nullptr, nullptr};
     if (!image_target) { S.image_format = P.out_format; S.image_is_frame = false; }
     static const char* phase_log_path = std::getenv("NMR_PHASE_LOG");      // measurement aid: see FrameOut::phase_log
@@ -598,6 +622,28 @@ void destroy_lane(nmr_ctx* l) {
 void sync_lane(nmr_ctx* l, const nmr_ctx* parent) {
     l->mesh_dev = parent->mesh_dev; l->mesh_scale = parent->mesh_scale; l->debug_flags = parent->debug_flags;
     l->scene_has_lens = parent->scene_has_lens; l->surface_mode = parent->surface_mode; l->overlap = parent->overlap;
+}
+
+// frame() with more than one NeRF loaded (NerfMeshRenderer::render_frame, S/nerf_mesh_renderer.cu:561-597): every NeRF renders the
+// frame into the per-sample linear frame / depth buffers, the mesh hand-off goes to the first one only (:554-558), the buffers are
+// merged by depth (the first NeRF's copied, the others through combineBuffersKernel's rule), and the displayed image is the
+// accumulate + tonemap of the merged frame with the first NeRF's background and curve.  (The reference tonemaps every NeRF into
+// the same texture, so on its screen the last NeRF simply wins and nothing reads the merged buffers; here they are the picture.)
+void enqueue_multi_nerf_frame(nmr_ctx* ctx) {
+    Surfaces& S = ctx->surf;
+    const uint32_t n_px = (uint32_t)ctx->width * (uint32_t)ctx->height;
+    S.comb_frame.ensure(n_px); S.comb_accum.ensure(n_px); S.comb_depth.ensure(n_px); S.image_alt.ensure(n_px);
+    FrameParams P0{};
+    for (size_t i = 0; i < ctx->nerfs.size(); ++i) {
+        Nerf& n = *ctx->nerfs[i];
+        const FrameParams P = make_params(ctx, n, ctx->width, ctx->height, ctx->cam12, S.spp, true, i == 0);
+        if (i == 0) P0 = P;
+        enqueue_pass(ctx, n, P, i + 1 == ctx->nerfs.size(), S.image_alt.p, true);
+        launch_combine_buffers(S.depth.p, S.frame.p, S.comb_depth.p, S.comb_frame.p, n_px, i == 0, ctx->stream);
+    }
+    launch_present(P0, S.comb_frame.p, S.comb_accum.p, S.image.p, n_px, ctx->stream);
+    S.image_format = kPixelF32; S.comb_valid = true;
+    CK(cudaGetLastError());
 }
 
 void set_camera_from_orbit(nmr_ctx* ctx) {
@@ -822,6 +868,35 @@ NMR_API int nmr_set_min_transmittance(nmr_ctx* ctx, int id, float v) {
     return guarded(ctx, [&]() -> int { try { get_nerf(ctx, id)->min_transmittance = v; return NMR_OK; } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); } });
 }
 
+NMR_API int nmr_set_model_transform(nmr_ctx* ctx, int id, const float translation[3], const float rotation_pi[3]) {
+    return guarded(ctx, [&]() -> int {
+        Nerf* n; try { n = get_nerf(ctx, id); } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); }
+        if (translation) std::memcpy(n->model_translation, translation, 12);
+        if (rotation_pi) std::memcpy(n->model_rotation_pi, rotation_pi, 12);
+        // AngleAxis(rx pi, X) * AngleAxis(ry pi, Y) * AngleAxis(rz pi, Z) (S/ngp/testbed.cu:1538-1541), evaluated in double
+        const double kPi = 3.14159265358979323846;
+        const double ax = n->model_rotation_pi[0] * kPi, ay = n->model_rotation_pi[1] * kPi, az = n->model_rotation_pi[2] * kPi;
+        const double cx = std::cos(ax), sx = std::sin(ax), cy = std::cos(ay), sy = std::sin(ay), cz = std::cos(az), sz = std::sin(az);
+        const double Rx[9] = {1, 0, 0, 0, cx, -sx, 0, sx, cx}, Ry[9] = {cy, 0, sy, 0, 1, 0, -sy, 0, cy}, Rz[9] = {cz, -sz, 0, sz, cz, 0, 0, 0, 1};
+        double T[9], Rm[9];
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { T[i * 3 + j] = 0; for (int k = 0; k < 3; ++k) T[i * 3 + j] += Rx[i * 3 + k] * Ry[k * 3 + j]; }
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { Rm[i * 3 + j] = 0; for (int k = 0; k < 3; ++k) Rm[i * 3 + j] += T[i * 3 + k] * Rz[k * 3 + j]; }
+        const bool zero = n->model_rotation_pi[0] == 0.f && n->model_rotation_pi[1] == 0.f && n->model_rotation_pi[2] == 0.f;
+        for (int k = 0; k < 9; ++k) n->model_rot[k] = zero ? (k % 4 == 0 ? 1.f : 0.f) : (float)Rm[k];
+        ctx->surf.spp = 0;
+        return NMR_OK;
+    });
+}
+NMR_API int nmr_get_model_transform(nmr_ctx* ctx, int id, float translation[3], float rotation_pi[3], float matrix3x3[9]) {
+    return guarded(ctx, [&]() -> int {
+        Nerf* n; try { n = get_nerf(ctx, id); } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); }
+        if (translation) std::memcpy(translation, n->model_translation, 12);
+        if (rotation_pi) std::memcpy(rotation_pi, n->model_rotation_pi, 12);
+        if (matrix3x3) std::memcpy(matrix3x3, n->model_rot, 36);
+        return NMR_OK;
+    });
+}
+
 NMR_API int nmr_get_nerf_info(nmr_ctx* ctx, int id, nmr_nerf_info* o) {
     return guarded(ctx, [&]() -> int {
         if (!o) return fail(ctx, NMR_ERR_INVALID, "out is null");
@@ -921,7 +996,9 @@ NMR_API int nmr_frame(nmr_ctx* ctx, int* keep_running) {
         Nerf& n = *ctx->nerfs[0];
         ctx->surf.resize(ctx->width, ctx->height, ctx->mesh_scale);
         const FrameParams P = make_params(ctx, n, ctx->width, ctx->height, ctx->cam12, ctx->surf.spp, true, true);
-        if (ctx->frame_target) enqueue_gather_frame(ctx, n, P); else enqueue_pass(ctx, n, P, true);
+        ctx->surf.comb_valid = false;
+        if (ctx->nerfs.size() > 1 && !ctx->frame_target && ctx->shard_world == 1) enqueue_multi_nerf_frame(ctx);
+        else if (ctx->frame_target) enqueue_gather_frame(ctx, n, P); else enqueue_pass(ctx, n, P, true);
         ctx->surf.image_is_frame = true;
         ++ctx->surf.spp;
         CK(cudaStreamSynchronize(ctx->stream));   // frame() returns a finished frame (S/nerf_mesh_renderer.cu:578)
@@ -945,6 +1022,22 @@ NMR_API int nmr_read_frame(nmr_ctx* ctx, float* out_rgba) {
             return fail(ctx, NMR_ERR_STATE, "the last image on this context is not a frame(): call frame() before read_frame()");
         const float4* src = (ctx->gather_image.p && ctx->frame_target == ctx->gather_image.p) ? ctx->gather_image.p : ctx->surf.image.p;
         CK(cudaMemcpyAsync(out_rgba, src, (size_t)ctx->width * ctx->height * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return NMR_OK;
+    });
+}
+
+NMR_API int nmr_read_combined(nmr_ctx* ctx, float* out_frame_rgba, float* out_depth) {
+    return guarded(ctx, [&]() -> int {
+        Surfaces& S = ctx->surf;
+        if (!S.image_is_frame || S.w != ctx->width || S.h != ctx->height) return fail(ctx, NMR_ERR_STATE, "the last image on this context is not a frame()");
+        const size_t n = (size_t)ctx->width * ctx->height;
+        const float4* f = nullptr; const float* d = nullptr;
+        if (S.comb_valid) { f = S.comb_frame.p; d = S.comb_depth.p; }
+        else if ((ctx->debug_flags & kDebugKeepProbes) && S.frame.p && S.depth.p) { f = S.frame.p; d = S.depth.p; }     // one NeRF: its own buffers are the merged ones
+        else return fail(ctx, NMR_ERR_STATE, "frame / depth buffers are only kept for frames of several NeRFs, or with debug flag 4 set before the frame");
+        if (out_frame_rgba) CK(cudaMemcpyAsync(out_frame_rgba, f, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_depth) CK(cudaMemcpyAsync(out_depth, d, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         return NMR_OK;
     });
@@ -1200,7 +1293,9 @@ NMR_API int nmr_frame_async(nmr_ctx* ctx) {
         Nerf& n = *ctx->nerfs[0];
         ctx->surf.resize(ctx->width, ctx->height, ctx->mesh_scale);
         const FrameParams P = make_params(ctx, n, ctx->width, ctx->height, ctx->cam12, ctx->surf.spp, true, true);
-        if (ctx->frame_target) enqueue_gather_frame(ctx, n, P); else enqueue_pass(ctx, n, P, true);
+        ctx->surf.comb_valid = false;
+        if (ctx->nerfs.size() > 1 && !ctx->frame_target && ctx->shard_world == 1) enqueue_multi_nerf_frame(ctx);
+        else if (ctx->frame_target) enqueue_gather_frame(ctx, n, P); else enqueue_pass(ctx, n, P, true);
         ctx->surf.image_is_frame = true;
         ++ctx->surf.spp;
         return NMR_OK;
@@ -1219,6 +1314,67 @@ NMR_API int nmr_set_density_bitfield(nmr_ctx* ctx, int id, const uint8_t* in) {
     return guarded(ctx, [&]() -> int {
         Nerf* n; try { n = get_nerf(ctx, id); } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); }
         CK(cudaMemcpyAsync(n->d_bitfield.p, in, kBitfieldBytes, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        update_occupied_box(ctx, *n);
+        ctx->surf.spp = 0;
+        return NMR_OK;
+    });
+}
+
+// NerfMeshRenderer::dumpDensityGrid / loadDensityGrid (S/nerf_mesh_renderer.cu:239-358): the occupancy bitfield as 8 x 128^3 bytes
+// (0 / 1), cell (x, y, z) of cascade `mip` at x + 128 y + 128^2 z + 128^3 mip; the bit of that cell is the Morton code of
+// (x, y, z) inside the cascade (pos_to_cascaded_grid_idx of the cell's centre-aligned position, which maps back to (x, y, z)).
+namespace {
+uint32_t host_expand_bits(uint32_t v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu; v = (v * 0x00000101u) & 0x0F00F00Fu; v = (v * 0x00000011u) & 0xC30C30C3u; v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+}  // namespace
+NMR_API int nmr_dump_density_grid(nmr_ctx* ctx, int id, const char* path, uint8_t* out_cells) {
+    return guarded(ctx, [&]() -> int {
+        Nerf* n; try { n = get_nerf(ctx, id); } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); }
+        if (!path && !out_cells) return fail(ctx, NMR_ERR_INVALID, "neither a path nor a buffer given");
+        std::vector<uint8_t> bits(kBitfieldBytes), cells((size_t)kCascades * kGridCells);
+        CK(cudaMemcpyAsync(bits.data(), n->d_bitfield.p, kBitfieldBytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (uint32_t mip = 0; mip < kCascades; ++mip)
+            for (uint32_t z = 0; z < kGridSize; ++z) for (uint32_t y = 0; y < kGridSize; ++y) for (uint32_t x = 0; x < kGridSize; ++x) {
+                const uint32_t idx = host_expand_bits(x) | (host_expand_bits(y) << 1) | (host_expand_bits(z) << 2);
+                cells[x + kGridSize * (y + kGridSize * (z + (size_t)kGridSize * mip))] = (bits[idx / 8 + (size_t)mip * kGridCells / 8] >> (idx % 8)) & 1u;
+            }
+        if (out_cells) std::memcpy(out_cells, cells.data(), cells.size());
+        if (path) {
+            FILE* f = std::fopen(path, "wb");
+            if (!f) return fail(ctx, NMR_ERR_IO, std::string("cannot open ") + path);
+            const size_t w = std::fwrite(cells.data(), 1, cells.size(), f);
+            std::fclose(f);
+            if (w != cells.size()) return fail(ctx, NMR_ERR_IO, std::string("short write to ") + path);
+        }
+        return NMR_OK;
+    });
+}
+NMR_API int nmr_load_density_grid(nmr_ctx* ctx, int id, const char* path, const uint8_t* in_cells) {
+    return guarded(ctx, [&]() -> int {
+        Nerf* n; try { n = get_nerf(ctx, id); } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); }
+        if (!path && !in_cells) return fail(ctx, NMR_ERR_INVALID, "neither a path nor a buffer given");
+        std::vector<uint8_t> cells;
+        if (path) {
+            FILE* f = std::fopen(path, "rb");
+            if (!f) return fail(ctx, NMR_ERR_IO, std::string("cannot open ") + path);
+            cells.resize((size_t)kCascades * kGridCells);
+            const size_t r = std::fread(cells.data(), 1, cells.size(), f);
+            std::fclose(f);
+            if (r != cells.size()) return fail(ctx, NMR_ERR_FORMAT, "density grid file must hold 8 x 128^3 bytes");
+            in_cells = cells.data();
+        }
+        std::vector<uint8_t> bits(kBitfieldBytes, 0);
+        for (uint32_t mip = 0; mip < kCascades; ++mip)
+            for (uint32_t z = 0; z < kGridSize; ++z) for (uint32_t y = 0; y < kGridSize; ++y) for (uint32_t x = 0; x < kGridSize; ++x) {
+                if (!in_cells[x + kGridSize * (y + kGridSize * (z + (size_t)kGridSize * mip))]) continue;
+                const uint32_t idx = host_expand_bits(x) | (host_expand_bits(y) << 1) | (host_expand_bits(z) << 2);
+                bits[idx / 8 + (size_t)mip * kGridCells / 8] |= (uint8_t)(1u << (idx % 8));
+            }
+        CK(cudaMemcpyAsync(n->d_bitfield.p, bits.data(), kBitfieldBytes, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         update_occupied_box(ctx, *n);
         ctx->surf.spp = 0;
@@ -1334,6 +1490,7 @@ static void debug_mesh_stage(nmr_ctx* ctx, int width, int height, FrameParams& P
     P = FrameParams{};
     P.width = width; P.height = height; std::memcpy(P.cam, ctx->cam12, sizeof(P.cam));
     P.shard_world = 1; P.shard_band = 8; P.mesh_scale = ms; std::memcpy(P.light, ctx->light, 12);
+    P.model_rot[0] = P.model_rot[4] = P.model_rot[8] = 1.f;
     invert3(ctx->cam12, P.cam_inv);
     mesh_screen_box(ctx, P);
     P.lens_on = (ctx->scene_has_lens && ctx->lens_enabled) ? 1 : 0;

@@ -86,6 +86,10 @@ struct FrameParams {
     int lens_on;
     float lens_f0, lens_k[3], lens_kmean;
     int out_format;                   // PixelFormat of FrameOut::image (nmr_pixel_format of include/nmr.h)
+    // Testbed::m_model_rotation / m_model_translation (S/ngp/testbed.cu:1537-1542, consumed at :442-446): ray direction = R d,
+    // NeRF-space ray origin = R eye + 0.5 + R t_model (evaluated on the host, make_params).  The identity leaves eye + 0.5.
+    float model_rot[9];               // row-major
+    float ray_origin[3];
 };
 
 // Displayed image formats.  kPixelU8 is what render.py turns every frame into on the host (np.uint8(img * 255), V/render.py:62-66):
@@ -328,6 +332,13 @@ __device__ __forceinline__ float occupied_exit(const FrameParams& P, V3 o, V3 d,
     return tmax;
 }
 
+// R d (glm-style left-to-right sums); the identity - the only value reachable without nmr_set_model_transform - returns d itself
+__device__ __forceinline__ V3 model_rotate(const FrameParams& P, V3 d) {
+    const float* m = P.model_rot;
+    if (m[0] == 1.f && m[4] == 1.f && m[8] == 1.f && m[1] == 0.f && m[2] == 0.f && m[3] == 0.f && m[5] == 0.f && m[6] == 0.f && m[7] == 0.f) return d;
+    return v3((m[0] * d.x + m[1] * d.y) + m[2] * d.z, (m[3] * d.x + m[4] * d.y) + m[5] * d.z, (m[6] * d.x + m[7] * d.y) + m[8] * d.z);
+}
+
 __device__ __forceinline__ RayInit init_ray(const FrameParams& P, uint32_t x, uint32_t y) {
     const float* c = P.cam;
     const float ux = 2.0f * (((float)x + 0.5f) / (float)P.width) - 1.0f;
@@ -336,7 +347,8 @@ __device__ __forceinline__ RayInit init_ray(const FrameParams& P, uint32_t x, ui
     const float z = edot(d, d);
     if (z > 0.0f) { const float n = sqrtf(z); d = v3(d.x / n, d.y / n, d.z / n); }
     RayInit r;
-    r.origin = v3(c[9] + 0.5f, c[10] + 0.5f, c[11] + 0.5f);
+    r.origin = v3(P.ray_origin[0], P.ray_origin[1], P.ray_origin[2]);
+    d = model_rotate(P, d);
     r.dir = d;
     r.t = fmaxf(box_ray_tmin(P.aabb_min, P.aabb_max, r.origin, d), 0.0f) + 1e-6f;
     r.alive = box_contains(P.aabb_min, P.aabb_max, vadd(r.origin, vmul(d, r.t)));

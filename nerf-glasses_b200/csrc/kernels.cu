@@ -399,8 +399,9 @@ __device__ __forceinline__ void init_one_ray(const FrameParams& P, const DeviceM
         const float* c = P.cam;
         const float ux = 2.0f * (((float)x + 0.5f) / (float)P.width) - 1.0f;
         const float uy = 2.0f * (((float)y + 0.5f) / (float)P.height) - 1.0f;
-        const float d[3] = {c[0] * ux + (c[3] * uy + c[6]), c[1] * ux + (c[4] * uy + c[7]), c[2] * ux + (c[5] * uy + c[8])};
-        const float o[3] = {c[9] + 0.5f, c[10] + 0.5f, c[11] + 0.5f};
+        const V3 dm = model_rotate(P, v3(c[0] * ux + (c[3] * uy + c[6]), c[1] * ux + (c[4] * uy + c[7]), c[2] * ux + (c[5] * uy + c[8])));
+        const float d[3] = {dm.x, dm.y, dm.z};
+        const float o[3] = {P.ray_origin[0], P.ray_origin[1], P.ray_origin[2]};
         float tmin = 0.f, tmax = 3.402823466e+38f;        // only the part of the line in front of the eye counts
         bool miss = false;
 #pragma unroll
@@ -434,7 +435,8 @@ __device__ __forceinline__ void init_one_ray(const FrameParams& P, const DeviceM
     q1[0] = t_start; q1[1] = t_surface; q1[3] = r.t_limit;
     queue[(size_t)slot * kRayRecordFloat4s + 2] = make_float4(surf[0], surf[1], surf[2], surf[3]);
     if (L.w > 0.f) {
-        out.lens[(size_t)idx * 2] = make_float4(L.n.x, L.n.y, L.n.z, L.t);
+        const V3 ln = model_rotate(P, L.n);     // the mirror direction is taken in NeRF space
+        out.lens[(size_t)idx * 2] = make_float4(ln.x, ln.y, ln.z, L.t);
         out.lens[(size_t)idx * 2 + 1] = make_float4(L.w, 0.f, 0.f, 0.f);
     }
     // the ready word last, with release semantics: whoever reads it (acquire) also sees the rest of the record and the lens entry
@@ -504,6 +506,43 @@ __global__ void __launch_bounds__(256) background_kernel(FrameParams P, FrameOut
         if (box.nx > 0 && x >= bx0 && x < bx1 && ly >= by0 && ly < by1) continue;
         background_pixel(P, out, (uint32_t)x + W * (uint32_t)shard_row(P, ly));
     }
+}
+
+// Several NeRFs in one frame (NerfMeshRenderer::render_frame, S/nerf_mesh_renderer.cu:582-597): every NeRF renders into its own
+// linear frame + depth buffers; the first one's are copied, the others z-merged with combineBuffersKernel's rule
+// (S/nerf_mesh_renderer.cu:34-48): the nearer depth takes the pixel.
+__global__ void combine_buffers_kernel(const float* __restrict__ in_depth, const float4* __restrict__ in_frame, float* __restrict__ out_depth, float4* __restrict__ out_frame, uint32_t n, int first) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float d = in_depth[i];
+    if (first || d < out_depth[i]) { out_depth[i] = d; out_frame[i] = in_frame[i]; }
+}
+void launch_combine_buffers(const float* d_in_depth, const float4* d_in_frame, float* d_out_depth, float4* d_out_frame, uint32_t n, bool first, cudaStream_t s) {
+    combine_buffers_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_in_depth, d_in_frame, d_out_depth, d_out_frame, n, first ? 1 : 0);
+}
+// accumulate + tonemap of a merged linear frame (the tail of finish_pixel: S/ngp/render_buffer.cu:232-267, 537-566)
+__global__ void present_kernel(FrameParams P, const float4* __restrict__ frame, float4* __restrict__ accum, void* __restrict__ image, uint32_t n) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const float4 fb = frame[idx];
+    float4 acc = fb;
+    if (P.spp_index != 0) {
+        const float sc = (float)P.spp_index;
+        const float4 prev = accum[idx];
+        acc = make_float4((prev.x * sc + fb.x) / (sc + 1), (prev.y * sc + fb.y) / (sc + 1), (prev.z * sc + fb.z) / (sc + 1), (prev.w * sc + fb.w) / (sc + 1));
+    }
+    accum[idx] = acc;
+    const float w = (1 - acc.w) * P.background[3];
+    float cr = acc.x + P.background_linear[0] * w, cg = acc.y + P.background_linear[1] * w, cb = acc.z + P.background_linear[2] * w, ca = acc.w + w;
+    tonemap_curve_apply(cr, cg, cb, P.tonemap_curve);
+    if (P.to_srgb) {
+        cr = fminf(fmaxf(linear_to_srgb(cr), 0.f), 1.f); cg = fminf(fmaxf(linear_to_srgb(cg), 0.f), 1.f);
+        cb = fminf(fmaxf(linear_to_srgb(cb), 0.f), 1.f); ca = fminf(fmaxf(ca, 0.f), 1.f);
+    }
+    store_pixel(image, P.out_format, idx, cr, cg, cb, ca);
+}
+void launch_present(const FrameParams& P, const float4* d_frame, float4* d_accum, void* d_image, uint32_t n, cudaStream_t s) {
+    present_kernel<<<(n + 255) / 256, 256, 0, s>>>(P, d_frame, d_accum, d_image, n);
 }
 
 // Shared frame target, destination rank: the constant background of every pixel outside both screen rectangles (the same
@@ -985,7 +1024,7 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH
     const uint32_t sub = lane & (kRayLanes - 1);             // which of the group's samples this lane evaluates
     const uint32_t gbase = lane & ~(uint32_t)(kRayLanes - 1);
     const uint32_t gmask = ((1u << kRayLanes) - 1u) << gbase;
-    const V3 cam_origin = v3(P.cam[9] + 0.5f, P.cam[10] + 0.5f, P.cam[11] + 0.5f);
+    const V3 cam_origin = v3(P.ray_origin[0], P.ray_origin[1], P.ray_origin[2]);
     // lens rays park the state of their other segments here (one slot per ray group; all 8 lanes write the same values)
     float* __restrict__ stash = out.lens_scratch ? out.lens_scratch + ((size_t)blockIdx.x * (blockDim.x / kRayLanes) + threadIdx.x / kRayLanes) * kLensStash : nullptr;
 

@@ -95,6 +95,9 @@ void launch_march(const FrameParams& P, const DeviceModel& M, const float4* d_qu
 // density probes of the collision tool: mode 0 = NerfTracer::intersects (alpha at points), 1 = NerfTracer::collide (distance along dir)
 void launch_probe(const FrameParams& P, const DeviceModel& M, const float* d_points_world, const float dir[3], int64_t n, int mode, float* d_out,
                   uint32_t debug_flags, int num_sms, cudaStream_t s);
+// several NeRFs in one frame: z-merge of per-NeRF linear frame / depth buffers (first = plain copy), then accumulate + tonemap
+void launch_combine_buffers(const float* d_in_depth, const float4* d_in_frame, float* d_out_depth, float4* d_out_frame, uint32_t n, bool first, cudaStream_t s);
+void launch_present(const FrameParams& P, const float4* d_frame, float4* d_accum, void* d_image, uint32_t n, cudaStream_t s);
 // measurement helper (bench.py): L2 -> SM throughput probe, see kernels.cu
 void launch_l2_probe(const void* d_buf, uint32_t n_vec, uint32_t loads_per_thread, int mode, uint32_t* d_sink, int num_sms, cudaStream_t s);
 // parity probes

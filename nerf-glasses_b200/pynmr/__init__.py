@@ -85,6 +85,11 @@ def lib():
         "nmr_set_shard": (C.c_int, [vp, C.c_int, C.c_int, C.c_int]),
         "nmr_set_surface_insertion": (C.c_int, [vp, C.c_int]),
         "nmr_set_overlap": (C.c_int, [vp, C.c_int]),
+        "nmr_set_model_transform": (C.c_int, [vp, C.c_int, fp, fp]),
+        "nmr_get_model_transform": (C.c_int, [vp, C.c_int, fp, fp, fp]),
+        "nmr_dump_density_grid": (C.c_int, [vp, C.c_int, C.c_char_p, vp]),
+        "nmr_load_density_grid": (C.c_int, [vp, C.c_int, C.c_char_p, vp]),
+        "nmr_read_combined": (C.c_int, [vp, vp, vp]),
         "nmr_set_lens": (C.c_int, [vp, C.c_int, C.c_float, C.c_float, fp]),
         "nmr_get_nerf_info": (C.c_int, [vp, C.c_int, C.POINTER(NerfInfo)]),
         "nmr_get_stream": (C.c_int, [vp, C.POINTER(vp)]),
@@ -127,7 +132,8 @@ EXPORTED_SYMBOLS = [
     "nmr_set_camera", "nmr_frame", "nmr_frame_async", "nmr_read_frame", "nmr_render", "nmr_render_views", "nmr_set_shard", "nmr_set_surface_insertion", "nmr_set_lens", "nmr_debug_lens", "nmr_get_nerf_info", "nmr_gather_create", "nmr_gather_attach", "nmr_gather_detach", "nmr_get_stream", "nmr_probe_points", "nmr_probe_rays", "nmr_set_tonemap_curve", "nmr_get_tonemap_curve",
     "nmr_get_device_image", "nmr_copy_device_image", "nmr_flush_l2", "nmr_get_stats", "nmr_synchronize", "nmr_host_alloc", "nmr_host_free", "nmr_get_density_bitfield",
     "nmr_set_density_bitfield", "nmr_debug_encode", "nmr_debug_network", "nmr_debug_trace", "nmr_debug_mesh",
-    "nmr_debug_last_frame", "nmr_debug_set_flags", "nmr_render_format", "nmr_render_views_format", "nmr_debug_parse_gltf", "nmr_measure_l2", "nmr_set_overlap",
+    "nmr_debug_last_frame", "nmr_debug_set_flags", "nmr_render_format", "nmr_render_views_format", "nmr_debug_parse_gltf", "nmr_measure_l2", "nmr_set_overlap", "nmr_set_model_transform", "nmr_get_model_transform",
+    "nmr_dump_density_grid", "nmr_load_density_grid", "nmr_read_combined",
 ]
 
 
@@ -423,6 +429,48 @@ class Testbed:
     def camera_matrix(self, mat):
         self._r.view_projection_mat = mat
 
+    # -- Testbed::m_model_translation / m_model_rotation (GUI sliders in the reference; S/ngp/testbed.cuh:508-509)
+    def _model(self):
+        t = (C.c_float * 3)(); r = (C.c_float * 3)(); m = (C.c_float * 9)()
+        self._r._ck(lib().nmr_get_model_transform(self._r._h, self._id, t, r, m))
+        return np.array(list(t), np.float32), np.array(list(r), np.float32), np.array(list(m), np.float32).reshape(3, 3)
+
+    @property
+    def model_translation(self) -> np.ndarray:
+        return self._model()[0]
+
+    @model_translation.setter
+    def model_translation(self, t):
+        self._r._ck(lib().nmr_set_model_transform(self._r._h, self._id, _f3(t), None))
+
+    @property
+    def model_rotation(self) -> np.ndarray:
+        """three angles in units of pi about X, Y, Z (the reference's m_model_rotation)"""
+        return self._model()[1]
+
+    @model_rotation.setter
+    def model_rotation(self, r):
+        self._r._ck(lib().nmr_set_model_transform(self._r._h, self._id, None, _f3(r)))
+
+    @property
+    def model_matrix(self) -> np.ndarray:
+        """the 3x3 rotation in use (AngleAxis(rx pi, X) * AngleAxis(ry pi, Y) * AngleAxis(rz pi, Z))"""
+        return self._model()[2]
+
+    def dump_density_grid(self, path: str | None = None) -> np.ndarray:
+        """NerfMeshRenderer::dumpDensityGrid: uint8 [8, 128, 128, 128] (cascade, z, y, x), optionally written to `path`."""
+        cells = np.zeros((8, 128, 128, 128), dtype=np.uint8)
+        self._r._ck(lib().nmr_dump_density_grid(self._r._h, self._id, os.fsencode(path) if path else None, _ptr(cells)))
+        return cells
+
+    def load_density_grid(self, path_or_cells):
+        """NerfMeshRenderer::loadDensityGrid: from a file written by dump_density_grid (or the reference), or from an array."""
+        if isinstance(path_or_cells, (str, bytes, os.PathLike)):
+            self._r._ck(lib().nmr_load_density_grid(self._r._h, self._id, os.fsencode(path_or_cells), None))
+        else:
+            cells = np.ascontiguousarray(path_or_cells, dtype=np.uint8).reshape(8, 128, 128, 128)
+            self._r._ck(lib().nmr_load_density_grid(self._r._h, self._id, None, _ptr(cells)))
+
     def set_crop_box(self, box: BoundingBox):
         self._set_render_aabb(box.min, box.max)
 
@@ -574,6 +622,13 @@ class NerfMeshRenderer:
         out = _pinned_array((self.height, self.width, 4))
         self._ck(lib().nmr_read_frame(self._h, _ptr(out)))
         return out
+
+    def read_combined(self):
+        """(linear premultiplied frame float32[H, W, 4], depth float32[H, W]) merged over all NeRFs of the last frame()
+        (include/nmr.h: nmr_read_combined - the reference's _dFramebuffer / _dDepthBuffer)."""
+        fr = np.zeros((self.height, self.width, 4), dtype=np.float32); dp = np.zeros((self.height, self.width), dtype=np.float32)
+        self._ck(lib().nmr_read_combined(self._h, _ptr(fr), _ptr(dp)))
+        return fr, dp
 
     def frame_async(self):
         self._ck(lib().nmr_frame_async(self._h))

@@ -691,6 +691,9 @@ typedef struct {
     int32_t n_steps_mode;         /* 0: one sample per wavefront iteration; 1: the reference's clamp(N0/N_alive,1,8); 2: always 8 (what 1 gives
                                      while at most 1/8 of the FRAME's pixels are live - for windows of a larger frame) */
     int32_t x0, y0, x1, y1;       /* pixel window [x0,x1) x [y0,y1) to render (others untouched); all 0 = full frame */
+    /* Testbed::m_model_rotation / m_model_translation as the model matrix of S/ngp/testbed.cu:1537-1542: rotation row-major 3x3
+     * (all zeros = identity), translation in world units */
+    float model_rot[9], model_trans[3];
 } orc_render_params;
 
 typedef struct {
@@ -723,8 +726,8 @@ static inline v3 glm_mat3_mul(const float* m /* row-major */, v3 p) {
 }
 
 /* pixel_to_ray (S/ngp/ngp_common.cuh:334-394, perspective branch) + init_rays_with_payload_kernel_nerf
- * (S/ngp/testbed.cu:355-467) with the identity model matrix (m_model_rotation/translation are zero
- * and not reachable from the Python API): NeRF-space origin = eye + 0.5. */
+ * (S/ngp/testbed.cu:355-467).  Model matrix [R | t_model] (S/ngp/testbed.cu:1537-1542, consumed at :442-446):
+ * dir = R d, NeRF-space origin = R eye + 0.5 + R t_model; the identity gives eye + 0.5. */
 static void init_ray(const orc_render_params* P, const aabb_t* render_aabb, uint32_t x, uint32_t y, ray_t* r) {
     const float* c = P->camera;
     float ux = 2.0f * (((float)x + 0.5f) / (float)P->width) - 1.0f;
@@ -733,6 +736,19 @@ static void init_ray(const orc_render_params* P, const aabb_t* render_aabb, uint
     v3 o = v3_make(c[9], c[10], c[11]);
     d = normalize3(d);
     v3 to = v3_make(o.x + 0.5f, o.y + 0.5f, o.z + 0.5f);
+    {
+        const float* R = P->model_rot; int any = 0;
+        for (int k = 0; k < 9; ++k) any |= (R[k] != 0.f);
+        const int identity = !any || (R[0] == 1.f && R[4] == 1.f && R[8] == 1.f && R[1] == 0.f && R[2] == 0.f && R[3] == 0.f && R[5] == 0.f && R[6] == 0.f && R[7] == 0.f);
+        const v3 tm = v3_make(P->model_trans[0], P->model_trans[1], P->model_trans[2]);
+        if (!identity) {
+            d = glm_mat3_mul(R, d);
+            const v3 ro = glm_mat3_mul(R, o), rt = glm_mat3_mul(R, tm);
+            to = v3_make((ro.x + 0.5f) + rt.x, (ro.y + 0.5f) + rt.y, (ro.z + 0.5f) + rt.z);
+        } else if (tm.x != 0.f || tm.y != 0.f || tm.z != 0.f) {
+            to = v3_make((o.x + 0.5f) + tm.x, (o.y + 0.5f) + tm.y, (o.z + 0.5f) + tm.z);
+        }
+    }
     float tmin, tmax;
     aabb_ray_intersect(render_aabb, to, d, &tmin, &tmax);
     float t = fmaxf(tmin, 0.0f) + 1e-6f;

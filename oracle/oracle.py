@@ -39,6 +39,7 @@ class RenderParams(C.Structure):
         ("rgb_activation", C.c_int32), ("density_activation", C.c_int32),
         ("n_steps_mode", C.c_int32),
         ("x0", C.c_int32), ("y0", C.c_int32), ("x1", C.c_int32), ("y1", C.c_int32),
+        ("model_rot", C.c_float * 9), ("model_trans", C.c_float * 3),
     ]
 
 
@@ -219,7 +220,7 @@ class Model:
         return out.view(np.float16)
 
     def params_struct(self, width, height, camera12, aabb_min=None, aabb_max=None, spp_index=0, n_steps_mode=0,
-                      min_transmittance=0.01, rgb_activation=2, density_activation=3, window=None) -> RenderParams:
+                      min_transmittance=0.01, rgb_activation=2, density_activation=3, window=None, model_rot=None, model_trans=None) -> RenderParams:
         P = RenderParams()
         P.width, P.height = width, height
         P.camera[:] = [float(x) for x in camera12]
@@ -235,6 +236,8 @@ class Model:
         P.n_steps_mode = n_steps_mode
         if window is not None:
             P.x0, P.y0, P.x1, P.y1 = window
+        P.model_rot[:] = [1, 0, 0, 0, 1, 0, 0, 0, 1] if model_rot is None else [float(x) for x in np.asarray(model_rot, dtype=np.float32).reshape(9)]
+        P.model_trans[:] = [0, 0, 0] if model_trans is None else [float(x) for x in np.asarray(model_trans, dtype=np.float32).reshape(3)]
         return P
 
     def render_frame(self, P: RenderParams, surf_rgba=None, t_surface=None, lens=None):

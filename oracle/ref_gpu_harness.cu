@@ -130,6 +130,24 @@ REF_API int refgpu_set_tonemap_curve(void* h, int curve) {
     static_cast<RefCtx*>(h)->tb->m_tonemap_curve = (ETonemapCurve)curve;
     return 0;
 }
+// Testbed::m_model_translation / m_model_rotation (S/ngp/testbed.cuh:508-509; the GUI's "Position" / "Rotation" sliders)
+REF_API int refgpu_set_model_transform(void* h, const float* translation3, const float* rotation_pi3) {
+    Testbed& t = *static_cast<RefCtx*>(h)->tb;
+    for (int k = 0; k < 3; ++k) { t.m_model_translation[k] = translation3[k]; t.m_model_rotation[k] = rotation_pi3[k]; }
+    return 0;
+}
+// what NerfMeshRenderer::render_frame copies / z-merges after every NeRF's render_frame (S/nerf_mesh_renderer.cu:582-597): the
+// render surface's linear frame buffer [h][w][4] and depth buffer [h][w] of the last refgpu_render call
+REF_API int refgpu_get_buffers(void* h, int w, int hh, float* frame, float* depth) {
+    RefCtx* r = static_cast<RefCtx*>(h);
+    return guarded(r, [&] {
+        CudaRenderBuffer& rb = r->tb->m_windowless_render_surface;
+        const size_t n = (size_t)w * (size_t)hh;
+        if (rb.in_resolution().x() != w || rb.in_resolution().y() != hh) throw std::runtime_error{"render surface has another resolution"};
+        if (frame) CUDA_CHECK_THROW(cudaMemcpy(frame, rb.frame_buffer(), n * 16, cudaMemcpyDeviceToHost));
+        if (depth) CUDA_CHECK_THROW(cudaMemcpy(depth, rb.depth_buffer(), n * 4, cudaMemcpyDeviceToHost));
+    });
+}
 REF_API int refgpu_set_background(void* h, const float* rgba) {
     static_cast<RefCtx*>(h)->tb->m_background_color = Array4f{rgba[0], rgba[1], rgba[2], rgba[3]};
     return 0;

@@ -60,6 +60,9 @@ def lib():
         if hasattr(L, "refgpu_probe"):
             L.refgpu_probe.argtypes = [vp, C.c_int, vp, vp, C.c_int64, vp]
         L.refgpu_render.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp]
+        if hasattr(L, "refgpu_get_buffers"):
+            L.refgpu_get_buffers.argtypes = [vp, C.c_int, C.c_int, vp, vp]
+            L.refgpu_set_model_transform.argtypes = [vp, vp, vp]
         _lib = L
     return _lib
 
@@ -154,3 +157,15 @@ class ReferenceRenderer:
         ms = C.c_float(0)
         self._ck(self._L.refgpu_render(self._h, _p(cam12), W, H, spp, 1 if linear else 0, _p(s), _p(t), _p(out), repeat, C.byref(ms)))
         return out, float(ms.value)
+
+    def set_model_transform(self, translation, rotation_pi):
+        """Testbed::m_model_translation / m_model_rotation (angles in units of pi about X, Y, Z)."""
+        t = np.ascontiguousarray(translation, dtype=np.float32).reshape(3); r = np.ascontiguousarray(rotation_pi, dtype=np.float32).reshape(3)
+        self._ck(self._L.refgpu_set_model_transform(self._h, _p(t), _p(r)))
+
+    def buffers(self, W, H):
+        """Linear frame buffer [H, W, 4] and depth buffer [H, W] of the render surface after the last render() - what
+        NerfMeshRenderer::render_frame copies / z-merges per NeRF (S/nerf_mesh_renderer.cu:582-597)."""
+        frame = np.zeros((H, W, 4), np.float32); depth = np.zeros((H, W), np.float32)
+        self._ck(self._L.refgpu_get_buffers(self._h, W, H, _p(frame), _p(depth)))
+        return frame, depth

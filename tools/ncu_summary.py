@@ -1,7 +1,8 @@
 """Turns an `ncu --set full` report (.ncu-rep, read with the local ncu CLI) into the small JSON / text summary that is
 committed under profiles/: headline counters of the captured kernel plus the hottest source lines.
 
-    python tools/ncu_summary.py gpurun_out/X.ncu-rep profiles/r1_X_summary.json [--lines 25]
+    python tools/ncu_summary.py gpurun_out/X.ncu-rep profiles/r2_X_summary.json [--lines 25] [--samples N]
+(--samples: network evaluations of the captured launch, from the same command run without ncu - adds the per-sample figures)
 """
 import csv
 import io
@@ -68,6 +69,17 @@ def main():
             d[KEYS[h]] = x
     if "duration" in d:
         d["duration_us"] = d.pop("duration") * 1e6
+    if "--samples" in sys.argv:
+        n = float(sys.argv[sys.argv.index("--samples") + 1])
+        d["samples"] = n
+        if "l1_global_load_sectors" in d:
+            d["l1_sectors_per_sample"] = d["l1_global_load_sectors"] / n
+        if "l2_sectors_read_from_l1" in d:
+            d["l2_to_l1_bytes_per_sample"] = d["l2_sectors_read_from_l1"] * 32.0 / n
+        if "warp_instructions" in d:
+            d["warp_instructions_per_32_samples"] = d["warp_instructions"] * 32.0 / n
+        if "duration_us" in d:
+            d["msamples_per_s"] = n / d["duration_us"]
     # hottest source lines by executed warp instructions
     src = list(csv.reader(io.StringIO(ncu("-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda"))))
     cur, h2, lines = None, None, []
