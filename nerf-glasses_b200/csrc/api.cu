@@ -135,7 +135,7 @@ struct nmr_ctx {
     std::vector<std::unique_ptr<Mesh>> meshes;
     // concatenated world-space mesh on the device
     bool mesh_dirty = true;
-    DevBuf<float> d_wpos, d_wnrm, d_uv, d_tex;
+    DevBuf<float> d_wpos, d_wnrm, d_uv, d_tex, d_wtbn, d_xtex[4];
     DevBuf<uint32_t> d_idx;
     DevBuf<uint8_t> d_tri_lens;
     bool scene_has_lens = false;                          // some loaded mesh has a transmissive material
@@ -219,8 +219,9 @@ void invert3(const float* cam12, float out[9]) {
 
 void upload_mesh_if_dirty(nmr_ctx* ctx) {
     if (!ctx->mesh_dirty) return;
-    std::vector<float> wpos, wnrm, uv;
+    std::vector<float> wpos, wnrm, uv, wtbn;
     std::vector<uint32_t> idx;
+    float nmat0[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
     std::vector<uint8_t> tri_lens;
     bool any_lens = false;
     for (const auto& m : ctx->meshes) {
@@ -230,6 +231,12 @@ void upload_mesh_if_dirty(nmr_ctx* ctx) {
         wpos.insert(wpos.end(), p.begin(), p.end());
         wnrm.insert(wnrm.end(), n.begin(), n.end());
         uv.insert(uv.end(), m->host.texcoords.begin(), m->host.texcoords.end());
+        {
+            std::vector<float> f; float nm[9];
+            transform_tangent_frames(m->host, m->s, m->r, f, nm);
+            wtbn.insert(wtbn.end(), f.begin(), f.end());
+            if (&m == &ctx->meshes.front()) std::memcpy(nmat0, nm, sizeof(nm));
+        }
         for (uint32_t i : m->host.indices) idx.push_back(base + i);
         tri_lens.insert(tri_lens.end(), m->host.tri_lens.begin(), m->host.tri_lens.end());
         tri_lens.resize(idx.size() / 3, 0);
@@ -273,6 +280,34 @@ void upload_mesh_if_dirty(nmr_ctx* ctx) {
             ctx->d_tex.ensure(tex.size());
             CK(cudaMemcpyAsync(ctx->d_tex.p, tex.data(), tex.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
             d.tex_lin = ctx->d_tex.p; d.tex_w = m0.tex_w; d.tex_h = m0.tex_h;
+        }
+        // emissive (sRGB), metallic-roughness, normal, occlusion (linear) textures of the first mesh's material
+        const HostMesh::Texture* xt[4] = {&m0.tex_emissive, &m0.tex_metallic_roughness, &m0.tex_normal, &m0.tex_occlusion};
+        TexDev* xd[4] = {&d.tex_emissive, &d.tex_mr, &d.tex_normal, &d.tex_occ};
+        std::vector<float> xbuf[4];
+        for (int k = 0; k < 4; ++k) {
+            *xd[k] = TexDev{nullptr, 0, 0};
+            if (xt[k]->rgba8.empty()) continue;
+            const size_t px = (size_t)xt[k]->w * xt[k]->h;
+            xbuf[k].resize(px * 4);
+            for (size_t i = 0; i < px; ++i) {
+                for (int c = 0; c < 3; ++c) {
+                    const float sv = (float)xt[k]->rgba8[i * 4 + c] / 255.0f;
+                    xbuf[k][i * 4 + c] = k == 0 ? (sv <= 0.04045f ? sv / 12.92f : powf((sv + 0.055f) / 1.055f, 2.4f)) : sv;
+                }
+                xbuf[k][i * 4 + 3] = (float)xt[k]->rgba8[i * 4 + 3] / 255.0f;
+            }
+            ctx->d_xtex[k].ensure(xbuf[k].size());
+            CK(cudaMemcpyAsync(ctx->d_xtex[k].p, xbuf[k].data(), xbuf[k].size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+            *xd[k] = TexDev{ctx->d_xtex[k].p, xt[k]->w, xt[k]->h};
+        }
+        d.normal_scale = m0.normal_scale; d.occlusion_strength = m0.occlusion_strength;
+        std::memcpy(d.nmat, nmat0, sizeof(nmat0));
+        d.wtbn = nullptr;
+        if (d.tex_normal.p) {
+            ctx->d_wtbn.ensure(wtbn.size());
+            CK(cudaMemcpyAsync(ctx->d_wtbn.p, wtbn.data(), wtbn.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+            d.wtbn = ctx->d_wtbn.p;
         }
         CK(cudaStreamSynchronize(ctx->stream));   // host vectors go out of scope
         d.wpos = ctx->d_wpos.p; d.wnrm = ctx->d_wnrm.p; d.uv = ctx->d_uv.p; d.idx = ctx->d_idx.p;
@@ -1557,7 +1592,7 @@ NMR_API int nmr_debug_last_frame(nmr_ctx* ctx, float* o_frame, float* o_depth, u
     });
 }
 
-NMR_API int nmr_debug_parse_gltf(const char* path, int64_t out_counts[5], char* err, size_t err_len) {
+NMR_API int nmr_debug_parse_gltf(const char* path, int64_t out_counts[5], char* err, size_t err_len, float* out_tangents, size_t tangent_capacity) {
     auto put = [&](const std::string& m) { if (err && err_len) { std::snprintf(err, err_len, "%s", m.c_str()); } };
     put("");
     if (!path) { put("path is null"); return NMR_ERR_INVALID; }
@@ -1568,6 +1603,7 @@ NMR_API int nmr_debug_parse_gltf(const char* path, int64_t out_counts[5], char* 
             out_counts[0] = (int64_t)(m.positions.size() / 3); out_counts[1] = (int64_t)(m.indices.size() / 3); out_counts[2] = lens;
             out_counts[3] = m.tex_w; out_counts[4] = m.tex_h;
         }
+        if (out_tangents) std::memcpy(out_tangents, m.tangents.data(), std::min(tangent_capacity, m.tangents.size()) * sizeof(float));
         // what nmr_load_mesh does next on the host: the arrays transform_mesh walks must cover every vertex
         std::vector<float> wp, wn;
         const float t[3] = {0.f, 0.f, 0.f}, sc[3] = {1.f, 1.f, 1.f}, q[4] = {0.f, 0.f, 0.f, 1.f};

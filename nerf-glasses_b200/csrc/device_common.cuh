@@ -41,16 +41,22 @@ struct DeviceModel {
     uint32_t n_brick;
 };
 
+struct TexDev { const float* p; int w, h; };     // [h][w][4] floats (sRGB textures already linearised), p == nullptr: no texture
 struct MeshDevice {
     const float* wpos;      // [n_verts][3] world space
     const float* wnrm;      // [n_verts][3]
     const float* uv;        // [n_verts][2]
     const uint32_t* idx;    // [n_tris][3]
-    const float* tex_lin;   // [h][w][4] linearised texture or nullptr
+    const float* tex_lin;   // [h][w][4] linearised base colour texture or nullptr
     const uint8_t* tri_lens; // [n_tris] 1 = lens surface (transmissive material), or nullptr when the scene has none / lenses are off
     uint32_t n_tris;
     int tex_w, tex_h;
     float base_color[4], emissive[3], metallic, roughness;
+    // the other textures of the reference's closest-hit program (S/optix/optix_scene.cu:234-258)
+    TexDev tex_emissive, tex_mr, tex_normal, tex_occ;
+    float normal_scale, occlusion_strength;
+    const float* wtbn;      // [n_verts][8]: M3 n_obj (3), M3 t_obj (3), tangent handedness, 0 - M3 = R S of the mesh; only with a normal texture
+    float nmat[9];          // normal matrix R S^-1 of the first mesh, row-major (applied once more to the mapped normal, like the reference)
 };
 
 struct FrameParams {
@@ -675,17 +681,19 @@ __device__ __forceinline__ bool ray_tri(V3 o, V3 d, V3 v0, V3 v1, V3 v2, float& 
     return true;
 }
 
-__device__ __forceinline__ void tex_sample(const MeshDevice& M, float u, float v, float out[4]) {
-    const float fx = u * (float)M.tex_w - 0.5f, fy = v * (float)M.tex_h - 0.5f;
+// bilinear, wrap addressing, normalised coordinates (cudaTextureDesc of S/cuda_texture.cu:19-27; float weights instead of the
+// texture unit's 8-bit ones)
+__device__ __forceinline__ void tex_sample(const float* __restrict__ tex, int tw, int th, float u, float v, float out[4]) {
+    const float fx = u * (float)tw - 0.5f, fy = v * (float)th - 0.5f;
     const float flx = floorf(fx), fly = floorf(fy);
     const float ax = fx - flx, ay = fy - fly;
     const int x0 = (int)flx, y0 = (int)fly;
-    const int xa = ((x0 % M.tex_w) + M.tex_w) % M.tex_w, xb = (((x0 + 1) % M.tex_w) + M.tex_w) % M.tex_w;
-    const int ya = ((y0 % M.tex_h) + M.tex_h) % M.tex_h, yb = (((y0 + 1) % M.tex_h) + M.tex_h) % M.tex_h;
+    const int xa = ((x0 % tw) + tw) % tw, xb = (((x0 + 1) % tw) + tw) % tw;
+    const int ya = ((y0 % th) + th) % th, yb = (((y0 + 1) % th) + th) % th;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const float t00 = __ldg(M.tex_lin + ((size_t)ya * M.tex_w + xa) * 4 + k), t10 = __ldg(M.tex_lin + ((size_t)ya * M.tex_w + xb) * 4 + k);
-        const float t01 = __ldg(M.tex_lin + ((size_t)yb * M.tex_w + xa) * 4 + k), t11 = __ldg(M.tex_lin + ((size_t)yb * M.tex_w + xb) * 4 + k);
+        const float t00 = __ldg(tex + ((size_t)ya * tw + xa) * 4 + k), t10 = __ldg(tex + ((size_t)ya * tw + xb) * 4 + k);
+        const float t01 = __ldg(tex + ((size_t)yb * tw + xa) * 4 + k), t11 = __ldg(tex + ((size_t)yb * tw + xb) * 4 + k);
         const float top = t00 * (1.0f - ax) + t10 * ax, bot = t01 * (1.0f - ax) + t11 * ax;
         out[k] = top * (1.0f - ay) + bot * ay;
     }
@@ -703,12 +711,33 @@ __device__ __forceinline__ void shade_hit(const MeshDevice& M, const FrameParams
     const float uvx = (bu * __ldg(M.uv + i1 * 2) + bv * __ldg(M.uv + i2 * 2)) + bw * __ldg(M.uv + i0 * 2);
     const float uvy = (bu * __ldg(M.uv + i1 * 2 + 1) + bv * __ldg(M.uv + i2 * 2 + 1)) + bw * __ldg(M.uv + i0 * 2 + 1);
     float base[4] = {M.base_color[0], M.base_color[1], M.base_color[2], M.base_color[3]};
-    if (M.tex_lin) { float tx[4]; tex_sample(M, uvx, uvy, tx); for (int k = 0; k < 4; ++k) base[k] *= tx[k]; }
-    const float metallic = M.metallic, roughness = M.roughness, occlusion = 1.0f;
+    if (M.tex_lin) { float tx[4]; tex_sample(M.tex_lin, M.tex_w, M.tex_h, uvx, uvy, tx); for (int k = 0; k < 4; ++k) base[k] *= tx[k]; }
+    float emissive[3] = {M.emissive[0], M.emissive[1], M.emissive[2]};
+    if (M.tex_emissive.p) { float tx[4]; tex_sample(M.tex_emissive.p, M.tex_emissive.w, M.tex_emissive.h, uvx, uvy, tx); for (int k = 0; k < 3; ++k) emissive[k] *= tx[k]; }
+    float metallic = M.metallic, roughness = M.roughness, occlusion = 1.0f;
+    if (M.tex_mr.p) { float tx[4]; tex_sample(M.tex_mr.p, M.tex_mr.w, M.tex_mr.h, uvx, uvy, tx); metallic *= tx[2]; roughness *= tx[1]; }   // B = metallic, G = roughness
+    if (M.tex_occ.p) { float tx[4]; tex_sample(M.tex_occ.p, M.tex_occ.w, M.tex_occ.h, uvx, uvy, tx); occlusion = 1.0f + M.occlusion_strength * (tx[0] - 1.0f); }
+    V3 normal = n;
+    if (M.tex_normal.p && M.wtbn) {
+        // computeTbnMatrix (S/optix/optix_scene.cu:92-98) of the interpolated normal / tangent under the mesh's matrix, the mapped
+        // normal, and then - like the reference - the object-to-world normal transform on top (S/optix/optix_scene.cu:252-258)
+        const float* a0 = M.wtbn + (size_t)i0 * 8; const float* a1 = M.wtbn + (size_t)i1 * 8; const float* a2 = M.wtbn + (size_t)i2 * 8;
+        float q[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) q[k] = (bu * __ldg(a1 + k) + bv * __ldg(a2 + k)) + bw * __ldg(a0 + k);
+        V3 tn = gnormalize(v3(q[3], q[4], q[5]));
+        const V3 nn = gnormalize(v3(q[0], q[1], q[2]));
+        tn = gnormalize(vsub(tn, vmul(nn, gdot(tn, nn))));
+        const V3 bn = vmul(vcross(nn, tn), q[6]);
+        float tx[4]; tex_sample(M.tex_normal.p, M.tex_normal.w, M.tex_normal.h, uvx, uvy, tx);
+        const float mx = (tx[0] * 2.0f - 1.0f) * M.normal_scale, my = (tx[1] * 2.0f - 1.0f) * M.normal_scale, mz = tx[2] * 2.0f - 1.0f;
+        const V3 m = vadd(vadd(vmul(tn, mx), vmul(bn, my)), vmul(nn, mz));
+        normal = v3((M.nmat[0] * m.x + M.nmat[1] * m.y) + M.nmat[2] * m.z, (M.nmat[3] * m.x + M.nmat[4] * m.y) + M.nmat[5] * m.z, (M.nmat[6] * m.x + M.nmat[7] * m.y) + M.nmat[8] * m.z);
+    }
     const V3 eye = v3(P.cam[9], P.cam[10], P.cam[11]);
     const V3 light = v3(P.light[0], P.light[1], P.light[2]);
     const V3 hitPos = vadd(eye, vmul(dir, hitT));
-    const V3 N = gnormalize(n);
+    const V3 N = gnormalize(normal);
     const V3 V = gnormalize(vsub(eye, hitPos));
     const V3 L = gnormalize(vsub(light, hitPos));
     const V3 H = gnormalize(vadd(V, L));
@@ -738,7 +767,7 @@ __device__ __forceinline__ void shade_hit(const MeshDevice& M, const FrameParams
     for (int k = 0; k < 3; ++k) {
         const float fd = (1.0f - metallic) * base[k] * dl;
         const float ambient = base[k] * .2f * occlusion;
-        float c = ambient + (fd + fr[k]) + M.emissive[k];
+        float c = ambient + (fd + fr[k]) + emissive[k];
         c = clampf(c, 0.f, 1.f);
         rgba[k] = to_srgb_mesh(c);
     }

@@ -389,6 +389,22 @@ HostMesh load_gltf(const std::string& path) {
     };
 
     HostMesh m;
+    // texture reference {"index": i} -> decoded RGBA8 image; an unusable image is reported and the factor alone is used
+    auto read_texture = [&](const Value& ref, const char* what) -> HostMesh::Texture {
+        HostMesh::Texture t;
+        try {
+            const Value& tex = elem("textures", ref.at("index").as_int());
+            const Value& img = elem("images", tex.at("source").as_int());
+            std::vector<uint8_t> bytes;
+            if (img.contains("uri")) bytes = load_uri(img.at("uri").as_string(), base_dir);
+            else { size_t st; auto vb = view_bytes(img.at("bufferView").as_int(), st); bytes.assign(vb.first, vb.first + vb.second); }
+            decode_png(bytes.data(), bytes.size(), t.w, t.h, t.rgba8);
+        } catch (const std::exception& e) {
+            t = HostMesh::Texture{};
+            m.warning += (m.warning.empty() ? "" : "; ") + std::string(what) + " texture unusable (" + e.what() + "), using the factor only";
+        }
+        return t;
+    };
     const size_t scene_idx = nonneg(doc.value_int("scene", 0), "scene index");
     if (!doc.contains("scenes") || scene_idx >= doc.at("scenes").size()) throw std::runtime_error("gltf: no default scene");
     const Value& scene_nodes = doc.at("scenes").at(scene_idx).at("nodes");
@@ -397,7 +413,7 @@ HostMesh load_gltf(const std::string& path) {
     // depth-first over the scene like GltfScene::getMeshPrimitives; child transforms are ignored as in the reference
     std::vector<int64_t> stack;
     for (size_t i = scene_nodes.size(); i-- > 0;) stack.push_back(scene_nodes.at(i).as_int());
-    bool missing_normals = false;
+    bool missing_normals = false, missing_tangents = false;
     // a node is visited once: a child list that leads back to an ancestor (or a node shared by two parents) is not a tree
     std::vector<uint8_t> visited(doc.contains("nodes") ? doc.at("nodes").size() : 0, 0);
     while (!stack.empty()) {
@@ -420,6 +436,8 @@ HostMesh load_gltf(const std::string& path) {
             else { m.normals.resize(m.normals.size() + nv * 3, 0.f); missing_normals = true; }
             if (attrs.contains("TEXCOORD_0")) { if (read_accessor_f32(attrs.at("TEXCOORD_0").as_int(), 2, m.texcoords) != nv) throw std::runtime_error("gltf: TEXCOORD_0 count differs from POSITION count"); }
             else m.texcoords.resize(m.texcoords.size() + nv * 2, 0.f);
+            if (attrs.contains("TANGENT")) { if (read_accessor_f32(attrs.at("TANGENT").as_int(), 4, m.tangents) != nv) throw std::runtime_error("gltf: TANGENT count differs from POSITION count"); }
+            else { m.tangents.resize(m.tangents.size() + nv * 4, 0.f); missing_tangents = true; }
             if (prim.contains("indices")) read_indices(prim.at("indices").as_int(), base, m.indices);
             else for (uint32_t i = 0; i < (uint32_t)nv; ++i) m.indices.push_back(base + i);
             {   // lens material?  (flags cover every triangle appended so far)
@@ -455,18 +473,19 @@ HostMesh load_gltf(const std::string& path) {
                     m.metallic = (float)pbr.value("metallicFactor", 1.0);
                     m.roughness = (float)pbr.value("roughnessFactor", 1.0);
                     if (pbr.contains("baseColorTexture")) {
-                        try {
-                            const Value& tex = doc.at("textures").at((size_t)pbr.at("baseColorTexture").at("index").as_int());
-                            const Value& img = doc.at("images").at((size_t)tex.at("source").as_int());
-                            std::vector<uint8_t> bytes;
-                            if (img.contains("uri")) bytes = load_uri(img.at("uri").as_string(), base_dir);
-                            else { size_t st; auto vb = view_bytes(img.at("bufferView").as_int(), st); bytes.assign(vb.first, vb.first + vb.second); }
-                            decode_png(bytes.data(), bytes.size(), m.tex_w, m.tex_h, m.tex_rgba8);
-                        } catch (const std::exception& e) {
-                            m.tex_w = m.tex_h = 0; m.tex_rgba8.clear();
-                            m.warning = std::string("base colour texture unusable (") + e.what() + "), using baseColorFactor only";
-                        }
+                        HostMesh::Texture t = read_texture(pbr.at("baseColorTexture"), "base colour");
+                        m.tex_w = t.w; m.tex_h = t.h; m.tex_rgba8 = std::move(t.rgba8);
                     }
+                    if (pbr.contains("metallicRoughnessTexture")) m.tex_metallic_roughness = read_texture(pbr.at("metallicRoughnessTexture"), "metallic-roughness");
+                }
+                if (mat.contains("emissiveTexture")) m.tex_emissive = read_texture(mat.at("emissiveTexture"), "emissive");
+                if (mat.contains("normalTexture")) {
+                    m.tex_normal = read_texture(mat.at("normalTexture"), "normal");
+                    m.normal_scale = (float)mat.at("normalTexture").value("scale", 1.0);
+                }
+                if (mat.contains("occlusionTexture")) {
+                    m.tex_occlusion = read_texture(mat.at("occlusionTexture"), "occlusion");
+                    m.occlusion_strength = (float)mat.at("occlusionTexture").value("strength", 1.0);
                 }
             }
         }
@@ -488,6 +507,44 @@ HostMesh load_gltf(const std::string& path) {
         for (uint32_t v = 0; v < nverts; ++v) {
             float* n = &m.normals[v * 3];
             if (n[0] == 0.f && n[1] == 0.f && n[2] == 0.f) { n[0] = acc[v * 3]; n[1] = acc[v * 3 + 1]; n[2] = acc[v * 3 + 2]; }
+        }
+    }
+    if (missing_tangents) {
+        // per-triangle tangent / bitangent from the UV derivatives, accumulated per vertex; then orthogonalised against the normal
+        const size_t nv = nverts;
+        std::vector<float> tacc(nv * 3, 0.f), bacc(nv * 3, 0.f);
+        for (size_t t = 0; t + 2 < m.indices.size(); t += 3) {
+            const uint32_t i0 = m.indices[t], i1 = m.indices[t + 1], i2 = m.indices[t + 2];
+            const float* p0 = &m.positions[i0 * 3]; const float* p1 = &m.positions[i1 * 3]; const float* p2 = &m.positions[i2 * 3];
+            const float* u0 = &m.texcoords[i0 * 2]; const float* u1 = &m.texcoords[i1 * 2]; const float* u2 = &m.texcoords[i2 * 2];
+            const float e1[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]}, e2[3] = {p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2]};
+            const float du1 = u1[0] - u0[0], dv1 = u1[1] - u0[1], du2 = u2[0] - u0[0], dv2 = u2[1] - u0[1];
+            const float det = du1 * dv2 - du2 * dv1;
+            if (!(std::fabs(det) > 1e-20f)) continue;
+            const float r = 1.0f / det;
+            for (int k = 0; k < 3; ++k) {
+                const float tk = (e1[k] * dv2 - e2[k] * dv1) * r, bk = (e2[k] * du1 - e1[k] * du2) * r;
+                for (uint32_t v : {i0, i1, i2}) { tacc[v * 3 + k] += tk; bacc[v * 3 + k] += bk; }
+            }
+        }
+        for (size_t v = 0; v < nv; ++v) {
+            float* out = &m.tangents[v * 4];
+            if (out[0] != 0.f || out[1] != 0.f || out[2] != 0.f || out[3] != 0.f) continue;      // this primitive had a TANGENT attribute
+            const float* n = &m.normals[v * 3];
+            const float nl = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+            const float nn[3] = {nl > 0 ? n[0] / nl : 0.f, nl > 0 ? n[1] / nl : 0.f, nl > 0 ? n[2] / nl : 1.f};
+            const float d = nn[0] * tacc[v * 3] + nn[1] * tacc[v * 3 + 1] + nn[2] * tacc[v * 3 + 2];
+            float tv[3] = {tacc[v * 3] - nn[0] * d, tacc[v * 3 + 1] - nn[1] * d, tacc[v * 3 + 2] - nn[2] * d};
+            float tl = std::sqrt(tv[0] * tv[0] + tv[1] * tv[1] + tv[2] * tv[2]);
+            if (!(tl > 1e-20f)) {      // no usable UV derivative: any unit vector perpendicular to the normal
+                const float ax[3] = {std::fabs(nn[0]) < 0.9f ? 1.f : 0.f, std::fabs(nn[0]) < 0.9f ? 0.f : 1.f, 0.f};
+                const float dd = nn[0] * ax[0] + nn[1] * ax[1] + nn[2] * ax[2];
+                tv[0] = ax[0] - nn[0] * dd; tv[1] = ax[1] - nn[1] * dd; tv[2] = ax[2] - nn[2] * dd;
+                tl = std::sqrt(tv[0] * tv[0] + tv[1] * tv[1] + tv[2] * tv[2]);
+            }
+            out[0] = tv[0] / tl; out[1] = tv[1] / tl; out[2] = tv[2] / tl;
+            const float c[3] = {nn[1] * out[2] - nn[2] * out[1], nn[2] * out[0] - nn[0] * out[2], nn[0] * out[1] - nn[1] * out[0]};
+            out[3] = (c[0] * bacc[v * 3] + c[1] * bacc[v * 3 + 1] + c[2] * bacc[v * 3 + 2]) < 0.f ? -1.f : 1.f;
         }
     }
     // node 0 TRS (GltfLoader::traverse, S/gltf_scene.cpp:63-118); matrix-form nodes are not decomposed (load_mesh overwrites TRS anyway)
@@ -517,6 +574,29 @@ void transform_mesh(const HostMesh& m, const float t[3], const float s[3], const
         wn[i * 3 + 0] = (R[0] * nx + R[1] * ny) + R[2] * nz;
         wn[i * 3 + 1] = (R[3] * nx + R[4] * ny) + R[5] * nz;
         wn[i * 3 + 2] = (R[6] * nx + R[7] * ny) + R[8] * nz;
+    }
+}
+
+void transform_tangent_frames(const HostMesh& m, const float s[3], const float q[4], std::vector<float>& wtbn, float nmat[9]) {
+    const float qw = q[0], qx = q[1], qy = q[2], qz = q[3];
+    const float qxx = qx * qx, qyy = qy * qy, qzz = qz * qz, qxz = qx * qz, qxy = qx * qy, qyz = qy * qz, qwx = qw * qx, qwy = qw * qy, qwz = qw * qz;
+    const float R[9] = {
+        1.f - 2.f * (qyy + qzz), 2.f * (qxy - qwz), 2.f * (qxz + qwy),
+        2.f * (qxy + qwz), 1.f - 2.f * (qxx + qzz), 2.f * (qyz - qwx),
+        2.f * (qxz - qwy), 2.f * (qyz + qwx), 1.f - 2.f * (qxx + qyy)};
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) nmat[i * 3 + j] = R[i * 3 + j] / s[j];
+    const size_t nv = m.positions.size() / 3;
+    wtbn.assign(nv * 8, 0.f);
+    if (m.tangents.size() < nv * 4) return;
+    for (size_t i = 0; i < nv; ++i) {
+        const float nx = m.normals[i * 3] * s[0], ny = m.normals[i * 3 + 1] * s[1], nz = m.normals[i * 3 + 2] * s[2];
+        const float tx = m.tangents[i * 4] * s[0], ty = m.tangents[i * 4 + 1] * s[1], tz = m.tangents[i * 4 + 2] * s[2];
+        float* o = &wtbn[i * 8];
+        for (int k = 0; k < 3; ++k) {
+            o[k] = (R[k * 3] * nx + R[k * 3 + 1] * ny) + R[k * 3 + 2] * nz;
+            o[3 + k] = (R[k * 3] * tx + R[k * 3 + 1] * ty) + R[k * 3 + 2] * tz;
+        }
+        o[6] = m.tangents[i * 4 + 3];
     }
 }
 

@@ -59,6 +59,15 @@ struct HostMesh {
     float metallic = 1.f, roughness = 1.f;
     int tex_w = 0, tex_h = 0;
     std::vector<uint8_t> tex_rgba8;  // base colour texture (sRGB), row-major, may be empty
+    // the other textures of the reference's closest-hit program (S/optix/optix_scene.cu:234-258; S/gltf_scene.cpp:160-215):
+    // emissive (sRGB), metallicRoughness (linear; G = roughness, B = metallic), normal (linear, tangent space), occlusion (linear, R)
+    struct Texture { int w = 0, h = 0; std::vector<uint8_t> rgba8; };
+    Texture tex_emissive, tex_metallic_roughness, tex_normal, tex_occlusion;
+    float normal_scale = 1.f, occlusion_strength = 1.f;
+    // per-vertex tangents (xyz + handedness w): the file's TANGENT attribute, else generated from the UV derivatives
+    // (per-triangle tangents accumulated per vertex, Gram-Schmidt against the normal; the reference runs MikkTSpace here,
+    // S/gltf_mikktspace_handler.cpp, whose seam splitting and angle weighting are not reproduced)
+    std::vector<float> tangents;
     // node 0 TRS as loaded from the file (overwritten by load_mesh's t/s/r, S/nerf_mesh_renderer.cu:952-954)
     float t[3] = {0, 0, 0}, s[3] = {1, 1, 1}, r_wxyz[4] = {1, 0, 0, 0};
     std::string warning;            // e.g. "texture could not be decoded, using constant colour"
@@ -81,6 +90,9 @@ void decode_png(const uint8_t* data, size_t size, int& w, int& h, std::vector<ui
 // world-space vertices / normals for T*R*S (S/gltf_scene.h:122-127): out arrays sized like the inputs
 void transform_mesh(const HostMesh& m, const float t[3], const float s[3], const float r_wxyz[4],
                     std::vector<float>& world_pos, std::vector<float>& world_nrm);
+// what the normal map's TBN matrix needs (computeTbnMatrix, S/optix/optix_scene.cu:92-98): per vertex M3 n, M3 t (M3 = R S) and
+// the tangent's handedness, 8 floats each; and the normal matrix R S^-1 (row-major)
+void transform_tangent_frames(const HostMesh& m, const float s[3], const float r_wxyz[4], std::vector<float>& wtbn, float nmat[9]);
 
 // The NerfMeshRenderer camera (S/nerf_mesh_renderer.cuh:88-95; S/orbit_camera.h; flythrough_camera.h)
 struct OrbitCamera {

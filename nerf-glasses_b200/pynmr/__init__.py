@@ -81,7 +81,7 @@ def lib():
         "nmr_render_views": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp]),
         "nmr_render_format": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
         "nmr_render_views_format": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
-        "nmr_debug_parse_gltf": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64), C.c_char_p, C.c_size_t]),
+        "nmr_debug_parse_gltf": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64), C.c_char_p, C.c_size_t, vp, C.c_size_t]),
         "nmr_set_shard": (C.c_int, [vp, C.c_int, C.c_int, C.c_int]),
         "nmr_set_surface_insertion": (C.c_int, [vp, C.c_int]),
         "nmr_set_overlap": (C.c_int, [vp, C.c_int]),
@@ -152,15 +152,20 @@ def _pixel_format(dtype) -> int:
     raise ValueError(f"unsupported image dtype {dt}: float32, float16 or uint8")
 
 
-def parse_gltf(path: str) -> dict:
+def parse_gltf(path: str, tangents: bool = False) -> dict:
     """Host-only check of a .gltf / .glb through the loader behind load_mesh (no GPU needed).  Raises RuntimeError with the loader's
     message on malformed input."""
     counts = (C.c_int64 * 5)()
     err = C.create_string_buffer(512)
-    rc = lib().nmr_debug_parse_gltf(os.fsencode(path), counts, err, len(err))
+    rc = lib().nmr_debug_parse_gltf(os.fsencode(path), counts, err, len(err), None, 0)
     if rc != NMR_OK:
         raise RuntimeError(f"libnmr error {rc}: {err.value.decode(errors='replace')}")
-    return {"vertices": counts[0], "triangles": counts[1], "lens_triangles": counts[2], "texture": (counts[3], counts[4]), "warning": err.value.decode(errors="replace")}
+    out = {"vertices": counts[0], "triangles": counts[1], "lens_triangles": counts[2], "texture": (counts[3], counts[4]), "warning": err.value.decode(errors="replace")}
+    if tangents:
+        t = np.zeros((counts[0], 4), dtype=np.float32)
+        lib().nmr_debug_parse_gltf(os.fsencode(path), counts, err, len(err), _ptr(t), t.size)
+        out["tangents"] = t
+    return out
 
 
 def _f3(v):

@@ -1240,6 +1240,12 @@ typedef struct {
     int tex_w, tex_h;
     float* tex_lin;    /* [h][w][4] linearised sRGB texture (alpha linear) or NULL */
     uint8_t* tri_lens;   /* per triangle: 1 = lens surface (NULL: none) */
+    /* the other textures of __closesthit__ch (S/optix/optix_scene.cu:234-258): [0] emissive (sRGB), [1] metallicRoughness,
+     * [2] normal, [3] occlusion (all linear); tangents as M3 t_obj / M3 n_obj with M3 = R S, and the normal matrix R S^-1 */
+    float* xtex[4]; int xtex_w[4], xtex_h[4];
+    float normal_scale, occlusion_strength;
+    float* wtbn;       /* [n_verts][8]: M3 n (3), M3 t (3), tangent.w, 0; NULL without tangents */
+    float nmat[9];
 } orc_mesh;
 
 /* r_wxyz: the (w,x,y,z) quaternion NerfMeshRenderer::loadMesh builds from its Vector4f argument
@@ -1279,11 +1285,51 @@ ORC_API orc_mesh* orc_mesh_create(const float* pos, const float* nrm, const floa
     }
     return M;
 }
-ORC_API void orc_mesh_destroy(orc_mesh* M) { if (!M) return; free(M->wpos); free(M->wnrm); free(M->uv); free(M->idx); free(M->tex_lin); free(M->tri_lens); free(M); }
+ORC_API void orc_mesh_destroy(orc_mesh* M) {
+    if (!M) return;
+    free(M->wpos); free(M->wnrm); free(M->uv); free(M->idx); free(M->tex_lin); free(M->tri_lens); free(M->wtbn);
+    for (int k = 0; k < 4; ++k) free(M->xtex[k]);
+    free(M);
+}
+/* which: 0 emissive (sRGB-decoded like CudaTexture's bSrgb, S/gltf_scene.cpp:179), 1 metallicRoughness, 2 normal, 3 occlusion
+ * (linear, :196-211).  factor: normalTexture.scale / occlusionTexture.strength for 2 / 3, ignored otherwise. */
+ORC_API void orc_mesh_set_texture(orc_mesh* M, int which, const uint8_t* rgba8, int w, int h, float factor) {
+    if (which < 0 || which > 3) return;
+    free(M->xtex[which]); M->xtex[which] = NULL; M->xtex_w[which] = M->xtex_h[which] = 0;
+    if (which == 2) M->normal_scale = factor;
+    if (which == 3) M->occlusion_strength = factor;
+    if (!rgba8 || w <= 0 || h <= 0) return;
+    float* t = (float*)malloc(sizeof(float) * 4 * (size_t)w * h);
+    for (size_t i = 0; i < (size_t)w * h; ++i) {
+        for (int k = 0; k < 3; ++k) { float sv = (float)rgba8[i * 4 + k] / 255.0f; t[i * 4 + k] = which == 0 ? srgb_to_linear(sv) : sv; }
+        t[i * 4 + 3] = (float)rgba8[i * 4 + 3] / 255.0f;
+    }
+    M->xtex[which] = t; M->xtex_w[which] = w; M->xtex_h[which] = h;
+}
+/* object-space normals and tangents (xyz + handedness) + the mesh transform: what computeTbnMatrix needs */
+ORC_API void orc_mesh_set_tangents(orc_mesh* M, const float* nrm_obj, const float* tan4_obj, const float* s, const float* r_wxyz) {
+    free(M->wtbn); M->wtbn = NULL;
+    float qw = r_wxyz[0], qx = r_wxyz[1], qy = r_wxyz[2], qz = r_wxyz[3];
+    float qxx = qx * qx, qyy = qy * qy, qzz = qz * qz, qxz = qx * qz, qxy = qx * qy, qyz = qy * qz, qwx = qw * qx, qwy = qw * qy, qwz = qw * qz;
+    float R[9] = { 1.f - 2.f * (qyy + qzz), 2.f * (qxy - qwz), 2.f * (qxz + qwy), 2.f * (qxy + qwz), 1.f - 2.f * (qxx + qzz), 2.f * (qyz - qwx),
+                   2.f * (qxz - qwy), 2.f * (qyz + qwx), 1.f - 2.f * (qxx + qyy) };
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) M->nmat[i * 3 + j] = R[i * 3 + j] / s[j];
+    if (!tan4_obj) return;
+    M->wtbn = (float*)malloc(sizeof(float) * 8 * M->n_verts);
+    for (uint32_t i = 0; i < M->n_verts; ++i) {
+        v3 n = glm_mat3_mul(R, v3_make(nrm_obj[i * 3] * s[0], nrm_obj[i * 3 + 1] * s[1], nrm_obj[i * 3 + 2] * s[2]));
+        v3 t = glm_mat3_mul(R, v3_make(tan4_obj[i * 4] * s[0], tan4_obj[i * 4 + 1] * s[1], tan4_obj[i * 4 + 2] * s[2]));
+        float* o = M->wtbn + (size_t)i * 8;
+        o[0] = n.x; o[1] = n.y; o[2] = n.z; o[3] = t.x; o[4] = t.y; o[5] = t.z; o[6] = tan4_obj[i * 4 + 3]; o[7] = 0.f;
+    }
+}
 ORC_API void orc_mesh_world_positions(const orc_mesh* M, float* out) { memcpy(out, M->wpos, sizeof(v3) * M->n_verts); }
 
 /* bilinear, wrap addressing, normalised coordinates, texel centres at +0.5 (S/cuda_texture.cu:22-28) */
-static void tex_sample(const orc_mesh* M, float u, float v, float out[4]) {
+static void tex_sample_any(const float* tex, int tw, int th, float u, float v, float out[4]);
+static void tex_sample(const orc_mesh* M, float u, float v, float out[4]) { tex_sample_any(M->tex_lin, M->tex_w, M->tex_h, u, v, out); }
+static void tex_sample_any(const float* tex, int tw, int th, float u, float v, float out[4]) {
+    struct { int tex_w, tex_h; const float* tex_lin; } Ms = { tw, th, tex }, *M = &Ms;
     float fx = u * (float)M->tex_w - 0.5f, fy = v * (float)M->tex_h - 0.5f;
     float flx = floorf(fx), fly = floorf(fy);
     float ax = fx - flx, ay = fy - fly;
@@ -1331,7 +1377,26 @@ static void shade_hit(const orc_mesh* M, uint32_t tri, float bu, float bv, float
     float uvy = (bu * M->uv[i1 * 2 + 1] + bv * M->uv[i2 * 2 + 1]) + bw * M->uv[i0 * 2 + 1];
     float base[4] = { M->base_color[0], M->base_color[1], M->base_color[2], M->base_color[3] };
     if (M->tex_lin) { float tx[4]; tex_sample(M, uvx, uvy, tx); for (int k = 0; k < 4; ++k) base[k] *= tx[k]; }
-    const float metallic = M->metallic, roughness = M->roughness, occlusion = 1.0f;
+    float metallic = M->metallic, roughness = M->roughness, occlusion = 1.0f;
+    float emissive[3] = { M->emissive[0], M->emissive[1], M->emissive[2] };
+    if (M->xtex[0]) { float tx[4]; tex_sample_any(M->xtex[0], M->xtex_w[0], M->xtex_h[0], uvx, uvy, tx); for (int k = 0; k < 3; ++k) emissive[k] *= tx[k]; }
+    if (M->xtex[1]) { float tx[4]; tex_sample_any(M->xtex[1], M->xtex_w[1], M->xtex_h[1], uvx, uvy, tx); metallic *= tx[2]; roughness *= tx[1]; }
+    if (M->xtex[3]) { float tx[4]; tex_sample_any(M->xtex[3], M->xtex_w[3], M->xtex_h[3], uvx, uvy, tx); occlusion = 1.0f + M->occlusion_strength * (tx[0] - 1.0f); }
+    if (M->xtex[2] && M->wtbn) {
+        /* computeTbnMatrix (S/optix/optix_scene.cu:92-98), the mapped normal (:245-251), then the object-to-world normal
+         * transform once more, as the reference applies it to the already transformed vector (:252) */
+        const float* a0 = M->wtbn + (size_t)i0 * 8; const float* a1 = M->wtbn + (size_t)i1 * 8; const float* a2 = M->wtbn + (size_t)i2 * 8;
+        float q[7];
+        for (int k = 0; k < 7; ++k) q[k] = (bu * a1[k] + bv * a2[k]) + bw * a0[k];
+        v3 tn = glm_normalize3(v3_make(q[3], q[4], q[5]));
+        v3 nn = glm_normalize3(v3_make(q[0], q[1], q[2]));
+        tn = glm_normalize3(sub3(tn, mul3(nn, dot3(tn, nn))));
+        v3 bn = mul3(cross3(nn, tn), q[6]);
+        float tx[4]; tex_sample_any(M->xtex[2], M->xtex_w[2], M->xtex_h[2], uvx, uvy, tx);
+        float mx = (tx[0] * 2.0f - 1.0f) * M->normal_scale, my = (tx[1] * 2.0f - 1.0f) * M->normal_scale, mz = tx[2] * 2.0f - 1.0f;
+        v3 mm = add3(add3(mul3(tn, mx), mul3(bn, my)), mul3(nn, mz));
+        n = glm_mat3_mul(M->nmat, mm);
+    }
     v3 hitPos = add3(eye, mul3(dir, hitT));
     v3 N = glm_normalize3(n);
     v3 V = glm_normalize3(sub3(eye, hitPos));
@@ -1361,7 +1426,7 @@ static void shade_hit(const orc_mesh* M, uint32_t tri, float bu, float bv, float
     }
     for (int k = 0; k < 3; ++k) {
         float ambient = base[k] * .2f * occlusion;
-        float c = ambient + (fd[k] + fr[k]) + M->emissive[k];
+        float c = ambient + (fd[k] + fr[k]) + emissive[k];
         c = clampf(c, 0.f, 1.f);
         rgba[k] = to_srgb_optix(c);
     }

@@ -81,6 +81,8 @@ def lib():
         "orc_trace_samples": (None, [vp, C.POINTER(RenderParams), vp, C.c_int64, C.c_uint32, vp, vp, vp, vp, vp, vp]),
         "orc_mesh_create": (vp, [vp, vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp, vp, vp, C.c_float, C.c_float, vp, vp, C.c_int, C.c_int]),
         "orc_mesh_destroy": (None, [vp]),
+        "orc_mesh_set_texture": (None, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_float]),
+        "orc_mesh_set_tangents": (None, [vp, vp, vp, vp, vp]),
         "orc_mesh_world_positions": (None, [vp, vp]),
         "orc_mesh_render": (None, [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp]),
         "orc_mesh_resolve": (None, [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),
@@ -318,6 +320,22 @@ class Mesh:
                 self.h = None
         except Exception:
             pass
+
+    TEXTURES = {"emissive": 0, "metallic_roughness": 1, "normal": 2, "occlusion": 3}
+
+    def set_texture(self, which: str, rgba8, factor: float = 1.0):
+        """The other textures of the reference's closest-hit program; factor = normalTexture.scale / occlusionTexture.strength."""
+        if rgba8 is None:
+            lib().orc_mesh_set_texture(self.h, self.TEXTURES[which], None, 0, 0, float(factor))
+        else:
+            t = np.ascontiguousarray(rgba8, dtype=np.uint8)
+            lib().orc_mesh_set_texture(self.h, self.TEXTURES[which], _p(t), t.shape[1], t.shape[0], float(factor))
+
+    def set_tangents(self, normals_obj, tangents4_obj, s, r_wxyz):
+        """Object-space normals / tangents (xyz + handedness) and the mesh's scale / rotation, for the normal map's TBN matrix."""
+        n = np.ascontiguousarray(normals_obj, dtype=np.float32); t = np.ascontiguousarray(tangents4_obj, dtype=np.float32)
+        ss = np.asarray(s, dtype=np.float32); rr = np.asarray(r_wxyz, dtype=np.float32)
+        lib().orc_mesh_set_tangents(self.h, _p(n), _p(t), _p(ss), _p(rr))
 
     def set_lens(self, tri_lens):
         """Per-triangle lens flags (uint8) or None."""

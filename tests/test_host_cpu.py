@@ -280,3 +280,23 @@ def test_png_palette_index_is_bounds_checked(tmp_path):
     for pal, idx in ((bytes([10, 20, 30, 40, 50]), 1), (bytes([10, 20, 30]), 1), (bytes([10, 20]), 0)):       # k*3+2 == size, > size
         bad = pynmr.parse_gltf(_tiny_gltf(tmp_path, with_texture(png(pal, idx)), "bad.gltf"))
         assert bad["texture"] == (0, 0) and "palette" in bad["warning"]
+
+
+def test_gltf_loader_tangents_and_texture_slots(tmp_path):
+    """Every texture slot of the reference's closest-hit program is read (S/optix/optix_scene.cu:221-258), a TANGENT attribute is
+    taken as is, and a file without one gets tangents from its UV derivatives - equal to the numpy restatement in tools/synth.py."""
+    import pynmr
+    import synth
+    with_t = synth.write_textured_glasses_gltf(str(tmp_path / "a"), with_tangents=True)
+    without = synth.write_textured_glasses_gltf(str(tmp_path / "b"), with_tangents=False)
+    g = synth.read_gltf(with_t)
+    a = pynmr.parse_gltf(with_t, tangents=True)
+    b = pynmr.parse_gltf(without, tangents=True)
+    assert a["warning"] == "" and b["warning"] == "" and a["texture"] == (16, 16)
+    assert np.array_equal(a["tangents"], g["tangents"])                    # read verbatim
+    want = synth.np_tangents(g["positions"], g["normals"], g["texcoords"], g["indices"])
+    assert np.array_equal(b["tangents"][:, 3], want[:, 3])                 # handedness
+    assert float(np.abs(b["tangents"][:, :3] - want[:, :3]).max()) <= 2e-5  # same algorithm, float rounding of the sums apart
+    n = g["normals"] / np.linalg.norm(g["normals"], axis=1, keepdims=True)
+    assert float(np.abs(np.einsum("ij,ij->i", b["tangents"][:, :3], n)).max()) <= 1e-4      # perpendicular to the normal, unit length
+    assert float(np.abs(np.linalg.norm(b["tangents"][:, :3], axis=1) - 1).max()) <= 1e-5

@@ -558,6 +558,124 @@ def write_lens_glasses_gltf(out_dir: str, texture_rgba=(128, 128, 128, 255), npz
     return path
 
 
+def np_tangents(pos: np.ndarray, nrm: np.ndarray, uv: np.ndarray, idx: np.ndarray) -> np.ndarray:
+    """Per-vertex tangents (xyz + handedness) from the UV derivatives: per-triangle tangent / bitangent accumulated per vertex, then
+    Gram-Schmidt against the normal - the numpy restatement of what the C++ loader generates when a file has no TANGENT attribute
+    (csrc/host.cpp; the reference runs MikkTSpace there)."""
+    pos = pos.astype(np.float32); nrm = nrm.astype(np.float32); uv = uv.astype(np.float32)
+    tri = idx.reshape(-1, 3).astype(np.int64)
+    tacc = np.zeros_like(pos); bacc = np.zeros_like(pos)
+    for i0, i1, i2 in tri:
+        e1, e2 = pos[i1] - pos[i0], pos[i2] - pos[i0]
+        du1, dv1 = uv[i1] - uv[i0]; du2, dv2 = uv[i2] - uv[i0]
+        det = np.float32(du1 * dv2 - du2 * dv1)
+        if not abs(det) > 1e-20:
+            continue
+        r = np.float32(1.0) / det
+        t = (e1 * dv2 - e2 * dv1) * r; b = (e2 * du1 - e1 * du2) * r
+        for v in (i0, i1, i2):
+            tacc[v] += t; bacc[v] += b
+    out = np.zeros((pos.shape[0], 4), dtype=np.float32)
+    for v in range(pos.shape[0]):
+        n = nrm[v]; nl = np.sqrt(np.float32(n @ n))
+        nn = n / nl if nl > 0 else np.array([0, 0, 1], np.float32)
+        tv = tacc[v] - nn * np.float32(nn @ tacc[v]); tl = np.sqrt(np.float32(tv @ tv))
+        if not tl > 1e-20:
+            ax = np.array([1, 0, 0], np.float32) if abs(nn[0]) < 0.9 else np.array([0, 1, 0], np.float32)
+            tv = ax - nn * np.float32(nn @ ax); tl = np.sqrt(np.float32(tv @ tv))
+        t = tv / tl
+        out[v, :3] = t
+        out[v, 3] = -1.0 if np.cross(nn, t) @ bacc[v] < 0 else 1.0
+    return out
+
+
+def _test_texture(kind: str, n: int = 16) -> np.ndarray:
+    """Small procedural RGBA8 textures of the textured fixture (deterministic)."""
+    y, x = np.mgrid[0:n, 0:n].astype(np.float32) / (n - 1)
+    if kind == "base":
+        rgb = np.stack([0.35 + 0.6 * x, 0.3 + 0.5 * y, 0.8 - 0.5 * x * y], -1)
+    elif kind == "emissive":
+        rgb = np.stack([0.4 * (1 - x), 0.15 + 0.2 * y, 0.5 * x * (1 - y)], -1)
+    elif kind == "metallic_roughness":
+        rgb = np.stack([np.zeros_like(x), 0.25 + 0.7 * y, 0.2 + 0.75 * x], -1)          # G roughness, B metallic
+    elif kind == "normal":
+        nx, ny = 0.45 * np.sin(6.3 * x), 0.45 * np.cos(5.1 * y)
+        nz = np.sqrt(np.maximum(0.0, 1 - nx * nx - ny * ny))
+        rgb = np.stack([nx, ny, nz], -1) * 0.5 + 0.5
+    else:                                                                                # occlusion
+        rgb = np.stack([0.35 + 0.65 * (0.5 + 0.5 * np.sin(9 * x + 4 * y))] * 3, -1)
+    out = np.empty((n, n, 4), dtype=np.uint8)
+    out[..., :3] = np.clip(np.round(rgb * 255), 0, 255).astype(np.uint8); out[..., 3] = 255
+    return out
+
+
+def write_textured_glasses_gltf(out_dir: str, with_tangents: bool = True, npz_path: str = GLASSES_NPZ) -> str:
+    """The glasses geometry with a material that uses every texture slot of the reference's closest-hit program (base colour,
+    emissive, metallic-roughness, normal with scale, occlusion with strength; S/optix/optix_scene.cu:221-258).  The reference asset
+    carries only a base colour texture; this fixture exercises the rest of the shader.  with_tangents: write a TANGENT attribute
+    (np_tangents) so that every reader works from the same tangents; False leaves their generation to the loader."""
+    m = np.load(npz_path)
+    pos, nrm, uv, idx = m["positions"], m["normals"], m["texcoords"], m["indices"]
+    os.makedirs(out_dir, exist_ok=True)
+    parts = [pos.astype("<f4").tobytes(), nrm.astype("<f4").tobytes(), uv.astype("<f4").tobytes(), idx.astype("<u2").tobytes()]
+    if len(parts[3]) % 4:
+        parts[3] += b"\0" * (4 - len(parts[3]) % 4)
+    if with_tangents:
+        parts.append(np_tangents(pos, nrm, uv, idx).astype("<f4").tobytes())
+    offs = np.cumsum([0] + [len(p) for p in parts])
+    with open(os.path.join(out_dir, "glasses.bin"), "wb") as f:
+        f.write(b"".join(parts))
+    kinds = ["base", "emissive", "metallic_roughness", "normal", "occlusion"]
+    for k in kinds:
+        with open(os.path.join(out_dir, f"{k}.png"), "wb") as f:
+            f.write(_png_bytes(_test_texture(k)))
+    attrs = {"POSITION": 0, "NORMAL": 1, "TEXCOORD_0": 2}
+    accessors = [
+        {"bufferView": 0, "componentType": 5126, "count": int(pos.shape[0]), "type": "VEC3", "max": [float(x) for x in pos.max(0)], "min": [float(x) for x in pos.min(0)]},
+        {"bufferView": 1, "componentType": 5126, "count": int(nrm.shape[0]), "type": "VEC3"},
+        {"bufferView": 2, "componentType": 5126, "count": int(uv.shape[0]), "type": "VEC2"},
+        {"bufferView": 3, "componentType": 5123, "count": int(idx.shape[0]), "type": "SCALAR"}]
+    views = [{"buffer": 0, "byteLength": len(parts[i]) if i != 3 else idx.nbytes, "byteOffset": int(offs[i]), "target": 34963 if i == 3 else 34962} for i in range(len(parts))]
+    if with_tangents:
+        attrs["TANGENT"] = 4
+        accessors.append({"bufferView": 4, "componentType": 5126, "count": int(pos.shape[0]), "type": "VEC4"})
+    doc = {
+        "asset": {"generator": "nmr-b200 fixture writer", "version": "2.0"}, "scene": 0, "scenes": [{"name": "Scene", "nodes": [0]}],
+        "nodes": [{"mesh": 0, "name": "Glasses.001", "rotation": [float(x) for x in m["node_rotation_xyzw"]], "translation": [float(x) for x in m["node_translation"]]}],
+        "materials": [{"doubleSided": True, "name": "textured",
+                       "emissiveFactor": [0.8, 0.9, 1.0], "emissiveTexture": {"index": 1},
+                       "normalTexture": {"index": 3, "scale": 0.8}, "occlusionTexture": {"index": 4, "strength": 0.7},
+                       "pbrMetallicRoughness": {"baseColorFactor": [0.9, 0.95, 1.0, 1.0], "baseColorTexture": {"index": 0}, "metallicFactor": 0.8,
+                                                "roughnessFactor": 0.9, "metallicRoughnessTexture": {"index": 2}}}],
+        "meshes": [{"name": "Glasses.001", "primitives": [{"attributes": attrs, "indices": 3, "material": 0}]}],
+        "textures": [{"sampler": 0, "source": i} for i in range(5)],
+        "images": [{"mimeType": "image/png", "name": k, "uri": f"{k}.png"} for k in kinds],
+        "accessors": accessors, "bufferViews": views,
+        "samplers": [{"magFilter": 9729, "minFilter": 9987}],
+        "buffers": [{"byteLength": int(offs[-1]), "uri": "glasses.bin"}],
+    }
+    path = os.path.join(out_dir, "glasses.gltf")
+    with open(path, "w") as f:
+        json.dump(doc, f, indent=1)
+    return path
+
+
+def _read_png_rgba8(path: str) -> np.ndarray:
+    """Reader for the PNGs _png_bytes writes (8-bit RGBA, filter type 0 on every row)."""
+    data = open(path, "rb").read()
+    p, idat, w, h = 8, b"", 0, 0
+    while p < len(data):
+        n = struct.unpack(">I", data[p:p + 4])[0]; tag = data[p + 4:p + 8]; body = data[p + 8:p + 8 + n]
+        if tag == b"IHDR":
+            w, h = struct.unpack(">II", body[:8])
+        elif tag == b"IDAT":
+            idat += body
+        p += 12 + n
+    raw = np.frombuffer(zlib.decompress(idat), dtype=np.uint8).reshape(h, 1 + 4 * w)
+    assert (raw[:, 0] == 0).all()
+    return raw[:, 1:].reshape(h, w, 4).copy()
+
+
 def read_gltf(path: str) -> dict:
     """Test-side glTF reader (json + numpy), independent of the C++ loader."""
     with open(path) as f:
@@ -575,8 +693,10 @@ def read_gltf(path: str) -> dict:
         return arr.reshape(a["count"], ncomp) if ncomp > 1 else arr
     node = doc["nodes"][doc["scenes"][doc.get("scene", 0)]["nodes"][0]]
     prims = doc["meshes"][node["mesh"]]["primitives"]
-    mat = doc["materials"][prims[0]["material"]]["pbrMetallicRoughness"]
+    mat0 = doc["materials"][prims[0]["material"]]
+    mat = mat0["pbrMetallicRoughness"]
     P, N, T, I, L = [], [], [], [], []
+    TG = []
     lens = None
     base = 0
     for prim in prims:      # concatenated like the C++ loader; material of the first primitive; lens flags per triangle
@@ -584,6 +704,7 @@ def read_gltf(path: str) -> dict:
         P.append(p); N.append(acc(prim["attributes"]["NORMAL"]).astype(np.float32)); T.append(acc(prim["attributes"]["TEXCOORD_0"]).astype(np.float32))
         i = acc(prim["indices"]).astype(np.int64) + base
         I.append(i); base += p.shape[0]
+        TG.append(acc(prim["attributes"]["TANGENT"]).astype(np.float32) if "TANGENT" in prim["attributes"] else None)
         md = doc["materials"][prim["material"]]
         ext = md.get("extensions", {})
         tf = float(ext.get("KHR_materials_transmission", {}).get("transmissionFactor", 0.0))
@@ -594,7 +715,18 @@ def read_gltf(path: str) -> dict:
         L.append(np.full(i.size // 3, 1 if is_lens else 0, dtype=np.uint8))
         if is_lens and lens is None:
             lens = {"ior": float(ext.get("KHR_materials_ior", {}).get("ior", 1.5)), "transmission": tf, "tint": np.array(bc[:3], dtype=np.float32)}
+    def tex(ref):
+        if ref is None:
+            return None
+        img = doc["images"][doc["textures"][ref["index"]]["source"]]
+        return _read_png_rgba8(os.path.join(os.path.dirname(os.path.abspath(path)), img["uri"]))
+    textures = {"emissive": tex(mat0.get("emissiveTexture")), "metallic_roughness": tex(mat.get("metallicRoughnessTexture")),
+                "normal": tex(mat0.get("normalTexture")), "occlusion": tex(mat0.get("occlusionTexture"))}
     return {
+        "tangents": np.concatenate(TG) if all(t is not None for t in TG) else None,
+        "textures": textures, "base_texture_ref": mat.get("baseColorTexture"),
+        "normal_scale": float(mat0.get("normalTexture", {}).get("scale", 1.0)), "occlusion_strength": float(mat0.get("occlusionTexture", {}).get("strength", 1.0)),
+        "emissive": np.array(mat0.get("emissiveFactor", [0, 0, 0]), dtype=np.float32),
         "positions": np.concatenate(P), "normals": np.concatenate(N), "texcoords": np.concatenate(T),
         "indices": np.concatenate(I).astype(np.uint16), "tri_lens": np.concatenate(L), "lens": lens,
         "base_color": np.array(mat.get("baseColorFactor", [1, 1, 1, 1]), dtype=np.float32),
