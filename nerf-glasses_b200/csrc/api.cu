@@ -142,6 +142,7 @@ struct nmr_ctx {
     int lens_enabled = 1;                                 // nmr_set_lens
     float lens_ior = 1.5f, lens_transmission = 1.f, lens_tint[3] = {1.f, 1.f, 1.f};
     bool lens_params_set = false;                         // nmr_set_lens gave explicit parameters
+    int lens_model = 0; float lens_thickness = 0.f;      // nmr_set_lens_model
     MeshDevice mesh_dev{};
     float mesh_wmin[3] = {0.f, 0.f, 0.f}, mesh_wmax[3] = {0.f, 0.f, 0.f};   // world-space box of the concatenated mesh
     Surfaces surf;
@@ -465,6 +466,7 @@ FrameParams make_params(nmr_ctx* ctx, const Nerf& n, int W, int H, const float* 
         P.lens_f0 = r0 * r0;
         for (int k = 0; k < 3; ++k) P.lens_k[k] = ctx->lens_transmission * ctx->lens_tint[k];
         P.lens_kmean = (P.lens_k[0] + P.lens_k[1] + P.lens_k[2]) / 3.f;
+        P.lens_model = ctx->lens_model; P.lens_thickness = ctx->lens_thickness; P.lens_ior = ctx->lens_ior;
     }
     return P;
 }
@@ -657,6 +659,8 @@ void destroy_lane(nmr_ctx* l) {
 void sync_lane(nmr_ctx* l, const nmr_ctx* parent) {
     l->mesh_dev = parent->mesh_dev; l->mesh_scale = parent->mesh_scale; l->debug_flags = parent->debug_flags;
     l->scene_has_lens = parent->scene_has_lens; l->surface_mode = parent->surface_mode; l->overlap = parent->overlap;
+    l->lens_enabled = parent->lens_enabled; l->lens_ior = parent->lens_ior; l->lens_transmission = parent->lens_transmission;
+    std::memcpy(l->lens_tint, parent->lens_tint, 12); l->lens_model = parent->lens_model; l->lens_thickness = parent->lens_thickness;
 }
 
 // frame() with more than one NeRF loaded (NerfMeshRenderer::render_frame, S/nerf_mesh_renderer.cu:561-597): every NeRF renders the
@@ -980,6 +984,14 @@ NMR_API int nmr_set_lens(nmr_ctx* ctx, int enabled, float ior, float transmissio
             if (tint) std::memcpy(ctx->lens_tint, tint, 12);
         }
         ctx->surf.spp = 0;
+        return NMR_OK;
+    });
+}
+
+NMR_API int nmr_set_lens_model(nmr_ctx* ctx, int model, float thickness) {
+    return guarded(ctx, [&]() -> int {
+        if (model < 0 || model > 1 || !(thickness >= 0.f)) return fail(ctx, NMR_ERR_INVALID, "lens model must be 0 (thin sheet) or 1 (plate) with a thickness >= 0");
+        ctx->lens_model = model; ctx->lens_thickness = thickness; ctx->surf.spp = 0;
         return NMR_OK;
     });
 }

@@ -91,6 +91,8 @@ struct FrameParams {
     // transmission * tint and its mean.  lens_on == 0: no lens triangles in this frame.
     int lens_on;
     float lens_f0, lens_k[3], lens_kmean;
+    int lens_model;                   // 0 thin sheet (no bending), 1 plate of lens_thickness with parallel faces (two-interface Snell)
+    float lens_thickness, lens_ior;
     int out_format;                   // PixelFormat of FrameOut::image (nmr_pixel_format of include/nmr.h)
     // Testbed::m_model_rotation / m_model_translation (S/ngp/testbed.cu:1537-1542, consumed at :442-446): ray direction = R d,
     // NeRF-space ray origin = R eye + 0.5 + R t_model (evaluated on the host, make_params).  The identity leaves eye + 0.5.

@@ -332,6 +332,23 @@ __device__ __forceinline__ float lens_fresnel(const FrameParams& P, V3 d, V3 n, 
     return P.lens_f0 + (1.0f - P.lens_f0) * (m2 * m2 * m);
 }
 
+// Lens model 1 ("plate", oracle: lens_plate_shift): a pane of thickness d with parallel faces.  The ray refracts into the glass at
+// the hit point (Snell, relative index 1 / ior), crosses it and leaves parallel to its old direction: the transmitted segment is the
+// primary ray shifted sideways by `delta`, resumed at t_behind.  Model 0: no shift.
+__device__ __forceinline__ void lens_plate_shift(const FrameParams& P, V3 dir, V3 n, float t_lens, V3& delta, float& t_behind) {
+    delta = v3(0.f, 0.f, 0.f); t_behind = t_lens;
+    if (P.lens_model != 1 || !(P.lens_thickness > 0.f)) return;
+    float c = gdot(dir, n);
+    if (c > 0.f) { n = vmul(n, -1.f); c = -c; }
+    const float cosi = fmaxf(fminf(-c, 1.0f), 0.05f);
+    const float eta = 1.0f / P.lens_ior;
+    const float cost = sqrtf(fmaxf(0.f, 1.0f - (eta * eta) * (1.0f - cosi * cosi)));
+    const V3 td = vadd(vmul(dir, eta), vmul(n, eta * cosi - cost));
+    const float d = P.lens_thickness;
+    delta = vsub(vmul(td, d / cost), vmul(dir, d / cosi));
+    t_behind = t_lens + d / cosi;
+}
+
 // =================================================================================================================
 // pixel finish: shade_kernel_nerf + accumulate_kernel + tonemap_kernel
 // (S/ngp/testbed.cu:907-931; S/ngp/render_buffer.cu:232-267, 327-346, 537-566) fused into the ray's last step
@@ -1073,8 +1090,14 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH
                         V3 refl;
                         const float F = lens_fresnel(P, dir, v3(l0.x, l0.y, l0.z), refl);
                         const float wl = __ldg(out.lens + (size_t)idx * 2 + 1).x;
-                        stash[0] = cr; stash[1] = cg; stash[2] = cb; stash[3] = ca; stash[7] = t; stash[14] = F; stash[15] = wl;
+                        stash[0] = cr; stash[1] = cg; stash[2] = cb; stash[3] = ca; stash[14] = F; stash[15] = wl;
                         stash[4] = 0.f; stash[5] = 0.f; stash[6] = 0.f;
+                        {   // where the transmitted segment starts (behind the pane, shifted sideways under the plate model)
+                            V3 delta; float t_behind;
+                            lens_plate_shift(P, dir, v3(l0.x, l0.y, l0.z), l0.w, delta, t_behind);
+                            stash[7] = fmaxf(t, t_behind);
+                            stash[20] = cam_origin.x + delta.x; stash[21] = cam_origin.y + delta.y; stash[22] = cam_origin.z + delta.z;
+                        }
                         if (wl * F * (1.f - ca) >= 1.0f / 512.0f) {
                             // reflected segment: a fresh ray from the hit point along the mirror direction, NeRF only
                             stash[16] = dir.x; stash[17] = dir.y; stash[18] = dir.z;
@@ -1094,9 +1117,10 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH
                         stash[4] = cr + P.background[0] * k; stash[5] = cg + P.background[1] * k; stash[6] = cb + P.background[2] * k;
                     }
                     // transmitted segment: the primary ray carries on behind the lens, now with the opaque mesh surface (if any)
-                    origin = cam_origin;
+                    origin = v3(stash[20], stash[21], stash[22]);
                     dir = v3(stash[16], stash[17], stash[18]);
                     t = stash[7]; t_start = stash[8]; t_surface = stash[9]; sr = stash[10]; sg = stash[11]; sb = stash[12]; sw = stash[13]; t_limit = stash[19];
+                    if (P.lens_model == 1) { float t_in; t_limit = occupied_exit(P, origin, dir, t_in); }      // (the shifted ray's own exit from the occupied box)
                     cr = cg = cb = ca = 0.f;
                     phase = 3u;
                     continue;

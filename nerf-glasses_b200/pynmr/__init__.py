@@ -91,6 +91,7 @@ def lib():
         "nmr_load_density_grid": (C.c_int, [vp, C.c_int, C.c_char_p, vp]),
         "nmr_read_combined": (C.c_int, [vp, vp, vp]),
         "nmr_set_lens": (C.c_int, [vp, C.c_int, C.c_float, C.c_float, fp]),
+        "nmr_set_lens_model": (C.c_int, [vp, C.c_int, C.c_float]),
         "nmr_get_nerf_info": (C.c_int, [vp, C.c_int, C.POINTER(NerfInfo)]),
         "nmr_get_stream": (C.c_int, [vp, C.POINTER(vp)]),
         "nmr_set_tonemap_curve": (C.c_int, [vp, C.c_int, C.c_int]),
@@ -133,7 +134,7 @@ EXPORTED_SYMBOLS = [
     "nmr_get_device_image", "nmr_copy_device_image", "nmr_flush_l2", "nmr_get_stats", "nmr_synchronize", "nmr_host_alloc", "nmr_host_free", "nmr_get_density_bitfield",
     "nmr_set_density_bitfield", "nmr_debug_encode", "nmr_debug_network", "nmr_debug_trace", "nmr_debug_mesh",
     "nmr_debug_last_frame", "nmr_debug_set_flags", "nmr_render_format", "nmr_render_views_format", "nmr_debug_parse_gltf", "nmr_measure_l2", "nmr_set_overlap", "nmr_set_model_transform", "nmr_get_model_transform",
-    "nmr_dump_density_grid", "nmr_load_density_grid", "nmr_read_combined",
+    "nmr_dump_density_grid", "nmr_load_density_grid", "nmr_read_combined", "nmr_set_lens_model",
 ]
 
 
@@ -669,6 +670,12 @@ class NerfMeshRenderer:
     def set_lens(self, enabled: bool = True, ior: float = -1.0, transmission: float = -1.0, tint=None):
         """Lens surfaces and their secondary rays (include/nmr.h: nmr_set_lens).  Negative / None keeps a parameter."""
         self._ck(lib().nmr_set_lens(self._h, int(bool(enabled)), float(ior), float(transmission), _f3(tint) if tint is not None else None))
+
+    LENS_THIN, LENS_PLATE = 0, 1
+
+    def set_lens_model(self, model: int = 0, thickness: float = 0.0):
+        """Thin sheet (0, no bending) or a pane of `thickness` with parallel faces (1: two Snell interfaces) - include/nmr.h."""
+        self._ck(lib().nmr_set_lens_model(self._h, int(model), float(thickness)))
 
     def stream_ptr(self) -> int:
         """cudaStream_t of this renderer as an integer (e.g. for torch.cuda.ExternalStream)."""

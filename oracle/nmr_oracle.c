@@ -898,7 +898,25 @@ static void composite_ray(const orc_render_params* P, const aabb_t* train_aabb, 
  *   first-hit, total samples, wavefront iterations, rays hit}. */
 /* ---- lens rays (NEW functionality: the published reference traces primary rays only; this is the
  * executable specification of libnmr's secondary rays, DESIGN.md "Secondary rays") ---------------------------------- */
-typedef struct { float f0, k[3], kmean, background[4]; } lens_params_t;
+typedef struct { float f0, k[3], kmean, background[4]; int model; float thickness, ior; } lens_params_t;
+
+/* Lens model 1 ("plate"): a pane of glass of `thickness` with parallel faces.  The ray refracts into the glass at the hit point
+ * (Snell, relative index 1 / ior, normal turned towards the ray), crosses it, and leaves through the back face parallel to its old
+ * direction: the transmitted segment is the primary ray shifted sideways by delta and resumed behind the pane.  Model 0 (thin
+ * sheet): delta = 0.  The grazing-angle factor is capped (cos >= 0.05). */
+static void lens_plate_shift(const lens_params_t* L, v3 dir, v3 n, float t_lens, v3* delta, float* t_behind) {
+    *delta = v3_make(0.f, 0.f, 0.f); *t_behind = t_lens;
+    if (L->model != 1 || !(L->thickness > 0.f)) return;
+    float c = dot3(dir, n);
+    if (c > 0.f) { n = mul3(n, -1.f); c = -c; }
+    const float cosi = fmaxf(fminf(-c, 1.0f), 0.05f);
+    const float eta = 1.0f / L->ior;
+    const float cost = sqrtf(fmaxf(0.f, 1.0f - (eta * eta) * (1.0f - cosi * cosi)));
+    const v3 td = add3(mul3(dir, eta), mul3(n, eta * cosi - cost));          /* unit direction inside the glass */
+    const float d = L->thickness;
+    *delta = sub3(mul3(td, d / cost), mul3(dir, d / cosi));
+    *t_behind = t_lens + d / cosi;
+}
 
 /* Schlick reflectance of a thin lens for unit direction d and unit normal n (turned towards the ray); mirror direction out */
 static float lens_fresnel(const lens_params_t* L, v3 d, v3 n, v3* refl) {
@@ -951,7 +969,9 @@ static void march_lens_ray(const orc_model* m, const orc_render_params* P, const
         for (int c = 0; c < 3; ++c) LB[c] = b.rgba[c] + L->background[c] * k;
     }
     ray_t c3; memset(&c3, 0, sizeof(c3));
-    c3.origin = origin; c3.dir = dir; c3.t = t_resume; c3.t_start = t_start; c3.t_surface = t_surf; memcpy(c3.surf, surf, 16); c3.alive = 1; c3.idx = r->idx;
+    v3 delta; float t_behind;
+    lens_plate_shift(L, dir, nrm, t_lens, &delta, &t_behind);
+    c3.origin = add3(origin, delta); c3.dir = dir; c3.t = fmaxf(t_resume, t_behind); c3.t_start = t_start; c3.t_surface = t_surf; memcpy(c3.surf, surf, 16); c3.alive = 1; c3.idx = r->idx;
     r->n_samples += march_segment(m, P, render_aabb, train_aabb, &c3, n, INFINITY, 0);   /* payload.t semantics of the reference (composite_ray) */
     const float Tf = 1.f - front[3];
     for (int c = 0; c < 3; ++c) {
@@ -976,7 +996,9 @@ ORC_API int orc_render(const orc_model* m, const orc_render_params* P, const flo
 ORC_API int orc_render_lens(const orc_model* m, const orc_render_params* P, const float* surf_rgba, const float* t_surface,
                             const float* lens_w, const float* lens_t, const float* lens_n, const float* lens9,
                             float* frame, float* depth, uint32_t* n_samples, uint64_t* stats) {
+    /* lens9[9..11] = model, thickness, ior (model 0: thin sheet) */
     lens_params_t L; L.f0 = lens9[0]; L.k[0] = lens9[1]; L.k[1] = lens9[2]; L.k[2] = lens9[3]; L.kmean = lens9[4]; memcpy(L.background, lens9 + 5, 16);
+    L.model = (int)lens9[9]; L.thickness = lens9[10]; L.ior = lens9[11];
     return render_impl(m, P, surf_rgba, t_surface, lens_w, lens_t, lens_n, &L, frame, depth, n_samples, stats);
 }
 

@@ -256,7 +256,8 @@ class Model:
             lw = np.ascontiguousarray(lens["w"], dtype=np.float32); lt = np.ascontiguousarray(lens["t"], dtype=np.float32)
             ln = np.ascontiguousarray(lens["n"], dtype=np.float32)
             k = np.asarray(lens["k"], dtype=np.float32)
-            l9 = np.array([lens["f0"], k[0], k[1], k[2], float((k[0] + k[1] + k[2]) / np.float32(3.0)), *lens["background"]], dtype=np.float32)
+            l9 = np.array([lens["f0"], k[0], k[1], k[2], float((k[0] + k[1] + k[2]) / np.float32(3.0)), *lens["background"],
+                           float(lens.get("model", 0)), float(lens.get("thickness", 0.0)), float(lens.get("ior", 1.5))], dtype=np.float32)
             rc = lib().orc_render_lens(self.h, C.byref(P), sp, tp, _p(lw), _p(lt), _p(ln), _p(l9), _p(frame), _p(depth), _p(ns), _p(stats))
         else:
             rc = lib().orc_render(self.h, C.byref(P), sp, tp, _p(frame), _p(depth), _p(ns), _p(stats))

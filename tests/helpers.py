@@ -110,7 +110,8 @@ def oracle_scene(snap, width, height, cam12, glasses=None, spp_index=0, n_steps_
             lw, lt, lnn = O.lens_resolve(d2, ld2, ln2, ts, width, height, 2)
             lp = g["lens"]
             lens = {"w": lw, "t": lt, "n": lnn, "f0": O.lens_f0(lp["ior"]), "k": np.float32(lp["transmission"]) * lp["tint"].astype(np.float32),
-                    "background": (1.0, 1.0, 1.0, 1.0)}
+                    "background": (1.0, 1.0, 1.0, 1.0),
+                    "model": glasses.get("lens_model", 0), "thickness": glasses.get("lens_thickness", 0.0), "ior": lp["ior"]}
         else:
             rgba2, d2, _ = mesh.render(cam12, 2 * width, 2 * height)
             surf, ts = O.mesh_resolve(rgba2, d2, width, height, 2)

@@ -89,3 +89,27 @@ def test_lens_parameters_and_sharding(lens_scene):
         r.set_shard(0, 1, 8)
         r.set_surface_insertion(pynmr.NerfMeshRenderer.SURFACE_AUTO)
     assert np.array_equal(merged.view(np.uint32), full.view(np.uint32))
+
+
+def test_lens_plate_model_matches_oracle(lens_scene):
+    """Lens model 1: a pane of glass with two parallel Snell interfaces - the transmitted segment is shifted sideways and resumes
+    behind the pane (include/nmr.h: nmr_set_lens_model; oracle: lens_plate_shift).  Thickness 0 is the thin sheet, bit for bit."""
+    import pynmr
+    r, nerf, snap, g = lens_scene["r"], lens_scene["nerf"], lens_scene["snap"], lens_scene["glasses"]
+    thin = np.asarray(nerf.render(W, HH, 1, linear=False)).copy()
+    try:
+        r.set_lens_model(pynmr.NerfMeshRenderer.LENS_PLATE, 0.0)
+        assert np.array_equal(np.asarray(nerf.render(W, HH, 1, linear=False)).view(np.uint32), thin.view(np.uint32))
+        thickness = 0.03
+        r.set_lens_model(pynmr.NerfMeshRenderer.LENS_PLATE, thickness)
+        plate = np.asarray(nerf.render(W, HH, 1, linear=False)).copy()
+        want = H.oracle_scene(snap, W, HH, cam12(r), glasses=dict(g, lens_model=1, lens_thickness=thickness), n_steps_mode=1)[0]
+        assert np.max(np.abs(plate - want)) <= PIX_TOL and H.psnr(plate, want) >= 45.0
+        assert np.max(np.abs(plate - thin)) > 0.02                       # the shift is visible through the lenses
+        w, _, _ = H.debug_lens(r, W, HH)
+        assert np.array_equal((np.abs(plate - thin).max(axis=2) > 0) & (w == 0), np.zeros_like(w, dtype=bool))      # ... and only there
+        with pytest.raises(RuntimeError):
+            r.set_lens_model(7, 0.01)
+    finally:
+        r.set_lens_model(pynmr.NerfMeshRenderer.LENS_THIN, 0.0)
+    assert np.array_equal(np.asarray(nerf.render(W, HH, 1, linear=False)).view(np.uint32), thin.view(np.uint32))
