@@ -462,6 +462,37 @@ def stress_leg(args, local_rank: int, regime: str, zoom: float, steps: int = 12)
             "march_gbs_algorithmic": ALGO_BYTES_PER_SAMPLE * smp / mtot / 1e9, "march_tflops_algorithmic": ALGO_FLOP_PER_SAMPLE * smp / mtot / 1e12}
 
 
+def hashmap_sweep_leg(args, local_rank: int, sizes=(19, 22, 24), steps: int = 6):
+    """BASELINE configs[4]: the encoding-bound stress - synthetic models with log2_hashmap_size 19 / 22 / 24 (hash tables of 23 /
+    151 / 507 MiB: the larger ones leave the L2), 1080p hybrid frame with the head filling it and a translucent medium (13 M
+    samples per frame).  Device time of the march kernel, L2 flushed between frames."""
+    import pynmr
+    import synth
+    W, H = args.width, args.height
+    out = []
+    for log2T in sizes:
+        with tempfile.TemporaryDirectory() as tmp:
+            snap, gltf = make_inputs(tmp, log2T, "translucent")
+            r = pynmr.NerfMeshRenderer(W, H, local_rank)
+            nerf = r.load_nerf(snap)
+            if nerf is None or r.load_mesh(gltf, t=synth.GLASSES_T, s=synth.GLASSES_S, r=synth.GLASSES_R_WXYZ) is None:
+                raise RuntimeError("inputs failed to load")
+            os.remove(snap)
+            r.remove_floaties()
+        table_mib = (nerf.n_params - 10240) * 2 / 2 ** 20
+        r.orbit(0.0, 0.0, 4.0)
+        a, ms, mms, smp = 0.0, [], [], 0
+        for i in range(steps + 3):
+            a += 0.03; r.orbit(*orbit_step(a)); r.flush_l2(); r.frame_async(); st = r.stats()
+            if i >= 3:
+                ms.append(st["gpu_ms"]); mms.append(st["march_ms"]); smp += st["samples"]
+        tot, mtot = float(np.sum(ms)) / 1e3, float(np.sum(mms)) / 1e3
+        out.append({"log2_hashmap_size": log2T, "table_mib": round(table_mib, 1), "ms_per_frame": tot / steps * 1e3, "samples_per_frame": smp / steps,
+                    "march_msamples_per_s": smp / mtot / 1e6, "march_gbs_algorithmic": ALGO_BYTES_PER_SAMPLE * smp / mtot / 1e9})
+        del r, nerf
+    return {"workload": f"{W}x{H} hybrid, translucent medium, orbit zoom 4, log2_hashmap_size sweep (BASELINE configs[4]); {steps} frames each, L2 flushed between frames", "sizes": out}
+
+
 def pipelined_leg(args, local_rank: int, n_frames: int = 64, repeats: int = 5):
     """Informational (not the headline): independent frames of the same workload submitted together - nmr_render_views keeps
     several in flight on the GPU, images left in HBM.  Throughput of offline / multi-view rendering; a single frame's
@@ -771,6 +802,10 @@ def main():
             out["views_c3"] = views
         if world == 1 and not args.no_extras:
             out["stress"] = [stress_leg(args, local_rank, "opaque", 4.0), stress_leg(args, local_rank, "translucent", 4.0)]
+            try:
+                out["hashmap_sweep_c5"] = hashmap_sweep_leg(args, local_rank)
+            except Exception as e:
+                out["hashmap_sweep_c5"] = {"error": str(e)[:200]}
             try:
                 out["pipelined_frames"] = pipelined_leg(args, local_rank)
             except Exception as e:

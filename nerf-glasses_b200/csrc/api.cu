@@ -121,6 +121,8 @@ struct nmr_ctx {
     int mesh_scale = 2;                                   // mesh_render_size_factor, S/nerf_mesh_renderer.cuh:112
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;                   // device->host copies of nmr_render_views
+    cudaStream_t aux_stream = nullptr;                    // a frame's background kernel runs here, next to the mesh stage and the ray set-up
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_view[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // per image buffer: rendered, copied
     // nmr_render_views: views are independent frames, and a single frame leaves most of the GPU idle (both its kernels wait on
     // dependent chains).  Helper contexts ("lanes": own stream, ray queue, counters, visibility buffer, image) render several
@@ -322,7 +324,7 @@ void upload_mesh_if_dirty(nmr_ctx* ctx) {
 // exactly on its boundary), in general cascades 0..max_cascade+1; cascade c cells are 2^c / 128 wide and centred on 0.5.
 void update_occupied_box(nmr_ctx* ctx, Nerf& n) {
     {   // the coarse view of cascade 0 that the first-hit walk jumps through (NMR_NO_COARSE=1: plain walk, for A/B runs)
-        n.d_coarse.ensure((size_t)kCoarseRes * kCoarseRes);
+        n.d_coarse.ensure((size_t)kCoarseRes * kCoarseRes * kCoarseRowWords);
         DevBuf<uint8_t> d_occ; d_occ.ensure((size_t)kCoarseRes * kCoarseRes * kCoarseRes);
         launch_coarse_build(n.d_bitfield.p, d_occ.p, n.d_coarse.p, ctx->stream);
         CK(cudaStreamSynchronize(ctx->stream));
@@ -540,14 +542,30 @@ void enqueue_pass(nmr_ctx* ctx, Nerf& n, const FrameParams& P, bool timed, void*
     // cleared by one kernel (not four memset nodes)
     launch_frame_clear(ctx->d_counters.p, sched ? S.hist.p : nullptr, S.zbuf.p, zbuf_window_words(mesh, P), S.queue.p, ctx->stream);
     launches += 1;
+    // The background pixels (everything outside the tile box of the two screen rectangles) depend on nothing else in the frame:
+    // they are written on a side stream while the mesh stage and the ray set-up run (fork behind the clear kernel, which is
+    // behind the previous frame; join in front of the frame's closing event).  NMR_NO_AUX_STREAM=1: in line, for A/B runs.
+    const TileBox box = compute_tile_box(P, rows);
+    static const bool no_aux = std::getenv("NMR_NO_AUX_STREAM") != nullptr;
+    const bool side = !no_aux && ctx->aux_stream != nullptr && rows > 0;
+    if (side) {
+        CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+        launch_background(P, n.dev, out, rows, box, true, ctx->num_sms, ctx->aux_stream);
+        CK(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+    } else {
+        launch_background(P, n.dev, out, rows, box, true, ctx->num_sms, ctx->stream);
+    }
+    launches += rows > 0 ? 1 : 0;
     if (P.mesh_scale > 0) { launch_mesh_raster(mesh, P, rows, S.zbuf.p, ctx->stream, false); launches += 1; }
-    const int init_ctas = launch_init_rays(P, n.dev, mesh, S.zbuf.p, rows, S.queue.p, ctx->d_counters.p, out, ctx->num_sms, ctx->stream, false, sched ? S.surf_list.p : nullptr, 1);
-    launches += rows > 0 ? (init_ctas > 0 ? 2 : 1) : 0;                       // background kernel + set-up kernel over the tile box
+    const int init_ctas = launch_init_rays(P, n.dev, mesh, S.zbuf.p, rows, S.queue.p, ctx->d_counters.p, out, box, ctx->stream, sched ? S.surf_list.p : nullptr);
+    launches += init_ctas > 0 ? 1 : 0;
     if (timed && !overlap) CK(cudaEventRecord(ctx->ev[1], ctx->stream));      // (an event between the two kernels would serialise them)
     const uint32_t n_pixels = (uint32_t)P.width * (uint32_t)rows;
     launch_march(Pm, model_for(ctx, n), S.queue.p, ctx->d_counters.p, out, n_pixels, ctx->debug_flags, ctx->num_sms, ctx->stream, nullptr, nullptr, sched ? &sa : nullptr, ctx->march_ctas,
                  overlap ? init_ctas : -1);
     launches += 1;
+    if (side) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     if (timed) ctx->last_overlapped = overlap;
     if (sched) { enqueue_surface_pass(ctx, n, P, out, n_pixels, sa); launches += 1; }
     if (timed) {
@@ -638,6 +656,8 @@ nmr_ctx* make_lane(nmr_ctx* parent) {
     std::unique_ptr<nmr_ctx> l(new nmr_ctx());
     l->device = parent->device; l->num_sms = parent->num_sms; l->width = parent->width; l->height = parent->height;
     CK(cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&l->aux_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&l->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&l->ev_join, cudaEventDisableTiming));
     for (auto& ev : l->ev) CK(cudaEventCreate(&ev));
     for (auto& pair : l->ev_view) for (auto& ev : pair) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     l->d_counters.ensure(kNumCounters);
@@ -652,6 +672,9 @@ void destroy_lane(nmr_ctx* l) {
     if (l->h_counters) cudaFreeHost(l->h_counters);
     for (auto& ev : l->ev) if (ev) cudaEventDestroy(ev);
     for (auto& pair : l->ev_view) for (auto& ev : pair) if (ev) cudaEventDestroy(ev);
+    if (l->ev_fork) cudaEventDestroy(l->ev_fork);
+    if (l->ev_join) cudaEventDestroy(l->ev_join);
+    if (l->aux_stream) { cudaStreamSynchronize(l->aux_stream); cudaStreamDestroy(l->aux_stream); }
     if (l->stream) cudaStreamDestroy(l->stream);
     delete l;
 }
@@ -713,6 +736,8 @@ NMR_API int nmr_create(int width, int height, int device, nmr_ctx** out_ctx) {
         CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         for (auto& ev : ctx->ev) CK(cudaEventCreate(&ev));
         CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
         for (auto& pair : ctx->ev_view) for (auto& ev : pair) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ctx->ev_rows, cudaEventDisableTiming));
         ctx->d_counters.ensure(kNumCounters);
@@ -744,6 +769,9 @@ NMR_API void nmr_destroy(nmr_ctx* ctx) {
     for (auto& pair : ctx->ev_view) for (auto& ev : pair) if (ev) cudaEventDestroy(ev);
     if (ctx->ev_rows) cudaEventDestroy(ctx->ev_rows);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

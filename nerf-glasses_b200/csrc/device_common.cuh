@@ -273,12 +273,17 @@ __device__ __forceinline__ float lattice_advance(float t, int K) {
 // probability ~1e-4, by one step) - and from any landing point the walk falls back onto the reference's own sequence of
 // steps at the next voxel boundary with the same odds.  Two coarse cells (>= 4 voxel steps) separate a landing from the first
 // occupied cell, which puts a different first sample at ~1e-16 per ray; tests compare t bit for bit with the oracle's plain walk.
-constexpr int kCoarseRes = 32;
+#ifndef NMR_COARSE_RES
+#define NMR_COARSE_RES 32
+#endif
+constexpr int kCoarseRes = NMR_COARSE_RES;               // 32: cells of 4 voxels, reach 2 cells; 64: cells of 2 voxels, reach 3 cells
+constexpr int kCoarseReach = kCoarseRes == 32 ? 2 : 3;   // Chebyshev distance (in coarse cells) within which an occupied cell makes a cell "near"
+constexpr int kCoarseRowWords = kCoarseRes / 32;
 __device__ __forceinline__ bool coarse_near(const uint32_t* __restrict__ coarse, V3 pos) {
     const int cx = min(max(__float2int_rz(pos.x * (float)kCoarseRes), 0), kCoarseRes - 1);
     const int cy = min(max(__float2int_rz(pos.y * (float)kCoarseRes), 0), kCoarseRes - 1);
     const int cz = min(max(__float2int_rz(pos.z * (float)kCoarseRes), 0), kCoarseRes - 1);
-    return (__ldg(coarse + cz * kCoarseRes + cy) >> cx) & 1u;
+    return (__ldg(coarse + (cz * kCoarseRes + cy) * kCoarseRowWords + (cx >> 5)) >> (cx & 31)) & 1u;
 }
 // the walk's steps up to the first one at or behind the exit of the (empty) coarse cell around pos
 __device__ __forceinline__ float coarse_skip(float t, V3 pos, V3 dir, V3 idir) {

@@ -11,6 +11,7 @@
 // Reference behaviour restated per kernel: see the citations at each function and SURVEY.md section 8a.
 #include "kernels.cuh"
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 
 #include <cstdio>
@@ -89,34 +90,35 @@ void launch_occupancy_bounds(const uint8_t* d_bitfield, int* d_out48, cudaStream
 }
 
 // coarse "near" bits of cascade 0 (device_common.cuh: coarse_near).  A coarse cell is a (128 / kCoarseRes)^3 block of grid cells
-// aligned to its size, i.e. 64 consecutive Morton codes = 8 consecutive bytes of the bitfield.
+// aligned to its size, i.e. a run of consecutive Morton codes: 64 codes = 8 bytes of the bitfield (kCoarseRes 32) or 8 codes =
+// one byte (kCoarseRes 64).
 __global__ void coarse_occupied_kernel(const uint8_t* __restrict__ bitfield, uint8_t* __restrict__ occ) {
-    static_assert(NERF_GRIDSIZE / kCoarseRes == 4, "a coarse cell is 4 x 4 x 4 grid cells");
+    constexpr uint32_t V = NERF_GRIDSIZE / kCoarseRes;
+    static_assert(V == 4 || V == 2, "a coarse cell is 4 x 4 x 4 or 2 x 2 x 2 grid cells");
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= kCoarseRes * kCoarseRes * kCoarseRes) return;
     const uint32_t cx = i % kCoarseRes, cy = (i / kCoarseRes) % kCoarseRes, cz = i / (kCoarseRes * kCoarseRes);
-    const uint32_t m = morton3D(cx * 4u, cy * 4u, cz * 4u);                 // first of the block's 64 codes
-    const uint2 v = *reinterpret_cast<const uint2*>(bitfield + m / 8u);
-    occ[i] = (v.x | v.y) != 0u;
+    const uint32_t m = morton3D(cx * V, cy * V, cz * V);                    // first of the block's V^3 codes
+    if (V == 4) { const uint2 v = *reinterpret_cast<const uint2*>(bitfield + m / 8u); occ[i] = (v.x | v.y) != 0u; }
+    else occ[i] = bitfield[m / 8u] != 0u;
 }
 __global__ void coarse_near_kernel(const uint8_t* __restrict__ occ, uint32_t* __restrict__ near_bits) {
-    static_assert(kCoarseRes == 32, "one warp = one row of coarse cells = one word");
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;                    // one thread per coarse cell, one warp per row
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;                    // one thread per coarse cell; the words were zeroed
     if (i >= kCoarseRes * kCoarseRes * kCoarseRes) return;
     const int cx = i % kCoarseRes, cy = (i / kCoarseRes) % kCoarseRes, cz = i / (kCoarseRes * kCoarseRes);
     bool near_cell = cx == 0 || cy == 0 || cz == 0 || cx == kCoarseRes - 1 || cy == kCoarseRes - 1 || cz == kCoarseRes - 1;
-    for (int dz = -2; dz <= 2 && !near_cell; ++dz)
-        for (int dy = -2; dy <= 2 && !near_cell; ++dy)
-            for (int dx = -2; dx <= 2; ++dx) {
+    for (int dz = -kCoarseReach; dz <= kCoarseReach && !near_cell; ++dz)
+        for (int dy = -kCoarseReach; dy <= kCoarseReach && !near_cell; ++dy)
+            for (int dx = -kCoarseReach; dx <= kCoarseReach; ++dx) {
                 const int x = cx + dx, y = cy + dy, z = cz + dz;
                 if (x < 0 || y < 0 || z < 0 || x >= kCoarseRes || y >= kCoarseRes || z >= kCoarseRes) continue;
                 if (occ[(z * kCoarseRes + y) * kCoarseRes + x]) { near_cell = true; break; }
             }
-    const uint32_t word = __ballot_sync(0xffffffffu, near_cell);
-    if (cx == 0) near_bits[cz * kCoarseRes + cy] = word;
+    if (near_cell) atomicOr(near_bits + (cz * kCoarseRes + cy) * kCoarseRowWords + (cx >> 5), 1u << (cx & 31));
 }
 void launch_coarse_build(const uint8_t* d_bitfield, uint8_t* d_occ_scratch, uint32_t* d_near_bits, cudaStream_t s) {
     constexpr int n = kCoarseRes * kCoarseRes * kCoarseRes;
+    cudaMemsetAsync(d_near_bits, 0, sizeof(uint32_t) * kCoarseRes * kCoarseRes * kCoarseRowWords, s);
     coarse_occupied_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_bitfield, d_occ_scratch);
     coarse_near_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_occ_scratch, d_near_bits);
 }
@@ -477,7 +479,6 @@ __device__ __forceinline__ void background_pixel(const FrameParams& P, const Fra
 
 // The set-up kernel only covers the TILE BOX: the 16 x 8 pixel tiles [tile_x0, tile_x0 + gridDim.x) x [tile_y0, ...) of local
 // (owned) rows that the union of the two screen rectangles touches.  Everything else is background, written by background_kernel.
-struct TileBox { int x0, y0, nx, ny; };     // in tiles; nx == 0: no rectangle in view, no set-up kernel at all
 
 // 16 x 8 pixel CTA, each warp an 8 x 4 tile so queue neighbours are screen neighbours.  A pixel outside both the screen
 // rectangle of the box around the occupied cells (FrameParams::occ_px, projected on the host) and the mesh's screen rectangle
@@ -612,10 +613,9 @@ static int local_rows_below(const FrameParams& P, int y) {
     return full * P.shard_band + std::min(std::max(rem - P.shard_rank * P.shard_band, 0), P.shard_band);
 }
 
-int launch_init_rays(const FrameParams& P, const DeviceModel& M, const MeshDevice& mesh, const unsigned long long* d_zbuf, int rows_owned,
-                     float4* d_queue, uint32_t* d_counters, const FrameOut& out, int num_sms, cudaStream_t s, bool reset_counters, uint32_t* d_surf_list, int first_pass) {
-    if (reset_counters) cudaMemsetAsync(d_counters, 0, sizeof(uint32_t) * kFrameCounters, s);
-    if (rows_owned <= 0) return 0;
+TileBox compute_tile_box(const FrameParams& P, int rows_owned) {
+    TileBox box{0, 0, 0, 0, 0u, 0u};
+    if (rows_owned <= 0) return box;
     // union of the two screen rectangles in pixels (image rows), then in 16 x 8 tiles of local rows
     int x0 = P.width, y0 = P.height, x1 = 0, y1 = 0;
     const bool have_occ = P.occ_px[2] > P.occ_px[0] && P.occ_px[3] > P.occ_px[1];
@@ -625,34 +625,33 @@ int launch_init_rays(const FrameParams& P, const DeviceModel& M, const MeshDevic
         x0 = std::min(x0, P.zb_x0 / ms); y0 = std::min(y0, P.zb_y0 / ms);
         x1 = std::max(x1, (P.zb_x0 + P.zb_w + ms - 1) / ms); y1 = std::max(y1, (P.zb_y0 + P.zb_h + ms - 1) / ms);
     }
-    TileBox box{0, 0, 0, 0};
-    uint2 rot = make_uint2(0u, 0u);
-    if (x1 > x0 && y1 > y0) {
-        const int ly0 = local_rows_below(P, y0), ly1 = std::min(rows_owned, local_rows_below(P, y1));
-        x0 = std::max(0, x0); x1 = std::min(P.width, x1);
-        if (ly1 > ly0 && x1 > x0) {
-            box.x0 = x0 / 16; box.y0 = ly0 / 8; box.nx = (x1 + 15) / 16 - box.x0; box.ny = (ly1 + 7) / 8 - box.y0;
-            // first CTA column / row over the occupied cells; NMR_NO_BLOCK_ROTATION=1 for A/B runs
-            static const bool no_rot = std::getenv("NMR_NO_BLOCK_ROTATION") != nullptr;
-            if (!no_rot && have_occ) {
-                const int rx = std::max(x0, P.occ_px[0]) / 16 - box.x0, ry = local_rows_below(P, std::max(y0, P.occ_px[1])) / 8 - box.y0;
-                if (rx >= 0 && rx < box.nx && ry >= 0 && ry < box.ny) rot = make_uint2((unsigned)rx, (unsigned)ry);
-            }
-        }
+    if (!(x1 > x0 && y1 > y0)) return box;
+    const int ly0 = local_rows_below(P, y0), ly1 = std::min(rows_owned, local_rows_below(P, y1));
+    x0 = std::max(0, x0); x1 = std::min(P.width, x1);
+    if (!(ly1 > ly0 && x1 > x0)) return box;
+    box.x0 = x0 / 16; box.y0 = ly0 / 8; box.nx = (x1 + 15) / 16 - box.x0; box.ny = (ly1 + 7) / 8 - box.y0;
+    // first CTA column / row over the occupied cells; NMR_NO_BLOCK_ROTATION=1 for A/B runs
+    static const bool no_rot = std::getenv("NMR_NO_BLOCK_ROTATION") != nullptr;
+    if (!no_rot && have_occ) {
+        const int rx = std::max(x0, P.occ_px[0]) / 16 - box.x0, ry = local_rows_below(P, std::max(y0, P.occ_px[1])) / 8 - box.y0;
+        if (rx >= 0 && rx < box.nx && ry >= 0 && ry < box.ny) { box.rot_x = (unsigned)rx; box.rot_y = (unsigned)ry; }
     }
+    return box;
+}
+
+void launch_background(const FrameParams& P, const DeviceModel& M, const FrameOut& out, int rows_owned, const TileBox& box, bool prefetch_table, int num_sms, cudaStream_t s) {
+    if (rows_owned <= 0) return;
     // tables that fit the L2 comfortably are prefetched by the frame's first set-up pass; NMR_NO_PREFETCH=1 for A/B runs
     static const bool no_prefetch = std::getenv("NMR_NO_PREFETCH") != nullptr;
     const size_t table_bytes = ((size_t)M.level_offset[N_LEVELS - 1] + M.level_size[N_LEVELS - 1]) * sizeof(__half2);
-    const bool first = first_pass < 0 ? reset_counters : first_pass != 0;     // the frame's first set-up pass
-    const uint32_t prefetch_lines = (first && !no_prefetch && table_bytes <= ((size_t)48 << 20)) ? (uint32_t)(table_bytes / 128) : 0u;
+    const uint32_t prefetch_lines = (prefetch_table && !no_prefetch && table_bytes <= ((size_t)48 << 20)) ? (uint32_t)(table_bytes / 128) : 0u;
     background_kernel<<<num_sms * 4, 256, 0, s>>>(P, out, rows_owned, box, reinterpret_cast<const char*>(M.grid), prefetch_lines);
-    if (box.nx <= 0) return 0;
-    // NMR_INIT_SMEM_KB (tuning aid): unused dynamic shared memory that caps how many CTAs of the set-up kernel share an SM, so that
-    // CTAs of an overlapped march kernel find registers next to them
-    static const int pad_kb = [] { const char* v = std::getenv("NMR_INIT_SMEM_KB"); return v ? std::atoi(v) : 0; }();
-    static bool pad_attr = false;
-    if (pad_kb > 48 && !pad_attr) { cudaFuncSetAttribute(init_rays_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pad_kb * 1024); pad_attr = true; }
-    init_rays_kernel<<<dim3((unsigned)box.nx, (unsigned)box.ny), 128, (size_t)pad_kb * 1024, s>>>(P, M, mesh, d_zbuf, rows_owned, d_queue, d_counters, out, d_surf_list, box, rot);
+}
+
+int launch_init_rays(const FrameParams& P, const DeviceModel& M, const MeshDevice& mesh, const unsigned long long* d_zbuf, int rows_owned,
+                     float4* d_queue, uint32_t* d_counters, const FrameOut& out, const TileBox& box, cudaStream_t s, uint32_t* d_surf_list) {
+    if (rows_owned <= 0 || box.nx <= 0) return 0;
+    init_rays_kernel<<<dim3((unsigned)box.nx, (unsigned)box.ny), 128, 0, s>>>(P, M, mesh, d_zbuf, rows_owned, d_queue, d_counters, out, d_surf_list, box, make_uint2(box.rot_x, box.rot_y));
     return box.nx * box.ny;
 }
 
@@ -1388,17 +1387,17 @@ void launch_march(const FrameParams& P, const DeviceModel& M, const float4* d_qu
     if (sched) sa = *sched;
     const int per_sm = ctas_per_sm > 0 ? ctas_per_sm : kMarchCtasPerSm;
     if (debug_flags & kDebugScalarMlp) {
-        static bool attr_set_dev[64] = {};      // the opt-in to > 48 KB of dynamic shared memory is per device
+        static std::atomic<bool> attr_set_dev[64];     // the opt-in to > 48 KB of dynamic shared memory is per device (setting it twice from two threads is harmless)
         int dev = 0; cudaGetDevice(&dev);
-        bool& attr_set = attr_set_dev[dev & 63];
-        if (!attr_set) { cudaFuncSetAttribute(march_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmem)); cudaFuncSetAttribute(march_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(MarchSmem) + kSchedSmem)); attr_set = true; }
+        std::atomic<bool>& attr_set = attr_set_dev[dev & 63];
+        if (!attr_set.load(std::memory_order_acquire)) { cudaFuncSetAttribute(march_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmem)); cudaFuncSetAttribute(march_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(MarchSmem) + kSchedSmem)); attr_set.store(true, std::memory_order_release); }
         if (sa.pass == 2) launch_march_variant(march_kernel<false, true>, num_sms, kTile, sizeof(MarchSmem) + kSchedSmem, s, false, P, M, d_queue, d_counters, out, n_pixels, debug_flags, d_range_end, d_cursor, sa, -1);
         else launch_march_variant(march_kernel<false, false>, num_sms * 2, kTile, sizeof(MarchSmem), s, false, P, M, d_queue, d_counters, out, n_pixels, debug_flags, d_range_end, d_cursor, sa, -1);
     } else {
-        static bool attr_set_dev[64] = {};
+        static std::atomic<bool> attr_set_dev[64];
         int dev = 0; cudaGetDevice(&dev);
-        bool& attr_set = attr_set_dev[dev & 63];
-        if (!attr_set) { cudaFuncSetAttribute(march_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmemTC)); cudaFuncSetAttribute(march_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmemTC)); cudaFuncSetAttribute(march_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(MarchSmemTC) + kSchedSmem)); attr_set = true; }
+        std::atomic<bool>& attr_set = attr_set_dev[dev & 63];
+        if (!attr_set.load(std::memory_order_acquire)) { cudaFuncSetAttribute(march_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmemTC)); cudaFuncSetAttribute(march_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmemTC)); cudaFuncSetAttribute(march_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(MarchSmemTC) + kSchedSmem)); attr_set.store(true, std::memory_order_release); }
         if (sa.pass == 2) launch_march_variant(march_kernel<true, true>, num_sms * per_sm, kTile * kGroupsTC, sizeof(MarchSmemTC) + kSchedSmem, s, false, P, M, d_queue, d_counters, out, n_pixels, debug_flags, d_range_end, d_cursor, sa, -1);
         else if (overlap_init_ctas >= 0) launch_march_variant(march_kernel<true, false, true>, num_sms * per_sm, kTile * kGroupsTC, sizeof(MarchSmemTC), s, true, P, M, d_queue, d_counters, out, n_pixels, debug_flags, d_range_end, d_cursor, sa, overlap_init_ctas);
         else launch_march_variant(march_kernel<true, false>, num_sms * per_sm, kTile * kGroupsTC, sizeof(MarchSmemTC), s, false, P, M, d_queue, d_counters, out, n_pixels, debug_flags, d_range_end, d_cursor, sa, -1);
@@ -1571,10 +1570,10 @@ __global__ void __launch_bounds__(kTile * kGroupsTC) probe_kernel(FrameParams P,
 void launch_probe(const FrameParams& P, const DeviceModel& M, const float* d_points_world, const float dir[3], int64_t n, int mode, float* d_out,
                   uint32_t debug_flags, int num_sms, cudaStream_t s) {
     if (n <= 0) return;
-    static bool attr_set_dev[64] = {};
+    static std::atomic<bool> attr_set_dev[64];
     int dev = 0; cudaGetDevice(&dev);
-    bool& attr_set = attr_set_dev[dev & 63];
-    if (!attr_set) { cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmemTC)); attr_set = true; }
+    std::atomic<bool>& attr_set = attr_set_dev[dev & 63];
+    if (!attr_set.load(std::memory_order_acquire)) { cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MarchSmemTC)); attr_set.store(true, std::memory_order_release); }
     const int64_t per = kTile * kGroupsTC, want = (n + per - 1) / per, cap = (int64_t)num_sms * 2;
     probe_kernel<<<(unsigned)(want < cap ? want : cap), kTile * kGroupsTC, sizeof(MarchSmemTC), s>>>(P, M, d_points_world, dir[0], dir[1], dir[2], n, mode, d_out, debug_flags);
 }

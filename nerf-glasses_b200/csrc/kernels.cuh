@@ -78,11 +78,17 @@ void launch_fill_background(const FrameParams& P, void* d_image, cudaStream_t s)
 inline size_t pixel_bytes(int out_format) { return out_format == kPixelU8 ? 4 : (out_format == kPixelF16 ? 8 : 16); }
 void launch_gather_signal(uint32_t* d_flag, uint32_t seq, cudaStream_t s);
 void launch_gather_wait(uint32_t* d_flags, int first, int count, uint32_t seq, uint32_t* d_err, cudaStream_t s);
-// ray set-up of the owned rows: background_kernel (every pixel outside the tile box of the two screen rectangles) + init_rays_kernel
-// (the tile box).  Returns the number of CTAs of init_rays_kernel (what an overlapped march launch has to wait for; 0: not launched).
+// The set-up kernel only covers the TILE BOX: the 16 x 8 pixel tiles [x0, x0 + nx) x [y0, y0 + ny) of local (owned) rows that the
+// union of the two screen rectangles touches; everything else is background, written by the background kernel.  nx == 0: no
+// rectangle in view, no set-up kernel at all.  (rot_x, rot_y): first CTA column / row over the occupied cells, relative to the box.
+struct TileBox { int x0, y0, nx, ny; unsigned rot_x, rot_y; };
+TileBox compute_tile_box(const FrameParams& P, int rows_owned);
+// every owned pixel outside the tile box (+ the L2 prefetch of the hash table when prefetch_table); independent of the mesh stage
+// and of the set-up kernel, so a frame runs it on a side stream
+void launch_background(const FrameParams& P, const DeviceModel& M, const FrameOut& out, int rows_owned, const TileBox& box, bool prefetch_table, int num_sms, cudaStream_t s);
+// ray set-up of the tile box.  Returns the number of CTAs launched (what an overlapped march launch has to wait for; 0: not launched).
 int launch_init_rays(const FrameParams& P, const DeviceModel& M, const MeshDevice& mesh, const unsigned long long* d_zbuf, int rows_owned,
-                     float4* d_queue, uint32_t* d_counters, const FrameOut& out, int num_sms, cudaStream_t s, bool reset_counters = true, uint32_t* d_surf_list = nullptr, int first_pass = -1);
-// (first_pass: 1 / 0 = this is / is not the frame's first set-up pass, -1 = it is iff reset_counters)
+                     float4* d_queue, uint32_t* d_counters, const FrameOut& out, const TileBox& box, cudaStream_t s, uint32_t* d_surf_list = nullptr);
 // n_pixels: pixels traced by this context in this pass (the reference's m_n_rays_initialized), for SurfaceMode auto
 void launch_march(const FrameParams& P, const DeviceModel& M, const float4* d_queue, uint32_t* d_counters, const FrameOut& out,
                   uint32_t n_pixels, uint32_t debug_flags, int num_sms, cudaStream_t s, const uint32_t* d_range_end = nullptr, uint32_t* d_cursor = nullptr,

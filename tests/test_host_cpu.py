@@ -300,3 +300,31 @@ def test_gltf_loader_tangents_and_texture_slots(tmp_path):
     n = g["normals"] / np.linalg.norm(g["normals"], axis=1, keepdims=True)
     assert float(np.abs(np.einsum("ij,ij->i", b["tangents"][:, :3], n)).max()) <= 1e-4      # perpendicular to the normal, unit length
     assert float(np.abs(np.linalg.norm(b["tangents"][:, :3], axis=1) - 1).max()) <= 1e-5
+
+
+def test_integration_pybind11_stub_compiles_and_binds(tmp_path):
+    """INTEGRATION.md section B shows the pybind11 module a reference maintainer would compile instead of src/python_api.cu.
+    The test compiles exactly that text against include/nmr.h and libnmr.so and imports the result: the stub cannot rot."""
+    import subprocess
+    import sys
+    import sysconfig
+    import pybind11
+    import pynmr
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    code = re.search(r"```cpp\n(// pynmr_libnmr\.cpp.*?)```", text, re.S).group(1)
+    src = tmp_path / "pynmr_libnmr.cpp"
+    src.write_text(code)
+    libdir = os.path.dirname(pynmr.LIB_PATH)
+    out = tmp_path / ("pynmr_stub" + sysconfig.get_config_var("EXT_SUFFIX"))
+    code_named = code.replace("PYBIND11_MODULE(pynmr, m)", "PYBIND11_MODULE(pynmr_stub, m)")     # (do not shadow the ctypes shim)
+    src.write_text(code_named)
+    cmd = ["g++", "-O1", "-std=c++17", "-shared", "-fPIC", f"-I{pybind11.get_include()}", f"-I{sysconfig.get_paths()['include']}",
+           f"-I{os.path.join(ROOT, 'include')}", str(src), f"-L{libdir}", "-l:libnmr.so", f"-Wl,-rpath,{libdir}", "-o", str(out)]
+    subprocess.check_call(cmd)
+    probe = ("import sys; sys.path.insert(0, %r); import pynmr_stub as m; "
+             "assert hasattr(m, 'NerfMeshRenderer') and hasattr(m, 'Testbed') and hasattr(m, 'free_temporary_memory'); "
+             "names = dir(m.NerfMeshRenderer); "
+             "assert all(n in names for n in ('frame', 'load_nerf', 'load_mesh', 'remove_floaties', 'orbit', 'envmap', 'view_projection_mat')); "
+             "print('ok')") % str(tmp_path)
+    res = subprocess.run([sys.executable, "-c", probe], capture_output=True, text=True)
+    assert res.returncode == 0 and "ok" in res.stdout, res.stderr[-2000:]

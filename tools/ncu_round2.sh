@@ -10,6 +10,8 @@ export NMR_NO_OVERLAP=1     # the serial variant: CUDA events and ncu see the ma
 python tools/profile_frame.py --frames 4 > $O/r2_pf_opaque.log 2>&1 || exit 1
 python tools/profile_frame.py --frames 4 --zoom 4 --regime translucent > $O/r2_pf_translucent.log 2>&1 || exit 1
 ncu --set full --import-source on --clock-control none -k regex:march_kernel --launch-skip 2 -c 1 -f -o $O/r2_march_opaque python tools/profile_frame.py --frames 4 > $O/r2_ncu_o.log 2>&1
-ncu --set full --import-source on --clock-control none -k regex:march_kernel --launch-skip 4 -c 1 -f -o $O/r2_march_translucent python tools/profile_frame.py --frames 4 --zoom 4 --regime translucent > $O/r2_ncu_t.log 2>&1
+ncu --set full --import-source on --clock-control none -k regex:march_kernel --launch-skip 2 -c 1 -f -o $O/r2_march_translucent python tools/profile_frame.py --frames 4 --zoom 4 --regime translucent > $O/r2_ncu_t.log 2>&1
 ncu --set full --import-source on --clock-control none -k regex:init_rays_kernel --launch-skip 2 -c 1 -f -o $O/r2_init_rays python tools/profile_frame.py --frames 4 > $O/r2_ncu_i.log 2>&1
-tail -3 $O/r2_pf_opaque.log $O/r2_pf_translucent.log $O/r2_ncu_o.log $O/r2_ncu_t.log
+python tools/profile_frame.py --frames 4 --zoom 4 --regime translucent --log2T 24 > $O/r2_pf_translucent_T24.log 2>&1 || exit 1
+ncu --set full --import-source on --clock-control none -k regex:march_kernel --launch-skip 2 -c 1 -f -o $O/r2_march_translucent_T24 python tools/profile_frame.py --frames 4 --zoom 4 --regime translucent --log2T 24 > $O/r2_ncu_t24.log 2>&1
+for f in $O/r2_pf_opaque.log $O/r2_pf_translucent.log $O/r2_pf_translucent_T24.log; do tail -n 2 $f; done
