@@ -752,6 +752,7 @@ NMR_API int nmr_create(int width, int height, int device, nmr_ctx** out_ctx) {
     if (const char* v = std::getenv("NMR_MLP")) if (!std::strcmp(v, "scalar")) ctx->debug_flags |= kDebugScalarMlp;
     if (const char* v = std::getenv("NMR_UMMA_SWAP")) if (!std::strcmp(v, "1")) ctx->debug_flags |= kDebugSwapLboSbo;
     if (const char* v = std::getenv("NMR_NO_SHARED_ENCODE")) if (!std::strcmp(v, "1")) ctx->debug_flags |= kDebugNoSharedEncode;
+    if (const char* v = std::getenv("NMR_NO_BRICKS")) if (!std::strcmp(v, "1")) ctx->debug_flags |= kDebugNoBricks;
     *out_ctx = ctx.release();
     return NMR_OK;
 }
