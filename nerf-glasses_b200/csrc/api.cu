@@ -75,7 +75,6 @@ struct Mesh {
     float t[3], s[3], r[4];
 };
 
-constexpr size_t kQueueSlack = 32768;   // >= ray groups of a march launch (SMs x CTAs per SM x 32)
 
 struct Surfaces {
     int w = 0, h = 0;

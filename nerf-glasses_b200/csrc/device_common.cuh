@@ -5,6 +5,9 @@
 // expressions evaluate to (pinned on the host against the reference headers, tests/golden/ref_vectors.npz).  That
 // makes ray set-up, occupancy traversal (t, Morton cell, mip) and the fp16 hash-grid features reproducible to the bit.
 #pragma once
+#ifdef NMR_CHECKED
+#include <cstdio>
+#endif
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -18,6 +21,15 @@ constexpr int N_LEVELS = 16;
 constexpr int ENC_WIDTH = 32;
 
 // ---- plain data handed to kernels by value ------------------------------------------------------------------
+// Checked build (-DNMR_CHECKED, tools/all_paths.py): every index that reaches global memory is tested against the size of
+// its buffer and a violation stops the kernel with file:line.  compute-sanitizer is not available on the B200 pool; this build
+// is its stand-in for the index arithmetic of the traversal, the encoder, the ray queue and the frame writes.  Off: no code.
+#ifdef NMR_CHECKED
+#define NMR_DEVICE_CHECK(cond) do { if (!(cond)) { printf("nmr check failed: %s  (%s:%d, block %d thread %d)\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, (int)threadIdx.x); __trap(); } } while (0)
+#else
+#define NMR_DEVICE_CHECK(cond) ((void)0)
+#endif
+
 struct DeviceModel {
     const __half2* grid;              // hash-table entries, all levels back to back
     const __half* mlp;                // density net | rgb net, row-major [out][in] (params_binary order)
@@ -219,6 +231,7 @@ __device__ __forceinline__ uint32_t cascaded_grid_idx_at(V3 pos, uint32_t mip) {
 __device__ __forceinline__ bool occupied_at(V3 pos, const uint8_t* __restrict__ bitfield, uint32_t mip, uint32_t* cell_out = nullptr) {
     const uint32_t idx = cascaded_grid_idx_at(pos, mip);
     if (cell_out) *cell_out = idx;
+    NMR_DEVICE_CHECK(idx < GRID_CELLS && mip < 8u);
     return __ldg(bitfield + idx / 8 + (GRID_CELLS / 8) * mip) & (1u << (idx % 8));
 }
 __device__ __forceinline__ float distance_to_next_voxel(V3 pos, V3 dir, V3 idir, uint32_t res) {
@@ -558,6 +571,7 @@ __device__ __forceinline__ __half2 encode_level_t(const DeviceModel& M, int leve
         const uint32_t res = M.brick_res[level];
         if (c.gx < res && c.gy < res && c.gz < res) {
             const uint4* __restrict__ b = M.brick[level] + 2u * ((c.gz * res + c.gy) * res + c.gx);
+            NMR_DEVICE_CHECK(M.brick[level] != nullptr && res > 0u && res <= 256u);
             uint32_t r[8];
             asm("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(b));
@@ -571,7 +585,7 @@ __device__ __forceinline__ __half2 encode_level_t(const DeviceModel& M, int leve
         level_indices(M, level, c.gx, c.gy, c.gz, index);
         const __half2* __restrict__ grid = M.level_ptr[level];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = __ldg(grid + index[k]);
+        for (int k = 0; k < 8; ++k) { NMR_DEVICE_CHECK(index[k] < M.level_size[level]); v[k] = __ldg(grid + index[k]); }
     }
     return blend_corners(v, c);
 }

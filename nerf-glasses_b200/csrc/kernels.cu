@@ -207,6 +207,7 @@ __global__ void __launch_bounds__(256) mesh_raster_kernel(MeshDevice mesh, Frame
         float t, u, v;
         if (ray_tri(eye, dir, v0, v1, v2, t, u, v) && t < 1e16f) {
             const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | tri;
+            NMR_DEVICE_CHECK(y >= by0 && y - by0 < P.zb_h && x >= bx0 && x - bx0 < P.zb_w);
             atomicMin(zwin + (size_t)(y - by0) * P.zb_w + (x - bx0), key);
         }
     }
@@ -356,6 +357,7 @@ __device__ __forceinline__ void lens_plate_shift(const FrameParams& P, V3 dir, V
 // (S/ngp/testbed.cu:907-931; S/ngp/render_buffer.cu:232-267, 327-346, 537-566) fused into the ray's last step
 // =================================================================================================================
 __device__ __forceinline__ void finish_pixel(const FrameParams& P, const FrameOut& out, uint32_t idx, float r, float g, float b, float a, float depth, uint32_t n_samples) {
+    NMR_DEVICE_CHECK(idx < (uint32_t)(P.width * P.height));
     float4 fb = make_float4(0.f, 0.f, 0.f, 0.f);
     float d = 1e10f;
     if (a > 0.001f) {   // compact_kernel_nerf's hit criterion
@@ -447,6 +449,7 @@ __device__ __forceinline__ void init_one_ray(const FrameParams& P, const DeviceM
         return;
     }
     const uint32_t slot = atomicAdd(&counters[0], 1u);
+    NMR_DEVICE_CHECK(slot < (uint32_t)(P.width * P.height));
     queue[(size_t)slot * kRayRecordFloat4s + 0] = make_float4(r.dir.x, r.dir.y, r.dir.z, t);
     const bool carries_surface = L.w == 0.f && t_surface != 0.0f && surf[3] > 0.f;
     if (carries_surface && surf_list) surf_list[atomicAdd(&counters[7], 1u)] = slot;
@@ -1154,6 +1157,7 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH
                 } else {
                     slot = my_slot;
                 }
+                NMR_DEVICE_CHECK(slot < (uint32_t)(P.width * P.height) + kQueueSlack);
                 if (overlap) {
                     waiting = false;
                     // the record is there when its ready word is; when it is not and the set-up kernel has finished, re-read once (a
@@ -1171,6 +1175,7 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH
                 } else if (slot >= n_end) { exhausted = true; break; }
                 if (overlap) my_slot = kEmptyRecord;
                 if (pass2) slot = __ldg(sched.surf_list + slot);
+                NMR_DEVICE_CHECK(slot < (uint32_t)(P.width * P.height));
                 // (L2 loads: the records may have been written while this kernel was running)
                 const float4 q0 = __ldcg(queue + (size_t)slot * kRayRecordFloat4s), q1 = __ldcg(queue + (size_t)slot * kRayRecordFloat4s + 1), q2 = __ldcg(queue + (size_t)slot * kRayRecordFloat4s + 2);
                 dir = v3(q0.x, q0.y, q0.z); t = q0.w; t_start = q1.x; t_surface = q1.y; idx = __float_as_uint(q1.z); t_limit = q1.w;

@@ -47,6 +47,7 @@ constexpr int kRayRecordFloat4s = 3;   // queue record: (dir.xyz, t) (t_start, t
 // reads it first, with acquire semantics - so the march kernel can consume the queue while the set-up kernel is still appending to
 // it (overlapped frames).  Records that are not (yet) written hold kEmptyRecord there: the queue is filled with it when it is
 // allocated, and every frame's clear kernel resets the records of the frame before.
+constexpr uint32_t kQueueSlack = 32768;   // records allocated past width x height: >= ray groups of a march launch (SMs x CTAs per SM x 32), each of which may hold one slot past the last record in an overlapped frame
 constexpr uint32_t kEmptyRecord = 0xFFFFFFFFu;
 
 enum DebugFlags : uint32_t {
