@@ -511,7 +511,7 @@ void enqueue_pass(nmr_ctx* ctx, Nerf& n, const FrameParams& P, bool timed, void*
     if (!image_target) { S.image_format = P.out_format; S.image_is_frame = false; }
     static const char* phase_log_path = std::getenv("NMR_PHASE_LOG");      // measurement aid: see FrameOut::phase_log
     if (phase_log_path && timed) {
-        const size_t words = (size_t)ctx->num_sms * 4 * 2 * kPhaseIters * 5;
+        const size_t words = (size_t)ctx->num_sms * 4 * 2 * kPhaseIters * kPhaseWords;
         ctx->d_phase_log.ensure(words);
         CK(cudaMemsetAsync(ctx->d_phase_log.p, 0, words * 8, ctx->stream));
         out.phase_log = ctx->d_phase_log.p;

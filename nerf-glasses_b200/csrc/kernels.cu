@@ -1065,8 +1065,8 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH
     uint32_t tile_iter = 0;
     unsigned long long* plog = nullptr;
     if (TC && !PASS2 && out.phase_log && (threadIdx.x % kTile) == 0)
-        plog = out.phase_log + ((size_t)blockIdx.x * kGroupsTC + threadIdx.x / kTile) * kPhaseIters * 5;
-#define NMR_PLOG(k) do { if (plog && tile_iter < (uint32_t)kPhaseIters) plog[tile_iter * 5 + (k)] = clock64(); } while (0)
+        plog = out.phase_log + ((size_t)blockIdx.x * kGroupsTC + threadIdx.x / kTile) * kPhaseIters * kPhaseWords;
+#define NMR_PLOG(k) do { if (plog && tile_iter < (uint32_t)kPhaseIters) { plog[tile_iter * kPhaseWords + (k)] = clock64(); if ((k) == 0) { unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); plog[tile_iter * kPhaseWords + 5] = gt_; } } } while (0)
 #define NMR_PLOG_NEXT() (++tile_iter)
 #else
 #define NMR_PLOG(k) do { } while (0)
@@ -1349,6 +1349,7 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH
         NMR_PLOG(4);
         NMR_PLOG_NEXT();
     }
+    NMR_PLOG(0);      // (exit stamp)
 
     // evaluated-sample counter: one atomic per warp
     for (int o = 16; o > 0; o >>= 1) evaluated += __shfl_xor_sync(0xffffffffu, evaluated, o);

@@ -17,10 +17,10 @@ struct FrameOut {
     float4* lens;         // lens hand-off per pixel, 2 x W*H: (normal.xyz, t_lens) (coverage, -, -, -); null when the frame has no lens
     float* lens_scratch;  // per ray group of the march kernel: state parked across the segments of a lens ray (kLensStash floats each)
     // measurement aid (NMR_PHASE_LOG): per warpgroup of the march kernel and tile iteration, clock64 at the iteration's start, after
-    // batch generation, after the encoding, after the network, after compositing: [n_warpgroups][kPhaseIters][5]; null normally
+    // batch generation, after the encoding, after the network, after compositing, and globaltimer (ns) at the start; the warpgroup's last entry is its exit from the loop (start stamps only): [n_warpgroups][kPhaseIters][kPhaseWords]; null normally
     unsigned long long* phase_log;
 };
-constexpr int kPhaseIters = 16;
+constexpr int kPhaseIters = 32, kPhaseWords = 6;
 // The reference's n_steps schedule for frames with MORE than 1/8 live pixels (SurfaceMode auto): pass 1 marches every ray and
 // histograms the sample index at which each ray dies; pass 2 replays clamp(pixels / live rays, 1, 8) per wavefront iteration
 // over that histogram and re-marches the rays that carry a mesh surface with those batch sizes.
