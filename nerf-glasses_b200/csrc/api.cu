@@ -580,9 +580,10 @@ void enqueue_pass(nmr_ctx* ctx, Nerf& n, const FrameParams& P, bool timed, void*
 
 // nmr_render's single-sample path: the image crosses PCIe underneath the rendering instead of after it.
 // Rows above and below both screen rectangles (occupied box, mesh) are background whatever the GPU does - the host knows them
-// before anything is launched, and in render.py's framing they are most of the picture.  They leave at once on the copy stream
-// from an image of nothing but the background colour, so the copy engine, which bounds a float32 call, starts at time zero; the
-// rows in between follow as one block when the frame (one overlapped pass, exactly as in frame()) is complete.
+// before anything is launched, and in render.py's framing they are most of the picture; so are the columns left and right of the
+// rectangles in the rows in between.  They leave at once on the copy stream from an image of nothing but the background colour,
+// so the copy engine, which bounds a float32 call, starts at time zero; only the rectangle itself (a 2-D copy) waits for the
+// frame (one overlapped pass, exactly as in frame()) - for the compact formats that is what is left on the critical path.
 void enqueue_pass_with_copy(nmr_ctx* ctx, Nerf& n, const FrameParams& P0, void* out_host) {
     Surfaces& S = ctx->surf;
     const size_t bpp = pixel_bytes(P0.out_format);
@@ -591,16 +592,35 @@ void enqueue_pass_with_copy(nmr_ctx* ctx, Nerf& n, const FrameParams& P0, void* 
         const size_t off = (size_t)y0 * P0.width * bpp;
         CK(cudaMemcpyAsync(static_cast<char*>(out_host) + off, static_cast<const char*>(src) + off, (size_t)(y1 - y0) * P0.width * bpp, cudaMemcpyDeviceToHost, ctx->copy_stream));
     };
+    auto copy_rect = [&](int y0, int y1, int x0, int x1, const void* src) {      // columns [x0, x1) of rows [y0, y1)
+        if (y1 <= y0 || x1 <= x0) return;
+        if (x0 == 0 && x1 == P0.width) { copy_rows(y0, y1, src); return; }
+        const size_t pitch = (size_t)P0.width * bpp, off = (size_t)y0 * pitch + (size_t)x0 * bpp;
+        CK(cudaMemcpy2DAsync(static_cast<char*>(out_host) + off, pitch, static_cast<const char*>(src) + off, pitch, (size_t)(x1 - x0) * bpp, (size_t)(y1 - y0), cudaMemcpyDeviceToHost, ctx->copy_stream));
+    };
     int known_top = 0, known_bot = P0.height;          // rows [0, known_top) and [known_bot, H) are known background
+    int known_left = 0, known_right = P0.width;        // and so are columns [0, known_left) and [known_right, W) of the rows in between
     {
-        int r0 = P0.height, r1 = 0;                    // rows that may hold anything else: union of the rectangles
-        if (P0.occ_px[2] > P0.occ_px[0] && P0.occ_px[3] > P0.occ_px[1]) { r0 = std::min(r0, P0.occ_px[1]); r1 = std::max(r1, P0.occ_px[3]); }
+        int r0 = P0.height, r1 = 0, c0 = P0.width, c1 = 0;   // pixels that may hold anything else: union of the rectangles
+        if (P0.occ_px[2] > P0.occ_px[0] && P0.occ_px[3] > P0.occ_px[1]) {
+            r0 = std::min(r0, P0.occ_px[1]); r1 = std::max(r1, P0.occ_px[3]); c0 = std::min(c0, P0.occ_px[0]); c1 = std::max(c1, P0.occ_px[2]);
+        }
         if (P0.mesh_scale > 0 && P0.zb_w > 0 && P0.zb_h > 0) {
             r0 = std::min(r0, P0.zb_y0 / P0.mesh_scale); r1 = std::max(r1, (P0.zb_y0 + P0.zb_h + P0.mesh_scale - 1) / P0.mesh_scale);
+            c0 = std::min(c0, P0.zb_x0 / P0.mesh_scale); c1 = std::max(c1, (P0.zb_x0 + P0.zb_w + P0.mesh_scale - 1) / P0.mesh_scale);
         }
-        if (r1 <= r0) { known_top = P0.height; known_bot = P0.height; } else { known_top = std::max(0, r0); known_bot = std::min(P0.height, r1); }
+        if (r1 <= r0 || c1 <= c0) { known_top = P0.height; known_bot = P0.height; }
+        else {
+            known_top = std::max(0, r0); known_bot = std::min(P0.height, r1);
+            known_left = std::max(0, c0) & ~15; known_right = std::min(P0.width, (c1 + 15) & ~15);      // (whole 64-byte runs of the narrowest format)
+        }
         static const bool off = std::getenv("NMR_NO_KNOWN_ROWS") != nullptr;      // A/B aid
         if (off) { known_top = 0; known_bot = P0.height; }
+        static const bool off_cols = std::getenv("NMR_NO_KNOWN_COLS") != nullptr;
+        // Strips cost three more (2-D) copies: a win when the rectangle's copy is what the call waits for after the frame (sRGB8:
+        // 3230 -> 3650 calls/s at 1080p), a loss when the call is bound by PCIe as a whole (float32: 1500 -> 1440;
+        // profiles/r2_e2e_paths.txt).  Images up to 12 MiB take the strips.
+        if (off || off_cols || (size_t)P0.width * P0.height * bpp > ((size_t)12 << 20)) { known_left = 0; known_right = P0.width; }
         const size_t px = (size_t)P0.width * P0.height;
         if (S.bg_pixels != px || S.bg_format != P0.out_format || std::memcmp(S.bg_value, P0.background_out, 16) != 0) {
             S.bg_image.ensure(px);      // (float4 capacity: enough for every format)
@@ -616,9 +636,11 @@ void enqueue_pass_with_copy(nmr_ctx* ctx, Nerf& n, const FrameParams& P0, void* 
     enqueue_pass(ctx, n, P0, true);
     copy_rows(0, known_top, S.bg_image.p);
     copy_rows(known_bot, P0.height, S.bg_image.p);
+    copy_rect(known_top, known_bot, 0, known_left, S.bg_image.p);
+    copy_rect(known_top, known_bot, known_right, P0.width, S.bg_image.p);
     CK(cudaEventRecord(ctx->ev_rows, ctx->stream));
     CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rows, 0));
-    copy_rows(known_top, known_bot, S.image.p);
+    copy_rect(known_top, known_bot, known_left, known_right, S.image.p);
     CK(cudaGetLastError());
 }
 
