@@ -238,6 +238,25 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
     r.synchronize(); barrier()
     e2e_u8_s = time.perf_counter() - t0
 
+    # ---- the image kept by the caller and updated in place (Testbed.render_update, an addition): the same complete image in host
+    # memory after every call, but only the screen rectangle of head + mesh crosses PCIe - reported beside e2e, not instead of it ----
+    upd = {}
+    for name, dt in (("float32", np.float32), ("uint8", np.uint8)):
+        held = None
+        for _ in range(3):
+            a += 0.03; r.orbit(*orbit_step(a)); held = nerf.render_update(held, W, H, linear=False, dtype=dt)
+        r.synchronize(); barrier()
+        t0 = time.perf_counter()
+        moved = 0
+        for _ in range(args.steps):
+            a += 0.03; r.orbit(*orbit_step(a))
+            held = nerf.render_update(held, W, H, linear=False, dtype=dt)
+            checksum += float(held[H // 2, W // 2, 0]) / (255.0 if dt is np.uint8 else 1.0)
+            moved += nerf.last_update_bytes
+        r.synchronize(); barrier()
+        upd[name] = (time.perf_counter() - t0, moved / args.steps)
+        del held
+
     # what the L2 of this GPU delivers (roofline denominators; rank 0)
     l2_copy_gbs = l2_gather_gbs = None
     if rank == 0:
@@ -246,10 +265,11 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
     # max over ranks
     if dist is not None:
         import torch
-        t = torch.tensor([total_dev_ms, e2e_s, float(samples), float(np.sum(march_ms)), e2e_u8_s], dtype=torch.float64, device=f"cuda:{local_rank}")
+        t = torch.tensor([total_dev_ms, e2e_s, float(samples), float(np.sum(march_ms)), e2e_u8_s, upd["float32"][0], upd["uint8"][0]], dtype=torch.float64, device=f"cuda:{local_rank}")
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         total_dev_ms, e2e_s, e2e_u8_s = float(tmax[0]), float(tmax[1]), float(tmax[4])
+        upd = {"float32": (float(tmax[5]), upd["float32"][1]), "uint8": (float(tmax[6]), upd["uint8"][1])}
         samples_all = float(tsum[2])
     else:
         samples_all = float(samples)
@@ -279,6 +299,11 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
         "e2e_u8": {"value": rays_all / e2e_u8_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 48, "d2h_bytes_per_step": W * H * 4,
                    "fps": args.steps * world / e2e_u8_s,
                    "api": "pynmr.Testbed.render(width, height, 1, linear=False, dtype=np.uint8) -> pinned uint8[H,W,4] == np.uint8(float_image * 255), render.py's next line"},
+        "e2e_update": {k: {"value": rays_all / v[0] / 1e6, "unit": "Mrays/s", "fps": args.steps * world / v[0], "h2d_bytes_per_step": 48,
+                           "d2h_bytes_per_step": v[1], "full_image_bytes": W * H * (16 if k == "float32" else 4)} for k, v in upd.items()}
+                      | {"api": "img = pynmr.Testbed.render_update(img, width, height, linear=False, dtype=...): the caller keeps the pinned image, the call "
+                                "moves the screen rectangle of head + mesh (old and new) and leaves the background pixels, which are already there; "
+                                "bit-identical to render() after every call (tests/test_gpu_update.py); d2h_bytes_per_step = bytes actually moved (rank 0)"},
         "gpu_launches": int(launches),
         # The dominant kernel gathers from a hash table that is L2-resident (23 MiB at log2_hashmap_size 19, DRAM traffic per launch
         # ~0.1x the algorithmic bytes): the bound is the L2 -> SM path, measured on this GPU by nmr_measure_l2 just now.

@@ -167,6 +167,9 @@ struct nmr_ctx {
     nmr_stats stats{};
     bool stats_pending = false;
     std::string envmap_path;
+    // nmr_render_update: host images this context has filled and may update in place - the pixels outside `rect` hold the background
+    struct HostImage { void* p; int w, h, fmt; float bg[4]; int rect[4]; };
+    std::vector<HostImage> host_images;
     DevBuf<uint8_t> d_flush;
     DevBuf<unsigned long long> d_phase_log;               // NMR_PHASE_LOG (measurement aid)
 };
@@ -584,19 +587,25 @@ void enqueue_pass(nmr_ctx* ctx, Nerf& n, const FrameParams& P, bool timed, void*
 // rectangles in the rows in between.  They leave at once on the copy stream from an image of nothing but the background colour,
 // so the copy engine, which bounds a float32 call, starts at time zero; only the rectangle itself (a 2-D copy) waits for the
 // frame (one overlapped pass, exactly as in frame()) - for the compact formats that is what is left on the critical path.
-void enqueue_pass_with_copy(nmr_ctx* ctx, Nerf& n, const FrameParams& P0, void* out_host) {
+// `known` (nmr_render_update): the destination already holds a complete image of this size / format / background whose pixels
+// outside known->rect are background (it is the buffer of the previous call and nobody else wrote to it); then only the bounding
+// box of the old and the new rectangle is touched at all.  rect_out receives this frame's rectangle, copied the bytes moved.
+void enqueue_pass_with_copy(nmr_ctx* ctx, Nerf& n, const FrameParams& P0, void* out_host, const int* known_rect = nullptr, int* rect_out = nullptr, size_t* copied = nullptr) {
     Surfaces& S = ctx->surf;
     const size_t bpp = pixel_bytes(P0.out_format);
+    size_t moved = 0;
     auto copy_rows = [&](int y0, int y1, const void* src) {
         if (y1 <= y0) return;
         const size_t off = (size_t)y0 * P0.width * bpp;
         CK(cudaMemcpyAsync(static_cast<char*>(out_host) + off, static_cast<const char*>(src) + off, (size_t)(y1 - y0) * P0.width * bpp, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        moved += (size_t)(y1 - y0) * P0.width * bpp;
     };
     auto copy_rect = [&](int y0, int y1, int x0, int x1, const void* src) {      // columns [x0, x1) of rows [y0, y1)
         if (y1 <= y0 || x1 <= x0) return;
         if (x0 == 0 && x1 == P0.width) { copy_rows(y0, y1, src); return; }
         const size_t pitch = (size_t)P0.width * bpp, off = (size_t)y0 * pitch + (size_t)x0 * bpp;
         CK(cudaMemcpy2DAsync(static_cast<char*>(out_host) + off, pitch, static_cast<const char*>(src) + off, pitch, (size_t)(x1 - x0) * bpp, (size_t)(y1 - y0), cudaMemcpyDeviceToHost, ctx->copy_stream));
+        moved += (size_t)(x1 - x0) * bpp * (size_t)(y1 - y0);
     };
     int known_top = 0, known_bot = P0.height;          // rows [0, known_top) and [known_bot, H) are known background
     int known_left = 0, known_right = P0.width;        // and so are columns [0, known_left) and [known_right, W) of the rows in between
@@ -620,7 +629,7 @@ void enqueue_pass_with_copy(nmr_ctx* ctx, Nerf& n, const FrameParams& P0, void* 
         // Strips cost three more (2-D) copies: a win when the rectangle's copy is what the call waits for after the frame (sRGB8:
         // 3230 -> 3650 calls/s at 1080p), a loss when the call is bound by PCIe as a whole (float32: 1500 -> 1440;
         // profiles/r2_e2e_paths.txt).  Images up to 12 MiB take the strips.
-        if (off || off_cols || (size_t)P0.width * P0.height * bpp > ((size_t)12 << 20)) { known_left = 0; known_right = P0.width; }
+        if (!known_rect && (off || off_cols || (size_t)P0.width * P0.height * bpp > ((size_t)12 << 20))) { known_left = 0; known_right = P0.width; }
         const size_t px = (size_t)P0.width * P0.height;
         if (S.bg_pixels != px || S.bg_format != P0.out_format || std::memcmp(S.bg_value, P0.background_out, 16) != 0) {
             S.bg_image.ensure(px);      // (float4 capacity: enough for every format)
@@ -634,13 +643,23 @@ void enqueue_pass_with_copy(nmr_ctx* ctx, Nerf& n, const FrameParams& P0, void* 
     // The frame's kernels are submitted FIRST: copies submitted to the copy stream ahead of them hold them back until the copies
     // are done (measured: 0.87 ms per float32 call against 0.65 ms this way round, profiles/r2_experiments.md).
     enqueue_pass(ctx, n, P0, true);
-    copy_rows(0, known_top, S.bg_image.p);
-    copy_rows(known_bot, P0.height, S.bg_image.p);
-    copy_rect(known_top, known_bot, 0, known_left, S.bg_image.p);
-    copy_rect(known_top, known_bot, known_right, P0.width, S.bg_image.p);
+    if (known_top >= known_bot) { known_left = 0; known_right = 0; }                 // (nothing but background: an empty rectangle)
+    if (rect_out) { rect_out[0] = known_left; rect_out[1] = known_top; rect_out[2] = known_right; rect_out[3] = known_bot; }
+    // what leaves at once from the background image: everything outside this frame's rectangle - or, when the destination is
+    // known to hold background outside the previous frame's rectangle, just the part of that rectangle this frame no longer covers
+    int bx0 = 0, by0 = 0, bx1 = P0.width, by1 = P0.height;
+    if (known_rect && known_rect[2] > known_rect[0] && known_rect[3] > known_rect[1]) {
+        if (known_top < known_bot) { bx0 = std::min(known_left, known_rect[0]); by0 = std::min(known_top, known_rect[1]); bx1 = std::max(known_right, known_rect[2]); by1 = std::max(known_bot, known_rect[3]); }
+        else { bx0 = known_rect[0]; by0 = known_rect[1]; bx1 = known_rect[2]; by1 = known_rect[3]; known_top = known_bot = by0; known_left = bx0; known_right = bx1; }
+    } else if (known_rect) { bx0 = known_left; by0 = known_top; bx1 = known_right; by1 = known_bot; }
+    copy_rect(by0, known_top, bx0, bx1, S.bg_image.p);
+    copy_rect(known_bot, by1, bx0, bx1, S.bg_image.p);
+    copy_rect(known_top, known_bot, bx0, known_left, S.bg_image.p);
+    copy_rect(known_top, known_bot, known_right, bx1, S.bg_image.p);
     CK(cudaEventRecord(ctx->ev_rows, ctx->stream));
     CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rows, 0));
     copy_rect(known_top, known_bot, known_left, known_right, S.image.p);
+    if (copied) *copied = moved;
     CK(cudaGetLastError());
 }
 
@@ -1147,6 +1166,7 @@ NMR_API int nmr_render_format(nmr_ctx* ctx, int nerf_id, int width, int height, 
         const size_t bpp = pixel_bytes(format);
         Nerf* n;
         try { n = get_nerf(ctx, nerf_id); } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); }
+        ctx->host_images.erase(std::remove_if(ctx->host_images.begin(), ctx->host_images.end(), [&](const nmr_ctx::HostImage& h) { return h.p == out_rgba; }), ctx->host_images.end());
         upload_mesh_if_dirty(ctx);
         ctx->surf.resize(width, height, ctx->mesh_scale);
         ctx->surf.spp = 0;   // reset_accumulation (S/python_api.cu:85)
@@ -1172,6 +1192,33 @@ NMR_API int nmr_render_format(nmr_ctx* ctx, int nerf_id, int width, int height, 
         CK(cudaMemcpyAsync(out_rgba, ctx->surf.image.p, (size_t)width * height * bpp, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         ctx->surf.spp = 0;   // the next frame() starts a fresh accumulation at its own resolution
+        return NMR_OK;
+    });
+}
+NMR_API int nmr_render_update(nmr_ctx* ctx, int nerf_id, int width, int height, int linear, int format, void* out_rgba, int assume_valid, size_t* out_copied_bytes) {
+    return guarded(ctx, [&]() -> int {
+        if (width <= 0 || height <= 0 || !out_rgba) return fail(ctx, NMR_ERR_INVALID, "bad render arguments");
+        if (format < NMR_PIXEL_F32 || format > NMR_PIXEL_U8) return fail(ctx, NMR_ERR_INVALID, "bad pixel format");
+        if (ctx->shard_world != 1) return fail(ctx, NMR_ERR_STATE, "nmr_render_update: not on a sharded context");
+        Nerf* n;
+        try { n = get_nerf(ctx, nerf_id); } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); }
+        upload_mesh_if_dirty(ctx);
+        ctx->surf.resize(width, height, ctx->mesh_scale);
+        ctx->surf.spp = 0;
+        FrameParams P = make_params(ctx, *n, width, height, ctx->cam12, 0, !linear, true);
+        P.out_format = format;
+        auto it = std::find_if(ctx->host_images.begin(), ctx->host_images.end(), [&](const nmr_ctx::HostImage& h) { return h.p == out_rgba; });
+        const bool known = assume_valid != 0 && it != ctx->host_images.end() && it->w == width && it->h == height && it->fmt == format && std::memcmp(it->bg, P.background_out, 16) == 0;
+        nmr_ctx::HostImage rec{out_rgba, width, height, format, {P.background_out[0], P.background_out[1], P.background_out[2], P.background_out[3]}, {0, 0, 0, 0}};
+        const int prev[4] = {known ? it->rect[0] : 0, known ? it->rect[1] : 0, known ? it->rect[2] : 0, known ? it->rect[3] : 0};
+        if (it != ctx->host_images.end()) ctx->host_images.erase(it);        // (re-entered below once the copies are in the stream)
+        size_t moved = 0;
+        enqueue_pass_with_copy(ctx, *n, P, out_rgba, known ? prev : nullptr, rec.rect, &moved);
+        CK(cudaStreamSynchronize(ctx->copy_stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->host_images.size() >= 8) ctx->host_images.erase(ctx->host_images.begin());
+        ctx->host_images.push_back(rec);
+        if (out_copied_bytes) *out_copied_bytes = moved;
         return NMR_OK;
     });
 }

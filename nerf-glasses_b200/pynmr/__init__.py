@@ -108,6 +108,7 @@ def lib():
         "nmr_measure_l2": (C.c_int, [vp, C.c_size_t, C.c_int, fp]),
         "nmr_get_stats": (C.c_int, [vp, C.POINTER(Stats)]),
         "nmr_synchronize": (C.c_int, [vp]),
+        "nmr_render_update": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.POINTER(C.c_size_t)]),
         "nmr_host_alloc": (vp, [C.c_size_t]),
         "nmr_host_free": (None, [vp]),
         "nmr_get_density_bitfield": (C.c_int, [vp, C.c_int, vp]),
@@ -131,7 +132,7 @@ EXPORTED_SYMBOLS = [
     "nmr_get_mesh_transform", "nmr_set_envmap", "nmr_remove_floaties", "nmr_get_render_aabb", "nmr_set_render_aabb",
     "nmr_get_aabb", "nmr_get_background", "nmr_set_background", "nmr_set_min_transmittance", "nmr_orbit", "nmr_get_camera",
     "nmr_set_camera", "nmr_frame", "nmr_frame_async", "nmr_read_frame", "nmr_render", "nmr_render_views", "nmr_set_shard", "nmr_set_surface_insertion", "nmr_set_lens", "nmr_debug_lens", "nmr_get_nerf_info", "nmr_gather_create", "nmr_gather_attach", "nmr_gather_detach", "nmr_get_stream", "nmr_probe_points", "nmr_probe_rays", "nmr_set_tonemap_curve", "nmr_get_tonemap_curve",
-    "nmr_get_device_image", "nmr_copy_device_image", "nmr_flush_l2", "nmr_get_stats", "nmr_synchronize", "nmr_host_alloc", "nmr_host_free", "nmr_get_density_bitfield",
+    "nmr_get_device_image", "nmr_copy_device_image", "nmr_flush_l2", "nmr_get_stats", "nmr_synchronize", "nmr_host_alloc", "nmr_host_free", "nmr_render_update", "nmr_get_density_bitfield",
     "nmr_set_density_bitfield", "nmr_debug_encode", "nmr_debug_network", "nmr_debug_trace", "nmr_debug_mesh",
     "nmr_debug_last_frame", "nmr_debug_set_flags", "nmr_render_format", "nmr_render_views_format", "nmr_debug_parse_gltf", "nmr_measure_l2", "nmr_set_overlap", "nmr_set_model_transform", "nmr_get_model_transform",
     "nmr_dump_density_grid", "nmr_load_density_grid", "nmr_read_combined", "nmr_set_lens_model",
@@ -178,6 +179,7 @@ def _ptr(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
 
 
+_envmap_warned = False
 _pinned_pool: dict = {}     # size in bytes -> [device-registered host pointers ready for reuse]
 
 
@@ -496,6 +498,23 @@ class Testbed:
             self._r._ck(lib().nmr_render_format(self._r._h, self._id, int(width), int(height), int(spp), int(bool(linear)), fmt, _ptr(out)))
         return out
 
+    def render_update(self, out=None, width: int = 1920, height: int = 1080, linear: bool = True, dtype=np.float32) -> np.ndarray:
+        """Addition (include/nmr.h: nmr_render_update): render(spp=1) into an image the caller keeps.  Pass the array the previous
+        call returned as `out` and only the screen rectangle of head and mesh (old and new) crosses PCIe - the rest of the image
+        is the background colour and already there.  The result equals render()'s; `last_update_bytes` says how much was moved.
+        The array is returned read-only: whoever wants to draw into it copies it first (the next update relies on its contents)."""
+        fmt = _pixel_format(dtype)
+        fresh = out is None
+        if fresh:
+            out = _pinned_array((height, width, 4), dtype=np.dtype(dtype))
+        elif out.shape != (height, width, 4) or out.dtype != np.dtype(dtype) or not out.flags.c_contiguous:
+            raise ValueError("render_update: `out` must be the array a previous call returned for this size and dtype")
+        moved = C.c_size_t(0)
+        self._r._ck(lib().nmr_render_update(self._r._h, self._id, int(width), int(height), int(bool(linear)), fmt, C.c_void_p(out.ctypes.data), 0 if fresh else 1, C.byref(moved)))
+        self.last_update_bytes = int(moved.value)
+        out.flags.writeable = False
+        return out
+
     def probe_points(self, points_world, direction) -> np.ndarray:
         """NerfTracer::intersects over world-space points (include/nmr.h: nmr_probe_points) -> alpha per point."""
         pts = np.ascontiguousarray(points_world, dtype=np.float32).reshape(-1, 3)
@@ -620,6 +639,13 @@ class NerfMeshRenderer:
         self._ck(lib().nmr_set_camera(self._h, _f3(a.T.reshape(-1))))
 
     def envmap(self, path: str):
+        """V/render.py:228 calls this, but the reference module has no such method and its renderer no environment map
+        (primary rays over a constant background): accepted so that the script runs, ignored, and said so once."""
+        global _envmap_warned
+        if not _envmap_warned:
+            import warnings
+            warnings.warn("pynmr: envmap() has no effect - the renderer composites over the constant background colour, like the reference", stacklevel=2)
+            _envmap_warned = True
         self._ck(lib().nmr_set_envmap(self._h, os.fsencode(path)))
 
     # -- additions -----------------------------------------------------------------------------------------------
