@@ -422,6 +422,8 @@ FrameParams make_params(nmr_ctx* ctx, const Nerf& n, int W, int H, const float* 
     std::memcpy(P.taabb_min, n.host.aabb_min, 12); std::memcpy(P.taabb_max, n.host.aabb_max, 12);
     P.cone_angle = n.host.cone_angle_constant;
     P.spp_index = spp_index;
+    static const int debug_pixel = [] { const char* v = std::getenv("NMR_DEBUG_PIXEL"); return v ? std::atoi(v) : -1; }();
+    P.debug_pixel = debug_pixel;
     P.min_transmittance = n.min_transmittance;
     P.rgb_activation = n.host.rgb_activation; P.density_activation = n.host.density_activation;
     std::memcpy(P.background, n.background, 16);

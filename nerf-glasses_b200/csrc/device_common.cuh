@@ -110,6 +110,7 @@ struct FrameParams {
     // NeRF-space ray origin = R eye + 0.5 + R t_model (evaluated on the host, make_params).  The identity leaves eye + 0.5.
     float model_rot[9];               // row-major
     float ray_origin[3];
+    int debug_pixel;                  // checked builds (-DNMR_CHECKED): the march kernel narrates this pixel's ray (NMR_DEBUG_PIXEL), -1: none
 };
 
 // Displayed image formats.  kPixelU8 is what render.py turns every frame into on the host (np.uint8(img * 255), V/render.py:62-66):

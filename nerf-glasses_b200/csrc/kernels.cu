@@ -221,7 +221,7 @@ __global__ void frame_clear_kernel(uint32_t* __restrict__ counters, uint32_t* __
     const uint32_t prev = counters[kCntPrevCount];
     if (queue) for (size_t k = i; k < (size_t)prev; k += stride) reinterpret_cast<uint32_t*>(queue + k * kRayRecordFloat4s + 1)[2] = kEmptyRecord;
     if (i < (size_t)kFrameCounters) counters[i] = 0u;
-    if (i == 0) { counters[kCntMarchStart] = 0xFFFFFFFFu; counters[kCntMarchStart + 1] = 0xFFFFFFFFu; counters[kCntMarchEnd] = 0u; counters[kCntMarchEnd + 1] = 0u; }
+    if (i == 0) { counters[kCntLensRays] = 0u; counters[kCntMarchStart] = 0xFFFFFFFFu; counters[kCntMarchStart + 1] = 0xFFFFFFFFu; counters[kCntMarchEnd] = 0u; counters[kCntMarchEnd + 1] = 0u; }
     if (hist) for (size_t k = i; k < kSchedBins; k += stride) hist[k] = 0u;
     if (zbuf2) for (size_t k = i; k < zbuf_pairs; k += stride) zbuf2[k] = make_ulonglong2(~0ull, ~0ull);
 }
@@ -457,6 +457,7 @@ __device__ __forceinline__ void init_one_ray(const FrameParams& P, const DeviceM
     q1[0] = t_start; q1[1] = t_surface; q1[3] = r.t_limit;
     queue[(size_t)slot * kRayRecordFloat4s + 2] = make_float4(surf[0], surf[1], surf[2], surf[3]);
     if (L.w > 0.f) {
+        atomicAdd(&counters[kCntLensRays], 1u);
         const V3 ln = model_rotate(P, L.n);     // the mirror direction is taken in NeRF space
         out.lens[(size_t)idx * 2] = make_float4(ln.x, ln.y, ln.z, L.t);
         out.lens[(size_t)idx * 2 + 1] = make_float4(L.w, 0.f, 0.f, 0.f);
@@ -991,7 +992,8 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH
     // this launch consumes the queue records [*cursor at launch, *range_end): the whole queue of a frame (range_end =
     // &counters[0], cursor = &counters[1]) or one band of it (nmr_render's copy-overlapped bands); the surface rule always
     // looks at the whole frame's live-ray count
-    const uint32_t n_rays = overlap ? 0u : counters[0], n_end = overlap ? 0u : *range_end;
+    uint32_t n_rays = 0u, n_end = 0u;
+    if (!overlap) { n_rays = counters[0]; n_end = *range_end; }
     // mesh surface insertion rule (SurfaceMode): the reference's 8-sample batches while <= 1/8 of the pixels are live
     const bool batch8 = P.surface_mode == kSurfaceBatch8 || (P.surface_mode == kSurfaceAuto && (unsigned long long)n_rays * 8ull <= (unsigned long long)n_pixels);
     // more than 1/8 live pixels under the auto rule: the reference's batch size varies per wavefront iteration (SchedArgs)
@@ -1007,7 +1009,7 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH
     if (pass2) {
         uint32_t* len_s = reinterpret_cast<uint32_t*>(sched_s + kSchedMax + 2);
         if (threadIdx.x == 0) {
-            uint32_t alive = n_rays, s = 0, k = 0;
+            uint32_t alive = n_rays - min(n_rays, counters[kCntLensRays]), s = 0, k = 0;      // the wavefront holds the ordinary rays only
             while (alive > 0u && k + 1u < kSchedMax && s < kSchedBins + 8u) {
                 const uint32_t q = n_pixels / alive, n = q < 1u ? 1u : (q > 8u ? 8u : q);
                 sched_s[k++] = (uint16_t)s;
@@ -1088,10 +1090,10 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH
                     // ---- lens ray: the segment in front of the lens (1) or the reflected segment (2) has ended ----
                     if (phase == 1u) {
                         // split at the lens: park what was accumulated in front of it and where the primary walk stands
-                        const float4 l0 = __ldg(out.lens + (size_t)idx * 2);
+                        const float4 l0 = __ldg(out.lens + (size_t)(idx & ~kLensRayFlag) * 2);
                         V3 refl;
                         const float F = lens_fresnel(P, dir, v3(l0.x, l0.y, l0.z), refl);
-                        const float wl = __ldg(out.lens + (size_t)idx * 2 + 1).x;
+                        const float wl = __ldg(out.lens + (size_t)(idx & ~kLensRayFlag) * 2 + 1).x;
                         stash[0] = cr; stash[1] = cg; stash[2] = cb; stash[3] = ca; stash[14] = F; stash[15] = wl;
                         stash[4] = 0.f; stash[5] = 0.f; stash[6] = 0.f;
                         {   // where the transmitted segment starts (behind the pane, shifted sideways under the plate model)
@@ -1141,10 +1143,11 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH
                 if (two_pass && !pass2) {
                     // first of two passes: record where this ray dies in the reference's wavefront (sample index of the batch
                     // that kills it); rays that carry a mesh surface are composited again by the second pass
-                    if (sub == 0) atomicAdd(sched.hist + min(sat ? n_samples - 1u : n_samples, kSchedBins - 1u), 1u);
+                    // (lens rays are marched on their own, outside the wavefront whose schedule is being replayed: oracle render_impl)
+                    if (sub == 0 && !(idx & kLensRayFlag)) atomicAdd(sched.hist + min(sat ? n_samples - 1u : n_samples, kSchedBins - 1u), 1u);
                     if (idx & kSurfRayFlag) { active = false; continue; }
                 }
-                if (sub == 0) finish_pixel(P, out, idx & ~kSurfRayFlag, cr, cg, cb, ca, depth, n_samples);
+                if (sub == 0) finish_pixel(P, out, idx & ~(kSurfRayFlag | kLensRayFlag), cr, cg, cb, ca, depth, n_samples);
                 active = false;
             }
             if (!active) {
@@ -1185,9 +1188,9 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH
                 phase = 0u; kb = 0u; sat = false;
                 if (idx & kLensRayFlag) {
                     // lens ray, first segment: samples up to the lens only, the opaque mesh surface waits behind it
-                    idx &= ~kLensRayFlag;
+                    // (the flag stays in idx for the ray's lifetime: a lens ray is not part of the wavefront schedule)
                     stash[8] = t_start; stash[9] = t_surface; stash[10] = sr; stash[11] = sg; stash[12] = sb; stash[13] = sw; stash[19] = t_limit;
-                    t_limit = fminf(t_limit, __ldg(out.lens + (size_t)idx * 2).w);
+                    t_limit = fminf(t_limit, __ldg(out.lens + (size_t)(idx & ~kLensRayFlag) * 2).w);
                     t_surface = 0.f; sr = sg = sb = sw = 0.f;
                     phase = 1u;
                 }
@@ -1313,10 +1316,18 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH
             const V3 dd = vsub(pos, v3(P.cam[9], P.cam[10], P.cam[11]));   // NeRF-space sample vs world-space eye, as in the reference
             a_depth = sqrtf(edot(dd, dd));
         }
+#ifdef NMR_CHECKED
+        if (P.debug_pixel >= 0 && active && sub == 0 && (idx & ~(kSurfRayFlag | kLensRayFlag)) == (uint32_t)P.debug_pixel)
+            printf("[gpu ray %d] batch: phase %u n_valid %u ended %d paused %d pending_finish %d t %.7f t_batch_end %.7f t_limit %.7f t_surface %.7f sw %.3f ca %.5f n_samples %u\n", P.debug_pixel, phase, n_valid, (int)ended, (int)paused, (int)pending_finish, t, t_batch_end, t_limit, t_surface, sw, ca, n_samples);
+#endif
         if (active && !pending_finish) {
             bool done = false;
             // reference rule: the batch's end (payload.t after generate_next_nerf_network_inputs) decides, before its first sample
-            const bool pre_blend = batch_rule && sw > 0.f && n_valid == (pass2 ? batch_cap : (uint32_t)kRayLanes) && t_batch_end > t_surface;
+            // (payload.t is only advanced by a FULL batch, S/ngp/testbed.cu:620-633: a batch that came back short is judged by where
+            // it started.  An ordinary ray never starts a batch behind its surface with the surface still pending; the transmitted
+            // segment of a lens ray does when the opaque surface lies less than a step behind the lens.)
+            const bool full_batch = n_valid == (pass2 ? batch_cap : (uint32_t)kRayLanes);
+            const bool pre_blend = batch_rule && sw > 0.f && (full_batch ? t_batch_end : t) > t_surface;
 #pragma unroll 1
             for (uint32_t j = 0; j < n_valid; ++j) {
                 const uint32_t src = gbase + j;

@@ -39,9 +39,10 @@ constexpr int kLensStash = 24;
 // [7] rays that carry a mesh surface (length of the surface list), [8] CTAs of the set-up kernel that have finished (the march
 // kernel of an overlapped frame learns from it that the queue is complete).  These nine are zeroed at the head of a frame.
 // [9] queue records the PREVIOUS frame wrote (its march kernel stores it; the next frame's clear kernel resets their ready words),
-// [10..11] / [12..13] globaltimer of the first march CTA's start / the last one's end (64-bit min / max) of this frame.
+// [10..11] / [12..13] globaltimer of the first march CTA's start / the last one's end (64-bit min / max) of this frame,
+// [14] lens rays among [0] (zeroed with the frame counters).
 constexpr int kNumCounters = 16, kFrameCounters = 9;
-constexpr int kCntInitDone = 8, kCntPrevCount = 9, kCntMarchStart = 10, kCntMarchEnd = 12;
+constexpr int kCntInitDone = 8, kCntPrevCount = 9, kCntMarchStart = 10, kCntMarchEnd = 12, kCntLensRays = 14;
 constexpr int kRayRecordFloat4s = 3;   // queue record: (dir.xyz, t) (t_start, t_surface, idx, t_limit) (surface rgba)
 // The idx word of a record is its READY word: the set-up kernel stores it last, with release semantics, and the march kernel
 // reads it first, with acquire semantics - so the march kernel can consume the queue while the set-up kernel is still appending to

@@ -954,7 +954,11 @@ static void march_lens_ray(const orc_model* m, const orc_render_params* P, const
     const v3 dir = r->dir, origin = r->origin;
     const float t_start = r->t_start;
     r->t_surface = 0.f; r->surf[0] = r->surf[1] = r->surf[2] = r->surf[3] = 0.f;
+    const char* dbg_env = getenv("ORC_DEBUG_PIXEL");      /* diagnostics: the segments of one lens ray on stderr */
+    const int dbg = dbg_env && (uint32_t)atoi(dbg_env) == r->idx;
+    if (dbg) fprintf(stderr, "[oracle lens %u] n %u w %.4f t_lens %.7f t0 %.7f t_start %.7f t_surf %.7f surf_w %.3f\n", r->idx, n, w, t_lens, r->t, t_start, t_surf, surf[3]);
     r->n_samples += march_segment(m, P, render_aabb, train_aabb, r, n, t_lens, 1);   /* r->t must end where the walk stood: segment 3 resumes there */
+    if (dbg) fprintf(stderr, "[oracle lens %u] segment 1: samples %u saturated %d alpha %.5f t_resume %.7f\n", r->idx, r->n_samples, r->saturated, r->rgba[3], r->t);
     if (r->saturated) return;
     float front[4]; memcpy(front, r->rgba, 16);
     const float t_resume = r->t;
@@ -972,7 +976,9 @@ static void march_lens_ray(const orc_model* m, const orc_render_params* P, const
     v3 delta; float t_behind;
     lens_plate_shift(L, dir, nrm, t_lens, &delta, &t_behind);
     c3.origin = add3(origin, delta); c3.dir = dir; c3.t = fmaxf(t_resume, t_behind); c3.t_start = t_start; c3.t_surface = t_surf; memcpy(c3.surf, surf, 16); c3.alive = 1; c3.idx = r->idx;
+    if (dbg) fprintf(stderr, "[oracle lens %u] F %.5f mirror segment taken %d, samples so far %u; segment 3 starts at t %.7f\n", r->idx, F, w * F * (1.f - front[3]) >= 1.0f / 512.0f, r->n_samples, c3.t);
     r->n_samples += march_segment(m, P, render_aabb, train_aabb, &c3, n, INFINITY, 0);   /* payload.t semantics of the reference (composite_ray) */
+    if (dbg) fprintf(stderr, "[oracle lens %u] segment 3: samples total %u, behind rgba %.4f %.4f %.4f %.4f\n", r->idx, r->n_samples, c3.rgba[0], c3.rgba[1], c3.rgba[2], c3.rgba[3]);
     const float Tf = 1.f - front[3];
     for (int c = 0; c < 3; ++c) {
         float kc = (1.f - F) * L->k[c];
@@ -1032,9 +1038,12 @@ static int render_impl(const orc_model* m, const orc_render_params* P, const flo
     for (size_t i = 0; i < N; ++i) n_alive0 += rays[i].alive ? 1 : 0;
     uint64_t total_samples = 0, iterations = 0;
     uint32_t step = 1;
-    /* lens rays are marched on their own after the wavefront loop, with the batch size the first iteration would use */
+    /* Lens rays are marched on their own, outside the wavefront loop (which then holds the ordinary rays only).  Where the opaque
+     * mesh surface behind a lens enters their compositing order: in batches of 8 samples while at most 1/8 of the pixels hold a
+     * live ray - the regime in which the reference's own n_steps is the constant 8, i.e. a ray-local rule - and at the exact
+     * sample otherwise (the reference's varying n_steps is a property of its wavefront, which lens rays are not part of). */
     uint32_t n_lens = 1;
-    if (P->n_steps_mode == 1 && n_alive0 > 0) { uint64_t q = (uint64_t)N / n_alive0; n_lens = (uint32_t)(q < 1 ? 1 : (q > 8 ? 8 : q)); }
+    if (P->n_steps_mode == 1 && n_alive0 > 0) n_lens = ((uint64_t)N / n_alive0 >= 8) ? 8u : 1u;
     if (P->n_steps_mode == 2) n_lens = 8;
     uint64_t lens_samples = 0;
     if (L) {

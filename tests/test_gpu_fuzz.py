@@ -1,0 +1,21 @@
+"""Random camera poses, GPU frame against the CPU oracle (tools/fuzz_poses.py): orbit steps of any size, dollies from far
+outside to inside the head, sideways shifts - live rays from none to every pixel, the batch-8 regime and the replayed
+n_steps schedule of close-ups, lens pixels from none to the whole frame.  Round 2's runs of this (900 poses) found the two
+cases that the hand-picked poses of the other tests do not reach: lens rays inside the schedule replay of a close-up, and a
+transmitted lens segment that starts behind an opaque surface with a short batch (march_kernel: `pre_blend`)."""
+import os
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+
+
+@pytest.mark.parametrize("with_lens,seed,n", [(True, 4, 110), (True, 6, 60), (False, 11, 60)])
+def test_random_poses_match_the_oracle(with_lens, seed, n):
+    import fuzz_poses
+    violations, worst, over = fuzz_poses.run(n, seed, with_lens, verbose=False)
+    assert violations == 0
+    assert over == 0 and worst <= 2.0 / 255.0          # not one pixel over the tolerance (seed 4 holds both cases named above)
