@@ -19,3 +19,14 @@ def test_random_poses_match_the_oracle(with_lens, seed, n):
     violations, worst, over = fuzz_poses.run(n, seed, with_lens, verbose=False)
     assert violations == 0
     assert over == 0 and worst <= 2.0 / 255.0          # not one pixel over the tolerance (seed 4 holds both cases named above)
+
+
+def test_random_poses_match_the_reference_renderer():
+    """The same kind of poses, plus random crop boxes (Testbed.render_aabb) and model transforms, against the reference's own
+    kernels on this GPU (tools/fuzz_reference.py); per pose the tolerances of tests/test_gpu_vs_reference.py."""
+    from oracle import refgpu
+    if not refgpu.available():
+        pytest.skip("oracle/_ref/libnmr_refgpu.so not built")
+    import fuzz_reference
+    violations, worst_psnr, worst_frac = fuzz_reference.run(80, 1, verbose=False)
+    assert violations == 0 and worst_psnr >= 45.0 and worst_frac <= 0.004
