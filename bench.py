@@ -12,9 +12,17 @@ The camera follows render.py's orbit loop (orbit(-sin(1.733a)/100, cos(1.733a)/2
 
 Prints ONE JSON line (rank 0).  `value` = whole-job Mrays/s with model and mesh resident in HBM and the image left in
 HBM (device time, CUDA events on the renderer's stream, L2 flushed between steps); `e2e` = the same metric through the
-public API call Testbed.render() with the image copied to pinned host memory every step.
+public API call Testbed.render() with the whole image copied to pinned host memory every step (float32; `e2e_u8` = the same
+call returning sRGB8).  `e2e_update` (extra) = Testbed.render_update(): the caller keeps the host image and only the screen
+rectangle of head + mesh is moved - same pixels, `d2h_bytes_per_step` = what was actually copied.
+`roofline` = the march kernel alone (K further frames with the set-up / march overlap off, CUDA events around the kernel)
+against the L2 rate measured in this run, the sustained tensor rate and the HBM rate; `cpu_baseline` / `--impl reference` = the
+oracle port on the host cores over the same full frame.
 With N > 1 each rank renders its own views (weak scaling by view, no data-path collective); torch.distributed is used
-for the barrier and the max-over-ranks only.
+for the barrier and the max-over-ranks only.  Every N also reports `tiles_4k` (BASELINE configs[3]: one 3840x2160 lens frame
+split over the ranks, fused peer stores and NCCL gather, bit-identity to the single-GPU frame) and `views_c3` (configs[2]: 64
+views at 512x512 dealt to the ranks); N = 1 adds the stress frames, the hash-map sweep of configs[4], pipelined frames and the
+reference's own renderer on this GPU (`reference_gpu`).
 """
 import argparse
 import json

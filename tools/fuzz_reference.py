@@ -16,13 +16,13 @@ W, HH = 192, 108
 TOL = 2.0 / 255.0
 
 
-def run(n_poses: int = 100, seed: int = 0, verbose: bool = True):
+def run(n_poses: int = 100, seed: int = 0, verbose: bool = True, regime: str = "opaque", aabb_scale: int = 1, snap_seed: int = 1337):
     """-> (violations, worst psnr, worst fraction of pixels over tolerance)"""
     from oracle import refgpu
     rng = np.random.default_rng(seed)
     say = print if verbose else (lambda *a, **k: None)
     with tempfile.TemporaryDirectory() as d:
-        path = os.path.join(d, "s.msgpack"); synth.write_snapshot(path, seed=1337, log2_hashmap_size=15)
+        path = os.path.join(d, "s.msgpack"); synth.write_snapshot(path, seed=snap_seed, log2_hashmap_size=15, regime=regime, aabb_scale=aabb_scale)
         gltf = synth.write_glasses_gltf(os.path.join(d, "mesh"))
         ref = refgpu.ReferenceRenderer(path)
         r = pynmr.NerfMeshRenderer(W, HH, 0)
@@ -70,9 +70,11 @@ def run(n_poses: int = 100, seed: int = 0, verbose: bool = True):
         finally:
             ref.close()
         a = np.array(alive_all)
-        say(f"{n_poses} poses, seed {seed}: violations {bad}, worst psnr {worst_ps:.1f} dB, worst fraction over tolerance {worst_frac:.4%}; live rays per pose min {a.min()} median {int(np.median(a))} max {a.max()} of {W * HH}")
+        say(f"{n_poses} poses, seed {seed}, scene {regime} / aabb_scale {aabb_scale} / snapshot seed {snap_seed}: violations {bad}, worst psnr {worst_ps:.1f} dB, worst fraction over tolerance {worst_frac:.4%}; live rays per pose min {a.min()} median {int(np.median(a))} max {a.max()} of {W * HH}")
         return bad, worst_ps, worst_frac
 
 
 if __name__ == "__main__":
-    sys.exit(1 if run(int(sys.argv[1]) if len(sys.argv) > 1 else 100, int(sys.argv[2]) if len(sys.argv) > 2 else 0)[0] else 0)
+    kw = dict(a.split("=") for a in sys.argv[3:])        # regime=translucent aabb_scale=4 snap_seed=7
+    sys.exit(1 if run(int(sys.argv[1]) if len(sys.argv) > 1 else 100, int(sys.argv[2]) if len(sys.argv) > 2 else 0,
+                      regime=kw.get("regime", "opaque"), aabb_scale=int(kw.get("aabb_scale", 1)), snap_seed=int(kw.get("snap_seed", 1337)))[0] else 0)
