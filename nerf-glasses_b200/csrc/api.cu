@@ -167,6 +167,7 @@ struct nmr_ctx {
     nmr_stats stats{};
     bool stats_pending = false;
     std::string envmap_path;
+    const void* l2_window_ptr = nullptr;                  // NMR_L2_PERSIST: what the stream's access-policy window covers
     // nmr_render_update: host images this context has filled and may update in place - the pixels outside `rect` hold the background
     struct HostImage { void* p; int w, h, fmt; float bg[4]; int rect[4]; };
     std::vector<HostImage> host_images;
@@ -514,6 +515,23 @@ void enqueue_pass(nmr_ctx* ctx, Nerf& n, const FrameParams& P, bool timed, void*
     const bool probes = force_probes || (ctx->debug_flags & kDebugKeepProbes) != 0;
     FrameOut out{image_target ? image_target : static_cast<void*>(S.image.p), S.accum.p, probes ? S.frame.p : nullptr, probes ? S.depth.p : nullptr, probes ? S.n_samples.p : nullptr, nullptr, nullptr};
     if (!image_target) { S.image_format = P.out_format; S.image_is_frame = false; }
+    // Experiment (NMR_L2_PERSIST=1, profiles/r2_experiments.md): the hash table of the NeRF being rendered inside a persisting L2
+    // access-policy window of the frame's stream, instead of / next to the prefetch of launch_background.
+    static const bool l2_persist = std::getenv("NMR_L2_PERSIST") != nullptr;
+    if (l2_persist && ctx->l2_window_ptr != static_cast<const void*>(n.dev.grid)) {
+        cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, ctx->device));
+        const size_t table_bytes = ((size_t)n.dev.level_offset[N_LEVELS - 1] + n.dev.level_size[N_LEVELS - 1]) * sizeof(__half2);
+        CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min((size_t)prop.persistingL2CacheMaxSize, table_bytes)));
+        cudaStreamAttrValue attr{};
+        attr.accessPolicyWindow.base_ptr = const_cast<__half2*>(n.dev.grid);
+        attr.accessPolicyWindow.num_bytes = std::min(table_bytes, (size_t)prop.accessPolicyMaxWindowSize);
+        attr.accessPolicyWindow.hitRatio = 1.0f;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        CK(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+        ctx->l2_window_ptr = n.dev.grid;
+        std::fprintf(stderr, "libnmr: persisting L2 window over %zu MiB of hash table (device limits: %d MiB persisting, %d MiB window)\n", table_bytes >> 20, prop.persistingL2CacheMaxSize >> 20, prop.accessPolicyMaxWindowSize >> 20);
+    }
     static const char* phase_log_path = std::getenv("NMR_PHASE_LOG");      // measurement aid: see FrameOut::phase_log
     if (phase_log_path && timed) {
         const size_t words = (size_t)ctx->num_sms * 4 * 2 * kPhaseIters * kPhaseWords;
