@@ -30,3 +30,10 @@ def test_random_poses_match_the_reference_renderer():
     import fuzz_reference
     violations, worst_psnr, worst_frac = fuzz_reference.run(80, 1, verbose=False)
     assert violations == 0 and worst_psnr >= 45.0 and worst_frac <= 0.004
+
+
+def test_random_poses_every_path_gives_the_same_bits():
+    """frame() with / without overlap, render() in three formats, render_update(), render_views(), three row shards: one picture
+    (tools/fuzz_paths.py)."""
+    import fuzz_paths
+    assert fuzz_paths.run(50, 3, verbose=False) == []
