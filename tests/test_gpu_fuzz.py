@@ -37,3 +37,16 @@ def test_random_poses_every_path_gives_the_same_bits():
     (tools/fuzz_paths.py)."""
     import fuzz_paths
     assert fuzz_paths.run(50, 3, verbose=False) == []
+
+
+def test_random_mesh_transforms_match_the_oracle():
+    """Random rotations / scales / offsets of the textured glTF (all texture slots) and random cameras: visibility bit for bit,
+    shading and the hybrid frame within tolerance (tools/fuzz_mesh.py)."""
+    import fuzz_mesh
+    assert fuzz_mesh.run(25, 2, verbose=False) == []
+
+
+def test_random_poses_plate_lenses_match_the_oracle():
+    import fuzz_poses
+    violations, worst, over = fuzz_poses.run(60, 8, True, verbose=False, plate=True)
+    assert violations == 0 and over == 0 and worst <= 2.0 / 255.0
