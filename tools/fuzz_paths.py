@@ -17,7 +17,8 @@ def same(a, b):
     return np.array_equal(np.ascontiguousarray(a).view(np.uint8), np.ascontiguousarray(b).view(np.uint8))
 
 
-def run(n_poses: int = 60, seed: int = 0, verbose: bool = True):
+def run(n_poses: int = 60, seed: int = 0, verbose: bool = True, size=None):
+    W, HH = size if size else (globals()["W"], globals()["HH"])
     rng = np.random.default_rng(seed)
     say = print if verbose else (lambda *a, **k: None)
     failures = []
@@ -74,9 +75,11 @@ def run(n_poses: int = 60, seed: int = 0, verbose: bool = True):
             prev_cam, prev_img = cam, A
             if verbose and k % 20 == 0:
                 say(f"pose {k}: live rays {alive} of {W * HH}", flush=True)
-    say(f"{n_poses} poses, seed {seed}: {len(failures)} disagreements {failures[:8]}")
+    say(f"{n_poses} poses, seed {seed}, {W}x{HH}: {len(failures)} disagreements {failures[:8]}")
     return failures
 
 
 if __name__ == "__main__":
-    sys.exit(1 if run(int(sys.argv[1]) if len(sys.argv) > 1 else 60, int(sys.argv[2]) if len(sys.argv) > 2 else 0) else 0)
+    kw = dict(a.split("=") for a in sys.argv[3:])        # size=333x217
+    sys.exit(1 if run(int(sys.argv[1]) if len(sys.argv) > 1 else 60, int(sys.argv[2]) if len(sys.argv) > 2 else 0,
+                      size=tuple(int(v) for v in kw["size"].split("x")) if "size" in kw else None) else 0)

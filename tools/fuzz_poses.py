@@ -15,7 +15,8 @@ W, HH = 160, 96
 TOL = 2.0 / 255.0
 
 
-def run(n_poses: int = 100, seed: int = 0, with_lens: bool = True, only=None, verbose: bool = True, regime: str = "opaque", aabb_scale: int = 1, snap_seed: int = 1337, plate: bool = False):
+def run(n_poses: int = 100, seed: int = 0, with_lens: bool = True, only=None, verbose: bool = True, regime: str = "opaque", aabb_scale: int = 1, snap_seed: int = 1337, plate: bool = False, size=None):
+    W, HH = size if size else (globals()["W"], globals()["HH"])
     """-> (violations, worst pixel difference, pixels over tolerance in total)"""
     rng = np.random.default_rng(seed)
     say = print if verbose else (lambda *a, **k: None)
@@ -81,7 +82,7 @@ def run(n_poses: int = 100, seed: int = 0, with_lens: bool = True, only=None, ve
                 bad += 1
                 say(f"pose {k}: alive {st['rays_alive']} vs {ost['alive_after_first_hit']}, max |d| {px:.4f}, psnr {ps:.1f} dB, pixels over tolerance {frac:.4%}", flush=True)
         a = np.array(alive_all); l = np.array(lens_all)
-        say(f"{n_poses} poses, seed {seed}, scene {regime} / aabb_scale {aabb_scale} / snapshot seed {snap_seed}{" / plate lenses" if plate else ""}: violations {bad}, worst pixel difference {worst['pix']:.4f}, worst psnr {worst['psnr']:.1f} dB; live rays per pose: "
+        say(f"{n_poses} poses, seed {seed}, scene {regime} / aabb_scale {aabb_scale} / snapshot seed {snap_seed}{" / plate lenses" if plate else ""} / {W}x{HH}: violations {bad}, worst pixel difference {worst['pix']:.4f}, worst psnr {worst['psnr']:.1f} dB; live rays per pose: "
               f"min {a.min()} median {int(np.median(a))} max {a.max()} of {W * HH} ({int((a == 0).sum())} poses see nothing), lens pixels median {int(np.median(l))} max {l.max()}")
         return bad, worst["pix"], over_total
 
@@ -92,4 +93,4 @@ if __name__ == "__main__":
     with_lens = (sys.argv[3] != "nolens") if len(sys.argv) > 3 else True
     only = int(os.environ["FUZZ_ONLY"]) if "FUZZ_ONLY" in os.environ else None      # one pose of the sequence, with the hand-offs of the offending pixels
     kw = dict(a.split("=") for a in sys.argv[4:])        # regime=translucent aabb_scale=4 snap_seed=7
-    sys.exit(1 if run(n_poses, seed, with_lens, only, regime=kw.get("regime", "opaque"), aabb_scale=int(kw.get("aabb_scale", 1)), snap_seed=int(kw.get("snap_seed", 1337)), plate=kw.get("plate", "0") == "1")[0] else 0)
+    sys.exit(1 if run(n_poses, seed, with_lens, only, regime=kw.get("regime", "opaque"), aabb_scale=int(kw.get("aabb_scale", 1)), snap_seed=int(kw.get("snap_seed", 1337)), plate=kw.get("plate", "0") == "1", size=tuple(int(v) for v in kw["size"].split("x")) if "size" in kw else None)[0] else 0)
