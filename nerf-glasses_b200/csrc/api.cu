@@ -129,6 +129,8 @@ struct nmr_ctx {
     std::vector<nmr_ctx*> lanes;
     int march_ctas = 0;                                   // CTAs per SM of this context's march kernel (0 = default); lanes share the SMs
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_tl[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // NMR_TIMELINE=1 (measurement aid): events between a frame's kernels
+    bool tl_pending = false;
     OrbitCamera camera;
     float cam12[12];
     float light[3] = {1.f, 1.f, 1.f};                     // S/nerf_mesh_renderer.cuh:95
@@ -562,8 +564,14 @@ void enqueue_pass(nmr_ctx* ctx, Nerf& n, const FrameParams& P, bool timed, void*
     if (overlap && proved_batch8) Pm.surface_mode = kSurfaceBatch8;
     // counters, schedule histogram, the mesh visibility window and the ready words of the last frame's queue records are
     // cleared by one kernel (not four memset nodes)
+    // NMR_TIMELINE=1: where a frame's time goes kernel by kernel (events between the kernels - they serialise the frame, so this
+    // is for serial frames, NMR_NO_OVERLAP=1); printed by the next nmr_get_stats
+    static const bool timeline = std::getenv("NMR_TIMELINE") != nullptr;
+    const bool tl = timeline && timed && !overlap;
+    if (tl) { for (auto& e : ctx->ev_tl) if (!e) CK(cudaEventCreate(&e)); CK(cudaEventRecord(ctx->ev_tl[0], ctx->stream)); }
     launch_frame_clear(ctx->d_counters.p, sched ? S.hist.p : nullptr, S.zbuf.p, zbuf_window_words(mesh, P), S.queue.p, ctx->stream);
     launches += 1;
+    if (tl) CK(cudaEventRecord(ctx->ev_tl[1], ctx->stream));
     // The background pixels (everything outside the tile box of the two screen rectangles) depend on nothing else in the frame:
     // they are written on a side stream while the mesh stage and the ray set-up run (fork behind the clear kernel, which is
     // behind the previous frame; join in front of the frame's closing event).  NMR_NO_AUX_STREAM=1: in line, for A/B runs.
@@ -580,13 +588,16 @@ void enqueue_pass(nmr_ctx* ctx, Nerf& n, const FrameParams& P, bool timed, void*
     }
     launches += rows > 0 ? 1 : 0;
     if (P.mesh_scale > 0) { launch_mesh_raster(mesh, P, rows, S.zbuf.p, ctx->stream, false); launches += 1; }
+    if (tl) CK(cudaEventRecord(ctx->ev_tl[2], ctx->stream));
     const int init_ctas = launch_init_rays(P, n.dev, mesh, S.zbuf.p, rows, S.queue.p, ctx->d_counters.p, out, box, ctx->stream, sched ? S.surf_list.p : nullptr);
     launches += init_ctas > 0 ? 1 : 0;
     if (timed && !overlap) CK(cudaEventRecord(ctx->ev[1], ctx->stream));      // (an event between the two kernels would serialise them)
+    if (tl) CK(cudaEventRecord(ctx->ev_tl[3], ctx->stream));
     const uint32_t n_pixels = (uint32_t)P.width * (uint32_t)rows;
     launch_march(Pm, model_for(ctx, n), S.queue.p, ctx->d_counters.p, out, n_pixels, ctx->debug_flags, ctx->num_sms, ctx->stream, nullptr, nullptr, sched ? &sa : nullptr, ctx->march_ctas,
                  overlap ? init_ctas : -1);
     launches += 1;
+    if (tl) { CK(cudaEventRecord(ctx->ev_tl[4], ctx->stream)); ctx->tl_pending = true; }
     if (side) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     if (timed) ctx->last_overlapped = overlap;
     if (sched) { enqueue_surface_pass(ctx, n, P, out, n_pixels, sa); launches += 1; }
@@ -702,6 +713,14 @@ void finish_stats(nmr_ctx* ctx) {
         CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2])); ctx->stats.march_ms = ms;
     }
     ctx->stats_pending = false;
+    if (ctx->tl_pending) {
+        float a = 0, b = 0, c = 0, d = 0, e0 = 0, e1 = 0;
+        cudaEventElapsedTime(&a, ctx->ev_tl[0], ctx->ev_tl[1]); cudaEventElapsedTime(&b, ctx->ev_tl[1], ctx->ev_tl[2]); cudaEventElapsedTime(&c, ctx->ev_tl[2], ctx->ev_tl[3]);
+        cudaEventElapsedTime(&d, ctx->ev_tl[3], ctx->ev_tl[4]); cudaEventElapsedTime(&e0, ctx->ev[0], ctx->ev_tl[0]); cudaEventElapsedTime(&e1, ctx->ev_tl[4], ctx->ev[2]);
+        std::fprintf(stderr, "libnmr timeline (us): open %.1f | clear %.1f | mesh raster %.1f | set-up %.1f | march %.1f | close (join of the background stream) %.1f | frame %.1f\n",
+                     e0 * 1e3f, a * 1e3f, b * 1e3f, c * 1e3f, d * 1e3f, e1 * 1e3f, ctx->stats.gpu_ms * 1e3f);
+        ctx->tl_pending = false;
+    }
     if (const char* path = std::getenv("NMR_PHASE_LOG")) {
         if (ctx->d_phase_log.p) {        // raw dump of the last timed frame's phase clocks
             std::vector<unsigned long long> h(ctx->d_phase_log.n);
@@ -827,6 +846,7 @@ NMR_API void nmr_destroy(nmr_ctx* ctx) {
     ctx->nerfs.clear(); ctx->meshes.clear();
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->ev_tl) if (ev) cudaEventDestroy(ev);
     for (auto& pair : ctx->ev_view) for (auto& ev : pair) if (ev) cudaEventDestroy(ev);
     if (ctx->ev_rows) cudaEventDestroy(ctx->ev_rows);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }

@@ -164,6 +164,7 @@ constexpr unsigned long long kZMiss = ~0ull;
 // tens of thousands of sub-pixels (a lens pane at 4K) does not hang on one warp.
 // Replaces optixLaunch(2W x 2H) + RT-core traversal (S/nerf_mesh_renderer.cu:1454-1487, S/optix/optix_scene.cu:120-174).
 __global__ void __launch_bounds__(256) mesh_raster_kernel(MeshDevice mesh, FrameParams P, int W2, int H2, unsigned long long* __restrict__ zbuf, uint32_t slices) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // (the set-up kernel waits for this grid's end by itself)
     const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t tri = warp_id / slices, slice = warp_id % slices;
     const uint32_t lane = threadIdx.x & 31;
@@ -200,6 +201,8 @@ __global__ void __launch_bounds__(256) mesh_raster_kernel(MeshDevice mesh, Frame
     // shard: only sub-pixel rows belonging to owned image rows are needed, but testing ownership per row is cheap enough
     const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
     const int ms = P.mesh_scale;
+    // the triangle set-up above only reads the mesh; the visibility window is the clear kernel's to reset first (launch_chained)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int i = (int)(slice * 32u + lane); i < bw * bh; i += 32 * (int)slices) {
         const int x = x0 + i % bw, y = y0 + i / bw;
         if (P.shard_world > 1 && ((y / ms) / P.shard_band) % P.shard_world != P.shard_rank) continue;
@@ -213,9 +216,25 @@ __global__ void __launch_bounds__(256) mesh_raster_kernel(MeshDevice mesh, Frame
     }
 }
 
+// Programmatic dependent launch of a frame's small leading kernels (clear -> mesh raster -> set-up): each is launched while its
+// predecessor still runs, sits in griddepcontrol.wait until that one has finished and flushed, and so starts without the launch
+// gap.  (griddepcontrol.wait is a no-op in a grid that was launched the ordinary way.)  NMR_NO_PDL_CHAIN=1: ordinary launches.
+static bool pdl_chain() { static const bool off = std::getenv("NMR_NO_PDL_CHAIN") != nullptr; return !off; }
+template <typename K, typename... Args>
+static void launch_chained(K kernel, dim3 grid, dim3 block, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_chain() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 // One launch instead of three memset nodes at the head of a frame: device counters, the schedule histogram and the mesh
 // visibility window (every stream node costs 2-4 us of device time on a 250 us frame).
 __global__ void frame_clear_kernel(uint32_t* __restrict__ counters, uint32_t* __restrict__ hist, ulonglong2* __restrict__ zbuf2, size_t zbuf_pairs, float4* __restrict__ queue) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // (the mesh raster behind this kernel waits for its end by itself)
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
     // ready words of the records the previous frame queued (its march kernel left their number; nobody writes that word here)
     const uint32_t prev = counters[kCntPrevCount];
@@ -244,7 +263,7 @@ void launch_mesh_raster(const MeshDevice& mesh, const FrameParams& P, int rows_o
     if (clear) cudaMemsetAsync(d_zbuf, 0xFF, (size_t)P.zb_w * P.zb_h * sizeof(unsigned long long) * (mesh.tri_lens ? 2 : 1), s);
     const uint32_t slices = mesh.tri_lens ? 16u : 2u;
     const uint32_t threads = mesh.n_tris * 32u * slices;
-    mesh_raster_kernel<<<(threads + 255) / 256, 256, 0, s>>>(mesh, P, W2, H2, d_zbuf, slices);
+    launch_chained(mesh_raster_kernel, dim3((threads + 255) / 256), dim3(256), s, mesh, P, W2, H2, d_zbuf, slices);
 }
 
 // closest hit of one sub-pixel -> shaded RGBA (alpha 1) and hitT; false on miss
@@ -507,6 +526,9 @@ __global__ void __launch_bounds__(128) init_rays_kernel(FrameParams P, DeviceMod
     // Overlapped frames: the march kernel behind this one is launched with programmatic stream serialisation - it may start as
     // soon as every CTA of this grid has got here (i.e. is resident or done; the tile box is at most a few waves), and then
     // consumes the queue while the first-hit walks are still running.  Harmless when the next kernel is an ordinary launch.
+    // This grid itself may have been launched early (launch_chained): first wait for the mesh raster (and, through it, the clear
+    // kernel) - only then may the march kernel be let loose on the counters and ready words they reset.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     init_rays_body(P, M, mesh, zbuf, rows_owned, queue, counters, out, surf_list, box, block_rot);
     // this CTA's records are complete: count it (the march kernel compares the count with the grid size to learn that the queue is final)
@@ -655,7 +677,7 @@ void launch_background(const FrameParams& P, const DeviceModel& M, const FrameOu
 int launch_init_rays(const FrameParams& P, const DeviceModel& M, const MeshDevice& mesh, const unsigned long long* d_zbuf, int rows_owned,
                      float4* d_queue, uint32_t* d_counters, const FrameOut& out, const TileBox& box, cudaStream_t s, uint32_t* d_surf_list) {
     if (rows_owned <= 0 || box.nx <= 0) return 0;
-    init_rays_kernel<<<dim3((unsigned)box.nx, (unsigned)box.ny), 128, 0, s>>>(P, M, mesh, d_zbuf, rows_owned, d_queue, d_counters, out, d_surf_list, box, make_uint2(box.rot_x, box.rot_y));
+    launch_chained(init_rays_kernel, dim3((unsigned)box.nx, (unsigned)box.ny), dim3(128), s, P, M, mesh, d_zbuf, rows_owned, d_queue, d_counters, out, d_surf_list, box, make_uint2(box.rot_x, box.rot_y));
     return box.nx * box.ny;
 }
 
