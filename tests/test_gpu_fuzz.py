@@ -50,3 +50,10 @@ def test_random_poses_plate_lenses_match_the_oracle():
     import fuzz_poses
     violations, worst, over = fuzz_poses.run(60, 8, True, verbose=False, plate=True)
     assert violations == 0 and over == 0 and worst <= 2.0 / 255.0
+
+
+def test_random_poses_accumulation_and_two_nerfs_match_the_oracle():
+    """frame() repeated 1 - 4 times on a still camera (the reference's per-sample jitter) and two NeRFs merged by depth, at random
+    poses (tools/fuzz_scene.py)."""
+    import fuzz_scene
+    assert fuzz_scene.run(20, 5, verbose=False) == []
