@@ -749,7 +749,11 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // Layer semantics of T/src/fully_fused_mlp.cu:499-557: y = act(W x), fp16 activations between layers.
 // =================================================================================================================
 constexpr int kTile = 128;          // samples per MMA tile = threads per warpgroup
-constexpr int kGroupsTC = 2;        // warpgroups per CTA on the tensor path (they share the weights in shared memory)
+#ifndef NMR_GROUPS_TC
+#define NMR_GROUPS_TC 2
+#endif
+constexpr int kGroupsTC = NMR_GROUPS_TC;   // warpgroups per CTA on the tensor path (they share the weights in shared memory); 6 with NMR_MARCH_CTAS=1: one 768-thread CTA per SM
+constexpr uint32_t kTmemCols = 64 * kGroupsTC <= 128 ? 128u : (64 * kGroupsTC <= 256 ? 256u : 512u);   // tcgen05.alloc takes powers of two
 // weight matrices in params order: [out][in] row-major halves
 constexpr int kWD0 = 0, kWD1 = kWD0 + 64 * 32, kWR0 = kWD1 + 16 * 64, kWR1 = kWR0 + 64 * 32, kWR2 = kWR1 + 64 * 64, kWTotal = kWR2 + 16 * 64;   // 10240 halves
 
@@ -934,7 +938,7 @@ __device__ __forceinline__ void network_tc(char* a_row, TcCtx& c, V3 dir01, floa
 
 // CTA prologue of the tensor path: TMEM allocation (64 columns per warpgroup), mbarriers, weights -> smem
 __device__ __forceinline__ TcCtx tc_setup(MarchSmemTC& S, const DeviceModel& M, uint32_t debug_flags) {
-    if (threadIdx.x < 32) tmem_alloc(&S.tmem_base, 64 * kGroupsTC);
+    if (threadIdx.x < 32) tmem_alloc(&S.tmem_base, kTmemCols);
     if (threadIdx.x == 0) { for (int g = 0; g < kGroupsTC; ++g) mbar_init(&S.mbar[g], 1); fence_barrier_init(); }
     if (M.mlp_tc) {
         // weights already in the canonical layout (weights_to_canonical_kernel at load time): one 20 KB bulk copy per CTA
@@ -965,7 +969,7 @@ __device__ __forceinline__ TcCtx tc_setup(MarchSmemTC& S, const DeviceModel& M, 
 __device__ __forceinline__ void tc_teardown(MarchSmemTC& S) {
     tc_fence_before();
     __syncthreads();
-    if (threadIdx.x < 32) tmem_dealloc(S.tmem_base, 64 * kGroupsTC);
+    if (threadIdx.x < 32) tmem_dealloc(S.tmem_base, kTmemCols);
 }
 
 // =================================================================================================================
