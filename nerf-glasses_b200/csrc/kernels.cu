@@ -986,7 +986,10 @@ __device__ __forceinline__ void tc_teardown(MarchSmemTC& S) {
 // middle levels; all per-ray state is replicated in the 8 lanes (same arithmetic in every lane), so no state is exchanged.
 // Groups pull new rays from the queue when their ray ends; tiles stay full until the queue drains.
 // =================================================================================================================
-constexpr int kRayLanes = 8;
+#ifndef NMR_RAY_LANES
+#define NMR_RAY_LANES 8
+#endif
+constexpr int kRayLanes = NMR_RAY_LANES;      // (4: measurement builds only - the 8-sample batch rule of the mesh surface needs 8)
 #ifndef NMR_ENCODE_UNROLL
 #define NMR_ENCODE_UNROLL 1
 #endif
