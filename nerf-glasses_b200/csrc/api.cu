@@ -1063,6 +1063,14 @@ NMR_API int nmr_get_nerf_info(nmr_ctx* ctx, int id, nmr_nerf_info* o) {
 NMR_API int nmr_orbit(nmr_ctx* ctx, float daz, float dpol, float dzoom) {
     return guarded(ctx, [&]() -> int { ctx->camera.orbit(daz, dpol, dzoom); set_camera_from_orbit(ctx); return NMR_OK; });
 }
+NMR_API int nmr_trajectory_pose(nmr_ctx* ctx, float angle, float distance, float height, const float lookat[3]) {
+    return guarded(ctx, [&]() -> int {
+        const float zero[3] = {0.f, 0.f, 0.f};
+        ctx->camera.trajectory_pose(angle, distance, height, lookat ? lookat : zero);
+        set_camera_from_orbit(ctx);
+        return NMR_OK;
+    });
+}
 NMR_API int nmr_get_camera(nmr_ctx* ctx, float out12[12]) {
     return guarded(ctx, [&]() -> int { std::memcpy(out12, ctx->cam12, sizeof(ctx->cam12)); return NMR_OK; });
 }

@@ -651,6 +651,20 @@ void OrbitCamera::orbit(float delta_azimuth, float delta_polar, float delta_scro
     build_view(eye, look, up, view);
 }
 
+void OrbitCamera::look_from(const float eye3[3], const float look3[3]) {
+    for (int k = 0; k < 3; ++k) { eye[k] = eye3[k]; look[k] = look3[k]; }
+    build_view(eye, look, up, view);
+}
+// One pose of the trajectory tool's arc (S/nerf_mesh_renderer.cu:649-658): the eye on a circle of `distance` at `height`, looking at
+// `lookat` (glm::normalize = v * inversesqrt(dot(v, v)), dot summed left to right)
+void OrbitCamera::trajectory_pose(float angle, float distance, float height, const float lookat3[3]) {
+    const float e[3] = {cosf(angle) * distance, height, sinf(angle) * distance};
+    const float d[3] = {lookat3[0] - e[0], lookat3[1] - e[1], lookat3[2] - e[2]};
+    const float inv = 1.0f / sqrtf((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]);
+    const float l[3] = {d[0] * inv, d[1] * inv, d[2] * inv};
+    look_from(e, l);
+}
+
 // updateModelViewProj (S/nerf_mesh_renderer.cu:919-932): vLength = tanf(0.5f * 45) is evaluated in radians
 void OrbitCamera::matrix(int screen_w, int screen_h, float out[12]) const {
     const float aspect = (float)(uint32_t)screen_w / (float)(uint32_t)screen_h;

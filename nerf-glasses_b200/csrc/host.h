@@ -103,6 +103,8 @@ struct OrbitCamera {
     float up[3] = {0.f, 1.f, 0.f};
     OrbitCamera();
     void orbit(float delta_azimuth, float delta_polar, float delta_scroll);
+    void look_from(const float eye3[3], const float look3[3]);       // flythrough_camera_look_to(cam_pos, cam_look, up, viewMat, 0)
+    void trajectory_pose(float angle, float distance, float height, const float lookat3[3]);   // the GUI's trajectory tool, S/nerf_mesh_renderer.cu:649-658
     void matrix(int screen_w, int screen_h, float out12[12]) const;   // updateModelViewProj
 };
 

@@ -108,6 +108,7 @@ def lib():
         "nmr_measure_l2": (C.c_int, [vp, C.c_size_t, C.c_int, fp]),
         "nmr_get_stats": (C.c_int, [vp, C.POINTER(Stats)]),
         "nmr_synchronize": (C.c_int, [vp]),
+        "nmr_trajectory_pose": (C.c_int, [vp, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_float)]),
         "nmr_render_update": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.POINTER(C.c_size_t)]),
         "nmr_host_alloc": (vp, [C.c_size_t]),
         "nmr_host_free": (None, [vp]),
@@ -132,7 +133,7 @@ EXPORTED_SYMBOLS = [
     "nmr_get_mesh_transform", "nmr_set_envmap", "nmr_remove_floaties", "nmr_get_render_aabb", "nmr_set_render_aabb",
     "nmr_get_aabb", "nmr_get_background", "nmr_set_background", "nmr_set_min_transmittance", "nmr_orbit", "nmr_get_camera",
     "nmr_set_camera", "nmr_frame", "nmr_frame_async", "nmr_read_frame", "nmr_render", "nmr_render_views", "nmr_set_shard", "nmr_set_surface_insertion", "nmr_set_lens", "nmr_debug_lens", "nmr_get_nerf_info", "nmr_gather_create", "nmr_gather_attach", "nmr_gather_detach", "nmr_get_stream", "nmr_probe_points", "nmr_probe_rays", "nmr_set_tonemap_curve", "nmr_get_tonemap_curve",
-    "nmr_get_device_image", "nmr_copy_device_image", "nmr_flush_l2", "nmr_get_stats", "nmr_synchronize", "nmr_host_alloc", "nmr_host_free", "nmr_render_update", "nmr_get_density_bitfield",
+    "nmr_get_device_image", "nmr_copy_device_image", "nmr_flush_l2", "nmr_get_stats", "nmr_synchronize", "nmr_host_alloc", "nmr_host_free", "nmr_render_update", "nmr_trajectory_pose", "nmr_get_density_bitfield",
     "nmr_set_density_bitfield", "nmr_debug_encode", "nmr_debug_network", "nmr_debug_trace", "nmr_debug_mesh",
     "nmr_debug_last_frame", "nmr_debug_set_flags", "nmr_render_format", "nmr_render_views_format", "nmr_debug_parse_gltf", "nmr_measure_l2", "nmr_set_overlap", "nmr_set_model_transform", "nmr_get_model_transform",
     "nmr_dump_density_grid", "nmr_load_density_grid", "nmr_read_combined", "nmr_set_lens_model",
@@ -199,6 +200,30 @@ def _pinned_array(shape, dtype=np.float32) -> np.ndarray:
     buf = (C.c_char * n).from_address(p)
     weakref.finalize(buf, _pinned_release, n, p)
     return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+
+def format_transform(mat) -> str:
+    """A 3 x 4 float matrix as the reference's trajectory tool writes it to `transform_N` (S/nerf_mesh_renderer.cu:639-642:
+    `viewProjectionMat.format(Eigen::IOFormat(Eigen::FullPrecision, 0, ", ", ",\\n", "[", "]", "[", "]"))`): six significant digits
+    (%g), every entry right-aligned to the widest one, rows "[...]" joined by ",\\n" with one space of indent after the first, the
+    whole in "[...]".  Pinned on strings produced by the reference's own Eigen (tests/golden/ref_trajectory.npz)."""
+    m = np.asarray(mat, dtype=np.float32).reshape(3, 4)
+    cells = [["%.6g" % float(v) for v in row] for row in m]
+    width = max(len(c) for row in cells for c in row)
+    rows = ["[" + ", ".join(c.rjust(width) for c in row) + "]" for row in cells]
+    return "[" + ",\n ".join(rows) + "]"
+
+
+def _write_png_rgb8(path: str, rgb: np.ndarray):
+    """uint8 [H, W, 3], top row first -> PNG (stdlib zlib only)."""
+    import struct, zlib
+    h, w, _ = rgb.shape
+    raw = b"".join(b"\x00" + rgb[y].tobytes() for y in range(h))
+
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 2, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))
 
 
 def free_pinned_pool():
@@ -637,6 +662,41 @@ class NerfMeshRenderer:
     def view_projection_mat(self, mat):
         a = np.asarray(mat, dtype=np.float32).reshape(3, 4)
         self._ck(lib().nmr_set_camera(self._h, _f3(a.T.reshape(-1))))
+
+    # -- the GUI's trajectory tool ("Run Trajectory", S/nerf_mesh_renderer.cu:604-659, 806-826), without the GUI
+    def trajectory_pose(self, angle: float, distance: float = 1.1, height: float = 0.1, lookat=(0.0, 0.0, 0.0)):
+        """The camera of one step of the tool's arc: eye = (cos(angle) distance, height, sin(angle) distance), looking at `lookat`."""
+        self._ck(lib().nmr_trajectory_pose(self._h, float(angle), float(distance), float(height), _f3(lookat)))
+
+    def export_trajectory(self, out_dir: str = ".", start_angle: float = 0.5, end_angle: float = 2.5, num_images: int = 10,
+                          distance: float = 1.1, height: float = 0.1, lookat=(0.0, 0.0, 0.0)) -> int:
+        """Walks the arc like the reference's GUI loop (defaults = its sliders' initial values) and writes, per step N = 1, 2, ...:
+        `transform_N` - view_projection_mat in the text layout of the reference (Eigen::IOFormat(FullPrecision, 0, ", ", ",\\n",
+        "[", "]", "[", "]"), see format_transform) - and the displayed frame as `trajectory_N.png` (the reference writes a JPEG of
+        the same picture through stb_image_write; no JPEG encoder here, PNG is lossless).  Returns the number of steps written.
+        As in the reference the pose of the step that reaches end_angle is set but not written."""
+        os.makedirs(out_dir, exist_ok=True)
+        f32 = np.float32
+        angle, idx, running = f32(start_angle), 0, True
+        step = f32(f32(f32(end_angle) - f32(start_angle)) / f32(num_images))
+        while running:
+            if idx > 0:
+                self._ck_frame()
+                img = np.asarray(self.read_frame())
+                rgb = np.uint8(np.clip(img[::-1, :, :3], 0.0, 1.0) * f32(255.0))       # row 0 of a frame is the bottom of the picture
+                _write_png_rgb8(os.path.join(out_dir, f"trajectory_{idx}.png"), rgb)
+                with open(os.path.join(out_dir, f"transform_{idx}"), "w") as fh:
+                    fh.write(format_transform(self.view_projection_mat))
+            angle = f32(angle + step)
+            idx += 1
+            if angle >= f32(end_angle):
+                running = False
+            self.trajectory_pose(float(angle), distance, height, lookat)
+        return idx - 1
+
+    def _ck_frame(self):
+        if not self.frame():
+            raise RuntimeError("frame() asked to stop")
 
     def envmap(self, path: str):
         """V/render.py:228 calls this, but the reference module has no such method and its renderer no environment map

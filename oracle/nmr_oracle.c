@@ -305,6 +305,18 @@ ORC_API void orc_camera_orbit(orc_camera* c, float delta_azimuth, float delta_po
     look_to(eye, c->look, c->up, c->view);
 }
 
+/* One pose of the GUI's trajectory tool (S/nerf_mesh_renderer.cu:649-658): cam_pos on a circle, cam_look = glm::normalize(lookat -
+ * cam_pos) = v * (1 / sqrt(x*x + y*y + z*z)) (glm func_geometric.inl:82-90, 48-55), flythrough_camera_look_to. */
+ORC_API void orc_camera_trajectory_pose(orc_camera* c, float angle, float distance, float height, const float* lookat3) {
+    c->eye[0] = cosf(angle) * distance;
+    c->eye[1] = height;
+    c->eye[2] = sinf(angle) * distance;
+    const float d[3] = { lookat3[0] - c->eye[0], lookat3[1] - c->eye[1], lookat3[2] - c->eye[2] };
+    const float inv = 1.0f / sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    c->look[0] = d[0] * inv; c->look[1] = d[1] * inv; c->look[2] = d[2] * inv;
+    look_to(c->eye, c->look, c->up, c->view);
+}
+
 /* updateModelViewProj(): 3x4 camera, stored column-major in out12 (col0,col1,col2,col3) */
 ORC_API void orc_camera_matrix(const orc_camera* c, int screen_w, int screen_h, float* out12) {
     float aspect = (float)(uint32_t)screen_w / (float)(uint32_t)screen_h;

@@ -92,6 +92,7 @@ def lib():
         "orc_camera_init": (None, [C.POINTER(Camera)]),
         "orc_camera_orbit": (None, [C.POINTER(Camera), C.c_float, C.c_float, C.c_float]),
         "orc_camera_matrix": (None, [C.POINTER(Camera), C.c_int, C.c_int, vp]),
+        "orc_camera_trajectory_pose": (None, [C.POINTER(Camera), C.c_float, C.c_float, C.c_float, vp]),
         "orc_f2h": (None, [vp, vp, C.c_int64]),
         "orc_h2f": (None, [vp, vp, C.c_int64]),
         "orc_morton3D": (C.c_uint32, [C.c_uint32, C.c_uint32, C.c_uint32]),
@@ -136,6 +137,15 @@ class OrbitCamera:
 
     def orbit(self, delta_azimuth: float, delta_polar: float, delta_zoom: float):
         lib().orc_camera_orbit(C.byref(self.c), delta_azimuth, delta_polar, delta_zoom)
+
+    def trajectory_pose(self, angle: float, distance: float = 1.1, height: float = 0.1, lookat=(0.0, 0.0, 0.0)):
+        """One pose of the GUI's trajectory tool (S/nerf_mesh_renderer.cu:649-658)."""
+        la = np.ascontiguousarray(lookat, dtype=np.float32)
+        lib().orc_camera_trajectory_pose(C.byref(self.c), C.c_float(angle), C.c_float(distance), C.c_float(height), _p(la))
+
+    @property
+    def view(self):
+        return np.array(list(self.c.view), dtype=np.float32)
 
     def matrix(self) -> np.ndarray:
         """float32[12], column-major 3x4 (col0=right*uLen, col1=up*vLen, col2=fwd, col3=eye)."""

@@ -85,3 +85,30 @@ REF_API void ref_pixel_to_ray(uint32_t spp, int px, int py, int W, int H, const 
     out9[3] = ray.d.x(); out9[4] = ray.d.y(); out9[5] = ray.d.z();
     out9[6] = nd.x(); out9[7] = nd.y(); out9[8] = nd.z();
 }
+
+// ---- the GUI's trajectory tool (S/nerf_mesh_renderer.cu:630-659): where it puts the camera for an angle of its arc, and the text
+// it writes to transform_N.  The reference's own flythrough_camera_look_to, glm::normalize and Eigen::IOFormat. ----
+#include <glm/glm.hpp>
+#include <sstream>
+REF_API void ref_trajectory_camera(float angle, float distance, float height, const float* lookat3, float* eye3, float* look3, float* view16) {
+    float cam_pos[3], cam_look[3], up[3] = {0.f, 1.f, 0.f};
+    cam_pos[0] = cosf(angle) * distance;
+    cam_pos[1] = height;
+    cam_pos[2] = sinf(angle) * distance;
+    glm::vec3 look{lookat3[0] - cam_pos[0], lookat3[1] - cam_pos[1], lookat3[2] - cam_pos[2]};
+    look = glm::normalize(look);
+    cam_look[0] = look.x; cam_look[1] = look.y; cam_look[2] = look.z;
+    flythrough_camera_look_to(cam_pos, cam_look, up, view16, 0);
+    for (int k = 0; k < 3; ++k) { eye3[k] = cam_pos[k]; look3[k] = cam_look[k]; }
+}
+REF_API int ref_format_transform(const float* m12_rowmajor, char* out, int cap) {
+    Eigen::Matrix<float, 3, 4> M;
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) M(r, c) = m12_rowmajor[r * 4 + c];
+    Eigen::IOFormat json_format(Eigen::FullPrecision, 0, ", ", ",\n", "[", "]", "[", "]");
+    std::ostringstream ss;
+    ss << M.format(json_format);
+    const std::string t = ss.str();
+    if ((int)t.size() + 1 > cap) return -1;
+    std::memcpy(out, t.c_str(), t.size() + 1);
+    return (int)t.size();
+}

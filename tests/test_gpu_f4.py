@@ -191,3 +191,59 @@ def test_two_nerfs_merge_by_depth(small_snapshot, second_snapshot, glasses_gltf)
         assert same_owner.mean() > 0.995
         d = np.abs(frame - ref_frame)[same_owner]
         assert float(np.mean(d.max(axis=-1) > 6e-3)) <= 0.004
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+def _read_png_rgb8(path):
+    """8-bit RGB, filter type 0 on every row (what pynmr writes)"""
+    import struct, zlib
+    data = open(path, "rb").read()
+    assert data[:8] == b"\x89PNG\r\n\x1a\n"
+    p, idat, w, h = 8, b"", 0, 0
+    while p < len(data):
+        n = struct.unpack(">I", data[p:p + 4])[0]; tag = data[p + 4:p + 8]; body = data[p + 8:p + 8 + n]
+        assert struct.unpack(">I", data[p + 8 + n:p + 12 + n])[0] == (zlib.crc32(tag + body) & 0xFFFFFFFF)
+        if tag == b"IHDR":
+            w, h, depth, colour = struct.unpack(">IIBB", body[:10]); assert (depth, colour) == (8, 2)
+        elif tag == b"IDAT":
+            idat += body
+        p += 12 + n
+    raw = np.frombuffer(zlib.decompress(idat), dtype=np.uint8).reshape(h, 1 + 3 * w)
+    assert (raw[:, 0] == 0).all()
+    return raw[:, 1:].reshape(h, w, 3)
+
+
+def test_trajectory_export(small_snapshot, glasses_gltf, tmp_path):
+    """The GUI's trajectory tool without the GUI (SURVEY 8f.4 side formats): poses bit-exact vs the oracle (which is pinned on the
+    reference's own camera code, tests/golden/ref_trajectory.npz), transform_N in Eigen's text layout, one PNG per step."""
+    import pynmr
+    import synth
+    from oracle import oracle as O
+    path, snap = small_snapshot
+    r = pynmr.NerfMeshRenderer(W, HH)
+    nerf = r.load_nerf(path)
+    assert r.load_mesh(glasses_gltf, t=synth.GLASSES_T, s=synth.GLASSES_S, r=synth.GLASSES_R_WXYZ) is not None
+    cam = O.OrbitCamera(W, HH)
+    rng = np.random.default_rng(3)
+    for _ in range(50):
+        a, d, h = float(rng.uniform(-7, 7)), float(rng.uniform(0.3, 4.0)), float(rng.uniform(-1.5, 1.5))
+        la = rng.uniform(-0.4, 0.4, 3).astype(np.float32)
+        r.trajectory_pose(a, d, h, la); cam.trajectory_pose(a, d, h, la)
+        assert np.array_equal(cam12(r).view(np.uint32), cam.matrix().view(np.uint32))
+    out = str(tmp_path / "traj")
+    n = r.export_trajectory(out, num_images=5)                  # the sliders' other defaults: arc 0.5 .. 2.5 at distance 1.1, height 0.1
+    assert n == 4 and sorted(os.listdir(out)) == sorted([f"trajectory_{k}.png" for k in range(1, 5)] + [f"transform_{k}" for k in range(1, 5)])
+    step = np.float32(np.float32(2.5) - np.float32(0.5)) / np.float32(5)
+    angle = np.float32(0.5)
+    for k in range(1, 5):
+        angle = np.float32(angle + step)
+        cam.trajectory_pose(float(angle), 1.1, 0.1)
+        want = cam.matrix().reshape(4, 3).T                     # 3 x 4, like view_projection_mat
+        assert open(os.path.join(out, f"transform_{k}")).read() == pynmr.format_transform(want)
+        png = _read_png_rgb8(os.path.join(out, f"trajectory_{k}.png"))
+        r.trajectory_pose(float(angle), 1.1, 0.1)
+        assert r.frame()
+        img = np.asarray(r.read_frame())
+        assert png.shape[:2] == (HH, W)
+        assert np.array_equal(png[..., :3], np.uint8(np.clip(img[::-1, :, :3], 0.0, 1.0) * np.float32(255.0)))
+        assert png[..., :3].std() > 5                           # a picture, not a constant
