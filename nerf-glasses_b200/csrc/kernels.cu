@@ -1213,6 +1213,7 @@ __global__ void __launch_bounds__(TC ? kTile * kGroupsTC : kTile, TC ? NMR_MARCH
                 dir = v3(q0.x, q0.y, q0.z); t = q0.w; t_start = q1.x; t_surface = q1.y; idx = __float_as_uint(q1.z); t_limit = q1.w;
                 sr = q2.x; sg = q2.y; sb = q2.z; sw = q2.w;
                 cr = cg = cb = ca = 0.f; max_weight = 0.f; depth = 0.f; n_samples = 0;
+                origin = cam_origin;       // (the group's previous ray may have been a lens ray under the plate model: its transmitted segment starts beside the eye)
                 active = true;
                 phase = 0u; kb = 0u; sat = false;
                 if (idx & kLensRayFlag) {

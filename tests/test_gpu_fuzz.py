@@ -57,3 +57,17 @@ def test_random_poses_accumulation_and_two_nerfs_match_the_oracle():
     poses (tools/fuzz_scene.py)."""
     import fuzz_scene
     assert fuzz_scene.run(20, 5, verbose=False) == []
+
+
+def test_random_call_sequences_leave_no_state_behind():
+    """A renderer driven through random API calls ends up rendering its final state exactly like a fresh renderer put into that
+    state (tools/fuzz_state.py).  Round 2's runs found a lens ray's shifted origin (plate model) leaking into the next ray of its
+    ray group - visible only in frames large enough for a group to march more than one ray."""
+    import fuzz_state
+    assert fuzz_state.run(25, 1, verbose=False) == []
+
+
+def test_plate_lenses_in_frames_where_ray_groups_march_several_rays():
+    import fuzz_poses
+    violations, worst, over = fuzz_poses.run(8, 31, True, verbose=False, plate=True, size=(512, 384))
+    assert violations == 0 and over == 0 and worst <= 2.0 / 255.0
