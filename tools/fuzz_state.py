@@ -20,7 +20,7 @@ def make_ops(rng, box0):
     """a random call sequence: [(name, args)] - all arguments drawn here, so that any sub-sequence can be replayed"""
     ops = []
     for _ in range(int(rng.integers(8, 30))):
-        k = int(rng.integers(0, 21))
+        k = int(rng.integers(0, 22))
         if k == 0: ops.append(("orbit", (float(rng.uniform(-1, 1)), float(rng.uniform(-0.5, 0.5)), float(rng.uniform(-1, 4)))))
         elif k == 1: ops.append(("dolly", (float(rng.uniform(0, 0.8)),)))
         elif k == 2:
@@ -43,6 +43,7 @@ def make_ops(rng, box0):
         elif k == 17: ops.append(("update", ()))
         elif k == 18: ops.append(("shard", (int(rng.integers(0, 3)),)))
         elif k == 19: ops.append(("probes", (rng.uniform(-0.3, 0.3, (64, 3)).astype(np.float32),)))
+        elif k == 20: ops.append(("floaties", ()))
         else: ops.append(("render", (W, HH, 1, False, "u8")))
     return ops
 
@@ -55,6 +56,7 @@ def apply_state(r, nerf, mesh, st):
     nerf.nerf.render_min_transmittance = st["min_t"]
     nerf.model_translation = st["model_t"]; nerf.model_rotation = st["model_r"]
     mesh.nodes[0].translation = st["mesh_t"]; mesh.nodes[0].scale = st["mesh_s"]
+    if st["floaties"]: r.remove_floaties()
     r.set_lens(st["lens_on"]); r.set_lens_model(st["lens_model"], st["lens_thickness"])
     r.set_surface_insertion(st["surface"])
     r.set_overlap(st["overlap"])
@@ -83,7 +85,7 @@ def run(n_seq: int = 20, seed: int = 0, verbose: bool = True):
             r, nerf, mesh = fresh()
             st = {"aabb": box0, "background": bg0, "curve": 0, "min_t": 0.01, "model_t": np.zeros(3, np.float32), "model_r": np.zeros(3, np.float32),
                   "mesh_t": list(synth.GLASSES_T), "mesh_s": list(synth.GLASSES_S), "lens_on": True, "lens_model": 0, "lens_thickness": 0.0,
-                  "surface": 0, "overlap": True, "cam": cam0}
+                  "surface": 0, "overlap": True, "cam": cam0, "floaties": False}
             kept = None
             for name, a in ops:
                 if name == "orbit": r.orbit(*a); st["cam"] = r.view_projection_mat.copy()
@@ -106,6 +108,7 @@ def run(n_seq: int = 20, seed: int = 0, verbose: bool = True):
                 elif name == "views": r.render_views(nerf, np.stack([st["cam"]] * a[0]), a[1], a[2], dtype=DT[a[3]])
                 elif name == "update": kept = nerf.render_update(kept, W, HH, linear=False)
                 elif name == "shard": r.set_shard(a[0], 3, 16); r.frame(); r.set_shard(0, 1, 16)
+                elif name == "floaties": st["floaties"] = True; r.remove_floaties()
                 elif name == "probes": nerf.probe_points(a[0], [0, -1, 0]); nerf.probe_rays(a[0], [0, -1, 0])
             # the picture of the final state, by the driven renderer and by a fresh one
             r.view_projection_mat = st["cam"]
