@@ -326,6 +326,10 @@ def run_ours(args, rank: int, world: int, local_rank: int, dist):
                      "l1_sectors_per_sample": (float(cap["l1_global_load_sectors"]) / max(1.0, float(cap.get("samples", 0)))) if cap and cap.get("samples") else None,
                      "tensor_pipe_active_pct_ncu": cap.get("tensor_pipe_active_pct") if cap else None,
                      "l2_hit_rate_pct_ncu": cap.get("l2_hit_rate_pct") if cap else None,
+                     # what actually limits the kernel: instruction issue - ~4100 warp instructions per 32 samples
+                     # at ~55 % of the issue slots; none of the memory roofs above is near
+                     "issue_slot_utilisation_pct_ncu": cap.get("issue_slot_utilisation_pct") if cap else None,
+                     "warp_instructions_per_32_samples_ncu": cap.get("warp_instructions_per_32_samples") if cap else None,
                      "kernel": "march_kernel<tcgen05>",
                      "algorithmic_bytes_per_sample": ALGO_BYTES_PER_SAMPLE, "algorithmic_flop_per_sample": ALGO_FLOP_PER_SAMPLE,
                      "samples_per_launch": samples_per_launch, "kernel_ms_per_launch": float(np.mean(march_ms)),
