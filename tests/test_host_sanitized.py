@@ -124,3 +124,19 @@ def test_snapshot_reader_survives_mutated_files(harness, tmp_path):
         p = str(tmp_path / f"head_{k}.msgpack"); open(p, "wb").write(bytes(b)); files.append(p)
     out = run(harness, "snapshot", files)
     assert "rejected" in out
+
+
+def test_readers_reject_pathological_nesting_and_lengths(harness, tmp_path):
+    """millions of nested containers, declared lengths of 4 G entries, empty files: rejected, no stack overflow, no huge allocation"""
+    snaps = {"nest_arr": b"\x91" * 2000000 + b"\x00", "nest_map": b"\x81\xa1k" * 500000 + b"\x00", "huge_arr": b"\xdd\xff\xff\xff\xff" + b"\x00" * 10,
+             "huge_map": b"\xdf\xff\xff\xff\xff" + b"\xa1k\x00" * 3, "huge_bin": b"\x81\xa1k\xc6\xff\xff\xff\xff" + b"\x00" * 10,
+             "huge_str": b"\xdb\xff\xff\xff\xff" + b"a" * 10, "empty": b""}
+    files = []
+    for name, data in snaps.items():
+        p = tmp_path / f"{name}.msgpack"; p.write_bytes(data); files.append(str(p))
+    assert f"accepted 0 rejected {len(files)}" in run(harness, "snapshot", files)
+    docs = {"deep_arr": "[" * 1000000, "deep_obj": '{"a":' * 500000 + "1" + "}" * 500000, "empty": "", "just_null": "null"}
+    files = []
+    for name, text in docs.items():
+        p = tmp_path / f"{name}.gltf"; p.write_text(text); files.append(str(p))
+    assert f"accepted 0 rejected {len(files)}" in run(harness, "gltf", files)
