@@ -1,0 +1,68 @@
+"""The C ABI with arguments it must refuse (GPU box): every call returns an error code and a message - no crash, no CUDA error left
+behind - and the context renders normally afterwards.  (The reference's bindings throw Python exceptions or print and return None
+for the same mistakes, S/python_api.cu:286-331.)"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+W, HH = 128, 72
+
+
+def test_bad_arguments_are_refused_and_leave_the_context_usable(small_snapshot, glasses_gltf, tmp_path):
+    import pynmr
+    import synth
+    L = pynmr.lib()
+    path, _ = small_snapshot
+    r = pynmr.NerfMeshRenderer(W, HH)
+    nerf = r.load_nerf(path)
+    assert r.load_mesh(glasses_gltf, t=synth.GLASSES_T, s=synth.GLASSES_S, r=synth.GLASSES_R_WXYZ) is not None
+    r.orbit(0.3, -0.1, 4.0)
+    good = np.asarray(nerf.render(W, HH, 1, linear=False)).copy()
+    h = r._h
+    out = np.zeros((HH, W, 4), np.float32)
+    p = out.ctypes.data_as(C.c_void_p)
+    cam = np.zeros(12, np.float32)
+    f3 = (C.c_float * 3)(0, 0, 0)
+    pts = np.zeros((4, 3), np.float32)
+    res = np.zeros(4, np.float32)
+    calls = {
+        "render: zero width": lambda: L.nmr_render(h, nerf._id, 0, HH, 1, 0, p),
+        "render: negative height": lambda: L.nmr_render(h, nerf._id, W, -5, 1, 0, p),
+        "render: zero samples": lambda: L.nmr_render(h, nerf._id, W, HH, 0, 0, p),
+        "render: null image": lambda: L.nmr_render(h, nerf._id, W, HH, 1, 0, None),
+        "render: unknown nerf": lambda: L.nmr_render(h, 99, W, HH, 1, 0, p),
+        "render: negative nerf": lambda: L.nmr_render(h, -1, W, HH, 1, 0, p),
+        "render_format: bad format": lambda: L.nmr_render_format(h, nerf._id, W, HH, 1, 0, 7, p),
+        "render_update: null image": lambda: L.nmr_render_update(h, nerf._id, W, HH, 0, 0, None, 0, None),
+        "render_views: no views": lambda: L.nmr_render_views_format(h, nerf._id, 0, cam.ctypes.data_as(C.c_void_p), W, HH, 0, 0, p),
+        "render_views: null cameras": lambda: L.nmr_render_views_format(h, nerf._id, 2, None, W, HH, 0, 0, p),
+        "set_shard: rank >= world": lambda: L.nmr_set_shard(h, 3, 3, 8),
+        "set_shard: zero world": lambda: L.nmr_set_shard(h, 0, 0, 8),
+        "set_shard: zero band": lambda: L.nmr_set_shard(h, 0, 2, 0),
+        "lens model: unknown": lambda: L.nmr_set_lens_model(h, 5, 0.01),
+        "lens model: negative thickness": lambda: L.nmr_set_lens_model(h, 1, -1.0),
+        "surface rule: unknown": lambda: L.nmr_set_surface_insertion(h, 9),
+        "tonemap curve: unknown": lambda: L.nmr_set_tonemap_curve(h, nerf._id, 11),
+        "render_aabb: unknown nerf": lambda: L.nmr_set_render_aabb(h, 42, f3, f3),
+        "probe_points: unknown nerf": lambda: L.nmr_probe_points(h, 42, 4, pts.ctypes.data_as(C.c_void_p), f3, res.ctypes.data_as(C.c_void_p)),
+        "load_nerf: no such file": lambda: L.nmr_load_nerf(h, str(tmp_path / "nope.msgpack").encode(), C.byref(C.c_int())),
+        "load_mesh: no such file": lambda: L.nmr_load_mesh(h, str(tmp_path / "nope.gltf").encode(), f3, f3, (C.c_float * 4)(1, 0, 0, 0), C.byref(C.c_int())),
+        "load_density_grid: no such file": lambda: L.nmr_load_density_grid(h, nerf._id, str(tmp_path / "nope.bin").encode(), None),
+        "read_combined: nothing merged": lambda: L.nmr_read_combined(h, p, None),
+    }
+    for name, call in calls.items():
+        rc = call()
+        assert rc != 0, name
+        assert L.nmr_last_error(h), name
+        # the context still renders, and renders the same picture
+        again = np.asarray(nerf.render(W, HH, 1, linear=False))
+        assert np.array_equal(again.view(np.uint32), good.view(np.uint32)), name
+    # a garbage file under a real name
+    bad = tmp_path / "garbage.msgpack"; bad.write_bytes(b"\x93\x01\x02")
+    assert r.load_nerf(str(bad)) is None
+    badg = tmp_path / "garbage.gltf"; badg.write_text("{\"asset\": 1")
+    assert r.load_mesh(str(badg)) is None
+    assert np.array_equal(np.asarray(nerf.render(W, HH, 1, linear=False)).view(np.uint32), good.view(np.uint32))
