@@ -181,11 +181,25 @@ def _ptr(a: np.ndarray):
 
 
 _envmap_warned = False
-_pinned_pool: dict = {}     # size in bytes -> [device-registered host pointers ready for reuse]
+_pinned_pool: dict = {}     # size in bytes -> [device-registered host pointers ready for reuse]; insertion order = age of a size
+_PINNED_POOL_CAP = 512 << 20   # bytes kept for reuse; beyond it the sizes not used for longest go back to the driver
 
 
 def _pinned_release(nbytes: int, p: int):
-    _pinned_pool.setdefault(nbytes, []).append(p)
+    try:
+        blocks = _pinned_pool.pop(nbytes, [])
+        blocks.append(p)
+        _pinned_pool[nbytes] = blocks                      # most recently used size last
+        total = sum(n * len(b) for n, b in _pinned_pool.items())
+        while total > _PINNED_POOL_CAP and _pinned_pool:
+            n0 = next(iter(_pinned_pool))                  # the size that has not been released to for longest
+            b0 = _pinned_pool[n0]
+            lib().nmr_host_free(b0.pop())
+            total -= n0
+            if not b0:
+                del _pinned_pool[n0]
+    except Exception:       # (interpreter shutdown)
+        pass
 
 
 def _pinned_array(shape, dtype=np.float32) -> np.ndarray:
@@ -357,16 +371,15 @@ class _NerfSettings:
         return self.ACTIVATIONS[self._tb._info().density_activation]
 
     def __init__(self, tb):
-        self._tb = tb
-        self._min_t = 0.01
+        self._tb = tb            # (created per access by Testbed.nerf: no reference cycle that would keep a renderer alive until the GC runs)
 
     @property
     def render_min_transmittance(self):
-        return self._min_t
+        return self._tb._min_t
 
     @render_min_transmittance.setter
     def render_min_transmittance(self, v):
-        self._min_t = float(v)
+        self._tb._min_t = float(v)
         self._tb._r._ck(lib().nmr_set_min_transmittance(self._tb._r._h, self._tb._id, float(v)))
 
 
@@ -383,8 +396,11 @@ class Testbed:
 
     def __init__(self, renderer: "NerfMeshRenderer", nerf_id: int):
         self._r, self._id = renderer, nerf_id
-        self.nerf = _NerfSettings(self)
-        self._render_aabb = BoundingBox(_owner=self)
+        self._min_t = 0.01
+
+    @property
+    def nerf(self) -> "_NerfSettings":
+        return _NerfSettings(self)
 
     # -- crop box
     def _get_render_aabb(self):
@@ -397,7 +413,7 @@ class Testbed:
 
     @property
     def render_aabb(self) -> BoundingBox:
-        return self._render_aabb
+        return BoundingBox(_owner=self)
 
     @render_aabb.setter
     def render_aabb(self, box: BoundingBox):
