@@ -194,8 +194,9 @@ def _pinned_release(nbytes: int, p: int):
         while total > _PINNED_POOL_CAP and _pinned_pool:
             n0 = next(iter(_pinned_pool))                  # the size that has not been released to for longest
             b0 = _pinned_pool[n0]
-            lib().nmr_host_free(b0.pop())
-            total -= n0
+            if b0:
+                lib().nmr_host_free(b0.pop())
+                total -= n0
             if not b0:
                 del _pinned_pool[n0]
     except Exception:       # (interpreter shutdown)
@@ -209,6 +210,8 @@ def _pinned_array(shape, dtype=np.float32) -> np.ndarray:
     n = int(np.prod(shape)) * np.dtype(dtype).itemsize
     free = _pinned_pool.get(n)
     p = free.pop() if free else lib().nmr_host_alloc(n)
+    if free is not None and not free:
+        del _pinned_pool[n]                                # (no empty lists: the pool's first key is always a size with a block to give back)
     if not p:
         raise MemoryError("nmr_host_alloc failed")
     buf = (C.c_char * n).from_address(p)

@@ -328,3 +328,22 @@ def test_integration_pybind11_stub_compiles_and_binds(tmp_path):
              "print('ok')") % str(tmp_path)
     res = subprocess.run([sys.executable, "-c", probe], capture_output=True, text=True)
     assert res.returncode == 0 and "ok" in res.stdout, res.stderr[-2000:]
+
+
+def test_pinned_pool_is_bounded(monkeypatch):
+    """The shim's pool of page-locked blocks gives the least recently used sizes back to the driver beyond its cap - also when
+    sizes whose blocks are all in use sit at the front of the pool (no GPU: the library is replaced by a recorder)."""
+    import pynmr
+    freed = []
+
+    class Fake:
+        def nmr_host_free(self, p):
+            freed.append(p)
+    monkeypatch.setattr(pynmr, "lib", lambda: Fake())
+    monkeypatch.setattr(pynmr, "_PINNED_POOL_CAP", 1000)
+    monkeypatch.setattr(pynmr, "_pinned_pool", {300: []})
+    for n, p in [(400, 1), (400, 2), (300, 3), (200, 4), (500, 5)]:
+        pynmr._pinned_release(n, p)
+    assert freed == [2, 1]
+    assert pynmr._pinned_pool == {300: [3], 200: [4], 500: [5]}
+    assert sum(n * len(b) for n, b in pynmr._pinned_pool.items()) <= 1000
