@@ -959,10 +959,16 @@ NMR_API int nmr_load_mesh(nmr_ctx* ctx, const char* path, const float t[3], cons
     });
 }
 
+namespace {
+// setters refuse values a kernel cannot make sense of (a NaN in the camera would turn screen rectangles into garbage grid sizes)
+bool all_finite(const float* v, int n) { if (!v) return true; for (int i = 0; i < n; ++i) if (!std::isfinite(v[i])) return false; return true; }
+}  // namespace
+
 NMR_API int nmr_set_mesh_transform(nmr_ctx* ctx, int mesh_id, const float t[3], const float s[3], const float r_wxyz[4]) {
     return guarded(ctx, [&]() -> int {
         if (mesh_id < 0 || mesh_id >= (int)ctx->meshes.size()) return fail(ctx, NMR_ERR_INVALID, "unknown mesh id");
         Mesh& m = *ctx->meshes[(size_t)mesh_id];
+        if (!all_finite(t, 3) || !all_finite(s, 3) || !all_finite(r_wxyz, 4)) return fail(ctx, NMR_ERR_INVALID, "mesh transform: values must be finite");
         if (t) std::memcpy(m.t, t, 12);
         if (s) std::memcpy(m.s, s, 12);
         if (r_wxyz) std::memcpy(m.r, r_wxyz, 16);
@@ -989,7 +995,7 @@ NMR_API int nmr_get_render_aabb(nmr_ctx* ctx, int id, float mn[3], float mx[3]) 
     return guarded(ctx, [&]() -> int { try { Nerf* n = get_nerf(ctx, id); std::memcpy(mn, n->render_aabb_min, 12); std::memcpy(mx, n->render_aabb_max, 12); return NMR_OK; } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); } });
 }
 NMR_API int nmr_set_render_aabb(nmr_ctx* ctx, int id, const float mn[3], const float mx[3]) {
-    return guarded(ctx, [&]() -> int { try { Nerf* n = get_nerf(ctx, id); if (mn) std::memcpy(n->render_aabb_min, mn, 12); if (mx) std::memcpy(n->render_aabb_max, mx, 12); ctx->surf.spp = 0; return NMR_OK; } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); } });
+    return guarded(ctx, [&]() -> int { try { Nerf* n = get_nerf(ctx, id); if (!all_finite(mn, 3) || !all_finite(mx, 3)) return fail(ctx, NMR_ERR_INVALID, "render_aabb: values must be finite"); if (mn) std::memcpy(n->render_aabb_min, mn, 12); if (mx) std::memcpy(n->render_aabb_max, mx, 12); ctx->surf.spp = 0; return NMR_OK; } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); } });
 }
 NMR_API int nmr_get_aabb(nmr_ctx* ctx, int id, float mn[3], float mx[3]) {
     return guarded(ctx, [&]() -> int { try { Nerf* n = get_nerf(ctx, id); std::memcpy(mn, n->host.aabb_min, 12); std::memcpy(mx, n->host.aabb_max, 12); return NMR_OK; } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); } });
@@ -998,7 +1004,7 @@ NMR_API int nmr_get_background(nmr_ctx* ctx, int id, float rgba[4]) {
     return guarded(ctx, [&]() -> int { try { std::memcpy(rgba, get_nerf(ctx, id)->background, 16); return NMR_OK; } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); } });
 }
 NMR_API int nmr_set_background(nmr_ctx* ctx, int id, const float rgba[4]) {
-    return guarded(ctx, [&]() -> int { try { std::memcpy(get_nerf(ctx, id)->background, rgba, 16); return NMR_OK; } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); } });
+    return guarded(ctx, [&]() -> int { try { if (!rgba || !all_finite(rgba, 4)) return fail(ctx, NMR_ERR_INVALID, "background: four finite values"); std::memcpy(get_nerf(ctx, id)->background, rgba, 16); return NMR_OK; } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); } });
 }
 NMR_API int nmr_set_tonemap_curve(nmr_ctx* ctx, int id, int curve) {
     return guarded(ctx, [&]() -> int {
@@ -1013,12 +1019,13 @@ NMR_API int nmr_get_tonemap_curve(nmr_ctx* ctx, int id, int* out_curve) {
     });
 }
 NMR_API int nmr_set_min_transmittance(nmr_ctx* ctx, int id, float v) {
-    return guarded(ctx, [&]() -> int { try { get_nerf(ctx, id)->min_transmittance = v; return NMR_OK; } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); } });
+    return guarded(ctx, [&]() -> int { try { if (!(v >= 0.f && v <= 1.f)) return fail(ctx, NMR_ERR_INVALID, "min_transmittance must lie in [0, 1]"); get_nerf(ctx, id)->min_transmittance = v; return NMR_OK; } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); } });
 }
 
 NMR_API int nmr_set_model_transform(nmr_ctx* ctx, int id, const float translation[3], const float rotation_pi[3]) {
     return guarded(ctx, [&]() -> int {
         Nerf* n; try { n = get_nerf(ctx, id); } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); }
+        if (!all_finite(translation, 3) || !all_finite(rotation_pi, 3)) return fail(ctx, NMR_ERR_INVALID, "model transform: values must be finite");
         if (translation) std::memcpy(n->model_translation, translation, 12);
         if (rotation_pi) std::memcpy(n->model_rotation_pi, rotation_pi, 12);
         // AngleAxis(rx pi, X) * AngleAxis(ry pi, Y) * AngleAxis(rz pi, Z) (S/ngp/testbed.cu:1538-1541), evaluated in double
@@ -1061,11 +1068,15 @@ NMR_API int nmr_get_nerf_info(nmr_ctx* ctx, int id, nmr_nerf_info* o) {
 }
 
 NMR_API int nmr_orbit(nmr_ctx* ctx, float daz, float dpol, float dzoom) {
-    return guarded(ctx, [&]() -> int { ctx->camera.orbit(daz, dpol, dzoom); set_camera_from_orbit(ctx); return NMR_OK; });
+    return guarded(ctx, [&]() -> int {
+        if (!std::isfinite(daz) || !std::isfinite(dpol) || !std::isfinite(dzoom)) return fail(ctx, NMR_ERR_INVALID, "orbit: values must be finite");
+        ctx->camera.orbit(daz, dpol, dzoom); set_camera_from_orbit(ctx); return NMR_OK;
+    });
 }
 NMR_API int nmr_trajectory_pose(nmr_ctx* ctx, float angle, float distance, float height, const float lookat[3]) {
     return guarded(ctx, [&]() -> int {
         const float zero[3] = {0.f, 0.f, 0.f};
+        if (!std::isfinite(angle) || !std::isfinite(distance) || !std::isfinite(height) || !all_finite(lookat, 3)) return fail(ctx, NMR_ERR_INVALID, "trajectory pose: values must be finite");
         ctx->camera.trajectory_pose(angle, distance, height, lookat ? lookat : zero);
         set_camera_from_orbit(ctx);
         return NMR_OK;
@@ -1076,6 +1087,7 @@ NMR_API int nmr_get_camera(nmr_ctx* ctx, float out12[12]) {
 }
 NMR_API int nmr_set_camera(nmr_ctx* ctx, const float in12[12]) {
     return guarded(ctx, [&]() -> int {
+        if (!in12 || !all_finite(in12, 12)) return fail(ctx, NMR_ERR_INVALID, "camera: twelve finite values");
         std::memcpy(ctx->cam12, in12, sizeof(ctx->cam12));
         for (int k = 0; k < 3; ++k) ctx->camera.eye[k] = in12[9 + k];   // keeps orbit() and the mesh stage coherent with the new pose
         ctx->surf.spp = 0;
@@ -1277,6 +1289,7 @@ NMR_API int nmr_render(nmr_ctx* ctx, int nerf_id, int width, int height, int spp
 NMR_API int nmr_render_views_format(nmr_ctx* ctx, int nerf_id, int n_views, const float* cams12, int width, int height, int linear, int format, void* out_rgba_v) {
     return guarded(ctx, [&]() -> int {
         if (width <= 0 || height <= 0 || n_views < 1 || !cams12) return fail(ctx, NMR_ERR_INVALID, "bad render_views arguments");
+        for (int v = 0; v < n_views; ++v) if (!all_finite(cams12 + (size_t)v * 12, 12)) return fail(ctx, NMR_ERR_INVALID, "render_views: cameras must be finite");
         if (format < NMR_PIXEL_F32 || format > NMR_PIXEL_U8) return fail(ctx, NMR_ERR_INVALID, "bad pixel format");
         const size_t bpp = pixel_bytes(format);
         char* out_rgba = static_cast<char*>(out_rgba_v);

@@ -52,6 +52,16 @@ def test_bad_arguments_are_refused_and_leave_the_context_usable(small_snapshot, 
         "load_mesh: no such file": lambda: L.nmr_load_mesh(h, str(tmp_path / "nope.gltf").encode(), f3, f3, (C.c_float * 4)(1, 0, 0, 0), C.byref(C.c_int())),
         "load_density_grid: no such file": lambda: L.nmr_load_density_grid(h, nerf._id, str(tmp_path / "nope.bin").encode(), None),
         "read_combined: nothing merged": lambda: L.nmr_read_combined(h, p, None),
+        "camera: NaN": lambda: L.nmr_set_camera(h, np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, float("nan"), 2], np.float32).ctypes.data_as(C.POINTER(C.c_float))),
+        "camera: inf": lambda: L.nmr_set_camera(h, np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, float("inf"), 0, 2], np.float32).ctypes.data_as(C.POINTER(C.c_float))),
+        "orbit: NaN": lambda: L.nmr_orbit(h, float("nan"), 0.0, 0.0),
+        "render_aabb: NaN": lambda: L.nmr_set_render_aabb(h, nerf._id, (C.c_float * 3)(float("nan"), 0, 0), f3),
+        "background: inf": lambda: L.nmr_set_background(h, nerf._id, (C.c_float * 4)(float("inf"), 0, 0, 1)),
+        "min transmittance: 2": lambda: L.nmr_set_min_transmittance(h, nerf._id, 2.0),
+        "model transform: NaN": lambda: L.nmr_set_model_transform(h, nerf._id, (C.c_float * 3)(0, float("nan"), 0), None),
+        "mesh transform: inf scale": lambda: L.nmr_set_mesh_transform(h, 0, None, (C.c_float * 3)(1, float("inf"), 1), None),
+        "render_views: NaN camera": lambda: L.nmr_render_views_format(h, nerf._id, 1, np.full(12, np.nan, np.float32).ctypes.data_as(C.c_void_p), W, HH, 0, 0, p),
+        "trajectory pose: inf": lambda: L.nmr_trajectory_pose(h, float("inf"), 1.1, 0.1, None),
     }
     for name, call in calls.items():
         rc = call()
