@@ -380,6 +380,9 @@ __device__ __forceinline__ RayInit init_ray(const FrameParams& P, uint32_t x, ui
     r.t = fmaxf(box_ray_tmin(P.aabb_min, P.aabb_max, r.origin, d), 0.0f) + 1e-6f;
     r.alive = box_contains(P.aabb_min, P.aabb_max, vadd(r.origin, vmul(d, r.t)));
     r.t_limit = occupied_exit(P, r.origin, d, r.t_occ_in);
+    // A walk gets nowhere once a step no longer changes t (t beyond ~4e4 with the scene in the unit cube: a camera in the wrong
+    // units) and the reference's loops would spin for ever; such a ray - and one whose set-up produced a NaN - sees nothing.
+    if (!(r.t_limit + min_cone_stepsize() > r.t_limit)) { r.alive = false; r.t_limit = -1.f; }
     return r;
 }
 

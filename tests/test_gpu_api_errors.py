@@ -76,3 +76,29 @@ def test_bad_arguments_are_refused_and_leave_the_context_usable(small_snapshot, 
     badg = tmp_path / "garbage.gltf"; badg.write_text("{\"asset\": 1")
     assert r.load_mesh(str(badg)) is None
     assert np.array_equal(np.asarray(nerf.render(W, HH, 1, linear=False)).view(np.uint32), good.view(np.uint32))
+
+
+def test_absurd_but_finite_cameras_return(small_snapshot, glasses_gltf):
+    """A camera in the wrong units (1e4 .. 3e38 away), one looking exactly along an axis, one whose direction block is zero: the frame
+    comes back, finite, at once.  (At |t| beyond ~4e4 a step of the reference's walk no longer changes t and its loops would never
+    end; such rays are declared dead at set-up, device_common.cuh: init_ray.)"""
+    import time
+    import pynmr
+    import synth
+    path, _ = small_snapshot
+    r = pynmr.NerfMeshRenderer(W, HH)
+    r.load_nerf(path)
+    assert r.load_mesh(glasses_gltf, t=synth.GLASSES_T, s=synth.GLASSES_S, r=synth.GLASSES_R_WXYZ) is not None
+    base = r.view_projection_mat.copy()
+    cams = []
+    for dist in (1e2, 1e4, 4e4, 1e5, 1e9, 1e20, 3e38):
+        m = base.copy(); m[:, 3] = -m[:, 2] * dist
+        cams.append(m)
+    cams.append(np.array([[1, 0, 0, 0.5], [0, 1, 0, 0.5], [0, 0, -1, 3.0]], np.float32))
+    cams.append(np.array([[0, 0, 0, 0], [0, 0, 0, 0], [0, 0, 0, 2.0]], np.float32))
+    for m in cams:
+        t0 = time.time()
+        r.view_projection_mat = m
+        assert r.frame()
+        img = np.asarray(r.read_frame())
+        assert np.isfinite(img).all() and time.time() - t0 < 5.0
