@@ -94,6 +94,11 @@ def test_absurd_but_finite_cameras_return(small_snapshot, glasses_gltf):
     for dist in (1e2, 1e4, 4e4, 1e5, 1e9, 1e20, 3e38):
         m = base.copy(); m[:, 3] = -m[:, 2] * dist
         cams.append(m)
+    d0 = float(np.linalg.norm(base[:, 3]))
+    for dist in (3e4, 3.5e4, 4e4, 1e5, 1e6):          # telephoto views of the same framing: rays that DO aim at the head from that far
+        m = base.copy(); k = dist / d0
+        m[:, 3] = base[:, 3] * k; m[:, 0] = base[:, 0] / k; m[:, 1] = base[:, 1] / k
+        cams.append(m)
     cams.append(np.array([[1, 0, 0, 0.5], [0, 1, 0, 0.5], [0, 0, -1, 3.0]], np.float32))
     cams.append(np.array([[0, 0, 0, 0], [0, 0, 0, 0], [0, 0, 0, 2.0]], np.float32))
     for m in cams:
