@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libnmr.so")
-SOURCES = ["api.cu", "host.cpp", "value.cpp", "kernels.cu", "floaties.cu"]
+SOURCES = ["api.cu", "host.cpp", "value.cpp", "mikk.cpp", "kernels.cu", "floaties.cu"]
 HEADERS = ["host.h", "value.h", "kernels.cuh", "device_common.cuh", os.path.join("..", "..", "include", "nmr.h")]
 
 NVCC_FLAGS = [

@@ -1790,6 +1790,17 @@ NMR_API int nmr_debug_parse_gltf(const char* path, int64_t out_counts[5], char* 
     }
 }
 
+NMR_API int nmr_mikk_tangents(const float* positions, const float* normals, const float* texcoords, int64_t n_vertices,
+                              const uint32_t* indices, int64_t n_indices, float* out_tangents) {
+    if (!positions || !normals || !texcoords || !indices || !out_tangents || n_vertices <= 0 || n_indices < 0) return NMR_ERR_INVALID;
+    for (int64_t i = 0; i < n_indices; ++i) if ((int64_t)indices[i] >= n_vertices) return NMR_ERR_INVALID;
+    try {
+        for (int64_t v = 0; v < n_vertices; ++v) { float* o = out_tangents + v * 4; o[0] = 1.f; o[1] = 0.f; o[2] = 0.f; o[3] = -1.f; }
+        mikk_tangents(positions, normals, texcoords, (size_t)n_vertices, indices, (size_t)n_indices, out_tangents);
+        return NMR_OK;
+    } catch (const std::exception&) { return NMR_ERR_INVALID; }
+}
+
 // debug knob: bit 0 CUDA-core MLP, bit 1 swap UMMA descriptor offsets
 NMR_API int nmr_debug_set_flags(nmr_ctx* ctx, uint32_t flags) {
     return guarded(ctx, [&]() -> int { ctx->debug_flags = flags; return NMR_OK; });

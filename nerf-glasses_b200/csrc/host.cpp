@@ -413,7 +413,9 @@ HostMesh load_gltf(const std::string& path) {
     // depth-first over the scene like GltfScene::getMeshPrimitives; child transforms are ignored as in the reference
     std::vector<int64_t> stack;
     for (size_t i = scene_nodes.size(); i-- > 0;) stack.push_back(scene_nodes.at(i).as_int());
-    bool missing_normals = false, missing_tangents = false;
+    bool missing_normals = false;
+    struct PrimRange { uint32_t vbase; size_t nv, ibegin, iend; };
+    std::vector<PrimRange> untangented;     // primitives without TANGENT: generated below, one primitive at a time like the reference
     // a node is visited once: a child list that leads back to an ancestor (or a node shared by two parents) is not a tree
     std::vector<uint8_t> visited(doc.contains("nodes") ? doc.at("nodes").size() : 0, 0);
     while (!stack.empty()) {
@@ -437,9 +439,10 @@ HostMesh load_gltf(const std::string& path) {
             if (attrs.contains("TEXCOORD_0")) { if (read_accessor_f32(attrs.at("TEXCOORD_0").as_int(), 2, m.texcoords) != nv) throw std::runtime_error("gltf: TEXCOORD_0 count differs from POSITION count"); }
             else m.texcoords.resize(m.texcoords.size() + nv * 2, 0.f);
             if (attrs.contains("TANGENT")) { if (read_accessor_f32(attrs.at("TANGENT").as_int(), 4, m.tangents) != nv) throw std::runtime_error("gltf: TANGENT count differs from POSITION count"); }
-            else { m.tangents.resize(m.tangents.size() + nv * 4, 0.f); missing_tangents = true; }
+            else { m.tangents.resize(m.tangents.size() + nv * 4, 0.f); untangented.push_back({base, nv, m.indices.size(), 0}); }
             if (prim.contains("indices")) read_indices(prim.at("indices").as_int(), base, m.indices);
             else for (uint32_t i = 0; i < (uint32_t)nv; ++i) m.indices.push_back(base + i);
+            if (!attrs.contains("TANGENT")) untangented.back().iend = m.indices.size() / 3 * 3;
             {   // lens material?  (flags cover every triangle appended so far)
                 bool lens = false; float ior = 1.5f, transmission = 1.f, tint[3] = {1.f, 1.f, 1.f};
                 if (prim.contains("material") && doc.contains("materials")) {
@@ -509,43 +512,16 @@ HostMesh load_gltf(const std::string& path) {
             if (n[0] == 0.f && n[1] == 0.f && n[2] == 0.f) { n[0] = acc[v * 3]; n[1] = acc[v * 3 + 1]; n[2] = acc[v * 3 + 2]; }
         }
     }
-    if (missing_tangents) {
-        // per-triangle tangent / bitangent from the UV derivatives, accumulated per vertex; then orthogonalised against the normal
-        const size_t nv = nverts;
-        std::vector<float> tacc(nv * 3, 0.f), bacc(nv * 3, 0.f);
-        for (size_t t = 0; t + 2 < m.indices.size(); t += 3) {
-            const uint32_t i0 = m.indices[t], i1 = m.indices[t + 1], i2 = m.indices[t + 2];
-            const float* p0 = &m.positions[i0 * 3]; const float* p1 = &m.positions[i1 * 3]; const float* p2 = &m.positions[i2 * 3];
-            const float* u0 = &m.texcoords[i0 * 2]; const float* u1 = &m.texcoords[i1 * 2]; const float* u2 = &m.texcoords[i2 * 2];
-            const float e1[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]}, e2[3] = {p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2]};
-            const float du1 = u1[0] - u0[0], dv1 = u1[1] - u0[1], du2 = u2[0] - u0[0], dv2 = u2[1] - u0[1];
-            const float det = du1 * dv2 - du2 * dv1;
-            if (!(std::fabs(det) > 1e-20f)) continue;
-            const float r = 1.0f / det;
-            for (int k = 0; k < 3; ++k) {
-                const float tk = (e1[k] * dv2 - e2[k] * dv1) * r, bk = (e2[k] * du1 - e1[k] * du2) * r;
-                for (uint32_t v : {i0, i1, i2}) { tacc[v * 3 + k] += tk; bacc[v * 3 + k] += bk; }
-            }
-        }
-        for (size_t v = 0; v < nv; ++v) {
-            float* out = &m.tangents[v * 4];
-            if (out[0] != 0.f || out[1] != 0.f || out[2] != 0.f || out[3] != 0.f) continue;      // this primitive had a TANGENT attribute
-            const float* n = &m.normals[v * 3];
-            const float nl = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
-            const float nn[3] = {nl > 0 ? n[0] / nl : 0.f, nl > 0 ? n[1] / nl : 0.f, nl > 0 ? n[2] / nl : 1.f};
-            const float d = nn[0] * tacc[v * 3] + nn[1] * tacc[v * 3 + 1] + nn[2] * tacc[v * 3 + 2];
-            float tv[3] = {tacc[v * 3] - nn[0] * d, tacc[v * 3 + 1] - nn[1] * d, tacc[v * 3 + 2] - nn[2] * d};
-            float tl = std::sqrt(tv[0] * tv[0] + tv[1] * tv[1] + tv[2] * tv[2]);
-            if (!(tl > 1e-20f)) {      // no usable UV derivative: any unit vector perpendicular to the normal
-                const float ax[3] = {std::fabs(nn[0]) < 0.9f ? 1.f : 0.f, std::fabs(nn[0]) < 0.9f ? 0.f : 1.f, 0.f};
-                const float dd = nn[0] * ax[0] + nn[1] * ax[1] + nn[2] * ax[2];
-                tv[0] = ax[0] - nn[0] * dd; tv[1] = ax[1] - nn[1] * dd; tv[2] = ax[2] - nn[2] * dd;
-                tl = std::sqrt(tv[0] * tv[0] + tv[1] * tv[1] + tv[2] * tv[2]);
-            }
-            out[0] = tv[0] / tl; out[1] = tv[1] / tl; out[2] = tv[2] / tl;
-            const float c[3] = {nn[1] * out[2] - nn[2] * out[1], nn[2] * out[0] - nn[0] * out[2], nn[0] * out[1] - nn[1] * out[0]};
-            out[3] = (c[0] * bacc[v * 3] + c[1] * bacc[v * 3 + 1] + c[2] * bacc[v * 3 + 2]) < 0.f ? -1.f : 1.f;
-        }
+    for (const PrimRange& pr : untangented) {
+        // Mikkelsen's tangent space per primitive (S/gltf_scene.cpp:150-155); vertices outside every triangle get the method's
+        // default frame (1, 0, 0, -1) instead of the zeros the reference leaves there
+        if (pr.iend <= pr.ibegin) continue;
+        std::vector<uint32_t> local(m.indices.begin() + (ptrdiff_t)pr.ibegin, m.indices.begin() + (ptrdiff_t)pr.iend);
+        for (uint32_t& i : local) { i -= pr.vbase; if (i >= pr.nv) throw std::runtime_error("gltf: index outside its primitive's vertices"); }
+        float* tg = &m.tangents[(size_t)pr.vbase * 4];
+        for (size_t v = 0; v < pr.nv; ++v) { tg[v * 4] = 1.f; tg[v * 4 + 1] = 0.f; tg[v * 4 + 2] = 0.f; tg[v * 4 + 3] = -1.f; }
+        mikk_tangents(&m.positions[(size_t)pr.vbase * 3], &m.normals[(size_t)pr.vbase * 3], &m.texcoords[(size_t)pr.vbase * 2], pr.nv,
+                      local.data(), local.size(), tg);
     }
     // node 0 TRS (GltfLoader::traverse, S/gltf_scene.cpp:63-118); matrix-form nodes are not decomposed (load_mesh overwrites TRS anyway)
     const Value& n0 = doc.at("nodes").at((size_t)scene_nodes.at(0).as_int());

@@ -84,6 +84,11 @@ struct HostMesh {
 // glTF 2.0 (.gltf + external/embedded buffers, or .glb): all primitives of all nodes of the default scene are
 // concatenated like GltfScene::getMeshPrimitives (S/gltf_scene.h:195-224); material of the first primitive.
 HostMesh load_gltf(const std::string& path);
+// Tangents (xyz + handedness, 4 floats per vertex) of an indexed triangle list without a TANGENT attribute: Mikkelsen's method as the
+// reference runs it per mesh primitive (S/gltf_scene.cpp:150-155, S/gltf_mikktspace_handler.cpp:14-66).  mikk.cpp.  Vertices no
+// triangle uses keep what `tangents` held.
+void mikk_tangents(const float* positions, const float* normals, const float* texcoords, size_t n_vert,
+                   const uint32_t* indices, size_t n_idx, float* tangents);
 // 8-bit PNG (grey / grey+alpha / RGB / RGBA / palette, non-interlaced) -> RGBA8.  Throws on anything else.
 void decode_png(const uint8_t* data, size_t size, int& w, int& h, std::vector<uint8_t>& rgba);
 

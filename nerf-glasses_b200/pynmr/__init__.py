@@ -82,6 +82,7 @@ def lib():
         "nmr_render_format": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
         "nmr_render_views_format": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
         "nmr_debug_parse_gltf": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64), C.c_char_p, C.c_size_t, vp, C.c_size_t]),
+        "nmr_mikk_tangents": (C.c_int, [vp, vp, vp, C.c_int64, vp, C.c_int64, vp]),
         "nmr_set_shard": (C.c_int, [vp, C.c_int, C.c_int, C.c_int]),
         "nmr_set_surface_insertion": (C.c_int, [vp, C.c_int]),
         "nmr_set_overlap": (C.c_int, [vp, C.c_int]),
@@ -136,7 +137,7 @@ EXPORTED_SYMBOLS = [
     "nmr_get_device_image", "nmr_copy_device_image", "nmr_flush_l2", "nmr_get_stats", "nmr_synchronize", "nmr_host_alloc", "nmr_host_free", "nmr_render_update", "nmr_trajectory_pose", "nmr_get_density_bitfield",
     "nmr_set_density_bitfield", "nmr_debug_encode", "nmr_debug_network", "nmr_debug_trace", "nmr_debug_mesh",
     "nmr_debug_last_frame", "nmr_debug_set_flags", "nmr_render_format", "nmr_render_views_format", "nmr_debug_parse_gltf", "nmr_measure_l2", "nmr_set_overlap", "nmr_set_model_transform", "nmr_get_model_transform",
-    "nmr_dump_density_grid", "nmr_load_density_grid", "nmr_read_combined", "nmr_set_lens_model",
+    "nmr_dump_density_grid", "nmr_load_density_grid", "nmr_read_combined", "nmr_set_lens_model", "nmr_mikk_tangents",
 ]
 
 
@@ -168,6 +169,22 @@ def parse_gltf(path: str, tangents: bool = False) -> dict:
         t = np.zeros((counts[0], 4), dtype=np.float32)
         lib().nmr_debug_parse_gltf(os.fsencode(path), counts, err, len(err), _ptr(t), t.size)
         out["tangents"] = t
+    return out
+
+
+def mikk_tangents(positions, normals, texcoords, indices) -> np.ndarray:
+    """Host-only: per-vertex tangents (xyz + handedness) of an indexed triangle list by the reference's tangent generator for
+    primitives without a TANGENT attribute (S/gltf_scene.cpp:150-155 -> mikktspace.c); what load_mesh computes for such a file."""
+    p = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+    n = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
+    t = np.ascontiguousarray(texcoords, dtype=np.float32).reshape(-1, 2)
+    i = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1)
+    if not (len(p) == len(n) == len(t)):
+        raise ValueError("positions, normals and texcoords need one entry per vertex")
+    out = np.zeros((len(p), 4), dtype=np.float32)
+    rc = lib().nmr_mikk_tangents(_ptr(p), _ptr(n), _ptr(t), len(p), _ptr(i), i.size, _ptr(out))
+    if rc != NMR_OK:
+        raise RuntimeError(f"libnmr error {rc}")
     return out
 
 

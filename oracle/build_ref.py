@@ -22,7 +22,26 @@ def available() -> bool:
     return os.path.exists(OUT)
 
 
+MIKK_OUT = os.path.join(HERE, "_ref", "libmikk_ref.so")
+MIKK_SRC = os.path.join(HERE, "ref_mikk_harness.c")
+
+
+def build_mikk(force: bool = False) -> str | None:
+    """oracle/_ref/libmikk_ref.so: the reference's vendored mikktspace.c (compiled where it lies) + oracle/ref_mikk_harness.c (ours).
+    Plain gcc -O2 for x86-64 (no FMA contraction possible without -mfma), like the reference's CMake default for this C file."""
+    mk = R + "/dependencies/MikkTSpace"
+    if not os.path.isdir(mk) or shutil.which("gcc") is None:
+        return MIKK_OUT if os.path.exists(MIKK_OUT) else None
+    if not force and os.path.exists(MIKK_OUT) and os.path.getmtime(MIKK_OUT) >= os.path.getmtime(MIKK_SRC):
+        return MIKK_OUT
+    os.makedirs(os.path.dirname(MIKK_OUT), exist_ok=True)
+    subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-fvisibility=hidden", "-w", "-I", mk, "-o", MIKK_OUT,
+                           MIKK_SRC, mk + "/mikktspace.c", "-lm"])
+    return MIKK_OUT
+
+
 def build(force: bool = False) -> str | None:
+    build_mikk(force)
     if not os.path.isdir(R) or shutil.which("nvcc") is None:
         return OUT if os.path.exists(OUT) else None
     if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= os.path.getmtime(SRC):
@@ -41,4 +60,4 @@ def build(force: bool = False) -> str | None:
 
 
 if __name__ == "__main__":
-    print(build(force=True))
+    print(build(force=True), MIKK_OUT)

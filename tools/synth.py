@@ -744,3 +744,61 @@ if __name__ == "__main__":
     a = ap.parse_args()
     r = write_snapshot(a.out, a.seed, log2_hashmap_size=a.log2_hashmap_size, regime=a.regime)
     print(a.out, r["params"].size, "params")
+
+
+# ---- meshes for the tangent generator (nmr_mikk_tangents vs the reference's mikktspace.c) ---------------------------------------
+
+def tangent_test_grid(nu: int, nv: int, rng, mirror: bool = False, jitter: float = 0.0, explode: bool = False):
+    """A band of a sphere as an indexed grid (shared vertices, seam columns equal in position but not in uv).  mirror folds the u
+    coordinate (both UV orientations in one mesh), jitter roughens it, explode gives every face its own three vertices (the welding
+    step has to join them again).  Faces are shuffled.  -> positions, normals, texcoords, indices (n, 3)."""
+    u, v = np.meshgrid(np.linspace(0, 1, nu), np.linspace(0, 1, nv), indexing="ij")
+    th = u * 2 * np.pi; ph = (v * 0.8 + 0.1) * np.pi
+    p = np.stack([np.sin(ph) * np.cos(th), np.cos(ph), np.sin(ph) * np.sin(th)], -1).reshape(-1, 3)
+    p = p * (1 + jitter * rng.standard_normal(p.shape))
+    n = p / np.linalg.norm(p, axis=1, keepdims=True)
+    uv = np.stack([u, v], -1).reshape(-1, 2).copy()
+    if mirror:
+        uv[:, 0] = np.abs(uv[:, 0] - 0.5) * 2
+    a, b = np.meshgrid(np.arange(nu - 1), np.arange(nv - 1), indexing="ij")
+    i0 = (a * nv + b).reshape(-1); i1 = ((a + 1) * nv + b).reshape(-1); i2 = i1 + 1; i3 = i0 + 1
+    f = np.concatenate([np.stack([i0, i1, i2], 1), np.stack([i0, i2, i3], 1)]).astype(np.uint32)
+    f = f[rng.permutation(len(f))]
+    p, n, uv = p.astype(np.float32), n.astype(np.float32), uv.astype(np.float32)
+    if explode:
+        p, n, uv = p[f.reshape(-1)], n[f.reshape(-1)], uv[f.reshape(-1)]
+        f = np.arange(len(p), dtype=np.uint32).reshape(-1, 3)
+    return p, n, uv, f
+
+
+def tangent_test_soup(rng, nv: int, nf: int, dup: float = 0.3, degen: float = 0.05, flat: float = 0.05):
+    """Random triangles over few vertices: edges shared by many triangles, whole-vertex duplicates (welded), position-only duplicates
+    (not welded), triangles with two equal corners (set aside) and triangles without UV area (group with anything)."""
+    p = rng.integers(-3, 4, (nv, 3)).astype(np.float32) * 0.25 + (rng.standard_normal((nv, 3)) * 0.01).astype(np.float32)
+    n = rng.standard_normal((nv, 3)).astype(np.float32); n /= np.linalg.norm(n, axis=1, keepdims=True)
+    uv = rng.random((nv, 2)).astype(np.float32)
+    k = int(nv * dup); src = rng.integers(0, nv, k); dst = rng.integers(0, nv, k)
+    p[dst] = p[src]; n[dst] = n[src]; uv[dst] = uv[src]
+    k = int(nv * 0.1); src = rng.integers(0, nv, k); dst = rng.integers(0, nv, k)
+    p[dst] = p[src]
+    f = rng.integers(0, nv, (nf, 3)).astype(np.uint32)
+    d = rng.random(nf) < degen; f[d, 1] = f[d, 0]
+    for t in np.nonzero(rng.random(nf) < flat)[0]:
+        uv[f[t, 2]] = uv[f[t, 1]]
+    return p, n, uv, f
+
+
+def tangent_test_cases(seed: int = 20260102, n_soup: int = 24, n_grid: int = 8):
+    """The fixed list of meshes behind tests/golden/ref_mikk.npz."""
+    rng = np.random.default_rng(seed)
+    cases = []
+    for s in range(n_soup):
+        cases.append(tangent_test_soup(rng, int(rng.integers(4, 60)), int(rng.integers(1, 400)), dup=float(rng.random() * 0.5),
+                                       degen=float(rng.random() * 0.2), flat=float(rng.random() * 0.2)))
+    for s in range(n_grid):
+        cases.append(tangent_test_grid(int(rng.integers(3, 28)), int(rng.integers(3, 28)), rng, mirror=bool(s & 1), jitter=0.02 * (s % 3), explode=(s % 4 == 0)))
+    g = np.load(GLASSES_NPZ)
+    keys = set(g.files)
+    if {"positions", "normals", "texcoords", "indices"} <= keys:
+        cases.append((g["positions"].astype(np.float32), g["normals"].astype(np.float32), g["texcoords"].astype(np.float32), g["indices"].astype(np.uint32).reshape(-1, 3)))
+    return cases
