@@ -183,19 +183,26 @@ void sort_edges(Edge* e, int left, int right, int ch, uint32_t seed) {
     if (a < right) sort_edges(e, a, right, ch, seed);
 }
 
-// step 5: depth-first growth of one group around its vertex
-void grow(std::vector<Tri>& tris, std::vector<Group>& groups, int g, int t) {
-    Tri& T = tris[t];
-    Group& G = groups[g];
-    const int k = T.v[0] == G.vertex ? 0 : T.v[1] == G.vertex ? 1 : 2;
-    if (T.group[k] != -1) return;                                   // already in this group, or in another one
-    if (T.any && T.group[0] == -1 && T.group[1] == -1 && T.group[2] == -1) T.preserving = G.preserving;
-    if (T.preserving != G.preserving) return;
-    G.tris.push_back(t);
-    T.group[k] = g;
-    const int out = T.nb[k], in = T.nb[k > 0 ? k - 1 : 2];
-    if (out >= 0) grow(tris, groups, g, out);
-    if (in >= 0) grow(tris, groups, g, in);
+// step 5: depth-first growth of one group around its vertex, from the triangles `first` and `second` (either may be -1).  The order
+// is the published recursion's - a triangle joins, then everything behind the edge leaving the vertex, then behind the edge
+// entering it - walked with an explicit stack: a fan of a million triangles around one vertex must not overflow the call stack.
+void grow(std::vector<Tri>& tris, Group& G, int g, int first, int second, std::vector<int>& stack) {
+    stack.clear();
+    if (second >= 0) stack.push_back(second);
+    if (first >= 0) stack.push_back(first);
+    while (!stack.empty()) {
+        const int t = stack.back(); stack.pop_back();
+        Tri& T = tris[t];
+        const int k = T.v[0] == G.vertex ? 0 : T.v[1] == G.vertex ? 1 : 2;
+        if (T.group[k] != -1) continue;                             // already in this group, or in another one
+        if (T.any && T.group[0] == -1 && T.group[1] == -1 && T.group[2] == -1) T.preserving = G.preserving;
+        if (T.preserving != G.preserving) continue;
+        G.tris.push_back(t);
+        T.group[k] = g;
+        const int out = T.nb[k], in = T.nb[k > 0 ? k - 1 : 2];
+        if (in >= 0) stack.push_back(in);
+        if (out >= 0) stack.push_back(out);
+    }
 }
 
 }  // namespace
@@ -272,16 +279,16 @@ void mikk_tangents(const float* positions, const float* normals, const float* te
 
     // step 5
     std::vector<Group> groups;
-    groups.reserve((size_t)n_tri * 3);                              // grow() keeps references into the vector
-    for (int t = 0; t < n_tri; ++t) for (int k = 0; k < 3; ++k) {
-        if (tris[t].any || tris[t].group[k] != -1) continue;
-        const int g = (int)groups.size();
-        groups.push_back({tris[t].v[k], tris[t].preserving, {}});
-        groups[g].tris.push_back(t);
-        tris[t].group[k] = g;
-        const int out = tris[t].nb[k], in = tris[t].nb[k > 0 ? k - 1 : 2];
-        if (out >= 0) grow(tris, groups, g, out);
-        if (in >= 0) grow(tris, groups, g, in);
+    {
+        std::vector<int> stack;
+        for (int t = 0; t < n_tri; ++t) for (int k = 0; k < 3; ++k) {
+            if (tris[t].any || tris[t].group[k] != -1) continue;
+            const int g = (int)groups.size();
+            groups.push_back({tris[t].v[k], tris[t].preserving, {}});
+            groups[g].tris.push_back(t);
+            tris[t].group[k] = g;
+            grow(tris, groups[g], g, tris[t].nb[k], tris[t].nb[k > 0 ? k - 1 : 2], stack);
+        }
     }
 
     // step 6

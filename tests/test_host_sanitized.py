@@ -1,4 +1,4 @@
-"""The host-side file readers (msgpack snapshot, glTF, PNG: csrc/host.cpp, csrc/value.cpp) under AddressSanitizer + UBSan, fed
+"""The host-side file readers (msgpack snapshot, glTF with its tangent generator, PNG: csrc/host.cpp, csrc/value.cpp, csrc/mikk.cpp) under AddressSanitizer + UBSan, fed
 with valid files and with hundreds of mutated ones (byte flips, truncations, numbers replaced by extremes inside the JSON).
 A reader may reject a file; it must not touch memory it does not own, overflow, or hang.  CPU only (g++ -fsanitize)."""
 import json
@@ -20,7 +20,7 @@ def harness(tmp_path_factory):
         pytest.skip("no g++")
     out = str(tmp_path_factory.mktemp("asan") / "host_fuzz")
     cmd = ["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer",
-           "-I", CSRC, os.path.join(ROOT, "tests", "native", "host_fuzz.cpp"), os.path.join(CSRC, "host.cpp"), os.path.join(CSRC, "value.cpp"), "-lz", "-o", out]
+           "-I", CSRC, os.path.join(ROOT, "tests", "native", "host_fuzz.cpp"), os.path.join(CSRC, "host.cpp"), os.path.join(CSRC, "value.cpp"), os.path.join(CSRC, "mikk.cpp"), "-lz", "-o", out]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         if "asan" in r.stderr.lower() or "sanitize" in r.stderr.lower():
