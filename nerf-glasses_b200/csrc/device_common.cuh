@@ -246,10 +246,37 @@ __device__ __forceinline__ float distance_to_next_voxel(V3 pos, V3 dir, V3 idir,
     // float by 2^k is never inexact above the subnormal range, and t / r is then flushed to >= 0 by the max anyway)
     return fmaxf(t * __uint_as_float((254u << 23) - __float_as_uint(r)), 0.0f);
 }
+// `do { t += dt0; } while (t < t_target);` of the uniform-step walk, landed on directly.  While t and t_target share a binade the
+// k-th addition yields the bit pattern bits(t) + k * inc (see lattice_advance below), and positive floats order like their bit
+// patterns, so the loop ends at the smallest k >= 1 with bits(t) + k * inc >= bits(t_target): one rounded-down float quotient,
+// corrected upwards.  Anything else (another binade, a landing beyond the binade's top, an increment of zero, a NaN) takes the
+// additions themselves.  Bit-identical to the loop (tests/test_host_cpu.py restates it; the GPU traversal tests pass with it) but SLOWER on the B200 - the
+// extra live values cost the march kernel 4 % and the set-up kernel as much (profiles/r2_ab_direct_landing.txt) - so it is only
+// compiled with -DNMR_DIRECT_LANDING.
+__device__ __forceinline__ float uniform_steps_past(float t, float t_target) {
+    const float dt0 = min_cone_stepsize();
+#ifdef NMR_DIRECT_LANDING
+    const uint32_t b = __float_as_uint(t), e = b & 0xFF800000u, bt = __float_as_uint(t_target);
+    const uint32_t inc = __float_as_uint(__uint_as_float(e) + dt0) - e;
+    if ((bt & 0xFF800000u) == e && inc - 1u < 0x00400000u) {            // same binade, 0 < inc <= 2^22
+        uint32_t k = 1u;
+        if (bt > b) {
+            const uint32_t diff = bt - b;                                // < 2^23
+            k = (uint32_t)(__uint2float_rz(diff) * __frcp_rz(__uint2float_ru(inc)));      // <= diff / inc
+            if (k * inc < diff) ++k;
+            if (k * inc < diff) ++k;
+        }
+        const uint32_t r = b + k * inc;
+        if (k * inc >= bt - b && (k == 1u || (k - 1u) * inc < bt - b) && r <= (e | 0x007FFFFFu)) return __uint_as_float(r);
+    }
+#endif
+    do { t += dt0; } while (t < t_target);
+    return t;
+}
 // uniform_dt: the cone angle is zero, so calc_dt(t, 0) = clamp(t * 0) is the constant minimum step for every finite t
 __device__ __forceinline__ float advance_to_next_voxel(float t, float cone_angle, bool uniform_dt, V3 pos, V3 dir, V3 idir, uint32_t res) {
     const float t_target = t + distance_to_next_voxel(pos, dir, idir, res);
-    if (uniform_dt) { const float dt0 = min_cone_stepsize(); do { t += dt0; } while (t < t_target); }
+    if (uniform_dt) t = uniform_steps_past(t, t_target);
     else { do { t += calc_dt(t, cone_angle); } while (t < t_target); }
     return t;
 }
@@ -404,7 +431,10 @@ __device__ __forceinline__ bool advance_pos(const FrameParams& P, const uint8_t*
         // Zero cone angle: where the walk goes next does not depend on what the occupancy tests return, only whether it goes
         // on.  So the next kWalkBatch steps are laid out first (arithmetic only) with their occupancy loads in flight together,
         // and are then judged in order - the walk's critical path holds one memory latency per batch instead of one per step.
-        constexpr int kWalkBatch = 4;
+#ifndef NMR_WALK_BATCH
+#define NMR_WALK_BATCH 4
+#endif
+        constexpr int kWalkBatch = NMR_WALK_BATCH;      // 4 measured best (profiles/r2_experiments.md)
         const float dt0 = min_cone_stepsize();
         bool hit = false;
         while (!hit) {

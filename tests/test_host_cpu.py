@@ -133,6 +133,54 @@ def _lattice_advance_np(t, K):
     return t
 
 
+def _uniform_steps_past_np(t, t_target):
+    """numpy restatement of device_common.cuh: uniform_steps_past (same integer arithmetic; the rounded-down quotient is taken a
+    little low, which the two corrections absorb exactly as on the device).  Returns (landing, took_the_direct_path)."""
+    f32 = np.float32
+    dt0 = f32(np.sqrt(f32(3.0)) / f32(1024.0))
+    b = int(np.array(t, f32).view(np.uint32)); e = b & 0xFF800000; bt = int(np.array(t_target, f32).view(np.uint32))
+    inc = (int(f32(np.array(e, np.uint32).view(f32) + dt0).view(np.uint32)) - e) & 0xFFFFFFFF
+    if (bt & 0xFF800000) == e and 0 < inc <= 0x400000:
+        k = 1
+        if bt > b:
+            diff = bt - b
+            k = int(np.float64(diff) * np.float64(np.nextafter(f32(1.0) / f32(inc), f32(0))))
+            for _ in range(2):
+                if k * inc < diff:
+                    k += 1
+        d = (bt - b) & 0xFFFFFFFF
+        r = b + k * inc
+        if k * inc >= d and (k == 1 or (k - 1) * inc < d) and r <= (e | 0x7FFFFF):
+            return np.array(r, np.uint32).view(f32)[()], True
+    while True:
+        t = f32(t + dt0)
+        if not (t < t_target):
+            return t, False
+
+
+def test_direct_landing_equals_the_step_loop():
+    """advance_to_next_voxel with a zero cone angle lands on `do { t += dt0; } while (t < t_target);` without running it
+    (device_common.cuh: uniform_steps_past).  Against the loop itself in fp32, bit for bit: random t in every binade a walk visits,
+    voxel distances of every cascade, t exactly on and just above powers of two, and zero distances."""
+    f32 = np.float32
+    dt0 = f32(np.sqrt(f32(3.0)) / f32(1024.0))
+    rng = np.random.default_rng(5)
+    direct = 0
+    for i in range(60000):
+        t = f32(rng.uniform(0.001, 8.0)) if i % 3 else f32(2.0 ** int(rng.integers(-3, 3))) * f32(1 + rng.random() * 1e-3 * (i % 2))
+        dist = f32(rng.random() * 0.0136 * 2 ** int(rng.integers(0, 8))) if i % 7 else f32(0)
+        tt = f32(t + dist)
+        want = t
+        while True:
+            want = f32(want + dt0)
+            if not (want < tt):
+                break
+        got, fast = _uniform_steps_past_np(t, tt)
+        direct += fast
+        assert np.array(got, f32).view(np.uint32) == np.array(want, f32).view(np.uint32), (t, tt, got, want)
+    assert direct > 40000          # the direct path is the common one
+
+
 def test_uniform_step_lattice_is_exact():
     """The first-hit walk's empty-space jumps (device_common.cuh: lattice_advance) rest on `t += dt0` advancing the bit pattern
     of t by a constant inside a binade: no rounding tie for dt0 = sqrt(3)/1024 in any binade a walk can reach, and the
