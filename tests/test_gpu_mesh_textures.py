@@ -67,3 +67,33 @@ def test_textured_mesh_stage_matches_oracle(small_snapshot, glasses_gltf, tmp_pa
     want_img, _ = O.accumulate_tonemap(frame, None, 0, to_srgb=True)
     img = np.asarray(nerf.render(W, HH, 1, linear=False))
     assert float(np.abs(img - want_img).max()) <= PIX_TOL and H.psnr(img, want_img) >= 45.0
+
+
+def test_normal_mapped_mesh_without_tangent_attribute(small_snapshot, tmp_path):
+    """A glTF whose primitive has a normal map but no TANGENT attribute: load_mesh generates the tangents the way the reference does
+    (S/gltf_scene.cpp:150-155 -> mikktspace.c; the generator itself is pinned bit for bit on the reference's file in
+    tests/test_host_cpu.py), and the shader's TBN matrix uses them - the mesh stage equals the oracle fed with those tangents, and
+    differs from the same file shaded with the fixture's own (unweighted) tangents."""
+    import pynmr
+    import synth
+    path, _ = small_snapshot
+    without = synth.write_textured_glasses_gltf(str(tmp_path / "no_tangent"), with_tangents=False)
+    with_t = synth.write_textured_glasses_gltf(str(tmp_path / "tangent"), with_tangents=True)
+    t, s, rq = synth.GLASSES_T, (0.17, 0.2, 0.15), (0.6830127, 0.6830127, 0.1830127, -0.1830127)
+    r = pynmr.NerfMeshRenderer(W, HH)
+    r.load_nerf(path)
+    assert r.load_mesh(without, t=t, s=s, r=rq) is not None
+    r.orbit(0.35, -0.2, 4.0)
+    c12 = np.ascontiguousarray(r.view_projection_mat.T.reshape(-1))
+    rgba2, d2, tri2, _, _ = H.debug_mesh(r, W, HH)
+    mesh, g = oracle_mesh(with_t, t, s, rq)                              # same geometry, material and textures
+    gen = pynmr.mikk_tangents(g["positions"], g["normals"], g["texcoords"], g["indices"])
+    assert np.array_equal(pynmr.parse_gltf(without, tangents=True)["tangents"].view(np.uint32), gen.view(np.uint32))
+    file_tangents_picture = mesh.render(c12, 2 * W, 2 * HH)[0]
+    mesh.set_tangents(g["normals"], gen, s, rq)
+    want_rgba2, want_d2, want_tri = mesh.render(c12, 2 * W, 2 * HH)
+    hit = want_tri >= 0
+    assert hit.mean() > 0.002 and np.array_equal(tri2, want_tri)
+    assert np.array_equal(d2[hit].view(np.uint32), want_d2[hit].view(np.uint32))
+    assert float(np.abs(rgba2 - want_rgba2).max()) <= 2e-4
+    assert float(np.abs(file_tangents_picture - want_rgba2)[hit].max()) > 1e-3      # the tangents reach the picture
