@@ -31,6 +31,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <stdexcept>
 #include <algorithm>
 #include <unordered_map>
 #include <vector>
@@ -212,6 +213,7 @@ void mikk_tangents(const float* positions, const float* normals, const float* te
     const Mesh m{positions, normals, texcoords, indices};
     const size_t n_face = n_idx / 3;
     if (n_face == 0) return;
+    if (n_face >= (size_t)1 << 29) throw std::length_error("mikk_tangents: more than 2^29 triangles");      // a vertex name is (face << 2) | corner in an int
     (void)n_vert;
     const std::vector<int> name = weld(m, (int)n_face);
 
