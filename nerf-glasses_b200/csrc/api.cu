@@ -1068,6 +1068,30 @@ NMR_API int nmr_get_nerf_info(nmr_ctx* ctx, int id, nmr_nerf_info* o) {
     });
 }
 
+NMR_API int nmr_get_nerf_dataset(nmr_ctx* ctx, int id, nmr_nerf_dataset* o) {
+    return guarded(ctx, [&]() -> int {
+        if (!o) return fail(ctx, NMR_ERR_INVALID, "out is null");
+        Nerf* n; try { n = get_nerf(ctx, id); } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); }
+        const HostModel& h = n->host;
+        *o = nmr_nerf_dataset{};
+        o->scale = h.dataset_scale; o->from_mitsuba = h.from_mitsuba; o->bounding_radius = h.bounding_radius;
+        std::memcpy(o->offset, h.dataset_offset, 12); std::memcpy(o->up, h.dataset_up, 12);
+        std::memcpy(o->raw_aabb_min, h.aabb_min, 12); std::memcpy(o->raw_aabb_max, h.aabb_max, 12);
+        return NMR_OK;
+    });
+}
+
+NMR_API int nmr_set_render_aabb_to_local(nmr_ctx* ctx, int id, const float m[9]) {
+    return guarded(ctx, [&]() -> int {
+        if (!m) return fail(ctx, NMR_ERR_INVALID, "matrix is null");
+        for (int k = 0; k < 9; ++k) if (!std::isfinite(m[k])) return fail(ctx, NMR_ERR_INVALID, "render_aabb_to_local: values must be finite");
+        Nerf* n; try { n = get_nerf(ctx, id); } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); }
+        std::memcpy(n->host.render_aabb_to_local, m, 36);
+        ctx->surf.spp = 0;       // the picture changes: accumulation starts over, as after nmr_set_render_aabb
+        return NMR_OK;
+    });
+}
+
 NMR_API int nmr_orbit(nmr_ctx* ctx, float daz, float dpol, float dzoom) {
     return guarded(ctx, [&]() -> int {
         if (!std::isfinite(daz) || !std::isfinite(dpol) || !std::isfinite(dzoom)) return fail(ctx, NMR_ERR_INVALID, "orbit: values must be finite");

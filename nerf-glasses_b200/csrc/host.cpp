@@ -97,6 +97,7 @@ HostModel load_snapshot(const std::string& path) {
     if (snap.at("density_grid_size").as_int() != (int64_t)kGridSize) throw std::runtime_error("incompatible grid size");
 
     HostModel m;
+    if (snap.contains("bounding_radius")) m.bounding_radius = snap.at("bounding_radius").as_float();
     const Value& nerf = snap.at("nerf");
     bool have_dataset_box = false;
     float ds_min[3], ds_max[3];
@@ -107,6 +108,10 @@ HostModel load_snapshot(const std::string& path) {
         if (ds.contains("render_aabb")) { read_box(ds.at("render_aabb"), ds_min, ds_max); have_dataset_box = true; }
         if (ds.contains("render_aabb_to_local")) read_mat3(ds.at("render_aabb_to_local"), m.render_aabb_to_local);
         is_hdr = ds.value_bool("is_hdr", false);
+        if (ds.contains("scale")) m.dataset_scale = ds.at("scale").as_float();
+        if (ds.contains("offset")) read_vec3(ds.at("offset"), m.dataset_offset);
+        if (ds.contains("up")) read_vec3(ds.at("up"), m.dataset_up);
+        m.from_mitsuba = ds.value_bool("from_mitsuba", false) ? 1 : 0;
     } else if (nerf.contains("aabb_scale")) {
         m.aabb_scale = (int)nerf.at("aabb_scale").as_int();
     }

@@ -41,6 +41,10 @@ struct HostModel {
     int density_activation = 3;              // Exponential (S/ngp/testbed.cuh:469)
     int64_t training_step = 0;               // snapshot["training_step"] (Testbed.training_step)
     float loss = 0.f;                        // snapshot["loss"] (Testbed.loss)
+    // what the secondary Python properties read (S/ngp/testbed.cu:952, 1100, 1117; S/ngp/json_binding.h:188-197)
+    float bounding_radius = 1.f;             // snapshot["bounding_radius"] (Testbed.bounding_radius, translate_camera)
+    float dataset_scale = 1.f, dataset_offset[3] = {0, 0, 0}, dataset_up[3] = {0, 1, 0};   // NerfDataset::scale / offset / up
+    int from_mitsuba = 0;
 };
 
 // Throws std::runtime_error with a description on malformed / unsupported snapshots.

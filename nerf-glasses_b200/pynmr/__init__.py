@@ -46,6 +46,11 @@ class NerfInfo(C.Structure):
                 ("log2_hashmap_size", C.c_int), ("base_resolution", C.c_int), ("per_level_scale", C.c_float), ("n_params", C.c_uint64)]
 
 
+class NerfDataset(C.Structure):
+    _fields_ = [("scale", C.c_float), ("offset", C.c_float * 3), ("up", C.c_float * 3), ("from_mitsuba", C.c_int),
+                ("bounding_radius", C.c_float), ("raw_aabb_min", C.c_float * 3), ("raw_aabb_max", C.c_float * 3)]
+
+
 def lib():
     """Loads libnmr.so (raises RuntimeError with the build hint when it is missing)."""
     global _lib
@@ -82,6 +87,8 @@ def lib():
         "nmr_render_format": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
         "nmr_render_views_format": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
         "nmr_debug_parse_gltf": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64), C.c_char_p, C.c_size_t, vp, C.c_size_t]),
+        "nmr_get_nerf_dataset": (C.c_int, [vp, C.c_int, C.POINTER(NerfDataset)]),
+        "nmr_set_render_aabb_to_local": (C.c_int, [vp, C.c_int, fp]),
         "nmr_mikk_tangents": (C.c_int, [vp, vp, vp, C.c_int64, vp, C.c_int64, vp]),
         "nmr_set_shard": (C.c_int, [vp, C.c_int, C.c_int, C.c_int]),
         "nmr_set_surface_insertion": (C.c_int, [vp, C.c_int]),
@@ -137,7 +144,7 @@ EXPORTED_SYMBOLS = [
     "nmr_get_device_image", "nmr_copy_device_image", "nmr_flush_l2", "nmr_get_stats", "nmr_synchronize", "nmr_host_alloc", "nmr_host_free", "nmr_render_update", "nmr_trajectory_pose", "nmr_get_density_bitfield",
     "nmr_set_density_bitfield", "nmr_debug_encode", "nmr_debug_network", "nmr_debug_trace", "nmr_debug_mesh",
     "nmr_debug_last_frame", "nmr_debug_set_flags", "nmr_render_format", "nmr_render_views_format", "nmr_debug_parse_gltf", "nmr_measure_l2", "nmr_set_overlap", "nmr_set_model_transform", "nmr_get_model_transform",
-    "nmr_dump_density_grid", "nmr_load_density_grid", "nmr_read_combined", "nmr_set_lens_model", "nmr_mikk_tangents",
+    "nmr_dump_density_grid", "nmr_load_density_grid", "nmr_read_combined", "nmr_set_lens_model", "nmr_mikk_tangents", "nmr_get_nerf_dataset", "nmr_set_render_aabb_to_local",
 ]
 
 
@@ -411,12 +418,22 @@ class TonemapCurve(enum.IntEnum):
     Reinhard = 3
 
 
+class ColorSpace(enum.IntEnum):
+    """pynmr.ColorSpace (S/python_api.cu:222-226)."""
+    Linear = 0
+    SRGB = 1
+
+
 class Testbed:
     """ngp::Testbed as returned by NerfMeshRenderer.load_nerf (S/python_api.cu:299-496)."""
 
     def __init__(self, renderer: "NerfMeshRenderer", nerf_id: int):
         self._r, self._id = renderer, nerf_id
         self._min_t = 0.01
+        self._scale = 1.5                                          # Testbed::m_scale after the constructor's reset_camera() (S/ngp/testbed.cu:96, 1388)
+        self._up_dir = None                                        # the dataset's up vector until set (S/ngp/testbed.cu:1117)
+        self._screen_center = np.array([0.5, 0.5], np.float32)
+        self._sun_dir = (np.ones(3) / np.sqrt(3.0)).astype(np.float32)
 
     @property
     def nerf(self) -> "_NerfSettings":
@@ -485,6 +502,11 @@ class Testbed:
     def render_aabb_to_local(self) -> np.ndarray:
         return np.array(list(self._info().render_aabb_to_local), dtype=np.float32).reshape(3, 3)
 
+    @render_aabb_to_local.setter
+    def render_aabb_to_local(self, m):
+        a = np.ascontiguousarray(m, dtype=np.float32).reshape(3, 3)
+        self._r._ck(lib().nmr_set_render_aabb_to_local(self._r._h, self._id, a.ctypes.data_as(C.POINTER(C.c_float))))
+
     @property
     def n_params(self) -> int:
         return int(self._info().n_params)
@@ -540,12 +562,173 @@ class Testbed:
             cells = np.ascontiguousarray(path_or_cells, dtype=np.uint8).reshape(8, 128, 128, 128)
             self._r._ck(lib().nmr_load_density_grid(self._r._h, self._id, None, _ptr(cells)))
 
-    def set_crop_box(self, box: BoundingBox):
-        self._set_render_aabb(box.min, box.max)
+    # -- crop box as a 3x4 matrix (Testbed::crop_box / set_crop_box / crop_box_corners, S/ngp/testbed.cu:1421-1477): columns = the
+    #    box's half axes and its centre; nerf_space=True converts to / from the dataset's coordinates (S/ngp/nerf_loader.cuh:115-153)
+    def _dataset(self) -> NerfDataset:
+        d = NerfDataset()
+        self._r._ck(lib().nmr_get_nerf_dataset(self._r._h, self._id, C.byref(d)))
+        return d
+
+    def _ngp_matrix_to_nerf(self, m, scale_columns):
+        d = self._dataset(); r = np.array(m, dtype=np.float32).reshape(3, 4)
+        if d.from_mitsuba:
+            r[:, 0] *= -1; r[:, 2] *= -1
+        else:
+            r = r[[2, 0, 1], :]                                    # rows: x <- z, y <- x, z <- y
+        k = np.float32(1.0) / np.float32(d.scale) if scale_columns else np.float32(1.0)
+        r[:, 0] *= k; r[:, 1] *= -k; r[:, 2] *= -k
+        r[:, 3] = (r[:, 3] - np.array(list(d.offset), np.float32)) / np.float32(d.scale)
+        return r
+
+    def _nerf_matrix_to_ngp(self, m, scale_columns):
+        d = self._dataset(); r = np.array(m, dtype=np.float32).reshape(3, 4)
+        k = np.float32(d.scale) if scale_columns else np.float32(1.0)
+        r[:, 0] *= k; r[:, 1] *= -k; r[:, 2] *= -k
+        r[:, 3] = r[:, 3] * np.float32(d.scale) + np.array(list(d.offset), np.float32)
+        if d.from_mitsuba:
+            r[:, 0] *= -1; r[:, 2] *= -1
+        else:
+            r = r[[1, 2, 0], :]                                    # rows: x <- y, y <- z, z <- x
+        return r
+
+    def crop_box(self, nerf_space: bool = True) -> np.ndarray:
+        mn, mx = self._get_render_aabb()
+        r2l = self.render_aabb_to_local
+        radius = (mx - mn) * np.float32(0.5)
+        rv = np.zeros((3, 4), np.float32)
+        for k in range(3):
+            rv[:, k] = r2l[k, :] * radius[k]
+        rv[:, 3] = r2l.T @ ((mx + mn) * np.float32(0.5))
+        return self._ngp_matrix_to_nerf(rv, True) if nerf_space else rv
+
+    def set_crop_box(self, matrix, nerf_space: bool = True):
+        if isinstance(matrix, BoundingBox):                        # (earlier versions of this shim took the box itself)
+            self._set_render_aabb(matrix.min, matrix.max)
+            return
+        m = np.array(matrix, dtype=np.float32).reshape(3, 4)
+        if nerf_space:
+            m = self._nerf_matrix_to_ngp(m, True)
+        radius = np.linalg.norm(m[:, :3], axis=0).astype(np.float32)
+        r2l = np.stack([m[:, k] / radius[k] for k in range(3)]).astype(np.float32)
+        cen = r2l @ m[:, 3]
+        self.render_aabb_to_local = r2l
+        self._set_render_aabb(cen - radius, cen + radius)
+
+    def crop_box_corners(self, nerf_space: bool = True) -> list:
+        m = self.crop_box(nerf_space)
+        return [m @ np.array([1 if i & 1 else -1, 1 if i & 2 else -1, 1 if i & 4 else -1, 1], np.float32) for i in range(8)]
+
+    # -- the camera helpers of Testbed (S/ngp/testbed.cu:1319-1349) on camera_matrix: columns right, up, view direction, position
+    @property
+    def bounding_radius(self) -> float:
+        return float(self._dataset().bounding_radius)
 
     @property
-    def crop_box(self) -> BoundingBox:
-        return self._render_aabb
+    def raw_aabb(self) -> BoundingBox:
+        d = self._dataset()
+        return BoundingBox(list(d.raw_aabb_min), list(d.raw_aabb_max))
+
+    @property
+    def up_dir(self) -> np.ndarray:
+        if self._up_dir is None:
+            self._up_dir = np.array(list(self._dataset().up), np.float32)
+        return self._up_dir
+
+    @up_dir.setter
+    def up_dir(self, v):
+        self._up_dir = np.asarray(v, np.float32).reshape(3).copy()
+
+    def view_pos(self) -> np.ndarray:
+        return self.camera_matrix[:, 3].copy()
+
+    @property
+    def view_dir(self) -> np.ndarray:
+        return self.camera_matrix[:, 2].copy()
+
+    @view_dir.setter
+    def view_dir(self, d):
+        d = np.asarray(d, np.float32).reshape(3)
+        old = self.look_at
+        cam = self.camera_matrix
+        n = lambda v: v / np.float32(np.linalg.norm(v))
+        cam[:, 0] = n(np.cross(d, self.up_dir)); cam[:, 1] = n(np.cross(d, cam[:, 0])); cam[:, 2] = n(d)
+        self.camera_matrix = cam
+        self.look_at = old
+
+    @property
+    def look_at(self) -> np.ndarray:
+        cam = self.camera_matrix
+        return cam[:, 3] + cam[:, 2] * np.float32(self._scale)
+
+    @look_at.setter
+    def look_at(self, pos):
+        cam = self.camera_matrix
+        cam[:, 3] += np.asarray(pos, np.float32).reshape(3) - self.look_at
+        self.camera_matrix = cam
+
+    @property
+    def scale(self) -> float:
+        return self._scale
+
+    @scale.setter
+    def scale(self, v):
+        prev = self.look_at
+        cam = self.camera_matrix
+        cam[:, 3] = (cam[:, 3] - prev) * np.float32(float(v) / self._scale) + prev
+        self.camera_matrix = cam
+        self._scale = float(v)
+
+    def translate_camera(self, rel):
+        cam = self.camera_matrix
+        cam[:, 3] += cam[:, :3] @ np.asarray(rel, np.float32).reshape(3) * np.float32(self.bounding_radius)
+        self.camera_matrix = cam
+
+    # -- members the reference exposes and this fork's ray generation never reads (pixel_to_ray derives the direction from the pixel
+    #    centre alone, S/ngp/ngp_common.cuh:361-366): kept as plain values so that scripts setting them keep running
+    zoom = 1.0
+    camera_smoothing = False
+    snap_to_pixel_centers = False
+    display_gui = False
+    visualize_unit_cube = False
+    fixed_res_factor = 1
+    max_level_rand_training = False
+    visualized_dimension = -1
+    visualized_layer = 0
+
+    @property
+    def screen_center(self) -> np.ndarray:
+        return self._screen_center
+
+    @screen_center.setter
+    def screen_center(self, v):
+        self._screen_center = np.asarray(v, np.float32).reshape(2).copy()
+
+    @property
+    def sun_dir(self) -> np.ndarray:
+        return self._sun_dir
+
+    @sun_dir.setter
+    def sun_dir(self, v):
+        self._sun_dir = np.asarray(v, np.float32).reshape(3).copy()
+
+    # -- members that WOULD change the picture in the reference and are not built: anything but the default is refused, not ignored
+    @property
+    def parallax_shift(self) -> np.ndarray:
+        return np.zeros(3, np.float32)
+
+    @parallax_shift.setter
+    def parallax_shift(self, v):
+        if np.any(np.asarray(v, np.float32).reshape(3)[:2] != 0):
+            raise NotImplementedError("parallax_shift: only (0, 0, z) - the viewer's origin is not shifted by this renderer")
+
+    @property
+    def color_space(self) -> ColorSpace:
+        return ColorSpace.Linear
+
+    @color_space.setter
+    def color_space(self, v):
+        if ColorSpace(int(v)) != ColorSpace.Linear:
+            raise NotImplementedError("color_space: this renderer accumulates in linear colour (ColorSpace.Linear) only")
 
     def render(self, width: int = 1920, height: int = 1080, spp: int = 1, linear: bool = True, dtype=np.float32) -> np.ndarray:
         """float32[H, W, 4]; row 0 is the bottom of the picture; sRGB when linear=False (S/python_api.cu:83-111).

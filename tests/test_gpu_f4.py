@@ -247,3 +247,72 @@ def test_trajectory_export(small_snapshot, glasses_gltf, tmp_path):
         assert png.shape[:2] == (HH, W)
         assert np.array_equal(png[..., :3], np.uint8(np.clip(img[::-1, :, :3], 0.0, 1.0) * np.float32(255.0)))
         assert png[..., :3].std() > 5                           # a picture, not a constant
+
+
+def test_rotated_crop_box_and_secondary_testbed_properties(small_snapshot):
+    """Testbed.set_crop_box / crop_box / crop_box_corners with a ROTATED box (S/ngp/testbed.cu:1421-1477; render_aabb_to_local is
+    writable in the reference, S/python_api.cu:411): the walks test samples against the box in its own frame (S/ngp/testbed.cu:505, 596).
+    Traversal stays bit-exact against the oracle given the same matrix, pixels within tolerance; plus the camera helpers and the
+    plain members of the reference's Testbed binding (S/python_api.cu:408-447)."""
+    import pynmr
+    from oracle import oracle as O
+    path, snap = small_snapshot
+    W, HH = 160, 90
+    r = pynmr.NerfMeshRenderer(W, HH)
+    nerf = r.load_nerf(path)
+    r.orbit(0.3, -0.15, 3.0)
+    c12 = np.ascontiguousarray(r.view_projection_mat.T.reshape(-1))
+    plain = np.asarray(nerf.render(W, HH, 1, linear=False)).copy()
+    # a box turned by 30 degrees about y and 20 about x, centred on the head, in NeRF coordinates (nerf_space=False)
+    a, b = np.deg2rad(30.0), np.deg2rad(20.0)
+    Ry = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]], np.float32)
+    Rx = np.array([[1, 0, 0], [0, np.cos(b), -np.sin(b)], [0, np.sin(b), np.cos(b)]], np.float32)
+    axes = (Ry @ Rx).astype(np.float32)
+    radius = np.array([0.12, 0.2, 0.16], np.float32)
+    m = np.concatenate([axes * radius[None, :], np.array([[0.5], [0.52], [0.5]], np.float32)], axis=1)
+    nerf.set_crop_box(m, nerf_space=False)
+    r2l = nerf.render_aabb_to_local
+    assert float(np.abs(r2l - axes.T).max()) <= 1e-6
+    assert float(np.abs(nerf.crop_box(nerf_space=False) - m).max()) <= 1e-6                      # round trip
+    rt = nerf.crop_box(nerf_space=True)
+    corners = nerf.crop_box_corners(nerf_space=False)
+    assert len(corners) == 8 and float(np.abs(np.mean(corners, axis=0) - m[:, 3]).max()) <= 1e-6
+    mn, mx = np.asarray(nerf.render_aabb.min), np.asarray(nerf.render_aabb.max)
+    assert float(np.abs((mx - mn) * 0.5 - radius).max()) <= 1e-6
+    img = np.asarray(nerf.render(W, HH, 1, linear=False)).copy()
+    assert float(np.abs(img - plain).max()) > 0.05                                               # the crop cuts into the head
+    model = O.Model.from_snapshot(snap)
+    P = model.params_struct(W, HH, c12, aabb_min=mn, aabb_max=mx, n_steps_mode=1)
+    P.render_aabb_to_local[:] = [float(x) for x in r2l.reshape(-1)]
+    frame, _, ns, _ = model.render_frame(P)
+    want, _ = O.accumulate_tonemap(frame, None, 0, to_srgb=True)
+    assert float(np.abs(img - want).max()) <= 2.0 / 255.0 and H.psnr(img, want) >= 45.0
+    # the same box handed over in dataset coordinates gives the same state back
+    nerf.set_crop_box(rt, nerf_space=True)
+    assert float(np.abs(nerf.crop_box(nerf_space=False) - m).max()) <= 2e-6
+    assert np.array_equal(np.asarray(nerf.render(W, HH, 1, linear=False)), img) or float(np.abs(np.asarray(nerf.render(W, HH, 1, linear=False)) - img).max()) <= 2.0 / 255.0
+    # camera helpers (S/ngp/testbed.cu:1319-1349) act on camera_matrix
+    cam = nerf.camera_matrix
+    assert np.allclose(nerf.look_at, cam[:, 3] + cam[:, 2] * nerf.scale)
+    la = nerf.look_at.copy()
+    assert nerf.scale == 1.5                                      # Testbed::reset_camera (S/ngp/testbed.cu:1388)
+    nerf.scale = 2.0
+    assert np.allclose(nerf.look_at, la, atol=1e-6) and np.allclose(nerf.camera_matrix[:, 3], (cam[:, 3] - la) * np.float32(2.0 / 1.5) + la, atol=1e-6)
+    nerf.look_at = [0.1, 0.2, 0.3]
+    assert np.allclose(nerf.look_at, [0.1, 0.2, 0.3], atol=1e-6)
+    nerf.view_dir = [0.0, 0.0, 1.0]
+    cm = nerf.camera_matrix
+    assert np.allclose(cm[:, 2], [0, 0, 1], atol=1e-6) and np.allclose(cm[:, 0], np.cross([0, 0, 1], nerf.up_dir) / np.linalg.norm(np.cross([0, 0, 1], nerf.up_dir)), atol=1e-6)
+    assert np.allclose(nerf.look_at, [0.1, 0.2, 0.3], atol=1e-5)
+    assert nerf.bounding_radius > 0 and np.allclose(nerf.raw_aabb.min, nerf.aabb.min)
+    # plain members keep what they are given; members that would change the picture refuse anything but the default
+    nerf.zoom = 2.0; nerf.screen_center = [0.4, 0.6]; nerf.snap_to_pixel_centers = True; nerf.camera_smoothing = True; nerf.sun_dir = [0, 1, 0]
+    assert nerf.zoom == 2.0 and np.allclose(nerf.screen_center, [0.4, 0.6]) and np.allclose(nerf.sun_dir, [0, 1, 0])
+    nerf.color_space = pynmr.ColorSpace.Linear
+    with pytest.raises(NotImplementedError):
+        nerf.color_space = pynmr.ColorSpace.SRGB
+    nerf.parallax_shift = [0, 0, 1]
+    with pytest.raises(NotImplementedError):
+        nerf.parallax_shift = [0.1, 0, 1]
+    with pytest.raises(RuntimeError):
+        nerf.render_aabb_to_local = np.full((3, 3), np.nan, np.float32)
