@@ -867,9 +867,10 @@ NMR_API void* nmr_host_alloc(size_t bytes) {
 }
 NMR_API void nmr_host_free(void* p) { if (p) cudaFreeHost(p); }
 
-NMR_API int nmr_load_nerf(nmr_ctx* ctx, const char* path, int* out_id) {
-    return guarded(ctx, [&]() -> int {
-        if (!path) return fail(ctx, NMR_ERR_INVALID, "path is null");
+namespace {
+// Testbed::load_snapshot (S/ngp/testbed.cu:939-1135) for this renderer: the snapshot on the host, its parameters, occupancy bits,
+// tensor-core weight layout, brick layout and near-field bits on the device.  Throws like the loaders it calls.
+std::unique_ptr<Nerf> build_nerf(nmr_ctx* ctx, const char* path) {
         std::unique_ptr<Nerf> n(new Nerf());
         n->host = load_snapshot(path);
         HostModel& h = n->host;
@@ -936,9 +937,35 @@ NMR_API int nmr_load_nerf(nmr_ctx* ctx, const char* path, int* out_id) {
         n->n_params = h.params.size();
         std::vector<uint16_t>().swap(h.params);
         std::vector<uint16_t>().swap(h.density_grid);
+        return n;
+}
+}  // namespace
+
+NMR_API int nmr_load_nerf(nmr_ctx* ctx, const char* path, int* out_id) {
+    return guarded(ctx, [&]() -> int {
+        if (!path) return fail(ctx, NMR_ERR_INVALID, "path is null");
+        std::unique_ptr<Nerf> n = build_nerf(ctx, path);
         ctx->nerfs.push_back(std::move(n));
         ctx->surf.spp = 0;
         if (out_id) *out_id = (int)ctx->nerfs.size() - 1;
+        return NMR_OK;
+    });
+}
+
+NMR_API int nmr_reload_nerf(nmr_ctx* ctx, int id, const char* path) {
+    return guarded(ctx, [&]() -> int {
+        if (!path) return fail(ctx, NMR_ERR_INVALID, "path is null");
+        Nerf* old; try { old = get_nerf(ctx, id); } catch (const std::invalid_argument& e) { return fail(ctx, NMR_ERR_INVALID, e.what()); }
+        std::unique_ptr<Nerf> n = build_nerf(ctx, path);              // a file that does not load leaves the old model in place
+        // what load_snapshot does not touch in the reference stays: the members set through the Python properties
+        std::memcpy(n->background, old->background, sizeof(n->background));
+        n->min_transmittance = old->min_transmittance; n->tonemap_curve = old->tonemap_curve;
+        std::memcpy(n->model_translation, old->model_translation, 12); std::memcpy(n->model_rotation_pi, old->model_rotation_pi, 12);
+        std::memcpy(n->model_rot, old->model_rot, sizeof(n->model_rot));
+        CK(cudaDeviceSynchronize());                                  // nothing in flight (helper lanes included) reads the old buffers any more
+        ctx->l2_window_ptr = nullptr;
+        ctx->nerfs[(size_t)id] = std::move(n);
+        ctx->surf.spp = 0;
         return NMR_OK;
     });
 }

@@ -65,6 +65,7 @@ def lib():
         "nmr_destroy": (None, [vp]),
         "nmr_last_error": (C.c_char_p, [vp]),
         "nmr_load_nerf": (C.c_int, [vp, C.c_char_p, ip]),
+        "nmr_reload_nerf": (C.c_int, [vp, C.c_int, C.c_char_p]),
         "nmr_load_mesh": (C.c_int, [vp, C.c_char_p, fp, fp, fp, ip]),
         "nmr_set_mesh_transform": (C.c_int, [vp, C.c_int, fp, fp, fp]),
         "nmr_get_mesh_transform": (C.c_int, [vp, C.c_int, fp, fp, fp]),
@@ -144,7 +145,7 @@ EXPORTED_SYMBOLS = [
     "nmr_get_device_image", "nmr_copy_device_image", "nmr_flush_l2", "nmr_get_stats", "nmr_synchronize", "nmr_host_alloc", "nmr_host_free", "nmr_render_update", "nmr_trajectory_pose", "nmr_get_density_bitfield",
     "nmr_set_density_bitfield", "nmr_debug_encode", "nmr_debug_network", "nmr_debug_trace", "nmr_debug_mesh",
     "nmr_debug_last_frame", "nmr_debug_set_flags", "nmr_render_format", "nmr_render_views_format", "nmr_debug_parse_gltf", "nmr_measure_l2", "nmr_set_overlap", "nmr_set_model_transform", "nmr_get_model_transform",
-    "nmr_dump_density_grid", "nmr_load_density_grid", "nmr_read_combined", "nmr_set_lens_model", "nmr_mikk_tangents", "nmr_get_nerf_dataset", "nmr_set_render_aabb_to_local",
+    "nmr_dump_density_grid", "nmr_load_density_grid", "nmr_read_combined", "nmr_set_lens_model", "nmr_mikk_tangents", "nmr_get_nerf_dataset", "nmr_set_render_aabb_to_local", "nmr_reload_nerf",
 ]
 
 
@@ -369,6 +370,26 @@ class BoundingBox:
             self._min = np.minimum(self._min, p); self._max = np.maximum(self._max, p)
         self._push()
 
+    def ray_intersect(self, pos, dir):
+        """BoundingBox::ray_intersect (S/ngp/bounding_box.cuh:106-147): the slab test in fp32, axis by axis -> (tmin, tmax), both FLT_MAX
+        when the ray misses the box."""
+        f = np.float32
+        fmax = np.finfo(np.float32).max
+        p = np.asarray(pos, f).reshape(3); d = np.asarray(dir, f).reshape(3)
+        mn, mx = self.min.astype(f), self.max.astype(f)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            lo = (mn - p) / d; hi = (mx - p) / d
+        tmin, tmax = (hi[0], lo[0]) if lo[0] > hi[0] else (lo[0], hi[0])
+        for k in (1, 2):
+            a, b = (hi[k], lo[k]) if lo[k] > hi[k] else (lo[k], hi[k])
+            if tmin > b or a > tmax:
+                return fmax, fmax
+            if a > tmin:
+                tmin = a
+            if b < tmax:
+                tmax = b
+        return f(tmin), f(tmax)
+
     def intersection(self, other):
         return BoundingBox(np.maximum(self.min, other.min), np.minimum(self.max, other.max))
 
@@ -561,6 +582,12 @@ class Testbed:
         else:
             cells = np.ascontiguousarray(path_or_cells, dtype=np.uint8).reshape(8, 128, 128, 128)
             self._r._ck(lib().nmr_load_density_grid(self._r._h, self._id, None, _ptr(cells)))
+
+    def load_snapshot(self, path: str):
+        """Testbed.load_snapshot (S/python_api.cu:319): another snapshot into this Testbed; raises RuntimeError when it does not load
+        (the reference throws from load_snapshot as well) and keeps the old model in that case."""
+        self._r._ck(lib().nmr_reload_nerf(self._r._h, self._id, os.fsencode(path)))
+        self._up_dir = None
 
     # -- crop box as a 3x4 matrix (Testbed::crop_box / set_crop_box / crop_box_corners, S/ngp/testbed.cu:1421-1477): columns = the
     #    box's half axes and its centre; nerf_space=True converts to / from the dataset's coordinates (S/ngp/nerf_loader.cuh:115-153)

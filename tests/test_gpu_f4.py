@@ -316,3 +316,33 @@ def test_rotated_crop_box_and_secondary_testbed_properties(small_snapshot):
         nerf.parallax_shift = [0.1, 0, 1]
     with pytest.raises(RuntimeError):
         nerf.render_aabb_to_local = np.full((3, 3), np.nan, np.float32)
+
+
+def test_load_snapshot_into_an_existing_testbed(small_snapshot, second_snapshot, tmp_path):
+    """Testbed.load_snapshot(path) (S/python_api.cu:319): the second model replaces the first in the same Testbed - frames equal those of
+    a renderer that loaded the second model directly; the background colour set through the property survives; a file that does
+    not load raises and leaves the model in place."""
+    import pynmr
+    path_a, _ = small_snapshot
+    path_b, _ = second_snapshot
+    r = pynmr.NerfMeshRenderer(W, HH)
+    nerf = r.load_nerf(path_a)
+    nerf.background_color = [0.2, 0.4, 0.6, 1.0]
+    r.orbit(0.3, -0.2, 3.0)
+    img_a = np.asarray(nerf.render(W, HH, 1, linear=False)).copy()
+    nerf.load_snapshot(path_b)
+    img_b = np.asarray(nerf.render(W, HH, 1, linear=False)).copy()
+    fresh = pynmr.NerfMeshRenderer(W, HH)
+    nb = fresh.load_nerf(path_b)
+    nb.background_color = [0.2, 0.4, 0.6, 1.0]
+    fresh.view_projection_mat = r.view_projection_mat
+    want = np.asarray(nb.render(W, HH, 1, linear=False))
+    assert np.array_equal(img_b, want)
+    assert float(np.abs(img_b - img_a).max()) > 0.05
+    assert np.allclose(nerf.background_color, [0.2, 0.4, 0.6, 1.0])
+    bad = tmp_path / "broken.msgpack"
+    bad.write_bytes(open(path_a, "rb").read()[:1000])
+    with pytest.raises(RuntimeError):
+        nerf.load_snapshot(str(bad))
+    assert np.array_equal(np.asarray(nerf.render(W, HH, 1, linear=False)), img_b)
+    assert r.frame()

@@ -457,3 +457,22 @@ def test_pinned_pool_is_bounded(monkeypatch):
     assert freed == [2, 1]
     assert pynmr._pinned_pool == {300: [3], 200: [4], 500: [5]}
     assert sum(n * len(b) for n, b in pynmr._pinned_pool.items()) <= 1000
+
+
+def test_bounding_box_ray_intersect_equals_the_oracle():
+    """pynmr.BoundingBox.ray_intersect (S/python_api.cu:256 -> S/ngp/bounding_box.cuh:106-147) against the oracle's slab test, which is
+    pinned bit for bit on the reference's own BoundingBox (tests/test_oracle_golden.py, tests/test_oracle_vs_ref.py)."""
+    import pynmr
+    from oracle import oracle as O
+    rng = np.random.default_rng(3)
+    box = pynmr.BoundingBox([-0.2, 0.15, -0.2], [1.0, 1.0, 1.0])
+    bmin = np.array([-0.2, 0.15, -0.2], np.float32); bmax = np.array([1, 1, 1], np.float32)
+    for i in range(2000):
+        pos = rng.uniform(-2, 3, 3).astype(np.float32)
+        d = rng.normal(size=3).astype(np.float32)
+        if i % 10 == 0:
+            d[int(rng.integers(0, 3))] = 0.0                      # a ray parallel to a slab
+        want = np.zeros(2, np.float32)
+        O.lib().orc_aabb_ray_intersect(bmin.ctypes.data, bmax.ctypes.data, pos.ctypes.data, d.ctypes.data, want.ctypes.data)
+        got = np.array(box.ray_intersect(pos, d), np.float32)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)) or (np.isnan(got).any() and np.isnan(want).any()), (pos, d, got, want)
