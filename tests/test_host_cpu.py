@@ -476,3 +476,63 @@ def test_bounding_box_ray_intersect_equals_the_oracle():
         O.lib().orc_aabb_ray_intersect(bmin.ctypes.data, bmax.ctypes.data, pos.ctypes.data, d.ctypes.data, want.ctypes.data)
         got = np.array(box.ray_intersect(pos, d), np.float32)
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)) or (np.isnan(got).any() and np.isnan(want).any()), (pos, d, got, want)
+
+
+def test_testbed_crop_box_and_camera_helpers_host_arithmetic():
+    """The host arithmetic behind Testbed.crop_box / set_crop_box / crop_box_corners (S/ngp/testbed.cu:1421-1477 with
+    NerfDataset::ngp_matrix_to_nerf / nerf_matrix_to_ngp, S/ngp/nerf_loader.cuh:115-153) and scale / look_at / view_dir
+    (S/ngp/testbed.cu:1328-1349), on a Testbed whose device calls are replaced by plain members (no GPU needed)."""
+    import pynmr
+
+    class HostOnly(pynmr.Testbed):
+        def __init__(self):
+            self._scale = 1.5; self._up_dir = None
+            self._mn = np.array([0.3, 0.15, 0.3], np.float32); self._mx = np.array([1, 1, 1], np.float32)
+            self._r2l = np.eye(3, dtype=np.float32)
+            self._cam = np.array([[1, 0, 0, 0.1], [0, 1, 0, 0.2], [0, 0, 1, 2.0]], np.float32)
+
+        def _dataset(self):
+            d = pynmr.NerfDataset(); d.scale = 0.33; d.offset[:] = [0.5, 0.5, 0.5]; d.up[:] = [0, 1, 0]; d.from_mitsuba = 0; d.bounding_radius = 2.0
+            d.raw_aabb_min[:] = [0, 0, 0]; d.raw_aabb_max[:] = [1, 1, 1]
+            return d
+
+        def _get_render_aabb(self):
+            return self._mn.copy(), self._mx.copy()
+
+        def _set_render_aabb(self, mn, mx):
+            self._mn = np.asarray(mn, np.float32); self._mx = np.asarray(mx, np.float32)
+
+        render_aabb_to_local = property(lambda s: s._r2l.copy(), lambda s, m: setattr(s, "_r2l", np.asarray(m, np.float32).reshape(3, 3)))
+        camera_matrix = property(lambda s: s._cam.copy(), lambda s, m: setattr(s, "_cam", np.asarray(m, np.float32).reshape(3, 4)))
+
+    t = HostOnly()
+    ngp = t.crop_box(nerf_space=False)
+    assert np.allclose(ngp, [[0.35, 0, 0, 0.65], [0, 0.425, 0, 0.575], [0, 0, 0.35, 0.65]])
+    nerf = t.crop_box(nerf_space=True)
+    c = ngp[:, 3]
+    assert np.allclose(nerf[:, 3], (np.array([c[2], c[0], c[1]]) - 0.5) / 0.33, atol=1e-6)          # ngp_position_to_nerf of the centre
+    assert np.allclose(np.abs(nerf[:, :3]).sum(axis=0), np.array([0.35, 0.425, 0.35]) / 0.33, atol=1e-5)   # half axes scaled, axes cycled
+    # a rotated box survives the round trip through dataset coordinates
+    a = np.deg2rad(25.0)
+    R = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]], np.float32)
+    m = np.concatenate([R * np.array([0.1, 0.2, 0.3], np.float32)[None, :], np.array([[0.5], [0.5], [0.6]], np.float32)], axis=1)
+    t.set_crop_box(m, nerf_space=False)
+    assert np.allclose(t.render_aabb_to_local, R.T, atol=1e-6) and np.allclose(t.crop_box(False), m, atol=1e-6)
+    back = t.crop_box(True)
+    t.set_crop_box(np.eye(3, 4, dtype=np.float32), nerf_space=False)
+    t.set_crop_box(back, nerf_space=True)
+    assert np.allclose(t.crop_box(False), m, atol=2e-6)
+    corners = np.array(t.crop_box_corners(False))
+    assert corners.shape == (8, 3) and np.allclose(corners.mean(axis=0), m[:, 3], atol=1e-6)
+    assert np.allclose(np.linalg.norm(corners[1] - corners[0]), 0.2, atol=1e-6)                     # corner 1 - corner 0 = 2 x the first half axis
+    # camera helpers
+    assert np.allclose(t.look_at, [0.1, 0.2, 3.5]) and np.allclose(t.view_dir, [0, 0, 1])
+    t.scale = 3.0
+    assert np.allclose(t.look_at, [0.1, 0.2, 3.5]) and np.allclose(t.camera_matrix[:, 3], [0.1, 0.2, 0.5])
+    t.view_dir = [1, 0, 0]
+    cam = t.camera_matrix
+    assert np.allclose(cam[:, 2], [1, 0, 0]) and np.allclose(cam[:, 0], [0, 0, 1]) and np.allclose(cam[:, 1], [0, -1, 0])
+    assert np.allclose(t.look_at, [0.1, 0.2, 3.5], atol=1e-6)
+    t.translate_camera([0, 0, 1])
+    assert np.allclose(t.camera_matrix[:, 3], cam[:, 3] + 2.0 * cam[:, 2])                           # bounding_radius x the view direction
+    assert t.bounding_radius == 2.0 and np.allclose(t.up_dir, [0, 1, 0])
