@@ -167,21 +167,30 @@ struct Edge { int key[3]; };        // lower name, higher name, triangle
 // The method's quicksort on one key: two entries are compared directly; otherwise the pivot is the entry at (seed' mod n), seed'
 // from a fixed scramble of the seed handed down, and a Hoare partition follows.
 void sort_edges(Edge* e, int left, int right, int ch, uint32_t seed) {
-    const int n = right - left + 1;
-    if (n < 2) return;
-    if (n == 2) { if (e[left].key[ch] > e[right].key[ch]) std::swap(e[left], e[right]); return; }
-    const uint32_t r = seed & 31;
-    const uint32_t rot = r ? ((seed << r) | (seed >> (32 - r))) : seed;
-    seed = seed + rot + 3;
-    int a = left, b = right;
-    const int pivot = e[left + (int)(seed % (uint32_t)n)].key[ch];
-    do {
-        while (e[a].key[ch] < pivot) ++a;
-        while (e[b].key[ch] > pivot) --b;
-        if (a <= b) { std::swap(e[a], e[b]); ++a; --b; }
-    } while (a <= b);
-    if (left < b) sort_edges(e, left, b, ch, seed);
-    if (a < right) sort_edges(e, a, right, ch, seed);
+    // (the two halves of a partition are sorted independently with the same seed, so the smaller one is taken by recursion and the
+    //  larger one by the loop: the same result as two recursive calls with a call depth of log2 n whatever the keys are)
+    while (true) {
+        const int n = right - left + 1;
+        if (n < 2) return;
+        if (n == 2) { if (e[left].key[ch] > e[right].key[ch]) std::swap(e[left], e[right]); return; }
+        const uint32_t r = seed & 31;
+        const uint32_t rot = r ? ((seed << r) | (seed >> (32 - r))) : seed;
+        seed = seed + rot + 3;
+        int a = left, b = right;
+        const int pivot = e[left + (int)(seed % (uint32_t)n)].key[ch];
+        do {
+            while (e[a].key[ch] < pivot) ++a;
+            while (e[b].key[ch] > pivot) --b;
+            if (a <= b) { std::swap(e[a], e[b]); ++a; --b; }
+        } while (a <= b);
+        const bool lo = left < b, hi = a < right;
+        if (lo && hi) {
+            if (b - left < right - a) { sort_edges(e, left, b, ch, seed); left = a; }
+            else { sort_edges(e, a, right, ch, seed); right = b; }
+        } else if (lo) right = b;
+        else if (hi) left = a;
+        else return;
+    }
 }
 
 // step 5: depth-first growth of one group around its vertex, from the triangles `first` and `second` (either may be -1).  The order
