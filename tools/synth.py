@@ -560,8 +560,9 @@ def write_lens_glasses_gltf(out_dir: str, texture_rgba=(128, 128, 128, 255), npz
 
 def np_tangents(pos: np.ndarray, nrm: np.ndarray, uv: np.ndarray, idx: np.ndarray) -> np.ndarray:
     """Per-vertex tangents (xyz + handedness) from the UV derivatives: per-triangle tangent / bitangent accumulated per vertex, then
-    Gram-Schmidt against the normal - the numpy restatement of what the C++ loader generates when a file has no TANGENT attribute
-    (csrc/host.cpp; the reference runs MikkTSpace there)."""
+    Gram-Schmidt against the normal.  What the textured fixture writes into its TANGENT attribute (any sane tangent field would do:
+    a file's tangents are taken as they are).  Not what the loader generates for a file WITHOUT the attribute - that is the reference's
+    MikkTSpace generator, csrc/mikk.cpp."""
     pos = pos.astype(np.float32); nrm = nrm.astype(np.float32); uv = uv.astype(np.float32)
     tri = idx.reshape(-1, 3).astype(np.int64)
     tacc = np.zeros_like(pos); bacc = np.zeros_like(pos)
