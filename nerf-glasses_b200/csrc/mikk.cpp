@@ -67,6 +67,7 @@ struct Tri {
 };
 
 struct Group { int vertex; bool preserving; std::vector<int> tris; };
+constexpr size_t kMaxFan = 8192;
 
 // A vertex is named by one of its corners: name = (face << 2) | corner, as the method packs it.
 struct Mesh {
@@ -310,6 +311,9 @@ void mikk_tangents(const float* positions, const float* normals, const float* te
     std::vector<V3> sub_tangent;
     for (size_t g = 0; g < groups.size(); ++g) {
         const Group& G = groups[g];
+        // the sub-groups compare every member with every other one (as the published method does): refuse a vertex whose fan would
+        // take minutes - no modelled surface comes near this (the reference overflows its call stack long before)
+        if (G.tris.size() > kMaxFan) throw std::length_error("mikk_tangents: more than 8192 triangles of one orientation around a vertex");
         const V3 n = m.N(G.vertex);
         sub_members.clear(); sub_tangent.clear();
         for (int f : G.tris) {

@@ -536,3 +536,30 @@ def test_testbed_crop_box_and_camera_helpers_host_arithmetic():
     t.translate_camera([0, 0, 1])
     assert np.allclose(t.camera_matrix[:, 3], cam[:, 3] + 2.0 * cam[:, 2])                           # bounding_radius x the view direction
     assert t.bounding_radius == 2.0 and np.allclose(t.up_dir, [0, 1, 0])
+
+
+def test_mikk_tangents_on_hostile_meshes():
+    """Inputs a file can contain and a modeller never produces: every vertex identical, NaN / infinite coordinates, a fan of thousands
+    of triangles around one vertex (the method compares all of a vertex's triangles pairwise; the reference recurses once per
+    triangle of the fan).  The generator answers or refuses; it does not crash, hang or overflow the stack."""
+    import pynmr
+    import synth
+    rng = np.random.default_rng(11)
+    p = np.zeros((30, 3), np.float32); n = np.tile(np.array([0, 0, 1], np.float32), (30, 1)); t = np.zeros((30, 2), np.float32)
+    out = pynmr.mikk_tangents(p, n, t, rng.integers(0, 30, (40, 3)).astype(np.uint32))
+    assert np.array_equal(out, np.tile(np.array([1, 0, 0, -1], np.float32), (30, 1)))           # every triangle degenerate: default frames
+
+    def fan(k):
+        ang = np.linspace(0, 2 * np.pi, k + 1)[:-1]
+        p = np.concatenate([[[0, 0, 0]], np.stack([np.cos(ang), np.sin(ang), 0 * ang], 1)]).astype(np.float32)
+        i = np.stack([np.zeros(k, np.uint32), np.arange(1, k + 1, dtype=np.uint32), np.roll(np.arange(1, k + 1, dtype=np.uint32), -1)], 1)
+        return p, np.tile(np.array([0, 0, 1], np.float32), (k + 1, 1)), (p[:, :2] * 0.5 + 0.5).astype(np.float32), i
+    p, n, t, i = fan(1500)
+    out = pynmr.mikk_tangents(p, n, t, i)
+    assert float(np.abs(out[:, :3] - np.array([1, 0, 0], np.float32)).max()) <= 1e-3 and np.all(out[:, 3] == 1)   # a flat disc mapped by its own x, y
+    with pytest.raises(RuntimeError):
+        pynmr.mikk_tangents(*fan(20000))                                                         # refused, not ground through
+    p, n, t, i = synth.tangent_test_soup(rng, 40, 200)
+    p[3] = np.nan; p[7] = np.inf; t[5] = np.inf; n[::3] = 0
+    out = pynmr.mikk_tangents(p, n, t, i)
+    assert out.shape == (40, 4) and set(np.unique(out[:, 3])) <= {-1.0, 1.0}
