@@ -525,8 +525,14 @@ HostMesh load_gltf(const std::string& path) {
         for (uint32_t& i : local) { i -= pr.vbase; if (i >= pr.nv) throw std::runtime_error("gltf: index outside its primitive's vertices"); }
         float* tg = &m.tangents[(size_t)pr.vbase * 4];
         for (size_t v = 0; v < pr.nv; ++v) { tg[v * 4] = 1.f; tg[v * 4 + 1] = 0.f; tg[v * 4 + 2] = 0.f; tg[v * 4 + 3] = -1.f; }
-        mikk_tangents(&m.positions[(size_t)pr.vbase * 3], &m.normals[(size_t)pr.vbase * 3], &m.texcoords[(size_t)pr.vbase * 2], pr.nv,
-                      local.data(), local.size(), tg);
+        try {
+            mikk_tangents(&m.positions[(size_t)pr.vbase * 3], &m.normals[(size_t)pr.vbase * 3], &m.texcoords[(size_t)pr.vbase * 2], pr.nv,
+                          local.data(), local.size(), tg);
+        } catch (const std::length_error& e) {
+            // a mesh the generator refuses still loads: only a normal map reads the tangents, and it gets the default frame
+            for (size_t v = 0; v < pr.nv; ++v) { tg[v * 4] = 1.f; tg[v * 4 + 1] = 0.f; tg[v * 4 + 2] = 0.f; tg[v * 4 + 3] = -1.f; }
+            m.warning += (m.warning.empty() ? "" : "; ") + std::string("tangents not generated (") + e.what() + "), default frames used";
+        }
     }
     // node 0 TRS (GltfLoader::traverse, S/gltf_scene.cpp:63-118); matrix-form nodes are not decomposed (load_mesh overwrites TRS anyway)
     const Value& n0 = doc.at("nodes").at((size_t)scene_nodes.at(0).as_int());

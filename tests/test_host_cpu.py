@@ -563,3 +563,30 @@ def test_mikk_tangents_on_hostile_meshes():
     p[3] = np.nan; p[7] = np.inf; t[5] = np.inf; n[::3] = 0
     out = pynmr.mikk_tangents(p, n, t, i)
     assert out.shape == (40, 4) and set(np.unique(out[:, 3])) <= {-1.0, 1.0}
+
+
+def test_gltf_with_a_fan_the_tangent_generator_refuses_still_loads(tmp_path):
+    """A primitive without TANGENT whose fan exceeds what the generator accepts: the file loads with a warning and default frames."""
+    import base64
+    import json
+    import pynmr
+    k = 9000
+    ang = np.linspace(0, 2 * np.pi, k + 1)[:-1]
+    pos = np.concatenate([[[0, 0, 0]], np.stack([np.cos(ang), np.sin(ang), 0 * ang], 1)]).astype("<f4")
+    nrm = np.tile(np.array([0, 0, 1], "<f4"), (k + 1, 1)); uv = (pos[:, :2] * 0.5 + 0.5).astype("<f4")
+    idx = np.stack([np.zeros(k, "<u4"), np.arange(1, k + 1, dtype="<u4"), np.roll(np.arange(1, k + 1, dtype="<u4"), -1)], 1)
+    parts = [pos.tobytes(), nrm.tobytes(), uv.tobytes(), idx.tobytes()]
+    offs = np.cumsum([0] + [len(b) for b in parts])
+    doc = {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0]}], "nodes": [{"mesh": 0}],
+           "meshes": [{"primitives": [{"attributes": {"POSITION": 0, "NORMAL": 1, "TEXCOORD_0": 2}, "indices": 3}]}],
+           "buffers": [{"byteLength": int(offs[-1]), "uri": "data:application/octet-stream;base64," + base64.b64encode(b"".join(parts)).decode()}],
+           "bufferViews": [{"buffer": 0, "byteOffset": int(offs[j]), "byteLength": len(parts[j])} for j in range(4)],
+           "accessors": [{"bufferView": 0, "componentType": 5126, "count": k + 1, "type": "VEC3", "min": [-1, -1, 0], "max": [1, 1, 0]},
+                         {"bufferView": 1, "componentType": 5126, "count": k + 1, "type": "VEC3"},
+                         {"bufferView": 2, "componentType": 5126, "count": k + 1, "type": "VEC2"},
+                         {"bufferView": 3, "componentType": 5125, "count": 3 * k, "type": "SCALAR"}]}
+    path = tmp_path / "fan.gltf"
+    path.write_text(json.dumps(doc))
+    g = pynmr.parse_gltf(str(path), tangents=True)
+    assert g["triangles"] == k and "tangents not generated" in g["warning"]
+    assert np.array_equal(g["tangents"], np.tile(np.array([1, 0, 0, -1], np.float32), (k + 1, 1)))
