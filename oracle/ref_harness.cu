@@ -10,6 +10,7 @@
 //   S/ngp/ngp_common.cuh         pixel_to_ray, linear_to_srgb, srgb_to_linear
 //   T/include/tiny-cuda-nn/common_device.h   morton3D, morton3D_invert
 //   T/include/tiny-cuda-nn/encodings/grid.h  grid_scale, grid_resolution
+//   S/ngp/nerf_loader.cuh        NerfDataset::nerf_matrix_to_ngp / ngp_matrix_to_nerf (behind Testbed.crop_box(nerf_space=True))
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
@@ -21,6 +22,7 @@
 #include <tiny-cuda-nn/common_device.h>
 #include <tiny-cuda-nn/encodings/grid.h>
 
+#include "ngp/nerf_loader.cuh"
 #include "floatyremover.h"
 #define FLYTHROUGH_CAMERA_IMPLEMENTATION
 #include "orbit_camera.h"
@@ -111,4 +113,14 @@ REF_API int ref_format_transform(const float* m12_rowmajor, char* out, int cap) 
     if ((int)t.size() + 1 > cap) return -1;
     std::memcpy(out, t.c_str(), t.size() + 1);
     return (int)t.size();
+}
+
+// NerfDataset's coordinate conversions (S/ngp/nerf_loader.cuh:115-153) on a 3x4 matrix given and returned row-major
+REF_API void ref_dataset_matrix(int to_ngp, int scale_columns, float scale, const float* offset3, int from_mitsuba, const float* m12_rowmajor, float* out12_rowmajor) {
+    ngp::NerfDataset d;
+    d.scale = scale; d.offset = Eigen::Vector3f(offset3[0], offset3[1], offset3[2]); d.from_mitsuba = from_mitsuba != 0;
+    Eigen::Matrix<float, 3, 4> m;
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) m(r, c) = m12_rowmajor[r * 4 + c];
+    const Eigen::Matrix<float, 3, 4> o = to_ngp ? d.nerf_matrix_to_ngp(m, scale_columns != 0) : d.ngp_matrix_to_nerf(m, scale_columns != 0);
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) out12_rowmajor[r * 4 + c] = o(r, c);
 }

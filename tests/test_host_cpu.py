@@ -590,3 +590,26 @@ def test_gltf_with_a_fan_the_tangent_generator_refuses_still_loads(tmp_path):
     g = pynmr.parse_gltf(str(path), tangents=True)
     assert g["triangles"] == k and "tangents not generated" in g["warning"]
     assert np.array_equal(g["tangents"], np.tile(np.array([1, 0, 0, -1], np.float32), (k + 1, 1)))
+
+
+def test_dataset_matrix_conversions_equal_the_references_golden_vectors():
+    """The shim's NeRF <-> dataset coordinate conversions behind crop_box / set_crop_box (nerf_space=True) against
+    tests/golden/ref_dataset_matrix.npz: 240 matrices through the reference's own NerfDataset::nerf_matrix_to_ngp /
+    ngp_matrix_to_nerf (S/ngp/nerf_loader.cuh:115-153; tests/golden/make_ref_dataset_matrix.py), with and without column scaling,
+    both axis conventions - bit for bit."""
+    import pynmr
+    g = np.load(os.path.join(GOLDEN, "ref_dataset_matrix.npz"))
+
+    class T(pynmr.Testbed):
+        def __init__(self):
+            pass
+
+        def _dataset(self):
+            return self._d
+    t = T()
+    for i in range(len(g["mats"])):
+        d = pynmr.NerfDataset(); d.scale = float(g["scale"][i]); d.offset[:] = [float(x) for x in g["offset"][i]]; d.from_mitsuba = int(g["from_mitsuba"][i])
+        t._d = d
+        f = t._nerf_matrix_to_ngp if g["to_ngp"][i] else t._ngp_matrix_to_nerf
+        got = f(g["mats"][i], bool(g["scale_columns"][i]))
+        assert np.array_equal(got.view(np.uint32), g["out"][i].view(np.uint32)), (i, got, g["out"][i])
