@@ -125,6 +125,43 @@ REF_API int refgpu_get_render_aabb(void* h, float* mn, float* mx) {
     for (int k = 0; k < 3; ++k) { mn[k] = r->tb->m_render_aabb.min[k]; mx[k] = r->tb->m_render_aabb.max[k]; }
     return 0;
 }
+// Testbed::set_crop_box / crop_box / crop_box_corners (S/ngp/testbed.cu:1421-1477), matrices row-major 3x4.  set: what the call leaves
+// in m_render_aabb_to_local (3x3 row-major) and m_render_aabb; get: the matrix and its eight corners
+REF_API int refgpu_set_crop_box(void* h, const float* m12, int nerf_space, float* r2l9, float* mn3, float* mx3) {
+    Testbed& t = *static_cast<RefCtx*>(h)->tb;
+    Eigen::Matrix<float, 3, 4> m;
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) m(r, c) = m12[r * 4 + c];
+    t.set_crop_box(m, nerf_space != 0);
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) r2l9[r * 3 + c] = t.m_render_aabb_to_local(r, c);
+    for (int k = 0; k < 3; ++k) { mn3[k] = t.m_render_aabb.min[k]; mx3[k] = t.m_render_aabb.max[k]; }
+    return 0;
+}
+REF_API int refgpu_crop_box(void* h, int nerf_space, float* out12, float* corners24) {
+    Testbed& t = *static_cast<RefCtx*>(h)->tb;
+    const Eigen::Matrix<float, 3, 4> m = t.crop_box(nerf_space != 0);
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) out12[r * 4 + c] = m(r, c);
+    const auto corners = t.crop_box_corners(nerf_space != 0);
+    for (int i = 0; i < 8; ++i) for (int k = 0; k < 3; ++k) corners24[i * 3 + k] = corners[i][k];
+    return 0;
+}
+// The camera helpers of Testbed (S/ngp/testbed.cu:1328-1349) applied to a given camera in this order: set_scale, set_look_at,
+// set_view_dir; -> the camera afterwards, look_at() and scale().  m_scale starts at the constructor's value.
+REF_API int refgpu_camera_ops(void* h, const float* cam12, float new_scale, const float* look_at3, const float* view_dir3, const float* up3,
+                              float* cam_out12, float* look_at_out3, float* scale_before) {
+    Testbed& t = *static_cast<RefCtx*>(h)->tb;
+    const auto saved = t.m_camera; const float saved_scale = t.scale(); const auto saved_up = t.m_up_dir;
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) t.m_camera(r, c) = cam12[r * 4 + c];
+    t.m_up_dir = Vector3f{up3[0], up3[1], up3[2]};
+    *scale_before = t.scale();
+    t.set_scale(new_scale);
+    t.set_look_at(Vector3f{look_at3[0], look_at3[1], look_at3[2]});
+    t.set_view_dir(Vector3f{view_dir3[0], view_dir3[1], view_dir3[2]});
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) cam_out12[r * 4 + c] = t.m_camera(r, c);
+    const Vector3f la = t.look_at();
+    for (int k = 0; k < 3; ++k) look_at_out3[k] = la[k];
+    t.m_camera = saved; t.set_scale(saved_scale); t.m_camera = saved; t.m_up_dir = saved_up;
+    return 0;
+}
 // Testbed.tonemap_curve (S/python_api.cu:448): ETonemapCurve 0 Identity, 1 ACES, 2 Hable, 3 Reinhard
 REF_API int refgpu_set_tonemap_curve(void* h, int curve) {
     static_cast<RefCtx*>(h)->tb->m_tonemap_curve = (ETonemapCurve)curve;

@@ -63,6 +63,10 @@ def lib():
         if hasattr(L, "refgpu_get_buffers"):
             L.refgpu_get_buffers.argtypes = [vp, C.c_int, C.c_int, vp, vp]
             L.refgpu_set_model_transform.argtypes = [vp, vp, vp]
+        if hasattr(L, "refgpu_set_crop_box"):
+            L.refgpu_set_crop_box.argtypes = [vp, vp, C.c_int, vp, vp, vp]
+            L.refgpu_crop_box.argtypes = [vp, C.c_int, vp, vp]
+            L.refgpu_camera_ops.argtypes = [vp, vp, C.c_float, vp, vp, vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -162,6 +166,28 @@ class ReferenceRenderer:
         """Testbed::m_model_translation / m_model_rotation (angles in units of pi about X, Y, Z)."""
         t = np.ascontiguousarray(translation, dtype=np.float32).reshape(3); r = np.ascontiguousarray(rotation_pi, dtype=np.float32).reshape(3)
         self._ck(self._L.refgpu_set_model_transform(self._h, _p(t), _p(r)))
+
+    def set_crop_box(self, matrix34, nerf_space=True):
+        """Testbed::set_crop_box -> (render_aabb_to_local 3x3, render_aabb min, max) as the reference leaves them."""
+        m = np.ascontiguousarray(matrix34, dtype=np.float32).reshape(3, 4)
+        r2l = np.zeros((3, 3), np.float32); mn = np.zeros(3, np.float32); mx = np.zeros(3, np.float32)
+        self._ck(self._L.refgpu_set_crop_box(self._h, _p(m), int(bool(nerf_space)), _p(r2l), _p(mn), _p(mx)))
+        return r2l, mn, mx
+
+    def crop_box(self, nerf_space=True):
+        """Testbed::crop_box and crop_box_corners -> (3x4 matrix, corners [8, 3])."""
+        m = np.zeros((3, 4), np.float32); c = np.zeros((8, 3), np.float32)
+        self._ck(self._L.refgpu_crop_box(self._h, int(bool(nerf_space)), _p(m), _p(c)))
+        return m, c
+
+    def camera_ops(self, cam34, new_scale, look_at, view_dir, up):
+        """set_scale, set_look_at, set_view_dir on the given camera -> (camera afterwards 3x4, look_at(), scale() before)."""
+        cam = np.ascontiguousarray(cam34, dtype=np.float32).reshape(3, 4)
+        la = np.ascontiguousarray(look_at, dtype=np.float32).reshape(3); vd = np.ascontiguousarray(view_dir, dtype=np.float32).reshape(3)
+        u = np.ascontiguousarray(up, dtype=np.float32).reshape(3)
+        out = np.zeros((3, 4), np.float32); lo = np.zeros(3, np.float32); sb = C.c_float(0)
+        self._ck(self._L.refgpu_camera_ops(self._h, _p(cam), float(new_scale), _p(la), _p(vd), _p(u), _p(out), _p(lo), C.byref(sb)))
+        return out, lo, float(sb.value)
 
     def buffers(self, W, H):
         """Linear frame buffer [H, W, 4] and depth buffer [H, W] of the render surface after the last render() - what

@@ -194,3 +194,50 @@ def test_tonemap_curves_vs_reference(pair, curve):
     finally:
         ref.set_tonemap_curve(0)
         nerf.tonemap_curve = 0
+
+
+def test_rotated_crop_box_and_camera_helpers_vs_reference_testbed(small_snapshot):
+    """Testbed::set_crop_box / crop_box / crop_box_corners (S/ngp/testbed.cu:1421-1477) and set_scale / set_look_at / set_view_dir
+    (:1328-1349) of the reference's OWN Testbed against the shim's host arithmetic, and a frame rendered through the rotated crop box
+    by the reference's own kernels against ours (same B200, same snapshot, same camera)."""
+    from oracle import refgpu
+    if not refgpu.available() or not hasattr(refgpu.lib(), "refgpu_set_crop_box"):
+        pytest.skip("oracle/_ref/libnmr_refgpu.so without the crop-box entry points")
+    import pynmr
+    path, snap = small_snapshot
+    ref = refgpu.ReferenceRenderer(path)
+    try:
+        r = pynmr.NerfMeshRenderer(W, HH)
+        nerf = r.load_nerf(path)
+        r.orbit(0.3, -0.15, 3.0)
+        cam12 = np.ascontiguousarray(r.view_projection_mat.T.reshape(-1))
+        a, b = np.deg2rad(30.0), np.deg2rad(20.0)
+        Ry = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]], np.float32)
+        Rx = np.array([[1, 0, 0], [0, np.cos(b), -np.sin(b)], [0, np.sin(b), np.cos(b)]], np.float32)
+        m = np.concatenate([(Ry @ Rx).astype(np.float32) * np.array([0.12, 0.2, 0.16], np.float32)[None, :], np.array([[0.5], [0.52], [0.5]], np.float32)], axis=1)
+        for nerf_space in (False, True):
+            want_r2l, want_mn, want_mx = ref.set_crop_box(m if not nerf_space else ref.crop_box(True)[0], nerf_space)
+            nerf.set_crop_box(m if not nerf_space else nerf.crop_box(True), nerf_space)
+            assert float(np.abs(nerf.render_aabb_to_local - want_r2l).max()) <= 2e-6
+            assert float(np.abs(np.asarray(nerf.render_aabb.min) - want_mn).max()) <= 2e-6 and float(np.abs(np.asarray(nerf.render_aabb.max) - want_mx).max()) <= 2e-6
+            for space in (False, True):
+                want_m, want_c = ref.crop_box(space)
+                assert float(np.abs(nerf.crop_box(space) - want_m).max()) <= 1e-5
+                assert float(np.abs(np.array(nerf.crop_box_corners(space)) - want_c).max()) <= 1e-5
+        want, _ = ref.render(cam12, W, HH, 1, False)
+        got = np.asarray(nerf.render(W, HH, 1, linear=False))
+        mx, ps, frac = _cmp(got, want)
+        assert ps >= 45.0 and frac <= 0.002, (mx, ps, frac)
+        nerf.set_crop_box(np.concatenate([np.eye(3, dtype=np.float32) * 0.5, np.full((3, 1), 0.5, np.float32)], axis=1), nerf_space=False)
+        assert float(np.abs(np.asarray(nerf.render(W, HH, 1, linear=False)) - got).max()) > 0.05        # the crop box mattered
+        # camera helpers
+        cam = r.view_projection_mat
+        want_cam, want_la, scale0 = ref.camera_ops(cam, 2.25, [0.1, 0.2, 0.3], [0.3, -0.2, 0.9], [0, 1, 0])
+        assert scale0 == nerf.scale
+        nerf.up_dir = [0, 1, 0]
+        nerf.scale = 2.25
+        nerf.look_at = [0.1, 0.2, 0.3]
+        nerf.view_dir = [0.3, -0.2, 0.9]
+        assert float(np.abs(nerf.camera_matrix - want_cam).max()) <= 1e-5 and float(np.abs(nerf.look_at - want_la).max()) <= 1e-5
+    finally:
+        ref.close()
